@@ -1,0 +1,15 @@
+// Library probe entry points of the C ABI.
+#include "internal.h"
+
+extern "C" int mpl_version(void) { return 1; }
+
+extern "C" int mpl_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return MPL_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return MPL_ERR_CUDA;
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return MPL_OK;
+}

@@ -1,0 +1,408 @@
+// K1 — bf16 GEMM on the 5th-gen tensor cores:  C[M,N] = epilogue(A[M,K] · W[N,K]^T)
+//
+// Replaces every nn.Linear on the dense path of the reference (SURVEY.md §8a rows a-1,a-2,a-3,a-7,a-9,a-10,a-11;
+// reference call sites e.g. model/medplib/model/multimodal_projector/builder.py:39-46 and the HF LlamaAttention /
+// LlamaMLP linears driven from model/medplib/model/language_model/medplib_moe_llama.py:123-147).
+//
+// Design (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes {64 x 128} of A and {64 x BN} of W, 128-B swizzle,
+//               into a STAGES-deep shared-memory ring guarded by full/empty mbarriers
+//   warp 1      allocates TMEM, then one lane issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 in TMEM) and
+//               tcgen05.commit's the ring slot back to the producer / the accumulator to the epilogue
+//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (each warp owns its 32-lane TMEM quadrant), apply
+//               bias / activation / SiLU(gate)*up / residual, round to bf16 at the same points the reference's
+//               eager bf16 path rounds, and store. Two accumulator stages let the epilogue of tile i overlap
+//               the main loop of tile i+1.
+// Tiles are ordered m-fastest so CTAs running concurrently share one W panel (W streams from HBM once, A from L2).
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace mpl {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmDevParams {
+  int M, N, K;
+  void* C;
+  long long ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  const float* row_scale;
+  const int* m_dev;
+  int act;
+  int out_f32;
+  int dual;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case MPL_ACT_GELU:
+      return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    case MPL_ACT_QUICK_GELU:
+      return v / (1.0f + __expf(-1.702f * v));
+    case MPL_ACT_RELU:
+      return fmaxf(v, 0.0f);
+    case MPL_ACT_SILU:
+      return v / (1.0f + __expf(-v));
+    default:
+      return v;
+  }
+}
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmB2, const GemmDevParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int M = p.M;
+  if (p.m_dev != nullptr) M = min(M, *p.m_dev);
+  const int out_bn = p.dual ? BN / 2 : BN;
+  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_n = (p.N + out_bn - 1) / out_bn;
+  const int num_tiles = tiles_m * tiles_n;
+  const int kblocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.dual) tma_prefetch_desc(&tmB2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM;
+        const int n0 = (tile / tiles_m) * out_bn;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
+          if (p.dual) {
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES + Cfg::B_BYTES / 2, &tmB2, &full_bar[stage], kb * BK, n0);
+          } else {
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(a_addr + k * 32);
+            const uint64_t db = umma_desc_k_sw128(b_addr + k * 32);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // slot reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
+    const bool res_vec_ok = (p.ldr & 7) == 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * BM;
+      const int n0 = (tile / tiles_m) * out_bn;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.0f;
+#pragma unroll 1
+      for (int c = 0; c < out_bn / 32; ++c) {
+        uint32_t r[32];
+        float v[32];
+        tmem_ld_32x32(t_row + c * 32, r);
+        if (p.dual) {
+          uint32_t r2[32];
+          tmem_ld_32x32(t_row + BN / 2 + c * 32, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            // reference: down(silu(gate(x)) * up(x)) with every intermediate rounded to bf16
+            const float g = bf16_round(__uint_as_float(r[j]));
+            const float u = bf16_round(__uint_as_float(r2[j]));
+            const float s = bf16_round(g / (1.0f + __expf(-g)));
+            v[j] = s * u;
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        const int nc = n0 + c * 32;
+        if (nc >= p.N) continue;  // warp-uniform
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nc + j < p.N) v[j] += __bfloat162float(p.bias[nc + j]);
+        }
+        if (p.act != MPL_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(p.out_f32 ? v[j] : bf16_round(v[j]), p.act);
+        }
+        if (p.row_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (p.out_f32 ? v[j] : bf16_round(v[j])) * rscale;
+        }
+        if (!row_ok) continue;
+        const bool full = (nc + 32 <= p.N);
+        if (p.residual != nullptr) {
+          const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + nc;
+          if (full && res_vec_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rp + q * 8);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                v[q * 8 + e * 2] = (p.out_f32 ? v[q * 8 + e * 2] : bf16_round(v[q * 8 + e * 2])) + f.x;
+                v[q * 8 + e * 2 + 1] = (p.out_f32 ? v[q * 8 + e * 2 + 1] : bf16_round(v[q * 8 + e * 2 + 1])) + f.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) v[j] = (p.out_f32 ? v[j] : bf16_round(v[j])) + __bfloat162float(rp[j]);
+          }
+        }
+        if (p.out_f32) {
+          float* cp = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + nc;
+          if (full && vec_ok) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(cp + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) cp[j] = v[j];
+          }
+        } else {
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + nc;
+          if (full && vec_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(cp + q * 8) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = {64 cols, box_rows}.
+static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return MPL_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || ((ld * 2) & 15) != 0) return MPL_ERR_ALIGN;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MPL_OK : MPL_ERR_DRIVER;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return MPL_ERR_CUDA;
+    attr_set = true;
+  }
+  const int dual = a.B2 != nullptr;
+  CUtensorMap tmA, tmB, tmB2;
+  int rc = make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tmB, a.B, a.N, a.K, a.ldb, dual ? BN / 2 : BN);
+  if (rc) return rc;
+  if (dual) {
+    rc = make_tmap(&tmB2, a.B2, a.N, a.K, a.ldb, BN / 2);
+    if (rc) return rc;
+  } else {
+    tmB2 = tmB;
+  }
+  GemmDevParams p;
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.C = a.C;
+  p.ldc = a.ldc;
+  p.bias = static_cast<const __nv_bfloat16*>(a.bias);
+  p.residual = static_cast<const __nv_bfloat16*>(a.residual);
+  p.ldr = a.ldr;
+  p.row_scale = a.row_scale;
+  p.m_dev = a.m_dev;
+  p.act = a.act;
+  p.out_f32 = a.out_dtype == MPL_DT_F32;
+  p.dual = dual;
+  const int out_bn = dual ? BN / 2 : BN;
+  const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn);
+  int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  if (grid < 1) grid = 1;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB2, p);
+  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+}
+
+int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0) return MPL_OK;
+  if (a.K <= 0 || a.A == nullptr || a.B == nullptr || a.C == nullptr) return MPL_ERR_ARG;
+  if (a.tile_n == 128) return launch_gemm<128>(a, stream);
+  if (a.tile_n == 256) return launch_gemm<256>(a, stream);
+  // heuristic: pick the tile width that leaves the fewest idle SM-slots in the last wave
+  const int sms = num_sms();
+  const int dual = a.B2 != nullptr;
+  auto waves_cost = [&](int bn) {
+    const int out_bn = dual ? bn / 2 : bn;
+    const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    return static_cast<double>(waves) * bn;  // time ~ waves * tile width
+  };
+  return waves_cost(128) < waves_cost(256) ? launch_gemm<128>(a, stream) : launch_gemm<256>(a, stream);
+}
+
+}  // namespace mpl
+
+extern "C" int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream) {
+  if (args == nullptr) return MPL_ERR_ARG;
+  return mpl::gemm_bf16(*args, static_cast<cudaStream_t>(stream));
+}
