@@ -31,7 +31,7 @@ enum {
   MPL_ERR_UNSUPPORTED = -5
 };
 
-enum { MPL_ACT_NONE = 0, MPL_ACT_GELU = 1, MPL_ACT_QUICK_GELU = 2, MPL_ACT_RELU = 3, MPL_ACT_SILU = 4 };
+enum { MPL_ACT_NONE = 0, MPL_ACT_GELU = 1, MPL_ACT_QUICK_GELU = 2, MPL_ACT_RELU = 3, MPL_ACT_SILU = 4, MPL_ACT_SIGMOID = 5 };
 enum { MPL_DT_BF16 = 0, MPL_DT_F32 = 1 };
 
 /* Library / device probe. Returns the ABI version; fills sm count and compute capability when non-null. */
@@ -48,28 +48,306 @@ int mpl_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * and im2col'ed convs (model/segment_anything_med2d/modeling/image_encoder.py).
  * Epilogue order (each step rounds to bf16 first when the output is bf16, like the reference's eager ops):
  *   acc (+ bias) -> act -> (* row_scale[m]) -> (+ residual[m,n]) -> store
- * B2 != NULL selects the fused LlamaMLP front half: out[m,n] = silu(A·B[n]^T) * (A·B2[n]^T).
+ * nb in 1..3 weight matrices of identical shape share A in ONE launch (q/k/v projections): output i goes to C[i]
+ *   with bias[i]; this fills the 148 SMs where a single N=4096 projection leaves 40% of them idle.
+ * B2 != NULL (nb == 1) selects the fused LlamaMLP front half: out[m,n] = silu(A·B[0][n]^T) * (A·B2[n]^T).
  * m_dev != NULL: the effective M is min(M, *m_dev) read on the device (MoE expert loads without a host sync).
  */
 typedef struct {
   const void* A;   /* bf16 [M,K] */
   long long lda;
-  const void* B;   /* bf16 [N,K]  (nn.Linear.weight layout) */
-  const void* B2;  /* bf16 [N,K] or NULL */
+  const void* B[3]; /* bf16 [N,K]  (nn.Linear.weight layout) */
+  const void* B2;   /* bf16 [N,K] or NULL */
   long long ldb;
-  void* C;         /* bf16 or f32 [M,N] */
+  void* C[3];       /* bf16 or f32 [M,N] */
   long long ldc;
-  const void* bias;     /* bf16 [N] or NULL */
+  const void* bias[3];  /* bf16 [N] or NULL */
   const void* residual; /* bf16 [M,N] or NULL */
   long long ldr;
   const float* row_scale; /* f32 [M] or NULL */
   const int* m_dev;       /* device int or NULL */
   int M, N, K;
+  int nb;        /* number of weight matrices, 1..3 */
   int act;       /* MPL_ACT_* */
   int out_dtype; /* MPL_DT_* */
-  int tile_n;    /* 0 = auto, else 128 or 256 */
+  int tile_n;    /* 0 = auto, else 128, 192 or 256 */
 } mpl_gemm_args;
 int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream);
+
+/* K3  same contract as mpl_gemm_bf16 for M <= 16 (decode batch, [SEG] rows, mask-decoder tokens): HBM-bound
+ * streaming kernel, weights read once with 16-byte loads into mma.sync fragments (nb <= 3 as grid.y).
+ * mpl_linear_bf16 dispatches on M (<= 16 -> skinny, else tcgen05). */
+int mpl_skinny_gemm_bf16(const mpl_gemm_args* args, void* stream);
+int mpl_linear_bf16(const mpl_gemm_args* args, void* stream);
+
+/* K5  LlamaRMSNorm (transformers 4.31 semantics; used at
+ * model/medplib/model/language_model/medplib_moe_llama.py:123,139,286): y = w * bf16(x * rsqrt(mean(x^2)+eps)). */
+int mpl_rmsnorm(const void* x, long long ldx, const void* weight, void* y, long long ldy, int rows, int D, float eps,
+                void* stream);
+/* K5  nn.LayerNorm over the last dim (CLIP, SAM blocks, mask decoder; LayerNorm2d of
+ * model/segment_anything_med2d/modeling/common.py:31-45 on NHWC rows). act = MPL_ACT_GELU fuses the GELU that
+ * follows LayerNorm2d in mask_decoder.py:53-59. D % 8 == 0, D <= 4096. */
+int mpl_layernorm(const void* x, long long ldx, const void* weight, const void* bias, void* y, long long ldy,
+                  int rows, int D, float eps, int act, void* stream);
+/* K6  TokenCompressor front half (model/medplib/model/medplib_arch.py:67-77): AdaptiveAvgPool1d(t_in -> t_out)
+ * over tokens fused with LayerNorm(D). x [n,t_in,D] -> y [n,t_out,D], contiguous bf16. */
+int mpl_pool_layernorm(const void* x, const void* weight, const void* bias, void* y, int n, int t_in, int t_out,
+                       int D, float eps, void* stream);
+
+/* K2 / K2b / K2c / K3  softmax(scale * q k^T + bias + masks) v, fp32 softmax, bf16 in/out.
+ * Replaces the eager matmul-softmax-matmul of HF LlamaAttention (causal + key padding),
+ * HF CLIPAttention (App. A.2), SAM-Med2D Attention with decomposed relative positions
+ * (model/segment_anything_med2d/modeling/image_encoder.py:280-296,381-421) and the mask decoder's Attention
+ * (model/segment_anything_med2d/modeling/transformer.py:185-244).
+ * Tensors are addressed base + b*stride[0] + t*stride[1] + h*stride[2] + d (elements; innermost contiguous).
+ * head_dim in {16,32,64,128}. Tq == 1 with head_dim 128 takes the HBM-bound KV-cache decode kernel, where
+ * tk_dev (device int) may override Tk so one CUDA graph serves every decode step. */
+typedef struct {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  long long q_stride[3], k_stride[3], v_stride[3], o_stride[3];
+  int B, H, Tq, Tk, head_dim;
+  float scale;
+  int causal;                   /* key j visible to query i iff j <= i + (Tk - Tq) */
+  const unsigned char* kv_mask; /* [B,Tk] 1 = attend, or NULL */
+  long long kv_mask_stride;     /* row stride of kv_mask in bytes; 0 = Tk */
+  const float* rel_h;           /* [B*H,Tq,rel_kh] f32 or NULL: bias = rel_h[q][k / rel_kw] + rel_w[q][k % rel_kw] */
+  const float* rel_w;           /* [B*H,Tq,rel_kw] */
+  int rel_kh, rel_kw;
+  const int* tk_dev;
+} mpl_attn_args;
+int mpl_attention(const mpl_attn_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K4  MoE router + top-k token scatter/gather. Replaces deepspeed.moe.layer.MoE (DeepSpeed 0.13.1 TopKGate /
+ * top1gating / top2gating / MOELayer einsum dispatch+combine) as the reference calls it at
+ * model/MedPLIB.py:253-263 and model/medplib/model/language_model/medplib_moe_llama.py:141-147,604-614.
+ * mpl_moe_route: logits = h.float() @ wg^T (fp32), gates = softmax, top-k selection (k = 1 or 2), slot of every
+ *   (token, route) in the [E*capacity, D] expert buffer in cumsum (position) order, -1 when dropped by capacity.
+ *   noise (f32 [S,E] or NULL): k = 1 -> the Random-Token-Selection uniforms used when an expert overflows;
+ *   k = 2 -> the Gumbel noise added to the logits for the second choice. gate[s,j] = combine weight (0 if dropped;
+ *   for k = 2 the two kept values renormalised by their sum). kept[e] = rows used in expert e's buffer (feeds
+ *   mpl_gemm_args.m_dev, no host sync); exp_counts[e] = first-choice tokens before dropping; l_aux as DeepSpeed.
+ * mpl_moe_dispatch: xperm[slot[s,j]] = h[s].   mpl_moe_combine: out[s] = residual[s] + bf16(sum_j bf16(gate[s,j]) *
+ *   y[slot[s,j]]) (residual may be NULL). */
+typedef struct {
+  const void* h; /* bf16 [S,D] */
+  long long ldh;
+  const float* wg;    /* f32 [E,D] */
+  const float* noise; /* f32 [S,E] or NULL */
+  int S, D, E, k, capacity;
+  float* logits;   /* [S,E] out */
+  float* gates;    /* [S,E] out */
+  int* expert;     /* [S,k] out */
+  float* gate;     /* [S,k] out */
+  int* slot;       /* [S,k] out */
+  int* kept;       /* [E] out */
+  int* exp_counts; /* [E] out */
+  float* l_aux;    /* [1] out */
+} mpl_moe_route_args;
+int mpl_moe_route(const mpl_moe_route_args* args, void* stream);
+int mpl_moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D, void* stream);
+int mpl_moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
+                    long long ldo, int S, int k, int D, void* stream);
+
+/* RoPE (HF 4.31 apply_rotary_pos_emb with rotate_half; bf16 cos/sin tables [max_pos, head_dim])
+ * applied in place to q and k rows ([B*T] rows of leading dimension ld, H heads of head_dim), position of row (b,t) =
+ * (pos_dev ? *pos_dev : pos0) + t, and append of the rotated k and of v to the KV cache [B,H,Tmax,head_dim]
+ * (k_cache/v_cache may be NULL). */
+int mpl_rope_kv(void* q, void* k, const void* v, long long ld, const void* cos_t, const void* sin_t, void* k_cache,
+                void* v_cache, int B, int T, int H, int head_dim, int Tmax, int pos0, const int* pos_dev, void* stream);
+
+/* K9  row gather: out[r] = idx[r] >= 0 ? table[idx[r]] : idx[r] == -1 ? 0 : feats[-idx[r]-2]. One kernel for the
+ * embedding lookup + multimodal splice (model/medplib/model/medplib_arch.py:296-527), SAM window (un)partition
+ * (image_encoder.py:299-345) and the pixel shuffle of the k2/s2 transposed convs (mask_decoder.py:53-59). */
+int mpl_gather_rows(const void* table, long long ld_table, const void* feats, long long ld_feats, const int* idx,
+                    void* out, long long ld_out, int rows, int D, void* stream);
+
+/* Greedy token selection (HF greedy_search argmax; lowest index wins ties): out[r] = argmax_v x[r, v]. */
+int mpl_argmax_f32(const float* x, long long ld, int rows, int V, long long* out, void* stream);
+
+/* Patch-embedding im2col for stride == kernel convs (CLIPVisionEmbeddings; SAM PatchEmbed image_encoder.py:424-455):
+ * img bf16 [B,C,H,W] -> out [B*(H/P)*(W/P), Kpad], column (c*P+ky)*P+kx, columns >= C*P*P zero. */
+int mpl_im2col_patch(const void* img, void* out, int B, int C, int H, int W, int P, int Kpad, void* stream);
+/* General im2col on token-major activations x bf16 [B,H,W,C] -> [B*Ho*Wo, kh*kw*C], column (ky*kw+kx)*C+c, zero
+ * padding; gate (bf16 [B,C] or NULL) multiplies x per channel first (Adapter_Layer channel gate, image_encoder.py:44-46). */
+int mpl_im2col_nhwc(const void* x, const void* gate, void* out, int B, int H, int W, int C, int kh, int kw, int stride,
+                    int pad, void* stream);
+/* CLIPVisionEmbeddings tail: out[b,0] = cls + pos[0]; out[b,1+i] = patch[b,i] + pos[1+i]. */
+int mpl_clip_embed(const void* patch, const void* cls, const void* pos, void* out, int B, int n_patches, int D,
+                   void* stream);
+/* add_decomposed_rel_pos terms (image_encoder.py:381-421): rel_h[bh,t,k] = bf16(q[b,t,h,:] . rel_pos_h[y-k+hh-1]),
+ * rel_w likewise with x; outputs f32 [B*H, hh*ww, hh] / [.., ww] for mpl_attention. */
+int mpl_sam_relpos(const void* q, long long q_sb, long long q_st, long long q_sh, const void* rel_pos_h,
+                   const void* rel_pos_w, float* rel_h, float* rel_w, int B, int H, int hh, int ww, int head_dim,
+                   void* stream);
+/* Mean over tokens: x bf16 [B,T,C] -> out bf16 [B,C] (Adapter_Layer avg_pool, image_encoder.py:43-45). */
+int mpl_col_mean(const void* x, void* out, int B, int T, int C, void* stream);
+/* col2im of ConvTranspose2d(k=4,s=2,p=1) computed as cols = x @ W' (f32 [B*Hi*Wi, 16*C], column (ky*4+kx)*C+co):
+ * out[b,oy,ox,:] = skip + relu(bf16(sum of taps)) (Adapter_Layer spatial branch + skip, image_encoder.py:33-36,48-51). */
+int mpl_convt4s2_col2im(const float* cols, const void* skip, void* out, int B, int Hi, int Wi, int C, void* stream);
+/* out = bf16(a + b); b is bf16 or f32 and repeats every b_period elements (positional-encoding adds,
+ * transformer.py:160-175 — the dense PE is fp32, App. B-8). */
+int mpl_add(const void* a, const void* b, int b_is_f32, void* out, long long n, long long b_period, void* stream);
+/* F.interpolate(bilinear, align_corners=False) of postprocess_masks (model/MedPLIB.py:682-701): in bf16
+ * [N, Hin, Win] with strides (elements) -> out [N,Hout,Wout] contiguous, out_dtype MPL_DT_*. */
+int mpl_bilinear_resize(const void* in, long long in_stride_n, long long in_stride_y, int Hin, int Win, void* out,
+                        int out_dtype, int Hout, int Wout, int N, void* stream);
+/* extract_region_feature (model/medplib/model/medplib_arch.py:580-614): mean over P points of the bilinear
+ * (align_corners=True, fp32) samples of fmap bf16 [h*w, C] at pts f32 [P,2] = (x,y) in [0,1]; out bf16 [C]. */
+int mpl_region_sample_mean(const void* fmap, const float* pts, int P, int h, int w, int C, void* out, void* stream);
+
+/* =========================================================================================================
+ * Native stack runners: ONE call enqueues every kernel of a sub-model forward (no Python between kernels).
+ * Weight structs hold device pointers into the caller's nn.Parameters (read in place; nothing is copied or
+ * retained); arrays of per-layer structs are HOST arrays. workspace is caller-owned device scratch of at least
+ * mpl_*_workspace_bytes(). All activations bf16 row-major (token-major).
+ * ========================================================================================================= */
+#define MPL_MAX_EXPERTS 8
+
+/* LLaMA decoder layer (HF 4.31 LlamaDecoderLayer as patched by MoELlamaDecoderLayer_forward,
+ * model/medplib/model/language_model/medplib_moe_llama.py:110-162). wg == NULL: dense LlamaMLP from expert slot 0. */
+typedef struct {
+  const void* input_ln; /* bf16 [D] */
+  const void* wq;       /* bf16 [D,D] */
+  const void* wk;
+  const void* wv;
+  const void* wo;
+  const void* post_ln;
+  const float* wg; /* f32 [E,D]: mlp.deepspeed_moe.gate.wg.weight */
+  int n_experts;
+  const void* w_gate[MPL_MAX_EXPERTS]; /* bf16 [F,D]: ...experts.deepspeed_experts.{e}.gate_proj.weight */
+  const void* w_up[MPL_MAX_EXPERTS];   /* bf16 [F,D] */
+  const void* w_down[MPL_MAX_EXPERTS]; /* bf16 [D,F] */
+} mpl_llama_layer;
+
+typedef struct {
+  int n_layers, hidden, n_heads, ffn;
+  float rms_eps;
+  int top_k;             /* 1 or 2 */
+  float capacity_factor; /* train: moe.capacity_factor, eval: moe.eval_capacity_factor (caller picks) */
+  int min_capacity;
+  const mpl_llama_layer* layers; /* host array [n_layers] */
+  const void* final_norm;        /* bf16 [D] */
+  const void* rope_cos;          /* bf16 [rope_len, head_dim] (HF 4.31 cached tables) */
+  const void* rope_sin;
+  int rope_len;
+} mpl_llama_model;
+
+/* MoELlamaModel_forward (medplib_moe_llama.py:165-305) on inputs_embeds. Rows are (b,t) with t fastest. */
+typedef struct {
+  void* x;                    /* bf16 [B*T, D] in: inputs_embeds; out: output of the last decoder layer */
+  void* out_norm;             /* bf16 [B*T, D] out: final RMSNorm (hidden_states[-1]); may be NULL */
+  void* const* hidden_states; /* NULL or host array [n_layers] of bf16 [B*T,D] buffers receiving each layer's INPUT */
+  int B, T, past_len;
+  void* k_cache; /* bf16 [n_layers, B, H, Tmax, head_dim]; rows [past_len, past_len+T) are written */
+  void* v_cache;
+  int Tmax;
+  const unsigned char* kv_mask; /* [B, >= past_len+T] 1 = attend (padding mask) or NULL */
+  long long kv_mask_stride;
+  const int* pos_dev; /* NULL, or device int overriding past_len (T == 1 decode under CUDA graphs) */
+  const int* tk_dev;  /* NULL, or device int = *pos_dev + 1 */
+  const float* const* moe_noise; /* NULL or host array [n_layers] of f32 [B*T,E] (see mpl_moe_route) */
+  float* gate_logits;            /* NULL or f32 [n_layers, B*T, E] out (what a forward hook on wg observes) */
+  float* l_aux;                  /* NULL or f32 [n_layers] out */
+  int* exp_counts;               /* NULL or int [n_layers, E] out */
+  void* workspace;
+  long long workspace_bytes;
+} mpl_llama_io;
+long long mpl_llama_workspace_bytes(const mpl_llama_model* model, int B, int T);
+int mpl_llama_forward(const mpl_llama_model* model, const mpl_llama_io* io, void* stream);
+
+/* CLIP ViT encoder layer / tower (HF 4.31 CLIPEncoderLayer, CLIPVisionTransformer) as used by
+ * CLIPVisionTower.forward (model/medplib/model/multimodal_encoder/clip_encoder.py:41-60). */
+typedef struct {
+  const void *ln1_w, *ln1_b;
+  const void *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo;
+  const void *ln2_w, *ln2_b;
+  const void *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} mpl_clip_layer;
+typedef struct {
+  int n_layers; /* layers to RUN = index of the selected hidden state (23 for select_layer=-2 of 24) */
+  int hidden, n_heads, mlp, image_size, patch;
+  int k_pad;    /* 3*patch*patch rounded up to a multiple of 8 */
+  float ln_eps;
+  const void* patch_w; /* bf16 [hidden, k_pad]: patch_embedding.weight.view(hidden,-1) zero-padded */
+  const void* cls;     /* bf16 [hidden] */
+  const void* pos;     /* bf16 [n_patches+1, hidden] */
+  const void *pre_ln_w, *pre_ln_b;
+  const mpl_clip_layer* layers; /* host array */
+} mpl_clip_model;
+long long mpl_clip_workspace_bytes(const mpl_clip_model* model, int B);
+/* images bf16 [B,3,S,S] -> feats bf16 [B, n_patches, hidden] = hidden_states[n_layers][:, 1:]. */
+int mpl_clip_forward(const mpl_clip_model* model, const void* images, int B, void* feats, void* workspace,
+                     long long workspace_bytes, void* stream);
+
+/* SAM-Med2D image encoder (model/segment_anything_med2d/modeling/image_encoder.py: ImageEncoderViT.forward :151-162,
+ * Block.forward :214-238, Attention :280-296, Adapter_Layer :18-56). Conv weights are passed repacked for the
+ * im2col GEMMs (done once by the host for these frozen weights):
+ *   ad_conv  [C, 9*C]   = spatial.0.weight.permute(0,2,3,1).reshape(C, 9*C)            (co | ky,kx,ci)
+ *   ad_convt [16*C, C]  = spatial.2.weight.permute(2,3,1,0).reshape(16*C, C)           (ky,kx,co | ci)
+ *   neck2_w  [O, 9*O]   = neck.2.weight.permute(0,2,3,1).reshape(O, 9*O) */
+typedef struct {
+  const void *ln1_w, *ln1_b;
+  const void *qkv_w, *qkv_b, *proj_w, *proj_b;
+  const void *rel_pos_h, *rel_pos_w; /* bf16 [2*s-1, head_dim], s = window or grid size */
+  int window;                        /* 0 = global attention */
+  const void *ln2_w, *ln2_b;
+  const void *lin1_w, *lin1_b, *lin2_w, *lin2_b;
+  const void *ad_ch0, *ad_ch2; /* [C/4, C], [C, C/4]; ad_ch0 == NULL: block has no adapter */
+  const void *ad_conv, *ad_convt;
+  const void *ad_norm_w, *ad_norm_b;
+} mpl_sam_block;
+typedef struct {
+  int depth, hidden, n_heads, mlp, image_size, patch, out_chans;
+  const void *patch_w, *patch_b; /* bf16 [hidden, 3*patch*patch], [hidden] */
+  const void* pos_embed;         /* bf16 [grid*grid, hidden] */
+  const mpl_sam_block* blocks;   /* host array */
+  const void *neck0_w, *neck1_w, *neck1_b, *neck2_w, *neck3_w, *neck3_b;
+} mpl_sam_encoder;
+long long mpl_sam_encoder_workspace_bytes(const mpl_sam_encoder* model, int B);
+/* images bf16 [B,3,S,S] -> out bf16 [B, grid*grid, out_chans] (token-major = NCHW output permuted (0,2,3,1)).
+ * win_part (device int [B*nw*ws*ws]) / win_unpart (device int [B*grid*grid]): mpl_gather_rows index maps of
+ * window_partition / window_unpartition (image_encoder.py:299-345) for windowed blocks (-1 = zero padding). */
+int mpl_sam_encoder_forward(const mpl_sam_encoder* model, const void* images, int B, const int* win_part,
+                            const int* win_unpart, int n_windows, void* out, void* workspace,
+                            long long workspace_bytes, void* stream);
+
+/* SAM-Med2D mask decoder (model/segment_anything_med2d/modeling/mask_decoder.py:113-153 over
+ * transformer.py:62-244) for ONE text prompt (batch 1, multimask_output=False), fed by PromptEncoder.forward
+ * (prompt_encoder.py:140-187): tokens = [iou_token; mask_tokens; text_embed], src = image_embedding + no_mask_embed. */
+typedef struct {
+  const void *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b;
+} mpl_sam_attn;
+typedef struct {
+  mpl_sam_attn self_attn, t2i, i2t;
+  const void *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b, *n4_w, *n4_b;
+  const void *lin1_w, *lin1_b, *lin2_w, *lin2_b;
+} mpl_sam_twoway_layer;
+typedef struct {
+  int dim, n_heads, mlp, depth, n_mask_tokens, grid;
+  const void* iou_token;   /* bf16 [dim] */
+  const void* mask_tokens; /* bf16 [n_mask_tokens, dim] */
+  const void* no_mask;     /* bf16 [dim]: prompt_encoder.no_mask_embed.weight */
+  const float* dense_pe;   /* f32 [grid*grid, dim]: get_dense_pe() token-major (input independent, cached by host) */
+  const mpl_sam_twoway_layer* layers; /* host array [depth] */
+  mpl_sam_attn final_attn;
+  const void *nf_w, *nf_b;
+  const void *up0_w, *up0_b; /* repacked convT k2s2: bf16 [4*dim/4, dim] rows (ky,kx,co), bias tiled [4*dim/4] */
+  const void *up_ln_w, *up_ln_b;
+  const void *up1_w, *up1_b; /* bf16 [4*dim/8, dim/4], bias tiled */
+  const int* shuffle_idx;    /* device int [16*grid*grid]: raster pixel -> row of the twice-upscaled buffer */
+  const void *hyper_w[3], *hyper_b[3]; /* output_hypernetworks_mlps[0] (mask 0 is the one returned) */
+  const void *iou_w[3], *iou_b[3];     /* iou_prediction_head */
+} mpl_sam_mask_decoder;
+long long mpl_sam_mask_decoder_workspace_bytes(const mpl_sam_mask_decoder* model);
+/* image_embedding bf16 [grid*grid, dim] (token-major), text_embed bf16 [dim] -> low_res_mask bf16 [4*grid, 4*grid],
+ * iou bf16 [n_mask_tokens] (caller takes [0]). */
+int mpl_sam_mask_decoder_forward(const mpl_sam_mask_decoder* model, const void* image_embedding,
+                                 const void* text_embed, void* low_res_mask, void* iou, void* workspace,
+                                 long long workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,416 @@
+// K2 / K2b / K2c / K3 — attention.
+//   flash_fwd   : tiled online-softmax attention (fp32 softmax, bf16 P·V) on mma.sync m16n8k16 fragments,
+//                 64 query rows x 64 keys per step, XOR-swizzled shared memory + ldmatrix. Used for
+//                   * LLaMA prefill: causal, head_dim 128, optional key-padding mask (HF-4.31 LlamaAttention,
+//                     SURVEY.md App. A.1; call site model/medplib/model/language_model/medplib_moe_llama.py:127-135)
+//                   * CLIP ViT-L: non-causal, 577 tokens, head_dim 64 (App. A.2; clip_encoder.py:53-57)
+//                   * SAM-Med2D: windows of 196 / global 256 tokens, head_dim 64, decomposed relative-position
+//                     bias rel_h[q, k/kw] + rel_w[q, k%kw] added in-kernel
+//                     (model/segment_anything_med2d/modeling/image_encoder.py:280-296,381-421)
+//                   * SAM mask decoder token<->image attention, head_dim 16/32
+//                     (model/segment_anything_med2d/modeling/transformer.py:185-244)
+//   decode      : one query token per sequence against the KV cache (HBM-bound): 8 lanes per key, 16-byte loads,
+//                 warp-shuffle reductions, 8 warps per (batch, head) combined through shared memory.
+// Layout: q/k/v/o are addressed as base + b*stride_b + t*stride_t + h*stride_h + d (elements), so fused-QKV
+// buffers, KV caches and per-head views need no copies.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace mpl {
+
+struct AttnParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  __nv_bfloat16* o;
+  long long q_sb, q_st, q_sh;
+  long long k_sb, k_st, k_sh;
+  long long v_sb, v_st, v_sh;
+  long long o_sb, o_st, o_sh;
+  int B, H, Tq, Tk;
+  float scale;
+  int causal;                    // key j visible to query i iff j <= i + (Tk - Tq)
+  const unsigned char* kv_mask;  // [B, Tk] 1 = attend, or NULL
+  long long kv_mask_stride;
+  const float* rel_h;            // [B*H, Tq, rel_kh] or NULL
+  const float* rel_w;            // [B*H, Tq, rel_kw]
+  int rel_kh, rel_kw;
+  const int* tk_dev;             // optional device-side Tk (decode under CUDA graphs)
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int FA_BM = 64, FA_BN = 64, FA_THREADS = 128;
+
+// Byte offset of 16-byte chunk `c` of row `r` inside a [rows][D] bf16 tile with XOR swizzle.
+template <int D>
+__device__ __forceinline__ uint32_t swz(int r, int c) {
+  constexpr int CPR = D / 8;
+  constexpr int MASK = CPR < 8 ? CPR - 1 : 7;
+  return static_cast<uint32_t>(r * (D * 2) + ((c ^ (r & MASK)) << 4));
+}
+
+template <int D>
+__device__ __forceinline__ void load_tile(uint32_t smem_base, const __nv_bfloat16* g, long long stride_t, int t0,
+                                          int t_end, int rows) {
+  constexpr int CPR = D / 8;  // 16-byte chunks per row
+  for (int idx = threadIdx.x; idx < rows * CPR; idx += FA_THREADS) {
+    const int r = idx / CPR, c = idx % CPR;
+    const int t = t0 + r;
+    const bool ok = t < t_end;
+    const __nv_bfloat16* src = g + static_cast<long long>(ok ? t : t0) * stride_t + c * 8;
+    cp_async16(smem_base + swz<D>(r, c), src, ok);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(FA_THREADS) flash_fwd_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t fa_smem[];
+  const uint32_t sQ = smem_u32(fa_smem);
+  const uint32_t sK = sQ + FA_BM * D * 2;
+  const uint32_t sV = sK + FA_BN * D * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int q0 = blockIdx.x * FA_BM;
+  const int Tk = p.tk_dev ? *p.tk_dev : p.Tk;
+  const int off = Tk - p.Tq;
+  const __nv_bfloat16* qg = p.q + b * p.q_sb + h * p.q_sh;
+  const __nv_bfloat16* kg = p.k + b * p.k_sb + h * p.k_sh;
+  const __nv_bfloat16* vg = p.v + b * p.v_sb + h * p.v_sh;
+
+  load_tile<D>(sQ, qg, p.q_st, q0, p.Tq, FA_BM);
+  cp_async_wait_all();
+  __syncthreads();
+  // Q fragments for this warp's 16 rows, all of D
+  uint32_t qf[D / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+    const int r = warp * 16 + (lane & 15);
+    const int c = kk * 2 + (lane >> 4);
+    ldmatrix_x4(qf[kk], sQ + swz<D>(r, c));
+  }
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.0f;
+  float row_max[2] = {-INFINITY, -INFINITY};
+  float row_sum[2] = {0.0f, 0.0f};
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const int qrow[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
+
+  int k_end = Tk;
+  if (p.causal) k_end = min(Tk, q0 + FA_BM + off);
+  const unsigned char* mrow = p.kv_mask ? p.kv_mask + static_cast<long long>(b) * p.kv_mask_stride : nullptr;
+  const float* relh[2] = {nullptr, nullptr};
+  const float* relw[2] = {nullptr, nullptr};
+  if (p.rel_h) {
+    const long long bh = static_cast<long long>(b) * p.H + h;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int qr = min(qrow[rr], p.Tq - 1);
+      relh[rr] = p.rel_h + (bh * p.Tq + qr) * p.rel_kh;
+      relw[rr] = p.rel_w + (bh * p.Tq + qr) * p.rel_kw;
+    }
+  }
+
+  for (int k0 = 0; k0 < k_end; k0 += FA_BN) {
+    __syncthreads();  // previous iteration's reads of sK/sV done
+    load_tile<D>(sK, kg, p.k_st, k0, Tk, FA_BN);
+    load_tile<D>(sV, vg, p.v_st, k0, Tk, FA_BN);
+    cp_async_wait_all();
+    __syncthreads();
+
+    float s[FA_BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < FA_BN / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+      for (int np = 0; np < FA_BN / 16; ++np) {
+        uint32_t kf[4];
+        const int r = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int c = kk * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4(kf, sK + swz<D>(r, c));
+        mma_16816(s[np * 2], qf[kk], kf[0], kf[1]);
+        mma_16816(s[np * 2 + 1], qf[kk], kf[2], kf[3]);
+      }
+    }
+    // scale (log2 domain), bias, masks
+    float tile_max[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < FA_BN / 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = j >> 1;
+        const int key = k0 + nt * 8 + t4 * 2 + (j & 1);
+        float val = s[nt][j] * sl2;
+        bool ok = key < Tk;
+        if (p.causal) ok = ok && (key <= qrow[rr] + off);
+        if (mrow != nullptr && ok) ok = mrow[key] != 0;
+        if (relh[0] != nullptr && ok)
+          val += (relh[rr][key / p.rel_kw] + relw[rr][key % p.rel_kw]) * 1.4426950408889634f;
+        val = ok ? val : -INFINITY;
+        s[nt][j] = val;
+        tile_max[rr] = fmaxf(tile_max[rr], val);
+      }
+    }
+    float corr[2], mnew[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float m = tile_max[rr];
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      mnew[rr] = fmaxf(row_max[rr], m);
+      const float msafe = (mnew[rr] == -INFINITY) ? 0.0f : mnew[rr];
+      corr[rr] = exp2f(row_max[rr] - msafe);  // row_max = -inf -> 0
+      row_max[rr] = mnew[rr];
+      mnew[rr] = msafe;
+      row_sum[rr] *= corr[rr];
+    }
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+      o[i][0] *= corr[0];
+      o[i][1] *= corr[0];
+      o[i][2] *= corr[1];
+      o[i][3] *= corr[1];
+    }
+    uint32_t pf[FA_BN / 16][4];
+#pragma unroll
+    for (int nt = 0; nt < FA_BN / 8; ++nt) {
+      const float p0 = exp2f(s[nt][0] - mnew[0]);
+      const float p1 = exp2f(s[nt][1] - mnew[0]);
+      const float p2 = exp2f(s[nt][2] - mnew[1]);
+      const float p3 = exp2f(s[nt][3] - mnew[1]);
+      row_sum[0] += p0 + p1;
+      row_sum[1] += p2 + p3;
+      pf[nt >> 1][(nt & 1) * 2] = pack_bf16(p0, p1);
+      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+#pragma unroll
+    for (int kk = 0; kk < FA_BN / 16; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < D / 16; ++dp) {
+        uint32_t vf[4];
+        const int r = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        const int c = dp * 2 + (lane >> 4);
+        ldmatrix_x4_trans(vf, sV + swz<D>(r, c));
+        mma_16816(o[dp * 2], pf[kk], vf[0], vf[1]);
+        mma_16816(o[dp * 2 + 1], pf[kk], vf[2], vf[3]);
+      }
+    }
+  }
+  // finalize
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    float sres = row_sum[rr];
+    sres += __shfl_xor_sync(0xffffffffu, sres, 1);
+    sres += __shfl_xor_sync(0xffffffffu, sres, 2);
+    row_sum[rr] = sres > 0.0f ? 1.0f / sres : 0.0f;
+  }
+  __nv_bfloat16* og = p.o + b * p.o_sb + h * p.o_sh;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    if (qrow[rr] < p.Tq) {
+      __nv_bfloat16* orow = og + static_cast<long long>(qrow[rr]) * p.o_st;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        const uint32_t packed = pack_bf16(o[i][rr * 2] * row_sum[rr], o[i][rr * 2 + 1] * row_sum[rr]);
+        *reinterpret_cast<uint32_t*>(orow + i * 8 + t4 * 2) = packed;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ decode (Tq == 1)
+constexpr int DEC_WARPS = 8;
+template <int D>
+__global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(const AttnParams p) {
+  static_assert(D == 128, "decode kernel is written for head_dim 128");
+  __shared__ float s_o[DEC_WARPS][D];
+  __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, gl = lane & 7;  // 4 keys per warp step, 8 lanes x 16 dims per key
+  const int Tk = p.tk_dev ? *p.tk_dev : p.Tk;
+  const __nv_bfloat16* qg = p.q + b * p.q_sb + h * p.q_sh + gl * 16;
+  const __nv_bfloat16* kg = p.k + b * p.k_sb + h * p.k_sh + gl * 16;
+  const __nv_bfloat16* vg = p.v + b * p.v_sb + h * p.v_sh + gl * 16;
+  const unsigned char* mrow = p.kv_mask ? p.kv_mask + static_cast<long long>(b) * p.kv_mask_stride : nullptr;
+  float qf[16];
+  {
+    const uint4 a = *reinterpret_cast<const uint4*>(qg);
+    const uint4 c = *reinterpret_cast<const uint4*>(qg + 8);
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(ha[e]), fc = __bfloat1622float2(hc[e]);
+      qf[2 * e] = fa.x;
+      qf[2 * e + 1] = fa.y;
+      qf[8 + 2 * e] = fc.x;
+      qf[8 + 2 * e + 1] = fc.y;
+    }
+  }
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float m = -INFINITY, l = 0.0f;
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+  for (int key = warp * 4 + grp; key < Tk; key += DEC_WARPS * 4) {
+    const __nv_bfloat16* kr = kg + static_cast<long long>(key) * p.k_st;
+    const __nv_bfloat16* vr = vg + static_cast<long long>(key) * p.v_st;
+    const uint4 ka = *reinterpret_cast<const uint4*>(kr), kc = *reinterpret_cast<const uint4*>(kr + 8);
+    const uint4 va = *reinterpret_cast<const uint4*>(vr), vc = *reinterpret_cast<const uint4*>(vr + 8);
+    const __nv_bfloat162* hka = reinterpret_cast<const __nv_bfloat162*>(&ka);
+    const __nv_bfloat162* hkc = reinterpret_cast<const __nv_bfloat162*>(&kc);
+    float dot = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(hka[e]), fc = __bfloat1622float2(hkc[e]);
+      dot += qf[2 * e] * fa.x + qf[2 * e + 1] * fa.y + qf[8 + 2 * e] * fc.x + qf[8 + 2 * e + 1] * fc.y;
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    float sc = dot * sl2;
+    if (mrow != nullptr && mrow[key] == 0) sc = -INFINITY;
+    const float mn = fmaxf(m, sc);
+    const float msafe = (mn == -INFINITY) ? 0.0f : mn;
+    const float corr = exp2f(m - msafe);
+    // P is rounded to bf16 before multiplying V, as the reference's softmax(...).to(bf16) @ v does
+    const float pexp = exp2f(sc - msafe);
+    const float pv = bf16_round(pexp);
+    l = l * corr + pexp;
+    m = mn;
+    const __nv_bfloat162* hva = reinterpret_cast<const __nv_bfloat162*>(&va);
+    const __nv_bfloat162* hvc = reinterpret_cast<const __nv_bfloat162*>(&vc);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(hva[e]), fc = __bfloat1622float2(hvc[e]);
+      acc[2 * e] = acc[2 * e] * corr + pv * fa.x;
+      acc[2 * e + 1] = acc[2 * e + 1] * corr + pv * fa.y;
+      acc[8 + 2 * e] = acc[8 + 2 * e] * corr + pv * fc.x;
+      acc[8 + 2 * e + 1] = acc[8 + 2 * e + 1] * corr + pv * fc.y;
+    }
+  }
+  // merge the 4 key groups of the warp (lanes differing in bits 3,4)
+#pragma unroll
+  for (int sh = 8; sh <= 16; sh <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, sh);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, sh);
+    const float mn = fmaxf(m, m2);
+    const float msafe = (mn == -INFINITY) ? 0.0f : mn;
+    const float c1 = exp2f(m - msafe), c2 = exp2f(m2 - msafe);
+    l = l * c1 + l2 * c2;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float a2 = __shfl_xor_sync(0xffffffffu, acc[e], sh);
+      acc[e] = acc[e] * c1 + a2 * c2;
+    }
+    m = mn;
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s_o[warp][gl * 16 + e] = acc[e];
+    if (gl == 0) {
+      s_m[warp] = m;
+      s_l[warp] = l;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) mm = fmaxf(mm, s_m[w]);
+    const float msafe = (mm == -INFINITY) ? 0.0f : mm;
+    float lt = 0.0f, ot = 0.0f;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) {
+      const float c = exp2f(s_m[w] - msafe);
+      lt += s_l[w] * c;
+      ot += s_o[w][threadIdx.x] * c;
+    }
+    p.o[b * p.o_sb + h * p.o_sh + threadIdx.x] = __float2bfloat16_rn(lt > 0.0f ? ot / lt : 0.0f);
+  }
+}
+
+template <int D>
+static int launch_flash(const AttnParams& p, cudaStream_t stream) {
+  constexpr int smem = (FA_BM + 2 * FA_BN) * D * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(flash_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return MPL_ERR_CUDA;
+    attr_set = true;
+  }
+  dim3 grid((p.Tq + FA_BM - 1) / FA_BM, p.H, p.B);
+  flash_fwd_kernel<D><<<grid, FA_THREADS, smem, stream>>>(p);
+  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+}
+
+}  // namespace mpl
+
+extern "C" int mpl_attention(const mpl_attn_args* a, void* stream_) {
+  using namespace mpl;
+  if (a == nullptr || a->q == nullptr || a->k == nullptr || a->v == nullptr || a->o == nullptr) return MPL_ERR_ARG;
+  if (a->B <= 0 || a->H <= 0 || a->Tq <= 0) return MPL_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  AttnParams p;
+  p.q = static_cast<const __nv_bfloat16*>(a->q);
+  p.k = static_cast<const __nv_bfloat16*>(a->k);
+  p.v = static_cast<const __nv_bfloat16*>(a->v);
+  p.o = static_cast<__nv_bfloat16*>(a->o);
+  p.q_sb = a->q_stride[0]; p.q_st = a->q_stride[1]; p.q_sh = a->q_stride[2];
+  p.k_sb = a->k_stride[0]; p.k_st = a->k_stride[1]; p.k_sh = a->k_stride[2];
+  p.v_sb = a->v_stride[0]; p.v_st = a->v_stride[1]; p.v_sh = a->v_stride[2];
+  p.o_sb = a->o_stride[0]; p.o_st = a->o_stride[1]; p.o_sh = a->o_stride[2];
+  p.B = a->B; p.H = a->H; p.Tq = a->Tq; p.Tk = a->Tk;
+  p.scale = a->scale;
+  p.causal = a->causal;
+  p.kv_mask = a->kv_mask;
+  p.kv_mask_stride = a->kv_mask_stride > 0 ? a->kv_mask_stride : a->Tk;
+  p.rel_h = a->rel_h; p.rel_w = a->rel_w; p.rel_kh = a->rel_kh; p.rel_kw = a->rel_kw;
+  p.tk_dev = a->tk_dev;
+  // 16-byte vector access on every row
+  const long long strides[] = {p.q_sb, p.q_st, p.q_sh, p.k_sb, p.k_st, p.k_sh, p.v_sb, p.v_st, p.v_sh};
+  for (long long s : strides)
+    if (s % 8 != 0) return MPL_ERR_ALIGN;
+  if (a->Tq == 1 && a->head_dim == 128 && a->rel_h == nullptr) {
+    dim3 grid(p.H, p.B);
+    decode_attn_kernel<128><<<grid, DEC_WARPS * 32, 0, stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  }
+  if (p.tk_dev != nullptr) return MPL_ERR_UNSUPPORTED;  // device-side Tk only on the decode path
+  if (p.o_st % 2 != 0 || p.o_sh % 2 != 0 || p.o_sb % 2 != 0) return MPL_ERR_ALIGN;
+  switch (a->head_dim) {
+    case 16: return launch_flash<16>(p, stream);
+    case 32: return launch_flash<32>(p, stream);
+    case 64: return launch_flash<64>(p, stream);
+    case 128: return launch_flash<128>(p, stream);
+    default: return MPL_ERR_UNSUPPORTED;
+  }
+}

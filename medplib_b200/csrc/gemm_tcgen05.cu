@@ -32,9 +32,10 @@ constexpr int GEMM_THREADS = 192;
 
 struct GemmDevParams {
   int M, N, K;
-  void* C;
+  int nb;
+  void* C[3];
   long long ldc;
-  const __nv_bfloat16* bias;
+  const __nv_bfloat16* bias[3];
   const __nv_bfloat16* residual;
   long long ldr;
   const float* row_scale;
@@ -54,6 +55,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
       return fmaxf(v, 0.0f);
     case MPL_ACT_SILU:
       return v / (1.0f + __expf(-v));
+    case MPL_ACT_SIGMOID:
+      return 1.0f / (1.0f + __expf(-v));
     default:
       return v;
   }
@@ -61,17 +64,19 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
+  static constexpr int ACC_STRIDE = (BN == 192) ? 256 : BN;  // column offset between the two accumulator stages
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;           // power of two >= 32
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmB2, const GemmDevParams p) {
+                         const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
+                         const GemmDevParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -91,14 +96,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (p.m_dev != nullptr) M = min(M, *p.m_dev);
   const int out_bn = p.dual ? BN / 2 : BN;
   const int tiles_m = (M + BM - 1) / BM;
-  const int tiles_n = (p.N + out_bn - 1) / out_bn;
+  const int tiles_n1 = (p.N + out_bn - 1) / out_bn;  // per weight matrix
+  const int tiles_n = tiles_n1 * p.nb;
   const int num_tiles = tiles_m * tiles_n;
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.dual) tma_prefetch_desc(&tmB2);
+    if (p.dual || p.nb > 2) tma_prefetch_desc(&tmB2);
+    if (p.nb > 1) tma_prefetch_desc(&tmB1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -122,7 +129,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile % tiles_m) * BM;
-        const int n0 = (tile / tiles_m) * out_bn;
+        const int nt = tile / tiles_m;
+        const int which = nt / tiles_n1;
+        const int n0 = (nt % tiles_n1) * out_bn;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
@@ -131,7 +140,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
             tma_load_2d(sB + stage * Cfg::B_BYTES + Cfg::B_BYTES / 2, &tmB2, &full_bar[stage], kb * BK, n0);
           } else {
-            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+            // explicit branches: the tensor maps must be addressed in param space (no local copies)
+            if (which == 0)
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
+            else if (which == 1)
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB1, &full_bar[stage], kb * BK, n0);
+            else
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB2, &full_bar[stage], kb * BK, n0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -151,7 +166,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -185,13 +200,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const bool res_vec_ok = (p.ldr & 7) == 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % tiles_m) * BM;
-      const int n0 = (tile / tiles_m) * out_bn;
+      const int nt = tile / tiles_m;
+      const int which = nt / tiles_n1;
+      const int n0 = (nt % tiles_n1) * out_bn;
+      const __nv_bfloat16* bias = which == 0 ? p.bias[0] : (which == 1 ? p.bias[1] : p.bias[2]);
+      void* Cout = which == 0 ? p.C[0] : (which == 1 ? p.C[1] : p.C[2]);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < M;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
       const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.0f;
+      const bool f32 = p.out_f32 != 0;
 #pragma unroll 1
       for (int c = 0; c < out_bn / 32; ++c) {
         uint32_t r[32];
@@ -215,23 +235,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int nc = n0 + c * 32;
-        if (nc >= p.N) continue;  // warp-uniform
-        if (p.bias != nullptr) {
+        if (nc >= p.N || !row_ok) continue;
+        const bool full = (nc + 32 <= p.N);
+        if (bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (nc + j < p.N) v[j] += __bfloat162float(p.bias[nc + j]);
+            if (full || nc + j < p.N) v[j] += __bfloat162float(bias[nc + j]);
         }
         if (p.act != MPL_ACT_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(p.out_f32 ? v[j] : bf16_round(v[j]), p.act);
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(f32 ? v[j] : bf16_round(v[j]), p.act);
         }
         if (p.row_scale != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (p.out_f32 ? v[j] : bf16_round(v[j])) * rscale;
+          for (int j = 0; j < 32; ++j) v[j] = (f32 ? v[j] : bf16_round(v[j])) * rscale;
         }
-        if (!row_ok) continue;
-        const bool full = (nc + 32 <= p.N);
         if (p.residual != nullptr) {
+          if (!f32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+          }
           const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + nc;
           if (full && res_vec_ok) {
 #pragma unroll
@@ -241,18 +264,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = __bfloat1622float2(h[e]);
-                v[q * 8 + e * 2] = (p.out_f32 ? v[q * 8 + e * 2] : bf16_round(v[q * 8 + e * 2])) + f.x;
-                v[q * 8 + e * 2 + 1] = (p.out_f32 ? v[q * 8 + e * 2 + 1] : bf16_round(v[q * 8 + e * 2 + 1])) + f.y;
+                v[q * 8 + e * 2] += f.x;
+                v[q * 8 + e * 2 + 1] += f.y;
               }
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) v[j] = (p.out_f32 ? v[j] : bf16_round(v[j])) + __bfloat162float(rp[j]);
+              if (nc + j < p.N) v[j] += __bfloat162float(rp[j]);
           }
         }
-        if (p.out_f32) {
-          float* cp = reinterpret_cast<float*>(p.C) + static_cast<long long>(row) * p.ldc + nc;
+        if (f32) {
+          float* cp = reinterpret_cast<float*>(Cout) + static_cast<long long>(row) * p.ldc + nc;
           if (full && vec_ok) {
 #pragma unroll
             for (int q = 0; q < 8; ++q)
@@ -263,7 +286,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               if (nc + j < p.N) cp[j] = v[j];
           }
         } else {
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<long long>(row) * p.ldc + nc;
+          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<long long>(row) * p.ldc + nc;
           if (full && vec_ok) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -350,24 +373,37 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
     attr_set = true;
   }
   const int dual = a.B2 != nullptr;
-  CUtensorMap tmA, tmB, tmB2;
+  const int nb = a.nb < 1 ? 1 : a.nb;
+  if (nb > 3 || (dual && nb != 1)) return MPL_ERR_ARG;
+  CUtensorMap tmA, tmB, tmB1, tmB2;
   int rc = make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM);
   if (rc) return rc;
-  rc = make_tmap(&tmB, a.B, a.N, a.K, a.ldb, dual ? BN / 2 : BN);
+  rc = make_tmap(&tmB, a.B[0], a.N, a.K, a.ldb, dual ? BN / 2 : BN);
   if (rc) return rc;
+  tmB1 = tmB;
+  tmB2 = tmB;
   if (dual) {
     rc = make_tmap(&tmB2, a.B2, a.N, a.K, a.ldb, BN / 2);
     if (rc) return rc;
-  } else {
-    tmB2 = tmB;
+  }
+  if (nb > 1) {
+    rc = make_tmap(&tmB1, a.B[1], a.N, a.K, a.ldb, BN);
+    if (rc) return rc;
+  }
+  if (nb > 2) {
+    rc = make_tmap(&tmB2, a.B[2], a.N, a.K, a.ldb, BN);
+    if (rc) return rc;
   }
   GemmDevParams p;
   p.M = a.M;
   p.N = a.N;
   p.K = a.K;
-  p.C = a.C;
+  p.nb = nb;
+  for (int i = 0; i < 3; ++i) {
+    p.C[i] = a.C[i];
+    p.bias[i] = static_cast<const __nv_bfloat16*>(a.bias[i]);
+  }
   p.ldc = a.ldc;
-  p.bias = static_cast<const __nv_bfloat16*>(a.bias);
   p.residual = static_cast<const __nv_bfloat16*>(a.residual);
   p.ldr = a.ldr;
   p.row_scale = a.row_scale;
@@ -376,28 +412,35 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   p.out_f32 = a.out_dtype == MPL_DT_F32;
   p.dual = dual;
   const int out_bn = dual ? BN / 2 : BN;
-  const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn);
+  const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn) * nb;
   int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   if (grid < 1) grid = 1;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB2, p);
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB1, tmB2, p);
   return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
 }
 
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return MPL_OK;
-  if (a.K <= 0 || a.A == nullptr || a.B == nullptr || a.C == nullptr) return MPL_ERR_ARG;
+  if (a.K <= 0 || a.A == nullptr || a.B[0] == nullptr || a.C[0] == nullptr) return MPL_ERR_ARG;
   if (a.tile_n == 128) return launch_gemm<128>(a, stream);
+  if (a.tile_n == 192) return launch_gemm<192>(a, stream);
   if (a.tile_n == 256) return launch_gemm<256>(a, stream);
-  // heuristic: pick the tile width that leaves the fewest idle SM-slots in the last wave
+  if (a.tile_n != 0) return MPL_ERR_ARG;
+  // Pick the tile width with the lowest (waves x per-tile time) estimate. Per-tile time is ~ proportional to the
+  // tile width; the narrower tiles carry a measured efficiency penalty (A traffic per flop, fewer MMAs in flight).
   const int sms = num_sms();
   const int dual = a.B2 != nullptr;
-  auto waves_cost = [&](int bn) {
+  const int nb = a.nb < 1 ? 1 : a.nb;
+  auto cost = [&](int bn, double penalty) {
     const int out_bn = dual ? bn / 2 : bn;
-    const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn);
+    const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn) * nb;
     const long long waves = (tiles + sms - 1) / sms;
-    return static_cast<double>(waves) * bn;  // time ~ waves * tile width
+    return static_cast<double>(waves) * bn * penalty;
   };
-  return waves_cost(128) < waves_cost(256) ? launch_gemm<128>(a, stream) : launch_gemm<256>(a, stream);
+  const double c256 = cost(256, 1.0), c192 = cost(192, 1.08), c128 = cost(128, 1.25);
+  if (c256 <= c192 && c256 <= c128) return launch_gemm<256>(a, stream);
+  if (c192 <= c128) return launch_gemm<192>(a, stream);
+  return launch_gemm<128>(a, stream);
 }
 
 }  // namespace mpl

@@ -7,4 +7,10 @@
 namespace mpl {
 int num_sms();
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream);
+int skinny_gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream);
+int linear_bf16(const mpl_gemm_args& a, cudaStream_t stream);
+int moe_route(const mpl_moe_route_args& a, cudaStream_t stream);
+int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D, cudaStream_t stream);
+int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
+                long long ldo, int S, int k, int D, cudaStream_t stream);
 }  // namespace mpl

@@ -1,0 +1,340 @@
+// K4 — MoE router + top-k token scatter / gather (HBM-bound, warp-shuffle reductions, 16-byte row copies).
+//
+// Replaces deepspeed.moe.layer.MoE as the reference calls it (model/MedPLIB.py:253-263,
+// model/medplib/model/language_model/medplib_moe_llama.py:141-147,604-614; DeepSpeed 0.13.1 semantics restated in
+// SURVEY.md App. A.3 / oracle/moe.py): fp32 gate GEMV -> softmax -> top-1 (or top-2) -> capacity -> slot per token.
+// DeepSpeed materialises dispatch/combine as dense one-hot einsums over [S,E,C]; here a token's row is copied
+// straight to row e*C+slot of the expert buffer and gathered back scaled by its gate value. Expert loads stay on the
+// device (kept[e] feeds the expert GEMMs' m_dev), so there is no exp_counts.to('cpu') sync per layer.
+//   router  : one warp per token, E dot products of length D against the fp32 gate, shuffle-reduced
+//   scan    : one CTA; per-thread token segments -> per-expert counts -> exclusive scan -> slots (deterministic,
+//             position order = torch.cumsum order)
+//   dispatch: one CTA per (token, route): 16-byte vector copy of the row into its slot
+//   combine : one CTA per token: out = residual + bf16(sum_j bf16(gate_j) * y[slot_j])
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace mpl {
+
+constexpr int MOE_MAX_E = 8;
+
+__global__ void __launch_bounds__(128) moe_router_kernel(const __nv_bfloat16* __restrict__ h, long long ldh,
+                                                         const float* __restrict__ wg, int S, int D, int E,
+                                                         float* __restrict__ logits, float* __restrict__ gates) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 4 + warp;
+  if (s >= S) return;
+  const __nv_bfloat16* hr = h + static_cast<long long>(s) * ldh;
+  float acc[MOE_MAX_E];
+#pragma unroll
+  for (int e = 0; e < MOE_MAX_E; ++e) acc[e] = 0.0f;
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(hr + c);
+    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(hp[i]);
+      x[2 * i] = f.x;
+      x[2 * i + 1] = f.y;
+    }
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e) {
+      if (e < E) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wg + static_cast<long long>(e) * D + c);
+        const float4 w1 = *reinterpret_cast<const float4*>(wg + static_cast<long long>(e) * D + c + 4);
+        acc[e] += x[0] * w0.x + x[1] * w0.y + x[2] * w0.z + x[3] * w0.w + x[4] * w1.x + x[5] * w1.y + x[6] * w1.z +
+                  x[7] * w1.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < MOE_MAX_E; ++e) acc[e] = warp_sum(acc[e]);
+  if (lane == 0) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e)
+      if (e < E) m = fmaxf(m, acc[e]);
+    float ex[MOE_MAX_E];
+    float sum = 0.0f;
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e)
+      if (e < E) {
+        ex[e] = expf(acc[e] - m);
+        sum += ex[e];
+      }
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e)
+      if (e < E) {
+        logits[static_cast<long long>(s) * E + e] = acc[e];
+        gates[static_cast<long long>(s) * E + e] = ex[e] / sum;
+      }
+  }
+}
+
+constexpr int SCAN_THREADS = 1024;
+
+// One CTA. Selection (top-1 / top-2), capacity, slots, kept counts, exp_counts, l_aux.
+__global__ void __launch_bounds__(SCAN_THREADS) moe_scan_kernel(const float* __restrict__ logits,
+                                                                const float* __restrict__ gates,
+                                                                const float* __restrict__ noise, int S, int E, int k,
+                                                                int C, int* __restrict__ expert,
+                                                                float* __restrict__ gate, int* __restrict__ slot,
+                                                                int* __restrict__ kept, int* __restrict__ exp_counts,
+                                                                float* __restrict__ l_aux) {
+  __shared__ int cnt[SCAN_THREADS][MOE_MAX_E];  // per-thread segment counts, then exclusive offsets
+  __shared__ int total1[MOE_MAX_E], total2[MOE_MAX_E];
+  __shared__ float me_sum[MOE_MAX_E];
+  __shared__ float red[SCAN_THREADS / 32];
+  const int tid = threadIdx.x;
+  const int seg = (S + SCAN_THREADS - 1) / SCAN_THREADS;
+  const int s0 = tid * seg, s1 = min(S, s0 + seg);
+
+  // ---- pass 0: choose experts; me = sum_s gates[s,e]
+  float me_loc[MOE_MAX_E];
+#pragma unroll
+  for (int e = 0; e < MOE_MAX_E; ++e) me_loc[e] = 0.0f;
+  for (int s = s0; s < s1; ++s) {
+    const float* g = gates + static_cast<long long>(s) * E;
+    int i1 = 0;
+    float best = g[0];
+    for (int e = 0; e < E; ++e) {
+      if (e < MOE_MAX_E) me_loc[e] += g[e];
+      if (g[e] > best) {
+        best = g[e];
+        i1 = e;
+      }
+    }
+    expert[s * k] = i1;
+    if (k == 2) {
+      const float* lg = logits + static_cast<long long>(s) * E;
+      int i2 = -1;
+      float b2 = -INFINITY;
+      for (int e = 0; e < E; ++e) {
+        if (e == i1) continue;
+        const float v = lg[e] + (noise ? noise[static_cast<long long>(s) * E + e] : 0.0f);
+        if (i2 < 0 || v > b2) {
+          b2 = v;
+          i2 = e;
+        }
+      }
+      expert[s * k + 1] = i2;
+    }
+  }
+  for (int e = 0; e < E; ++e) {
+    float v = warp_sum(me_loc[e]);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid < 32) {
+      float t = red[tid];
+      t = warp_sum(t);
+      if (tid == 0) me_sum[e] = t;
+    }
+  }
+  __syncthreads();
+
+  // ---- routes: j = 0 (first choice), j = 1 (second choice; its locations start after all first choices)
+  for (int j = 0; j < k; ++j) {
+    for (int e = 0; e < E; ++e) cnt[tid][e] = 0;
+    for (int s = s0; s < s1; ++s) cnt[tid][expert[s * k + j]] += 1;
+    __syncthreads();
+    // exclusive scan over threads, one warp per expert
+    const int w = tid >> 5, lane = tid & 31;
+    if (w < E) {
+      int run = 0;
+      for (int base = 0; base < SCAN_THREADS; base += 32) {
+        const int v = cnt[base + lane][w];
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int n = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += n;
+        }
+        cnt[base + lane][w] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) {
+        if (j == 0)
+          total1[w] = run;
+        else
+          total2[w] = run;
+      }
+    }
+    __syncthreads();
+    // top-1 with Random Token Selection: when an expert overflows, keep the C tokens with the largest uniforms.
+    const bool rts = (k == 1 && noise != nullptr);
+    int run[MOE_MAX_E];
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e) run[e] = (e < E) ? cnt[tid][e] : 0;
+    for (int s = s0; s < s1; ++s) {
+      const int e = expert[s * k + j];
+      int loc = 0;
+#pragma unroll
+      for (int q = 0; q < MOE_MAX_E; ++q)
+        if (q == e) loc = run[q]++;
+      if (j == 1) loc += total1[e];
+      bool keep = loc < C;
+      if (rts && total1[e] > C) {
+        const float u = noise[static_cast<long long>(s) * E + e];
+        int rank = 0;
+        for (int t = 0; t < S; ++t) {
+          if (expert[t] != e || t == s) continue;
+          const float ut = noise[static_cast<long long>(t) * E + e];
+          if (ut > u || (ut == u && t < s)) ++rank;
+        }
+        keep = rank < C;
+        loc = -2;  // resolved below (locations are the cumsum over KEPT tokens)
+      }
+      slot[s * k + j] = keep ? loc : -1;
+    }
+    __syncthreads();
+    if (rts) {
+      // overflowing experts: recompute locations over kept tokens (serial per expert; training-only rare path)
+      if (tid < E && total1[tid] > C) {
+        int loc = 0;
+        for (int s = 0; s < S; ++s)
+          if (expert[s] == tid && slot[s] == -2) slot[s] = loc++;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- finalize: global rows, gate values, counts, l_aux
+  for (int s = s0; s < s1; ++s) {
+    float gsel[2] = {0.0f, 0.0f};
+    for (int j = 0; j < k; ++j) {
+      const int e = expert[s * k + j];
+      const int loc = slot[s * k + j];
+      gsel[j] = loc >= 0 ? gates[static_cast<long long>(s) * E + e] : 0.0f;
+      slot[s * k + j] = loc >= 0 ? e * C + loc : -1;
+    }
+    if (k == 2) {
+      const float denom = fmaxf(gsel[0] + gsel[1], 1.1920928955078125e-07f);
+      gsel[0] /= denom;
+      gsel[1] /= denom;
+    }
+    for (int j = 0; j < k; ++j) gate[s * k + j] = gsel[j];
+  }
+  if (tid < E) {
+    const int c1 = total1[tid];
+    exp_counts[tid] = c1;
+    int kc = min(c1, C);
+    if (k == 2) kc = min(c1 + total2[tid], C);
+    kept[tid] = kc;
+  }
+  if (tid == 0) {
+    float acc = 0.0f;
+    for (int e = 0; e < E; ++e) acc += (me_sum[e] / S) * (static_cast<float>(total1[e]) / S);
+    *l_aux = acc * E;
+  }
+}
+
+__global__ void __launch_bounds__(128) moe_dispatch_kernel(const __nv_bfloat16* __restrict__ h, long long ldh,
+                                                           const int* __restrict__ slot,
+                                                           __nv_bfloat16* __restrict__ xperm, int k, int D) {
+  const int r = blockIdx.x;  // token * k + route
+  const int dst = slot[r];
+  if (dst < 0) return;
+  const uint4* src = reinterpret_cast<const uint4*>(h + static_cast<long long>(r / k) * ldh);
+  uint4* out = reinterpret_cast<uint4*>(xperm + static_cast<long long>(dst) * D);
+  for (int c = threadIdx.x; c < D / 8; c += 128) out[c] = src[c];
+}
+
+__global__ void __launch_bounds__(128) moe_combine_kernel(const __nv_bfloat16* __restrict__ y,
+                                                          const int* __restrict__ slot,
+                                                          const float* __restrict__ gate,
+                                                          const __nv_bfloat16* __restrict__ residual, long long ldr,
+                                                          __nv_bfloat16* __restrict__ out, long long ldo, int k,
+                                                          int D) {
+  const int s = blockIdx.x;
+  int sl[2] = {-1, -1};
+  float g[2] = {0.0f, 0.0f};
+  for (int j = 0; j < k; ++j) {
+    sl[j] = slot[s * k + j];
+    g[j] = bf16_round(gate[s * k + j]);  // combine_weights.type_as(input)
+  }
+  const __nv_bfloat16* rr = residual ? residual + static_cast<long long>(s) * ldr : nullptr;
+  __nv_bfloat16* orow = out + static_cast<long long>(s) * ldo;
+  for (int c = threadIdx.x * 8; c < D; c += 128 * 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int j = 0; j < k; ++j) {
+      if (sl[j] < 0) continue;
+      const uint4 raw = *reinterpret_cast<const uint4*>(y + static_cast<long long>(sl[j]) * D + c);
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(hp[i]);
+        acc[2 * i] += g[j] * f.x;
+        acc[2 * i + 1] += g[j] * f.y;
+      }
+    }
+    if (rr != nullptr) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(rr + c);
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(hp[i]);
+        acc[2 * i] = bf16_round(acc[2 * i]) + f.x;
+        acc[2 * i + 1] = bf16_round(acc[2 * i + 1]) + f.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]);
+    o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]);
+    o.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(orow + c) = o;
+  }
+}
+
+int moe_route(const mpl_moe_route_args& a, cudaStream_t stream) {
+  if (a.S <= 0) return MPL_OK;
+  if (a.h == nullptr || a.wg == nullptr || a.logits == nullptr || a.gates == nullptr || a.expert == nullptr ||
+      a.gate == nullptr || a.slot == nullptr || a.kept == nullptr || a.exp_counts == nullptr || a.l_aux == nullptr)
+    return MPL_ERR_ARG;
+  if (a.E < 1 || a.E > MOE_MAX_E || a.k < 1 || a.k > 2 || a.k > a.E || a.capacity < 1) return MPL_ERR_UNSUPPORTED;
+  if ((a.D % 8) != 0 || (a.ldh % 8) != 0) return MPL_ERR_ALIGN;
+  moe_router_kernel<<<(a.S + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(a.h), a.ldh, a.wg, a.S, a.D,
+                                                      a.E, a.logits, a.gates);
+  moe_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(a.logits, a.gates, a.noise, a.S, a.E, a.k, a.capacity, a.expert,
+                                                  a.gate, a.slot, a.kept, a.exp_counts, a.l_aux);
+  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+}
+
+int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D,
+                 cudaStream_t stream) {
+  if (S <= 0) return MPL_OK;
+  if (h == nullptr || slot == nullptr || xperm == nullptr) return MPL_ERR_ARG;
+  if ((D % 8) != 0 || (ldh % 8) != 0) return MPL_ERR_ALIGN;
+  moe_dispatch_kernel<<<S * k, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(h), ldh, slot,
+                                                 static_cast<__nv_bfloat16*>(xperm), k, D);
+  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+}
+
+int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
+                long long ldo, int S, int k, int D, cudaStream_t stream) {
+  if (S <= 0) return MPL_OK;
+  if (y == nullptr || slot == nullptr || gate == nullptr || out == nullptr) return MPL_ERR_ARG;
+  if ((D % 8) != 0 || (ldr % 8) != 0 || (ldo % 8) != 0 || k < 1 || k > 2) return MPL_ERR_ALIGN;
+  moe_combine_kernel<<<S, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), slot, gate,
+                                            static_cast<const __nv_bfloat16*>(residual), ldr,
+                                            static_cast<__nv_bfloat16*>(out), ldo, k, D);
+  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+}
+
+}  // namespace mpl
+
+extern "C" int mpl_moe_route(const mpl_moe_route_args* a, void* stream) {
+  if (a == nullptr) return MPL_ERR_ARG;
+  return mpl::moe_route(*a, static_cast<cudaStream_t>(stream));
+}
+extern "C" int mpl_moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D,
+                                void* stream) {
+  return mpl::moe_dispatch(h, ldh, slot, xperm, S, k, D, static_cast<cudaStream_t>(stream));
+}
+extern "C" int mpl_moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr,
+                               void* out, long long ldo, int S, int k, int D, void* stream) {
+  return mpl::moe_combine(y, slot, gate, residual, ldr, out, ldo, S, k, D, static_cast<cudaStream_t>(stream));
+}

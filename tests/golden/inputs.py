@@ -1,0 +1,72 @@
+"""Deterministic inputs of the golden fixtures (torch CPU generator, fixed seeds). Shared by make_golden.py (which runs
+the reference on them) and by the tests (which run the oracle / the CUDA path on them), so only the reference's OUTPUTS
+need to be stored in the .pt files."""
+import torch
+
+SAM_ENC_CFG = dict(embed_dim=64, depth=4, num_heads=1, image_size=256, patch_size=16, out_chans=32)
+SAM_ENC_SEED, SAM_HEAD_SEED = 11, 12
+
+
+def sam_encoder_images():
+    return torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16).float()
+
+
+def sam_head_inputs(dim=256):
+    g = torch.Generator().manual_seed(6)
+    emb = torch.randn(1, dim, 16, 16, generator=g).to(torch.bfloat16).float()
+    text = torch.randn(1, 1, dim, generator=g).to(torch.bfloat16).float()
+    return emb, text
+
+
+def arch_inputs(D=64, Dv=32):
+    g = torch.Generator().manual_seed(7)
+    params = {}
+    shapes = dict(projector={"0.weight": (D, Dv), "0.bias": (D,), "2.weight": (D, D), "2.bias": (D,)},
+                  compressor={"norm.weight": (D,), "norm.bias": (D,), "proj.weight": (D, D), "proj.bias": (D,)},
+                  mask_encoder={"encoder.0.weight": (64, 1, 3, 3), "encoder.0.bias": (64,),
+                                "encoder.2.weight": (128, 64, 3, 3), "encoder.2.bias": (128,),
+                                "encoder.4.weight": (256, 128, 3, 3), "encoder.4.bias": (256,),
+                                "encoder.6.weight": (256, 256, 3, 3), "encoder.6.bias": (256,),
+                                "proj.weight": (D, 256), "proj.bias": (D,), "norm.weight": (D,), "norm.bias": (D,)})
+    for mod, d in shapes.items():
+        params[mod] = {k: (torch.randn(s, generator=g) * (0.2 if len(s) < 4 else (s[1] * 9) ** -0.5)) for k, s in d.items()}
+    feats = torch.randn(2, 576, Dv, generator=g)
+    masks = (torch.rand(2, 1, 336, 336, generator=g) > 0.8).float()
+    fmap = torch.randn(2, 576, D, generator=g)
+    rmasks = [[(torch.rand(24, 24, generator=g) > 0.7).float(), (torch.rand(24, 24, generator=g) > 0.9).float()],
+              [(torch.rand(24, 24, generator=g) > 0.5).float()]]
+    return params, feats, masks, fmap, rmasks
+
+
+def splice_inputs(use_se, D=16, V=50, n_img=6):
+    g = torch.Generator().manual_seed(8 + int(use_se))
+    embed = torch.randn(V, D, generator=torch.Generator().manual_seed(9))
+    ids = torch.randint(3, V, (2, 12), generator=g)
+    ids[0, 2], ids[0, 7] = -200, -300
+    ids[1, 1] = -200
+    labels = ids.clone()
+    labels[labels < 0] = -100
+    am = torch.ones(2, 12, dtype=torch.bool)
+    am[1, 9:] = False
+    feats = torch.randn(2, n_img, D, generator=g)
+    feats_r = torch.randn(2, 4, D, generator=g)  # 2x2 feature map for the region path
+    rm = [[(torch.rand(24, 24, generator=g) > 0.6).float()]]  # one entry per VALID sample
+    valid = [[True], []]
+    ids2 = ids.clone()
+    ids2[0, 7] = 5
+    return dict(embed=embed, ids=ids, ids2=ids2, labels=labels, am=am, feats=feats, feats_r=feats_r, region_masks=rm,
+                valid=valid)
+
+
+def heads_inputs():
+    g = torch.Generator().manual_seed(10)
+    low = torch.randn(1, 1, 64, 64, generator=g)
+    ids = torch.randint(3, 40, (2, 10), generator=g)
+    ids[0, 1], ids[0, 6], ids[1, 0], ids[1, 4], ids[1, 9] = -200, 42, -200, -200, 42
+    pred = torch.randn(1, 30, 40, generator=g) * 3
+    gt = (torch.rand(1, 30, 40, generator=g) > 0.6).float()
+    piou = torch.rand(1, generator=g)
+    return dict(low=low, ids=ids, pred=pred, gt=gt, piou=piou)
+
+
+POSTPROCESS_CASES = dict(square=((256, 256), (336, 336)), wide=((256, 192), (300, 225)), tiny=((48, 256), (60, 320)))
