@@ -280,9 +280,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(const AttnP
   float acc[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
-  for (int key = warp * 4 + grp; key < Tk; key += DEC_WARPS * 4) {
-    const __nv_bfloat16* kr = kg + static_cast<long long>(key) * p.k_st;
-    const __nv_bfloat16* vr = vg + static_cast<long long>(key) * p.v_st;
+  // The trip count is warp-uniform (full-mask shuffles inside): groups past the end compute a masked dummy key.
+  for (int k0 = warp * 4; k0 < Tk; k0 += DEC_WARPS * 4) {
+    const int key = k0 + grp;
+    const bool valid = key < Tk;
+    const int kk = valid ? key : Tk - 1;
+    const __nv_bfloat16* kr = kg + static_cast<long long>(kk) * p.k_st;
+    const __nv_bfloat16* vr = vg + static_cast<long long>(kk) * p.v_st;
     const uint4 ka = *reinterpret_cast<const uint4*>(kr), kc = *reinterpret_cast<const uint4*>(kr + 8);
     const uint4 va = *reinterpret_cast<const uint4*>(vr), vc = *reinterpret_cast<const uint4*>(vr + 8);
     const __nv_bfloat162* hka = reinterpret_cast<const __nv_bfloat162*>(&ka);
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(const AttnP
     dot += __shfl_xor_sync(0xffffffffu, dot, 2);
     dot += __shfl_xor_sync(0xffffffffu, dot, 4);
     float sc = dot * sl2;
-    if (mrow != nullptr && mrow[key] == 0) sc = -INFINITY;
+    if (!valid || (mrow != nullptr && mrow[kk] == 0)) sc = -INFINITY;
     const float mn = fmaxf(m, sc);
     const float msafe = (mn == -INFINITY) ? 0.0f : mn;
     const float corr = exp2f(m - msafe);

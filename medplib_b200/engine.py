@@ -15,8 +15,31 @@ from . import _lib, ops
 bf16 = torch.bfloat16
 
 
+_SINK = None  # list collecting every tensor whose address goes into a weight table (keeps the storage alive)
+
+
 def _p(t):
-    return t.data_ptr() if t is not None else None
+    if t is None:
+        return None
+    if _SINK is not None:
+        _SINK.append(t)
+    return t.data_ptr()
+
+
+class _collect:
+    """with _collect(engine): every _p() inside records its tensor in engine._refs."""
+
+    def __init__(self, owner):
+        self.owner = owner
+
+    def __enter__(self):
+        global _SINK
+        self.owner._refs = []
+        self.prev, _SINK = _SINK, self.owner._refs
+
+    def __exit__(self, *a):
+        global _SINK
+        _SINK = self.prev
 
 
 def _vp(t):
@@ -66,6 +89,10 @@ class LlamaEngine:
         self.refresh(sd)
 
     def refresh(self, sd):
+        with _collect(self):
+            self._refresh(sd)
+
+    def _refresh(self, sd):
         c, p = self.cfg, self.prefix
         L = c["num_layers"]
         self._keep = []
@@ -181,6 +208,10 @@ class ClipEngine:
         self.refresh(sd)
 
     def refresh(self, sd):
+        with _collect(self):
+            self._refresh(sd)
+
+    def _refresh(self, sd):
         c, p = self.cfg, self.prefix + "vision_model."
         L = c["num_layers"]
         n_run = self.select_layer if self.select_layer >= 0 else L + 1 + self.select_layer
@@ -258,6 +289,10 @@ class SamEncoderEngine:
         self.refresh(sd)
 
     def refresh(self, sd):
+        with _collect(self):
+            self._refresh(sd)
+
+    def _refresh(self, sd):
         c, p = self.cfg, self.prefix
         depth, D = c["depth"], c["embed_dim"]
         self._keep = []
@@ -337,6 +372,10 @@ class MaskDecoderEngine:
         self.refresh(sd)
 
     def refresh(self, sd):
+        with _collect(self):
+            self._refresh(sd)
+
+    def _refresh(self, sd):
         p = self.prefix + "mask_decoder."
         pe = self.prefix + "prompt_encoder."
         self._keep = []

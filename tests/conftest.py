@@ -25,3 +25,10 @@ def pytest_runtest_logstart(nodeid, location):
     if os.environ.get("MPL_TEST_TRACE"):
         sys.stderr.write(f"START {nodeid}\n")
         sys.stderr.flush()
+
+
+def pytest_runtest_logreport(report):
+    # immediate, flushed failure text (a later hung kernel would otherwise swallow pytest's end-of-run summary)
+    if os.environ.get("MPL_TEST_TRACE") and report.failed:
+        sys.stderr.write(f"\nRESULT FAILED {report.nodeid} [{report.when}]\n{report.longreprtext[-1500:]}\n")
+        sys.stderr.flush()

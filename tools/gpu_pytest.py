@@ -43,6 +43,13 @@ while remaining:
                     results.setdefault(current, "done")
                 current, last, first = m.group(1), time.time(), False
         if p.poll() is not None:
+            try:
+                raw = os.read(p.stdout.fileno(), 1 << 20)
+                tail = raw.decode("utf-8", "replace")
+                buf += tail
+                log.write(tail); log.flush()
+            except (BlockingIOError, OSError):
+                pass
             break
         limit = 240.0 if first else args.per_test  # the first import of torch on a fresh box is slow
         if time.time() - last > limit:
@@ -52,6 +59,8 @@ while remaining:
         time.sleep(0.2)
     if current is not None and not hung:
         results.setdefault(current, "done")
+    for m in re.finditer(r"^RESULT (FAILED) (\S+)", buf, re.M):
+        results[m.group(2)] = m.group(1)
     for m in re.finditer(r"^(FAILED|ERROR) (\S+)", buf, re.M):
         results[m.group(2)] = m.group(1)
     if hung and current is not None:
