@@ -1,0 +1,320 @@
+"""bench.py — MedPLIB-7B pixel grounding (BASELINE.json configs[1]) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W              ours: hand-written sm_100a kernels behind the C ABI
+  python bench.py --impl reference --gpus N --steps K ...    the reference's path on the host cores (CPU oracle port)
+  python bench.py --workload decode ...                      secondary: VQA decode B=8 (configs[2]), tokens/s
+
+A "step" is one image through MedPLIBForCausalLM.evaluate(): CLIP-L/14-336 -> mm_projector -> splice (T = 40 + 575) ->
+LLaMA-7B-MoE (2 experts, top-1) prefill -> 8 greedy decode tokens (<SEG> forced at new token 4, since random weights
+never emit it) -> text_hidden_fcs -> SAM-Med2D ViT-B encoder -> two-way mask decoder -> bilinear resize to 336x336.
+Weights: random init of the reference architecture (no checkpoints offline), bf16. Inference shards as independent
+replicas: with N ranks every rank runs its own images, value = N * K images / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+bf16 = torch.bfloat16
+SEG = 32003
+N_TEXT, N_NEW, SEG_AT = 40, 8, 4
+DIMS = dict(D=4096, F=11008, L=32, H=32, V=32267, E=2)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sus=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+def make_inputs(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    images_clip = torch.randn(1, 3, 336, 336, generator=torch.Generator().manual_seed(0))
+    images = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(1))
+    ids = torch.randint(3, 31999, (1, N_TEXT), generator=torch.Generator().manual_seed(2))
+    ids[0, 2], ids[0, 3], ids[0, 4] = 32001, -200, 32002  # <im_start> IMAGE <im_end>
+    return images_clip, images, ids
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def build_model(dev, small=False):
+    from medplib_b200.model import MedPLIBForCausalLM, MedPLIBMoELlamaConfig
+    d = DIMS if not small else dict(D=512, F=1024, L=2, H=4, V=32267, E=2)
+    cfg = MedPLIBMoELlamaConfig(hidden_size=d["D"], intermediate_size=d["F"], num_hidden_layers=d["L"],
+                                num_attention_heads=d["H"], num_key_value_heads=d["H"], vocab_size=d["V"],
+                                rms_norm_eps=1e-5, max_position_embeddings=4096, mm_vision_select_layer=-2,
+                                mm_projector_type="mlp2x_gelu", max_sample_point=512)
+    cfg.moe = dict(num_experts=[d["E"]], top_k_experts=1, capacity_factor=1.5, eval_capacity_factor=2.0,
+                   min_capacity=0, use_residual=False, router_aux_loss_coef=0.01, moe_layers_idx=None,
+                   moe_mode="dense", ep_size=1)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(bf16)
+    try:
+        with torch.device(dev):
+            m = MedPLIBForCausalLM(cfg, test_only=True, seg_token_idx=SEG)
+    finally:
+        torch.set_default_dtype(old)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "deepspeed_experts.1." in n:  # experts start as copies (like the reference); make them differ
+                p.normal_(0.0, 0.02)
+    m.config.eos_token_id = -1  # never stop early: fixed work per step
+    m.config.mm_use_im_start_end = True
+    return m.to(bf16).to(dev).eval()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.rows, self.p, self.gpu = [], None, gpu
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = max([int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 4 + i and r[4 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def gemm_flops_per_image(T=N_TEXT - 1 + 576):
+    """Algorithmic FLOPs of the tcgen05 GEMM launches of one step (2*M*N*K; top-1 MoE = dense FFN FLOPs)."""
+    d = DIMS
+    llama = T * d["L"] * (4 * d["D"] * d["D"] + 3 * d["D"] * d["F"]) * 2
+    clip = 577 * 23 * (4 * 1024 * 1024 + 2 * 1024 * 4096) * 2 + 576 * 592 * 1024 * 2
+    proj = 576 * (1024 * 4096 + 4096 * 4096) * 2
+    sam = 12 * (256 * (4 * 768 * 768 + 2 * 768 * 3072) * 2) + 8 * (784 - 256) * 3 * 768 * 768 * 2 \
+        + 12 * (64 * 6912 * 768 + 64 * 768 * 12288) * 2 + 256 * (768 * 256 + 2304 * 256) * 2
+    return float(llama + clip + proj + sam)
+
+
+def run_ours(args, rank, world, dev):
+    import ctypes
+    from medplib_b200 import _lib
+    lib = _lib.load()
+    torch.cuda.set_device(dev)
+    m = build_model(dev, small=args.small)
+    images_clip, images, ids = make_inputs()
+    label = torch.zeros(336, 336)
+    forced = {SEG_AT: SEG}
+    # value: inputs already resident in HBM
+    d_clip, d_img, d_ids = images_clip.to(dev).to(bf16), images.to(dev).to(bf16), ids.to(dev)
+    # e2e: pinned host buffers, fp32 like the reference's collator output; cast on the device
+    h_clip, h_img, h_ids = images_clip.pin_memory(), images.pin_memory(), ids.pin_memory()
+
+    def step_resident():
+        return m.evaluate(d_clip, d_img, d_ids, [(256, 256)], [label], max_new_tokens=N_NEW, forced_tokens=forced)
+
+    def step_e2e():
+        c = h_clip.to(dev, non_blocking=True).to(bf16)
+        i = h_img.to(dev, non_blocking=True).to(bf16)
+        t = h_ids.to(dev, non_blocking=True)
+        out_ids, masks = m.evaluate(c, i, t, [(256, 256)], [label], max_new_tokens=N_NEW, forced_tokens=forced)
+        return out_ids.cpu(), masks[0].cpu()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.mpl_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.mpl_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+    clocks = ClockSampler(dev.index or 0)
+    clocks.start()
+    ms, launches = timed(step_resident, args.steps)
+    ck = clocks.stop()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    # in-situ duration of the dominant kernel (every tcgen05 GEMM launch of a step), CUDA events on the launch stream
+    lib.mpl_profile_gemm(1)
+    psteps = min(args.steps, 3)
+    for _ in range(psteps):
+        step_resident()
+    tot, cnt = ctypes.c_float(0), ctypes.c_int(0)
+    lib.mpl_profile_gemm_read(ctypes.byref(tot), ctypes.byref(cnt))
+    lib.mpl_profile_gemm(0)
+    pk = peaks()
+    gemm_ms = tot.value / psteps
+    ach = gemm_flops_per_image() / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 and not args.small else None
+    if rank != 0:
+        return
+    h2d = (h_clip.numel() + h_img.numel()) * 4 + h_ids.numel() * 8
+    d2h = 336 * 336 * 2 + (N_TEXT + N_NEW) * 8
+    line = {
+        "metric": "pixel-grounding images/sec at 7B (MedPLIB-7B-2e, bf16, batch 1)", "value": world * args.steps / (ms * 1e-3),
+        "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "MedPLIB-7B pixel-grounding (--eval_seg) bf16, batch 1: evaluate() = CLIP-L/14-336 + "
+                               "projector + LLaMA-7B-MoE(2 experts, top-1) prefill T=615 + 8 decode tokens (<SEG> forced)"
+                               " + text_hidden_fcs + SAM-Med2D ViT-B@256 + mask decoder + resize 336x336",
+                   "weights": "random init, 11.07 B params", "parallelism": f"replicas x{world}",
+                   "l2": "every step streams ~22 GB of weights (>> 126 MB L2), no explicit flush needed",
+                   "small": bool(args.small)},
+        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": ck,
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s",
+                     "frac": (ach / pk["tf_sus"]) if ach else None, "traffic": None,
+                     "kernel": "gemm_bf16_tcgen05_kernel (all launches of a step: algorithmic 2MNK / summed CUDA-event"
+                               " durations)", "kernel_ms_per_step": gemm_ms, "kernel_launches_per_step": cnt.value / psteps,
+                     "peak_source": pk["src"] + " sustained bf16"},
+    }
+    if args.cpu_baseline and world >= 1:
+        line["cpu_baseline"] = cpu_reference(sample_steps=1)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference(sample_steps=1):
+    """The reference's path on the host cores: oracle port (fp32, all threads) on a bounded sample — ONE decoder layer,
+    ONE CLIP layer and ONE SAM block at full 7B width on the benchmark's shapes — scaled by the layer counts."""
+    from oracle import clip, llama, sam, weights, arch, heads
+    torch.set_num_threads(os.cpu_count() or 1)
+    d = DIMS
+    t0 = time.time()
+    lcfg = dict(hidden_size=d["D"], intermediate_size=d["F"], num_layers=1, num_heads=d["H"], vocab_size=64,
+                rms_norm_eps=1e-5, max_position_embeddings=4096, rope_theta=1e4,
+                moe=dict(num_experts=2, top_k_experts=1, capacity_factor=1.5, eval_capacity_factor=2.0, min_capacity=0,
+                         router_aux_loss_coef=0.01))
+    sd = weights.llama(lcfg, seed=0, dtype=torch.float32)
+    T = N_TEXT - 1 + 576
+    x = torch.randn(1, T, d["D"])
+    ccfg = dict(hidden_size=1024, intermediate_size=4096, num_layers=1, num_heads=16, image_size=336, patch_size=14)
+    csd = weights.clip(ccfg, seed=1, dtype=torch.float32)
+    scfg = dict(embed_dim=768, depth=1, num_heads=12, image_size=256, patch_size=16, out_chans=256)
+    ssd = weights.sam_encoder(scfg, seed=2, dtype=torch.float32)
+    hsd = weights.sam_head(seed=3, dtype=torch.float32)
+    img_c, img_s = torch.randn(1, 3, 336, 336), torch.randn(1, 3, 256, 256)
+    setup = time.time() - t0
+    times = []
+    with torch.no_grad():
+        for _ in range(sample_steps):
+            t = time.time()
+            out = llama.model_forward(sd, lcfg, x)
+            t_pre = time.time() - t
+            t = time.time()
+            kv = out["past_key_values"]
+            for s in range(N_NEW - 1):
+                o = llama.model_forward(sd, lcfg, torch.randn(1, 1, d["D"]), torch.ones(1, T + s + 1, dtype=torch.bool), kv)
+                kv = o["past_key_values"]
+            t_dec = time.time() - t
+            t = time.time()
+            clip.vision_tower(csd, "", img_c, ccfg, select_layer=1)
+            t_clip = time.time() - t
+            t = time.time()
+            emb = sam.image_encoder(ssd, "", img_s, num_heads=12)
+            t_sam = time.time() - t
+            t = time.time()
+            dpe = sam.dense_pe(hsd, "prompt_encoder.", (16, 16))
+            sp, de = sam.prompt_encoder_text(hsd, "prompt_encoder.", torch.randn(1, 1, 256), (16, 16))
+            low, _ = sam.mask_decoder(hsd, "mask_decoder.", emb, dpe, sp, de)
+            heads.postprocess_masks(low, (256, 256), (336, 336))
+            t_head = time.time() - t
+            times.append((t_pre + t_dec) * d["L"] + t_clip * 23 + t_sam * 12 + t_head)
+    sec = sorted(times)[len(times) // 2]
+    return {"value": 1.0 / sec, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle port, fp32, all host threads: 1 of 32 LLaMA-MoE layers (prefill T=615 + 7 decode steps), "
+                      "1 of 23 CLIP layers, 1 of 12 SAM blocks (+neck) and the full mask head timed at 7B width; "
+                      f"per-image time = layer times x layer counts = {sec:.1f} s (weight setup {setup:.0f} s untimed)",
+            "seconds_per_image_scaled": sec}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(1)
+    t0 = time.time()
+    res = [cpu_reference(1) for _ in range(min(args.steps, 3))]
+    wall = time.time() - t0
+    sec = sorted(r["seconds_per_image_scaled"] for r in res)[len(res) // 2]
+    val = 1.0 / sec
+    cb = dict(res[0], value=val)
+    print(json.dumps({
+        "impl": "reference", "metric": "pixel-grounding images/sec at 7B (MedPLIB-7B-2e, bf16, batch 1)", "value": val,
+        "unit": "images/s", "n_gpus": world, "steps": len(res), "warmup": min(args.warmup, 1),
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "same workload as the default arm, reference path on host cores (oracle port; the "
+                               "reference's third-party deps transformers 4.31 / deepspeed 0.13.1 are not installable "
+                               "offline)", "wall_s": wall},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--small", action="store_true", help="2-layer toy LLaMA (plumbing check, not a benchmark)")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: medplib_b200 has no CPU path (use --impl reference for the CPU arm)")
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        torch.cuda.set_device(dev)
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    args.cpu_baseline = args.cpu_baseline and rank == 0 and world == 1
+    run_ours(args, rank, world, dev)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

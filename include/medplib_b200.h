@@ -37,6 +37,8 @@ enum { MPL_DT_BF16 = 0, MPL_DT_F32 = 1 };
 /* Library / device probe. Returns the ABI version; fills sm count and compute capability when non-null. */
 int mpl_version(void);
 int mpl_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches is a delta of this). */
+long long mpl_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * K1  C[M,N] = epilogue(A[M,K] · W[N,K]^T)      tcgen05 + TMA, bf16 in, fp32 accumulate in TMEM
@@ -73,6 +75,10 @@ typedef struct {
   int tile_n;    /* 0 = auto, else 128, 192 or 256 */
 } mpl_gemm_args;
 int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream);
+/* In-situ timing of the tcgen05 GEMM launches (bench.py roofline): enable, run, then read the summed CUDA-event
+ * durations (ms) and the launch count since enabling; reading synchronises the device and resets the counters. */
+int mpl_profile_gemm(int enable);
+int mpl_profile_gemm_read(float* total_ms, int* launches);
 
 /* K3  same contract as mpl_gemm_bf16 for M <= 16 (decode batch, [SEG] rows, mask-decoder tokens): HBM-bound
  * streaming kernel, weights read once with 16-byte loads into mma.sync fragments (nb <= 3 as grid.y).

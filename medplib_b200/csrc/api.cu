@@ -1,7 +1,12 @@
 // Library probe entry points of the C ABI.
 #include "internal.h"
 
+namespace mpl {
+unsigned long long g_launches = 0;
+}
+
 extern "C" int mpl_version(void) { return 1; }
+extern "C" long long mpl_launch_count(void) { return static_cast<long long>(mpl::g_launches); }
 
 extern "C" int mpl_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

@@ -373,7 +373,7 @@ static int launch_flash(const AttnParams& p, cudaStream_t stream) {
   }
   dim3 grid((p.Tq + FA_BM - 1) / FA_BM, p.H, p.B);
   flash_fwd_kernel<D><<<grid, FA_THREADS, smem, stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  return mpl::launch_status();
 }
 
 }  // namespace mpl
@@ -406,7 +406,7 @@ extern "C" int mpl_attention(const mpl_attn_args* a, void* stream_) {
   if (a->Tq == 1 && a->head_dim == 128 && a->rel_h == nullptr) {
     dim3 grid(p.H, p.B);
     decode_attn_kernel<128><<<grid, DEC_WARPS * 32, 0, stream>>>(p);
-    return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+    return mpl::launch_status();
   }
   if (p.tk_dev != nullptr) return MPL_ERR_UNSUPPORTED;  // device-side Tk only on the decode path
   if (p.o_st % 2 != 0 || p.o_sh % 2 != 0 || p.o_sb % 2 != 0) return MPL_ERR_ALIGN;

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -352,6 +353,20 @@ static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long lon
   return r == CUDA_SUCCESS ? MPL_OK : MPL_ERR_DRIVER;
 }
 
+// Optional in-situ timing of every tcgen05 GEMM launch (bench.py roofline): CUDA events recorded on the launching
+// stream around each launch, summed by mpl_profile_gemm_read after a synchronise.
+static bool g_prof = false;
+static std::vector<cudaEvent_t> g_prof_ev;  // pairs (start, stop)
+static size_t g_prof_used = 0;
+static cudaEvent_t prof_event() {
+  if (g_prof_used == g_prof_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof_ev.push_back(e);
+  }
+  return g_prof_ev[g_prof_used++];
+}
+
 static int g_num_sms = 0;
 int num_sms() {
   if (g_num_sms == 0) {
@@ -415,8 +430,10 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn) * nb;
   int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   if (grid < 1) grid = 1;
+  if (g_prof) cudaEventRecord(prof_event(), stream);
   gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB1, tmB2, p);
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  if (g_prof) cudaEventRecord(prof_event(), stream);
+  return mpl::launch_status();
 }
 
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
@@ -444,6 +461,25 @@ int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
 }
 
 }  // namespace mpl
+
+extern "C" int mpl_profile_gemm(int enable) {
+  mpl::g_prof = enable != 0;
+  mpl::g_prof_used = 0;
+  return MPL_OK;
+}
+extern "C" int mpl_profile_gemm_read(float* total_ms, int* launches) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return MPL_ERR_CUDA;
+  float sum = 0.0f;
+  for (size_t i = 0; i + 1 < mpl::g_prof_used; i += 2) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, mpl::g_prof_ev[i], mpl::g_prof_ev[i + 1]) != cudaSuccess) return MPL_ERR_CUDA;
+    sum += ms;
+  }
+  if (total_ms) *total_ms = sum;
+  if (launches) *launches = static_cast<int>(mpl::g_prof_used / 2);
+  mpl::g_prof_used = 0;
+  return MPL_OK;
+}
 
 extern "C" int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream) {
   if (args == nullptr) return MPL_ERR_ARG;

@@ -5,6 +5,12 @@
 #include "../../include/medplib_b200.h"
 
 namespace mpl {
+// number of kernels this library has launched in this process (bench.py reports the delta over its timed region)
+extern unsigned long long g_launches;
+inline int launch_status(int n = 1) {
+  g_launches += n;
+  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+}
 int num_sms();
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream);
 int skinny_gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream);

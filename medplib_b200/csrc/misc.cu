@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(128) region_sample_kernel(const __nv_bfloat16*
   out[c] = __float2bfloat16_rn(P > 0 ? acc / static_cast<float>(P) : 0.0f);
 }
 
-static inline int launched() { return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA; }
+static inline int launched() { return launch_status(); }
 
 }  // namespace mpl
 

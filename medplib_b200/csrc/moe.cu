@@ -300,7 +300,7 @@ int moe_route(const mpl_moe_route_args& a, cudaStream_t stream) {
                                                       a.E, a.logits, a.gates);
   moe_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(a.logits, a.gates, a.noise, a.S, a.E, a.k, a.capacity, a.expert,
                                                   a.gate, a.slot, a.kept, a.exp_counts, a.l_aux);
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  return launch_status(2);
 }
 
 int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D,
@@ -310,7 +310,7 @@ int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int
   if ((D % 8) != 0 || (ldh % 8) != 0) return MPL_ERR_ALIGN;
   moe_dispatch_kernel<<<S * k, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(h), ldh, slot,
                                                  static_cast<__nv_bfloat16*>(xperm), k, D);
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  return mpl::launch_status();
 }
 
 int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
@@ -321,7 +321,7 @@ int moe_combine(const void* y, const int* slot, const float* gate, const void* r
   moe_combine_kernel<<<S, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), slot, gate,
                                             static_cast<const __nv_bfloat16*>(residual), ldr,
                                             static_cast<__nv_bfloat16*>(out), ldo, k, D);
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  return mpl::launch_status();
 }
 
 }  // namespace mpl

@@ -231,7 +231,7 @@ extern "C" int mpl_rmsnorm(const void* x, long long ldx, const void* weight, voi
   mpl::rmsnorm_kernel<<<rows, mpl::NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
       static_cast<__nv_bfloat16*>(y), ldy, D, eps);
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  return mpl::launch_status();
 }
 
 extern "C" int mpl_layernorm(const void* x, long long ldx, const void* weight, const void* bias, void* y,
@@ -241,7 +241,7 @@ extern "C" int mpl_layernorm(const void* x, long long ldx, const void* weight, c
   mpl::layernorm_kernel<<<rows, mpl::NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
       static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), ldy, D, eps, act);
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  return mpl::launch_status();
 }
 
 extern "C" int mpl_pool_layernorm(const void* x, const void* weight, const void* bias, void* y, int n, int t_in,
@@ -251,5 +251,5 @@ extern "C" int mpl_pool_layernorm(const void* x, const void* weight, const void*
   mpl::pool_ln_kernel<<<n * t_out, mpl::NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight),
       static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), t_in, t_out, D, eps);
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  return mpl::launch_status();
 }

@@ -214,7 +214,7 @@ int skinny_gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
     else
       skinny_gemm_kernel<2, false><<<grid, SK_THREADS, 0, stream>>>(p);
   }
-  return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
+  return mpl::launch_status();
 }
 
 }  // namespace mpl

@@ -52,6 +52,7 @@ class GenerateOutput(ModelOutput):
     sequences: torch.LongTensor = None
     hidden_states: Optional[Tuple] = None
     last_hidden_state: Optional[torch.Tensor] = None  # [B, P_spliced + new - 1, D]: concat of per-step last-layer states
+    scores: Optional[Tuple] = None  # per-step fp32 logits [B, V] when output_scores=True
 
 
 class CLIPVisionTower(nn.Module):
@@ -64,6 +65,7 @@ class CLIPVisionTower(nn.Module):
         self.select_layer = getattr(args, "mm_vision_select_layer", -2)
         self.select_feature = getattr(args, "mm_vision_select_feature", "patch")
         self._engine = None
+        self._clip_config = getattr(args, "clip_config", None)  # dict: random-init tower of a given size (tests)
         if not delay_load:
             self.load_model()
 
@@ -74,9 +76,9 @@ class CLIPVisionTower(nn.Module):
             cfg = CLIPVisionConfig.from_pretrained(name)
             self.image_processor = CLIPImageProcessor.from_pretrained(name)
         else:  # no network in this build: random-init tower of the reference architecture
-            cfg = CLIPVisionConfig(**CLIP_L_336)
-            self.image_processor = CLIPImageProcessor(size={"shortest_edge": 336},
-                                                      crop_size={"height": 336, "width": 336})
+            cfg = CLIPVisionConfig(**(self._clip_config or CLIP_L_336))
+            self.image_processor = CLIPImageProcessor(size={"shortest_edge": cfg.image_size},
+                                                      crop_size={"height": cfg.image_size, "width": cfg.image_size})
         self.vision_tower = M.CLIPVisionModelHolder(cfg)
         if name and os.path.isdir(str(name)):
             _load_checkpoint_into(self.vision_tower, name)
@@ -675,7 +677,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
                  valid_region_masks_bool=None, mask_images=None, image_token_types=None, do_sample=False,
                  temperature=1.0, top_p=None, num_beams=1, max_new_tokens=512, use_cache=True,
                  output_hidden_states=False, return_dict_in_generate=False, eos_token_id=None,
-                 forced_tokens=None, **_unused):
+                 forced_tokens=None, output_scores=False, **_unused):
         """Greedy / sampled decoding with the reference's keyword surface (vqa_infer.py:430-442, MedPLIB.py:592-606).
         Prefill runs the tcgen05 path over the spliced prompt; every decode step is rmsnorm -> streaming GEMMs ->
         KV-cache attention -> MoE scatter/gather over B rows, fed by the device-side argmax (no host sync per token
@@ -713,10 +715,11 @@ class MedPLIBForCausalLM(PreTrainedModel):
         last = h[:, -1].contiguous()
         tokens = torch.zeros((B, max_new_tokens), dtype=torch.int64, device=dev)
         logits = torch.empty((B, self.lm_head.weight.shape[0]), dtype=torch.float32, device=dev)
-        n_done = max_new_tokens
-        finished_at = None
+        scores = [] if output_scores else None
         for step in range(max_new_tokens):
             ops.linear(last, self.lm_head.weight, out_dtype=torch.float32, out=logits)
+            if scores is not None:
+                scores.append(logits.clone())
             if do_sample and temperature and temperature > 0:
                 nxt = _sample(logits, temperature, top_p)
             else:
@@ -752,7 +755,8 @@ class MedPLIBForCausalLM(PreTrainedModel):
         if not return_dict_in_generate:
             return seq
         lh = hidden_all[:, :T + n_new - 1] if hidden_all is not None else None
-        return GenerateOutput(sequences=seq, hidden_states=None, last_hidden_state=lh)
+        return GenerateOutput(sequences=seq, hidden_states=None, last_hidden_state=lh,
+                              scores=tuple(scores) if scores is not None else None)
 
     def _has_gate_hooks(self):
         for layer in self.model.layers:

@@ -1,0 +1,139 @@
+"""GPU end-to-end parity of MedPLIBForCausalLM (evaluate / model_forward(inference=True) / generate) against the CPU
+oracle pipeline on a small random-init model with the reference's architecture (MoE top-1, 2 experts, SAM adapters).
+
+Stated tolerances (bf16 path vs bf16 oracle): step logits and mask logits within 6e-2 * max|ref|; greedy token ids
+bit-exact wherever the oracle's top-2 logit margin exceeds that noise; mask indices (logit > logit(0.1), the
+reference's `sigmoid(pred) > 0.1`, vqa_infer.py:565) bit-exact wherever the oracle's logit is farther than the noise
+from the threshold."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+SEG = 299
+CLIP_CFG = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, image_size=56,
+                patch_size=14, layer_norm_eps=1e-5)
+
+
+def build(dev, compress=False):
+    from medplib_b200.model import MedPLIBForCausalLM, MedPLIBMoELlamaConfig
+    torch.manual_seed(0)
+    cfg = MedPLIBMoELlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                                num_key_value_heads=2, vocab_size=300, rms_norm_eps=1e-5, max_position_embeddings=512,
+                                mm_vision_select_layer=-2, mm_projector_type="mlp2x_gelu", max_sample_point=512,
+                                initializer_range=0.06)
+    cfg.clip_config = CLIP_CFG
+    cfg.sam_config = dict(image_size=256, embed_dim=128, depth=3, num_heads=2)
+    cfg.moe = dict(num_experts=[2], top_k_experts=1, capacity_factor=1.5, eval_capacity_factor=2.0, min_capacity=0,
+                   use_residual=False, router_aux_loss_coef=0.01, moe_layers_idx=None, moe_mode="dense", ep_size=1)
+    m = MedPLIBForCausalLM(cfg, test_only=True, seg_token_idx=SEG, mm_token_compress=compress, use_mm_start_end=True)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():  # make experts differ, norms / biases / rel-pos non-trivial, router decisive
+        for n, p in m.named_parameters():
+            if "deepspeed_experts.1" in n or "rel_pos" in n or "pos_embed" in n or n.endswith(".bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.06)
+            if "wg.weight" in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            if "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+    m.config.mm_use_im_start_end = True
+    m = m.to(bf16).to(dev).eval()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    sd.update({k: v.detach().cpu() for k, v in m.named_buffers()})
+    ocfg = dict(clip=dict(hidden_size=128, intermediate_size=256, num_layers=3, num_heads=2, image_size=56,
+                          patch_size=14),
+                llama=dict(hidden_size=256, intermediate_size=512, num_layers=2, num_heads=2, vocab_size=300,
+                           rms_norm_eps=1e-5, max_position_embeddings=512, rope_theta=1e4, moe=m.config.moe),
+                sam=dict(num_heads=2), mm_use_im_start_end=True, mm_token_compress=compress)
+    return m, sd, ocfg
+
+
+def inputs(n_text=12, seg_in_prompt=False):
+    g = torch.Generator().manual_seed(2)
+    ids = torch.randint(3, 290, (1, n_text), generator=g)
+    ids[0, 2] = -200
+    if seg_in_prompt:
+        ids[0, 8] = SEG
+    clip_img = torch.randn(1, 3, 56, 56, generator=g).to(bf16)
+    sam_img = torch.randn(1, 3, 256, 256, generator=g).to(bf16)
+    return ids, clip_img, sam_img
+
+
+def _check(got, ref, rtol, name):
+    got, ref = got.float().cpu(), ref.float()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= rtol * scale, f"{name}: max err {err:.4e} > {rtol} * {scale:.4e}"
+
+
+def test_evaluate_matches_oracle(dev):
+    from oracle import pipeline
+    m, sd, ocfg = build(dev)
+    ids, clip_img, sam_img = inputs()
+    label = torch.zeros(70, 90)
+    forced = {3: SEG}
+    ref = pipeline.evaluate(sd, ocfg, clip_img, sam_img, ids, [(256, 256)], [tuple(label.shape)], 6, SEG,
+                            forced_tokens=forced)
+    ref_new = ref["output_ids"][0, ids.shape[1]:]
+    # feed the oracle's tokens so both sides follow the same trajectory; compare per-step logits and argmax
+    force_all = {i: int(t) for i, t in enumerate(ref_new)}
+    gen = m.generate(input_ids=ids.to(dev), images=clip_img.to(dev), max_new_tokens=6, output_hidden_states=True,
+                     return_dict_in_generate=True, output_scores=True, forced_tokens=force_all, eos_token_id=-1)
+    assert torch.equal(gen.sequences.cpu(), ref["output_ids"])
+    _check(gen.last_hidden_state, ref["hidden"], 6e-2, "hidden states")
+    for s, (got, want) in enumerate(zip(gen.scores, ref["step_logits"])):
+        _check(got, want, 6e-2, f"step {s} logits")
+        top2 = want[0].topk(2).values
+        if s not in forced and (top2[0] - top2[1]) > 6e-2 * want.abs().max():
+            assert int(got[0].argmax()) == int(want[0].argmax()), f"argmax at step {s}"
+    out_ids, masks = m.evaluate(clip_img.to(dev), sam_img.to(dev), ids.to(dev), [(256, 256)], [label],
+                                max_new_tokens=6, forced_tokens=force_all)
+    assert torch.equal(out_ids.cpu(), ref["output_ids"])
+    assert masks[0].shape == (1, 70, 90)
+    _check(masks[0], ref["pred_masks"][0], 8e-2, "mask logits")
+    thr = math.log(0.1 / 0.9)
+    want = ref["pred_masks"][0].float()
+    far = (want - thr).abs() > 8e-2 * want.abs().max()
+    assert far.float().mean() > 0.5
+    assert torch.equal((masks[0].float().cpu() > thr)[far], (want > thr)[far]), "mask indices"
+
+
+def test_grounding_forward_matches_oracle(dev):
+    from oracle import pipeline
+    m, sd, ocfg = build(dev)
+    ids, clip_img, sam_img = inputs(seg_in_prompt=True)
+    label = torch.zeros(336, 336)
+    ref = pipeline.grounding_forward(sd, ocfg, clip_img, sam_img, ids, [(256, 256)], [(336, 336)], SEG)
+    out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=None,
+            labels=None, attention_mask=torch.ones_like(ids, dtype=torch.bool).to(dev), offset=None,
+            masks_list=[label], label_list=[label], resize_list=[(256, 256)], inference=True)
+    assert set(out) == {"pred_masks", "gt_masks"}
+    _check(out["pred_masks"][0], ref["pred_masks"][0], 8e-2, "mask logits")
+
+
+def test_gate_hooks_and_lm_forward(dev):
+    """vqa_infer.py:157-165: forward hooks on the `wg` Linears observe the router logits."""
+    m, sd, ocfg = build(dev)
+    ids, clip_img, _ = inputs()
+    seen = []
+    for n, mod in m.named_modules():
+        if "wg" in n and isinstance(mod, torch.nn.Linear):
+            mod.register_forward_hook(lambda mod_, i, o: seen.append(o.detach().cpu()))
+    out = m(input_ids=ids.to(dev), images=clip_img.to(dev), past_key_values=None, use_cache=True,
+            attention_mask=torch.ones_like(ids, dtype=torch.bool).to(dev))
+    T = ids.shape[1] - 1 + 16
+    assert out.logits.shape == (1, T, 300) and out.logits.dtype == torch.float32
+    assert len(seen) == 2 and seen[0].shape == (T, 2)
+    assert out.past_key_values.len == T
+    nxt = out.logits[:, -1].argmax(-1, keepdim=True)
+    out2 = m(input_ids=nxt, images=clip_img.to(dev), past_key_values=out.past_key_values, use_cache=True,
+             attention_mask=torch.ones((1, T + 1), dtype=torch.bool, device=dev))
+    assert out2.logits.shape == (1, 1, 300) and out2.past_key_values.len == T + 1
+
+
+def test_cpu_tensors_fail_loudly(dev):
+    from medplib_b200 import ops, _lib
+    with pytest.raises(_lib.MplError):
+        ops.linear(torch.zeros(4, 8, dtype=bf16), torch.zeros(8, 8, dtype=bf16))
