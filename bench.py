@@ -162,6 +162,15 @@ def run_ours(args, rank, world, dev):
             ms = float(t.item())
         return ms, launches
 
+    if args.ncu:
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     for _ in range(max(args.warmup, 3)):
         step_resident()
         step_e2e()
@@ -297,6 +306,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--small", action="store_true", help="2-layer toy LLaMA (plumbing check, not a benchmark)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--ncu", action="store_true",
+                    help="profiling aid: warm up, then run ONE step between cudaProfilerStart/Stop (use with "
+                         "ncu --profile-from-start off); prints no bench line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
