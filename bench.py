@@ -220,6 +220,91 @@ def run_ours(args, rank, world, dev):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------- VQA decode (configs[2])
+def run_decode(args, rank, world, dev):
+    """Secondary workload: MedPLIB-7B VQA autoregressive decode, bf16, batch B (default 8), prompt T=615 (40 text ids
+    + one 576-token image), `--new-tokens` greedy tokens with EOS disabled. HBM-bound: the roofline is the algorithmic
+    bytes of a decode step (active weights once + the KV cache of every sequence) / measured copy bandwidth."""
+    from medplib_b200 import _lib
+    lib = _lib.load()
+    torch.cuda.set_device(dev)
+    m = build_model(dev, small=args.small)
+    B, new = args.batch, args.new_tokens
+    images_clip, _, ids = make_inputs()
+    d_clip = images_clip.to(dev).to(bf16).expand(B, -1, -1, -1).contiguous()
+    d_ids = ids.to(dev).expand(B, -1).contiguous()
+    h_clip, h_ids = images_clip.expand(B, -1, -1, -1).contiguous().pin_memory(), ids.expand(B, -1).contiguous().pin_memory()
+
+    def gen(n, e2e=False):
+        if e2e:
+            c, t = h_clip.to(dev, non_blocking=True).to(bf16), h_ids.to(dev, non_blocking=True)
+            return m.generate(input_ids=t, images=c, max_new_tokens=n, do_sample=False).cpu()
+        return m.generate(input_ids=d_ids, images=d_clip, max_new_tokens=n, do_sample=False)
+
+    def timed(fn, reps):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.mpl_launch_count()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / reps, (lib.mpl_launch_count() - n0) // reps
+
+    for _ in range(max(args.warmup, 3)):
+        gen(8)
+    if args.ncu:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        gen(4)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    gen(8, e2e=True)
+    clocks = ClockSampler(dev.index or 0)
+    clocks.start()
+    ms_full, launches = timed(lambda: gen(new), args.steps)
+    ck = clocks.stop()
+    ms_pre, _ = timed(lambda: gen(1), max(args.steps, 3))
+    ms_e2e, _ = timed(lambda: gen(new, e2e=True), args.steps)
+    if rank != 0:
+        return
+    d = DIMS if not args.small else dict(D=512, F=1024, L=2, H=4, V=32267, E=2)
+    step_ms = (ms_full - ms_pre) / max(new - 1, 1)
+    T = N_TEXT - 1 + 576
+    experts_hit = min(B, d["E"])
+    w_bytes = d["L"] * (4 * d["D"] ** 2 + experts_hit * 3 * d["D"] * d["F"]) * 2 + d["V"] * d["D"] * 2
+    kv_bytes = 2 * d["L"] * d["D"] * 2 * (T + new / 2.0) * B
+    pk = peaks()
+    ach = (w_bytes + kv_bytes) / (step_ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "VQA-decode tokens/sec at 7B (MedPLIB-7B-2e, bf16)", "value": world * B * new / (ms_full * 1e-3),
+        "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_full,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"MedPLIB-7B VQA autoregressive decode bf16, batch {B}, prompt T={T} (40 ids + 576 image "
+                               f"tokens), {new} new tokens greedy, EOS disabled; generate() incl. CLIP + prefill",
+                   "weights": "random init, 11.07 B params", "parallelism": f"replicas x{world}",
+                   "l2": "every decode step streams >= 13 GB of weights (>> 126 MB L2)", "small": bool(args.small)},
+        "e2e": {"value": world * B * new / (ms_e2e * 1e-3), "unit": "tokens/s",
+                "h2d_bytes_per_step": h_clip.numel() * 4 + h_ids.numel() * 8, "d2h_bytes_per_step": B * (N_TEXT + new) * 8},
+        "gpu_launches": int(launches), "clocks": ck,
+        "decode_step_ms": step_ms, "prefill_ms": ms_pre, "decode_tokens_per_s": world * B / (step_ms * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                     "traffic": None, "kernel": "decode step (streaming GEMMs + KV-cache attention): algorithmic bytes = "
+                     f"active weights {w_bytes / 1e9:.2f} GB + mean KV {kv_bytes / 1e9:.2f} GB per step / step time",
+                     "peak_source": pk["src"] + " copy bandwidth"}}), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------- reference arm (CPU)
 def cpu_reference(sample_steps=1):
     """The reference's path on the host cores: oracle port (fp32, all threads) on a bounded sample — ONE decoder layer,
@@ -304,6 +389,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="grounding", choices=["grounding", "decode"])
+    ap.add_argument("--batch", type=int, default=8, help="decode workload: sequences per GPU")
+    ap.add_argument("--new-tokens", type=int, default=512, help="decode workload: generated tokens per sequence")
     ap.add_argument("--small", action="store_true", help="2-layer toy LLaMA (plumbing check, not a benchmark)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--ncu", action="store_true",
@@ -323,7 +411,10 @@ def main():
         torch.cuda.set_device(dev)
         torch.distributed.init_process_group("nccl", device_id=dev)
     args.cpu_baseline = args.cpu_baseline and rank == 0 and world == 1
-    run_ours(args, rank, world, dev)
+    if args.workload == "decode":
+        run_decode(args, rank, world, dev)
+    else:
+        run_ours(args, rank, world, dev)
     if world > 1:
         torch.distributed.destroy_process_group()
 

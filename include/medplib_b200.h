@@ -33,6 +33,7 @@ enum {
 
 enum { MPL_ACT_NONE = 0, MPL_ACT_GELU = 1, MPL_ACT_QUICK_GELU = 2, MPL_ACT_RELU = 3, MPL_ACT_SILU = 4, MPL_ACT_SIGMOID = 5 };
 enum { MPL_DT_BF16 = 0, MPL_DT_F32 = 1 };
+#define MPL_MAX_EXPERTS 8
 
 /* Library / device probe. Returns the ABI version; fills sm count and compute capability when non-null. */
 int mpl_version(void);
@@ -73,6 +74,8 @@ typedef struct {
   int act;       /* MPL_ACT_* */
   int out_dtype; /* MPL_DT_* */
   int tile_n;    /* 0 = auto, else 128, 192 or 256 */
+  const void* ln_weight; /* streaming (M <= 16) path only: fused LlamaRMSNorm prologue on A, bf16 [K] or NULL */
+  float ln_eps;
 } mpl_gemm_args;
 int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream);
 /* In-situ timing of the tcgen05 GEMM launches (bench.py roofline): enable, run, then read the summed CUDA-event
@@ -85,6 +88,33 @@ int mpl_profile_gemm_read(float* total_ms, int* launches);
  * mpl_linear_bf16 dispatches on M (<= 16 -> skinny, else tcgen05). */
 int mpl_skinny_gemm_bf16(const mpl_gemm_args* args, void* stream);
 int mpl_linear_bf16(const mpl_gemm_args* args, void* stream);
+
+/* The experts of one MoE layer in ONE launch: group g multiplies rows [g*a_group_stride/lda ...) of A — the expert
+ * buffer written by mpl_moe_dispatch / mpl_moe_route_small — by B[g] (and B2[g]: fused SiLU(gate)*up), with the row
+ * count of every group read on the device (m_dev[g]; an expert without tokens costs nothing). row_map/row_gate (M <= 16
+ * only): instead of writing group-major rows, scatter row m of group g to output row row_map[g*map_group_stride+m]
+ * scaled by bf16(row_gate[..]) and add residual there — the DeepSpeed combine (einsum 'sec,ecm->sm') fused into the
+ * down projection. */
+typedef struct {
+  const void* A;
+  long long lda, a_group_stride;
+  const void* B[MPL_MAX_EXPERTS];
+  const void* B2[MPL_MAX_EXPERTS];
+  long long ldb;
+  void* C;
+  long long ldc, c_group_stride;
+  const void* residual;
+  long long ldr;
+  const int* m_dev;
+  const int* a_row_map; /* M <= 16 only: A row m of group g = A[a_row_map[g*map_group_stride+m]] (fused MoE dispatch) */
+  const int* row_map;
+  const float* row_gate;
+  long long map_group_stride;
+  int groups, M, N, K, act, out_dtype;
+  int m_dev_stable; /* 1: m_dev was already final before the PREVIOUS launch on this stream began, so the weight
+                       stream may start before the dependency wait (programmatic dependent launch) */
+} mpl_grouped_gemm_args;
+int mpl_grouped_gemm_bf16(const mpl_grouped_gemm_args* args, void* stream);
 
 /* K5  LlamaRMSNorm (transformers 4.31 semantics; used at
  * model/medplib/model/language_model/medplib_moe_llama.py:123,139,286): y = w * bf16(x * rsqrt(mean(x^2)+eps)). */
@@ -123,6 +153,9 @@ typedef struct {
   const float* rel_w;           /* [B*H,Tq,rel_kw] */
   int rel_kh, rel_kw;
   const int* tk_dev;
+  void* scratch;             /* decode only, optional: zero-initialised once, >= B*H*4 + B*H*nsplit*520 bytes; enables
+                                split-K over the keys (flash-decoding) so B*H < #SM still fills the GPU */
+  long long scratch_bytes;
 } mpl_attn_args;
 int mpl_attention(const mpl_attn_args* args, void* stream);
 
@@ -154,6 +187,12 @@ typedef struct {
   float* l_aux;    /* [1] out */
 } mpl_moe_route_args;
 int mpl_moe_route(const mpl_moe_route_args* args, void* stream);
+/* Decode-time variant for S <= 64 tokens, ONE launch: h = RMSNorm(x) (ln_weight may be NULL: x is already normalised),
+ * route, assign slots, copy the rows into xperm; also writes slot -> token (tok_of_slot) and per-slot gate values for
+ * mpl_grouped_gemm_bf16's fused combine. Not for k = 1 with RTS noise (training). */
+int mpl_moe_route_small(const mpl_moe_route_args* args, const void* x, long long ldx, const void* ln_weight,
+                        float ln_eps, void* h, long long ldh, void* xperm, int* tok_of_slot, float* gate_of_slot,
+                        void* stream);
 int mpl_moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D, void* stream);
 int mpl_moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
                     long long ldo, int S, int k, int D, void* stream);
@@ -211,8 +250,6 @@ int mpl_region_sample_mean(const void* fmap, const float* pts, int P, int h, int
  * retained); arrays of per-layer structs are HOST arrays. workspace is caller-owned device scratch of at least
  * mpl_*_workspace_bytes(). All activations bf16 row-major (token-major).
  * ========================================================================================================= */
-#define MPL_MAX_EXPERTS 8
-
 /* LLaMA decoder layer (HF 4.31 LlamaDecoderLayer as patched by MoELlamaDecoderLayer_forward,
  * model/medplib/model/language_model/medplib_moe_llama.py:110-162). wg == NULL: dense LlamaMLP from expert slot 0. */
 typedef struct {
@@ -255,6 +292,8 @@ typedef struct {
   long long kv_mask_stride;
   const int* pos_dev; /* NULL, or device int overriding past_len (T == 1 decode under CUDA graphs) */
   const int* tk_dev;  /* NULL, or device int = *pos_dev + 1 */
+  void* attn_scratch; /* optional zero-initialised scratch for split-K decode attention (see mpl_attn_args.scratch) */
+  long long attn_scratch_bytes;
   const float* const* moe_noise; /* NULL or host array [n_layers] of f32 [B*T,E] (see mpl_moe_route) */
   float* gate_logits;            /* NULL or f32 [n_layers, B*T, E] out (what a forward hook on wg observes) */
   float* l_aux;                  /* NULL or f32 [n_layers] out */

@@ -28,6 +28,20 @@ class GemmArgs(ctypes.Structure):
         ("row_scale", c_void_p), ("m_dev", c_void_p),
         ("M", c_int), ("N", c_int), ("K", c_int),
         ("nb", c_int), ("act", c_int), ("out_dtype", c_int), ("tile_n", c_int),
+        ("ln_weight", c_void_p), ("ln_eps", c_float),
+    ]
+
+
+class GroupedGemmArgs(ctypes.Structure):
+    """mpl_grouped_gemm_args (include/medplib_b200.h)."""
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_ll), ("a_group_stride", c_ll),
+        ("B", c_void_p * 8), ("B2", c_void_p * 8), ("ldb", c_ll),
+        ("C", c_void_p), ("ldc", c_ll), ("c_group_stride", c_ll),
+        ("residual", c_void_p), ("ldr", c_ll), ("m_dev", c_void_p), ("a_row_map", c_void_p),
+        ("row_map", c_void_p), ("row_gate", c_void_p), ("map_group_stride", c_ll),
+        ("groups", c_int), ("M", c_int), ("N", c_int), ("K", c_int), ("act", c_int), ("out_dtype", c_int),
+        ("m_dev_stable", c_int),
     ]
 
 
@@ -39,7 +53,7 @@ class AttnArgs(ctypes.Structure):
         ("B", c_int), ("H", c_int), ("Tq", c_int), ("Tk", c_int), ("head_dim", c_int),
         ("scale", c_float), ("causal", c_int),
         ("kv_mask", c_void_p), ("kv_mask_stride", c_ll), ("rel_h", c_void_p), ("rel_w", c_void_p),
-        ("rel_kh", c_int), ("rel_kw", c_int), ("tk_dev", c_void_p),
+        ("rel_kh", c_int), ("rel_kw", c_int), ("tk_dev", c_void_p), ("scratch", c_void_p), ("scratch_bytes", c_ll),
     ]
 
 
@@ -82,6 +96,7 @@ class LlamaIO(ctypes.Structure):
         ("B", c_int), ("T", c_int), ("past_len", c_int),
         ("k_cache", c_void_p), ("v_cache", c_void_p), ("Tmax", c_int),
         ("kv_mask", c_void_p), ("kv_mask_stride", c_ll), ("pos_dev", c_void_p), ("tk_dev", c_void_p),
+        ("attn_scratch", c_void_p), ("attn_scratch_bytes", c_ll),
         ("moe_noise", ctypes.POINTER(c_void_p)), ("gate_logits", c_void_p), ("l_aux", c_void_p),
         ("exp_counts", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_ll),
     ]
@@ -152,7 +167,7 @@ class SamMaskDecoder(ctypes.Structure):
 
 # Every symbol include/medplib_b200.h declares; tests/test_abi.py checks the built library exports all of them.
 EXPORTS = [
-    "mpl_version", "mpl_device_info", "mpl_launch_count", "mpl_gemm_bf16", "mpl_profile_gemm", "mpl_profile_gemm_read", "mpl_skinny_gemm_bf16", "mpl_linear_bf16",
+    "mpl_version", "mpl_device_info", "mpl_launch_count", "mpl_gemm_bf16", "mpl_profile_gemm", "mpl_profile_gemm_read", "mpl_skinny_gemm_bf16", "mpl_linear_bf16", "mpl_grouped_gemm_bf16", "mpl_moe_route_small",
     "mpl_rmsnorm", "mpl_layernorm", "mpl_pool_layernorm", "mpl_attention",
     "mpl_moe_route", "mpl_moe_dispatch", "mpl_moe_combine", "mpl_rope_kv", "mpl_gather_rows", "mpl_argmax_f32",
     "mpl_im2col_patch", "mpl_im2col_nhwc", "mpl_clip_embed", "mpl_sam_relpos", "mpl_col_mean",

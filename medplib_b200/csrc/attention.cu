@@ -36,6 +36,8 @@ struct AttnParams {
   const float* rel_w;            // [B*H, Tq, rel_kw]
   int rel_kh, rel_kw;
   const int* tk_dev;             // optional device-side Tk (decode under CUDA graphs)
+  float* scratch;                // decode split-K partials: [B*H] int counters (zeroed) then [B*H, nsplit, D+2] floats
+  int nsplit;
 };
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -253,9 +255,15 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(const AttnP
   __shared__ float s_o[DEC_WARPS][D];
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   const int b = blockIdx.y, h = blockIdx.x;
+  griddep_launch_dependents();  // the o_proj streaming GEMM may start prefetching its weights
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, gl = lane & 7;  // 4 keys per warp step, 8 lanes x 16 dims per key
   const int Tk = p.tk_dev ? *p.tk_dev : p.Tk;
+  // split-K over the keys (flash-decoding): blockIdx.z owns keys [k_lo, k_hi), a multiple of 32 keys per split
+  const int nsplit = gridDim.z;
+  const int per = ((Tk + nsplit - 1) / nsplit + 31) & ~31;
+  const int k_lo = blockIdx.z * per;
+  const int k_hi = min(Tk, k_lo + per);
   const __nv_bfloat16* qg = p.q + b * p.q_sb + h * p.q_sh + gl * 16;
   const __nv_bfloat16* kg = p.k + b * p.k_sb + h * p.k_sh + gl * 16;
   const __nv_bfloat16* vg = p.v + b * p.v_sb + h * p.v_sh + gl * 16;
@@ -281,9 +289,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(const AttnP
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
   // The trip count is warp-uniform (full-mask shuffles inside): groups past the end compute a masked dummy key.
-  for (int k0 = warp * 4; k0 < Tk; k0 += DEC_WARPS * 4) {
+  for (int k0 = k_lo + warp * 4; k0 < k_hi; k0 += DEC_WARPS * 4) {
     const int key = k0 + grp;
-    const bool valid = key < Tk;
+    const bool valid = key < k_hi;
     const int kk = valid ? key : Tk - 1;
     const __nv_bfloat16* kr = kg + static_cast<long long>(kk) * p.k_st;
     const __nv_bfloat16* vr = vg + static_cast<long long>(kk) * p.v_st;
@@ -346,19 +354,54 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(const AttnP
     }
   }
   __syncthreads();
+  __shared__ int s_last;
+  float mm = -INFINITY, lt = 0.0f, ot = 0.0f;
   if (threadIdx.x < D) {
-    float mm = -INFINITY;
 #pragma unroll
     for (int w = 0; w < DEC_WARPS; ++w) mm = fmaxf(mm, s_m[w]);
     const float msafe = (mm == -INFINITY) ? 0.0f : mm;
-    float lt = 0.0f, ot = 0.0f;
 #pragma unroll
     for (int w = 0; w < DEC_WARPS; ++w) {
       const float c = exp2f(s_m[w] - msafe);
       lt += s_l[w] * c;
       ot += s_o[w][threadIdx.x] * c;
     }
-    p.o[b * p.o_sb + h * p.o_sh + threadIdx.x] = __float2bfloat16_rn(lt > 0.0f ? ot / lt : 0.0f);
+  }
+  __nv_bfloat16* optr = p.o + b * p.o_sb + h * p.o_sh;
+  if (nsplit == 1) {
+    if (threadIdx.x < D) optr[threadIdx.x] = __float2bfloat16_rn(lt > 0.0f ? ot / lt : 0.0f);
+    return;
+  }
+  // publish this split's (max, sum, acc); the last CTA to arrive for (b,h) merges all splits
+  const int bh = b * gridDim.x + h;
+  int* counters = reinterpret_cast<int*>(p.scratch);
+  float* part = p.scratch + gridDim.x * gridDim.y + static_cast<long long>(bh) * nsplit * (D + 2);
+  if (threadIdx.x < D) {
+    float* mine = part + blockIdx.z * (D + 2);
+    mine[threadIdx.x] = ot;
+    if (threadIdx.x == 0) {
+      mine[D] = mm;
+      mine[D + 1] = lt;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&counters[bh], 1) == nsplit - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < D) {
+    float gm = -INFINITY;
+    for (int z = 0; z < nsplit; ++z) gm = fmaxf(gm, __ldcg(part + z * (D + 2) + D));
+    const float gsafe = (gm == -INFINITY) ? 0.0f : gm;
+    float gl_ = 0.0f, go = 0.0f;
+    for (int z = 0; z < nsplit; ++z) {
+      const float c = exp2f(__ldcg(part + z * (D + 2) + D) - gsafe);
+      gl_ += __ldcg(part + z * (D + 2) + D + 1) * c;
+      go += __ldcg(part + z * (D + 2) + threadIdx.x) * c;
+    }
+    optr[threadIdx.x] = __float2bfloat16_rn(gl_ > 0.0f ? go / gl_ : 0.0f);
+    if (threadIdx.x == 0) counters[bh] = 0;  // self-cleaning for the next launch
   }
 }
 
@@ -404,7 +447,20 @@ extern "C" int mpl_attention(const mpl_attn_args* a, void* stream_) {
   for (long long s : strides)
     if (s % 8 != 0) return MPL_ERR_ALIGN;
   if (a->Tq == 1 && a->head_dim == 128 && a->rel_h == nullptr) {
-    dim3 grid(p.H, p.B);
+    int nsplit = 1;
+    if (a->scratch != nullptr) {
+      const int bh = p.B * p.H;
+      nsplit = (2 * num_sms() + bh - 1) / bh;
+      const int by_keys = (p.Tk + 63) / 64;  // at least 64 keys per split
+      if (nsplit > by_keys) nsplit = by_keys;
+      if (nsplit > 32) nsplit = 32;
+      while (nsplit > 1 && static_cast<long long>(bh) * 4 + static_cast<long long>(bh) * nsplit * 130 * 4 > a->scratch_bytes)
+        --nsplit;
+      if (nsplit < 1) nsplit = 1;
+    }
+    p.scratch = static_cast<float*>(a->scratch);
+    p.nsplit = nsplit;
+    dim3 grid(p.H, p.B, nsplit);
     decode_attn_kernel<128><<<grid, DEC_WARPS * 32, 0, stream>>>(p);
     return mpl::launch_status();
   }

@@ -353,6 +353,30 @@ static int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long lon
   return r == CUDA_SUCCESS ? MPL_OK : MPL_ERR_DRIVER;
 }
 
+// Generic bf16 tensor-map encoder shared with the streaming GEMM (128-B swizzle, 256-B L2 promotion, zero OOB fill).
+// strides_bytes has rank-1 entries (dimension 0 is contiguous).
+int encode_tmap_bf16(void* out, const void* ptr, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return MPL_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return MPL_ERR_ALIGN;
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) {
+      st[i] = strides_bytes[i];
+      if (st[i] & 15) return MPL_ERR_ALIGN;
+    }
+  }
+  CUresult r = fn(static_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, st,
+                  b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MPL_OK : MPL_ERR_DRIVER;
+}
+
 // Optional in-situ timing of every tcgen05 GEMM launch (bench.py roofline): CUDA events recorded on the launching
 // stream around each launch, summed by mpl_profile_gemm_read after a synchronise.
 static bool g_prof = false;
@@ -458,6 +482,35 @@ int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
   if (c256 <= c192 && c256 <= c128) return launch_gemm<256>(a, stream);
   if (c192 <= c128) return launch_gemm<192>(a, stream);
   return launch_gemm<128>(a, stream);
+}
+
+// Grouped (per-expert) GEMM for M > 16: one tcgen05 launch per group for now (device-side row counts via m_dev).
+int grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
+  if (a.row_map != nullptr || a.a_row_map != nullptr) return MPL_ERR_UNSUPPORTED;
+  const long long csz = a.out_dtype == MPL_DT_F32 ? 4 : 2;
+  for (int g = 0; g < a.groups; ++g) {
+    mpl_gemm_args x;
+    memset(&x, 0, sizeof(x));
+    x.A = static_cast<const char*>(a.A) + static_cast<long long>(g) * a.a_group_stride * 2;
+    x.lda = a.lda;
+    x.B[0] = a.B[g];
+    x.B2 = a.B2[g];
+    x.ldb = a.ldb;
+    x.C[0] = static_cast<char*>(a.C) + static_cast<long long>(g) * a.c_group_stride * csz;
+    x.ldc = a.ldc;
+    x.residual = a.residual;
+    x.ldr = a.ldr;
+    x.m_dev = a.m_dev ? a.m_dev + g : nullptr;
+    x.M = a.M;
+    x.N = a.N;
+    x.K = a.K;
+    x.nb = 1;
+    x.act = a.act;
+    x.out_dtype = a.out_dtype;
+    const int rc = gemm_bf16(x, stream);
+    if (rc != MPL_OK) return rc;
+  }
+  return MPL_OK;
 }
 
 }  // namespace mpl

@@ -12,9 +12,15 @@ inline int launch_status(int n = 1) {
   return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
 }
 int num_sms();
+int encode_tmap_bf16(void* out, const void* ptr, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box);
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream);
 int skinny_gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream);
 int linear_bf16(const mpl_gemm_args& a, cudaStream_t stream);
+int grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream);
+int skinny_grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream);
+int moe_route_small(const mpl_moe_route_args& a, const void* x, long long ldx, const void* ln_w, float eps, void* h,
+                    long long ldh, void* xperm, int* tok_of_slot, float* gate_of_slot, cudaStream_t stream);
 int moe_route(const mpl_moe_route_args& a, cudaStream_t stream);
 int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D, cudaStream_t stream);
 int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,

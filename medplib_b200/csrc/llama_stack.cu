@@ -33,6 +33,8 @@ struct LlamaWs {
   int* kept;
   int* exp_counts;
   float* l_aux;
+  int* tok_of_slot;
+  float* gate_of_slot;
   long long total;
 };
 
@@ -81,6 +83,8 @@ static LlamaWs carve(const mpl_llama_model& m, int B, int T, char* base) {
   w.kept = reinterpret_cast<int*>(take(MPL_MAX_EXPERTS * 4));
   w.exp_counts = reinterpret_cast<int*>(take(MPL_MAX_EXPERTS * 4));
   w.l_aux = reinterpret_cast<float*>(take(256));
+  w.tok_of_slot = reinterpret_cast<int*>(take(erows * 4));
+  w.gate_of_slot = reinterpret_cast<float*>(take(erows * 4));
   w.total = off;
   return w;
 }
@@ -128,10 +132,15 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
       if (cudaMemcpyAsync(io.hidden_states[l], io.x, static_cast<size_t>(S) * D * 2, cudaMemcpyDeviceToDevice, st) !=
           cudaSuccess)
         return MPL_ERR_CUDA;
-    // ---- attention block
-    MPL_TRY(mpl_rmsnorm(io.x, D, L.input_ln, w.h, D, S, D, m.rms_eps, st_));
+    // ---- attention block (decode: the RMSNorm runs as the prologue of the streaming q,k,v GEMM)
+    const bool small = S <= 16;
+    if (!small) MPL_TRY(mpl_rmsnorm(io.x, D, L.input_ln, w.h, D, S, D, m.rms_eps, st_));
     {
-      mpl_gemm_args g = gemm_base(w.h, D, S, D, D);
+      mpl_gemm_args g = gemm_base(small ? io.x : w.h, D, S, D, D);
+      if (small) {
+        g.ln_weight = L.input_ln;
+        g.ln_eps = m.rms_eps;
+      }
       g.nb = 3;
       g.B[0] = L.wq;
       g.B[1] = L.wk;
@@ -172,6 +181,8 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
       a.kv_mask = io.kv_mask;
       a.kv_mask_stride = io.kv_mask_stride;
       a.tk_dev = io.tk_dev;
+      a.scratch = io.attn_scratch;
+      a.scratch_bytes = io.attn_scratch_bytes;
       MPL_TRY(mpl_attention(&a, st_));
     }
     {
@@ -183,9 +194,13 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
       MPL_TRY(linear_bf16(g, st));
     }
     // ---- FFN block
-    MPL_TRY(mpl_rmsnorm(io.x, D, L.post_ln, w.h, D, S, D, m.rms_eps, st_));
     if (L.wg == nullptr) {
-      mpl_gemm_args g = gemm_base(w.h, D, S, F, D);
+      if (!small) MPL_TRY(mpl_rmsnorm(io.x, D, L.post_ln, w.h, D, S, D, m.rms_eps, st_));
+      mpl_gemm_args g = gemm_base(small ? io.x : w.h, D, S, F, D);
+      if (small) {
+        g.ln_weight = L.post_ln;
+        g.ln_eps = m.rms_eps;
+      }
       g.B[0] = L.w_gate[0];
       g.B2 = L.w_up[0];
       g.C[0] = w.h1;
@@ -219,24 +234,73 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
     r.kept = w.kept;
     r.exp_counts = io.exp_counts ? io.exp_counts + static_cast<long long>(l) * E : w.exp_counts;
     r.l_aux = io.l_aux ? io.l_aux + l : w.l_aux;
-    MPL_TRY(moe_route(r, st));
-    MPL_TRY(moe_dispatch(w.h, D, w.slot, w.xperm, S, m.top_k, D, st));
-    for (int e = 0; e < E; ++e) {
-      const char* xe = w.xperm + static_cast<long long>(e) * C * D * 2;
-      char* h1e = w.h1 + static_cast<long long>(e) * C * F * 2;
-      char* ye = w.y + static_cast<long long>(e) * C * D * 2;
-      mpl_gemm_args g = gemm_base(xe, D, C, F, D);
-      g.B[0] = L.w_gate[e];
-      g.B2 = L.w_up[e];
-      g.C[0] = h1e;
-      g.m_dev = w.kept + e;
-      MPL_TRY(linear_bf16(g, st));
-      mpl_gemm_args d = gemm_base(h1e, F, C, D, F);
-      d.B[0] = L.w_down[e];
-      d.C[0] = ye;
-      d.m_dev = w.kept + e;
-      MPL_TRY(linear_bf16(d, st));
+    const bool fused_front = small && !(m.top_k == 1 && r.noise != nullptr);
+    const bool gather = fused_front && C <= 16;  // streaming expert GEMMs read their rows through tok_of_slot
+    if (fused_front) {
+      // one launch: RMSNorm + router + slots (+ slot->token map for the fused dispatch / combine)
+      MPL_TRY(moe_route_small(r, io.x, D, L.post_ln, m.rms_eps, w.h, D, gather ? nullptr : w.xperm, w.tok_of_slot,
+                              w.gate_of_slot, st));
+    } else {
+      MPL_TRY(mpl_rmsnorm(io.x, D, L.post_ln, w.h, D, S, D, m.rms_eps, st_));
+      MPL_TRY(moe_route(r, st));
+      MPL_TRY(moe_dispatch(w.h, D, w.slot, w.xperm, S, m.top_k, D, st));
     }
+    const bool fused_combine = fused_front && m.top_k == 1 && C <= 16;
+    {
+      mpl_grouped_gemm_args g;
+      memset(&g, 0, sizeof(g));
+      g.A = gather ? w.h : w.xperm;
+      g.lda = D;
+      g.a_group_stride = static_cast<long long>(C) * D;
+      if (gather) {
+        g.a_row_map = w.tok_of_slot;
+        g.map_group_stride = C;
+      }
+      for (int e = 0; e < E; ++e) {
+        g.B[e] = L.w_gate[e];
+        g.B2[e] = L.w_up[e];
+      }
+      g.ldb = D;
+      g.C = w.h1;
+      g.ldc = F;
+      g.c_group_stride = static_cast<long long>(C) * F;
+      g.m_dev = w.kept;
+      g.groups = E;
+      g.M = C;
+      g.N = F;
+      g.K = D;
+      g.out_dtype = MPL_DT_BF16;
+      MPL_TRY(mpl_grouped_gemm_bf16(&g, st_));
+      mpl_grouped_gemm_args d;
+      memset(&d, 0, sizeof(d));
+      d.A = w.h1;
+      d.lda = F;
+      d.a_group_stride = static_cast<long long>(C) * F;
+      for (int e = 0; e < E; ++e) d.B[e] = L.w_down[e];
+      d.ldb = F;
+      d.m_dev = w.kept;
+      d.m_dev_stable = 1;  // kept[] was written two launches back (router), before the gate/up GEMM started
+      d.groups = E;
+      d.M = C;
+      d.N = D;
+      d.K = F;
+      d.out_dtype = MPL_DT_BF16;
+      if (fused_combine) {
+        d.C = io.x;
+        d.ldc = D;
+        d.residual = io.x;
+        d.ldr = D;
+        d.row_map = w.tok_of_slot;
+        d.row_gate = w.gate_of_slot;
+        d.map_group_stride = C;
+      } else {
+        d.C = w.y;
+        d.ldc = D;
+        d.c_group_stride = static_cast<long long>(C) * D;
+      }
+      MPL_TRY(mpl_grouped_gemm_bf16(&d, st_));
+    }
+    if (fused_combine) continue;
     MPL_TRY(moe_combine(w.y, w.slot, w.gate, io.x, D, io.x, D, S, m.top_k, D, st));
   }
   if (io.out_norm != nullptr) MPL_TRY(mpl_rmsnorm(io.x, D, m.final_norm, io.out_norm, D, S, D, m.rms_eps, st_));

@@ -264,32 +264,49 @@ __global__ void __launch_bounds__(256) sam_relpos_kernel(const __nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------------------------------------- column mean
-__global__ void __launch_bounds__(128) col_mean_kernel(const __nv_bfloat16* __restrict__ x,
+// block = 32 channel-chunks (8 channels each) x 8 row groups; rows strided over the groups, reduced through smem.
+__global__ void __launch_bounds__(256) col_mean_kernel(const __nv_bfloat16* __restrict__ x,
                                                        __nv_bfloat16* __restrict__ out, int T, int C) {
+  __shared__ float part[8][32][8];
   const int b = blockIdx.y;
-  const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (c >= C) return;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cx) * 8;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * C + c;
-  for (int t = 0; t < T; ++t) {
-    const uint4 a = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(t) * C);
-    const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
+  if (c < C) {
+    const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * C + c;
+    for (int t = ry; t < T; t += 8) {
+      const uint4 a = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(t) * C);
+      const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(ap[i]);
-      acc[2 * i] += f.x;
-      acc[2 * i + 1] += f.y;
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(ap[i]);
+        acc[2 * i] += f.x;
+        acc[2 * i + 1] += f.y;
+      }
     }
   }
-  const float inv = 1.0f / static_cast<float>(T);
-  uint4 o;
-  o.x = pack_bf16(acc[0] * inv, acc[1] * inv);
-  o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
-  o.z = pack_bf16(acc[4] * inv, acc[5] * inv);
-  o.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-  *reinterpret_cast<uint4*>(out + static_cast<long long>(b) * C + c) = o;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[ry][cx][i] = acc[i];
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    const float inv = 1.0f / static_cast<float>(T);
+    float tot[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v += part[r][cx][i];
+      tot[i] = v * inv;
+    }
+    uint4 o;
+    o.x = pack_bf16(tot[0], tot[1]);
+    o.y = pack_bf16(tot[2], tot[3]);
+    o.z = pack_bf16(tot[4], tot[5]);
+    o.w = pack_bf16(tot[6], tot[7]);
+    *reinterpret_cast<uint4*>(out + static_cast<long long>(b) * C + c) = o;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------- convT col2im
@@ -518,8 +535,8 @@ extern "C" int mpl_col_mean(const void* x, void* out, int B, int T, int C, void*
   if (B <= 0) return MPL_OK;
   if (x == nullptr || out == nullptr || T <= 0) return MPL_ERR_ARG;
   if ((C % 8) != 0) return MPL_ERR_ALIGN;
-  dim3 grid((C / 8 + 127) / 128, B);
-  col_mean_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(x), static_cast<bf*>(out),
+  dim3 grid((C / 8 + 31) / 32, B);
+  col_mean_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(x), static_cast<bf*>(out),
                                                                       T, C);
   return launched();
 }

@@ -289,6 +289,217 @@ __global__ void __launch_bounds__(128) moe_combine_kernel(const __nv_bfloat16* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ small-S fused path
+// Decode-time MoE front end for S <= 64 tokens in ONE CTA: [RMSNorm] -> router -> top-k -> slots -> dispatch.
+// Replaces five launches (rmsnorm, router, scan, dispatch + the host-visible bookkeeping) of the general path; also
+// emits the slot -> token map and per-slot gate values so the expert down-projection can do the combine in its
+// epilogue. Slot order = token order (torch.cumsum), like the general path. noise: only the k = 2 Gumbel term.
+constexpr int SMALL_S = 64;
+constexpr int SMALL_THREADS = 1024;
+__global__ void __launch_bounds__(SMALL_THREADS) moe_route_small_kernel(
+    const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ ln_w, float eps,
+    const float* __restrict__ wg, const float* __restrict__ noise, int S, int D, int E, int k, int C,
+    __nv_bfloat16* __restrict__ h, long long ldh, float* __restrict__ logits, float* __restrict__ gates,
+    int* __restrict__ expert, float* __restrict__ gate, int* __restrict__ slot, int* __restrict__ kept,
+    int* __restrict__ exp_counts, float* __restrict__ l_aux, __nv_bfloat16* __restrict__ xperm,
+    int* __restrict__ tok_of_slot, float* __restrict__ gate_of_slot) {
+  __shared__ float s_logit[SMALL_S][MOE_MAX_E];
+  __shared__ float s_gates[SMALL_S][MOE_MAX_E];
+  __shared__ int s_slot[SMALL_S][2];
+  __shared__ float s_part[32][MOE_MAX_E + 1];  // per-warp partials: [0] sum of squares, [1+e] router dot products
+  griddep_launch_dependents();  // the next kernel (a PDL streaming GEMM) may become resident; it waits for our results
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- phase 1: a group of `wpt` warps per token (the whole row in one or two 16-byte loads per lane when S is
+  // small): normalise, store h, router logits from the stored (rounded) values
+  int wpt = 16;
+  while (wpt > 1 && wpt * S > 32) wpt >>= 1;
+  const int per_round = 32 / wpt;
+  const int grp = warp / wpt, wig = warp % wpt;
+  const int step = wpt * 256;
+  for (int s0 = 0; s0 < S; s0 += per_round) {
+    const int s = s0 + grp;
+    const bool live = s < S && grp < per_round;
+    const __nv_bfloat16* xr = x + static_cast<long long>(live ? s : 0) * ldx;
+    __nv_bfloat16* hr = h + static_cast<long long>(live ? s : 0) * ldh;
+    float rstd = 1.0f;
+    if (ln_w != nullptr) {
+      float ss = 0.0f;
+      if (live) {
+#pragma unroll 4
+        for (int c = (wig * 32 + lane) * 8; c < D; c += step) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(xr + c);
+          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(hp[i]);
+            ss += f.x * f.x + f.y * f.y;
+          }
+        }
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) s_part[warp][0] = ss;
+      __syncthreads();
+      float tot = 0.0f;
+      for (int w = 0; w < wpt; ++w) tot += s_part[grp * wpt + w][0];
+      rstd = rsqrtf(tot / static_cast<float>(D) + eps);
+    }
+    float acc[MOE_MAX_E];
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e) acc[e] = 0.0f;
+    if (live) {
+#pragma unroll 2
+      for (int c = (wig * 32 + lane) * 8; c < D; c += step) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(xr + c);
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        float v[8];
+        if (ln_w != nullptr) {
+          const uint4 wraw = *reinterpret_cast<const uint4*>(ln_w + c);
+          const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&wraw);
+          uint4 o;
+          uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(hp[i]), wf = __bfloat1622float2(wp[i]);
+            const float a = bf16_round(wf.x * bf16_round(f.x * rstd)), b = bf16_round(wf.y * bf16_round(f.y * rstd));
+            v[2 * i] = a;
+            v[2 * i + 1] = b;
+            op[i] = pack_bf16(a, b);
+          }
+          *reinterpret_cast<uint4*>(hr + c) = o;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(hp[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+          }
+          if (hr != xr) *reinterpret_cast<uint4*>(hr + c) = raw;
+        }
+#pragma unroll
+        for (int e = 0; e < MOE_MAX_E; ++e) {
+          if (e < E) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wg + static_cast<long long>(e) * D + c);
+            const float4 w1 = *reinterpret_cast<const float4*>(wg + static_cast<long long>(e) * D + c + 4);
+            acc[e] += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y +
+                      v[6] * w1.z + v[7] * w1.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e)
+      if (e < E) acc[e] = warp_sum(acc[e]);
+    __syncthreads();  // s_part[.][0] fully consumed above
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < MOE_MAX_E; ++e)
+        if (e < E) s_part[warp][1 + e] = acc[e];
+    }
+    __syncthreads();
+    if (live && wig == 0 && lane == 0) {
+      float lg[MOE_MAX_E];
+      float m = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < MOE_MAX_E; ++e)
+        if (e < E) {
+          float t = 0.0f;
+          for (int w = 0; w < wpt; ++w) t += s_part[grp * wpt + w][1 + e];
+          lg[e] = t;
+          m = fmaxf(m, t);
+        }
+      float ex[MOE_MAX_E];
+      float sum = 0.0f;
+#pragma unroll
+      for (int e = 0; e < MOE_MAX_E; ++e)
+        if (e < E) {
+          ex[e] = expf(lg[e] - m);
+          sum += ex[e];
+        }
+#pragma unroll
+      for (int e = 0; e < MOE_MAX_E; ++e)
+        if (e < E) {
+          const float gv = ex[e] / sum;
+          s_logit[s][e] = lg[e];
+          s_gates[s][e] = gv;
+          logits[static_cast<long long>(s) * E + e] = lg[e];
+          gates[static_cast<long long>(s) * E + e] = gv;
+        }
+    }
+    __syncthreads();
+  }
+  // ---- phase 2: sequential slot assignment (S <= 64)
+  if (threadIdx.x == 0) {
+    int c1[MOE_MAX_E], c2[MOE_MAX_E];
+    float me[MOE_MAX_E];
+    for (int e = 0; e < E; ++e) c1[e] = c2[e] = 0, me[e] = 0.0f;
+    for (int s = 0; s < S; ++s) {
+      int i1 = 0;
+      float best = s_gates[s][0];
+      for (int e = 0; e < E; ++e) {
+        me[e] += s_gates[s][e];
+        if (s_gates[s][e] > best) best = s_gates[s][e], i1 = e;
+      }
+      expert[s * k] = i1;
+      s_slot[s][0] = c1[i1]++;
+      if (k == 2) {
+        int i2 = -1;
+        float b2 = -INFINITY;
+        for (int e = 0; e < E; ++e) {
+          if (e == i1) continue;
+          const float v = s_logit[s][e] + (noise ? noise[static_cast<long long>(s) * E + e] : 0.0f);
+          if (i2 < 0 || v > b2) b2 = v, i2 = e;
+        }
+        expert[s * k + 1] = i2;
+        s_slot[s][1] = c2[i2]++;
+      }
+    }
+    float aux = 0.0f;
+    for (int e = 0; e < E; ++e) {
+      exp_counts[e] = c1[e];
+      kept[e] = min(k == 2 ? c1[e] + c2[e] : c1[e], C);
+      aux += (me[e] / S) * (static_cast<float>(c1[e]) / S);
+    }
+    *l_aux = aux * E;
+    for (int s = 0; s < S; ++s) {
+      float gsel[2] = {0.0f, 0.0f};
+      int row[2] = {-1, -1};
+      for (int j = 0; j < k; ++j) {
+        const int e = expert[s * k + j];
+        int loc = s_slot[s][j] + (j == 1 ? c1[e] : 0);
+        if (loc < C) {
+          row[j] = e * C + loc;
+          gsel[j] = s_gates[s][e];
+        }
+      }
+      if (k == 2) {
+        const float denom = fmaxf(gsel[0] + gsel[1], 1.1920928955078125e-07f);
+        gsel[0] /= denom;
+        gsel[1] /= denom;
+      }
+      for (int j = 0; j < k; ++j) {
+        s_slot[s][j] = row[j];
+        slot[s * k + j] = row[j];
+        gate[s * k + j] = gsel[j];
+        if (row[j] >= 0 && tok_of_slot != nullptr) {
+          tok_of_slot[row[j]] = s;
+          gate_of_slot[row[j]] = gsel[j];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: dispatch (rows are L2-hot)
+  if (xperm == nullptr) return;  // the expert GEMM gathers its rows through tok_of_slot instead
+  for (int r = warp; r < S * k; r += SMALL_THREADS / 32) {
+    const int dst = s_slot[r / k][r % k];
+    if (dst < 0) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(h + static_cast<long long>(r / k) * ldh);
+    uint4* out = reinterpret_cast<uint4*>(xperm + static_cast<long long>(dst) * D);
+    for (int c = lane; c < D / 8; c += 32) out[c] = src[c];
+  }
+}
+
 int moe_route(const mpl_moe_route_args& a, cudaStream_t stream) {
   if (a.S <= 0) return MPL_OK;
   if (a.h == nullptr || a.wg == nullptr || a.logits == nullptr || a.gates == nullptr || a.expert == nullptr ||
@@ -324,7 +535,33 @@ int moe_combine(const void* y, const int* slot, const float* gate, const void* r
   return mpl::launch_status();
 }
 
+int moe_route_small(const mpl_moe_route_args& a, const void* x, long long ldx, const void* ln_w, float eps, void* h,
+                    long long ldh, void* xperm, int* tok_of_slot, float* gate_of_slot, cudaStream_t stream) {
+  if (a.S <= 0) return MPL_OK;
+  if (a.S > SMALL_S || (a.k == 1 && a.noise != nullptr)) return MPL_ERR_UNSUPPORTED;
+  if (x == nullptr || h == nullptr || a.wg == nullptr || a.logits == nullptr ||
+      a.gates == nullptr || a.expert == nullptr || a.gate == nullptr || a.slot == nullptr || a.kept == nullptr ||
+      a.exp_counts == nullptr || a.l_aux == nullptr)
+    return MPL_ERR_ARG;
+  if (a.E < 1 || a.E > MOE_MAX_E || a.k < 1 || a.k > 2 || a.k > a.E || a.capacity < 1) return MPL_ERR_UNSUPPORTED;
+  if ((a.D % 8) != 0 || (ldx % 8) != 0 || (ldh % 8) != 0) return MPL_ERR_ALIGN;
+  moe_route_small_kernel<<<1, SMALL_THREADS, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                               static_cast<const __nv_bfloat16*>(ln_w), eps, a.wg, a.noise, a.S, a.D,
+                                               a.E, a.k, a.capacity, static_cast<__nv_bfloat16*>(h), ldh, a.logits,
+                                               a.gates, a.expert, a.gate, a.slot, a.kept, a.exp_counts, a.l_aux,
+                                               static_cast<__nv_bfloat16*>(xperm), tok_of_slot, gate_of_slot);
+  return launch_status();
+}
+
 }  // namespace mpl
+
+extern "C" int mpl_moe_route_small(const mpl_moe_route_args* a, const void* x, long long ldx, const void* ln_weight,
+                                   float ln_eps, void* h, long long ldh, void* xperm, int* tok_of_slot,
+                                   float* gate_of_slot, void* stream) {
+  if (a == nullptr) return MPL_ERR_ARG;
+  return mpl::moe_route_small(*a, x, ldx, ln_weight, ln_eps, h, ldh, xperm, tok_of_slot, gate_of_slot,
+                              static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int mpl_moe_route(const mpl_moe_route_args* a, void* stream) {
   if (a == nullptr) return MPL_ERR_ARG;

@@ -151,6 +151,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
          | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// wait: blocks until every prerequisite grid has completed and its writes are visible (no-op without a dependency).
+// launch_dependents: lets the next kernel in the stream (launched with the programmatic-serialization attribute)
+// start its prologue -- for the streaming GEMMs: the weight prefetch -- while this grid is still running.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ int ld_cg_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -138,6 +138,7 @@ class LlamaEngine:
         self.model = m
         self.head_dim = hd
         self.E = max([layers[i].n_experts for i in range(L)])
+        self.attn_scratch = torch.zeros(4 << 20, dtype=torch.uint8, device=dev)  # split-K decode attention
 
     def new_cache(self, B, Tmax):
         c = self.cfg
@@ -190,6 +191,7 @@ class LlamaEngine:
             l_aux = torch.zeros((L,), dtype=torch.float32, device=x.device)
             exp_counts = torch.zeros((L, self.E), dtype=torch.int32, device=x.device)
             io.gate_logits, io.l_aux, io.exp_counts = gate_logits.data_ptr(), l_aux.data_ptr(), exp_counts.data_ptr()
+        io.attn_scratch, io.attn_scratch_bytes = self.attn_scratch.data_ptr(), self.attn_scratch.numel()
         io.workspace, io.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.mpl_llama_forward(ctypes.byref(self.model), ctypes.byref(io), _stream()), "mpl_llama_forward")
         if pos_dev is None:

@@ -40,7 +40,7 @@ def _rows(x):
 
 
 def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scale=None, m_dev=None,
-           out_dtype=bf16, out=None, tile_n=0, force=None):
+           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5):
     """y = epilogue(x @ weight.T); x [..., K] bf16, weight [N, K] bf16 (nn.Linear layout).
 
     weight may be a list/tuple of 1..3 same-shape matrices sharing x in one launch (returns a list of outputs).
@@ -92,6 +92,9 @@ def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scal
     a.act = _ACT[act]
     a.out_dtype = DT_F32 if outs[0].dtype == torch.float32 else DT_BF16
     a.tile_n = tile_n
+    if ln_weight is not None:  # fused LlamaRMSNorm prologue (streaming path, M <= 16)
+        _req(ln_weight, bf16, "ln_weight")
+        a.ln_weight, a.ln_eps = ln_weight.data_ptr(), ln_eps
     fn = {None: lib.mpl_linear_bf16, "tc": lib.mpl_gemm_bf16, "skinny": lib.mpl_skinny_gemm_bf16}[force]
     _lib.check(fn(ctypes.byref(a), _stream()), "mpl_linear_bf16")
     lead = x.shape[:-1]
@@ -135,7 +138,8 @@ def pool_layernorm(x, weight, bias, t_out, eps):
     return y
 
 
-def attention(q, k, v, scale, causal=False, kv_mask=None, rel_h=None, rel_w=None, tk_dev=None, out=None):
+def attention(q, k, v, scale, causal=False, kv_mask=None, rel_h=None, rel_w=None, tk_dev=None, out=None,
+              scratch=None):
     """softmax(scale * q k^T + bias + masks) v.  q [B, Tq, H, d], k/v [B, Tk, H, d] (any strides, d contiguous).
 
     Returns o [B, Tq, H, d] (contiguous unless `out` is given). rel_h/rel_w: f32 [B*H, Tq, kh] / [B*H, Tq, kw].
@@ -165,6 +169,8 @@ def attention(q, k, v, scale, causal=False, kv_mask=None, rel_h=None, rel_w=None
     if tk_dev is not None:
         _req(tk_dev, torch.int32, "tk_dev")
         a.tk_dev = tk_dev.data_ptr()
+    if scratch is not None:  # zero-initialised uint8/float buffer: split-K decode
+        a.scratch, a.scratch_bytes = scratch.data_ptr(), scratch.numel() * scratch.element_size()
     _lib.check(lib.mpl_attention(ctypes.byref(a), _stream()), "mpl_attention")
     return o
 
@@ -363,4 +369,71 @@ def region_sample_mean(fmap, pts, h, w):
     out = torch.empty((C,), dtype=bf16, device=fmap.device)
     _lib.check(lib.mpl_region_sample_mean(_ptr(fmap), _ptr(pts), pts.shape[0], h, w, C, _ptr(out), _stream()),
                "mpl_region_sample_mean")
+    return out
+
+
+def grouped_linear(xperm, weights, m_dev, rows_per_group, weights2=None, out=None, row_map=None, row_gate=None,
+                   residual=None, a_row_map=None):
+    """Per-expert linears in one launch (mpl_grouped_gemm_bf16). xperm bf16 [G*rows_per_group, K]; weights: list of
+    G [N,K]; m_dev int32 [G]. With row_map/row_gate (+residual): fused MoE combine into `out` [S, N] (token rows).
+    With a_row_map (slot -> token): `xperm` is the un-dispatched [S, K] token matrix (fused MoE dispatch)."""
+    lib = _lib.load()
+    G = len(weights)
+    K = xperm.shape[-1]
+    N = weights[0].shape[0]
+    a = _lib.GroupedGemmArgs()
+    a.A, a.lda, a.a_group_stride = xperm.data_ptr(), xperm.stride(0), rows_per_group * xperm.stride(0)
+    for g in range(G):
+        a.B[g] = weights[g].data_ptr()
+        if weights2 is not None:
+            a.B2[g] = weights2[g].data_ptr()
+    a.ldb = weights[0].stride(0)
+    if out is None:
+        out = torch.empty((G * rows_per_group, N), dtype=bf16, device=xperm.device)
+    a.C, a.ldc, a.c_group_stride = out.data_ptr(), out.stride(0), rows_per_group * out.stride(0)
+    a.m_dev = m_dev.data_ptr()
+    if row_map is not None:
+        a.row_map, a.row_gate, a.map_group_stride = row_map.data_ptr(), row_gate.data_ptr(), rows_per_group
+    if a_row_map is not None:
+        a.a_row_map, a.map_group_stride = a_row_map.data_ptr(), rows_per_group
+    if residual is not None:
+        a.residual, a.ldr = residual.data_ptr(), residual.stride(0)
+    a.groups, a.M, a.N, a.K = G, rows_per_group, N, K
+    a.out_dtype = DT_BF16
+    _lib.check(lib.mpl_grouped_gemm_bf16(ctypes.byref(a), _stream()), "mpl_grouped_gemm_bf16")
+    return out
+
+
+def moe_route_small(x, wg, k, capacity, ln_weight=None, ln_eps=1e-5, noise=None):
+    """One-launch decode MoE front end (S <= 64): RMSNorm + route + slots + dispatch. Returns the mpl_moe_route dict
+    plus h, xperm [E*capacity, D], tok_of_slot, gate_of_slot."""
+    lib = _lib.load()
+    _req(x, bf16, "x"); _req(wg, torch.float32, "wg")
+    x2 = _rows(x)
+    S, D = x2.shape
+    E = wg.shape[0]
+    dev = x.device
+    out = dict(logits=torch.empty((S, E), dtype=torch.float32, device=dev),
+               gates=torch.empty((S, E), dtype=torch.float32, device=dev),
+               expert=torch.empty((S, k), dtype=torch.int32, device=dev),
+               gate=torch.empty((S, k), dtype=torch.float32, device=dev),
+               slot=torch.empty((S, k), dtype=torch.int32, device=dev),
+               kept=torch.empty((E,), dtype=torch.int32, device=dev),
+               exp_counts=torch.empty((E,), dtype=torch.int32, device=dev),
+               l_aux=torch.empty((1,), dtype=torch.float32, device=dev),
+               h=torch.empty((S, D), dtype=bf16, device=dev),
+               xperm=torch.zeros((E * capacity, D), dtype=bf16, device=dev),
+               tok_of_slot=torch.full((E * capacity,), -1, dtype=torch.int32, device=dev),
+               gate_of_slot=torch.zeros((E * capacity,), dtype=torch.float32, device=dev))
+    a = _lib.MoeRouteArgs()
+    a.wg = wg.contiguous().data_ptr()
+    if noise is not None:
+        a.noise = noise.contiguous().data_ptr()
+    a.S, a.D, a.E, a.k, a.capacity = S, D, E, k, capacity
+    for name in ("logits", "gates", "expert", "gate", "slot", "kept", "exp_counts", "l_aux"):
+        setattr(a, name, out[name].data_ptr())
+    _lib.check(lib.mpl_moe_route_small(ctypes.byref(a), _ptr(x2), _ll(x2.stride(0)), _ptr(ln_weight),
+                                       ctypes.c_float(ln_eps), _ptr(out["h"]), _ll(D), _ptr(out["xperm"]),
+                                       _ptr(out["tok_of_slot"]), _ptr(out["gate_of_slot"]), _stream()),
+               "mpl_moe_route_small")
     return out

@@ -228,6 +228,12 @@ def test_attention_decode(dev, B, H, Tk, use_dev):
     scale = 1 / math.sqrt(d)
     ref = _ref_attention(q, kc[:, :, :Tk].permute(0, 2, 1, 3), vc[:, :, :Tk].permute(0, 2, 1, 3), scale)
     kd, vd = kc.to(dev), vc.to(dev)
+    # split-K over the keys (scratch given) must agree with the single-CTA-per-head result
+    scratch = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(2):  # twice: the counters are self-cleaning
+        o2 = ops.attention(q.to(dev), kd[:, :, :Tk].permute(0, 2, 1, 3), vd[:, :, :Tk].permute(0, 2, 1, 3), scale,
+                           scratch=scratch)
+        _close(o2, ref, 2e-2, "decode attention split-K")
     if use_dev:
         tk_dev = torch.tensor([Tk], dtype=torch.int32, device=dev)
         o = ops.attention(q.to(dev), kd.permute(0, 2, 1, 3), vd.permute(0, 2, 1, 3), scale, tk_dev=tk_dev)

@@ -1,0 +1,74 @@
+"""Dev tool: per-layer / per-token error of the native LLaMA-MoE stack against the bf16 oracle for one test case, and a
+decode-step probe (CPU enqueue time vs GPU time). Usage: python tools/dev_llama.py [case|probe] ..."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+bf16 = torch.bfloat16
+dev = torch.device("cuda:0")
+
+
+def case(name="tiny_moe", B=8, T=17):
+    import test_stacks_gpu as t
+    from medplib_b200 import engine
+    from oracle import llama, weights
+    cfg = t.LLAMA_CFGS[name]
+    sd = weights.llama(cfg, seed=21)
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn(B, T, cfg["hidden_size"], generator=g).to(bf16)
+    am = torch.ones(B, T + 4, dtype=torch.bool)
+    ref = llama.model_forward(sd, cfg, x, am[:, :T])
+    eng = engine.LlamaEngine({k: v.to(dev) for k, v in sd.items()}, cfg)
+    cache = eng.new_cache(B, T + 8)
+    out = eng.forward(x.to(dev).clone(), cache, kv_mask=am.to(dev), want_hidden_states=True, want_router=True)
+    torch.cuda.synchronize()
+    for l in range(cfg["num_layers"]):
+        got, want = out["hidden_states"][l].cpu().float(), ref["hidden_states"][l].float()
+        err = (got - want).abs().amax(-1).reshape(-1)
+        lg, lr = out["gate_logits"][l].cpu(), ref["gate_logits"][l]
+        flip = (lg.argmax(-1) != lr.argmax(-1))
+        margin = (lr[:, 0] - lr[:, 1]).abs() / lr.abs().max()
+        print(f"layer {l}: hidden-in err max {err.max():.3e} (scale {want.abs().max():.2e}); router err "
+              f"{(lg - lr).abs().max():.3e} scale {lr.abs().max():.2e}; flips {flip.nonzero().flatten().tolist()} "
+              f"margins {[round(float(margin[i]), 4) for i in flip.nonzero().flatten()]}")
+        worst = err.topk(5)
+        print("   worst tokens", worst.indices.tolist(), [f"{v:.3f}" for v in worst.values.tolist()])
+    got, want = out["last_hidden_state"].cpu().float(), ref["last_hidden_state"].float()
+    err = (got - want).abs().amax(-1).reshape(-1)
+    print("last: ", err.topk(8).indices.tolist(), [f"{v:.3f}" for v in err.topk(8).values.tolist()])
+
+
+def probe(B=1, steps=32):
+    import bench
+    m = bench.build_model(dev)
+    eng = m._llama()
+    T = 615
+    cache = eng.new_cache(B, T + steps + 8)
+    x = torch.randn(B, T, 4096, device=dev).to(bf16)
+    eng.forward(x, cache)
+    torch.cuda.synchronize()
+    xs = torch.randn(B, 1, 4096, device=dev).to(bf16)
+    for want_router in (False, True):
+        for _ in range(3):
+            eng.forward(xs.clone(), cache, want_router=want_router)
+        cache.len = T
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            eng.forward(xs.clone(), cache, want_router=want_router)
+        e1.record()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"B={B} want_router={want_router}: enqueue {1e3 * (t1 - t0) / steps:.3f} ms/step, "
+              f"gpu {e0.elapsed_time(e1) / steps:.3f} ms/step, wall {1e3 * (t2 - t0) / steps:.3f} ms/step", flush=True)
+        cache.len = T
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "probe":
+        probe(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    else:
+        case(*(sys.argv[2:3] or ["tiny_moe"]), *[int(a) for a in sys.argv[3:5]])
