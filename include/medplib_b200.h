@@ -294,6 +294,8 @@ typedef struct {
   const int* tk_dev;  /* NULL, or device int = *pos_dev + 1 */
   void* attn_scratch; /* optional zero-initialised scratch for split-K decode attention (see mpl_attn_args.scratch) */
   long long attn_scratch_bytes;
+  const void* decode_plan; /* optional, from mpl_llama_decode_plan_build: T == 1 steps with B <= 8 and top-1 routing run
+                              as ONE persistent cooperative kernel (llama_decode.cu) instead of ~7 launches per layer */
   const float* const* moe_noise; /* NULL or host array [n_layers] of f32 [B*T,E] (see mpl_moe_route) */
   float* gate_logits;            /* NULL or f32 [n_layers, B*T, E] out (what a forward hook on wg observes) */
   float* l_aux;                  /* NULL or f32 [n_layers] out */
@@ -302,6 +304,10 @@ typedef struct {
   long long workspace_bytes;
 } mpl_llama_io;
 long long mpl_llama_workspace_bytes(const mpl_llama_model* model, int B, int T);
+/* Device-resident decode plan (TMA descriptors of every weight matrix + the grid-barrier words). Build once per weight
+ * set into a caller-owned device buffer of mpl_llama_decode_plan_bytes(); rebuild when a weight tensor moves. */
+long long mpl_llama_decode_plan_bytes(const mpl_llama_model* model);
+int mpl_llama_decode_plan_build(const mpl_llama_model* model, void* plan, void* stream);
 int mpl_llama_forward(const mpl_llama_model* model, const mpl_llama_io* io, void* stream);
 
 /* CLIP ViT encoder layer / tower (HF 4.31 CLIPEncoderLayer, CLIPVisionTransformer) as used by

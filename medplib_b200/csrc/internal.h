@@ -22,6 +22,11 @@ int skinny_grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream
 int moe_route_small(const mpl_moe_route_args& a, const void* x, long long ldx, const void* ln_w, float eps, void* h,
                     long long ldh, void* xperm, int* tok_of_slot, float* gate_of_slot, cudaStream_t stream);
 int moe_route(const mpl_moe_route_args& a, cudaStream_t stream);
+bool llama_decode_supported(const mpl_llama_model& m, const mpl_llama_io& io);
+long long llama_decode_plan_bytes(const mpl_llama_model& m);
+int llama_decode_plan_build(const mpl_llama_model& m, void* plan_dev, cudaStream_t st);
+int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qkv, void* attn, void* h1,
+                      const int* cap_by_e, int emax, cudaStream_t st);
 int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D, cudaStream_t stream);
 int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
                 long long ldo, int S, int k, int D, cudaStream_t stream);

@@ -124,6 +124,14 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
   const LlamaWs w = carve(m, B, T, static_cast<char*>(io.workspace));
   if (w.total > io.workspace_bytes) return MPL_ERR_ARG;
   void* st_ = static_cast<void*>(st);
+  if (llama_decode_supported(m, io)) {
+    // decode step: one persistent kernel for all layers (h1 holds E*B rows: erows >= E*C >= the rows it needs)
+    int cap[MPL_MAX_EXPERTS + 1];
+    for (int e = 0; e <= MPL_MAX_EXPERTS; ++e) cap[e] = e > 0 ? moe_capacity(m, S, e) : 0;
+    const int emax = max_experts(m);
+    if (static_cast<long long>(emax) * B * F * 2 <= (w.y - w.h1))
+      return llama_decode_step(m, io, w.qkv, w.attn, w.h1, cap, emax, st);
+  }
   const long long cache_layer = static_cast<long long>(B) * H * io.Tmax * hd;  // elements per layer
 
   for (int l = 0; l < m.n_layers; ++l) {
@@ -312,6 +320,15 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
 extern "C" long long mpl_llama_workspace_bytes(const mpl_llama_model* m, int B, int T) {
   if (m == nullptr || m->layers == nullptr || B <= 0 || T <= 0) return 0;
   return mpl::carve(*m, B, T, nullptr).total;
+}
+
+extern "C" long long mpl_llama_decode_plan_bytes(const mpl_llama_model* m) {
+  if (m == nullptr || m->layers == nullptr) return 0;
+  return mpl::llama_decode_plan_bytes(*m);
+}
+extern "C" int mpl_llama_decode_plan_build(const mpl_llama_model* m, void* plan, void* stream) {
+  if (m == nullptr) return MPL_ERR_ARG;
+  return mpl::llama_decode_plan_build(*m, plan, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mpl_llama_forward(const mpl_llama_model* m, const mpl_llama_io* io, void* stream) {

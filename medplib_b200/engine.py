@@ -138,7 +138,16 @@ class LlamaEngine:
         self.model = m
         self.head_dim = hd
         self.E = max([layers[i].n_experts for i in range(L)])
-        self.attn_scratch = torch.zeros(4 << 20, dtype=torch.uint8, device=dev)  # split-K decode attention
+        self.attn_scratch = torch.zeros(5 << 20, dtype=torch.uint8, device=dev)  # split-K decode attention
+        # decode plan: TMA descriptors of every weight matrix for the one-kernel decode step (llama_decode.cu)
+        self.decode_plan = None
+        self.use_decode_kernel = True
+        if dev is not None and dev.type == "cuda":
+            lib = _lib.load()
+            nbytes = lib.mpl_llama_decode_plan_bytes(ctypes.byref(m))
+            plan = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            if lib.mpl_llama_decode_plan_build(ctypes.byref(m), _vp(plan), _stream()) == 0:
+                self.decode_plan = plan
 
     def new_cache(self, B, Tmax):
         c = self.cfg
@@ -192,6 +201,8 @@ class LlamaEngine:
             exp_counts = torch.zeros((L, self.E), dtype=torch.int32, device=x.device)
             io.gate_logits, io.l_aux, io.exp_counts = gate_logits.data_ptr(), l_aux.data_ptr(), exp_counts.data_ptr()
         io.attn_scratch, io.attn_scratch_bytes = self.attn_scratch.data_ptr(), self.attn_scratch.numel()
+        if self.decode_plan is not None and self.use_decode_kernel:
+            io.decode_plan = self.decode_plan.data_ptr()
         io.workspace, io.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.mpl_llama_forward(ctypes.byref(self.model), ctypes.byref(io), _stream()), "mpl_llama_forward")
         if pos_dev is None:
