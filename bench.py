@@ -230,10 +230,15 @@ def run_decode(args, rank, world, dev):
     torch.cuda.set_device(dev)
     m = build_model(dev, small=args.small)
     B, new = args.batch, args.new_tokens
-    images_clip, _, ids = make_inputs()
-    d_clip = images_clip.to(dev).to(bf16).expand(B, -1, -1, -1).contiguous()
-    d_ids = ids.to(dev).expand(B, -1).contiguous()
-    h_clip, h_ids = images_clip.expand(B, -1, -1, -1).contiguous().pin_memory(), ids.expand(B, -1).contiguous().pin_memory()
+    # B different prompts of the same length (different images and token ids, so the sequences route independently)
+    _, _, ids0 = make_inputs()
+    images_clip = torch.randn(B, 3, 336, 336, generator=torch.Generator().manual_seed(10))
+    ids = torch.randint(3, 31999, (B, N_TEXT), generator=torch.Generator().manual_seed(12))
+    ids[0] = ids0[0]
+    ids[:, 2], ids[:, 3], ids[:, 4] = 32001, -200, 32002
+    d_clip = images_clip.to(dev).to(bf16)
+    d_ids = ids.to(dev)
+    h_clip, h_ids = images_clip.pin_memory(), ids.pin_memory()
 
     def gen(n, e2e=False):
         if e2e:

@@ -308,6 +308,9 @@ long long mpl_llama_workspace_bytes(const mpl_llama_model* model, int B, int T);
  * set into a caller-owned device buffer of mpl_llama_decode_plan_bytes(); rebuild when a weight tensor moves. */
 long long mpl_llama_decode_plan_bytes(const mpl_llama_model* model);
 int mpl_llama_decode_plan_build(const mpl_llama_model* model, void* plan, void* stream);
+/* Dev tool: layer >= 0 makes the decode kernel record per-phase %globaltimer stamps of that layer (-1: off); out != NULL
+ * (host, 160*16 u64: [CTA][stamp]) receives the last recorded stamps after a device synchronise. */
+int mpl_debug_decode_timing(int layer, unsigned long long* out);
 int mpl_llama_forward(const mpl_llama_model* model, const mpl_llama_io* io, void* stream);
 
 /* CLIP ViT encoder layer / tower (HF 4.31 CLIPEncoderLayer, CLIPVisionTransformer) as used by

@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -40,6 +41,7 @@ constexpr int DK_MAXB = 8;
 constexpr int DK_MAXE = MPL_MAX_EXPERTS;
 constexpr int DK_RP = 9;  // reduction row pitch (floats)
 constexpr int DK_RED_FLOATS = DK_CONSUMERS * 16 * DK_RP;
+constexpr int DK_WG_SMEM = 32768;  // router weights staged in shared memory when E*D*4 fits
 
 // Per-layer device-resident description (the "decode plan"): tensor maps + the small raw pointers.
 struct alignas(64) DecLayerDev {
@@ -64,7 +66,7 @@ struct DecParams {
   __nv_bfloat16* qkv;   // [B, 3D]
   __nv_bfloat16* attn;  // [B, D]
   __nv_bfloat16* h1;    // [E*B, F]
-  float* attn_part;     // split-K partials [B*H][nsplit][130]
+  float* attn_part;     // split-K partials [B*H][nsplit][132]
   int* attn_cnt;        // [B*H] zero-initialised, self-cleaning
   __nv_bfloat16* kc;
   __nv_bfloat16* vc;
@@ -77,10 +79,30 @@ struct DecParams {
   float* gate_logits;  // [L, B, Emax] or NULL
   float* l_aux;        // [L] or NULL
   int* exp_counts;     // [L, Emax] or NULL
-  int B, D, H, F, L, Tmax, pos, nsplit, Emax;
+  int B, D, H, F, L, Tmax, pos, nsplit, Emax, timing_layer;
   int cap[DK_MAXE + 1];  // capacity for a layer with E experts (index E)
   float eps, scale;
 };
+
+// Optional per-phase timestamps (dev tool): consumer thread 0 of every CTA records %globaltimer at the phase boundaries
+// of layer `timing_layer`.
+constexpr int DK_TSLOTS = 16;
+__device__ unsigned long long g_dk_times[160 * DK_TSLOTS];
+static int g_timing_layer = -1;
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DK_STAMP(i)                                                                              \
+  do {                                                                                           \
+    if (l == p.timing_layer && threadIdx.x == 0 && blockIdx.x < 160) g_dk_times[blockIdx.x * DK_TSLOTS + (i)] = globaltimer(); \
+  } while (0)
+
+#define DK_STAMP_L(layer_, i)                                                                           \
+  do {                                                                                                   \
+    if ((layer_) == p.timing_layer && threadIdx.x == 0 && blockIdx.x < 160) g_dk_times[blockIdx.x * DK_TSLOTS + (i)] = globaltimer(); \
+  } while (0)
 
 struct Ring {
   uint8_t* base;
@@ -120,9 +142,9 @@ __device__ __forceinline__ uint4 dk_lds128(uint32_t addr) {
   return r;
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -133,11 +155,12 @@ __device__ __forceinline__ void grid_sync(unsigned int* ctr, unsigned int& targe
   consumer_sync();
   if (threadIdx.x == 0) {
     target += gridDim.x;
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    while (ld_acquire_u32(ctr) < target) {
+    // release (cumulative over the CTA's writes ordered by the bar.sync above) ... relaxed polling ... one acquire
+    // fence, which also invalidates this SM's L1 (SASS: MEMBAR.ALL.GPU + RED / LDG.STRONG / MEMBAR + CCTL.IVALL)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    while (ld_relaxed_u32(ctr) < target) {
     }
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   consumer_sync();
 }
@@ -164,19 +187,20 @@ __device__ __forceinline__ void consume_tile(Ring& r, int chunks, int K, const _
   constexpr int ROWS = DUAL ? 8 : 16;
   float acc0[4] = {0.f, 0.f, 0.f, 0.f};  // one accumulator, same HMMA order as the streaming kernel: identical bits
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  uint4 xn0 = zero, xn1 = zero;
-  {
-    const int k = warp * 64 + t * 8;
-    if (arow != nullptr && k < K) xn0 = *reinterpret_cast<const uint4*>(arow + k);
-    if (arow != nullptr && k + 32 < K) xn1 = *reinterpret_cast<const uint4*>(arow + k + 32);
-  }
+  // activation fragments run two chunks ahead of the weights (global-memory A of the down projection: L2 latency)
+  auto load_a = [&](int c, uint4& x0, uint4& x1) {
+    const int k = c * DK_KC + warp * 64 + t * 8;
+    x0 = (arow != nullptr && c < chunks && k < K) ? *reinterpret_cast<const uint4*>(arow + k) : zero;
+    x1 = (arow != nullptr && c < chunks && k + 32 < K) ? *reinterpret_cast<const uint4*>(arow + k + 32) : zero;
+  };
+  uint4 xa0, xa1, xn0, xn1;
+  load_a(0, xa0, xa1);
+  load_a(1, xn0, xn1);
   for (int c = 0; c < chunks; ++c) {
-    const uint4 xb0 = xn0, xb1 = xn1;
-    if (c + 1 < chunks) {  // next chunk's activation fragment in flight while this chunk's weights are consumed
-      const int k = (c + 1) * DK_KC + warp * 64 + t * 8;
-      xn0 = (arow != nullptr && k < K) ? *reinterpret_cast<const uint4*>(arow + k) : zero;
-      xn1 = (arow != nullptr && k + 32 < K) ? *reinterpret_cast<const uint4*>(arow + k + 32) : zero;
-    }
+    const uint4 xb0 = xa0, xb1 = xa1;
+    xa0 = xn0;
+    xa1 = xn1;
+    load_a(c + 2, xn0, xn1);
     mbar_wait(&r.full[r.stage], r.phase);
     const uint32_t sbase = smem_u32(r.base + r.stage * DK_STAGE_BYTES) + warp * (ROWS * 128) + g * 128;
     const uint32_t hi = DUAL ? DK_STAGE_BYTES / 2 : 1024;
@@ -211,156 +235,261 @@ __device__ __forceinline__ float reduce_rows(const float* rbuf, int r, int m) {
   return v;
 }
 
-// RMSNorm of the B activation rows into shared memory (one warp per row), HF LlamaRMSNorm roundings:
-// w * bf16(x * rstd). ln == NULL: plain copy.
-__device__ __forceinline__ void stage_rows(const DecParams& p, const __nv_bfloat16* src, const __nv_bfloat16* ln,
-                                           uint8_t* s_a, int pitch) {
+// Activation staging. The B rows (and the norm weight) are brought into shared memory by bulk-async copies issued by one
+// thread (L2 -> smem at TMA speed, no register staging, not affected by the L1 invalidation of the grid barrier); the
+// RMSNorm then runs smem -> smem, one warp per row, with HF LlamaRMSNorm's roundings w * bf16(x * rstd) and the
+// summation order of rmsnorm_kernel (lane-strided, then the xor-shuffle tree), so the bits agree with the general path.
+struct ActStage {
+  uint8_t* s_a;    // [B][pitch]
+  uint64_t* bar;   // completion of the row copies
+  uint32_t phase;  // parity of the next completion
+  int pitch;
+};
+__device__ __forceinline__ void dk_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// s_ln: the norm weight, already in shared memory (copied long before, completion on ln_bar / ln_phase), or NULL.
+// All 8 warps share every row (a single warp per row costs ~2 us of pure issue time at D = 4096): thread t owns the
+// 16-byte vectors t, t + 256, ...; the sum of squares is reduced lane -> warp (shuffles) -> CTA (fixed order 0..7).
+__device__ __noinline__ void stage_rows(ActStage& st, const __nv_bfloat16* src, const uint8_t* s_ln, uint64_t* ln_bar,
+                                        uint32_t ln_phase, int B, int D, float eps, float* s_part) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < p.B) {
-    const __nv_bfloat16* xr = src + static_cast<long long>(warp) * p.D;
-    uint8_t* dst = s_a + warp * pitch;
-    float rstd = 1.0f;
-    if (ln != nullptr) {
-      float ss = 0.0f;
-      for (int k = lane * 8; k < p.D; k += 256) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(xr + k);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  // fields copied to locals: the stores below go through a byte pointer, which may alias the struct itself
+  uint8_t* const s_a = st.s_a;
+  uint64_t* const bar = st.bar;
+  const int pitch = st.pitch;
+  const uint32_t phase = st.phase;
+  st.phase = phase ^ 1;
+  if (threadIdx.x == 0) {
+    fence_proxy_async();  // earlier generic-proxy accesses of s_a are ordered before the async-proxy writes
+    mbar_expect_tx(bar, static_cast<uint32_t>(B * D * 2));
+    for (int m = 0; m < B; ++m)
+      dk_bulk_g2s(s_a + m * pitch, src + static_cast<long long>(m) * D, static_cast<uint32_t>(D * 2), bar);
+  }
+  mbar_wait(bar, phase);
+  if (s_ln == nullptr) return;
+  mbar_wait(ln_bar, ln_phase);
+  for (int m = 0; m < B; ++m) {
+    const uint8_t* row = s_a + m * pitch;
+    float ss = 0.0f;
+    for (int k = threadIdx.x * 8; k < D; k += DK_CONSUMERS * 32 * 8) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(row + k * 2);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(h[i]);
-          ss += f.x * f.x + f.y * f.y;
-        }
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        ss += f.x * f.x + f.y * f.y;
       }
-      ss = warp_sum(ss);
-      rstd = rsqrtf(ss / static_cast<float>(p.D) + p.eps);
     }
-    for (int k = lane * 8; k < p.D; k += 256) {
-      uint4 v = *reinterpret_cast<const uint4*>(xr + k);
-      if (ln != nullptr) {
-        const uint4 w = *reinterpret_cast<const uint4*>(ln + k);
-        const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&v);
-        const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&w);
-        uint4 o;
-        uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+    ss = warp_sum(ss);
+    if (lane == 0) s_part[m * DK_CONSUMERS + warp] = ss;
+  }
+  consumer_sync();
+  for (int m = 0; m < B; ++m) {
+    float tot = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 xf = __bfloat1622float2(xp[i]), wf = __bfloat1622float2(wp[i]);
-          op[i] = pack_bf16(wf.x * bf16_round(xf.x * rstd), wf.y * bf16_round(xf.y * rstd));
-        }
-        v = o;
+    for (int w = 0; w < DK_CONSUMERS; ++w) tot += s_part[m * DK_CONSUMERS + w];
+    const float rstd = rsqrtf(tot / static_cast<float>(D) + eps);
+    uint8_t* row = s_a + m * pitch;
+    for (int k = threadIdx.x * 8; k < D; k += DK_CONSUMERS * 32 * 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(row + k * 2);
+      const uint4 w = *reinterpret_cast<const uint4*>(s_ln + k * 2);
+      const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&w);
+      uint4 o;
+      uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xf = __bfloat1622float2(xp[i]), wf = __bfloat1622float2(wp[i]);
+        op[i] = pack_bf16(wf.x * bf16_round(xf.x * rstd), wf.y * bf16_round(xf.y * rstd));
       }
-      *reinterpret_cast<uint4*>(dst + k * 2) = v;
+      *reinterpret_cast<uint4*>(row + k * 2) = o;
     }
   }
+  consumer_sync();  // s_part is reused; the rows are complete for every reader
+}
+
+// L2 prefetch of small per-layer tensors (router weights, norm weights) well before they are needed.
+__device__ __forceinline__ void prefetch_l2(const void* ptr, long long bytes) {
+  const char* c = static_cast<const char*>(ptr);
+  for (long long off = static_cast<long long>(threadIdx.x) * 128; off < bytes; off += DK_CONSUMERS * 32 * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
 }
 
 // ------------------------------------------------------------------------------------------------ attention item
 // One (b, h, split) of the decode attention: 8 warps, 4 keys per warp step, 8 lanes x 16 dims per key. q and the new
 // key are rotated on the fly from the q,k,v buffer; the split that owns position `pos` appends k,v to the cache.
-__device__ __forceinline__ void rope16(const __nv_bfloat16* src, const __nv_bfloat16* cr, const __nv_bfloat16* sr,
-                                       int gl, float (&out)[16]) {
-  // dims d = gl*16 .. +15 of a 128-wide head; partner = d + 64 (first half, rotated with a minus sign) or d - 64
-  const int d0 = gl * 16;
-  const bool first = gl < 4;
-  const __nv_bfloat16* own = src + d0;
-  const __nv_bfloat16* par = src + (first ? d0 + 64 : d0 - 64);
+__device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (&f)[16]) {
+  const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const float f = __bfloat162float(own[e]), fp = __bfloat162float(par[e]);
-    const float c = __bfloat162float(cr[d0 + e]), s = __bfloat162float(sr[d0 + e]);
-    const float a = bf16_round(f * c);
-    const float b = bf16_round((first ? -fp : fp) * s);
-    out[e] = bf16_round(a + b);
+  for (int e = 0; e < 4; ++e) {
+    const float2 x = __bfloat1622float2(ha[e]), y = __bfloat1622float2(hb[e]);
+    f[2 * e] = x.x;
+    f[2 * e + 1] = x.y;
+    f[8 + 2 * e] = y.x;
+    f[8 + 2 * e + 1] = y.y;
   }
 }
+// RoPE of dims d = gl*16 .. +15 of a 128-wide head (partner = d + 64 for the first half, rotated with a minus sign, or
+// d - 64), HF apply_rotary_pos_emb in bf16: every product and the sum rounded. Result packed as bf16.
+__device__ __forceinline__ void rope16(const __nv_bfloat16* src, const __nv_bfloat16* cr, const __nv_bfloat16* sr,
+                                       int gl, uint4& o0, uint4& o1) {
+  const int d0 = gl * 16;
+  const bool first = gl < 4;
+  const uint4* own = reinterpret_cast<const uint4*>(src + d0);
+  const uint4* par = reinterpret_cast<const uint4*>(src + (first ? d0 + 64 : d0 - 64));
+  const uint4* cp = reinterpret_cast<const uint4*>(cr + d0);
+  const uint4* sp = reinterpret_cast<const uint4*>(sr + d0);
+  const uint4 a0 = own[0], a1 = own[1], p0 = par[0], p1 = par[1], c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+  float f[16], fp[16], c[16], sn[16], out[16];
+  unpack16(a0, a1, f);
+  unpack16(p0, p1, fp);
+  unpack16(c0, c1, c);
+  unpack16(s0, s1, sn);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float a = bf16_round(f[e] * c[e]);
+    const float b = bf16_round((first ? -fp[e] : fp[e]) * sn[e]);
+    out[e] = a + b;
+  }
+  o0.x = pack_bf16(out[0], out[1]); o0.y = pack_bf16(out[2], out[3]); o0.z = pack_bf16(out[4], out[5]); o0.w = pack_bf16(out[6], out[7]);
+  o1.x = pack_bf16(out[8], out[9]); o1.y = pack_bf16(out[10], out[11]); o1.z = pack_bf16(out[12], out[13]); o1.w = pack_bf16(out[14], out[15]);
+}
 
-__device__ void attention_item(const DecParams& p, int layer, int b, int h, int z, int Tk, float* s_f) {
+// P2. One (b, h, split) per WARP: 4 keys per step (8 lanes x 16 dims per key), 4 steps (16 keys, 8 KB) in flight per
+// warp, no CTA-level synchronisation: the 4 key groups merge by shuffles, splits merge through global scratch by the
+// last warp to arrive (atomic counter per (b, h), self-cleaning). The cached keys do not depend on this layer's q,k,v,
+// so the first 16 keys of the item are requested BEFORE the grid barrier that ends P1 and arrive while it is waiting.
+__device__ __noinline__ void attention_phase(const DecParams& p, int layer, int Tk, unsigned int& bar_target) {
   constexpr int D = 128;
-  float* s_o = s_f;                     // [8][128]
-  float* s_m = s_f + DK_CONSUMERS * D;  // [8]
-  float* s_l = s_m + DK_CONSUMERS;      // [8]
-  int* s_last = reinterpret_cast<int*>(s_l + DK_CONSUMERS);
+  constexpr int UNR = 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, gl = lane & 7;
   const int nsplit = p.nsplit;
   const int per = ((Tk + nsplit - 1) / nsplit + 31) & ~31;
-  const int k_lo = z * per;
-  const int k_hi = min(Tk, k_lo + per);
   const int pos = Tk - 1;
-  const __nv_bfloat16* qrow = p.qkv + static_cast<long long>(b) * 3 * p.D + h * D;
-  const __nv_bfloat16* krow = qrow + p.D;
-  const __nv_bfloat16* vrow = qrow + 2 * p.D;
+  const int n_items = p.B * p.H * nsplit;
+  const int stride = gridDim.x * DK_CONSUMERS;
   const __nv_bfloat16* cr = p.cos_t + static_cast<long long>(pos) * D;
   const __nv_bfloat16* sr = p.sin_t + static_cast<long long>(pos) * D;
-  const long long head_off = (static_cast<long long>(b) * p.H + h) * p.Tmax * D;
-  __nv_bfloat16* kc = p.kc + layer * p.cache_layer + head_off;
-  __nv_bfloat16* vc = p.vc + layer * p.cache_layer + head_off;
-  const unsigned char* mrow = p.kv_mask ? p.kv_mask + static_cast<long long>(b) * p.kv_mask_stride : nullptr;
-  float qf[16];
-  rope16(qrow, cr, sr, gl, qf);
   const float sl2 = p.scale * 1.4426950408889634f;
-  float m = -INFINITY, l = 0.0f;
-  float acc[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
-  for (int k0 = k_lo + warp * 4; k0 < k_hi; k0 += DK_CONSUMERS * 4) {
-    const int key = k0 + grp;
-    const bool valid = key < k_hi;
-    const int kk = valid ? key : k_lo;
-    float kf[16], vf[16];
-    if (kk == pos) {
-      rope16(krow, cr, sr, gl, kf);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) vf[e] = __bfloat162float(vrow[gl * 16 + e]);
-      if (valid) {  // KV-cache append (exactly one lane group of one split owns the new position)
-        uint4 o0, o1;
-        o0.x = pack_bf16(kf[0], kf[1]); o0.y = pack_bf16(kf[2], kf[3]); o0.z = pack_bf16(kf[4], kf[5]); o0.w = pack_bf16(kf[6], kf[7]);
-        o1.x = pack_bf16(kf[8], kf[9]); o1.y = pack_bf16(kf[10], kf[11]); o1.z = pack_bf16(kf[12], kf[13]); o1.w = pack_bf16(kf[14], kf[15]);
-        __nv_bfloat16* kd = kc + static_cast<long long>(pos) * D + gl * 16;
-        *reinterpret_cast<uint4*>(kd) = o0;
-        *reinterpret_cast<uint4*>(kd + 8) = o1;
-        __nv_bfloat16* vd = vc + static_cast<long long>(pos) * D + gl * 16;
-        *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(vrow + gl * 16);
-        *reinterpret_cast<uint4*>(vd + 8) = *reinterpret_cast<const uint4*>(vrow + gl * 16 + 8);
+  bool synced = false;
+  // items are dealt round-robin over the CTAs first, so every SM pulls on the KV cache
+  for (int item = warp * gridDim.x + blockIdx.x; item < n_items || !synced; item += stride) {
+    const bool has = item < n_items;
+    const int z = has ? item % nsplit : 0, bh = has ? item / nsplit : 0;
+    const int b = bh / p.H, h = bh % p.H;
+    const int k_lo = z * per;
+    const int k_hi = has ? min(Tk, k_lo + per) : k_lo;
+    const __nv_bfloat16* qrow = p.qkv + static_cast<long long>(b) * 3 * p.D + h * D;
+    const __nv_bfloat16* krow = qrow + p.D;
+    const __nv_bfloat16* vrow = qrow + 2 * p.D;
+    const long long head_off = (static_cast<long long>(b) * p.H + h) * p.Tmax * D;
+    __nv_bfloat16* kc = p.kc + layer * p.cache_layer + head_off;
+    __nv_bfloat16* vc = p.vc + layer * p.cache_layer + head_off;
+    const unsigned char* mrow = p.kv_mask ? p.kv_mask + static_cast<long long>(b) * p.kv_mask_stride : nullptr;
+
+    // cached K/V of one key for this lane's 16 dims (packed bf16); the new position is filled in later
+    auto load_cached = [&](int k0, uint4& ka, uint4& kb, uint4& va, uint4& vb) {
+      const int key = k0 + grp;
+      const int kk = (key < k_hi && key != pos) ? key : k_lo;
+      if (kk == pos) {  // (k_lo == pos: nothing cached to read)
+        ka = kb = va = vb = make_uint4(0, 0, 0, 0);
+        return;
       }
-    } else {
       const __nv_bfloat16* kr = kc + static_cast<long long>(kk) * D + gl * 16;
       const __nv_bfloat16* vr = vc + static_cast<long long>(kk) * D + gl * 16;
-      const uint4 ka = *reinterpret_cast<const uint4*>(kr), kb = *reinterpret_cast<const uint4*>(kr + 8);
-      const uint4 va = *reinterpret_cast<const uint4*>(vr), vb = *reinterpret_cast<const uint4*>(vr + 8);
-      const __nv_bfloat162* hka = reinterpret_cast<const __nv_bfloat162*>(&ka);
-      const __nv_bfloat162* hkb = reinterpret_cast<const __nv_bfloat162*>(&kb);
-      const __nv_bfloat162* hva = reinterpret_cast<const __nv_bfloat162*>(&va);
-      const __nv_bfloat162* hvb = reinterpret_cast<const __nv_bfloat162*>(&vb);
+      ka = *reinterpret_cast<const uint4*>(kr);
+      kb = *reinterpret_cast<const uint4*>(kr + 8);
+      va = *reinterpret_cast<const uint4*>(vr);
+      vb = *reinterpret_cast<const uint4*>(vr + 8);
+    };
+    // the new position: rotate k from the q,k,v buffer, append k,v to the cache (one lane group of one split owns it)
+    auto fix_new = [&](int k0, uint4& ka, uint4& kb, uint4& va, uint4& vb) {
+      if (k0 + grp != pos || pos >= k_hi) return;
+      rope16(krow, cr, sr, gl, ka, kb);
+      va = *reinterpret_cast<const uint4*>(vrow + gl * 16);
+      vb = *reinterpret_cast<const uint4*>(vrow + gl * 16 + 8);
+      __nv_bfloat16* kd = kc + static_cast<long long>(pos) * D + gl * 16;
+      *reinterpret_cast<uint4*>(kd) = ka;
+      *reinterpret_cast<uint4*>(kd + 8) = kb;
+      __nv_bfloat16* vd = vc + static_cast<long long>(pos) * D + gl * 16;
+      *reinterpret_cast<uint4*>(vd) = va;
+      *reinterpret_cast<uint4*>(vd + 8) = vb;
+    };
+
+    // two register buffers of UNR steps (8 keys) each, ping-pong: one is consumed while the other is in flight
+    uint4 ka[2][UNR], kb[2][UNR], va[2][UNR], vb[2][UNR];
+    auto load_round = [&](int kb0, int w) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 a = __bfloat1622float2(hka[e]), c = __bfloat1622float2(hkb[e]);
-        kf[2 * e] = a.x; kf[2 * e + 1] = a.y; kf[8 + 2 * e] = c.x; kf[8 + 2 * e + 1] = c.y;
-        const float2 a2 = __bfloat1622float2(hva[e]), c2 = __bfloat1622float2(hvb[e]);
-        vf[2 * e] = a2.x; vf[2 * e + 1] = a2.y; vf[8 + 2 * e] = c2.x; vf[8 + 2 * e + 1] = c2.y;
+      for (int u = 0; u < UNR; ++u)
+        if (kb0 + 4 * u < k_hi) load_cached(kb0 + 4 * u, ka[w][u], kb[w][u], va[w][u], vb[w][u]);
+    };
+    load_round(k_lo, 0);
+    load_round(k_lo + 4 * UNR, 1);
+    if (!synced) {
+      DK_STAMP_L(layer, 2);
+      grid_sync(p.sync, bar_target);  // q,k,v of this layer are complete; the first keys are already in flight
+      DK_STAMP_L(layer, 3);
+      synced = true;
+    }
+    if (!has) break;
+    float qf[16];
+    {
+      uint4 q0, q1;
+      rope16(qrow, cr, sr, gl, q0, q1);
+      unpack16(q0, q1, qf);
+    }
+    float m = -INFINITY, l = 0.0f;
+    float acc[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
+    auto compute_round = [&](int kb0, int w) {
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (kb0 + 4 * u >= k_hi) break;  // warp-uniform
+        fix_new(kb0 + 4 * u, ka[w][u], kb[w][u], va[w][u], vb[w][u]);
+        const int key = kb0 + 4 * u + grp;
+        const bool valid = key < k_hi;
+        const int kk = valid ? key : k_lo;
+        float kf[16], vf[16];
+        unpack16(ka[w][u], kb[w][u], kf);
+        unpack16(va[w][u], vb[w][u], vf);
+        // same association as the general decode kernel: pairs (e, e+1) of the low and the high 8 dims per step
+        float dot = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          dot += qf[2 * e] * kf[2 * e] + qf[2 * e + 1] * kf[2 * e + 1] + qf[8 + 2 * e] * kf[8 + 2 * e] +
+                 qf[8 + 2 * e + 1] * kf[8 + 2 * e + 1];
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+        float sc = dot * sl2;
+        if (!valid || (mrow != nullptr && mrow[kk] == 0)) sc = -INFINITY;
+        const float mn = fmaxf(m, sc);
+        const float msafe = (mn == -INFINITY) ? 0.0f : mn;
+        const float corr = exp2f(m - msafe);
+        const float pexp = exp2f(sc - msafe);
+        const float pv = bf16_round(pexp);  // P rounded to bf16 before P·V (softmax(...).to(bf16) @ v)
+        l = l * corr + pexp;
+        m = mn;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = acc[e] * corr + pv * vf[e];
+      }
+    };
+    for (int kb0 = k_lo; kb0 < k_hi; kb0 += 8 * UNR) {
+      compute_round(kb0, 0);
+      load_round(kb0 + 8 * UNR, 0);
+      if (kb0 + 4 * UNR < k_hi) {
+        compute_round(kb0 + 4 * UNR, 1);
+        load_round(kb0 + 12 * UNR, 1);
       }
     }
-    // same association as the general decode kernel: pairs (e, e+1) of the low and the high 8 dims per step
-    float dot = 0.0f;
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      dot += qf[2 * e] * kf[2 * e] + qf[2 * e + 1] * kf[2 * e + 1] + qf[8 + 2 * e] * kf[8 + 2 * e] +
-             qf[8 + 2 * e + 1] * kf[8 + 2 * e + 1];
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    float sc = dot * sl2;
-    if (!valid || (mrow != nullptr && mrow[kk] == 0)) sc = -INFINITY;
-    const float mn = fmaxf(m, sc);
-    const float msafe = (mn == -INFINITY) ? 0.0f : mn;
-    const float corr = exp2f(m - msafe);
-    const float pexp = exp2f(sc - msafe);
-    const float pv = bf16_round(pexp);  // P rounded to bf16 before P·V (softmax(...).to(bf16) @ v)
-    l = l * corr + pexp;
-    m = mn;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) acc[e] = acc[e] * corr + pv * vf[e];
-  }
+  // merge the 4 key groups of the warp (lanes differing in bits 3,4)
 #pragma unroll
   for (int sh = 8; sh <= 16; sh <<= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, sh);
@@ -376,68 +505,77 @@ __device__ void attention_item(const DecParams& p, int layer, int b, int h, int 
     }
     m = mn;
   }
-  if (grp == 0) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) s_o[warp * D + gl * 16 + e] = acc[e];
-    if (gl == 0) {
-      s_m[warp] = m;
-      s_l[warp] = l;
-    }
-  }
-  consumer_sync();
-  float mm = -INFINITY, lt = 0.0f, ot = 0.0f;
-  if (threadIdx.x < D) {
-#pragma unroll
-    for (int w = 0; w < DK_CONSUMERS; ++w) mm = fmaxf(mm, s_m[w]);
-    const float msafe = (mm == -INFINITY) ? 0.0f : mm;
-#pragma unroll
-    for (int w = 0; w < DK_CONSUMERS; ++w) {
-      const float c = exp2f(s_m[w] - msafe);
-      lt += s_l[w] * c;
-      ot += s_o[w * D + threadIdx.x] * c;
-    }
-  }
   __nv_bfloat16* optr = p.attn + static_cast<long long>(b) * p.D + h * D;
   if (nsplit == 1) {
-    if (threadIdx.x < D) optr[threadIdx.x] = __float2bfloat16_rn(lt > 0.0f ? ot / lt : 0.0f);
-    consumer_sync();  // s_o / s_m are reused by the next item
-    return;
+    if (grp == 0) {
+      const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+      uint4 o0, o1;
+      o0.x = pack_bf16(acc[0] * inv, acc[1] * inv); o0.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+      o0.z = pack_bf16(acc[4] * inv, acc[5] * inv); o0.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+      o1.x = pack_bf16(acc[8] * inv, acc[9] * inv); o1.y = pack_bf16(acc[10] * inv, acc[11] * inv);
+      o1.z = pack_bf16(acc[12] * inv, acc[13] * inv); o1.w = pack_bf16(acc[14] * inv, acc[15] * inv);
+      *reinterpret_cast<uint4*>(optr + gl * 16) = o0;
+      *reinterpret_cast<uint4*>(optr + gl * 16 + 8) = o1;
+    }
+    continue;
   }
-  const int bh = b * p.H + h;
-  float* part = p.attn_part + static_cast<long long>(bh) * nsplit * (D + 2);
-  if (threadIdx.x < D) {
-    float* mine = part + z * (D + 2);
-    mine[threadIdx.x] = ot;
-    if (threadIdx.x == 0) {
-      mine[D] = mm;
-      mine[D + 1] = lt;
+
+  float* part = p.attn_part + static_cast<long long>(bh) * nsplit * (D + 4);
+  if (grp == 0) {
+    float* mine = part + z * (D + 4);
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      *reinterpret_cast<float4*>(mine + gl * 16 + q4 * 4) =
+          make_float4(acc[q4 * 4], acc[q4 * 4 + 1], acc[q4 * 4 + 2], acc[q4 * 4 + 3]);
+    if (gl == 0) {
+      mine[D] = m;
+      mine[D + 1] = l;
     }
   }
   __threadfence();
-  consumer_sync();
-  if (threadIdx.x == 0) *s_last = (atomicAdd(&p.attn_cnt[bh], 1) == nsplit - 1);
-  consumer_sync();
-  if (*s_last) {
-    __threadfence();
-    if (threadIdx.x < D) {
-      float gm = -INFINITY;
-      for (int zz = 0; zz < nsplit; ++zz) gm = fmaxf(gm, __ldcg(part + zz * (D + 2) + D));
-      const float gsafe = (gm == -INFINITY) ? 0.0f : gm;
-      float gl_ = 0.0f, go = 0.0f;
-      for (int zz = 0; zz < nsplit; ++zz) {
-        const float c = exp2f(__ldcg(part + zz * (D + 2) + D) - gsafe);
-        gl_ += __ldcg(part + zz * (D + 2) + D + 1) * c;
-        go += __ldcg(part + zz * (D + 2) + threadIdx.x) * c;
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) last = (atomicAdd(&p.attn_cnt[bh], 1) == nsplit - 1);
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) continue;
+  __threadfence();
+  // this warp merges all splits. Lane zz first fetches (max, sum) of split zz -- one round trip for all splits --
+  // then every lane accumulates its 4 dims over the splits with the loads of 8 splits in flight at a time.
+  const float mz = lane < nsplit ? __ldcg(part + lane * (D + 4) + D) : -INFINITY;
+  const float lz = lane < nsplit ? __ldcg(part + lane * (D + 4) + D + 1) : 0.0f;
+  const float gm = warp_max(mz);
+  const float gsafe = (gm == -INFINITY) ? 0.0f : gm;
+  const float cz = exp2f(mz - gsafe);  // 0 for absent / empty splits
+  const float gl_ = warp_sum(lz * cz);
+  float go[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int z0 = 0; z0 < nsplit; z0 += 8) {
+    float4 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = z0 + j < nsplit ? __ldcg(reinterpret_cast<const float4*>(part + (z0 + j) * (D + 4) + lane * 4))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float c = __shfl_sync(0xffffffffu, cz, (z0 + j) & 31);
+      if (z0 + j < nsplit) {
+        go[0] += o[j].x * c;
+        go[1] += o[j].y * c;
+        go[2] += o[j].z * c;
+        go[3] += o[j].w * c;
       }
-      optr[threadIdx.x] = __float2bfloat16_rn(gl_ > 0.0f ? go / gl_ : 0.0f);
-      if (threadIdx.x == 0) p.attn_cnt[bh] = 0;
     }
   }
-  consumer_sync();
+  const float inv = gl_ > 0.0f ? 1.0f / gl_ : 0.0f;
+  uint2 o;
+  o.x = pack_bf16(go[0] * inv, go[1] * inv);
+  o.y = pack_bf16(go[2] * inv, go[3] * inv);
+  *reinterpret_cast<uint2*>(optr + lane * 4) = o;
+  if (lane == 0) p.attn_cnt[bh] = 0;  // self-cleaning for the next layer / launch
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecParams p) {
+__global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __grid_constant__ DecParams p) {
   extern __shared__ uint8_t dk_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dk_raw) + 1023) & ~uintptr_t(1023));
   const int pitch = p.D * 2 + 64;  // activation row pitch in shared memory (conflict-free 16-byte reads)
@@ -446,7 +584,13 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecPa
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 2 * DK_RED_FLOATS);
   uint64_t* empty_bar = full_bar + DK_STAGES;
   uint64_t* route_bar = empty_bar + DK_STAGES;
-  RouteSmem* rt = reinterpret_cast<RouteSmem*>(route_bar + 2);
+  uint64_t* act_bar = route_bar + 1;
+  uint64_t* wg_bar = route_bar + 2;  // post-attention norm weight + router weights of the layer
+  uint64_t* lnin_bar = route_bar + 3;  // input norm weight of the next layer (or the final norm)
+  RouteSmem* rt = reinterpret_cast<RouteSmem*>(route_bar + 4);
+  uint8_t* s_ln_in = reinterpret_cast<uint8_t*>(rt) + ((sizeof(RouteSmem) + 127) & ~size_t(127));  // [D] bf16
+  uint8_t* s_ln_post = s_ln_in + p.D * 2;                                                           // [D] bf16
+  float* s_wg = reinterpret_cast<float*>(s_ln_post + p.D * 2);  // [E][D] f32 router weights (when they fit)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
@@ -456,6 +600,9 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecPa
       mbar_init(&empty_bar[s], DK_CONSUMERS);
     }
     mbar_init(route_bar, 1);
+    mbar_init(act_bar, 1);
+    mbar_init(wg_bar, 1);
+    mbar_init(lnin_bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
@@ -498,13 +645,31 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecPa
   const int g = lane >> 2;
   unsigned int bar_target = 0;
   int buf = 0;
+  ActStage act{s_a, act_bar, 0u, pitch};
+  uint32_t wg_phase = 0, lnin_phase = 0;
+  if (threadIdx.x == 0) {  // input norm weight of layer 0
+    mbar_expect_tx(lnin_bar, static_cast<uint32_t>(D * 2));
+    dk_bulk_g2s(s_ln_in, p.layers[0].input_ln, static_cast<uint32_t>(D * 2), lnin_bar);
+  }
   const int pos = p.pos_dev ? *p.pos_dev : p.pos;
   const int Tk = pos + 1;
   for (int l = 0; l < p.L; ++l) {
     const DecLayerDev* L = p.layers + l;
+    DK_STAMP(0);
+    const int E = L->wg != nullptr ? L->n_experts : 1;
+    const bool wg_smem = L->wg != nullptr && static_cast<long long>(E) * D * 4 <= DK_WG_SMEM;
+    if (threadIdx.x == 0) {  // small weights of this layer: in shared memory long before P4 needs them
+      fence_proxy_async();
+      mbar_expect_tx(wg_bar, static_cast<uint32_t>(D * 2 + (wg_smem ? E * D * 4 : 0)));
+      dk_bulk_g2s(s_ln_post, L->post_ln, static_cast<uint32_t>(D * 2), wg_bar);
+      if (wg_smem)
+        for (int e = 0; e < E; ++e) dk_bulk_g2s(s_wg + e * D, L->wg + static_cast<long long>(e) * D, D * 4, wg_bar);
+    }
     // ---------------------------------------------------------- P1: q,k,v = RMSNorm(x) Wqkv^T
-    stage_rows(p, p.x, L->input_ln, s_a, pitch);
+    stage_rows(act, p.x, s_ln_in, lnin_bar, lnin_phase, B, D, p.eps, red);
+    lnin_phase ^= 1;
     consumer_sync();
+    DK_STAMP(1);
     {
       const __nv_bfloat16* arow = g < B ? reinterpret_cast<const __nv_bfloat16*>(s_a + g * pitch) : nullptr;
       for (int tile = blockIdx.x; tile < 3 * tiles_d; tile += G) {
@@ -519,16 +684,20 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecPa
         }
       }
     }
+    // ---------------------------------------------------------- P2 (includes the grid barrier that ends P1)
+    attention_phase(p, l, Tk, bar_target);
+    DK_STAMP(4);
     grid_sync(p.sync, bar_target);
-    // ---------------------------------------------------------- P2: RoPE + KV append + attention over the cache
-    for (int item = blockIdx.x; item < B * p.H * p.nsplit; item += G) {
-      const int z = item % p.nsplit, bh = item / p.nsplit;
-      attention_item(p, l, bh / p.H, bh % p.H, z, Tk, red);
-    }
-    grid_sync(p.sync, bar_target);
+    DK_STAMP(5);
     // ---------------------------------------------------------- P3: x += attn Wo^T
-    stage_rows(p, p.attn, nullptr, s_a, pitch);
+    stage_rows(act, p.attn, nullptr, nullptr, 0u, B, D, p.eps, red);
+    if (threadIdx.x == 0) {  // s_ln_in is free (all CTA threads are past P1's staging): next layer's input norm weight
+      fence_proxy_async();
+      mbar_expect_tx(lnin_bar, static_cast<uint32_t>(D * 2));
+      dk_bulk_g2s(s_ln_in, l + 1 < p.L ? p.layers[l + 1].input_ln : p.final_norm, static_cast<uint32_t>(D * 2), lnin_bar);
+    }
     consumer_sync();
+    DK_STAMP(6);
     {
       const __nv_bfloat16* arow = g < B ? reinterpret_cast<const __nv_bfloat16*>(s_a + g * pitch) : nullptr;
       for (int tile = blockIdx.x; tile < tiles_d; tile += G) {
@@ -545,58 +714,66 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecPa
         }
       }
     }
+    DK_STAMP(7);
     grid_sync(p.sync, bar_target);
+    DK_STAMP(8);
     // ---------------------------------------------------------- P4: h = RMSNorm(x), router (every CTA, no barrier)
-    stage_rows(p, p.x, L->post_ln, s_a, pitch);
-    const int E = L->wg != nullptr ? L->n_experts : 1;
-    if (L->wg != nullptr && warp < B) {
-      // logits from the stored (bf16-rounded) h, same per-lane order as moe_router_kernel
-      __syncwarp();
-      const uint8_t* hr = s_a + warp * pitch;
-      float acc[DK_MAXE];
+    stage_rows(act, p.x, s_ln_post, wg_bar, wg_phase, B, D, p.eps, red);  // (wg_bar also covers the router weights)
+    wg_phase ^= 1;
+    if (L->wg != nullptr) {
+      // router logits from the stored (bf16-rounded) h, fp32 like DeepSpeed's TopKGate; all 8 warps share every row
+      // (thread t owns k = 8t, 8t + 2048, ...), partial sums reduced lane -> warp -> CTA in a fixed order
+      const float* wgp = wg_smem ? s_wg : L->wg;  // generic pointer: shared-memory copy when it fits
+      float* s_rp = red + 64;                     // [B][DK_MAXE][8 warps]
+      for (int m = 0; m < B; ++m) {
+        const uint8_t* hr = s_a + m * pitch;
+        float acc[DK_MAXE];
 #pragma unroll
-      for (int e = 0; e < DK_MAXE; ++e) acc[e] = 0.0f;
-      for (int c = lane * 8; c < D; c += 256) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(hr + c * 2);
-        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
-        float xv[8];
+        for (int e = 0; e < DK_MAXE; ++e) acc[e] = 0.0f;
+        for (int c = threadIdx.x * 8; c < D; c += DK_CONSUMERS * 32 * 8) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(hr + c * 2);
+          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          float xv[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(hp[i]);
-          xv[2 * i] = f.x;
-          xv[2 * i + 1] = f.y;
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(hp[i]);
+            xv[2 * i] = f.x;
+            xv[2 * i + 1] = f.y;
+          }
+#pragma unroll
+          for (int e = 0; e < DK_MAXE; ++e) {
+            if (e < E) {
+              const float4 w0 = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + c);
+              const float4 w1 = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + c + 4);
+              acc[e] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x + xv[5] * w1.y +
+                        xv[6] * w1.z + xv[7] * w1.w;
+            }
+          }
         }
 #pragma unroll
         for (int e = 0; e < DK_MAXE; ++e) {
           if (e < E) {
-            const float4 w0 = *reinterpret_cast<const float4*>(L->wg + static_cast<long long>(e) * D + c);
-            const float4 w1 = *reinterpret_cast<const float4*>(L->wg + static_cast<long long>(e) * D + c + 4);
-            acc[e] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x + xv[5] * w1.y +
-                      xv[6] * w1.z + xv[7] * w1.w;
+            const float t = warp_sum(acc[e]);
+            if (lane == 0) s_rp[(m * DK_MAXE + e) * DK_CONSUMERS + warp] = t;
           }
         }
       }
+      consumer_sync();
+      if (threadIdx.x < B * E) {
+        const int m = threadIdx.x / E, e = threadIdx.x % E;
+        float t = 0.0f;
 #pragma unroll
-      for (int e = 0; e < DK_MAXE; ++e) acc[e] = warp_sum(acc[e]);
-      if (lane == 0) {
+        for (int w = 0; w < DK_CONSUMERS; ++w) t += s_rp[(m * DK_MAXE + e) * DK_CONSUMERS + w];
+        rt->logits[m][e] = t;
+      }
+      consumer_sync();
+      if (threadIdx.x < B) {
+        const int m = threadIdx.x;
         float mx = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < DK_MAXE; ++e)
-          if (e < E) mx = fmaxf(mx, acc[e]);
-        float ex[DK_MAXE];
+        for (int e = 0; e < E; ++e) mx = fmaxf(mx, rt->logits[m][e]);
         float sum = 0.0f;
-#pragma unroll
-        for (int e = 0; e < DK_MAXE; ++e)
-          if (e < E) {
-            ex[e] = expf(acc[e] - mx);
-            sum += ex[e];
-          }
-#pragma unroll
-        for (int e = 0; e < DK_MAXE; ++e)
-          if (e < E) {
-            rt->logits[warp][e] = acc[e];
-            rt->gates[warp][e] = ex[e] / sum;
-          }
+        for (int e = 0; e < E; ++e) sum += expf(rt->logits[m][e] - mx);
+        for (int e = 0; e < E; ++e) rt->gates[m][e] = expf(rt->logits[m][e] - mx) / sum;
       }
     }
     consumer_sync();
@@ -644,6 +821,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecPa
       mbar_arrive(route_bar);  // release: the producer may read the expert choice
     }
     consumer_sync();
+    DK_STAMP(9);
     const unsigned int amask = rt->amask;
     const int nact = __popc(amask);
     // ---------------------------------------------------------- P5: h1 = SiLU(h Wgate^T) * (h Wup^T) per active expert
@@ -665,7 +843,9 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecPa
         }
       }
     }
+    DK_STAMP(10);
     grid_sync(p.sync, bar_target);
+    DK_STAMP(11);
     // ---------------------------------------------------------- P6: x += gate * (h1 Wdown^T)
     for (int tile = blockIdx.x; tile < nact * tiles_d; tile += G) {
       const int e = __fns(amask, 0, tile / tiles_d + 1);
@@ -685,11 +865,13 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const DecPa
         }
       }
     }
+    DK_STAMP(12);
     grid_sync(p.sync, bar_target);
+    DK_STAMP(13);
   }
   // ------------------------------------------------------------ final RMSNorm (hidden_states[-1])
   if (p.out_norm != nullptr && blockIdx.x == 0) {
-    stage_rows(p, p.x, p.final_norm, s_a, pitch);
+    stage_rows(act, p.x, s_ln_in, lnin_bar, lnin_phase, B, D, p.eps, red);
     consumer_sync();
     for (int i = threadIdx.x; i < B * (D / 8); i += DK_CONSUMERS * 32) {
       const int m = i / (D / 8), c = (i % (D / 8)) * 8;
@@ -717,7 +899,8 @@ static int tmap3(CUtensorMap* out, const void* W, int N, int K, int rows) {
 
 static long long decode_smem_bytes(int D) {
   return 1024 + static_cast<long long>(DK_STAGES) * DK_STAGE_BYTES + static_cast<long long>(DK_MAXB) * (D * 2 + 64) +
-         2LL * DK_RED_FLOATS * 4 + (2 * DK_STAGES + 2) * 8 + static_cast<long long>(sizeof(RouteSmem)) + 64;
+         2LL * DK_RED_FLOATS * 4 + (2 * DK_STAGES + 4) * 8 + static_cast<long long>(sizeof(RouteSmem)) + 128 + 2 * D * 2 +
+         DK_WG_SMEM + 64;
 }
 
 bool llama_decode_supported(const mpl_llama_model& m, const mpl_llama_io& io) {
@@ -802,19 +985,20 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
   p.Tmax = io.Tmax;
   p.pos = io.past_len;
   p.Emax = emax;
+  p.timing_layer = g_timing_layer;
   for (int e = 0; e <= DK_MAXE; ++e) p.cap[e] = cap_by_e[e];
   p.eps = m.rms_eps;
   p.scale = 1.0f / sqrtf(128.0f);
   const int G = num_sms();
-  // split-K over the keys: aim at ~6 work items per CTA, at least 64 keys per split, within the scratch buffer
+  // split-K over the keys: one work item per consumer warp of the grid, at least 32 keys per split, within the scratch
   const int bh = io.B * H;
   const int Tk = io.past_len + 1;
-  int nsplit = (6 * G + bh - 1) / bh;
-  const int by_keys = (Tk + 63) / 64;
+  int nsplit = (G * DK_CONSUMERS) / bh;  // one (b, h, split) per warp, at most one round
+  const int by_keys = (Tk + 31) / 32;
   if (nsplit > by_keys) nsplit = by_keys;
   if (nsplit > 32) nsplit = 32;
   if (nsplit < 1) nsplit = 1;
-  while (nsplit > 1 && static_cast<long long>(bh) * 4 + 256 + static_cast<long long>(bh) * nsplit * 130 * 4 > io.attn_scratch_bytes)
+  while (nsplit > 1 && static_cast<long long>(bh) * 4 + 256 + static_cast<long long>(bh) * nsplit * 132 * 4 > io.attn_scratch_bytes)
     --nsplit;
   p.nsplit = nsplit;
   p.attn_cnt = static_cast<int*>(io.attn_scratch);
@@ -822,13 +1006,18 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
   const int smem = static_cast<int>(decode_smem_bytes(D));
   static int attr_smem = 0;
   if (attr_smem < smem) {
-    if (cudaFuncSetAttribute(llama_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    const cudaError_t e = cudaFuncSetAttribute(llama_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "medplib_b200: decode kernel smem attribute (%d B): %s\n", smem, cudaGetErrorString(e));
       return MPL_ERR_CUDA;
+    }
     attr_smem = smem;
   }
   void* args[] = {&p};
-  if (cudaLaunchCooperativeKernel(reinterpret_cast<void*>(llama_decode_kernel), dim3(G), dim3(DK_THREADS), args, smem,
-                                  st) != cudaSuccess) {
+  const cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(llama_decode_kernel), dim3(G),
+                                                     dim3(DK_THREADS), args, smem, st);
+  if (le != cudaSuccess) {
+    fprintf(stderr, "medplib_b200: decode kernel launch (grid %d, smem %d B): %s\n", G, smem, cudaGetErrorString(le));
     cudaGetLastError();
     return MPL_ERR_CUDA;
   }
@@ -836,3 +1025,15 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
 }
 
 }  // namespace mpl
+
+// Dev tool: layer >= 0 enables per-phase timestamps of that layer in the decode kernel; out (host, [160*16] u64) != NULL
+// copies the last recorded stamps back (after a device synchronise).
+extern "C" int mpl_debug_decode_timing(int layer, unsigned long long* out) {
+  mpl::g_timing_layer = layer;
+  if (out != nullptr) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return MPL_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(out, mpl::g_dk_times, sizeof(unsigned long long) * 160 * mpl::DK_TSLOTS) != cudaSuccess)
+      return MPL_ERR_CUDA;
+  }
+  return MPL_OK;
+}

@@ -241,7 +241,10 @@ def test_decode_kernel_matches_general_path(dev, name, B, T, steps, padded):
         _close(a["last_hidden_state"][same], b["last_hidden_state"][same], 2e-2, f"step {s} hidden")
         k0, k1 = caches[0].k[:, :, :, T + s], caches[1].k[:, :, :, T + s]
         v0, v1 = caches[0].v[:, :, :, T + s], caches[1].v[:, :, :, T + s]
-        assert torch.equal(k0[0], k1[0]) and torch.equal(v0[0], v1[0])  # layer 0: identical inputs -> identical bits
+        # layer 0 sees identical inputs: same RoPE roundings; the RMSNorm statistic is reduced in a different (fixed)
+        # order, so a value may land on the other side of a bf16 rounding boundary once in a while
+        _close(k0[0], k1[0], 2 ** -7, f"step {s} layer-0 k row")
+        _close(v0[0], v1[0], 2 ** -7, f"step {s} layer-0 v row")
         _close(k0[:, same], k1[:, same], 2e-2, f"step {s} k rows")
         _close(v0[:, same], v1[:, same], 2e-2, f"step {s} v rows")
         # keep both caches on the same trajectory for the next step

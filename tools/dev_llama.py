@@ -67,7 +67,42 @@ def probe(B=1, steps=32):
         cache.len = T
 
 
+def timing(B=1, layer=5):
+    """Per-phase durations of one layer of the decode kernel (stamps by consumer thread 0 of every CTA)."""
+    import ctypes
+    import bench
+    from medplib_b200 import _lib
+    lib = _lib.load()
+    m = bench.build_model(dev)
+    eng = m._llama()
+    T = 615
+    cache = eng.new_cache(B, T + 64)
+    eng.forward(torch.randn(B, T, 4096, device=dev).to(bf16), cache)
+    xs = torch.randn(B, 1, 4096, device=dev).to(bf16)
+    for _ in range(3):
+        eng.forward(xs.clone(), cache)
+    lib.mpl_debug_decode_timing(layer, None)
+    eng.forward(xs.clone(), cache)
+    buf = (ctypes.c_ulonglong * (160 * 16))()
+    lib.mpl_debug_decode_timing(-1, buf)
+    t = torch.tensor(list(buf), dtype=torch.float64).view(160, 16)[:148, :14]
+    names = ["P1 stage", "P1 tiles", "bar1", "P2 attn", "bar2", "P3 stage", "P3 tiles", "bar3", "P4 route", "P5 tiles",
+             "bar4", "P6 tiles", "bar5"]
+    d = (t[:, 1:] - t[:, :-1]) / 1e3
+    print(f"B={B} layer {layer}: total {(t[:, 13] - t[:, 0]).mean() / 1e3:.1f} us (per-CTA mean)")
+    for i, n in enumerate(names):
+        print(f"  {n:10s} mean {d[:, i].mean():7.2f} us  min {d[:, i].min():7.2f}  max {d[:, i].max():7.2f}")
+    # phase end skew: when does the LAST CTA finish the phase's work relative to the first stamp
+    t0 = t[:, 0].min()
+    for i in (2, 4, 7, 10, 12):
+        print(f"  work before barrier stamp {i}: first CTA done at {(t[:, i].min() - t0) / 1e3:7.2f} us, last at "
+              f"{(t[:, i].max() - t0) / 1e3:7.2f} us")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "timing":
+        timing(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "probe":
         probe(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
     else:
