@@ -120,6 +120,8 @@ struct Ring {
 
 // routing decision of the current layer, written by consumer thread 0, read by everyone (and by the producer)
 struct RouteSmem {
+  int cnt[DK_MAXE];   // tokens whose first choice is e (before the capacity cut)
+  float me[DK_MAXE];  // sum of the gate probabilities of e
   int kept[DK_MAXE];
   int tok_of_slot[DK_MAXE][DK_MAXB];
   float gate_of_slot[DK_MAXE][DK_MAXB];
@@ -235,14 +237,13 @@ __device__ __forceinline__ float reduce_rows(const float* rbuf, int r, int m) {
   return v;
 }
 
-// Activation staging. The B rows (and the norm weight) are brought into shared memory by bulk-async copies issued by one
-// thread (L2 -> smem at TMA speed, no register staging, not affected by the L1 invalidation of the grid barrier); the
-// RMSNorm then runs smem -> smem, one warp per row, with HF LlamaRMSNorm's roundings w * bf16(x * rstd) and the
-// summation order of rmsnorm_kernel (lane-strided, then the xor-shuffle tree), so the bits agree with the general path.
+// Activation staging: the B rows go global (L2) -> registers -> shared memory with EVERY load of a thread issued before
+// its first store (thread t owns the 16-byte vectors t and t + 256 of every row: one L2 round trip for the whole block,
+// and not queued behind the weight ring in the TMA unit as a bulk copy would be). With a norm weight (already in shared
+// memory, completion on ln_bar / ln_phase) the rows are RMS-normalised on the way with HF LlamaRMSNorm's roundings
+// w * bf16(x * rstd); the sum of squares is reduced lane -> warp (shuffles) -> CTA (fixed order 0..7).
 struct ActStage {
-  uint8_t* s_a;    // [B][pitch]
-  uint64_t* bar;   // completion of the row copies
-  uint32_t phase;  // parity of the next completion
+  uint8_t* s_a;  // [B][pitch]
   int pitch;
 };
 __device__ __forceinline__ void dk_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -251,65 +252,82 @@ __device__ __forceinline__ void dk_bulk_g2s(void* smem_dst, const void* gsrc, ui
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// s_ln: the norm weight, already in shared memory (copied long before, completion on ln_bar / ln_phase), or NULL.
-// All 8 warps share every row (a single warp per row costs ~2 us of pure issue time at D = 4096): thread t owns the
-// 16-byte vectors t, t + 256, ...; the sum of squares is reduced lane -> warp (shuffles) -> CTA (fixed order 0..7).
-__device__ __noinline__ void stage_rows(ActStage& st, const __nv_bfloat16* src, const uint8_t* s_ln, uint64_t* ln_bar,
-                                        uint32_t ln_phase, int B, int D, float eps, float* s_part) {
+__device__ __noinline__ void stage_rows(ActStage st, const __nv_bfloat16* __restrict__ src, const uint8_t* s_ln,
+                                        uint64_t* ln_bar, uint32_t ln_phase, int B, int D, float eps, float* s_part) {
+  constexpr int NV = 2;  // vectors per thread and row: D <= 4096
+  constexpr int RG = 4;  // rows per register group (spills are ruinous here: shared memory leaves almost no L1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // fields copied to locals: the stores below go through a byte pointer, which may alias the struct itself
   uint8_t* const s_a = st.s_a;
-  uint64_t* const bar = st.bar;
   const int pitch = st.pitch;
-  const uint32_t phase = st.phase;
-  st.phase = phase ^ 1;
-  if (threadIdx.x == 0) {
-    fence_proxy_async();  // earlier generic-proxy accesses of s_a are ordered before the async-proxy writes
-    mbar_expect_tx(bar, static_cast<uint32_t>(B * D * 2));
-    for (int m = 0; m < B; ++m)
-      dk_bulk_g2s(s_a + m * pitch, src + static_cast<long long>(m) * D, static_cast<uint32_t>(D * 2), bar);
-  }
-  mbar_wait(bar, phase);
-  if (s_ln == nullptr) return;
-  mbar_wait(ln_bar, ln_phase);
-  for (int m = 0; m < B; ++m) {
-    const uint8_t* row = s_a + m * pitch;
-    float ss = 0.0f;
-    for (int k = threadIdx.x * 8; k < D; k += DK_CONSUMERS * 32 * 8) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(row + k * 2);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  if (s_ln != nullptr) mbar_wait(ln_bar, ln_phase);
+#pragma unroll 1
+  for (int m0 = 0; m0 < B; m0 += RG) {
+    uint4 v[RG][NV];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(h[i]);
-        ss += f.x * f.x + f.y * f.y;
+    for (int r = 0; r < RG; ++r)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int k = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
+        v[r][j] = (m0 + r < B && k < D) ? *reinterpret_cast<const uint4*>(src + static_cast<long long>(m0 + r) * D + k)
+                                        : zero;
+      }
+    if (s_ln != nullptr) {
+      float ss[RG];
+#pragma unroll
+      for (int r = 0; r < RG; ++r) {
+        ss[r] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[r][j]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+            ss[r] += f.x * f.x + f.y * f.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < RG; ++r) ss[r] += __shfl_xor_sync(0xffffffffu, ss[r], o);  // independent trees
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < RG; ++r) s_part[r * DK_CONSUMERS + warp] = ss[r];
+      }
+      consumer_sync();
+#pragma unroll
+      for (int r = 0; r < RG; ++r) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int wi = 0; wi < DK_CONSUMERS; ++wi) tot += s_part[r * DK_CONSUMERS + wi];
+        const float rstd = rsqrtf(tot / static_cast<float>(D) + eps);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int k = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
+          const uint4 w = k < D ? *reinterpret_cast<const uint4*>(s_ln + k * 2) : zero;
+          const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&v[r][j]);
+          const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&w);
+          uint4 o;
+          uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 xf = __bfloat1622float2(xp[i]), wf = __bfloat1622float2(wp[i]);
+            op[i] = pack_bf16(wf.x * bf16_round(xf.x * rstd), wf.y * bf16_round(xf.y * rstd));
+          }
+          v[r][j] = o;
+        }
       }
     }
-    ss = warp_sum(ss);
-    if (lane == 0) s_part[m * DK_CONSUMERS + warp] = ss;
-  }
-  consumer_sync();
-  for (int m = 0; m < B; ++m) {
-    float tot = 0.0f;
 #pragma unroll
-    for (int w = 0; w < DK_CONSUMERS; ++w) tot += s_part[m * DK_CONSUMERS + w];
-    const float rstd = rsqrtf(tot / static_cast<float>(D) + eps);
-    uint8_t* row = s_a + m * pitch;
-    for (int k = threadIdx.x * 8; k < D; k += DK_CONSUMERS * 32 * 8) {
-      const uint4 v = *reinterpret_cast<const uint4*>(row + k * 2);
-      const uint4 w = *reinterpret_cast<const uint4*>(s_ln + k * 2);
-      const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&v);
-      const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&w);
-      uint4 o;
-      uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+    for (int r = 0; r < RG; ++r)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 xf = __bfloat1622float2(xp[i]), wf = __bfloat1622float2(wp[i]);
-        op[i] = pack_bf16(wf.x * bf16_round(xf.x * rstd), wf.y * bf16_round(xf.y * rstd));
+      for (int j = 0; j < NV; ++j) {
+        const int k = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
+        if (m0 + r < B && k < D) *reinterpret_cast<uint4*>(s_a + (m0 + r) * pitch + k * 2) = v[r][j];
       }
-      *reinterpret_cast<uint4*>(row + k * 2) = o;
-    }
+    consumer_sync();  // rows complete for every reader; s_part reusable
   }
-  consumer_sync();  // s_part is reused; the rows are complete for every reader
 }
 
 // L2 prefetch of small per-layer tensors (router weights, norm weights) well before they are needed.
@@ -580,7 +598,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dk_raw) + 1023) & ~uintptr_t(1023));
   const int pitch = p.D * 2 + 64;  // activation row pitch in shared memory (conflict-free 16-byte reads)
   uint8_t* s_a = smem + DK_STAGES * DK_STAGE_BYTES;
-  float* red = reinterpret_cast<float*>(s_a + DK_MAXB * pitch);  // [2][8][16][9], also the attention scratch
+  float* red = reinterpret_cast<float*>(s_a + p.B * pitch);  // [2][8][16][9]; staging / router scratch between phases
+  // (shared memory is sized by the actual B: what it does not take stays L1, which the few spilled values need)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 2 * DK_RED_FLOATS);
   uint64_t* empty_bar = full_bar + DK_STAGES;
   uint64_t* route_bar = empty_bar + DK_STAGES;
@@ -645,7 +664,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
   const int g = lane >> 2;
   unsigned int bar_target = 0;
   int buf = 0;
-  ActStage act{s_a, act_bar, 0u, pitch};
+  const ActStage act{s_a, pitch};
   uint32_t wg_phase = 0, lnin_phase = 0;
   if (threadIdx.x == 0) {  // input norm weight of layer 0
     mbar_expect_tx(lnin_bar, static_cast<uint32_t>(D * 2));
@@ -725,36 +744,60 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
       // (thread t owns k = 8t, 8t + 2048, ...), partial sums reduced lane -> warp -> CTA in a fixed order
       const float* wgp = wg_smem ? s_wg : L->wg;  // generic pointer: shared-memory copy when it fits
       float* s_rp = red + 64;                     // [B][DK_MAXE][8 warps]
-      for (int m = 0; m < B; ++m) {
-        const uint8_t* hr = s_a + m * pitch;
-        float acc[DK_MAXE];
+#pragma unroll 1
+      for (int e0 = 0; e0 < E; e0 += 2)
+#pragma unroll 1
+      for (int m0 = 0; m0 < B; m0 += 4) {
+        float acc[4][2];
 #pragma unroll
-        for (int e = 0; e < DK_MAXE; ++e) acc[e] = 0.0f;
-        for (int c = threadIdx.x * 8; c < D; c += DK_CONSUMERS * 32 * 8) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(hr + c * 2);
-          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
-          float xv[8];
+        for (int m = 0; m < 4; ++m) acc[m][0] = acc[m][1] = 0.0f;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(hp[i]);
-            xv[2 * i] = f.x;
-            xv[2 * i + 1] = f.y;
-          }
+        for (int j = 0; j < 2; ++j) {
+          const int c = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
+          if (c < D) {
+            float4 wv[2][2];
 #pragma unroll
-          for (int e = 0; e < DK_MAXE; ++e) {
-            if (e < E) {
-              const float4 w0 = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + c);
-              const float4 w1 = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + c + 4);
-              acc[e] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x + xv[5] * w1.y +
-                        xv[6] * w1.z + xv[7] * w1.w;
+            for (int ee = 0; ee < 2; ++ee) {
+              const int e = min(e0 + ee, E - 1);
+              wv[ee][0] = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + c);
+              wv[ee][1] = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + c + 4);
+            }
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              if (m0 + m < B) {
+                const uint4 raw = *reinterpret_cast<const uint4*>(s_a + (m0 + m) * pitch + c * 2);
+                const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                float xv[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = __bfloat1622float2(hp[i]);
+                  xv[2 * i] = f.x;
+                  xv[2 * i + 1] = f.y;
+                }
+#pragma unroll
+                for (int ee = 0; ee < 2; ++ee) {
+                  const float4 w0 = wv[ee][0], w1 = wv[ee][1];
+                  acc[m][ee] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x +
+                                xv[5] * w1.y + xv[6] * w1.z + xv[7] * w1.w;
+                }
+              }
             }
           }
         }
 #pragma unroll
-        for (int e = 0; e < DK_MAXE; ++e) {
-          if (e < E) {
-            const float t = warp_sum(acc[e]);
-            if (lane == 0) s_rp[(m * DK_MAXE + e) * DK_CONSUMERS + warp] = t;
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            acc[m][0] += __shfl_xor_sync(0xffffffffu, acc[m][0], o);
+            acc[m][1] += __shfl_xor_sync(0xffffffffu, acc[m][1], o);
+          }
+        if (lane == 0) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m0 + m < B) {
+              s_rp[((m0 + m) * DK_MAXE + e0) * DK_CONSUMERS + warp] = acc[m][0];
+              if (e0 + 1 < E) s_rp[((m0 + m) * DK_MAXE + e0 + 1) * DK_CONSUMERS + warp] = acc[m][1];
+            }
           }
         }
       }
@@ -781,8 +824,9 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
       // top-1 + capacity slots in token order (torch.cumsum), as moe_scan_kernel / moe_route_small_kernel
       const bool moe = L->wg != nullptr;
       const int C = p.cap[E];
-      int cnt[DK_MAXE];
-      float me[DK_MAXE];
+      // (counters live in shared memory: a dynamically indexed local array would sit in local memory, i.e. L2)
+      int* cnt = rt->cnt;
+      float* me = rt->me;
       for (int e = 0; e < E; ++e) cnt[e] = 0, me[e] = 0.0f, rt->kept[e] = 0;
       for (int s = 0; s < B; ++s) {
         int i1 = 0;
@@ -897,8 +941,8 @@ static int tmap3(CUtensorMap* out, const void* W, int N, int K, int rows) {
   return encode_tmap_bf16(out, W, 3, dims, strides, box);
 }
 
-static long long decode_smem_bytes(int D) {
-  return 1024 + static_cast<long long>(DK_STAGES) * DK_STAGE_BYTES + static_cast<long long>(DK_MAXB) * (D * 2 + 64) +
+static long long decode_smem_bytes(int D, int B) {
+  return 1024 + static_cast<long long>(DK_STAGES) * DK_STAGE_BYTES + static_cast<long long>(B) * (D * 2 + 64) +
          2LL * DK_RED_FLOATS * 4 + (2 * DK_STAGES + 4) * 8 + static_cast<long long>(sizeof(RouteSmem)) + 128 + 2 * D * 2 +
          DK_WG_SMEM + 64;
 }
@@ -908,7 +952,7 @@ bool llama_decode_supported(const mpl_llama_model& m, const mpl_llama_io& io) {
   if (io.hidden_states != nullptr || io.moe_noise != nullptr) return false;
   if (m.top_k != 1 || (m.hidden % 64) != 0 || (m.ffn % 64) != 0 || m.hidden != m.n_heads * 128) return false;
   if (io.attn_scratch == nullptr) return false;
-  if (decode_smem_bytes(m.hidden) > 227 * 1024) return false;
+  if (decode_smem_bytes(m.hidden, io.B) > 227 * 1024 || m.hidden > 4096) return false;
   return true;
 }
 
@@ -1003,7 +1047,7 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
   p.nsplit = nsplit;
   p.attn_cnt = static_cast<int*>(io.attn_scratch);
   p.attn_part = reinterpret_cast<float*>(static_cast<char*>(io.attn_scratch) + ((static_cast<long long>(bh) * 4 + 255) & ~255LL));
-  const int smem = static_cast<int>(decode_smem_bytes(D));
+  const int smem = static_cast<int>(decode_smem_bytes(D, io.B));
   static int attr_smem = 0;
   if (attr_smem < smem) {
     const cudaError_t e = cudaFuncSetAttribute(llama_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
