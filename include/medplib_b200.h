@@ -156,6 +156,8 @@ typedef struct {
   void* scratch;             /* decode only, optional: zero-initialised once, >= B*H*4 + B*H*nsplit*520 bytes; enables
                                 split-K over the keys (flash-decoding) so B*H < #SM still fills the GPU */
   long long scratch_bytes;
+  float* lse; /* Tq > 1 only, optional (training): f32 [B*H, Tq] out, log2-domain log-sum-exp of the scaled + masked scores
+                 (row i: max_j s_ij*log2e + log2 sum_j 2^(...)), consumed by mpl_attention_bwd; +inf for a fully masked row */
 } mpl_attn_args;
 int mpl_attention(const mpl_attn_args* args, void* stream);
 
@@ -402,6 +404,94 @@ long long mpl_sam_mask_decoder_workspace_bytes(const mpl_sam_mask_decoder* model
 int mpl_sam_mask_decoder_forward(const mpl_sam_mask_decoder* model, const void* image_embedding,
                                  const void* text_embed, void* low_res_mask, void* iou, void* workspace,
                                  long long workspace_bytes, void* stream);
+
+/* =========================================================================================================
+ * Train step: backward of the LLaMA-MoE stack with LoRA adapters, fused cross-entropy, mask
+ * losses, AdamW. Replaces what torch autograd + peft 0.10 + DeepSpeed run for train_ds_medplib.py:599-625
+ * (model_engine.backward / step). Every dX = dY·W contraction reuses mpl_gemm_bf16 against transposed weight copies
+ * (made once with mpl_transpose_bf16; the frozen 7B weights fit twice in 180 GB).
+ * ========================================================================================================= */
+/* out[c, r] = in[r, c] (bf16; any alignment). */
+int mpl_transpose_bf16(const void* in, long long ld_in, void* out, long long ld_out, int rows, int cols, void* stream);
+
+/* peft LoRA Linear (y = x W^T + s * (x A^T) B^T, A [r,K], B [N,r], r <= 16):
+ *   mpl_lora_down   u[m,j] = scale * sum_k x[m,k] A[j,k]            (u bf16 — the forward's rounding — or f32 [M,r])
+ *   mpl_lora_up_add y[m,n] = bf16(y + bf16(scale * bf16(sum_j u[m,j] Bm[n*sn + j*sr])))   in place
+ *   mpl_rank_wgrad  out[n*sn + j*sr] += scale * sum_m X[m,n] U[m,j]  (f32, atomic)  — dB = s dY^T u, dA = du^T x, dwg
+ * backward: du = s * dY B (lora_down with B^T), dX += du A (lora_up_add with Bm = A, sn = 1, sr = K). */
+int mpl_lora_down(const void* x, long long ldx, const void* A, long long lda, void* u, int u_is_f32, int M, int K, int r,
+                  float scale, void* stream);
+int mpl_lora_up_add(void* y, long long ldy, const void* u, int u_is_f32, const void* Bm, long long bm_stride_n,
+                    long long bm_stride_r, float scale, int M, int N, int r, void* stream);
+int mpl_rank_wgrad(const void* X, long long ldx, const void* U, int u_is_f32, float* out, long long out_stride_n,
+                   long long out_stride_r, float scale, int M, int N, int r, void* stream);
+
+/* LlamaRMSNorm backward: dx = bf16(rstd * (g - xhat * mean(g * xhat)) + add), g = dy * w, xhat = x * rstd;
+ * add (bf16 or NULL) = the gradient arriving on the residual branch; dweight (f32 [D] or NULL) += sum_rows dy * xhat. */
+int mpl_rmsnorm_bwd(const void* x, long long ldx, const void* weight, const void* dy, long long lddy, const void* add,
+                    long long ldadd, void* dx, long long lddx, float* dweight, int rows, int D, float eps, void* stream);
+/* LlamaMLP gate: h = bf16(silu(g)) * u and its backward (dg may alias g, du may alias u). n elements, n % 8 == 0. */
+int mpl_silu_mul(const void* g, const void* u, void* h, long long n, void* stream);
+int mpl_silu_mul_bwd(const void* g, const void* u, const void* dh, void* dg, void* du, long long n, void* stream);
+
+/* Backward of mpl_attention (self-attention over T tokens, no cache; head_dim 64 or 128) given the forward's lse:
+ * dq (f32 [B,T,H,d], zero-initialised by the caller, accumulated with atomics), dk / dv (bf16, own strides).
+ * q and k are the ROTATED tensors the forward saw; mpl_rope_bwd then rotates dq / dk back. */
+typedef struct {
+  const void *q, *k, *v, *o, *d_o;
+  long long q_stride[3], k_stride[3], v_stride[3], o_stride[3]; /* o strides address both o and d_o */
+  const float* lse; /* f32 [B*H, T] from mpl_attn_args.lse */
+  float* delta;     /* f32 [B*H, T] scratch: rowsum(dO * O) */
+  float* dq_f32;
+  void *dk, *dv;
+  long long dk_stride[3], dv_stride[3];
+  int B, H, T, head_dim;
+  float scale;
+  int causal;
+  const unsigned char* kv_mask;
+  long long kv_mask_stride;
+} mpl_attn_bwd_args;
+int mpl_attention_bwd(const mpl_attn_bwd_args* args, void* stream);
+/* dq = bf16(R(-pos) dq_f32) into rows of leading dimension ld; dk rotated in place (see mpl_rope_kv). */
+int mpl_rope_bwd(const float* dq_f32, void* dq, void* dk, long long ld, const void* cos_t, const void* sin_t, int B, int T,
+                 int H, int head_dim, int pos0, void* stream);
+
+/* MoE backward (DeepSpeed top-1 gating autograd):
+ *   mpl_moe_combine_bwd: dy[slot[s,j]] = gate[s,j] * dout[s]; dgate[s,j] = <dout[s], y[slot[s,j]]> (0 when dropped)
+ *   (the dispatch's backward is mpl_moe_combine with unit gates)
+ *   mpl_moe_router_bwd (k = 1): dlogits = softmax-backward of (dgate on the chosen expert + aux_scale * dl_aux/dgates);
+ *   dh[s,:] += dlogits[s,:] wg. dwg = dlogits^T h via mpl_rank_wgrad. */
+int mpl_moe_combine_bwd(const void* dout, long long ldd, const void* y, const int* slot, const float* gate, void* dy,
+                        float* dgate, int S, int k, int D, void* stream);
+int mpl_moe_router_bwd(const float* gates, const int* expert, const int* slot, const float* dgate, const int* exp_counts,
+                       float aux_scale, const float* wg, float* dlogits, void* dh, long long ldh, int S, int D, int E,
+                       void* stream);
+
+/* Shifted cross-entropy of medplib_moe_llama.py:399-421 on fp32 logits: labels i64 [rows] (already shifted; < 0 ignored).
+ * fwd: lse[r], acc[0] += sum of row losses, acc[1] += valid rows (acc zeroed by the caller; loss = acc[0]/acc[1]).
+ * bwd: dlogits bf16 [rows, ldd] = (softmax - onehot) * (*grad_out) / acc[1], columns [V, ldd) zero. */
+int mpl_ce_fwd(const float* logits, long long ld, const long long* labels, int rows, int V, float* lse, float* acc,
+               void* stream);
+int mpl_ce_bwd(const float* logits, long long ld, const long long* labels, int rows, int V, const float* lse,
+               const float* acc, const float* grad_out, void* dlogits, long long ldd, void* stream);
+/* Adjoint of mpl_gather_rows (embedding lookup + multimodal splice): f32 atomic accumulation into the embedding-table
+ * gradient (idx >= 0) and the feature-row gradient (idx <= -2); either target may be NULL. */
+int mpl_scatter_add_rows(const void* dx, long long ldx, const int* idx, float* dtable, long long ld_table, float* dfeats,
+                         long long ld_feats, int rows, int D, void* stream);
+
+/* Optimizer (train_ds_medplib.py:398-411: AdamW betas (0.9, 0.95), weight decay 0, gradient clipping 1.0):
+ * out[0] += sum g^2; AdamW on fp32 master weights + moments writing the bf16 / f32 parameter in place, with the clip
+ * coefficient min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)) applied on the fly (sumsq NULL: no clipping). */
+int mpl_sumsq_f32(const float* g, long long n, float* out, void* stream);
+int mpl_adamw(float* master, float* m, float* v, const float* grad, void* param, int param_is_bf16, long long n, float lr,
+              float beta1, float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
+              float grad_scale, void* stream);
+
+/* The four mask losses of model/MedPLIB.py:26-124 for ONE mask in one pass: pred bf16 [n] logits, gt f32 [n] in {0,1},
+ * pred_iou bf16 scalar -> out4 = {sigmoid_ce_loss, dice_loss, MaskIoULoss, FocalLoss}; sums6 (optional) = the six
+ * reductions (sum bce, sum p, sum t, sum p t, focal_pos, focal_neg). */
+int mpl_mask_losses(const void* pred, const float* gt, const void* pred_iou, long long n, float* out4, float* sums6,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,19 @@ class AttnArgs(ctypes.Structure):
         ("scale", c_float), ("causal", c_int),
         ("kv_mask", c_void_p), ("kv_mask_stride", c_ll), ("rel_h", c_void_p), ("rel_w", c_void_p),
         ("rel_kh", c_int), ("rel_kw", c_int), ("tk_dev", c_void_p), ("scratch", c_void_p), ("scratch_bytes", c_ll),
+        ("lse", c_void_p),
+    ]
+
+
+class AttnBwdArgs(ctypes.Structure):
+    """mpl_attn_bwd_args (include/medplib_b200.h)."""
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("o", c_void_p), ("d_o", c_void_p),
+        ("q_stride", c_ll * 3), ("k_stride", c_ll * 3), ("v_stride", c_ll * 3), ("o_stride", c_ll * 3),
+        ("lse", c_void_p), ("delta", c_void_p), ("dq_f32", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
+        ("dk_stride", c_ll * 3), ("dv_stride", c_ll * 3),
+        ("B", c_int), ("H", c_int), ("T", c_int), ("head_dim", c_int), ("scale", c_float), ("causal", c_int),
+        ("kv_mask", c_void_p), ("kv_mask_stride", c_ll),
     ]
 
 
@@ -175,6 +188,9 @@ EXPORTS = [
     "mpl_llama_workspace_bytes", "mpl_llama_forward", "mpl_clip_workspace_bytes", "mpl_clip_forward",
     "mpl_sam_encoder_workspace_bytes", "mpl_sam_encoder_forward", "mpl_sam_mask_decoder_workspace_bytes",
     "mpl_sam_mask_decoder_forward",
+    "mpl_transpose_bf16", "mpl_lora_down", "mpl_lora_up_add", "mpl_rank_wgrad", "mpl_rmsnorm_bwd", "mpl_silu_mul",
+    "mpl_silu_mul_bwd", "mpl_attention_bwd", "mpl_rope_bwd", "mpl_moe_combine_bwd", "mpl_moe_router_bwd", "mpl_ce_fwd",
+    "mpl_ce_bwd", "mpl_scatter_add_rows", "mpl_sumsq_f32", "mpl_adamw", "mpl_mask_losses",
 ]
 _LL_RET = {"mpl_launch_count", "mpl_llama_workspace_bytes", "mpl_clip_workspace_bytes", "mpl_sam_encoder_workspace_bytes",
            "mpl_sam_mask_decoder_workspace_bytes"}

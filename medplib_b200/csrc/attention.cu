@@ -38,6 +38,7 @@ struct AttnParams {
   const int* tk_dev;             // optional device-side Tk (decode under CUDA graphs)
   float* scratch;                // decode split-K partials: [B*H] int counters (zeroed) then [B*H, nsplit, D+2] floats
   int nsplit;
+  float* lse;                    // prefill only, optional: [B*H, Tq] log2-domain log-sum-exp of the scaled scores (training)
 };
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -231,6 +232,8 @@ __global__ void __launch_bounds__(FA_THREADS) flash_fwd_kernel(const AttnParams 
     float sres = row_sum[rr];
     sres += __shfl_xor_sync(0xffffffffu, sres, 1);
     sres += __shfl_xor_sync(0xffffffffu, sres, 2);
+    if (p.lse != nullptr && t4 == 0 && qrow[rr] < p.Tq)
+      p.lse[(static_cast<long long>(b) * p.H + h) * p.Tq + qrow[rr]] = sres > 0.0f ? row_max[rr] + log2f(sres) : INFINITY;
     row_sum[rr] = sres > 0.0f ? 1.0f / sres : 0.0f;
   }
   __nv_bfloat16* og = p.o + b * p.o_sb + h * p.o_sh;
@@ -442,6 +445,7 @@ extern "C" int mpl_attention(const mpl_attn_args* a, void* stream_) {
   p.kv_mask_stride = a->kv_mask_stride > 0 ? a->kv_mask_stride : a->Tk;
   p.rel_h = a->rel_h; p.rel_w = a->rel_w; p.rel_kh = a->rel_kh; p.rel_kw = a->rel_kw;
   p.tk_dev = a->tk_dev;
+  p.lse = a->lse;
   // 16-byte vector access on every row
   const long long strides[] = {p.q_sb, p.q_st, p.q_sh, p.k_sb, p.k_st, p.k_sh, p.v_sb, p.v_st, p.v_sh};
   for (long long s : strides)

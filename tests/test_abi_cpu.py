@@ -33,7 +33,7 @@ def test_struct_sizes_match_header():
     import subprocess
     import tempfile
     from medplib_b200 import _lib
-    pairs = {"mpl_gemm_args": _lib.GemmArgs, "mpl_attn_args": _lib.AttnArgs, "mpl_moe_route_args": _lib.MoeRouteArgs,
+    pairs = {"mpl_gemm_args": _lib.GemmArgs, "mpl_attn_args": _lib.AttnArgs, "mpl_attn_bwd_args": _lib.AttnBwdArgs, "mpl_moe_route_args": _lib.MoeRouteArgs,
              "mpl_llama_layer": _lib.LlamaLayer, "mpl_llama_model": _lib.LlamaModel, "mpl_llama_io": _lib.LlamaIO,
              "mpl_clip_layer": _lib.ClipLayer, "mpl_clip_model": _lib.ClipModel, "mpl_sam_block": _lib.SamBlock,
              "mpl_sam_encoder": _lib.SamEncoder, "mpl_sam_attn": _lib.SamAttn,
