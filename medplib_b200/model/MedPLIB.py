@@ -401,6 +401,10 @@ class MedPLIBForCausalLM(PreTrainedModel):
     def _llama(self):
         if "llama" not in self._eng:
             self._check_ready()
+            if any(hasattr(mod, "lora_A") for mod in self.model.layers.modules()):
+                raise _lib.MplError("LoRA adapters are attached: the inference engines read the base weights only; "
+                                    "call medplib_b200.train.merge_lora(model) first (the reference merges before "
+                                    "evaluation too)")
             self._eng["llama"] = engine.LlamaEngine(self._params(), llama_dims(self.config), "model.")
         return self._eng["llama"]
 
@@ -592,6 +596,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
         idx = torch.tensor([p + [-1] * (T - len(p)) for p in plans], dtype=torch.int32).to(dev)
         feats_all = torch.cat(feat_blocks + ([torch.stack(extra_rows)] if extra_rows else []), dim=0).contiguous()
         embeds = ops.gather_rows(idx.reshape(-1), self.model.embed_tokens.weight, feats_all, D=D).view(len(plans), T, D)
+        self._splice_idx = idx.reshape(-1)  # adjoint of the splice (embed_tokens gradient) in the train step
         lab_t = None
         if labels is not None:
             lab_t = torch.tensor([l + [IGNORE_INDEX] * (T - len(l)) for l in new_labels], dtype=labels.dtype, device=dev)
@@ -615,6 +620,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
         """medplib_moe_llama.py:324-438. past_key_values is a medplib_b200.engine.KVCache (or None)."""
         if output_attentions:
             raise _lib.MplError("attention maps are never materialised by the fused attention kernels")
+        self._splice_idx = None
         if inputs_embeds is None:
             input_ids, attention_mask, past_key_values, inputs_embeds, labels = \
                 self.prepare_inputs_labels_for_multimodal(input_ids, attention_mask, past_key_values, labels, images,
@@ -623,6 +629,9 @@ class MedPLIBForCausalLM(PreTrainedModel):
         if inputs_embeds is None:
             idx = input_ids.reshape(-1).to(torch.int32)
             inputs_embeds = ops.gather_rows(idx, self.model.embed_tokens.weight).view(*input_ids.shape, -1)
+            self._splice_idx = idx
+        if labels is not None:
+            return self._lm_forward_train(inputs_embeds, attention_mask, labels, _unused.get("moe_noise"))
         eng = self._llama()
         B, T, D = inputs_embeds.shape
         cache = past_key_values
@@ -645,14 +654,44 @@ class MedPLIBForCausalLM(PreTrainedModel):
         moe_losses = list(out["l_aux"].unbind(0)) if out["l_aux"] is not None else []
         moe_loss = self.router_aux_loss_coef * sum(moe_losses) if moe_losses else None
         loss = None
-        if labels is not None:
-            raise _lib.MplError("training losses (autograd through the fused stack) are not part of this build yet; "
-                                "inference paths: evaluate(), generate(), model_forward(inference=True)")
         hs = out["hidden_states"] if output_hidden_states else None
         return MoECausalLMOutputWithPast(loss=loss, moe_loss=moe_loss, logits=logits,
                                          past_key_values=cache if use_cache else None,
                                          hidden_states=hs if hs is not None else (hidden,),
                                          moe_loss_list=moe_losses)
+
+    # ------------------------------------------------------------------ train step (medplib_b200/train.py)
+    def trainer(self, **hyper):
+        """The Trainer (gradient arena + optimizer + tape nodes) bound to the current set of trainable parameters.
+        Rebuilt when that set changes (attach_lora / requires_grad edits) or when hyper-parameters are passed."""
+        from .. import train as _train
+        tr = getattr(self, "_trainer", None)
+        if tr is None or hyper or tr._sig != _train.Trainer.signature(self):
+            self._trainer = tr = _train.Trainer(self, **hyper)
+        return tr
+
+    def refresh_trained(self):
+        """After an optimizer step: engines that hold REPACKED copies of trainable weights (mask decoder) are rebuilt."""
+        self._eng.pop("sam_dec", None)
+
+    def _lm_forward_train(self, inputs_embeds, attention_mask, labels, moe_noise=None):
+        """Training branch of medplib_moe_llama.py:324-438: activations kept, loss = shifted CE + coef * sum(l_aux),
+        differentiable through medplib_b200.train's tape nodes (loss.backward() fills the gradient arena)."""
+        tr = self.trainer()
+        kv_mask = None
+        if attention_mask is not None and not bool(attention_mask.all()):
+            kv_mask = attention_mask
+        hidden, l_aux = tr.stack_hidden(inputs_embeds, kv_mask=kv_mask, moe_noise=moe_noise,
+                                        splice_idx=self._splice_idx)
+        self._fire_gate_hooks(tr.last_gate_logits)
+        loss, logits = tr.head_ce(hidden, labels)
+        moe_losses = list(l_aux.unbind(0)) if l_aux.numel() > 0 else []
+        moe_loss = None
+        if moe_losses:
+            moe_loss = self.router_aux_loss_coef * l_aux.sum()
+            loss = loss + moe_loss
+        return MoECausalLMOutputWithPast(loss=loss, moe_loss=moe_loss, logits=logits, past_key_values=None,
+                                         hidden_states=(hidden,), moe_loss_list=moe_losses)
 
     def _fire_gate_hooks(self, gate_logits):
         """vqa_infer.py:157-165 registers forward hooks on the `wg` Linears to read the router logits."""
@@ -662,7 +701,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
         for layer in self.model.layers:
             if isinstance(layer.mlp, M.MoE):
                 wg = layer.mlp.deepspeed_moe.gate.wg
-                for hook in wg._forward_hooks.values():
+                for hook in list(wg._forward_hooks.values()):
                     hook(wg, (None,), gate_logits[li])
                 li += 1
 
@@ -846,8 +885,9 @@ class MedPLIBForCausalLM(PreTrainedModel):
                       seg_flag=True, valid_mask_bool=None, rp_flag=False, valid_region_masks_bool=None, **kwargs):
         """MedPLIB.py:364-572. inference=True is the single-pass grounding forward ([SEG] in the prompt)."""
         if not inference:
-            raise _lib.MplError("model_forward(inference=False) needs the training losses + autograd through the fused "
-                                "stack, which this build does not provide yet; use inference=True / evaluate()")
+            return self._model_forward_train(images, images_clip, input_ids, region_masks, labels, attention_mask,
+                                             masks_list, label_list, resize_list, seg_flag, valid_mask_bool,
+                                             valid_region_masks_bool, **kwargs)
         with torch.no_grad():
             if seg_flag:
                 image_embeddings = self.expand_embedding(self.get_visual_embs(images), valid_mask_bool)
@@ -868,6 +908,46 @@ class MedPLIBForCausalLM(PreTrainedModel):
             sizes = [tuple(l.shape) for l in label_list]
             pred_masks, _ = self._decode_masks(pred_embeddings, image_embeddings, resize_list, sizes)
             return {"pred_masks": pred_masks, "gt_masks": masks_list}
+
+    def _model_forward_train(self, images, images_clip, input_ids, region_masks, labels, attention_mask, masks_list,
+                             label_list, resize_list, seg_flag, valid_mask_bool, valid_region_masks_bool, **kwargs):
+        """MedPLIB.py:403-572 with inference=False: CE (+ router aux) loss, and with seg_flag the four mask losses of
+        every [SEG] row; returns the reference's 10-key dict. out["loss"].backward() fills trainer().arena."""
+        if seg_flag:
+            image_embeddings = self.expand_embedding(self.get_visual_embs(images), valid_mask_bool)
+            seg_token_mask = self.build_seg_token_mask(input_ids, image_token_lengths=kwargs.get("image_token_lengths"))
+        out = self._lm_forward(images=images_clip, attention_mask=attention_mask, input_ids=input_ids, labels=labels,
+                               region_masks=region_masks, valid_region_masks_bool=valid_region_masks_bool,
+                               mask_images=kwargs.get("mask_images"),
+                               image_token_types=kwargs.get("image_token_types"), moe_noise=kwargs.get("moe_noise"))
+        ce_loss = out.loss * self.ce_loss_weight
+        if not seg_flag:
+            z = torch.zeros_like(ce_loss)
+            return {"loss": ce_loss, "ce_loss": ce_loss, "mask_bce_loss": z, "mask_dice_loss": z, "mask_loss": z,
+                    "unscale_mask_bce_loss": z, "unscale_mask_dice_loss": z, "unscale_mask_loss": z,
+                    "unscale_mask_iou_loss": z, "unscale_mask_focal_loss": z}
+        from .. import mask_train
+        hidden = out.hidden_states[-1]
+        seg_token_mask = seg_token_mask[:, :hidden.shape[1]]
+        tr = self.trainer()
+        rows = mask_train.select_rows(hidden, seg_token_mask)
+        pred_embeddings = mask_train.text_hidden_fcs(tr, self.model.text_hidden_fcs[0], rows)
+        if kwargs.get("icl_image_counts") is not None and len(masks_list) > 0:
+            pred_embeddings = pred_embeddings[-len(masks_list):]
+        sizes = [tuple(l.shape) for l in label_list]
+        sums = mask_train.mask_head_losses(tr, self, pred_embeddings, image_embeddings, resize_list, sizes, masks_list)
+        num_masks = sums["num_masks"]
+        un_bce = sums["bce"] / (num_masks + 1e-8)
+        un_dice = sums["dice"] / (num_masks + 1e-8)
+        un_iou = sums["iou"] / (num_masks + 1e-8)
+        un_focal = sums["focal"] / (num_masks + 1e-8)
+        bce, dice = self.bce_loss_weight * un_bce, self.dice_loss_weight * un_dice
+        iou, focal = self.iou_loss_weight * un_iou, self.focal_loss_weight * un_focal
+        mask_loss = bce + dice + iou + focal
+        return {"loss": ce_loss + mask_loss, "ce_loss": ce_loss, "mask_bce_loss": bce, "mask_dice_loss": dice,
+                "mask_loss": mask_loss, "unscale_mask_bce_loss": un_bce, "unscale_mask_dice_loss": un_dice,
+                "unscale_mask_loss": un_bce + un_dice + un_iou + un_focal, "unscale_mask_iou_loss": un_iou,
+                "unscale_mask_focal_loss": un_focal}
 
     def evaluate(self, images_clip, images, input_ids, resize_list, original_size_list, region_masks=[],
                  valid_region_masks_bool=[], max_new_tokens=512, tokenizer=None, attention_mask=None,

@@ -213,13 +213,14 @@ def moe_route(h, wg, k, capacity, noise=None):
     return out
 
 
-def moe_dispatch(h, slot, rows):
-    """xperm[slot[s,j]] = h[s]; returns xperm bf16 [rows, D] (rows = E * capacity; unused rows are uninitialised)."""
+def moe_dispatch(h, slot, rows, out=None):
+    """xperm[slot[s,j]] = h[s]; returns xperm bf16 [rows, D] (rows = E * capacity; unused rows keep what `out` held,
+    uninitialised when it is allocated here)."""
     lib = _lib.load()
     h2 = _rows(h)
     S, D = h2.shape
     k = slot.shape[1]
-    xperm = torch.empty((rows, D), dtype=bf16, device=h.device)
+    xperm = torch.empty((rows, D), dtype=bf16, device=h.device) if out is None else out
     _lib.check(lib.mpl_moe_dispatch(_ptr(h2), _ll(h2.stride(0)), _ptr(slot), _ptr(xperm), S, k, D, _stream()),
                "mpl_moe_dispatch")
     return xperm

@@ -1,0 +1,624 @@
+"""Train step of the hot path: LoRA adapters, the flat fp32 gradient arena, the LLaMA-MoE
+stack with a hand-scheduled backward, the lm_head + shifted cross-entropy tail, bucketed data-parallel all-reduce and
+fused AdamW. Replaces what peft 0.10 + torch autograd + DeepSpeed ZeRO-2 run for train_ds_medplib.py:294-302,398-439,
+599-625 around model/medplib/model/language_model/medplib_moe_llama.py:110-438.
+
+Design (B200-first, 180 GB per GPU):
+* No gradient checkpointing: the reference recomputes every decoder layer (medplib_moe_llama.py:252-263) because 80 GB
+  cards force it; here the activations of all 32 layers (~1 GB per layer at 8x639 tokens) stay resident, so a step is
+  fwd + bwd, not fwd + recompute + bwd.
+* Frozen base weights are kept twice (W and W^T, made once with mpl_transpose_bf16) so every dX = dY.W contraction is
+  the same K-major tcgen05 GEMM as the forward; q,k,v share one [D,3D] transposed matrix (one dgrad GEMM with K = 3D).
+* All trainable parameters' gradients live in ONE flat fp32 arena in backward-completion order; kernels accumulate
+  into it directly (no per-parameter .grad tensors, no bf16 gradient rounding), the data-parallel all-reduce runs over
+  arena buckets on NCCL as the backward passes them, and AdamW + gradient clipping run over the arena.
+* torch.autograd is only the tape between three coarse nodes (stack, lm_head+CE, mask head); every arithmetic kernel
+  is ours. There is no eager fallback: CPU tensors raise MplError.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from . import train_ops as T
+from .model import modules as M
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+LORA_EXCLUDE = ("visual_model", "vision_tower", "mm_projector")  # train_ds_medplib.py:272-281
+
+
+# ---------------------------------------------------------------------------------------------------- LoRA adapters
+def find_linear_layers(model, lora_target_modules):
+    """train_ds_medplib.py:265-291: names of nn.Linear modules matched by substring, vision parts excluded."""
+    names = set()
+    for name, module in model.named_modules():
+        if isinstance(module, nn.Linear) and all(x not in name for x in LORA_EXCLUDE) \
+                and any(x in name for x in lora_target_modules) and "lora_" not in name:
+            names.add(name)
+    return sorted(names)
+
+
+def attach_lora(model, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=("q_proj", "v_proj")):
+    """What get_peft_model(model, LoraConfig(r, lora_alpha, target_modules, lora_dropout, bias="none")) does to the
+    module tree (train_ds_medplib.py:294-302), without peft: every matched nn.Linear gets ``lora_A.default`` /
+    ``lora_B.default`` Linear children (peft's names; A kaiming-uniform, B zero), every other parameter is frozen.
+    The matched Linear keeps its own ``weight`` (peft moves it to ``base_layer.weight`` — see INTEGRATION.md)."""
+    if lora_dropout:
+        raise _lib.MplError("lora_dropout > 0 is not built yet (pass --lora_dropout 0)")
+    if isinstance(target_modules, str):
+        target_modules = target_modules.split(",")
+    names = find_linear_layers(model, list(target_modules))
+    for p in model.parameters():
+        p.requires_grad = False
+    mods = dict(model.named_modules())
+    for name in names:
+        lin = mods[name]
+        w = lin.weight
+        A = nn.Linear(lin.in_features, r, bias=False, device=w.device, dtype=w.dtype)
+        Bm = nn.Linear(r, lin.out_features, bias=False, device=w.device, dtype=w.dtype)
+        nn.init.kaiming_uniform_(A.weight, a=math.sqrt(5))
+        nn.init.zeros_(Bm.weight)
+        lin.lora_A = nn.ModuleDict({"default": A})
+        lin.lora_B = nn.ModuleDict({"default": Bm})
+        lin.scaling = {"default": lora_alpha / r}
+        lin.r = {"default": r}
+    if hasattr(model, "refresh_engines"):
+        model.refresh_engines()
+    return names
+
+
+def set_trainable(model, sft_modules):
+    """train_ds_medplib.py:316-326: parameters whose name contains one of the substrings become trainable."""
+    if isinstance(sft_modules, str):
+        sft_modules = [s for s in sft_modules.split(",") if s]
+    for n, p in model.named_parameters():
+        if any(x in n for x in sft_modules):
+            p.requires_grad = True
+
+
+class _Lora:
+    __slots__ = ("A", "B", "s", "gA", "gB")
+
+    def __init__(self, lin, arena):
+        self.A, self.B = lin.lora_A["default"].weight, lin.lora_B["default"].weight
+        self.s = float(lin.scaling["default"])
+        self.gA, self.gB = arena.of(self.A), arena.of(self.B)
+        if self.A.shape[0] > 16:
+            raise _lib.MplError("LoRA rank > 16 is not built (the reference trains with r = 8)")
+
+
+def _lora_of(lin, arena):
+    return _Lora(lin, arena) if hasattr(lin, "lora_A") else None
+
+
+# ------------------------------------------------------------------------------------------------- gradient arena
+class GradArena:
+    """One flat fp32 buffer holding the gradient of every trainable parameter, in the order given (the order the
+    backward completes them, so bucket i can be all-reduced while bucket i+1 is still being produced)."""
+
+    ALIGN = 64
+
+    def __init__(self, named_params, device):
+        self.names, self.params, self.offsets = [], [], []
+        off = 0
+        for n, p in named_params:
+            self.names.append(n)
+            self.params.append(p)
+            self.offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.flat = torch.zeros(max(off, 1), dtype=f32, device=device)
+        self._views = {id(p): self.flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)}
+        self._end = {id(p): o + p.numel() for p, o in zip(self.params, self.offsets)}
+
+    def of(self, p):
+        """fp32 gradient view of parameter p, or None when p is frozen."""
+        return self._views.get(id(p)) if p is not None else None
+
+    def end_of(self, p):
+        return self._end[id(p)]
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def grads(self):
+        return {n: self._views[id(p)] for n, p in zip(self.names, self.params)}
+
+    def export_grads(self):
+        """Materialise p.grad (param dtype) for code that expects torch-style gradients (DeepSpeed / torch.optim)."""
+        for p in self.params:
+            p.grad = self._views[id(p)].to(p.dtype)
+
+
+class BucketReducer:
+    """Data-parallel gradient exchange: all-reduce(mean) of the arena in fixed-size buckets, each
+    launched asynchronously as soon as the backward has passed its end, on the process group's own stream."""
+
+    def __init__(self, arena, bucket_elems=64 << 20, group=None):
+        import torch.distributed as dist
+        self.dist, self.arena, self.group = dist, arena, group
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.world = dist.get_world_size(group) if self.on else 1
+        n = arena.numel
+        self.bounds = [(a, min(a + bucket_elems, n)) for a in range(0, n, bucket_elems)] or [(0, 0)]
+        self.reset()
+
+    def reset(self):
+        self.next, self.work = 0, []
+
+    def ready(self, upto):
+        """Everything in arena[:upto] is final: launch the buckets that end at or before `upto`."""
+        if not self.on:
+            return
+        while self.next < len(self.bounds) and self.bounds[self.next][1] <= upto:
+            a, b = self.bounds[self.next]
+            self.work.append(self.dist.all_reduce(self.arena.flat[a:b], op=self.dist.ReduceOp.SUM, group=self.group,
+                                                  async_op=True))
+            self.next += 1
+
+    def finish(self):
+        """Launch what is left and make the current stream wait for every bucket. Returns 1/world (the mean factor the
+        optimizer folds into its gradient scale)."""
+        self.ready(self.arena.numel)
+        for w in self.work:
+            w.wait()
+        self.reset()
+        return 1.0 / self.world
+
+
+class FusedAdamW:
+    """AdamW over the arena (train_ds_medplib.py:398-411: betas (0.9, 0.95), weight decay 0, clipping 1.0) with fp32
+    master weights + moments, writing the bf16 / fp32 parameters in place. Clipping uses the global gradient norm
+    computed on the device (no .item())."""
+
+    def __init__(self, arena, lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0):
+        self.arena, self.lr, self.betas, self.eps, self.wd, self.max_norm = arena, lr, betas, eps, weight_decay, \
+            max_grad_norm
+        dev = arena.flat.device
+        self.master = torch.zeros_like(arena.flat)
+        for p, o in zip(arena.params, arena.offsets):
+            self.master[o:o + p.numel()].copy_(p.detach().reshape(-1).float())
+        self.m = torch.zeros_like(arena.flat)
+        self.v = torch.zeros_like(arena.flat)
+        self.sumsq = torch.zeros(1, dtype=f32, device=dev)
+        self.t = 0
+
+    def step(self, grad_scale=1.0, lr=None):
+        a = self.arena
+        self.t += 1
+        sumsq = None
+        if self.max_norm and self.max_norm > 0:
+            self.sumsq.zero_()
+            T.sumsq(a.flat, self.sumsq)
+            sumsq = self.sumsq
+        lr = self.lr if lr is None else lr
+        for p, o in zip(a.params, a.offsets):
+            n = p.numel()
+            T.adamw(self.master[o:o + n], self.m[o:o + n], self.v[o:o + n], a.flat[o:o + n], p.data, lr, self.betas[0],
+                    self.betas[1], self.eps, self.wd, self.t, sumsq_dev=sumsq, max_norm=self.max_norm or 0.0,
+                    grad_scale=grad_scale)
+
+    def grad_norm(self, grad_scale=1.0):
+        return self.sumsq.sqrt() * grad_scale
+
+
+# --------------------------------------------------------------------------------------- LLaMA-MoE stack, fwd + bwd
+class _Layer:
+    pass
+
+
+def _frozen(w, what):
+    if w.requires_grad:
+        raise _lib.MplError(f"full fine-tuning of {what} is not built: the reference trains the decoder through LoRA "
+                            "(train_ds_medplib.py:294-302); keep the base weight frozen")
+    return w
+
+
+class LlamaTrainStack:
+    """Training forward (activations kept) and backward of the decoder stack of a MedPLIBForCausalLM."""
+
+    def __init__(self, model, arena, reducer=None):
+        cfg = model.config
+        self.arena, self.reducer = arena, reducer
+        self.D, self.H, self.F = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
+        self.hd = self.D // self.H
+        self.eps = cfg.rms_norm_eps
+        moe = getattr(cfg, "moe", None) or {}
+        self.cf = float(moe.get("capacity_factor", 1.0) or 1.0)
+        self.min_cap = int(moe.get("min_capacity", 0) or 0)
+        self.top_k = int(moe.get("top_k_experts", 1) or 1)
+        self.aux_coef = float(getattr(model, "router_aux_loss_coef", 0.0) or 0.0)
+        self.use_rts = True  # DeepSpeed top1gating default (use_rts=True): random token selection on overflow
+        from .engine import rope_tables
+        from .model.config import llama_dims
+        dims = llama_dims(cfg)
+        self.rope_len = int(dims.get("max_position_embeddings", 4096))
+        self.cos, self.sin = rope_tables(self.hd, self.rope_len, dims.get("rope_theta", 1e4),
+                                         model.lm_head.weight.device)
+        self.norm_w = model.model.norm.weight
+        self.layers = []
+        for li, layer in enumerate(model.model.layers):
+            L = _Layer()
+            at = layer.self_attn
+            L.ln1, L.ln2 = layer.input_layernorm.weight, layer.post_attention_layernorm.weight
+            L.wq, L.wk, L.wv, L.wo = (_frozen(at.q_proj.weight, "q_proj"), _frozen(at.k_proj.weight, "k_proj"),
+                                      _frozen(at.v_proj.weight, "v_proj"), _frozen(at.o_proj.weight, "o_proj"))
+            L.lo = {n: _lora_of(getattr(at, n), arena) for n in ("q_proj", "k_proj", "v_proj", "o_proj")}
+            D = self.D
+            L.wqkvT = torch.empty((D, 3 * D), dtype=bf16, device=L.wq.device)
+            for j, w in enumerate((L.wq, L.wk, L.wv)):
+                T.transpose(w.detach(), out=L.wqkvT[:, j * D:(j + 1) * D])
+            L.woT = T.transpose(L.wo.detach())
+            if isinstance(layer.mlp, M.MoE):
+                if self.top_k != 1:
+                    raise _lib.MplError("the train step is built for top-1 gating (scripts/train_stage4.sh); top-2 "
+                                        "backward is not")
+                L.wg = layer.mlp.deepspeed_moe.gate.wg.weight
+                mlps = list(layer.mlp.deepspeed_moe.experts.deepspeed_experts)
+            else:
+                L.wg = None
+                mlps = [layer.mlp]
+            L.E = len(mlps)
+            L.w_gate = [_frozen(m.gate_proj.weight, "gate_proj") for m in mlps]
+            L.w_up = [_frozen(m.up_proj.weight, "up_proj") for m in mlps]
+            L.w_down = [_frozen(m.down_proj.weight, "down_proj") for m in mlps]
+            L.w_gateT = [T.transpose(w.detach()) for w in L.w_gate]
+            L.w_upT = [T.transpose(w.detach()) for w in L.w_up]
+            L.w_downT = [T.transpose(w.detach()) for w in L.w_down]
+            L.lo_mlp = [{n: _lora_of(getattr(m, n), arena) for n in ("gate_proj", "up_proj", "down_proj")}
+                        for m in mlps]
+            # arena offset below which everything is final once this layer's backward is done
+            ends = [arena.end_of(p) for p in layer.parameters() if arena.of(p) is not None]
+            L.arena_end = max(ends) if ends else None
+            self.layers.append(L)
+
+    # ------------------------------------------------------------------ helpers
+    def _lora_fwd(self, lo, x, y):
+        """y += s * (x A^T) B^T in peft's bf16 rounding; returns a = x A^T (bf16 [M, r])."""
+        a = T.lora_down(x, lo.A)
+        T.lora_up_add(y, a, lo.B, lo.s)
+        return a
+
+    def _lora_bwd(self, lo, x, a, dy, dx):
+        """Gradients of y = ... + s (x A^T) B^T: dB, dA into the arena, dx += du A."""
+        if lo.gB is not None:
+            T.rank_wgrad(dy, a, lo.gB, scale=lo.s)
+        du = T.lora_down(dy, T.transpose(lo.B.detach()), scale=lo.s, out_f32=True)
+        if lo.gA is not None:
+            T.rank_wgrad(x, du, lo.gA, transposed=True)
+        T.lora_up_add(dx, du, lo.A, 1.0, transposed=True)
+
+    def capacity(self, S, E):
+        return ops.moe_capacity(S, E, self.cf, self.min_cap, 1)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, B, Tn, kv_mask=None, moe_noise=None):
+        """x bf16 [B*Tn, D] spliced input embeddings. Returns (hidden [S,D] after the final norm, l_aux [n_moe] f32,
+        gate_logits list, saved)."""
+        D, H, hd, F_, eps = self.D, self.H, self.hd, self.F, self.eps
+        S = B * Tn
+        dev = x.device
+        if Tn > self.rope_len:
+            raise _lib.MplError("sequence longer than max_position_embeddings")
+        cos, sin = self.cos, self.sin
+        scale = 1.0 / math.sqrt(hd)
+        km = kv_mask.to(torch.uint8).contiguous() if kv_mask is not None else None
+        saved, l_aux, gate_logits = [], [], []
+        for li, L in enumerate(self.layers):
+            sv = {"x": x}
+            n1 = ops.rmsnorm(x, L.ln1, eps)
+            qkv = torch.empty((S, 3 * D), dtype=bf16, device=dev)
+            views = [qkv[:, j * D:(j + 1) * D] for j in range(3)]
+            ops.linear(n1, [L.wq, L.wk, L.wv], out=views)
+            for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+                if L.lo[nm] is not None:
+                    sv["a_" + nm] = self._lora_fwd(L.lo[nm], n1, views[j])
+            q5 = qkv.view(B, Tn, 3, H, hd)
+            q, k, v = q5[:, :, 0], q5[:, :, 1], q5[:, :, 2]
+            ops.rope_kv(q, k, None, cos, sin, 0)
+            o, lse = T.attention_fwd_lse(q, k, v, scale, causal=True, kv_mask=km)
+            o2 = o.view(S, D)
+            if L.lo["o_proj"] is None:
+                h1 = ops.linear(o2, L.wo, residual=x)
+            else:
+                y = ops.linear(o2, L.wo)
+                sv["a_o_proj"] = self._lora_fwd(L.lo["o_proj"], o2, y)
+                h1 = ops.add(x, y)
+            n2 = ops.rmsnorm(h1, L.ln2, eps)
+            sv.update(n1=n1, qkv=qkv, o=o, lse=lse, h1=h1, n2=n2)
+            E = L.E
+            if L.wg is not None:
+                C = self.capacity(S, E)
+                noise = moe_noise[li] if moe_noise is not None else None
+                if noise is None and self.use_rts:
+                    noise = torch.rand((S, E), dtype=f32, device=dev)
+                route = ops.moe_route(n2, L.wg.detach(), 1, C, noise)
+                l_aux.append(route["l_aux"])
+                gate_logits.append(route["logits"])
+                rows = E * C
+                xin = torch.zeros((rows, D), dtype=bf16, device=dev)
+                ops.moe_dispatch(n2, route["slot"], rows, out=xin)
+                sv.update(route=route, C=C)
+            else:
+                C, rows, xin, route = S, S, n2, None
+            g = torch.zeros((rows, F_), dtype=bf16, device=dev) if route is not None else \
+                torch.empty((rows, F_), dtype=bf16, device=dev)
+            u = torch.zeros_like(g) if route is not None else torch.empty_like(g)
+            y = torch.zeros((rows, D), dtype=bf16, device=dev) if route is not None else None
+            a_mlp = []
+            for e in range(E):
+                r0, r1 = e * C, (e + 1) * C
+                md = route["kept"][e:e + 1] if route is not None else None
+                force = "tc" if md is not None else None
+                ops.linear(xin[r0:r1], L.w_gate[e], out=g[r0:r1], m_dev=md, force=force)
+                ops.linear(xin[r0:r1], L.w_up[e], out=u[r0:r1], m_dev=md, force=force)
+                am = {}
+                for nm, buf in (("gate_proj", g), ("up_proj", u)):
+                    if L.lo_mlp[e][nm] is not None:
+                        am[nm] = self._lora_fwd(L.lo_mlp[e][nm], xin[r0:r1], buf[r0:r1])
+                a_mlp.append(am)
+            h = T.silu_mul(g, u)
+            for e in range(E):
+                r0, r1 = e * C, (e + 1) * C
+                md = route["kept"][e:e + 1] if route is not None else None
+                lo = L.lo_mlp[e]["down_proj"]
+                if route is None:
+                    if lo is None:
+                        x_next = ops.linear(h, L.w_down[0], residual=h1)
+                    else:
+                        yd = ops.linear(h, L.w_down[0])
+                        a_mlp[0]["down_proj"] = self._lora_fwd(lo, h, yd)
+                        x_next = ops.add(h1, yd)
+                else:
+                    ops.linear(h[r0:r1], L.w_down[e], out=y[r0:r1], m_dev=md, force="tc")
+                    if lo is not None:
+                        a_mlp[e]["down_proj"] = self._lora_fwd(lo, h[r0:r1], y[r0:r1])
+            if route is not None:
+                x_next = ops.moe_combine(y, route["slot"], route["gate"], residual=h1)
+            sv.update(xin=xin, g=g, u=u, h=h, y=y, a_mlp=a_mlp)
+            saved.append(sv)
+            x = x_next
+        hidden = ops.rmsnorm(x, self.norm_w, eps)
+        la = torch.cat(l_aux) if l_aux else None
+        return hidden, la, gate_logits, dict(layers=saved, x_last=x, B=B, T=Tn, kv_mask=km)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, saved, dhidden, aux_scale=0.0):
+        """dhidden bf16 [S, D] (gradient of the loss w.r.t. the normed last hidden state). Accumulates every trainable
+        parameter's gradient into the arena; returns dx0 bf16 [S, D] (gradient w.r.t. the input embeddings)."""
+        D, H, hd, eps = self.D, self.H, self.hd, self.eps
+        B, Tn, km = saved["B"], saved["T"], saved["kv_mask"]
+        S = B * Tn
+        dev = dhidden.device
+        ar = self.arena
+        cos, sin = self.cos, self.sin
+        scale = 1.0 / math.sqrt(hd)
+        dx = T.rmsnorm_bwd(saved["x_last"], self.norm_w, dhidden, eps, dweight=ar.of(self.norm_w))
+        if self.reducer is not None and ar.of(self.norm_w) is not None:
+            self.reducer.ready(ar.end_of(self.norm_w))
+        for li in range(len(self.layers) - 1, -1, -1):
+            L, sv = self.layers[li], saved["layers"][li]
+            E, C, route = L.E, sv.get("C", S), sv.get("route")
+            g, u, h, xin = sv["g"], sv["u"], sv["h"], sv["xin"]
+            rows = g.shape[0]
+            if route is not None:
+                dy, dgate = T.moe_combine_bwd(dx, sv["y"], route["slot"], route["gate"], rows)
+                dh = torch.zeros_like(h)
+            else:
+                dy, dgate = dx, None
+                dh = torch.empty_like(h)
+            for e in range(E):
+                r0, r1 = e * C, (e + 1) * C
+                md = route["kept"][e:e + 1] if route is not None else None
+                force = "tc" if md is not None else None
+                ops.linear(dy[r0:r1], L.w_downT[e], out=dh[r0:r1], m_dev=md, force=force)
+                lo = L.lo_mlp[e]["down_proj"]
+                if lo is not None:
+                    self._lora_bwd(lo, h[r0:r1], sv["a_mlp"][e]["down_proj"], dy[r0:r1], dh[r0:r1])
+            T.silu_mul_bwd(g, u, dh)  # g <- dg, u <- du
+            dxin = torch.zeros_like(xin) if route is not None else torch.empty_like(xin)
+            for e in range(E):
+                r0, r1 = e * C, (e + 1) * C
+                md = route["kept"][e:e + 1] if route is not None else None
+                force = "tc" if md is not None else None
+                ops.linear(g[r0:r1], L.w_gateT[e], out=dxin[r0:r1], m_dev=md, force=force)
+                ops.linear(u[r0:r1], L.w_upT[e], out=dxin[r0:r1], residual=dxin[r0:r1], m_dev=md, force=force)
+                for nm, buf in (("gate_proj", g), ("up_proj", u)):
+                    lo = L.lo_mlp[e][nm]
+                    if lo is not None:
+                        self._lora_bwd(lo, xin[r0:r1], sv["a_mlp"][e][nm], buf[r0:r1], dxin[r0:r1])
+            if route is not None:
+                ones = torch.ones_like(route["gate"])
+                dn2 = ops.moe_combine(dxin, route["slot"], ones)
+                dlogits = T.moe_router_bwd(route, dgate, L.wg.detach(), dn2, aux_scale=aux_scale)
+                gwg = ar.of(L.wg)
+                if gwg is not None:
+                    T.rank_wgrad(sv["n2"], dlogits, gwg, transposed=True)
+            else:
+                dn2 = dxin
+            dh1 = T.rmsnorm_bwd(sv["h1"], L.ln2, dn2, eps, add=dx, dweight=ar.of(L.ln2))
+            # attention block
+            o2 = sv["o"].view(S, D)
+            do = ops.linear(dh1, L.woT)
+            if L.lo["o_proj"] is not None:
+                self._lora_bwd(L.lo["o_proj"], o2, sv["a_o_proj"], dh1, do)
+            qkv = sv["qkv"]
+            q5 = qkv.view(B, Tn, 3, H, hd)
+            dqkv = torch.empty_like(qkv)
+            d5 = dqkv.view(B, Tn, 3, H, hd)
+            dq32 = T.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], sv["o"], do.view(B, Tn, H, hd), sv["lse"], scale,
+                                   d5[:, :, 1], d5[:, :, 2], causal=True, kv_mask=km)
+            T.rope_bwd(dq32, d5[:, :, 0], d5[:, :, 1], cos, sin, 0)
+            dn1 = ops.linear(dqkv, L.wqkvT)
+            for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+                if L.lo[nm] is not None:
+                    self._lora_bwd(L.lo[nm], sv["n1"], sv["a_" + nm], dqkv[:, j * D:(j + 1) * D], dn1)
+            dx = T.rmsnorm_bwd(sv["x"], L.ln1, dn1, eps, add=dh1, dweight=ar.of(L.ln1))
+            saved["layers"][li] = None  # free this layer's activations
+            if self.reducer is not None and L.arena_end is not None:
+                self.reducer.ready(L.arena_end)
+        return dx
+
+
+# ------------------------------------------------------------------------------------------- autograd tape nodes
+class _StackFn(torch.autograd.Function):
+    """hidden = decoder_stack(embeds). `anchor` is a dummy leaf that makes the output require grad."""
+
+    @staticmethod
+    def forward(ctx, anchor, tr, embeds, B, Tn, kv_mask, moe_noise, splice_idx):
+        hidden, l_aux, gate_logits, saved = tr.stack.forward(embeds, B, Tn, kv_mask, moe_noise)
+        ctx.tr, ctx.saved, ctx.splice_idx = tr, saved, splice_idx
+        tr.last_gate_logits = gate_logits
+        if l_aux is None:
+            l_aux = torch.zeros(0, dtype=f32, device=embeds.device)
+        return hidden.view(B, Tn, -1), l_aux
+
+    @staticmethod
+    def backward(ctx, dhidden, dl_aux):
+        tr = ctx.tr
+        D = ctx.saved["x_last"].shape[-1]
+        aux = 0.0
+        if dl_aux is not None and dl_aux.numel() > 0 and tr.stack.aux_coef != 0.0:
+            aux = float(dl_aux[0])  # d loss / d l_aux (same for every layer); one host read per step, only with aux loss
+        if dhidden is None:
+            dh = torch.zeros((ctx.saved["B"] * ctx.saved["T"], D), dtype=bf16, device=tr.anchor.device)
+        else:
+            dh = dhidden.to(bf16).reshape(-1, D).contiguous()
+        dx0 = tr.stack.backward(ctx.saved, dh, aux_scale=aux)
+        g_emb = tr.arena.of(tr.embed_weight)
+        if g_emb is not None and ctx.splice_idx is not None:
+            T.scatter_add_rows(dx0, ctx.splice_idx, dtable=g_emb)
+            if tr.reducer is not None:
+                tr.reducer.ready(tr.arena.end_of(tr.embed_weight))
+        ctx.saved = None
+        return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 7
+
+
+class _HeadCEFn(torch.autograd.Function):
+    """medplib_moe_llama.py:381-421: fp32 logits = lm_head(hidden); shifted cross-entropy over the valid labels."""
+
+    @staticmethod
+    def forward(ctx, hidden, tr, labels):
+        Bn, Tn, D = hidden.shape
+        h2 = hidden.reshape(-1, D)
+        W = tr.lm_head_weight
+        logits = ops.linear(h2, W.detach(), out_dtype=f32)
+        shift = torch.full_like(labels, -100)
+        shift[:, :-1] = labels[:, 1:]
+        lab = shift.reshape(-1).contiguous()
+        lse, acc = T.ce_fwd(logits, lab)
+        ctx.tr, ctx.h2, ctx.logits, ctx.lab, ctx.lse, ctx.acc = tr, h2, logits, lab, lse, acc
+        ctx.shape = hidden.shape
+        loss = acc[0] / acc[1]
+        logits3 = logits.view(Bn, Tn, -1)
+        ctx.mark_non_differentiable(logits3)
+        return loss, logits3
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits):
+        tr, h2, logits = ctx.tr, ctx.h2, ctx.logits
+        W = tr.lm_head_weight
+        V, D = W.shape
+        S = h2.shape[0]
+        Vp = (V + 7) // 8 * 8
+        dl = T.ce_bwd(logits, ctx.lab, ctx.lse, ctx.acc, grad_out=dloss.reshape(1).float().contiguous(), ldd=Vp)
+        WT = T.transpose(W.detach(), ld_out=Vp)  # [D, Vp], pad columns zero
+        dh = ops.linear(dl, WT)
+        gW = tr.arena.of(W)
+        if gW is not None:
+            Sp = (S + 7) // 8 * 8
+            dlT = T.transpose(dl, ld_out=Sp)[:V]  # [V, Sp]
+            hT = T.transpose(h2, ld_out=Sp)  # [D, Sp]
+            ops.linear(dlT, hT, out_dtype=f32, out=gW, force="tc")
+            if tr.reducer is not None:
+                tr.reducer.ready(tr.arena.end_of(W))
+        ctx.logits = ctx.h2 = None
+        return dh.view(ctx.shape), None, None
+
+
+class Trainer:
+    """Owns the arena, the reducer, the optimizer and the tape nodes for one MedPLIBForCausalLM. Created lazily by
+    the model on its first training forward (model.trainer()), or explicitly to pick hyper-parameters:
+
+        tr = model.trainer(lr=3e-4)          # after attach_lora / set_trainable, model in bf16 on the GPU
+        out = model(**batch); out["loss"].backward(); tr.step()
+    """
+
+    def __init__(self, model, lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
+                 bucket_elems=64 << 20, group=None):
+        model._check_ready()
+        self.model = model
+        dev = model.lm_head.weight.device
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if not named:
+            raise _lib.MplError("no trainable parameters (call attach_lora / set_trainable first)")
+        self.arena = GradArena(self._order(model, named), dev)
+        self.reducer = BucketReducer(self.arena, bucket_elems, group)
+        self.stack = LlamaTrainStack(model, self.arena, self.reducer)
+        self.opt = FusedAdamW(self.arena, lr, betas, eps, weight_decay, max_grad_norm)
+        self.lm_head_weight = model.lm_head.weight
+        self.embed_weight = model.model.embed_tokens.weight
+        self.anchor = torch.zeros(1, dtype=f32, device=dev, requires_grad=True)
+        self.loss_scale = 1.0
+        self.last_gate_logits = None
+        self._sig = self.signature(model)
+
+    @staticmethod
+    def signature(model):
+        return tuple((n, p.data_ptr()) for n, p in model.named_parameters() if p.requires_grad)
+
+    @staticmethod
+    def _order(model, named):
+        """Backward-completion order: mask head + text_hidden_fcs + lm_head + final norm, decoder layers last-to-first,
+        then embed_tokens and everything else (region adapter, projector-side modules)."""
+        def key(item):
+            n = item[0]
+            if "visual_model" in n or "text_hidden_fcs" in n:
+                return (0, 0)
+            if n.startswith("lm_head"):
+                return (1, 0)
+            if n == "model.norm.weight":
+                return (2, 0)
+            if n.startswith("model.layers."):
+                return (3, -int(n.split(".")[2]))
+            if "embed_tokens" in n:
+                return (4, 0)
+            return (5, 0)
+        return sorted(named, key=key)
+
+    # tape
+    def stack_hidden(self, embeds, kv_mask=None, moe_noise=None, splice_idx=None):
+        B, Tn, D = embeds.shape
+        x = embeds.to(bf16).reshape(B * Tn, D).contiguous()
+        return _StackFn.apply(self.anchor, self, x, B, Tn, kv_mask, moe_noise, splice_idx)
+
+    def head_ce(self, hidden, labels):
+        return _HeadCEFn.apply(hidden, self, labels)
+
+    def zero_grad(self):
+        self.arena.zero_()
+        self.reducer.reset()
+
+    def step(self, lr=None):
+        """all-reduce what is left (mean over the data-parallel group), clip, AdamW, zero the arena."""
+        scale = self.reducer.finish()
+        self.opt.step(grad_scale=scale, lr=lr)
+        self.zero_grad()
+        self.model.refresh_trained()
+
+
+def merge_lora(model):
+    """Offline tool (what peft's merge_and_unload does before the reference evaluates a trained model): fold every
+    adapter into its base weight, W += scaling * B A, and remove the adapter modules. Not on the hot path."""
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, nn.Linear) and hasattr(mod, "lora_A"):
+                A, Bm = mod.lora_A["default"].weight, mod.lora_B["default"].weight
+                mod.weight.add_((Bm.float() @ A.float() * mod.scaling["default"]).to(mod.weight.dtype))
+                del mod.lora_A, mod.lora_B, mod.scaling, mod.r
+    if hasattr(model, "refresh_engines"):
+        model.refresh_engines()
+    model._trainer = None
+    return model

@@ -65,13 +65,24 @@ def decoder_attention_mask(attention_mask, T, past, dtype):
     return (m + pad).clamp(min=minv)
 
 
+def linear(sd, name, x):
+    """nn.Linear (bias-free), or — when the state dict carries adapter weights for it — peft==0.10.0
+    ``tuners/lora/layer.py::Linear.forward`` (un-vendored, pinned at /root/reference/requirements.txt:80; call site
+    train_ds_medplib.py:294-302): result = base(x) + lora_B(lora_A(dropout(x))) * scaling, dropout inactive here."""
+    y = F.linear(x, sd[name + ".weight"])
+    a = sd.get(name + ".lora_A.default.weight")
+    if a is not None:
+        y = y + F.linear(F.linear(x, a), sd[name + ".lora_B.default.weight"]) * sd["lora_scaling"]
+    return y
+
+
 def attention(sd, prefix, x, cfg, mask, position_ids, past_kv, cos, sin):
     """LlamaAttention.forward eager path (4.31). Returns (out, (k, v)) with k,v [B,H,T_total,d]."""
     B, T, D = x.shape
     H, hd = cfg["num_heads"], cfg["hidden_size"] // cfg["num_heads"]
-    q = F.linear(x, sd[prefix + "self_attn.q_proj.weight"]).view(B, T, H, hd).transpose(1, 2)
-    k = F.linear(x, sd[prefix + "self_attn.k_proj.weight"]).view(B, T, H, hd).transpose(1, 2)
-    v = F.linear(x, sd[prefix + "self_attn.v_proj.weight"]).view(B, T, H, hd).transpose(1, 2)
+    q = linear(sd, prefix + "self_attn.q_proj", x).view(B, T, H, hd).transpose(1, 2)
+    k = linear(sd, prefix + "self_attn.k_proj", x).view(B, T, H, hd).transpose(1, 2)
+    v = linear(sd, prefix + "self_attn.v_proj", x).view(B, T, H, hd).transpose(1, 2)
     q, k = apply_rope(q, k, cos, sin, position_ids)
     if past_kv is not None:
         k = torch.cat([past_kv[0], k], dim=2)
@@ -80,17 +91,12 @@ def attention(sd, prefix, x, cfg, mask, position_ids, past_kv, cos, sin):
     w = w + mask
     w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
     o = torch.matmul(w, v).transpose(1, 2).reshape(B, T, D)
-    return F.linear(o, sd[prefix + "self_attn.o_proj.weight"]), (k, v)
+    return linear(sd, prefix + "self_attn.o_proj", o), (k, v)
 
 
-def mlp(x, gate_w, up_w, down_w):
-    """LlamaMLP.forward: down(silu(gate(x)) * up(x))."""
-    return F.linear(F.silu(F.linear(x, gate_w)) * F.linear(x, up_w), down_w)
-
-
-def expert_weights(sd, prefix, e):
-    p = f"{prefix}mlp.deepspeed_moe.experts.deepspeed_experts.{e}."
-    return sd[p + "gate_proj.weight"], sd[p + "up_proj.weight"], sd[p + "down_proj.weight"]
+def mlp(sd, p, x):
+    """LlamaMLP.forward: down(silu(gate(x)) * up(x)); p = module path incl. trailing dot."""
+    return linear(sd, p + "down_proj", F.silu(linear(sd, p + "gate_proj", x)) * linear(sd, p + "up_proj", x))
 
 
 def layer_mlp(sd, prefix, x, cfg, training, rts_uniform=None, gumbel=None):
@@ -99,14 +105,13 @@ def layer_mlp(sd, prefix, x, cfg, training, rts_uniform=None, gumbel=None):
     Returns (out, l_aux or None, exp_counts or None, router logits or None)."""
     wg_key = prefix + "mlp.deepspeed_moe.gate.wg.weight"
     if wg_key not in sd:
-        return mlp(x, sd[prefix + "mlp.gate_proj.weight"], sd[prefix + "mlp.up_proj.weight"],
-                   sd[prefix + "mlp.down_proj.weight"]), None, None, None
+        return mlp(sd, prefix + "mlp.", x), None, None, None
     m = cfg["moe"]
     E = sd[wg_key].shape[0]
-    experts = [expert_weights(sd, prefix, e) for e in range(E)]
+    experts = [f"{prefix}mlp.deepspeed_moe.experts.deepspeed_experts.{e}." for e in range(E)]
     cf = m["capacity_factor"] if training else m["eval_capacity_factor"]
     out, l_aux, exp_counts, logits = _moe.moe_layer(
-        x, sd[wg_key], [lambda t, w=w: mlp(t, *w) for w in experts], k=m["top_k_experts"], capacity_factor=cf,
+        x, sd[wg_key], [lambda t, p=p: mlp(sd, p, t) for p in experts], k=m["top_k_experts"], capacity_factor=cf,
         min_capacity=m["min_capacity"], rts_uniform=rts_uniform, gumbel=gumbel)
     return out, l_aux, exp_counts, logits
 

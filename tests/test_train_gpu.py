@@ -1,0 +1,171 @@
+"""GPU parity of the train step: losses and EVERY trainable parameter's gradient of
+MedPLIBForCausalLM.forward(inference=False) — hand-written backward kernels through the C ABI — against torch.autograd
+over the CPU oracle (oracle/train.py) in fp32 on the same bf16-rounded weights; then one optimizer step against
+torch.optim.AdamW on the oracle's gradients.
+
+Stated tolerances: losses within 2e-2 relative; a gradient tensor within 8e-2 * max|ref| (bf16 activations and bf16
+activation gradients through 2 decoder layers vs an fp32 reference; LoRA / router / norm gradients are fp32
+accumulations of bf16 products). Routing decisions (expert index, kept / dropped) are compared bit-exactly first."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+SEG = 299
+W = dict(ce=1.0, bce=2.0, dice=0.5, iou=1.0, focal=1.0)
+SFT = "wg,lm_head,embed_tokens,mask_decoder,text_hidden_fcs,region_fea_adapter"
+
+
+def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,down_proj", sft=SFT):
+    import test_model_gpu as tm
+    from medplib_b200 import train
+    m, _, ocfg = tm.build(dev)
+    m.config.moe["capacity_factor"] = cf
+    m.config.moe["router_aux_loss_coef"] = aux
+    m.router_aux_loss_coef = aux
+    m.ce_loss_weight, m.bce_loss_weight, m.dice_loss_weight = W["ce"], W["bce"], W["dice"]
+    m.iou_loss_weight, m.focal_loss_weight = W["iou"], W["focal"]
+    names = train.attach_lora(m, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=lora_targets)
+    assert len(names) == 2 * 2 + 2 * 2 * 3
+    train.set_trainable(m, sft)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "lora_B" in n:  # peft starts B at zero (dA would be identically 0): test a trained-looking adapter
+                p.copy_((torch.randn(p.shape, generator=g) * 0.05).to(p.dtype))
+            if "wg.weight" in n:
+                p.mul_(2.0)  # decisive routing: bf16-vs-fp32 activation noise must not flip an argmax
+    m.train()
+    sd = {k: v.detach().cpu().float() for k, v in m.state_dict().items()}
+    sd.update({k: v.detach().cpu().float() for k, v in m.named_buffers()})
+    sd["lora_scaling"] = 2.0
+    ocfg["llama"]["moe"] = dict(m.config.moe)
+    return m, sd, ocfg
+
+
+def batch(B=2, n_text=14, seg=False, pad=False):
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(3, 290, (B, n_text), generator=g)
+    ids[:, 2] = -200
+    labels = ids.clone()
+    labels[:, :6] = -100
+    am = torch.ones_like(ids, dtype=torch.bool)
+    if seg:
+        ids[:, 9] = SEG
+        labels[:, 9] = SEG
+    if pad:
+        am[1, -3:] = False
+        labels[1, -3:] = -100
+    clip_img = torch.randn(B, 3, 56, 56, generator=g).to(bf16)
+    sam_img = torch.randn(B, 3, 256, 256, generator=g).to(bf16)
+    gts = [(torch.rand(70, 90, generator=g) > 0.6).float() for _ in range(B)]
+    return ids, labels, am, clip_img, sam_img, gts
+
+
+def oracle_run(sd, ocfg, b, seg_flag, noise):
+    from oracle import train as otrain
+    ids, labels, am, clip_img, sam_img, gts = b
+    leaves = {}
+    for k, v in sd.items():
+        if isinstance(v, torch.Tensor) and v.is_floating_point():
+            leaves[k] = v
+    out, aux = otrain.train_losses(sd, ocfg, clip_img.float(), sam_img.float(), ids, labels, am, gts,
+                                   [tuple(g.shape) for g in gts], [(256, 256)] * len(gts), SEG, W, seg_flag=seg_flag,
+                                   rts_uniforms=noise)
+    return out, aux
+
+
+def _cmp(name, got, ref, rtol, report):
+    got, ref = got.detach().float().cpu(), ref.detach().float()
+    scale = max(ref.abs().max().item(), 1e-8)
+    err = (got - ref).abs().max().item()
+    report.append((err / scale, name, err, scale))
+    return err <= rtol * scale
+
+
+def run_case(dev, seg_flag, cf, pad, aux):
+    m, sd, ocfg = build(dev, cf=cf, aux=aux)
+    b = batch(seg=seg_flag, pad=pad)
+    ids, labels, am, clip_img, sam_img, gts = b
+    S = ids.shape[0] * (ids.shape[1] - 1 + 16)
+    g = torch.Generator().manual_seed(11)
+    noise = [torch.rand(S, 2, generator=g) for _ in range(2)]
+    train_names = [n for n, p in m.named_parameters() if p.requires_grad]
+    for n in train_names:
+        sd[n].requires_grad_(True)
+    ref, aux_o = oracle_run(sd, ocfg, b, seg_flag, noise)
+    ref["loss"].backward()
+    tr = m.trainer(lr=1e-2)
+    tr.zero_grad()
+    out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=None,
+            labels=labels.to(dev), attention_mask=am.to(dev), offset=None, masks_list=[x.to(dev) for x in gts],
+            label_list=[x.to(dev) for x in gts], resize_list=[(256, 256)] * len(gts), inference=False,
+            seg_flag=seg_flag, moe_noise=[x.to(dev) for x in noise])
+    assert set(out) == set(ref)
+    # routing must agree exactly, otherwise gradients are not comparable
+    for l, lg in enumerate(tr.last_gate_logits):
+        assert torch.equal(lg.argmax(-1).cpu(), aux_o["gate_logits"][l].argmax(-1)), f"routing differs in layer {l}"
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    report, bad = [], []
+    for k in ref:
+        r, o = float(ref[k]), float(out[k])
+        assert abs(o - r) <= 2e-2 * max(abs(r), 1e-3) + 1e-4, f"{k}: {o} vs oracle {r}"
+    grads = tr.arena.grads()
+    assert set(grads) == set(train_names)
+    for n in train_names:
+        rg = sd[n].grad
+        if rg is None:
+            rg = torch.zeros_like(sd[n])
+        if rg.abs().max() == 0:
+            assert grads[n].abs().max().item() == 0, f"{n}: gradient should be exactly zero"
+            continue
+        if not _cmp(n, grads[n], rg, 8e-2, report):
+            bad.append(n)
+    report.sort(reverse=True)
+    print("\nworst gradient errors (err/scale, name, err, scale):")
+    for r in report[:12]:
+        print("  %.3e  %s  %.3e  %.3e" % r)
+    assert not bad, f"gradients out of tolerance: {bad[:8]} ({len(bad)} of {len(train_names)})"
+    return m, tr, sd, train_names
+
+
+@pytest.mark.parametrize("cf,pad,aux", [(1.5, False, 0.01), (0.6, True, 0.0)])
+def test_text_loss_and_gradients(dev, cf, pad, aux):
+    """seg_flag=False: CE (+ aux) loss; LoRA q,v,gate,up,down of every expert, wg, lm_head, embed_tokens gradients.
+    cf=0.6 forces capacity overflow (tokens dropped by injected RTS uniforms); pad=True adds key padding."""
+    run_case(dev, False, cf, pad, aux)
+
+
+def test_grounding_loss_and_gradients(dev):
+    """seg_flag=True: + BCE / Dice / IoU / Focal on the decoded masks; gradients reach the mask decoder,
+    text_hidden_fcs and, through the [SEG] hidden rows, the decoder stack."""
+    run_case(dev, True, 1.5, False, 0.01)
+
+
+def test_optimizer_step_matches_adamw(dev):
+    """Trainer.step(): global-norm clipping at 1.0 + AdamW(0.9, 0.95) on fp32 masters vs torch.optim.AdamW fed the
+    oracle's gradients."""
+    m, tr, sd, names = run_case(dev, False, 1.5, False, 0.0)
+    params = [sd[n] for n in names]
+    before = {n: sd[n].detach().clone() for n in names}
+    torch.nn.utils.clip_grad_norm_(params, 1.0)
+    opt = torch.optim.AdamW(params, lr=1e-2, betas=(0.9, 0.95), weight_decay=0.0, eps=1e-8)
+    opt.step()
+    tr.step()
+    torch.cuda.synchronize()
+    got = dict(m.named_parameters())
+    worst = 0.0
+    for n in names:
+        delta_ref = (sd[n].detach() - before[n])
+        delta = got[n].detach().float().cpu() - before[n]
+        if delta_ref.abs().max() == 0:
+            continue
+        # Adam's first step moves every weight by ~lr * sign(g): compare the update where the gradient is not noise
+        big = sd[n].grad.abs() > 0.2 * sd[n].grad.abs().max()
+        err = ((delta - delta_ref).abs()[big]).max().item()
+        tol = 0.25 * 1e-2 + (2 ** -8) * before[n].abs().max().item()  # + one bf16 ulp of the stored parameter
+        worst = max(worst, err / tol)
+        assert err <= tol, f"{n}: update differs by {err:.3e} (tol {tol:.3e})"
+    assert float(tr.arena.flat.abs().max()) == 0.0  # arena zeroed for the next step
+    print(f"\nworst update error / tolerance: {worst:.3f}")
