@@ -493,6 +493,38 @@ int mpl_adamw(float* master, float* m, float* v, const float* grad, void* param,
 int mpl_mask_losses(const void* pred, const float* gt, const void* pred_iou, long long n, float* out4, float* sums6,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Grounding-head backward (train step with seg_flag): what torch autograd runs for model/MedPLIB.py:456-559 over
+ * text_hidden_fcs (:153-164), model/segment_anything_med2d/modeling/mask_decoder.py:71-153, transformer.py:16-244,
+ * postprocess_masks (:682-701) and the four mask losses (:26-124). Latency-bound small kernels (< 1 GFLOP per mask).
+ * --------------------------------------------------------------------------------------------------------- */
+/* C[m*ldc + n] (+)= sum_k A[m*a_stride_m + k*a_stride_k] * B[k*b_stride_k + n*b_stride_n]; A, B bf16 or f32; C bf16
+ * (overwritten) or f32 (accumulate = 1 adds). Strides express every transposition: dX = dY W, dW += dY^T X,
+ * outer products. */
+int mpl_gemm_small(const void* A, int a_is_f32, long long a_stride_m, long long a_stride_k, const void* B, int b_is_f32,
+                   long long b_stride_k, long long b_stride_n, void* C, int c_is_f32, long long ldc, int accumulate,
+                   int M, int N, int K, void* stream);
+/* out[n] += sum_m X[m*ld + n] (bias gradients; M = 1: accumulate a bf16 / f32 vector into an fp32 gradient). */
+int mpl_col_sum(const void* X, int x_is_f32, long long ld, float* out, int M, int N, void* stream);
+/* nn.LayerNorm / LayerNorm2d (rows = NHWC pixels) backward; dweight / dbias f32 [D] accumulated (NULL: skipped). */
+int mpl_layernorm_bwd(const void* x, long long ldx, const void* weight, const void* dy, long long lddy, void* dx,
+                      long long lddx, float* dweight, float* dbias, int rows, int D, float eps, void* stream);
+/* y = act(x) and dx = act'(x) dy for MPL_ACT_GELU (erf form; x = the input) / MPL_ACT_RELU (x = input or output). */
+int mpl_act_fwd(const void* x, void* y, long long n, int act, void* stream);
+int mpl_act_bwd(const void* x, const void* dy, void* dx, long long n, int act, void* stream);
+/* Backward of softmax(scale q k^T) v for the mask decoder's attentions (transformer.py:185-244): q [Tq, ld],
+ * k / v [Tk, ld], head h = columns [h*head_dim, (h+1)*head_dim), head_dim <= 32; one CTA per head. */
+int mpl_attn_small_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                       const void* d_o, long long ldo, void* dq, long long lddq, void* dk, long long lddk, void* dv,
+                       long long lddv, int Tq, int Tk, int H, int head_dim, float scale, void* stream);
+/* Adjoint of mpl_bilinear_resize: dy [N, Hout, Wout] (bf16 or f32) -> dx bf16 [N, Hin, Win] (strides given). */
+int mpl_bilinear_resize_bwd(const void* dy, int dy_is_f32, int Hout, int Wout, void* dx, long long dx_stride_n,
+                            long long dx_stride_y, int Hin, int Win, int N, void* stream);
+/* Backward of mpl_mask_losses: dloss4 = d total / d {bce, dice, iou, focal} (device f32[4]), sums6 from the forward
+ * -> dpred bf16 [n], dpred_iou f32[1] (optional). */
+int mpl_mask_losses_bwd(const void* pred, const float* gt, const void* pred_iou, const float* sums6, const float* dloss4,
+                        long long n, void* dpred, float* dpred_iou, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -231,6 +231,7 @@ class LlamaTrainStack:
         self.top_k = int(moe.get("top_k_experts", 1) or 1)
         self.aux_coef = float(getattr(model, "router_aux_loss_coef", 0.0) or 0.0)
         self.use_rts = True  # DeepSpeed top1gating default (use_rts=True): random token selection on overflow
+        self.debug = None  # dict: stage name -> tensor copies (tools/debug_train.py)
         from .engine import rope_tables
         from .model.config import llama_dims
         dims = llama_dims(cfg)
@@ -379,6 +380,10 @@ class LlamaTrainStack:
                 x_next = ops.moe_combine(y, route["slot"], route["gate"], residual=h1)
             sv.update(xin=xin, g=g, u=u, h=h, y=y, a_mlp=a_mlp)
             saved.append(sv)
+            if self.debug is not None:
+                self.debug.update({f"f{li}.n1": n1, f"f{li}.o": o2, f"f{li}.h1": h1, f"f{li}.n2": n2,
+                                   f"f{li}.out": x_next, f"f{li}.y": y, f"f{li}.slot": route["slot"] if route else None,
+                                   f"f{li}.gate": route["gate"] if route else None})
             x = x_next
         hidden = ops.rmsnorm(x, self.norm_w, eps)
         la = torch.cat(l_aux) if l_aux else None
@@ -455,7 +460,12 @@ class LlamaTrainStack:
             for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
                 if L.lo[nm] is not None:
                     self._lora_bwd(L.lo[nm], sv["n1"], sv["a_" + nm], dqkv[:, j * D:(j + 1) * D], dn1)
+            dx_in = dx
             dx = T.rmsnorm_bwd(sv["x"], L.ln1, dn1, eps, add=dh1, dweight=ar.of(L.ln1))
+            if self.debug is not None:
+                self.debug.update({f"b{li}.dout": dx_in, f"b{li}.dn2": dn2, f"b{li}.dh1": dh1, f"b{li}.do": do,
+                                   f"b{li}.dqkv": dqkv, f"b{li}.dn1": dn1, f"b{li}.dx": dx, f"b{li}.dxin": dxin,
+                                   f"b{li}.dy": dy, f"b{li}.dgate": dgate})
             saved["layers"][li] = None  # free this layer's activations
             if self.reducer is not None and L.arena_end is not None:
                 self.reducer.ready(L.arena_end)

@@ -243,3 +243,100 @@ def mask_losses(pred, gt, pred_iou):
     _lib.check(lib.mpl_mask_losses(_ptr(pred), _ptr(gt), _ptr(pred_iou), _ll(pred.numel()), _ptr(out), _ptr(sums),
                                    _stream()), "mpl_mask_losses")
     return out, sums
+
+
+# ------------------------------------------------------------------------------------------ grounding-head backward
+def _isf(t):
+    return int(t.dtype == f32)
+
+
+def gemm_small(A, Bm, out=None, trans_a=False, trans_b=False, out_dtype=bf16, accumulate=False):
+    """C = op(A) @ op(B) with op = transpose when trans_*; A, B 2-D bf16 / f32 (any strides). `out` f32 + accumulate
+    adds in place (weight gradients into the arena)."""
+    lib = _lib.load()
+    sam, sak = (A.stride(1), A.stride(0)) if trans_a else (A.stride(0), A.stride(1))
+    M, K = (A.shape[1], A.shape[0]) if trans_a else A.shape
+    sbk, sbn = (Bm.stride(1), Bm.stride(0)) if trans_b else (Bm.stride(0), Bm.stride(1))
+    Kb, N = (Bm.shape[1], Bm.shape[0]) if trans_b else Bm.shape
+    assert K == Kb, (A.shape, Bm.shape, trans_a, trans_b)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    _lib.check(lib.mpl_gemm_small(_ptr(A), _isf(A), _ll(sam), _ll(sak), _ptr(Bm), _isf(Bm), _ll(sbk), _ll(sbn), _ptr(out),
+                                  _isf(out), _ll(out.stride(0)), int(accumulate), M, N, K, _stream()), "mpl_gemm_small")
+    return out
+
+
+def col_sum(X, out):
+    """out (f32 [N]) += X.sum(0); X [M, N] bf16 / f32 (inner stride 1) or a vector."""
+    lib = _lib.load()
+    X2 = X.reshape(1, -1) if X.dim() == 1 else X
+    assert X2.stride(1) == 1 and out.is_contiguous() and out.numel() == X2.shape[1]
+    _lib.check(lib.mpl_col_sum(_ptr(X2), _isf(X2), _ll(X2.stride(0)), _ptr(out), X2.shape[0], X2.shape[1], _stream()),
+               "mpl_col_sum")
+
+
+def layernorm_bwd(x, weight, dy, eps, dweight=None, dbias=None):
+    lib = _lib.load()
+    x2, d2 = _rows(x), _rows(dy)
+    dx = torch.empty_like(x2)
+    _lib.check(lib.mpl_layernorm_bwd(_ptr(x2), _ll(x2.stride(0)), _ptr(weight), _ptr(d2), _ll(d2.stride(0)), _ptr(dx),
+                                     _ll(dx.stride(0)), _ptr(dweight), _ptr(dbias), x2.shape[0], x2.shape[1], _F(eps),
+                                     _stream()), "mpl_layernorm_bwd")
+    return dx.reshape(x.shape)
+
+
+def act_fwd(x, act):
+    lib = _lib.load()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.check(lib.mpl_act_fwd(_ptr(x), _ptr(y), _ll(x.numel()), _lib.ACT_GELU if act == "gelu" else _lib.ACT_RELU,
+                               _stream()), "mpl_act_fwd")
+    return y
+
+
+def act_bwd(x, dy, act):
+    lib = _lib.load()
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(dy)
+    _lib.check(lib.mpl_act_bwd(_ptr(x), _ptr(dy), _ptr(dx), _ll(x.numel()),
+                               _lib.ACT_GELU if act == "gelu" else _lib.ACT_RELU, _stream()), "mpl_act_bwd")
+    return dx
+
+
+def attn_small_bwd(q, k, v, d_o, H, scale):
+    """q [Tq, H*d], k / v [Tk, H*d], d_o [Tq, H*d] (inner stride 1) -> dq, dk, dv (bf16, contiguous)."""
+    lib = _lib.load()
+    Tq, C = q.shape
+    Tk = k.shape[0]
+    d = C // H
+    dq, dk, dv = torch.empty_like(q.contiguous()), torch.empty_like(k.contiguous()), torch.empty_like(v.contiguous())
+    for t in (q, k, v, d_o):
+        assert t.stride(1) == 1
+    _lib.check(lib.mpl_attn_small_bwd(_ptr(q), _ll(q.stride(0)), _ptr(k), _ll(k.stride(0)), _ptr(v), _ll(v.stride(0)),
+                                      _ptr(d_o), _ll(d_o.stride(0)), _ptr(dq), _ll(C), _ptr(dk), _ll(C), _ptr(dv), _ll(C),
+                                      Tq, Tk, H, d, _F(scale), _stream()), "mpl_attn_small_bwd")
+    return dq, dk, dv
+
+
+def bilinear_resize_bwd(dy, in_hw):
+    """dy [N, Hout, Wout] (bf16 / f32, contiguous) -> dx bf16 [N, Hin, Win]."""
+    lib = _lib.load()
+    dy = dy.contiguous()
+    N, Hout, Wout = dy.shape
+    Hin, Win = in_hw
+    dx = torch.empty((N, Hin, Win), dtype=bf16, device=dy.device)
+    _lib.check(lib.mpl_bilinear_resize_bwd(_ptr(dy), _isf(dy), Hout, Wout, _ptr(dx), _ll(Hin * Win), _ll(Win), Hin, Win,
+                                           N, _stream()), "mpl_bilinear_resize_bwd")
+    return dx
+
+
+def mask_losses_bwd(pred, gt, pred_iou, sums6, dloss4):
+    """-> (dpred bf16 like pred, dpred_iou f32 [1])."""
+    lib = _lib.load()
+    pred, gt = pred.contiguous(), gt.contiguous()
+    dpred = torch.empty_like(pred)
+    dpi = torch.zeros((1,), dtype=f32, device=pred.device)
+    _lib.check(lib.mpl_mask_losses_bwd(_ptr(pred), _ptr(gt), _ptr(pred_iou), _ptr(sums6), _ptr(dloss4.contiguous()),
+                                       _ll(pred.numel()), _ptr(dpred), _ptr(dpi), _stream()), "mpl_mask_losses_bwd")
+    return dpred, dpi

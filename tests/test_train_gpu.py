@@ -34,7 +34,9 @@ def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,d
             if "lora_B" in n:  # peft starts B at zero (dA would be identically 0): test a trained-looking adapter
                 p.copy_((torch.randn(p.shape, generator=g) * 0.05).to(p.dtype))
             if "wg.weight" in n:
-                p.mul_(2.0)  # decisive routing: bf16-vs-fp32 activation noise must not flip an argmax
+                # router logits of O(1): gates unsaturated (the router gradient is well conditioned); the batch seed
+                # below is one where every token's top-1 margin exceeds the bf16-vs-fp32 activation noise
+                p.mul_(0.2)
     m.train()
     sd = {k: v.detach().cpu().float() for k, v in m.state_dict().items()}
     sd.update({k: v.detach().cpu().float() for k, v in m.named_buffers()})
@@ -43,8 +45,8 @@ def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,d
     return m, sd, ocfg
 
 
-def batch(B=2, n_text=14, seg=False, pad=False):
-    g = torch.Generator().manual_seed(3)
+def batch(B=2, n_text=14, seg=False, pad=False, seed=5):
+    g = torch.Generator().manual_seed(seed)
     ids = torch.randint(3, 290, (B, n_text), generator=g)
     ids[:, 2] = -200
     labels = ids.clone()
@@ -65,10 +67,6 @@ def batch(B=2, n_text=14, seg=False, pad=False):
 def oracle_run(sd, ocfg, b, seg_flag, noise):
     from oracle import train as otrain
     ids, labels, am, clip_img, sam_img, gts = b
-    leaves = {}
-    for k, v in sd.items():
-        if isinstance(v, torch.Tensor) and v.is_floating_point():
-            leaves[k] = v
     out, aux = otrain.train_losses(sd, ocfg, clip_img.float(), sam_img.float(), ids, labels, am, gts,
                                    [tuple(g.shape) for g in gts], [(256, 256)] * len(gts), SEG, W, seg_flag=seg_flag,
                                    rts_uniforms=noise)
