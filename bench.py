@@ -3,6 +3,7 @@
   python bench.py --gpus N --steps K --warmup W              ours: hand-written sm_100a kernels behind the C ABI
   python bench.py --impl reference --gpus N --steps K ...    the reference's path on the host cores (CPU oracle port)
   python bench.py --workload decode ...                      secondary: VQA decode B=8 (configs[2]), tokens/s
+  python bench.py --workload train ...                       secondary: Stage-IV-flags train step (configs[3]), samples/s
 
 A "step" is one image through MedPLIBForCausalLM.evaluate(): CLIP-L/14-336 -> mm_projector -> splice (T = 40 + 575) ->
 LLaMA-7B-MoE (2 experts, top-1) prefill -> 8 greedy decode tokens (<SEG> forced at new token 4, since random weights
@@ -310,6 +311,149 @@ def run_decode(args, rank, world, dev):
                      "peak_source": pk["src"] + " copy bandwidth"}}), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------- train step (configs[3])
+N_TEXT_TRAIN = 64
+
+
+def train_batch(B, seed):
+    g = torch.Generator().manual_seed(100 + seed)
+    ids = torch.randint(3, 31999, (B, N_TEXT_TRAIN), generator=g)
+    ids[:, 2], ids[:, 3], ids[:, 4] = 32001, -200, 32002
+    ids[:, 40] = SEG
+    labels = ids.clone()
+    labels[:, :24] = -100  # the prompt part carries no loss (LazySupervisedDataset masks the human turn)
+    am = torch.ones_like(ids, dtype=torch.bool)
+    images_clip = torch.randn(B, 3, 336, 336, generator=g)
+    images = torch.randn(B, 3, 256, 256, generator=g)
+    gts = [(torch.rand(336, 336, generator=g) > 0.7).float() for _ in range(B)]
+    return ids, labels, am, images_clip, images, gts
+
+
+def run_train(args, rank, world, dev):
+    """Secondary workload: Stage-IV-flags train step (scripts/train_stage4.sh: --moe_enable, LoRA r=8 alpha=16 on
+    q,v,gate,up,down, sft wg,lm_head,embed_tokens,mask_decoder,text_hidden_fcs,region_fea_adapter; capacity 1.5, aux
+    coef 0), bf16, micro-batch `--batch` per GPU (default 8), T = 64 text ids + 575 = 639, one <SEG> + one 336x336
+    ground-truth mask per sample. A step = forward (activations kept) + hand-scheduled backward + bucketed NCCL
+    all-reduce of the fp32 gradient arena (N > 1) + clip + AdamW. Data-parallel: `scaling` weak, value = samples of all
+    ranks / max-over-ranks time."""
+    import ctypes
+    from medplib_b200 import _lib, train
+    lib = _lib.load()
+    torch.cuda.set_device(dev)
+    m = build_model(dev, small=args.small)
+    m.config.moe["router_aux_loss_coef"] = 0.0
+    m.router_aux_loss_coef = 0.0
+    m.ce_loss_weight, m.bce_loss_weight, m.dice_loss_weight, m.iou_loss_weight, m.focal_loss_weight = 1.0, 2.0, 0.5, 1.0, 1.0
+    train.attach_lora(m, r=8, lora_alpha=16, lora_dropout=0.0, target_modules="q_proj,v_proj,gate_proj,up_proj,down_proj")
+    train.set_trainable(m, "wg,lm_head,embed_tokens,mask_decoder,text_hidden_fcs,region_fea_adapter")
+    m.train()
+    tr = m.trainer(lr=3e-4)
+    B = args.batch
+    ids, labels, am, images_clip, images, gts = train_batch(B, rank)
+    d_in = dict(ids=ids.to(dev), labels=labels.to(dev), am=am.to(dev), clip=images_clip.to(dev).to(bf16),
+                img=images.to(dev).to(bf16), gts=[x.to(dev) for x in gts])
+    h_in = dict(ids=ids.pin_memory(), labels=labels.pin_memory(), am=am.pin_memory(), clip=images_clip.pin_memory(),
+                img=images.pin_memory(), gts=[x.pin_memory() for x in gts])
+
+    def step(x, read_loss=False):
+        out = m(images=x["img"], images_clip=x["clip"], input_ids=x["ids"], region_masks=None, labels=x["labels"],
+                attention_mask=x["am"], offset=None, masks_list=x["gts"], label_list=x["gts"],
+                resize_list=[(256, 256)] * B, inference=False, seg_flag=True)
+        out["loss"].backward()
+        tr.step()
+        return float(out["loss"].detach()) if read_loss else None
+
+    def step_e2e():
+        x = dict(ids=h_in["ids"].to(dev, non_blocking=True), labels=h_in["labels"].to(dev, non_blocking=True),
+                 am=h_in["am"].to(dev, non_blocking=True), clip=h_in["clip"].to(dev, non_blocking=True).to(bf16),
+                 img=h_in["img"].to(dev, non_blocking=True).to(bf16),
+                 gts=[t.to(dev, non_blocking=True) for t in h_in["gts"]])
+        return step(x, read_loss=True)
+
+    def timed(fn, steps):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.mpl_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, lib.mpl_launch_count() - n0
+
+    if args.ncu:
+        for _ in range(2):
+            step(d_in)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(d_in)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    loss0 = None
+    for i in range(max(args.warmup, 3)):
+        l = step(d_in, read_loss=True)
+        loss0 = l if loss0 is None else loss0
+    step_e2e()
+    clocks = ClockSampler(dev.index or 0)
+    clocks.start()
+    ms, launches = timed(lambda: step(d_in), args.steps)
+    ck = clocks.stop()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    loss1 = step(d_in, read_loss=True)
+    lib.mpl_profile_gemm(1)
+    psteps = min(args.steps, 2)
+    for _ in range(psteps):
+        step(d_in)
+    tot, cnt = ctypes.c_float(0), ctypes.c_int(0)
+    lib.mpl_profile_gemm_read(ctypes.byref(tot), ctypes.byref(cnt))
+    lib.mpl_profile_gemm(0)
+    if rank != 0:
+        return
+    d = DIMS if not args.small else dict(D=512, F=1024, L=2, H=4, V=32267, E=2)
+    T = N_TEXT_TRAIN - 1 + 576
+    lin = T * d["L"] * (4 * d["D"] ** 2 + 3 * d["D"] * d["F"]) * 2
+    head = T * d["D"] * d["V"] * 2
+    enc = gemm_flops_per_image(T) - (N_TEXT - 1 + 576) * DIMS["L"] * (4 * DIMS["D"] ** 2 + 3 * DIMS["D"] * DIMS["F"]) * 2
+    flops = B * (2 * lin + 3 * head + enc)  # fwd + dgrad through frozen weights; lm_head adds its wgrad; encoders fwd
+    pk = peaks()
+    gemm_ms = tot.value / psteps
+    ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 and not args.small else None
+    h2d = sum(t.numel() * t.element_size() for t in (ids, labels, am, images_clip, images)) + sum(g.numel() * 4 for g in gts)
+    print(json.dumps({
+        "metric": "Stage-IV train step samples/sec at 7B (MedPLIB-7B-2e, bf16, LoRA r=8 + sft modules)",
+        "value": world * B * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Stage-IV-flags train step bf16, micro-batch {B}/GPU x {world} GPU (global {B * world}), "
+                               f"T={T} (64 ids + 576 image tokens), 1 <SEG> + 336x336 GT mask per sample; MoE dense 32 "
+                               "layers E=2 top-1 cf=1.5; LoRA r=8 a=16 on q,v,gate,up,down; sft wg,lm_head,embed_tokens,"
+                               "mask_decoder,text_hidden_fcs; fwd + bwd + grad all-reduce + clip + AdamW; no region "
+                               "slots (region_fea_adapter gradient not built yet)",
+                   "weights": "random init, 11.07 B params", "parallelism": f"dp{world}",
+                   "trainable_params": int(tr.arena.numel), "l2": "activations + weights >> 126 MB L2",
+                   "small": bool(args.small)},
+        "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches // max(args.steps, 1)), "clocks": ck, "loss_first": loss0, "loss_last": loss1,
+        "tokens_per_s": world * B * T * args.steps / (ms * 1e-3),
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s",
+                     "frac": (ach / pk["tf_sus"]) if ach else None, "traffic": None,
+                     "kernel": "gemm_bf16_tcgen05_kernel (all launches of a train step: forward + dgrad + lm_head wgrad;"
+                               " algorithmic 2MNK / summed CUDA-event durations)", "kernel_ms_per_step": gemm_ms,
+                     "kernel_launches_per_step": cnt.value / psteps, "step_tflops": flops / (ms / args.steps * 1e-3) / 1e12,
+                     "peak_source": pk["src"] + " sustained bf16"}}), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------- reference arm (CPU)
 def cpu_reference(sample_steps=1):
     """The reference's path on the host cores: oracle port (fp32, all threads) on a bounded sample — ONE decoder layer,
@@ -394,7 +538,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="grounding", choices=["grounding", "decode"])
+    ap.add_argument("--workload", default="grounding", choices=["grounding", "decode", "train"])
     ap.add_argument("--batch", type=int, default=8, help="decode workload: sequences per GPU")
     ap.add_argument("--new-tokens", type=int, default=512, help="decode workload: generated tokens per sequence")
     ap.add_argument("--small", action="store_true", help="2-layer toy LLaMA (plumbing check, not a benchmark)")
@@ -418,6 +562,8 @@ def main():
     args.cpu_baseline = args.cpu_baseline and rank == 0 and world == 1
     if args.workload == "decode":
         run_decode(args, rank, world, dev)
+    elif args.workload == "train":
+        run_train(args, rank, world, dev)
     else:
         run_ours(args, rank, world, dev)
     if world > 1:
