@@ -74,6 +74,19 @@ __global__ void __launch_bounds__(128) moe_router_kernel(const __nv_bfloat16* __
 
 constexpr int SCAN_THREADS = 1024;
 
+__device__ __forceinline__ int block_sum_int(int v, int* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  int t = red[lane];  // SCAN_THREADS / 32 == 32 partial sums
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  return t;
+}
+
 // One CTA. Selection (top-1 / top-2), capacity, slots, kept counts, exp_counts, l_aux.
 __global__ void __launch_bounds__(SCAN_THREADS) moe_scan_kernel(const float* __restrict__ logits,
                                                                 const float* __restrict__ gates,
@@ -81,11 +94,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) moe_scan_kernel(const float* __r
                                                                 int C, int* __restrict__ expert,
                                                                 float* __restrict__ gate, int* __restrict__ slot,
                                                                 int* __restrict__ kept, int* __restrict__ exp_counts,
-                                                                float* __restrict__ l_aux) {
+                                                                float* __restrict__ l_aux, int skey_ok) {
+  extern __shared__ float skey[];  // [S] when skey_ok: RTS keys of one expert
   __shared__ int cnt[SCAN_THREADS][MOE_MAX_E];  // per-thread segment counts, then exclusive offsets
   __shared__ int total1[MOE_MAX_E], total2[MOE_MAX_E];
   __shared__ float me_sum[MOE_MAX_E];
   __shared__ float red[SCAN_THREADS / 32];
+  __shared__ int ired[SCAN_THREADS / 32];
   const int tid = threadIdx.x;
   const int seg = (S + SCAN_THREADS - 1) / SCAN_THREADS;
   const int s0 = tid * seg, s1 = min(S, s0 + seg);
@@ -164,6 +179,58 @@ __global__ void __launch_bounds__(SCAN_THREADS) moe_scan_kernel(const float* __r
     __syncthreads();
     // top-1 with Random Token Selection: when an expert overflows, keep the C tokens with the largest uniforms.
     const bool rts = (k == 1 && noise != nullptr);
+    if (rts && skey_ok) {
+      // keep the C largest uniforms of an overflowing expert (ties: earlier position first): the expert's keys are
+      // staged in shared memory and the C-th largest is found by bisection on the fp32 bit pattern (non-negative
+      // floats order like unsigned ints): 31 block-wide counts instead of an O(S^2) ranking
+      for (int e = 0; e < E; ++e) {
+        if (total1[e] <= C) continue;  // uniform branch
+        __syncthreads();
+        for (int t = tid; t < S; t += SCAN_THREADS)
+          skey[t] = expert[t] == e ? noise[static_cast<long long>(t) * E + e] : -1.0f;
+        __syncthreads();
+        auto count_ge = [&](unsigned v) {
+          int c = 0;
+          for (int t = tid; t < S; t += SCAN_THREADS) {
+            const float kf = skey[t];
+            c += (kf >= 0.0f && __float_as_uint(kf) >= v) ? 1 : 0;
+          }
+          return block_sum_int(c, ired);
+        };
+        unsigned lo = 0u, hi = 0x7f800000u;  // count_ge(lo) >= C > count_ge(hi)
+        while (hi - lo > 1u) {
+          const unsigned mid = lo + (hi - lo) / 2u;
+          if (count_ge(mid) >= C)
+            lo = mid;
+          else
+            hi = mid;
+        }
+        const unsigned thr = lo;
+        const int n_greater = count_ge(thr + 1u);
+        const int n_equal = count_ge(thr) - n_greater;
+        int allow = C - n_greater;  // >= 1
+        if (n_equal > allow) {      // exact ties at the threshold (rare): the earliest `allow` of them stay
+          if (tid == 0) {
+            for (int t = 0; t < S; ++t) {
+              const float kf = skey[t];
+              if (kf >= 0.0f && __float_as_uint(kf) == thr) {
+                if (allow > 0)
+                  --allow;
+                else
+                  skey[t] = -0.5f;
+              }
+            }
+          }
+          __syncthreads();
+        }
+        for (int s = s0; s < s1; ++s)
+          if (expert[s] == e) {
+            const float kf = skey[s];
+            slot[s] = (kf >= 0.0f && __float_as_uint(kf) >= thr) ? -2 : -1;  // -2: kept, location resolved below
+          }
+      }
+      __syncthreads();
+    }
     int run[MOE_MAX_E];
 #pragma unroll
     for (int e = 0; e < MOE_MAX_E; ++e) run[e] = (e < E) ? cnt[tid][e] : 0;
@@ -176,6 +243,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) moe_scan_kernel(const float* __r
       if (j == 1) loc += total1[e];
       bool keep = loc < C;
       if (rts && total1[e] > C) {
+        if (skey_ok) continue;  // decided above
         const float u = noise[static_cast<long long>(s) * E + e];
         int rank = 0;
         for (int t = 0; t < S; ++t) {
@@ -190,13 +258,45 @@ __global__ void __launch_bounds__(SCAN_THREADS) moe_scan_kernel(const float* __r
     }
     __syncthreads();
     if (rts) {
-      // overflowing experts: recompute locations over kept tokens (serial per expert; training-only rare path)
-      if (tid < E && total1[tid] > C) {
-        int loc = 0;
-        for (int s = 0; s < S; ++s)
-          if (expert[s] == tid && slot[s] == -2) slot[s] = loc++;
+      // overflowing experts: locations = cumsum over the KEPT tokens in position order (DeepSpeed recomputes
+      // locations1 after the RTS mask) — a second block scan over the kept flags
+      bool any = false;
+      for (int e = 0; e < E; ++e) any = any || total1[e] > C;
+      if (any) {
+        for (int e = 0; e < E; ++e) cnt[tid][e] = 0;
+        for (int s = s0; s < s1; ++s) {
+          const int e = expert[s];
+          if (total1[e] > C && slot[s] == -2) cnt[tid][e] += 1;
+        }
+        __syncthreads();
+        if (w < E) {
+          int run2 = 0;
+          for (int base = 0; base < SCAN_THREADS; base += 32) {
+            const int v = cnt[base + lane][w];
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int n = __shfl_up_sync(0xffffffffu, inc, o);
+              if (lane >= o) inc += n;
+            }
+            cnt[base + lane][w] = run2 + inc - v;
+            run2 += __shfl_sync(0xffffffffu, inc, 31);
+          }
+        }
+        __syncthreads();
+        int run2[MOE_MAX_E];
+#pragma unroll
+        for (int e = 0; e < MOE_MAX_E; ++e) run2[e] = (e < E) ? cnt[tid][e] : 0;
+        for (int s = s0; s < s1; ++s) {
+          const int e = expert[s];
+          if (total1[e] > C && slot[s] == -2) {
+#pragma unroll
+            for (int q = 0; q < MOE_MAX_E; ++q)
+              if (q == e) slot[s] = run2[q]++;
+          }
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   // ---- finalize: global rows, gate values, counts, l_aux
@@ -509,8 +609,19 @@ int moe_route(const mpl_moe_route_args& a, cudaStream_t stream) {
   if ((a.D % 8) != 0 || (a.ldh % 8) != 0) return MPL_ERR_ALIGN;
   moe_router_kernel<<<(a.S + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(a.h), a.ldh, a.wg, a.S, a.D,
                                                       a.E, a.logits, a.gates);
-  moe_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(a.logits, a.gates, a.noise, a.S, a.E, a.k, a.capacity, a.expert,
-                                                  a.gate, a.slot, a.kept, a.exp_counts, a.l_aux);
+  size_t skey_bytes = 0;
+  if (a.k == 1 && a.noise != nullptr && static_cast<size_t>(a.S) * 4 <= 160 * 1024) {
+    skey_bytes = static_cast<size_t>(a.S) * 4;
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(moe_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+        return MPL_ERR_CUDA;
+      attr = true;
+    }
+  }
+  moe_scan_kernel<<<1, SCAN_THREADS, skey_bytes, stream>>>(a.logits, a.gates, a.noise, a.S, a.E, a.k, a.capacity, a.expert,
+                                                           a.gate, a.slot, a.kept, a.exp_counts, a.l_aux,
+                                                           skey_bytes > 0 ? 1 : 0);
   return launch_status(2);
 }
 

@@ -200,6 +200,223 @@ __global__ void __launch_bounds__(256) rank_wgrad_kernel(const bf16_t* __restric
   }
 }
 
+
+// ---- bandwidth-shaped variants for r <= 8 with 16-byte aligned rows (the train step's shapes). All three are pure
+// HBM streams (x / y / dy read once): every lane moves 16 bytes per access, >= 4 accesses in flight per lane, and the
+// rank-r factors live in shared memory / registers.
+constexpr int LR8 = 8;
+constexpr int LD8_THREADS = 512;
+// u[m, j] = scale * sum_k x[m,k] A[j,k]: A (r x K) staged ONCE per CTA in shared memory (r*K*2 <= 200 KB), one CTA
+// per SM, every warp sweeps FOUR rows at a time so each staged A chunk is read once per four rows.
+__global__ void __launch_bounds__(LD8_THREADS) lora_down8_kernel(const bf16_t* __restrict__ x, long long ldx,
+                                                                 const bf16_t* __restrict__ A, long long lda,
+                                                                 void* __restrict__ u, int u_f32, int M, int K, int r,
+                                                                 float scale, int rows_per_cta) {
+  extern __shared__ __align__(16) unsigned char ld8_smem[];
+  bf16_t* sA = reinterpret_cast<bf16_t*>(ld8_smem);  // [r][K] bf16
+  for (int i = threadIdx.x * 8; i < r * K; i += LD8_THREADS * 8) {
+    const int j = i / K, c = i % K;
+    *reinterpret_cast<uint4*>(sA + i) = *reinterpret_cast<const uint4*>(A + static_cast<long long>(j) * lda + c);
+  }
+  __syncthreads();
+  constexpr int NW = LD8_THREADS / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m_beg = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long m_end = m_beg + rows_per_cta < M ? m_beg + rows_per_cta : M;
+  for (long long m = m_beg + warp; m < m_end; m += 4 * NW) {
+    float acc[4][LR8];
+    const bf16_t* xr[4];
+    bool ok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ok[q] = m + q * NW < m_end;
+      xr[q] = x + (ok[q] ? m + q * NW : m) * ldx;
+#pragma unroll
+      for (int j = 0; j < LR8; ++j) acc[q][j] = 0.0f;
+    }
+    for (int c = lane * 8; c < K; c += 256) {
+      uint4 raw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) raw[q] = ld_nc_v4(xr[q] + c);
+#pragma unroll
+      for (int j = 0; j < LR8; ++j) {
+        if (j < r) {
+          const uint4 ar = *reinterpret_cast<const uint4*>(sA + j * K + c);
+          const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&ar);
+          float2 f[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) f[i] = __bfloat1622float2(ap[i]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&raw[q]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 xv = __bfloat1622float2(xp[i]);
+              acc[q][j] = fmaf(xv.x, f[i].x, acc[q][j]);
+              acc[q][j] = fmaf(xv.y, f[i].y, acc[q][j]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < LR8; ++j) acc[q][j] = warp_sum(acc[q][j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!ok[q]) continue;
+        const long long mm = m + q * NW;
+        for (int j = 0; j < r; ++j) {
+          if (u_f32)
+            static_cast<float*>(u)[mm * r + j] = acc[q][j] * scale;
+          else
+            static_cast<bf16_t*>(u)[mm * r + j] = __float2bfloat16_rn(acc[q][j] * scale);
+        }
+      }
+    }
+  }
+}
+
+// y[m, n..n+8) += rank-r update; CTA = 2048 columns x 16 rows, 8 rows of loads in flight per lane.
+constexpr int UP8_ROWS = 16;
+__global__ void __launch_bounds__(256) lora_up_add8_kernel(bf16_t* __restrict__ y, long long ldy,
+                                                           const void* __restrict__ u, int u_f32,
+                                                           const bf16_t* __restrict__ Bm, long long sn, long long sr,
+                                                           float scale, int M, int N, int r) {
+  __shared__ float us[UP8_ROWS][LR8];
+  const int m0 = blockIdx.y * UP8_ROWS;
+  if (threadIdx.x < UP8_ROWS * LR8) {
+    const int rr = threadIdx.x / LR8, j = threadIdx.x % LR8;
+    const long long m = m0 + rr;
+    float v = 0.0f;
+    if (m < M && j < r)
+      v = u_f32 ? static_cast<const float*>(u)[m * r + j] : __bfloat162float(static_cast<const bf16_t*>(u)[m * r + j]);
+    us[rr][j] = v;
+  }
+  __syncthreads();
+  const long long n = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (n >= N) return;
+  float b[8][LR8];  // b[i][j] = Bm[(n+i)*sn + j*sr]
+  if (sr == 1 && sn == 8 && r == 8) {  // [N, 8] row-major: one 16-byte load per column
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(Bm + (n + i) * 8);
+      const bf16_t* bv = reinterpret_cast<const bf16_t*>(&raw);
+#pragma unroll
+      for (int j = 0; j < LR8; ++j) b[i][j] = __bfloat162float(bv[j]);
+    }
+  } else if (sn == 1 && (sr % 8) == 0) {  // [r, N] row-major: one 16-byte load per rank row
+#pragma unroll
+    for (int j = 0; j < LR8; ++j) {
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (j < r) raw = *reinterpret_cast<const uint4*>(Bm + j * sr + n);
+      const bf16_t* bv = reinterpret_cast<const bf16_t*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b[i][j] = __bfloat162float(bv[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < LR8; ++j) b[i][j] = j < r ? __bfloat162float(Bm[(n + i) * sn + j * sr]) : 0.0f;
+  }
+  const int rows = min(UP8_ROWS, M - m0);
+  bf16_t* y0 = y + static_cast<long long>(m0) * ldy + n;
+#pragma unroll
+  for (int half = 0; half < UP8_ROWS / 8; ++half) {
+    uint4 raw[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int rr = half * 8 + q;
+      raw[q] = rr < rows ? *reinterpret_cast<const uint4*>(y0 + static_cast<long long>(rr) * ldy) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int rr = half * 8 + q;
+      if (rr >= rows) continue;
+      bf16_t* yv = reinterpret_cast<bf16_t*>(&raw[q]);
+      float uu[LR8];
+#pragma unroll
+      for (int j = 0; j < LR8; ++j) uu[j] = us[rr][j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < LR8; ++j) a = fmaf(uu[j], b[i][j], a);
+        yv[i] = __float2bfloat16_rn(__bfloat162float(yv[i]) + bf16_round(scale * bf16_round(a)));
+      }
+      *reinterpret_cast<uint4*>(y0 + static_cast<long long>(rr) * ldy) = raw[q];
+    }
+  }
+}
+
+// out[n, j] += scale * sum_m X[m, n] U[m, j]: CTA = 256 columns (lane x 8) x WG8_ROWS rows (warp w takes rows w, w+8,
+// ...), warps combine through shared-memory atomics, then ONE global atomic per (column, j) per CTA.
+constexpr int WG8_ROWS = 256;
+__global__ void __launch_bounds__(256) rank_wgrad8_kernel(const bf16_t* __restrict__ X, long long ldx,
+                                                          const void* __restrict__ U, int u_f32, float* __restrict__ out,
+                                                          long long sn, long long sr, float scale, int M, int N, int r) {
+  __shared__ float us[WG8_ROWS][LR8];
+  __shared__ float sacc[256][LR8 + 1];
+  const int mbeg = blockIdx.y * WG8_ROWS;
+  const int rows = min(WG8_ROWS, M - mbeg);
+  for (int i = threadIdx.x; i < WG8_ROWS * LR8; i += 256) {
+    const int rr = i / LR8, j = i % LR8;
+    const long long m = mbeg + rr;
+    float v = 0.0f;
+    if (rr < rows && j < r)
+      v = u_f32 ? static_cast<const float*>(U)[m * r + j] : __bfloat162float(static_cast<const bf16_t*>(U)[m * r + j]);
+    us[rr][j] = v;
+  }
+  for (int i = threadIdx.x; i < 256 * (LR8 + 1); i += 256) (&sacc[0][0])[i] = 0.0f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n = static_cast<long long>(blockIdx.x) * 256 + lane * 8;
+  if (n < N) {
+    float acc[8][LR8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < LR8; ++j) acc[i][j] = 0.0f;
+    const bf16_t* xp = X + static_cast<long long>(mbeg) * ldx + n;
+    for (int rr = warp; rr < rows; rr += 32) {
+      uint4 raw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = rr + 8 * q;
+        raw[q] = row < rows ? ld_nc_v4(xp + static_cast<long long>(row) * ldx) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = min(rr + 8 * q, WG8_ROWS - 1);
+        const bf16_t* xv = reinterpret_cast<const bf16_t*>(&raw[q]);
+        float uu[LR8];
+#pragma unroll
+        for (int j = 0; j < LR8; ++j) uu[j] = us[row][j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xf = __bfloat162float(xv[i]);
+#pragma unroll
+          for (int j = 0; j < LR8; ++j) acc[i][j] = fmaf(xf, uu[j], acc[i][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < LR8; ++j) atomicAdd(&sacc[lane * 8 + i][j], acc[i][j]);
+  }
+  __syncthreads();
+  const long long nc = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (nc < N) {
+#pragma unroll
+    for (int j = 0; j < LR8; ++j)
+      if (j < r) atomicAdd(out + nc * sn + j * sr, scale * sacc[threadIdx.x][j]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- RMSNorm backward
 // y = w * (x * rstd):  dx = rstd * (g - xhat * mean(g * xhat)), g = dy * w;  out = bf16(dx + add);  dw += dy * xhat
 constexpr int RB_THREADS = 128;
@@ -808,6 +1025,22 @@ extern "C" int mpl_lora_down(const void* x, long long ldx, const void* A, long l
   if (M <= 0) return MPL_OK;
   if (x == nullptr || A == nullptr || u == nullptr || r < 1 || r > LORA_MAX_R) return MPL_ERR_ARG;
   if (K % 8 != 0 || ldx % 8 != 0 || lda % 8 != 0) return MPL_ERR_ALIGN;
+  if (r <= LR8 && static_cast<size_t>(r) * K * 2 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(lora_down8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return MPL_ERR_CUDA;
+      attr = true;
+    }
+    // one CTA per SM-sized slab of rows (A is staged once per CTA)
+    int rows = (M + num_sms() - 1) / num_sms();
+    if (rows < 16) rows = 16;
+    const int grid = (M + rows - 1) / rows;
+    lora_down8_kernel<<<grid, LD8_THREADS, static_cast<size_t>(r) * K * 2, ST(stream)>>>(
+        static_cast<const bf16_t*>(x), ldx, static_cast<const bf16_t*>(A), lda, u, u_is_f32, M, K, r, scale, rows);
+    return launch_status();
+  }
   lora_down_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(static_cast<const bf16_t*>(x), ldx, static_cast<const bf16_t*>(A),
                                                         lda, u, u_is_f32, M, K, r, scale);
   return launch_status();
@@ -817,6 +1050,12 @@ extern "C" int mpl_lora_up_add(void* y, long long ldy, const void* u, int u_is_f
                                long long bm_stride_r, float scale, int M, int N, int r, void* stream) {
   if (M <= 0 || N <= 0) return MPL_OK;
   if (y == nullptr || u == nullptr || Bm == nullptr || r < 1 || r > LORA_MAX_R) return MPL_ERR_ARG;
+  if (r <= LR8 && N % 8 == 0 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    dim3 g8((N + 2047) / 2048, (M + UP8_ROWS - 1) / UP8_ROWS);
+    lora_up_add8_kernel<<<g8, 256, 0, ST(stream)>>>(static_cast<bf16_t*>(y), ldy, u, u_is_f32,
+                                                    static_cast<const bf16_t*>(Bm), bm_stride_n, bm_stride_r, scale, M, N, r);
+    return launch_status();
+  }
   dim3 grid((N + 511) / 512, (M + UP_ROWS - 1) / UP_ROWS);
   lora_up_add_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<bf16_t*>(y), ldy, u, u_is_f32,
                                                    static_cast<const bf16_t*>(Bm), bm_stride_n, bm_stride_r, scale, M, N, r);
@@ -827,6 +1066,12 @@ extern "C" int mpl_rank_wgrad(const void* X, long long ldx, const void* U, int u
                               long long out_stride_r, float scale, int M, int N, int r, void* stream) {
   if (M <= 0 || N <= 0) return MPL_OK;
   if (X == nullptr || U == nullptr || out == nullptr || r < 1 || r > LORA_MAX_R) return MPL_ERR_ARG;
+  if (r <= LR8 && N % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    dim3 g8((N + 255) / 256, (M + WG8_ROWS - 1) / WG8_ROWS);
+    rank_wgrad8_kernel<<<g8, 256, 0, ST(stream)>>>(static_cast<const bf16_t*>(X), ldx, U, u_is_f32, out, out_stride_n,
+                                                   out_stride_r, scale, M, N, r);
+    return launch_status();
+  }
   const int gx = (N + 511) / 512;
   int split = (2 * num_sms() + gx - 1) / gx;
   const int max_split = (M + WG_ROWS - 1) / WG_ROWS;

@@ -9,7 +9,7 @@ import sys
 import time
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--per-test", type=float, default=60.0, help="seconds without a new START line before a kill")
+ap.add_argument("--per-test", type=float, default=150.0, help="seconds without a new START line before a kill")
 ap.add_argument("--log", default="gpurun_out/gpu_pytest.log")
 ap.add_argument("rest", nargs=argparse.REMAINDER)
 args = ap.parse_args()
