@@ -486,6 +486,11 @@ int mpl_sumsq_f32(const float* g, long long n, float* out, void* stream);
 int mpl_adamw(float* master, float* m, float* v, const float* grad, void* param, int param_is_bf16, long long n, float lr,
               float beta1, float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
               float grad_scale, void* stream);
+/* mpl_adamw over the whole flat gradient arena in ONE launch. chunks: device int64 [n_chunks, 4] = {arena offset, length
+ * (<= 4096), parameter base address, is_bf16 | (element offset within the parameter << 1)}. */
+int mpl_adamw_multi(float* master, float* m, float* v, const float* grad, const long long* chunks, int n_chunks, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, const float* sumsq, float max_norm,
+                    float grad_scale, void* stream);
 
 /* The four mask losses of model/MedPLIB.py:26-124 for ONE mask in one pass: pred bf16 [n] logits, gt f32 [n] in {0,1},
  * pred_iou bf16 scalar -> out4 = {sigmoid_ce_loss, dice_loss, MaskIoULoss, FocalLoss}; sums6 (optional) = the six
@@ -512,11 +517,12 @@ int mpl_layernorm_bwd(const void* x, long long ldx, const void* weight, const vo
 /* y = act(x) and dx = act'(x) dy for MPL_ACT_GELU (erf form; x = the input) / MPL_ACT_RELU (x = input or output). */
 int mpl_act_fwd(const void* x, void* y, long long n, int act, void* stream);
 int mpl_act_bwd(const void* x, const void* dy, void* dx, long long n, int act, void* stream);
-/* Backward of softmax(scale q k^T) v for the mask decoder's attentions (transformer.py:185-244): q [Tq, ld],
- * k / v [Tk, ld], head h = columns [h*head_dim, (h+1)*head_dim), head_dim <= 32; one CTA per head. */
+/* Backward of softmax(scale q k^T) v for the mask decoder's attentions (transformer.py:185-244): q [batch*Tq, ld],
+ * k / v [batch*Tk, ld] (batches stacked along rows), head h = columns [h*head_dim, (h+1)*head_dim), head_dim <= 32;
+ * one CTA per (head, batch). */
 int mpl_attn_small_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                        const void* d_o, long long ldo, void* dq, long long lddq, void* dk, long long lddk, void* dv,
-                       long long lddv, int Tq, int Tk, int H, int head_dim, float scale, void* stream);
+                       long long lddv, int batch, int Tq, int Tk, int H, int head_dim, float scale, void* stream);
 /* Adjoint of mpl_bilinear_resize: dy [N, Hout, Wout] (bf16 or f32) -> dx bf16 [N, Hin, Win] (strides given). */
 int mpl_bilinear_resize_bwd(const void* dy, int dy_is_f32, int Hout, int Wout, void* dx, long long dx_stride_n,
                             long long dx_stride_y, int Hin, int Win, int N, void* stream);

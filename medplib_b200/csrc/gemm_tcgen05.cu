@@ -380,6 +380,7 @@ int encode_tmap_bf16(void* out, const void* ptr, int rank, const unsigned long l
 // Optional in-situ timing of every tcgen05 GEMM launch (bench.py roofline): CUDA events recorded on the launching
 // stream around each launch, summed by mpl_profile_gemm_read after a synchronise.
 static bool g_prof = false;
+static bool g_prof_suppress = false;        // set while a fork/join region is timed as ONE interval by its caller
 static std::vector<cudaEvent_t> g_prof_ev;  // pairs (start, stop)
 static size_t g_prof_used = 0;
 static cudaEvent_t prof_event() {
@@ -454,9 +455,10 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn) * nb;
   int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
   if (grid < 1) grid = 1;
-  if (g_prof) cudaEventRecord(prof_event(), stream);
+  const bool prof = g_prof && !g_prof_suppress;
+  if (prof) cudaEventRecord(prof_event(), stream);
   gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB1, tmB2, p);
-  if (g_prof) cudaEventRecord(prof_event(), stream);
+  if (prof) cudaEventRecord(prof_event(), stream);
   return mpl::launch_status();
 }
 
@@ -484,11 +486,39 @@ int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
   return launch_gemm<128>(a, stream);
 }
 
-// Grouped (per-expert) GEMM for M > 16: one tcgen05 launch per group for now (device-side row counts via m_dev).
+// Grouped (per-expert) GEMM for M > 16: one tcgen05 launch per group (device-side row counts via m_dev). Each expert's
+// launch is a partial wave at prefill sizes (e.g. down_proj at M_e ~ 300: 66 tiles on 148 SMs), so the groups are
+// launched on side streams forked from / joined to the caller's stream and run CONCURRENTLY on disjoint SMs.
+static cudaStream_t g_aux_stream[MPL_MAX_EXPERTS];
+static cudaEvent_t g_fork_ev, g_join_ev[MPL_MAX_EXPERTS];
+static bool g_aux_ready = false;
+static bool aux_streams_ready() {
+  if (g_aux_ready) return true;
+  if (cudaEventCreateWithFlags(&g_fork_ev, cudaEventDisableTiming) != cudaSuccess) return false;
+  for (int i = 0; i < MPL_MAX_EXPERTS; ++i) {
+    if (cudaStreamCreateWithFlags(&g_aux_stream[i], cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&g_join_ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+  }
+  g_aux_ready = true;
+  return true;
+}
+
 int grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
   if (a.row_map != nullptr || a.a_row_map != nullptr) return MPL_ERR_UNSUPPORTED;
   const long long csz = a.out_dtype == MPL_DT_F32 ? 4 : 2;
-  for (int g = 0; g < a.groups; ++g) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cap);
+  const bool fork = a.groups > 1 && a.groups <= MPL_MAX_EXPERTS && cap == cudaStreamCaptureStatusNone &&
+                    aux_streams_ready();
+  // in-situ profiling: the concurrent launches are timed as one interval on the caller's stream (fork -> join)
+  const bool prof_region = fork && g_prof && !g_prof_suppress;
+  if (prof_region) {
+    cudaEventRecord(prof_event(), stream);
+    g_prof_suppress = true;
+  }
+  if (fork && cudaEventRecord(g_fork_ev, stream) != cudaSuccess) return MPL_ERR_CUDA;
+  int rc_all = MPL_OK;
+  for (int g = 0; g < a.groups && rc_all == MPL_OK; ++g) {
     mpl_gemm_args x;
     memset(&x, 0, sizeof(x));
     x.A = static_cast<const char*>(a.A) + static_cast<long long>(g) * a.a_group_stride * 2;
@@ -507,10 +537,22 @@ int grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
     x.nb = 1;
     x.act = a.act;
     x.out_dtype = a.out_dtype;
-    const int rc = gemm_bf16(x, stream);
-    if (rc != MPL_OK) return rc;
+    cudaStream_t s = stream;
+    if (fork && g > 0) {
+      s = g_aux_stream[g];
+      if (cudaStreamWaitEvent(s, g_fork_ev, 0) != cudaSuccess) return MPL_ERR_CUDA;
+    }
+    rc_all = gemm_bf16(x, s);
+    if (rc_all == MPL_OK && fork && g > 0) {
+      if (cudaEventRecord(g_join_ev[g], s) != cudaSuccess || cudaStreamWaitEvent(stream, g_join_ev[g], 0) != cudaSuccess)
+        rc_all = MPL_ERR_CUDA;
+    }
   }
-  return MPL_OK;
+  if (prof_region) {
+    g_prof_suppress = false;
+    cudaEventRecord(prof_event(), stream);
+  }
+  return rc_all;
 }
 
 }  // namespace mpl

@@ -29,12 +29,16 @@ constexpr int GS_T = 32;
 __global__ void __launch_bounds__(256) gemm_small_kernel(const void* __restrict__ A, int a_f32, long long sam,
                                                          long long sak, const void* __restrict__ B, int b_f32,
                                                          long long sbk, long long sbn, void* __restrict__ C, int c_f32,
-                                                         long long ldc, int accumulate, int M, int N, int K) {
+                                                         long long ldc, int accumulate, int M, int N, int K,
+                                                         int k_per_split) {
   __shared__ float sA[GS_T][GS_T + 1], sB[GS_T][GS_T + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int m0 = blockIdx.y * GS_T, n0 = blockIdx.x * GS_T;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k0 = 0; k0 < K; k0 += GS_T) {
+  // gridDim.z > 1: split-K (fp32 accumulate mode only; partial sums meet in fp32 atomics)
+  const int k_beg = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_beg + k_per_split);
+  for (int k0 = k_beg; k0 < k_end; k0 += GS_T) {
     // choose the fastest-varying index per operand so the global reads coalesce along its contiguous dimension
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -42,13 +46,13 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(const void* __restrict_
       {
         int m, k;
         if (sak == 1) { m = m0 + r; k = k0 + tx; } else { m = m0 + tx; k = k0 + r; }
-        const float v = (m < M && k < K) ? ld_any(A, a_f32, m * sam + k * sak) : 0.f;
+        const float v = (m < M && k < k_end) ? ld_any(A, a_f32, m * sam + k * sak) : 0.f;
         sA[m - m0][k - k0] = v;
       }
       {
         int k, n;
         if (sbn == 1) { k = k0 + r; n = n0 + tx; } else { k = k0 + tx; n = n0 + r; }
-        const float v = (k < K && n < N) ? ld_any(B, b_f32, k * sbk + n * sbn) : 0.f;
+        const float v = (k < k_end && n < N) ? ld_any(B, b_f32, k * sbk + n * sbn) : 0.f;
         sB[k - k0][n - n0] = v;
       }
     }
@@ -68,7 +72,10 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(const void* __restrict_
       const long long o = m * ldc + n;
       if (c_f32) {
         float* c = static_cast<float*>(C);
-        c[o] = accumulate ? c[o] + acc[i] : acc[i];
+        if (gridDim.z > 1)
+          atomicAdd(c + o, acc[i]);
+        else
+          c[o] = accumulate ? c[o] + acc[i] : acc[i];
       } else {
         static_cast<bf16_t*>(C)[o] = __float2bfloat16_rn(acc[i]);
       }
@@ -76,14 +83,19 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(const void* __restrict_
   }
 }
 
-// out[n] += sum_m X[m*ld + n]   (one thread per column, coalesced across the warp)
+// out[n] += sum_m X[m*ld + n]   (one thread per column, coalesced across the warp; blockIdx.y splits the rows)
+constexpr int CS_ROWS = 128;
 __global__ void __launch_bounds__(256) col_sum_kernel(const void* __restrict__ X, int x_f32, long long ld,
                                                       float* __restrict__ out, int M, int N) {
   const int n = blockIdx.x * 256 + threadIdx.x;
   if (n >= N) return;
+  const int m_beg = blockIdx.y * CS_ROWS, m_end = min(M, m_beg + CS_ROWS);
   float acc = 0.f;
-  for (int m = 0; m < M; ++m) acc += ld_any(X, x_f32, m * ld + n);
-  out[n] += acc;
+  for (int m = m_beg; m < m_end; ++m) acc += ld_any(X, x_f32, m * ld + n);
+  if (gridDim.y > 1)
+    atomicAdd(out + n, acc);
+  else
+    out[n] += acc;
 }
 
 // ------------------------------------------------------------------------------------------------- LayerNorm bwd
@@ -156,7 +168,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const bf16_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------- small attention bwd
-// One CTA per head. q [Tq, ldq], k/v [Tk, ld], head h owns columns [h*d, (h+1)*d), d <= 32.
+// One CTA per (head, batch). q [B*Tq, ldq], k/v [B*Tk, ld] (batches stacked along rows), head h owns columns
+// [h*d, (h+1)*d), d <= 32.
 // K, V and the dK, dV accumulators live in shared memory as fp32 (row pitch d+1); every warp walks query rows.
 __global__ void __launch_bounds__(256) attn_small_bwd_kernel(
     const bf16_t* __restrict__ q, long long ldq, const bf16_t* __restrict__ k, long long ldk,
@@ -172,6 +185,16 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(
   float* wbuf = sdV + Tk * P;  // per warp: p[Tk], ds[Tk], q[32], do[32]
   const int h = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col0 = h * d;
+  {
+    const long long bq = static_cast<long long>(blockIdx.y) * Tq, bk = static_cast<long long>(blockIdx.y) * Tk;
+    q += bq * ldq;
+    dO += bq * ldo;
+    dq += bq * lddq;
+    k += bk * ldk;
+    v += bk * ldv;
+    dk += bk * lddk;
+    dv += bk * lddv;
+  }
   for (int i = threadIdx.x; i < Tk * d; i += 256) {
     const int j = i / d, c = i % d;
     sK[j * P + c] = __bfloat162float(k[j * ldk + col0 + c]);
@@ -333,16 +356,30 @@ extern "C" int mpl_gemm_small(const void* A, int a_is_f32, long long a_stride_m,
   if (M <= 0 || N <= 0) return MPL_OK;
   if (A == nullptr || B == nullptr || C == nullptr || K <= 0) return MPL_ERR_ARG;
   if (accumulate && !c_is_f32) return MPL_ERR_ARG;
-  dim3 grid((N + 31) / 32, (M + 31) / 32);
+  dim3 grid((N + 31) / 32, (M + 31) / 32, 1);
+  int k_per_split = (K + 31) / 32 * 32;
+  if (accumulate && c_is_f32 && K >= 512) {
+    // few output tiles and a long reduction (weight gradients over thousands of rows): split K so the launch fills
+    // the machine
+    const long long tiles = static_cast<long long>(grid.x) * grid.y;
+    long long want = (2LL * mpl::num_sms() + tiles - 1) / tiles;
+    const long long max_split = K / 256;
+    if (want > max_split) want = max_split;
+    if (want > 1) {
+      k_per_split = static_cast<int>(((K + want - 1) / want + 31) / 32 * 32);
+      grid.z = static_cast<unsigned>((K + k_per_split - 1) / k_per_split);
+    }
+  }
   mpl::gemm_small_kernel<<<grid, 256, 0, ST(stream)>>>(A, a_is_f32, a_stride_m, a_stride_k, B, b_is_f32, b_stride_k,
-                                                       b_stride_n, C, c_is_f32, ldc, accumulate, M, N, K);
+                                                       b_stride_n, C, c_is_f32, ldc, accumulate, M, N, K, k_per_split);
   return mpl::launch_status();
 }
 
 extern "C" int mpl_col_sum(const void* X, int x_is_f32, long long ld, float* out, int M, int N, void* stream) {
   if (M <= 0 || N <= 0) return MPL_OK;
   if (X == nullptr || out == nullptr) return MPL_ERR_ARG;
-  mpl::col_sum_kernel<<<(N + 255) / 256, 256, 0, ST(stream)>>>(X, x_is_f32, ld, out, M, N);
+  mpl::col_sum_kernel<<<dim3((N + 255) / 256, (M + mpl::CS_ROWS - 1) / mpl::CS_ROWS), 256, 0, ST(stream)>>>(
+      X, x_is_f32, ld, out, M, N);
   return mpl::launch_status();
 }
 
@@ -374,9 +411,9 @@ extern "C" int mpl_act_bwd(const void* x, const void* dy, void* dx, long long n,
 
 extern "C" int mpl_attn_small_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                                   long long ldv, const void* d_o, long long ldo, void* dq, long long lddq, void* dk,
-                                  long long lddk, void* dv, long long lddv, int Tq, int Tk, int H, int head_dim,
+                                  long long lddk, void* dv, long long lddv, int batch, int Tq, int Tk, int H, int head_dim,
                                   float scale, void* stream) {
-  if (Tq <= 0 || Tk <= 0 || H <= 0) return MPL_OK;
+  if (Tq <= 0 || Tk <= 0 || H <= 0 || batch <= 0) return MPL_OK;
   if (q == nullptr || k == nullptr || v == nullptr || d_o == nullptr || dq == nullptr || dk == nullptr ||
       dv == nullptr)
     return MPL_ERR_ARG;
@@ -390,7 +427,7 @@ extern "C" int mpl_attn_small_bwd(const void* q, long long ldq, const void* k, l
       return MPL_ERR_CUDA;
     attr_set = true;
   }
-  mpl::attn_small_bwd_kernel<<<H, 256, smem, ST(stream)>>>(
+  mpl::attn_small_bwd_kernel<<<dim3(H, batch), 256, smem, ST(stream)>>>(
       static_cast<const bf16_t*>(q), ldq, static_cast<const bf16_t*>(k), ldk, static_cast<const bf16_t*>(v), ldv,
       static_cast<const bf16_t*>(d_o), ldo, static_cast<bf16_t*>(dq), lddq, static_cast<bf16_t*>(dk), lddk,
       static_cast<bf16_t*>(dv), lddv, Tq, Tk, head_dim, scale);

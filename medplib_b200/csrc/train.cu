@@ -417,6 +417,221 @@ __global__ void __launch_bounds__(256) rank_wgrad8_kernel(const bf16_t* __restri
   }
 }
 
+// ---- mma.sync (m16n8k16, bf16 -> fp32) variants of the three rank-r (r <= 8) operators. The rank dimension maps onto
+// the 8-wide N (or the zero-padded 16-wide M) of the warp-level MMA, which removes ~95 % of the issued instructions of
+// the FMA versions above and leaves these kernels as pure 16-byte-per-lane HBM streams. The contraction index may be
+// permuted freely as long as both operands use the same permutation, so every lane feeds fragments straight from the
+// 16-byte chunk it loaded (no shared-memory transposes).
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t u32_of(const uint4& v, int i) {
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// u[m, j] = scale * sum_k x[m,k] A[j,k].  CTA = 16 rows x 8 K-splits (one warp each); K % 32 == 0.
+// Lane (g = lane/4, t = lane%4) loads cols [32 blk + 8t, +8) of rows g and g+8 of x, and of row g of A (zero if g >= r).
+__global__ void __launch_bounds__(256) lora_down_mma_kernel(const bf16_t* __restrict__ x, long long ldx,
+                                                            const bf16_t* __restrict__ A, long long lda,
+                                                            void* __restrict__ u, int u_f32, int M, int K, int r,
+                                                            float scale) {
+  __shared__ float red[8][16][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long m0 = static_cast<long long>(blockIdx.x) * 16;
+  const bool ok0 = m0 + g < M, ok1 = m0 + g + 8 < M, okA = g < r;
+  const bf16_t* x0 = x + (ok0 ? m0 + g : 0) * ldx + 8 * t;
+  const bf16_t* x1 = x + (ok1 ? m0 + g + 8 : 0) * ldx + 8 * t;
+  const bf16_t* al = A + static_cast<long long>(okA ? g : 0) * lda + 8 * t;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int nblk = K / 32;
+  int blk = warp;
+  for (; blk + 24 < nblk; blk += 32) {  // 4 blocks (stride 8) per pass: 8 x-loads in flight per lane
+    uint4 xa[4], xb[4], av[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = (blk + 8 * q) * 32;
+      xa[q] = ok0 ? ld_nc_v4(x0 + c) : zero;
+      xb[q] = ok1 ? ld_nc_v4(x1 + c) : zero;
+      av[q] = okA ? *reinterpret_cast<const uint4*>(al + c) : zero;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      mma_bf16_16816(acc, xa[q].x, xb[q].x, xa[q].y, xb[q].y, av[q].x, av[q].y);
+      mma_bf16_16816(acc, xa[q].z, xb[q].z, xa[q].w, xb[q].w, av[q].z, av[q].w);
+    }
+  }
+  for (; blk < nblk; blk += 8) {
+    const int c = blk * 32;
+    const uint4 xa = ok0 ? ld_nc_v4(x0 + c) : zero;
+    const uint4 xb = ok1 ? ld_nc_v4(x1 + c) : zero;
+    const uint4 av = okA ? *reinterpret_cast<const uint4*>(al + c) : zero;
+    mma_bf16_16816(acc, xa.x, xb.x, xa.y, xb.y, av.x, av.y);
+    mma_bf16_16816(acc, xa.z, xb.z, xa.w, xb.w, av.z, av.w);
+  }
+  red[warp][g][2 * t] = acc[0];
+  red[warp][g][2 * t + 1] = acc[1];
+  red[warp][g + 8][2 * t] = acc[2];
+  red[warp][g + 8][2 * t + 1] = acc[3];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int row = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][row][j];
+    const long long m = m0 + row;
+    if (m < M && j < r) {
+      if (u_f32)
+        static_cast<float*>(u)[m * r + j] = v * scale;
+      else
+        static_cast<bf16_t*>(u)[m * r + j] = __float2bfloat16_rn(v * scale);
+    }
+  }
+}
+
+// y[m,n] = bf16(y + bf16(scale * bf16(sum_j u[m,j] Bm[n*sn + j*sr]))).  CTA = 256 columns (warp: 32) x UPM_ROWS rows.
+constexpr int UPM_ROWS = 64;
+__global__ void __launch_bounds__(256) lora_up_add_mma_kernel(bf16_t* __restrict__ y, long long ldy,
+                                                              const void* __restrict__ u, int u_f32,
+                                                              const bf16_t* __restrict__ Bm, long long sn, long long sr,
+                                                              float scale, int M, int N, int r) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long col0 = static_cast<long long>(blockIdx.x) * 256 + warp * 32;
+  if (col0 >= N) return;
+  // B fragments of the 4 MMAs of this warp's 32 columns: n' = g <-> column col0 + 8 (g / 2) + 2 q + (g % 2)
+  uint32_t bq[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const long long n = col0 + 8 * (g >> 1) + 2 * q + (g & 1);
+    float lo = 0.f, hi = 0.f;
+    if (n < N) {
+      if (2 * t < r) lo = __bfloat162float(Bm[n * sn + (2 * t) * sr]);
+      if (2 * t + 1 < r) hi = __bfloat162float(Bm[n * sn + (2 * t + 1) * sr]);
+    }
+    bq[q] = pack_bf16(lo, hi);
+  }
+  const bool col_ok = col0 + 8 * t < N;
+  const long long mbeg = static_cast<long long>(blockIdx.y) * UPM_ROWS;
+#pragma unroll 1
+  for (int rg = 0; rg < UPM_ROWS / 16; rg += 2) {  // two 16-row groups per pass: 4 y-loads in flight per lane
+    long long rows[4];
+    uint4 yv[4];
+    uint32_t ua[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      rows[h] = mbeg + (rg + (h >> 1)) * 16 + g + 8 * (h & 1);
+      const bool ok = rows[h] < M;
+      yv[h] = (ok && col_ok) ? *reinterpret_cast<const uint4*>(y + rows[h] * ldy + col0 + 8 * t) : make_uint4(0, 0, 0, 0);
+      float lo = 0.f, hi = 0.f;
+      if (ok) {
+        if (u_f32) {
+          const float* up = static_cast<const float*>(u) + rows[h] * r;
+          if (2 * t < r) lo = up[2 * t];
+          if (2 * t + 1 < r) hi = up[2 * t + 1];
+        } else {
+          const bf16_t* up = static_cast<const bf16_t*>(u) + rows[h] * r;
+          if (2 * t < r) lo = __bfloat162float(up[2 * t]);
+          if (2 * t + 1 < r) hi = __bfloat162float(up[2 * t + 1]);
+        }
+      }
+      ua[h] = pack_bf16(lo, hi);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float c[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        c[q][0] = c[q][1] = c[q][2] = c[q][3] = 0.f;
+        mma_bf16_16816(c[q], ua[2 * half], ua[2 * half + 1], 0u, 0u, bq[q], 0u);
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {  // hh = 0: row g, hh = 1: row g + 8
+        const int h = 2 * half + hh;
+        if (rows[h] >= M || !col_ok) continue;
+        bf16_t* e = reinterpret_cast<bf16_t*>(&yv[h]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float a = c[q][2 * hh + i];
+            e[2 * q + i] = __float2bfloat16_rn(__bfloat162float(e[2 * q + i]) + bf16_round(scale * bf16_round(a)));
+          }
+        }
+        *reinterpret_cast<uint4*>(y + rows[h] * ldy + col0 + 8 * t) = yv[h];
+      }
+    }
+  }
+}
+
+// out[n*sn + j*sr] += scale * sum_m X[m,n] U[m,j].  CTA = 64 columns x WGM_ROWS rows, 8 warps = 8 row ranges.
+// Lane (g, t): rank row j = g; loads rows base + 4t + {0,1,2,3}, cols [col0 + 8g, +8) of X (the MMA's B operand,
+// n' = g for the i-th of its 8 columns) and U[those rows][g] (the A operand, rows j >= 8 are zero padding).
+constexpr int WGM_ROWS = 512;
+__global__ void __launch_bounds__(256) rank_wgrad_mma_kernel(const bf16_t* __restrict__ X, long long ldx,
+                                                             const void* __restrict__ U, int u_f32,
+                                                             float* __restrict__ out, long long sn, long long sr,
+                                                             float scale, int M, int N, int r) {
+  __shared__ float red[8][8][64 + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const long long col0 = static_cast<long long>(blockIdx.x) * 64;
+  const bool col_ok = col0 + 8 * g < N;
+  const long long rbeg = static_cast<long long>(blockIdx.y) * WGM_ROWS + warp * (WGM_ROWS / 8);
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+  for (int step = 0; step < WGM_ROWS / 8 / 16; step += 2) {  // 2 x 16 rows per pass: 8 X-loads in flight per lane
+    uint4 raw[2][4];
+    uint32_t a0[2], a2[2];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const long long base = rbeg + (step + s2) * 16 + 4 * t;
+      float uv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long m = base + q;
+        const bool ok = m < M;
+        raw[s2][q] = (ok && col_ok) ? ld_nc_v4(X + m * ldx + col0 + 8 * g) : zero;
+        uv[q] = 0.f;
+        if (ok && g < r)
+          uv[q] = u_f32 ? static_cast<const float*>(U)[m * r + g] : __bfloat162float(static_cast<const bf16_t*>(U)[m * r + g]);
+      }
+      a0[s2] = pack_bf16(uv[0], uv[1]);
+      a2[s2] = pack_bf16(uv[2], uv[3]);
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t sel = (i & 1) ? 0x7632u : 0x5410u;
+        const uint32_t b0 = __byte_perm(u32_of(raw[s2][0], i >> 1), u32_of(raw[s2][1], i >> 1), sel);
+        const uint32_t b1 = __byte_perm(u32_of(raw[s2][2], i >> 1), u32_of(raw[s2][3], i >> 1), sel);
+        mma_bf16_16816(acc[i], a0[s2], 0u, a2[s2], 0u, b0, b1);
+      }
+    }
+  }
+  // acc[i][0..1] = out^T[j = g][col0 + 8 (2t) + i], [col0 + 8 (2t + 1) + i]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[warp][g][16 * t + i] = acc[i][0];
+    red[warp][g][16 * t + 8 + i] = acc[i][1];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 8 * 64; o += 256) {
+    const int j = o >> 6, c = o & 63;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][j][c];
+    const long long n = col0 + c;
+    if (j < r && n < N) atomicAdd(out + n * sn + j * sr, scale * v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- RMSNorm backward
 // y = w * (x * rstd):  dx = rstd * (g - xhat * mean(g * xhat)), g = dy * w;  out = bf16(dx + add);  dw += dy * xhat
 constexpr int RB_THREADS = 128;
@@ -969,6 +1184,44 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, 
     static_cast<float*>(param)[i] = w;
 }
 
+// The same update over the WHOLE gradient arena in one launch: `chunks` (device, 4 x int64 per chunk: arena offset, length,
+// parameter base address, is_bf16 | element offset within the parameter << 1) maps 4096-element chunks to parameters.
+constexpr int ADAMW_CHUNK = 4096;
+__global__ void __launch_bounds__(256) adamw_multi_kernel(float* __restrict__ master, float* __restrict__ m,
+                                                          float* __restrict__ v, const float* __restrict__ g,
+                                                          const long long* __restrict__ chunks, float lr, float b1,
+                                                          float b2, float eps, float wd, float bc1, float bc2,
+                                                          const float* __restrict__ sumsq, float max_norm,
+                                                          float grad_scale) {
+  const long long* c = chunks + static_cast<long long>(blockIdx.x) * 4;
+  const long long off = c[0], len = c[1], pbase = c[2], meta = c[3];
+  const bool is_bf16 = (meta & 1) != 0;
+  const long long poff = meta >> 1;
+  float clip = grad_scale;
+  if (sumsq != nullptr && max_norm > 0.0f) {
+    const float norm = sqrtf(*sumsq) * grad_scale;
+    clip *= fminf(1.0f, max_norm / (norm + 1e-6f));
+  }
+  const float rbc2 = rsqrtf(bc2), step = lr / bc1;
+  for (long long i = threadIdx.x; i < len; i += 256) {
+    const long long a = off + i;
+    const float gi = g[a] * clip;
+    float w = master[a];
+    w *= 1.0f - lr * wd;
+    const float mi = b1 * m[a] + (1.0f - b1) * gi;
+    const float vi = b2 * v[a] + (1.0f - b2) * gi * gi;
+    m[a] = mi;
+    v[a] = vi;
+    const float denom = sqrtf(vi) * rbc2 + eps;
+    w -= step * mi / denom;
+    master[a] = w;
+    if (is_bf16)
+      reinterpret_cast<bf16_t*>(pbase)[poff + i] = __float2bfloat16_rn(w);
+    else
+      reinterpret_cast<float*>(pbase)[poff + i] = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- mask losses
 // One CTA per mask. out[0..3] = BCE-with-logits mean, Dice loss, IoU-MSE loss, Focal loss (model/MedPLIB.py:26-124);
 // sums[0..5] = sum bce, sum p, sum t, sum p*t, focal_pos, focal_neg (kept for the backward).
@@ -1025,6 +1278,12 @@ extern "C" int mpl_lora_down(const void* x, long long ldx, const void* A, long l
   if (M <= 0) return MPL_OK;
   if (x == nullptr || A == nullptr || u == nullptr || r < 1 || r > LORA_MAX_R) return MPL_ERR_ARG;
   if (K % 8 != 0 || ldx % 8 != 0 || lda % 8 != 0) return MPL_ERR_ALIGN;
+  if (r <= 8 && K % 32 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+    lora_down_mma_kernel<<<(M + 15) / 16, 256, 0, ST(stream)>>>(static_cast<const bf16_t*>(x), ldx,
+                                                                static_cast<const bf16_t*>(A), lda, u, u_is_f32, M, K, r,
+                                                                scale);
+    return launch_status();
+  }
   if (r <= LR8 && static_cast<size_t>(r) * K * 2 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
     static bool attr = false;
@@ -1050,6 +1309,13 @@ extern "C" int mpl_lora_up_add(void* y, long long ldy, const void* u, int u_is_f
                                long long bm_stride_r, float scale, int M, int N, int r, void* stream) {
   if (M <= 0 || N <= 0) return MPL_OK;
   if (y == nullptr || u == nullptr || Bm == nullptr || r < 1 || r > LORA_MAX_R) return MPL_ERR_ARG;
+  if (r <= 8 && N % 8 == 0 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    dim3 gm((N + 255) / 256, (M + UPM_ROWS - 1) / UPM_ROWS);
+    lora_up_add_mma_kernel<<<gm, 256, 0, ST(stream)>>>(static_cast<bf16_t*>(y), ldy, u, u_is_f32,
+                                                       static_cast<const bf16_t*>(Bm), bm_stride_n, bm_stride_r, scale, M,
+                                                       N, r);
+    return launch_status();
+  }
   if (r <= LR8 && N % 8 == 0 && ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
     dim3 g8((N + 2047) / 2048, (M + UP8_ROWS - 1) / UP8_ROWS);
     lora_up_add8_kernel<<<g8, 256, 0, ST(stream)>>>(static_cast<bf16_t*>(y), ldy, u, u_is_f32,
@@ -1066,6 +1332,12 @@ extern "C" int mpl_rank_wgrad(const void* X, long long ldx, const void* U, int u
                               long long out_stride_r, float scale, int M, int N, int r, void* stream) {
   if (M <= 0 || N <= 0) return MPL_OK;
   if (X == nullptr || U == nullptr || out == nullptr || r < 1 || r > LORA_MAX_R) return MPL_ERR_ARG;
+  if (r <= 8 && N % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    dim3 gm((N + 63) / 64, (M + WGM_ROWS - 1) / WGM_ROWS);
+    rank_wgrad_mma_kernel<<<gm, 256, 0, ST(stream)>>>(static_cast<const bf16_t*>(X), ldx, U, u_is_f32, out, out_stride_n,
+                                                      out_stride_r, scale, M, N, r);
+    return launch_status();
+  }
   if (r <= LR8 && N % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
     dim3 g8((N + 255) / 256, (M + WG8_ROWS - 1) / WG8_ROWS);
     rank_wgrad8_kernel<<<g8, 256, 0, ST(stream)>>>(static_cast<const bf16_t*>(X), ldx, U, u_is_f32, out, out_stride_n,
@@ -1262,6 +1534,18 @@ extern "C" int mpl_adamw(float* master, float* m, float* v, const float* grad, v
   adamw_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ST(stream)>>>(master, m, v, grad, param, param_is_bf16, n, lr,
                                                                               beta1, beta2, eps, weight_decay, bc1, bc2,
                                                                               sumsq, max_norm, grad_scale);
+  return launch_status();
+}
+
+extern "C" int mpl_adamw_multi(float* master, float* m, float* v, const float* grad, const long long* chunks,
+                               int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                               const float* sumsq, float max_norm, float grad_scale, void* stream) {
+  if (n_chunks <= 0) return MPL_OK;
+  if (master == nullptr || m == nullptr || v == nullptr || grad == nullptr || chunks == nullptr || step < 1)
+    return MPL_ERR_ARG;
+  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
+  adamw_multi_kernel<<<n_chunks, 256, 0, ST(stream)>>>(master, m, v, grad, chunks, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                       bc2, sumsq, max_norm, grad_scale);
   return launch_status();
 }
 

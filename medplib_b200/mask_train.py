@@ -79,8 +79,9 @@ class LinFn(torch.autograd.Function):
         gW = tr.arena.of(ctx.W)
         if gW is not None:
             T.gemm_small(dy, x, out=gW, trans_a=True, accumulate=True)
-        elif ctx.needs_input_grad[1]:
-            dW = T.gemm_small(dy, x, trans_a=True, out_dtype=bf16)
+        elif ctx.needs_input_grad[1]:  # tape tensor: fp32 accumulate (split-K capable), handed back in bf16
+            dW32 = torch.zeros((dy.shape[1], x.shape[1]), dtype=f32, device=dy.device)
+            dW = T.gemm_small(dy, x, out=dW32, trans_a=True, accumulate=True).to(bf16)
         if ctx.b is not None:
             gb = tr.arena.of(ctx.b)
             if gb is not None:
@@ -121,24 +122,24 @@ def ln(tr, x, mod, eps=None):
 
 
 class AttnFn(torch.autograd.Function):
-    """softmax(q k^T / sqrt(d)) v per head; q [Tq, H*d], k / v [Tk, H*d]."""
+    """softmax(q k^T / sqrt(d)) v per (sample, head); q [B*Tq, H*d], k / v [B*Tk, H*d] (samples stacked along rows)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, H):
+    def forward(ctx, q, k, v, H, B):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
-        Tq, C = q.shape
-        Tk = k.shape[0]
+        C = q.shape[1]
+        Tq, Tk = q.shape[0] // B, k.shape[0] // B
         d = C // H
-        ctx.H, ctx.scale = H, 1.0 / math.sqrt(d)
-        o = ops.attention(q.view(1, Tq, H, d), k.view(1, Tk, H, d), v.view(1, Tk, H, d), ctx.scale)
+        ctx.H, ctx.B, ctx.scale = H, B, 1.0 / math.sqrt(d)
+        o = ops.attention(q.view(B, Tq, H, d), k.view(B, Tk, H, d), v.view(B, Tk, H, d), ctx.scale)
         ctx.save_for_backward(q, k, v)
-        return o.view(Tq, C)
+        return o.view(B * Tq, C)
 
     @staticmethod
     def backward(ctx, do):
         q, k, v = ctx.saved_tensors
-        dq, dk, dv = T.attn_small_bwd(q, k, v, do.contiguous(), ctx.H, ctx.scale)
-        return dq, dk, dv, None
+        dq, dk, dv = T.attn_small_bwd(q, k, v, do.contiguous(), ctx.H, ctx.scale, batch=ctx.B)
+        return dq, dk, dv, None, None
 
 
 class AddFn(torch.autograd.Function):
@@ -229,14 +230,14 @@ def text_hidden_fcs(tr, fc, rows):
     return lin_mod(tr, lin_mod(tr, rows, fc[0], act="relu"), fc[2])
 
 
-def _attention(tr, a, q_in, k_in, v_in, H):
+def _attention(tr, a, q_in, k_in, v_in, H, B):
     q = lin_mod(tr, q_in, a.q_proj)
     k = lin_mod(tr, k_in, a.k_proj)
     v = lin_mod(tr, v_in, a.v_proj)
-    return lin_mod(tr, AttnFn.apply(q, k, v, H), a.out_proj)
+    return lin_mod(tr, AttnFn.apply(q, k, v, H, B), a.out_proj)
 
 
-def _consts(tr, model):
+def _consts(tr, model, B):
     c = getattr(tr, "_mask_consts", None)
     if c is None:
         vm = model.model.visual_model
@@ -248,48 +249,57 @@ def _consts(tr, model):
         shuffle = src.reshape(-1)
         inv = torch.empty_like(shuffle)
         inv[shuffle] = torch.arange(shuffle.numel())
-        c = dict(grid=grid, dense_pe=engine.dense_pe(gauss.detach(), grid).to(dev),
-                 shuffle=shuffle.to(torch.int32).to(dev), shuffle_inv=inv.to(torch.int32).to(dev))
+        c = dict(grid=grid, dense_pe=engine.dense_pe(gauss.detach(), grid).to(dev), shuffle=shuffle, shuffle_inv=inv,
+                 dev=dev, per_batch={})
         tr._mask_consts = c
-    return c
+    if B not in c["per_batch"]:
+        P = c["shuffle"].numel()
+        off = (torch.arange(B) * P).repeat_interleave(P)
+        c["per_batch"][B] = dict(
+            dense_pe=c["dense_pe"].repeat(B, 1).contiguous(),
+            shuffle=(c["shuffle"].repeat(B) + off).to(torch.int32).to(c["dev"]),
+            shuffle_inv=(c["shuffle_inv"].repeat(B) + off).to(torch.int32).to(c["dev"]))
+    return c, c["per_batch"][B]
 
 
 def mask_decoder(tr, model, img_tok, text):
-    """img_tok bf16 [g*g, D] (frozen image embedding, token-major), text [D] (tape) -> (low_res [1, 4g, 4g],
-    iou [1]); multimask_output=False (mask / IoU of token 0), like MedPLIB.py:488-495."""
+    """img_tok bf16 [B, g*g, D] (frozen image embeddings, token-major), text [B, D] (tape) -> (low_res list of
+    [1, 4g, 4g], iou list of [1]); multimask_output=False (mask / IoU of token 0), like MedPLIB.py:488-495. The B masks
+    of a step run as ONE batch (samples stacked along the row dimension of every kernel)."""
     vm = model.model.visual_model
     md, tf = vm.mask_decoder, vm.mask_decoder.transformer
-    c = _consts(tr, model)
+    B, Tn, D = img_tok.shape
+    c, cb = _consts(tr, model, B)
     g = c["grid"]
-    Tn = g * g
     H = 8
-    tokens0 = torch.cat([param(tr, md.iou_token.weight), param(tr, md.mask_tokens.weight), text.view(1, -1)], dim=0)
-    keys = ops.add(img_tok.contiguous(), vm.prompt_encoder.no_mask_embed.weight.detach().reshape(-1))
-    dpe = c["dense_pe"]
+    base = torch.cat([param(tr, md.iou_token.weight), param(tr, md.mask_tokens.weight)], dim=0)  # [5, D]
+    nt = base.shape[0] + 1
+    tokens0 = torch.cat([base.unsqueeze(0).expand(B, -1, -1), text.view(B, 1, D)], dim=1).reshape(B * nt, D)
+    keys = ops.add(img_tok.reshape(B * Tn, D).contiguous(), vm.prompt_encoder.no_mask_embed.weight.detach().reshape(-1))
+    dpe = cb["dense_pe"]
     tok, tpe = tokens0, tokens0
 
     def token_to_image(tok, keys, a, norm):
-        o = _attention(tr, a, add(tok, tpe), add(keys, dpe), keys, H)
+        o = _attention(tr, a, add(tok, tpe), add(keys, dpe), keys, H, B)
         return ln(tr, add(tok, o), norm)
 
     for i, L in enumerate(tf.layers):
         if i == 0:
-            tok = _attention(tr, L.self_attn, tok, tok, tok, H)
+            tok = _attention(tr, L.self_attn, tok, tok, tok, H, B)
         else:
             qk = add(tok, tpe)
-            tok = add(tok, _attention(tr, L.self_attn, qk, qk, tok, H))
+            tok = add(tok, _attention(tr, L.self_attn, qk, qk, tok, H, B))
         tok = ln(tr, tok, L.norm1)
         tok = token_to_image(tok, keys, L.cross_attn_token_to_image, L.norm2)
         m = lin_mod(tr, lin_mod(tr, tok, L.mlp.lin1, act="relu"), L.mlp.lin2)
         tok = ln(tr, add(tok, m), L.norm3)
-        o = _attention(tr, L.cross_attn_image_to_token, add(keys, dpe), add(tok, tpe), tok, H)
+        o = _attention(tr, L.cross_attn_image_to_token, add(keys, dpe), add(tok, tpe), tok, H, B)
         keys = ln(tr, add(keys, o), L.norm4)
     tok = token_to_image(tok, keys, tf.final_attn_token_to_image, tf.norm_final_attn)
 
     # upscaling: ConvTranspose2d(k2,s2) = one GEMM against the [(ky,kx,co), ci] repack of its weight, rows become
-    # (pixel, tap); LayerNorm2d = LayerNorm over the channel rows; final row gather into raster order
+    # (sample, pixel, tap); LayerNorm2d = LayerNorm over the channel rows; final row gather into raster order
     up = md.output_upscaling
-    D = tok.shape[1]
     C4, C8 = D // 4, D // 8
 
     def convt_w(conv):
@@ -301,28 +311,35 @@ def mask_decoder(tr, model, img_tok, text):
 
     w0, b0 = convt_w(up[0])
     w1, b1 = convt_w(up[3])
-    u0 = lin(tr, keys, w0, b0).view(4 * Tn, C4)
+    u0 = lin(tr, keys, w0, b0).view(4 * B * Tn, C4)
     u0 = GeluFn.apply(ln(tr, u0, up[1], eps=1e-6))
-    u1 = GeluFn.apply(lin(tr, u0, w1, b1)).view(16 * Tn, C8)
-    ups = RowsFn.apply(u1, c["shuffle"], c["shuffle_inv"])  # [(4g)^2, C8] raster order
+    u1 = GeluFn.apply(lin(tr, u0, w1, b1)).view(16 * B * Tn, C8)
+    ups = RowsFn.apply(u1, cb["shuffle"], cb["shuffle_inv"])  # [B * (4g)^2, C8], raster order per sample
+    P = 16 * Tn
 
+    tok3 = tok.view(B, nt, D)
     hy = md.output_hypernetworks_mlps[0].layers
-    hv = lin_mod(tr, lin_mod(tr, lin_mod(tr, tok[1:2], hy[0], act="relu"), hy[1], act="relu"), hy[2])  # [1, C8]
-    low = lin(tr, hv, ups)  # [1, (4g)^2] = hyper_in @ upscaled
+    hv = lin_mod(tr, lin_mod(tr, lin_mod(tr, tok3[:, 1], hy[0], act="relu"), hy[1], act="relu"), hy[2])  # [B, C8]
     io = md.iou_prediction_head.layers
-    iou = lin_mod(tr, lin_mod(tr, lin_mod(tr, tok[0:1], io[0], act="relu"), io[1], act="relu"), io[2])  # [1, n_mask]
-    return low.view(1, 4 * g, 4 * g), iou[0, 0:1]
+    iou = lin_mod(tr, lin_mod(tr, lin_mod(tr, tok3[:, 0], io[0], act="relu"), io[1], act="relu"), io[2])  # [B, n_mask]
+    lows = [lin(tr, hv[b:b + 1], ups[b * P:(b + 1) * P]).view(1, 4 * g, 4 * g) for b in range(B)]  # hyper_in @ upscaled
+    return lows, [iou[b, 0:1] for b in range(B)]
 
 
 def mask_head_losses(tr, model, pred_embeddings, image_embeddings, resize_list, size_list, masks_list):
     """MedPLIB.py:473-545: one mask per [SEG] embedding; returns the SUMS over masks of the four losses (tape f32
     scalars) and num_masks; the caller divides and weights like :547-559."""
-    B, C, g, _ = image_embeddings.shape
-    tok = image_embeddings.permute(0, 2, 3, 1).reshape(B, g * g, C)
+    n = len(pred_embeddings)
+    Bi, C, g, _ = image_embeddings.shape
+    tok = image_embeddings.permute(0, 2, 3, 1).reshape(Bi, g * g, C)
     sums = {"bce": 0, "dice": 0, "iou": 0, "focal": 0, "num_masks": 0}
     pred_masks = []
-    for i in range(len(pred_embeddings)):
-        low, iou = mask_decoder(tr, model, tok[i], pred_embeddings[i])
+    if n == 0:
+        sums["pred_masks"] = pred_masks
+        return sums
+    lows, ious = mask_decoder(tr, model, tok[:n], pred_embeddings)
+    for i in range(n):
+        low, iou = lows[i], ious[i]
         inp, orig = resize_list[i], size_list[i]
         pad_h, pad_w = low.shape[-2] - inp[0], low.shape[-1] - inp[1]
         top, left = pad_h // 2, pad_w // 2

@@ -184,6 +184,16 @@ class FusedAdamW:
         self.v = torch.zeros_like(arena.flat)
         self.sumsq = torch.zeros(1, dtype=f32, device=dev)
         self.t = 0
+        # chunk table of the one-launch update: every 4096-element chunk of the arena -> its parameter
+        rows = []
+        for p, o in zip(arena.params, arena.offsets):
+            if not p.is_contiguous():
+                raise _lib.MplError("trainable parameters must be contiguous")
+            n, bf = p.numel(), int(p.dtype == bf16)
+            for c in range(0, n, 4096):
+                rows.append((o + c, min(4096, n - c), p.data_ptr(), bf | (c << 1)))
+        self.chunks = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self._ptrs = [p.data_ptr() for p in arena.params]
 
     def step(self, grad_scale=1.0, lr=None):
         a = self.arena
@@ -194,11 +204,11 @@ class FusedAdamW:
             T.sumsq(a.flat, self.sumsq)
             sumsq = self.sumsq
         lr = self.lr if lr is None else lr
-        for p, o in zip(a.params, a.offsets):
-            n = p.numel()
-            T.adamw(self.master[o:o + n], self.m[o:o + n], self.v[o:o + n], a.flat[o:o + n], p.data, lr, self.betas[0],
-                    self.betas[1], self.eps, self.wd, self.t, sumsq_dev=sumsq, max_norm=self.max_norm or 0.0,
-                    grad_scale=grad_scale)
+        if [p.data_ptr() for p in a.params] != self._ptrs:
+            raise _lib.MplError("a trainable parameter's storage moved since the optimizer was built; call "
+                                "model.trainer(...) again")
+        T.adamw_multi(self.master, self.m, self.v, a.flat, self.chunks, lr, self.betas[0], self.betas[1], self.eps,
+                      self.wd, self.t, sumsq_dev=sumsq, max_norm=self.max_norm or 0.0, grad_scale=grad_scale)
 
     def grad_norm(self, grad_scale=1.0):
         return self.sumsq.sqrt() * grad_scale

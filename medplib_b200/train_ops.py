@@ -233,6 +233,16 @@ def adamw(master, m, v, grad, param, lr, beta1, beta2, eps, weight_decay, step, 
                              _ptr(sumsq_dev), _F(max_norm), _F(grad_scale), _stream()), "mpl_adamw")
 
 
+def adamw_multi(master, m, v, grad, chunks, lr, beta1, beta2, eps, weight_decay, step, sumsq_dev=None, max_norm=0.0,
+                grad_scale=1.0):
+    """One launch over the arena; chunks int64 [n, 4] on the device (see mpl_adamw_multi)."""
+    lib = _lib.load()
+    _req(chunks, torch.int64, "chunks")
+    _lib.check(lib.mpl_adamw_multi(_ptr(master), _ptr(m), _ptr(v), _ptr(grad), _ptr(chunks), int(chunks.shape[0]), _F(lr),
+                                   _F(beta1), _F(beta2), _F(eps), _F(weight_decay), int(step), _ptr(sumsq_dev),
+                                   _F(max_norm), _F(grad_scale), _stream()), "mpl_adamw_multi")
+
+
 def mask_losses(pred, gt, pred_iou):
     """pred bf16 [..] logits of ONE mask, gt f32 same numel, pred_iou bf16 scalar tensor -> (out4 f32, sums6 f32)."""
     lib = _lib.load()
@@ -304,18 +314,18 @@ def act_bwd(x, dy, act):
     return dx
 
 
-def attn_small_bwd(q, k, v, d_o, H, scale):
-    """q [Tq, H*d], k / v [Tk, H*d], d_o [Tq, H*d] (inner stride 1) -> dq, dk, dv (bf16, contiguous)."""
+def attn_small_bwd(q, k, v, d_o, H, scale, batch=1):
+    """q [B*Tq, H*d], k / v [B*Tk, H*d], d_o like q (inner stride 1, batches stacked) -> dq, dk, dv (bf16, contiguous)."""
     lib = _lib.load()
-    Tq, C = q.shape
-    Tk = k.shape[0]
+    C = q.shape[1]
+    Tq, Tk = q.shape[0] // batch, k.shape[0] // batch
     d = C // H
     dq, dk, dv = torch.empty_like(q.contiguous()), torch.empty_like(k.contiguous()), torch.empty_like(v.contiguous())
     for t in (q, k, v, d_o):
         assert t.stride(1) == 1
     _lib.check(lib.mpl_attn_small_bwd(_ptr(q), _ll(q.stride(0)), _ptr(k), _ll(k.stride(0)), _ptr(v), _ll(v.stride(0)),
                                       _ptr(d_o), _ll(d_o.stride(0)), _ptr(dq), _ll(C), _ptr(dk), _ll(C), _ptr(dv), _ll(C),
-                                      Tq, Tk, H, d, _F(scale), _stream()), "mpl_attn_small_bwd")
+                                      batch, Tq, Tk, H, d, _F(scale), _stream()), "mpl_attn_small_bwd")
     return dq, dk, dv
 
 

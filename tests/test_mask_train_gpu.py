@@ -134,3 +134,25 @@ def test_mask_losses_bwd(dev, shape):
     dpred, dpi = T.mask_losses_bwd(pred.to(dev), gt.to(dev), piou.to(dev), sums, w4.to(dev))
     _close(dpred, pr.grad, 2e-2, "dpred")
     _close(dpi, ir.grad, 1e-2, "dpred_iou")
+
+
+def test_attn_small_bwd_batched(dev):
+    """Samples stacked along the row dimension (the B masks of a train step run as one batch)."""
+    from medplib_b200 import train_ops as T
+    B, Tq, Tk, H, d = 3, 6, 256, 8, 16
+    g = _g(99)
+    C = H * d
+    q = torch.randn(B * Tq, C, generator=g).to(bf16)
+    k = torch.randn(B * Tk, C, generator=g).to(bf16)
+    v = torch.randn(B * Tk, C, generator=g).to(bf16)
+    do = torch.randn(B * Tq, C, generator=g).to(bf16)
+    qr, kr, vr = (t.float().requires_grad_() for t in (q, k, v))
+    q4 = qr.view(B, Tq, H, d).permute(0, 2, 1, 3)
+    k4 = kr.view(B, Tk, H, d).permute(0, 2, 1, 3)
+    v4 = vr.view(B, Tk, H, d).permute(0, 2, 1, 3)
+    o = (torch.softmax(q4 @ k4.transpose(-1, -2) / math.sqrt(d), -1) @ v4).permute(0, 2, 1, 3).reshape(B * Tq, C)
+    o.backward(do.float())
+    dq, dk, dv = T.attn_small_bwd(q.to(dev), k.to(dev), v.to(dev), do.to(dev), H, 1.0 / math.sqrt(d), batch=B)
+    _close(dq, qr.grad, 2e-2, "dq")
+    _close(dk, kr.grad, 2e-2, "dk")
+    _close(dv, vr.grad, 2e-2, "dv")
