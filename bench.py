@@ -326,7 +326,20 @@ def train_batch(B, seed):
     images_clip = torch.randn(B, 3, 336, 336, generator=g)
     images = torch.randn(B, 3, 256, 256, generator=g)
     gts = [(torch.rand(336, 336, generator=g) > 0.7).float() for _ in range(B)]
-    return ids, labels, am, images_clip, images, gts
+    # a region slot (-300) with a 24x24 blob mask in every second sample (rp_flag batches, medplib_arch.py:426-429)
+    region_masks, valid = [], []
+    for b in range(B):
+        if b % 2 == 0:
+            ids[b, 12] = -300
+            labels[b, 12] = -100
+            m = torch.zeros(24, 24)
+            y0, x0 = int(torch.randint(0, 12, (1,), generator=g)), int(torch.randint(0, 12, (1,), generator=g))
+            m[y0:y0 + 10, x0:x0 + 10] = 1.0
+            region_masks.append([m])
+            valid.append([True])
+        else:
+            valid.append([False])
+    return ids, labels, am, images_clip, images, gts, region_masks, valid
 
 
 def run_train(args, rank, world, dev):
@@ -349,16 +362,18 @@ def run_train(args, rank, world, dev):
     m.train()
     tr = m.trainer(lr=3e-4)
     B = args.batch
-    ids, labels, am, images_clip, images, gts = train_batch(B, rank)
+    ids, labels, am, images_clip, images, gts, region_masks, valid = train_batch(B, rank)
+    d_rm = [[x.to(dev) for x in r] for r in region_masks]
     d_in = dict(ids=ids.to(dev), labels=labels.to(dev), am=am.to(dev), clip=images_clip.to(dev).to(bf16),
                 img=images.to(dev).to(bf16), gts=[x.to(dev) for x in gts])
     h_in = dict(ids=ids.pin_memory(), labels=labels.pin_memory(), am=am.pin_memory(), clip=images_clip.pin_memory(),
                 img=images.pin_memory(), gts=[x.pin_memory() for x in gts])
 
     def step(x, read_loss=False):
-        out = m(images=x["img"], images_clip=x["clip"], input_ids=x["ids"], region_masks=None, labels=x["labels"],
-                attention_mask=x["am"], offset=None, masks_list=x["gts"], label_list=x["gts"],
-                resize_list=[(256, 256)] * B, inference=False, seg_flag=True)
+        out = m(images=x["img"], images_clip=x["clip"], input_ids=x["ids"], region_masks=d_rm,
+                valid_region_masks_bool=valid, labels=x["labels"], attention_mask=x["am"], offset=None,
+                masks_list=x["gts"], label_list=x["gts"], resize_list=[(256, 256)] * B, inference=False, seg_flag=True,
+                rp_flag=True)
         out["loss"].backward()
         tr.step()
         return float(out["loss"].detach()) if read_loss else None
@@ -437,8 +452,8 @@ def run_train(args, rank, world, dev):
         "config": {"workload": f"Stage-IV-flags train step bf16, micro-batch {B}/GPU x {world} GPU (global {B * world}), "
                                f"T={T} (64 ids + 576 image tokens), 1 <SEG> + 336x336 GT mask per sample; MoE dense 32 "
                                "layers E=2 top-1 cf=1.5; LoRA r=8 a=16 on q,v,gate,up,down; sft wg,lm_head,embed_tokens,"
-                               "mask_decoder,text_hidden_fcs; fwd + bwd + grad all-reduce + clip + AdamW; no region "
-                               "slots (region_fea_adapter gradient not built yet)",
+                               "mask_decoder,text_hidden_fcs,region_fea_adapter; a 24x24 region slot in every second "
+                               "sample; fwd + bwd + grad all-reduce + clip + AdamW",
                    "weights": "random init, 11.07 B params", "parallelism": f"dp{world}",
                    "trainable_params": int(tr.arena.numel), "l2": "activations + weights >> 126 MB L2",
                    "small": bool(args.small)},

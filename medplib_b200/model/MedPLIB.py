@@ -472,11 +472,14 @@ class MedPLIBForCausalLM(PreTrainedModel):
         del ones
         return ops.layernorm(y, me.norm.weight, me.norm.bias, me.norm.eps)
 
-    def extract_region_feature(self, region_feature_map, region_masks, original_dtype=None, return_dtype=None):
-        """medplib_arch.py:580-614. Coordinates are rounded to the run dtype exactly like the reference does."""
+    def extract_region_feature(self, region_feature_map, region_masks, original_dtype=None, return_dtype=None,
+                               raw_feature_map=None, raw_out=None):
+        """medplib_arch.py:580-614. Coordinates are rounded to the run dtype exactly like the reference does.
+        raw_feature_map / raw_out (train step): the same points also sample the raw CLIP features — the region feature
+        is linear in the adapter (sample-mean and Linear commute), so d adapter = d feature (x) sampled raw feature."""
         out = []
         assert len(region_feature_map) == len(region_masks), f"{len(region_feature_map)}, {len(region_masks)}"
-        for fmap, masks in zip(region_feature_map, region_masks):
+        for bi, (fmap, masks) in enumerate(zip(region_feature_map, region_masks)):
             if len(masks) == 0:
                 out.append(None)
                 continue
@@ -489,6 +492,8 @@ class MedPLIBForCausalLM(PreTrainedModel):
                     nz = nz[torch.randperm(nz.shape[0])[: self.get_model().max_sample_point]]
                 pts = nz.flip(dims=(1,)).to(fmap.dtype).float()
                 feats.append(ops.region_sample_mean(fmap, pts.to(fmap.device), h, w))
+                if raw_out is not None:
+                    raw_out.append(ops.region_sample_mean(raw_feature_map[bi], pts.to(fmap.device), h, w))
             out.append(torch.stack(feats))
         return out
 
@@ -526,14 +531,22 @@ class MedPLIBForCausalLM(PreTrainedModel):
             feat_blocks = [f for f in img_f]
             per_token = True
         else:
-            _, img_f, rmap = self.encode_images(images, region_flag)
+            raw_f, img_f, rmap = self.encode_images(images, region_flag)
             feat_blocks = [f for f in img_f]
         region_features = None
         valid = None
+        self._region_ctx = None
+        raw_samples = None
         if region_flag:
             valid = [any(item) for item in valid_region_masks_bool]
-            rmap = rmap[torch.tensor(valid, device=rmap.device)]
-            region_features = self.extract_region_feature(rmap, region_masks)
+            vsel = torch.tensor(valid, device=rmap.device)
+            rmap = rmap[vsel]
+            adapter = self.get_model().region_fea_adapter
+            want_grad = labels is not None and torch.is_grad_enabled() and adapter.weight.requires_grad
+            raw_samples = [] if want_grad else None
+            region_features = self.extract_region_feature(rmap, region_masks,
+                                                          raw_feature_map=raw_f[vsel] if want_grad else None,
+                                                          raw_out=raw_samples)
 
         # ---- host-side plan: one int per output row
         D = self.config.hidden_size
@@ -597,6 +610,14 @@ class MedPLIBForCausalLM(PreTrainedModel):
         feats_all = torch.cat(feat_blocks + ([torch.stack(extra_rows)] if extra_rows else []), dim=0).contiguous()
         embeds = ops.gather_rows(idx.reshape(-1), self.model.embed_tokens.weight, feats_all, D=D).view(len(plans), T, D)
         self._splice_idx = idx.reshape(-1)  # adjoint of the splice (embed_tokens gradient) in the train step
+        if raw_samples:
+            # output rows that hold region features, in extra_rows order (plan entries <= -(off) - 2)
+            pos = [b * T + t for b, p in enumerate(plans) for t, v in enumerate(p) if v <= -off - 2]
+            order = sorted(range(len(pos)), key=lambda i: -(plans[pos[i] // T][pos[i] % T]) - 2 - off)
+            pos = [pos[i] for i in order]
+            assert len(pos) == len(raw_samples)
+            self._region_ctx = dict(pos=torch.tensor(pos, dtype=torch.int32, device=dev),
+                                    sampled=torch.stack(raw_samples).contiguous())
         lab_t = None
         if labels is not None:
             lab_t = torch.tensor([l + [IGNORE_INDEX] * (T - len(l)) for l in new_labels], dtype=labels.dtype, device=dev)
@@ -621,6 +642,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
         if output_attentions:
             raise _lib.MplError("attention maps are never materialised by the fused attention kernels")
         self._splice_idx = None
+        self._region_ctx = None
         if inputs_embeds is None:
             input_ids, attention_mask, past_key_values, inputs_embeds, labels = \
                 self.prepare_inputs_labels_for_multimodal(input_ids, attention_mask, past_key_values, labels, images,
@@ -682,7 +704,8 @@ class MedPLIBForCausalLM(PreTrainedModel):
         if attention_mask is not None and not bool(attention_mask.all()):
             kv_mask = attention_mask
         hidden, l_aux = tr.stack_hidden(inputs_embeds, kv_mask=kv_mask, moe_noise=moe_noise,
-                                        splice_idx=self._splice_idx)
+                                        splice_idx=self._splice_idx, region_ctx=getattr(self, "_region_ctx", None))
+        self._region_ctx = None
         self._fire_gate_hooks(tr.last_gate_logits)
         loss, logits = tr.head_ce(hidden, labels)
         moe_losses = list(l_aux.unbind(0)) if l_aux.numel() > 0 else []

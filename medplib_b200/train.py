@@ -487,9 +487,9 @@ class _StackFn(torch.autograd.Function):
     """hidden = decoder_stack(embeds). `anchor` is a dummy leaf that makes the output require grad."""
 
     @staticmethod
-    def forward(ctx, anchor, tr, embeds, B, Tn, kv_mask, moe_noise, splice_idx):
+    def forward(ctx, anchor, tr, embeds, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx):
         hidden, l_aux, gate_logits, saved = tr.stack.forward(embeds, B, Tn, kv_mask, moe_noise)
-        ctx.tr, ctx.saved, ctx.splice_idx = tr, saved, splice_idx
+        ctx.tr, ctx.saved, ctx.splice_idx, ctx.region_ctx = tr, saved, splice_idx, region_ctx
         tr.last_gate_logits = gate_logits
         if l_aux is None:
             l_aux = torch.zeros(0, dtype=f32, device=embeds.device)
@@ -512,8 +512,18 @@ class _StackFn(torch.autograd.Function):
             T.scatter_add_rows(dx0, ctx.splice_idx, dtable=g_emb)
             if tr.reducer is not None:
                 tr.reducer.ready(tr.arena.end_of(tr.embed_weight))
+        if ctx.region_ctx is not None:
+            # region_fea_adapter (medplib_arch.py:131,208,580-614): feature = sampled_raw_clip W^T + b, so
+            # dW += dfeat^T sampled_raw, db += sum dfeat, with dfeat = the input-embedding gradient at the region slots
+            ad = tr.model.model.region_fea_adapter
+            gW, gb = tr.arena.of(ad.weight), tr.arena.of(ad.bias)
+            dfeat = ops.gather_rows(ctx.region_ctx["pos"], table=dx0)
+            if gW is not None:
+                T.gemm_small(dfeat, ctx.region_ctx["sampled"], out=gW, trans_a=True, accumulate=True)
+            if gb is not None:
+                T.col_sum(dfeat, gb)
         ctx.saved = None
-        return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 7
+        return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 8
 
 
 class _HeadCEFn(torch.autograd.Function):
@@ -609,10 +619,10 @@ class Trainer:
         return sorted(named, key=key)
 
     # tape
-    def stack_hidden(self, embeds, kv_mask=None, moe_noise=None, splice_idx=None):
+    def stack_hidden(self, embeds, kv_mask=None, moe_noise=None, splice_idx=None, region_ctx=None):
         B, Tn, D = embeds.shape
         x = embeds.to(bf16).reshape(B * Tn, D).contiguous()
-        return _StackFn.apply(self.anchor, self, x, B, Tn, kv_mask, moe_noise, splice_idx)
+        return _StackFn.apply(self.anchor, self, x, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx)
 
     def head_ce(self, hidden, labels):
         return _HeadCEFn.apply(hidden, self, labels)

@@ -13,15 +13,25 @@ from . import arch, heads, llama, pipeline, sam
 
 
 def train_losses(sd, cfg, images_clip, images, input_ids, labels, attention_mask, masks_list, label_sizes,
-                 resize_list, seg_token_idx, w, seg_flag=True, rts_uniforms=None):
+                 resize_list, seg_token_idx, w, seg_flag=True, rts_uniforms=None, region_masks=None,
+                 valid_region=None):
     """Returns (10-key loss dict, aux dict with routing / hidden states for diagnostics). ``w`` = dict(ce, bce, dice,
     iou, focal) loss weights (MedPLIB.py:233-240)."""
     with torch.no_grad():
-        _, x = pipeline.encode_images(sd, cfg, images_clip)
+        feats, x = pipeline.encode_images(sd, cfg, images_clip)
         if seg_flag:
             image_emb = sam.image_encoder(sd, pipeline.SAM + "image_encoder.", images,
                                           num_heads=cfg["sam"]["num_heads"])
+    region_feats = None
+    if region_masks is not None and len(region_masks) > 0:
+        # medplib_arch.py:208,426-429,580-614: region_fea_adapter on the raw CLIP features of the valid samples, then
+        # point-sampled means spliced at the -300 slots (differentiable w.r.t. the adapter)
+        import torch.nn.functional as F
+        rmap = F.linear(feats, sd["model.region_fea_adapter.weight"], sd["model.region_fea_adapter.bias"])
+        rmap = rmap[torch.tensor([bool(v) for v in valid_region])]
+        region_feats = arch.region_features(rmap, region_masks, 512, rmap.dtype, rmap.dtype)
     emb, lab, am = arch.splice(sd["model.embed_tokens.weight"], input_ids, labels, attention_mask, x,
+                               region_feats=region_feats, valid_region=valid_region,
                                use_im_start_end=cfg.get("mm_use_im_start_end", True))
     out = llama.model_forward(sd, cfg["llama"], emb, am, training=True, rts_uniforms=rts_uniforms)
     hidden = out["last_hidden_state"]

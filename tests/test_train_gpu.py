@@ -49,13 +49,16 @@ def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,d
     return m, sd, ocfg
 
 
-def batch(B=2, n_text=14, seg=False, pad=False, seed=5):
+def batch(B=2, n_text=14, seg=False, pad=False, seed=5, region=False):
     g = torch.Generator().manual_seed(seed)
     ids = torch.randint(3, 290, (B, n_text), generator=g)
     ids[:, 2] = -200
     labels = ids.clone()
     labels[:, :6] = -100
     am = torch.ones_like(ids, dtype=torch.bool)
+    if region:  # one region slot per sample (medplib_arch.py:426-429): -300 after the image, no loss on it
+        ids[:, 7] = -300
+        labels[:, 7] = -100
     if seg:
         ids[:, 9] = SEG
         labels[:, 9] = SEG
@@ -65,15 +68,22 @@ def batch(B=2, n_text=14, seg=False, pad=False, seed=5):
     clip_img = torch.randn(B, 3, 56, 56, generator=g).to(bf16)
     sam_img = torch.randn(B, 3, 256, 256, generator=g).to(bf16)
     gts = [(torch.rand(70, 90, generator=g) > 0.6).float() for _ in range(B)]
+    if region:
+        rm = [[(torch.rand(8, 8, generator=g) > 0.6).float()] for _ in range(B)]
+        for r in rm:
+            r[0][3, 4] = 1.0
+        return ids, labels, am, clip_img, sam_img, gts, rm
     return ids, labels, am, clip_img, sam_img, gts
 
 
-def oracle_run(sd, ocfg, b, seg_flag, noise):
+def oracle_run(sd, ocfg, b, seg_flag, noise, dtype=torch.float32):
     from oracle import train as otrain
-    ids, labels, am, clip_img, sam_img, gts = b
-    out, aux = otrain.train_losses(sd, ocfg, clip_img.float(), sam_img.float(), ids, labels, am, gts,
+    ids, labels, am, clip_img, sam_img, gts = b[:6]
+    rm = b[6] if len(b) > 6 else None
+    out, aux = otrain.train_losses(sd, ocfg, clip_img.to(dtype), sam_img.to(dtype), ids, labels, am, gts,
                                    [tuple(g.shape) for g in gts], [(256, 256)] * len(gts), SEG, W, seg_flag=seg_flag,
-                                   rts_uniforms=noise)
+                                   rts_uniforms=noise, region_masks=rm,
+                                   valid_region=[True] * len(gts) if rm is not None else None)
     return out, aux
 
 
@@ -90,16 +100,12 @@ def oracle_pair(m, sd, ocfg, b, seg_flag, noise, train_names):
     bf16 noise) and bounds what any bf16 implementation can be held to."""
     sd16 = {k: ((v.to(bf16) if "wg.weight" not in k else v.detach().clone())
                 if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in sd.items()}
-    ids, labels, am, clip_img, sam_img, gts = b
-    b16 = (ids, labels, am, clip_img.to(bf16), sam_img.to(bf16), gts)
     for n in train_names:
         sd[n].requires_grad_(True)
         sd16[n].requires_grad_(True)
     ref, aux_o = oracle_run(sd, ocfg, b, seg_flag, noise)
     ref["loss"].backward()
-    from oracle import train as otrain
-    ref16, aux16 = otrain.train_losses(sd16, ocfg, b16[3], b16[4], ids, labels, am, gts, [tuple(g.shape) for g in gts],
-                                       [(256, 256)] * len(gts), SEG, W, seg_flag=seg_flag, rts_uniforms=noise)
+    ref16, aux16 = oracle_run(sd16, ocfg, b, seg_flag, noise, dtype=bf16)
     ref16["loss"].backward()
     return ref, aux_o, sd16, aux16
 
@@ -165,10 +171,11 @@ def calibrate_relu_margins(m, sd, ocfg, b, noise, rounds=12):
     raise AssertionError("ReLU margins did not converge")
 
 
-def run_case(dev, seg_flag, cf, pad, aux):
+def run_case(dev, seg_flag, cf, pad, aux, region=False):
     m, sd, ocfg = build(dev, cf=cf, aux=aux)
-    b = batch(seg=seg_flag, pad=pad)
-    ids, labels, am, clip_img, sam_img, gts = b
+    b = batch(seg=seg_flag, pad=pad, region=region, seed=27 if region else 5)
+    ids, labels, am, clip_img, sam_img, gts = b[:6]
+    rm = [[x.to(dev) for x in r] for r in b[6]] if region else None
     S = ids.shape[0] * (ids.shape[1] - 1 + 16)
     g = torch.Generator().manual_seed(11)
     noise = [torch.rand(S, 2, generator=g) for _ in range(2)]
@@ -178,7 +185,8 @@ def run_case(dev, seg_flag, cf, pad, aux):
     ref, aux_o, sd16, aux16 = oracle_pair(m, sd, ocfg, b, seg_flag, noise, train_names)
     tr = m.trainer(lr=1e-2)
     tr.zero_grad()
-    out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=None,
+    out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=rm,
+            valid_region_masks_bool=[[True]] * len(gts) if region else None,
             labels=labels.to(dev), attention_mask=am.to(dev), offset=None, masks_list=[x.to(dev) for x in gts],
             label_list=[x.to(dev) for x in gts], resize_list=[(256, 256)] * len(gts), inference=False,
             seg_flag=seg_flag, moe_noise=[x.to(dev) for x in noise])
@@ -229,6 +237,16 @@ def test_grounding_loss_and_gradients(dev):
     """seg_flag=True: + BCE / Dice / IoU / Focal on the decoded masks; gradients reach the mask decoder,
     text_hidden_fcs and, through the [SEG] hidden rows, the decoder stack."""
     run_case(dev, True, 1.5, False, 0.01)
+
+
+def test_region_prompt_gradients(dev):
+    """rp_flag batches (medplib_arch.py:426-429,580-614): a -300 slot per sample filled with the point-sampled
+    region_fea_adapter feature; the adapter's weight / bias gradients come from the input-embedding gradient at the
+    slot (sample-mean and Linear commute)."""
+    m, tr, sd, names = run_case(dev, False, 1.5, False, 0.0, region=True)
+    g = tr.arena.grads()
+    assert float(g["model.region_fea_adapter.weight"].abs().max()) > 0
+    assert float(sd["model.region_fea_adapter.weight"].grad.abs().max()) > 0
 
 
 def test_optimizer_step_matches_adamw(dev):
