@@ -77,3 +77,33 @@ def grounding_forward(sd, cfg, images_clip, images, input_ids, resize_list, size
     pred = heads.text_hidden_fcs(sd, "model.text_hidden_fcs.0.", hidden[mask])
     masks, low = decode_masks(sd, cfg, pred, images, resize_list, size_list)
     return dict(pred_masks=masks, low_res=low, hidden=hidden, pred_embeddings=pred)
+
+
+def grounding_forward_icl(sd, cfg, images_clip_list, mask_images_list, image_token_types, image_token_lengths, images,
+                          input_ids, resize_list, size_list, seg_token_idx, attention_mask=None):
+    """model_forward(inference=True) in MedPLIB-ICL separate mode (medplib_arch.py:246-266): every sample brings a
+    stack of CLIP images (exemplars + query) and a stack of exemplar masks; each IMAGE sentinel of the prompt is
+    replaced, in order, by the compressed image tokens (mm_token_compress) or the MaskTokenEncoder tokens named by
+    image_token_types; the [SEG] mask skips image_token_lengths entries per sentinel (MedPLIB.py:310-355)."""
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids, dtype=torch.bool)
+    _, x = encode_images(sd, cfg, torch.cat(list(images_clip_list), dim=0))
+    mf = arch.mask_token_encoder(sd, "model.mask_encoder.", torch.cat(list(mask_images_list), dim=0),
+                                 cfg.get("mask_encoder_token_count", 64))
+    combined, ii, mi = [], 0, 0
+    for types_ in image_token_types:
+        for t in types_:
+            if t == "mask":
+                combined.append(mf[mi])
+                mi += 1
+            else:
+                combined.append(x[ii])
+                ii += 1
+    emb, _, am = arch.splice(sd["model.embed_tokens.weight"], input_ids, None, attention_mask, combined,
+                             use_im_start_end=cfg.get("mm_use_im_start_end", True), per_token_features=True)
+    out = llama.model_forward(sd, cfg["llama"], emb, am)
+    hidden = out["last_hidden_state"]
+    mask = heads.seg_token_mask(input_ids, seg_token_idx, x.shape[1], image_token_lengths)[:, :hidden.shape[1]]
+    pred = heads.text_hidden_fcs(sd, "model.text_hidden_fcs.0.", hidden[mask])
+    masks, low = decode_masks(sd, cfg, pred, images, resize_list, size_list)
+    return dict(pred_masks=masks, low_res=low, hidden=hidden, pred_embeddings=pred, inputs_embeds=emb)

@@ -137,3 +137,74 @@ def test_cpu_tensors_fail_loudly(dev):
     from medplib_b200 import ops, _lib
     with pytest.raises(_lib.MplError):
         ops.linear(torch.zeros(4, 8, dtype=bf16), torch.zeros(8, 8, dtype=bf16))
+
+
+def build_icl(dev):
+    """BASELINE configs[4] at toy size: ICL separate mode, token compressor (16 -> 8 tokens per image) and the
+    MaskTokenEncoder (4 tokens per exemplar mask)."""
+    from medplib_b200.model import MedPLIBForCausalLM, MedPLIBMoELlamaConfig
+    torch.manual_seed(0)
+    cfg = MedPLIBMoELlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                                num_key_value_heads=2, vocab_size=300, rms_norm_eps=1e-5, max_position_embeddings=512,
+                                mm_vision_select_layer=-2, mm_projector_type="mlp2x_gelu", max_sample_point=512,
+                                initializer_range=0.06)
+    cfg.clip_config = CLIP_CFG
+    cfg.sam_config = dict(image_size=256, embed_dim=128, depth=3, num_heads=2)
+    cfg.moe = dict(num_experts=[2], top_k_experts=1, capacity_factor=1.5, eval_capacity_factor=2.0, min_capacity=0,
+                   use_residual=False, router_aux_loss_coef=0.01, moe_layers_idx=None, moe_mode="dense", ep_size=1)
+    m = MedPLIBForCausalLM(cfg, test_only=True, seg_token_idx=SEG, mm_token_compress=True, mm_compressed_token_count=8,
+                           icl_mask_encoder=True, mask_encoder_token_count=4, use_mm_start_end=True)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "deepspeed_experts.1" in n or "rel_pos" in n or "pos_embed" in n or n.endswith(".bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.06)
+            if "wg.weight" in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5)
+            if "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+    m.config.mm_use_im_start_end = True
+    m = m.to(bf16).to(dev).eval()
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    sd.update({k: v.detach().cpu() for k, v in m.named_buffers()})
+    ocfg = dict(clip=dict(hidden_size=128, intermediate_size=256, num_layers=3, num_heads=2, image_size=56,
+                          patch_size=14),
+                llama=dict(hidden_size=256, intermediate_size=512, num_layers=2, num_heads=2, vocab_size=300,
+                           rms_norm_eps=1e-5, max_position_embeddings=512, rope_theta=1e4, moe=m.config.moe),
+                sam=dict(num_heads=2), mm_use_im_start_end=True, mm_token_compress=True, mm_compressed_token_count=8,
+                mask_encoder_token_count=4)
+    return m, sd, ocfg
+
+
+def test_icl_separate_mode_matches_oracle(dev):
+    """MedPLIB-ICL separate mode (BASELINE configs[4]): two (image, mask) exemplars + the query image, compressed image
+    tokens, mask-encoder tokens, [SEG] in the prompt, single-pass model_forward(inference=True)."""
+    from oracle import pipeline
+    m, sd, ocfg = build_icl(dev)
+    g = torch.Generator().manual_seed(4)
+    types_ = [["image", "mask", "image", "mask", "image"]]
+    lengths = [[8, 4, 8, 4, 8]]
+    ids = torch.randint(3, 290, (1, 26), generator=g)
+    for k, pos in enumerate((2, 6, 10, 14, 18)):  # IMAGE sentinel followed by its <im_end> slot
+        ids[0, pos] = -200
+    ids[0, 23] = SEG
+    clip_imgs = [torch.randn(3, 3, 56, 56, generator=g).to(bf16)]
+    mask_imgs = [(torch.rand(2, 1, 56, 56, generator=g) > 0.8).to(bf16)]
+    sam_img = torch.randn(1, 3, 256, 256, generator=g).to(bf16)
+    label = torch.zeros(70, 90)
+    ref = pipeline.grounding_forward_icl(sd, ocfg, clip_imgs, mask_imgs, types_, lengths, sam_img, ids, [(256, 256)],
+                                         [(70, 90)], SEG)
+    T_ref = ref["hidden"].shape[1]
+    assert T_ref == 26 - 5 + 3 * 8 + 2 * 4
+    out = m(images=sam_img.to(dev), images_clip=[c.to(dev) for c in clip_imgs], input_ids=ids.to(dev), region_masks=None,
+            labels=None, attention_mask=torch.ones_like(ids, dtype=torch.bool).to(dev), offset=None,
+            masks_list=[label], label_list=[label], resize_list=[(256, 256)], inference=True,
+            mask_images=[x.to(dev) for x in mask_imgs], image_token_types=types_, image_token_lengths=lengths,
+            icl_image_counts=[3])
+    assert out["pred_masks"][0].shape == (1, 70, 90)
+    _check(out["pred_masks"][0], ref["pred_masks"][0], 8e-2, "ICL mask logits")
+    # the spliced prompt itself (compressor + mask encoder + sentinel order) against the oracle's inputs_embeds
+    _, _, _, emb, _ = m.prepare_inputs_labels_for_multimodal(
+        ids.to(dev), torch.ones_like(ids, dtype=torch.bool).to(dev), None, None, [c.to(dev) for c in clip_imgs], None,
+        None, mask_images=[x.to(dev) for x in mask_imgs], image_token_types=types_)
+    _check(emb, ref["inputs_embeds"], 4e-2, "ICL inputs_embeds")
