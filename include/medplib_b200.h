@@ -523,6 +523,10 @@ int mpl_act_bwd(const void* x, const void* dy, void* dx, long long n, int act, v
 int mpl_attn_small_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                        const void* d_o, long long ldo, void* dq, long long lddq, void* dk, long long lddk, void* dv,
                        long long lddv, int batch, int Tq, int Tk, int H, int head_dim, float scale, void* stream);
+/* peft lora_dropout (train_ds_medplib.py:296-300): out = (accumulate ? out : 0) + x * mask * scale over n bf16 elements
+ * (mask: one byte per element, scale = 1 / (1 - p)); forward on the adapter's input, backward on its input gradient. */
+int mpl_mask_scale_bf16(const void* x, const unsigned char* mask, float scale, void* out, int accumulate, long long n,
+                        void* stream);
 /* Adjoint of mpl_bilinear_resize: dy [N, Hout, Wout] (bf16 or f32) -> dx bf16 [N, Hin, Win] (strides given). */
 int mpl_bilinear_resize_bwd(const void* dy, int dy_is_f32, int Hout, int Wout, void* dx, long long dx_stride_n,
                             long long dx_stride_y, int Hin, int Win, int N, void* stream);

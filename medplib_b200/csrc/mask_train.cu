@@ -346,9 +346,43 @@ __global__ void __launch_bounds__(256) mask_losses_bwd_kernel(const bf16_t* __re
   dpred[i] = __float2bfloat16_rn(g);
 }
 
+// ------------------------------------------------------------------------------------------------- dropout
+// out = (accumulate ? out : 0) + x * mask * scale  (peft's lora_dropout: forward on the adapter input, backward on the
+// adapter's input gradient); 8 elements per thread, n % 8 == 0.
+__global__ void __launch_bounds__(256) mask_scale_kernel(const bf16_t* __restrict__ x,
+                                                         const unsigned char* __restrict__ mask, float scale,
+                                                         bf16_t* __restrict__ out, int accumulate, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
+  if (i >= n) return;
+  const uint4 xv = *reinterpret_cast<const uint4*>(x + i);
+  const uint2 mv = *reinterpret_cast<const uint2*>(mask + i);
+  uint4 ov = accumulate ? *reinterpret_cast<const uint4*>(out + i) : make_uint4(0, 0, 0, 0);
+  const bf16_t* xe = reinterpret_cast<const bf16_t*>(&xv);
+  const unsigned char* me = reinterpret_cast<const unsigned char*>(&mv);
+  bf16_t* oe = reinterpret_cast<bf16_t*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float v = me[j] ? __bfloat162float(xe[j]) * scale : 0.f;
+    oe[j] = __float2bfloat16_rn(accumulate ? __bfloat162float(oe[j]) + bf16_round(v) : v);
+  }
+  *reinterpret_cast<uint4*>(out + i) = ov;
+}
+
 }  // namespace mpl
 
 using mpl::bf16_t;
+
+extern "C" int mpl_mask_scale_bf16(const void* x, const unsigned char* mask, float scale, void* out, int accumulate,
+                                   long long n, void* stream) {
+  if (n <= 0) return MPL_OK;
+  if (x == nullptr || mask == nullptr || out == nullptr) return MPL_ERR_ARG;
+  if ((n % 8) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(mask) & 7))
+    return MPL_ERR_ALIGN;
+  mpl::mask_scale_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, ST(stream)>>>(
+      static_cast<const bf16_t*>(x), mask, scale, static_cast<bf16_t*>(out), accumulate, n);
+  return mpl::launch_status();
+}
 
 extern "C" int mpl_gemm_small(const void* A, int a_is_f32, long long a_stride_m, long long a_stride_k, const void* B,
                               int b_is_f32, long long b_stride_k, long long b_stride_n, void* C, int c_is_f32,

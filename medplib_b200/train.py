@@ -45,8 +45,8 @@ def attach_lora(model, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=("q_
     module tree (train_ds_medplib.py:294-302), without peft: every matched nn.Linear gets ``lora_A.default`` /
     ``lora_B.default`` Linear children (peft's names; A kaiming-uniform, B zero), every other parameter is frozen.
     The matched Linear keeps its own ``weight`` (peft moves it to ``base_layer.weight`` — see INTEGRATION.md)."""
-    if lora_dropout:
-        raise _lib.MplError("lora_dropout > 0 is not built yet (pass --lora_dropout 0)")
+    if not 0.0 <= float(lora_dropout) < 1.0:
+        raise _lib.MplError("lora_dropout must be in [0, 1)")
     if isinstance(target_modules, str):
         target_modules = target_modules.split(",")
     names = find_linear_layers(model, list(target_modules))
@@ -64,6 +64,8 @@ def attach_lora(model, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=("q_
         lin.lora_B = nn.ModuleDict({"default": Bm})
         lin.scaling = {"default": lora_alpha / r}
         lin.r = {"default": r}
+        lin.lora_dropout_p = float(lora_dropout)
+        lin.lora_name = name
     if hasattr(model, "refresh_engines"):
         model.refresh_engines()
     return names
@@ -79,11 +81,13 @@ def set_trainable(model, sft_modules):
 
 
 class _Lora:
-    __slots__ = ("A", "B", "s", "gA", "gB")
+    __slots__ = ("A", "B", "s", "gA", "gB", "p", "name")
 
     def __init__(self, lin, arena):
         self.A, self.B = lin.lora_A["default"].weight, lin.lora_B["default"].weight
         self.s = float(lin.scaling["default"])
+        self.p = float(getattr(lin, "lora_dropout_p", 0.0))
+        self.name = getattr(lin, "lora_name", "")
         self.gA, self.gB = arena.of(self.A), arena.of(self.B)
         if self.A.shape[0] > 16:
             raise _lib.MplError("LoRA rank > 16 is not built (the reference trains with r = 8)")
@@ -242,6 +246,8 @@ class LlamaTrainStack:
         self.aux_coef = float(getattr(model, "router_aux_loss_coef", 0.0) or 0.0)
         self.use_rts = True  # DeepSpeed top1gating default (use_rts=True): random token selection on overflow
         self.debug = None  # dict: stage name -> tensor copies (tools/debug_train.py)
+        self.training = True          # lora_dropout is active (model.train()); Trainer keeps it in sync with the model
+        self.dropout_masks = None     # tests: {adapted module name: keep mask [rows, in_features]} instead of torch.rand
         from .engine import rope_tables
         from .model.config import llama_dims
         dims = llama_dims(cfg)
@@ -287,19 +293,35 @@ class LlamaTrainStack:
 
     # ------------------------------------------------------------------ helpers
     def _lora_fwd(self, lo, x, y):
-        """y += s * (x A^T) B^T in peft's bf16 rounding; returns a = x A^T (bf16 [M, r])."""
-        a = T.lora_down(x, lo.A)
+        """y += s * (dropout(x) A^T) B^T in peft's bf16 rounding; returns what the backward needs: (a = dropout(x) A^T
+        (bf16 [M, r]), dropped input or None, keep mask or None)."""
+        xd = mask = None
+        if lo.p > 0.0 and self.training:
+            # peft: lora_B(lora_A(lora_dropout(x))) — every adapted Linear owns its dropout, masks are per call
+            inj = self.dropout_masks.get(lo.name) if self.dropout_masks is not None else None
+            if inj is not None:
+                mask = inj[:x.shape[0]].to(torch.uint8).contiguous()
+            else:
+                mask = (torch.rand(x.shape, device=x.device) >= lo.p).to(torch.uint8)
+            xd = T.mask_scale(x if x.is_contiguous() else x.contiguous(), mask, 1.0 / (1.0 - lo.p))
+        a = T.lora_down(xd if xd is not None else x, lo.A)
         T.lora_up_add(y, a, lo.B, lo.s)
-        return a
+        return (a, xd, mask)
 
-    def _lora_bwd(self, lo, x, a, dy, dx):
-        """Gradients of y = ... + s (x A^T) B^T: dB, dA into the arena, dx += du A."""
+    def _lora_bwd(self, lo, x, saved, dy, dx):
+        """Gradients of y = ... + s (dropout(x) A^T) B^T: dB, dA into the arena, dx += dropout'(du A)."""
+        a, xd, mask = saved
         if lo.gB is not None:
             T.rank_wgrad(dy, a, lo.gB, scale=lo.s)
         du = T.lora_down(dy, T.transpose(lo.B.detach()), scale=lo.s, out_f32=True)
         if lo.gA is not None:
-            T.rank_wgrad(x, du, lo.gA, transposed=True)
-        T.lora_up_add(dx, du, lo.A, 1.0, transposed=True)
+            T.rank_wgrad(xd if xd is not None else x, du, lo.gA, transposed=True)
+        if mask is None:
+            T.lora_up_add(dx, du, lo.A, 1.0, transposed=True)
+        else:
+            tmp = torch.zeros((dx.shape[0], dx.shape[1]), dtype=bf16, device=dx.device)
+            T.lora_up_add(tmp, du, lo.A, 1.0, transposed=True)
+            T.mask_scale(tmp, mask, 1.0 / (1.0 - lo.p), out=dx, accumulate=True)
 
     def capacity(self, S, E):
         return ops.moe_capacity(S, E, self.cf, self.min_cap, 1)
@@ -620,6 +642,7 @@ class Trainer:
 
     # tape
     def stack_hidden(self, embeds, kv_mask=None, moe_noise=None, splice_idx=None, region_ctx=None):
+        self.stack.training = bool(self.model.training)
         B, Tn, D = embeds.shape
         x = embeds.to(bf16).reshape(B * Tn, D).contiguous()
         return _StackFn.apply(self.anchor, self, x, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx)

@@ -350,3 +350,16 @@ def mask_losses_bwd(pred, gt, pred_iou, sums6, dloss4):
     _lib.check(lib.mpl_mask_losses_bwd(_ptr(pred), _ptr(gt), _ptr(pred_iou), _ptr(sums6), _ptr(dloss4.contiguous()),
                                        _ll(pred.numel()), _ptr(dpred), _ptr(dpi), _stream()), "mpl_mask_losses_bwd")
     return dpred, dpi
+
+
+def mask_scale(x, mask, scale, out=None, accumulate=False):
+    """out = (accumulate ? out : 0) + x * mask * scale; x / out bf16 contiguous, mask uint8 / bool same shape."""
+    lib = _lib.load()
+    _req(x, bf16, "x")
+    assert x.is_contiguous() and mask.is_contiguous() and mask.numel() == x.numel()
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.is_contiguous()
+    _lib.check(lib.mpl_mask_scale_bf16(_ptr(x), _ptr(mask), _F(scale), _ptr(out), int(accumulate), _ll(x.numel()),
+                                       _stream()), "mpl_mask_scale_bf16")
+    return out

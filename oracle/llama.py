@@ -68,11 +68,18 @@ def decoder_attention_mask(attention_mask, T, past, dtype):
 def linear(sd, name, x):
     """nn.Linear (bias-free), or — when the state dict carries adapter weights for it — peft==0.10.0
     ``tuners/lora/layer.py::Linear.forward`` (un-vendored, pinned at /root/reference/requirements.txt:80; call site
-    train_ds_medplib.py:294-302): result = base(x) + lora_B(lora_A(dropout(x))) * scaling, dropout inactive here."""
+    train_ds_medplib.py:294-302): result = base(x) + lora_B(lora_A(dropout(x))) * scaling. Dropout is applied only
+    when the state dict injects a keep mask for this module (``<name>.lora_dropout_mask`` [rows, in_features], with
+    ``lora_dropout_p``): x * mask / (1 - p), nn.Dropout's training-mode arithmetic with the random draw made explicit."""
     y = F.linear(x, sd[name + ".weight"])
     a = sd.get(name + ".lora_A.default.weight")
     if a is not None:
-        y = y + F.linear(F.linear(x, a), sd[name + ".lora_B.default.weight"]) * sd["lora_scaling"]
+        xd = x
+        mask = sd.get(name + ".lora_dropout_mask")
+        if mask is not None:
+            rows = x.numel() // x.shape[-1]
+            xd = x * mask[:rows].reshape(x.shape).to(x.dtype) / (1.0 - sd["lora_dropout_p"])
+        y = y + F.linear(F.linear(xd, a), sd[name + ".lora_B.default.weight"]) * sd["lora_scaling"]
     return y
 
 

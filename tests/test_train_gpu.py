@@ -20,7 +20,7 @@ SFT = "wg,lm_head,embed_tokens,mask_decoder,text_hidden_fcs,region_fea_adapter"
 TOL = 1e-1
 
 
-def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,down_proj", sft=SFT):
+def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,down_proj", sft=SFT, dropout=0.0):
     import test_model_gpu as tm
     from medplib_b200 import train
     m, _, ocfg = tm.build(dev)
@@ -29,7 +29,7 @@ def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,d
     m.router_aux_loss_coef = aux
     m.ce_loss_weight, m.bce_loss_weight, m.dice_loss_weight = W["ce"], W["bce"], W["dice"]
     m.iou_loss_weight, m.focal_loss_weight = W["iou"], W["focal"]
-    names = train.attach_lora(m, r=8, lora_alpha=16, lora_dropout=0.0, target_modules=lora_targets)
+    names = train.attach_lora(m, r=8, lora_alpha=16, lora_dropout=dropout, target_modules=lora_targets)
     assert len(names) == 2 * 2 + 2 * 2 * 3
     train.set_trainable(m, sft)
     g = torch.Generator().manual_seed(7)
@@ -171,9 +171,20 @@ def calibrate_relu_margins(m, sd, ocfg, b, noise, rounds=12):
     raise AssertionError("ReLU margins did not converge")
 
 
-def run_case(dev, seg_flag, cf, pad, aux, region=False):
-    m, sd, ocfg = build(dev, cf=cf, aux=aux)
-    b = batch(seg=seg_flag, pad=pad, region=region, seed=27 if region else 5)
+def dropout_masks(m, S, C, p, seed=21):
+    """One keep mask per adapted Linear, [rows, in_features]: rows = tokens for q / v, expert capacity for the MLPs."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name, mod in m.named_modules():
+        if hasattr(mod, "lora_A"):
+            rows = C if "deepspeed_experts" in name else S
+            out[name] = torch.rand(rows, mod.in_features, generator=g) >= p
+    return out
+
+
+def run_case(dev, seg_flag, cf, pad, aux, region=False, dropout=0.0):
+    m, sd, ocfg = build(dev, cf=cf, aux=aux, dropout=dropout)
+    b = batch(seg=seg_flag, pad=pad, region=region, seed=27 if region else (205 if dropout > 0 else 5))
     ids, labels, am, clip_img, sam_img, gts = b[:6]
     rm = [[x.to(dev) for x in r] for r in b[6]] if region else None
     S = ids.shape[0] * (ids.shape[1] - 1 + 16)
@@ -182,9 +193,17 @@ def run_case(dev, seg_flag, cf, pad, aux, region=False):
     if seg_flag:
         calibrate_relu_margins(m, sd, ocfg, b, noise)
     train_names = [n for n, p in m.named_parameters() if p.requires_grad]
+    masks = None
+    if dropout > 0:
+        from oracle import moe as omoe
+        masks = dropout_masks(m, S, omoe.capacity(S, 2, cf, 0), dropout)
+        sd["lora_dropout_p"] = dropout
+        for k, v in masks.items():
+            sd[k + ".lora_dropout_mask"] = v
     ref, aux_o, sd16, aux16 = oracle_pair(m, sd, ocfg, b, seg_flag, noise, train_names)
     tr = m.trainer(lr=1e-2)
     tr.zero_grad()
+    tr.stack.dropout_masks = {k: v.to(dev) for k, v in masks.items()} if masks else None
     out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=rm,
             valid_region_masks_bool=[[True]] * len(gts) if region else None,
             labels=labels.to(dev), attention_mask=am.to(dev), offset=None, masks_list=[x.to(dev) for x in gts],
@@ -247,6 +266,14 @@ def test_region_prompt_gradients(dev):
     g = tr.arena.grads()
     assert float(g["model.region_fea_adapter.weight"].abs().max()) > 0
     assert float(sd["model.region_fea_adapter.weight"].grad.abs().max()) > 0
+
+
+def test_lora_dropout(dev):
+    """peft's lora_dropout (scripts/train_stage4.sh uses 0.05) with the keep masks injected on both sides: forward
+    losses and every gradient, including the masked adapter-input gradient."""
+    m, tr, sd, names = run_case(dev, False, 1.5, False, 0.0, dropout=0.25)
+    # and it is really on: without the masks the loss differs
+    assert tr.stack.training
 
 
 def test_optimizer_step_matches_adamw(dev):
