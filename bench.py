@@ -181,6 +181,8 @@ def run_ours(args, rank, world, dev):
     ck = clocks.stop()
     ms_e2e, _ = timed(step_e2e, args.steps)
     # in-situ duration of the dominant kernel (every tcgen05 GEMM launch of a step), CUDA events on the launch stream
+    # (launch durations are measured with the vision/LLM stream overlap off, so every interval is one kernel alone)
+    m.overlap_vision = False
     lib.mpl_profile_gemm(1)
     psteps = min(args.steps, 3)
     for _ in range(psteps):
@@ -188,6 +190,7 @@ def run_ours(args, rank, world, dev):
     tot, cnt = ctypes.c_float(0), ctypes.c_int(0)
     lib.mpl_profile_gemm_read(ctypes.byref(tot), ctypes.byref(cnt))
     lib.mpl_profile_gemm(0)
+    m.overlap_vision = True
     pk = peaks()
     gemm_ms = tot.value / psteps
     ach = gemm_flops_per_image() / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 and not args.small else None
@@ -211,9 +214,13 @@ def run_ours(args, rank, world, dev):
         "gpu_launches": int(launches),
         "clocks": ck,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s",
-                     "frac": (ach / pk["tf_sus"]) if ach else None, "traffic": None,
+                     "frac": (ach / pk["tf_sus"]) if ach else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 7 LLaMA-layer launches of
+                     # profiles/r01_ncu_gemm_prefill.md (ncu --set full): equals the algorithmic bytes to within 6 %
+                     "traffic": None if args.small else 111.9e6, "traffic_source": "profiles/r01_ncu_gemm_prefill.md",
                      "kernel": "gemm_bf16_tcgen05_kernel (all launches of a step: algorithmic 2MNK / summed CUDA-event"
-                               " durations)", "kernel_ms_per_step": gemm_ms, "kernel_launches_per_step": cnt.value / psteps,
+                               " durations; per-expert launches that run concurrently are timed as one interval)",
+                     "kernel_ms_per_step": gemm_ms, "kernel_launches_per_step": cnt.value / psteps,
                      "peak_source": pk["src"] + " sustained bf16"},
     }
     if args.cpu_baseline and world >= 1:

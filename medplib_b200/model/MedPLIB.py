@@ -979,6 +979,16 @@ class MedPLIBForCausalLM(PreTrainedModel):
         """MedPLIB.py:574-680: generate, take the hidden state in front of the first <SEG> (or position -2 when there is
         none), project it, run SAM-Med2D on `images` and decode one mask."""
         with torch.no_grad():
+            # The SAM-Med2D image encoder does not depend on the language model (the reference runs it after decoding,
+            # MedPLIB.py:648): it is enqueued on a side stream so its small launch-bound GEMMs fill the SMs that the
+            # M = 615 prefill tiles and the HBM-bound decode steps leave idle; joined before the mask decoder.
+            side = image_embeddings = None
+            if getattr(self, "overlap_vision", True) and images.is_cuda:
+                main = torch.cuda.current_stream()
+                side = self._side_stream = getattr(self, "_side_stream", None) or torch.cuda.Stream(device=images.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    image_embeddings = self.get_visual_embs(images)
             gen = self.generate(images=images_clip, input_ids=input_ids, region_masks=region_masks,
                                 valid_region_masks_bool=valid_region_masks_bool, mask_images=mask_images,
                                 image_token_types=image_token_types, max_new_tokens=max_new_tokens, do_sample=False,
@@ -988,6 +998,8 @@ class MedPLIBForCausalLM(PreTrainedModel):
             hidden = gen.last_hidden_state
             has_seg = bool((output_ids[:, 1:] == self.seg_token_idx).any())
             if not has_seg and inference_demo:
+                if side is not None:
+                    torch.cuda.current_stream().wait_stream(side)
                 return output_ids, []
             seg_mask = self.build_seg_token_mask(output_ids, image_token_lengths=image_token_lengths)
             seg_mask = seg_mask[:, :hidden.shape[1]]  # App. B-1: the last mask entry is always False
@@ -997,7 +1009,11 @@ class MedPLIBForCausalLM(PreTrainedModel):
             elif rows.shape[0] == 0:
                 rows = hidden[:1, -2:-1, :].squeeze(1)
             pred_embeddings = self._seg_embeddings(rows)
-            image_embeddings = self.get_visual_embs(images)
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+                image_embeddings.record_stream(torch.cuda.current_stream())
+            else:
+                image_embeddings = self.get_visual_embs(images)
             sizes = [tuple(o.shape) for o in original_size_list]
             pred_masks, _ = self._decode_masks(pred_embeddings, image_embeddings, resize_list, sizes)
         return output_ids, pred_masks
