@@ -579,6 +579,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: medplib_b200 has no CPU path (use --impl reference for the CPU arm)")
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL's version banner goes to stdout at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(dev)
         torch.distributed.init_process_group("nccl", device_id=dev)
     args.cpu_baseline = args.cpu_baseline and rank == 0 and world == 1
