@@ -147,6 +147,7 @@ class BucketReducer:
         self.world = dist.get_world_size(group) if self.on else 1
         n = arena.numel
         self.bounds = [(a, min(a + bucket_elems, n)) for a in range(0, n, bucket_elems)] or [(0, 0)]
+        self.owner = None  # Trainer (for the gradient-accumulation guard)
         self.reset()
 
     def reset(self):
@@ -157,6 +158,8 @@ class BucketReducer:
         if not self.on:
             return
         while self.next < len(self.bounds) and self.bounds[self.next][1] <= upto:
+            if self.next == 0 and self.owner is not None:
+                self.launch_micro_step = self.owner.micro_steps
             a, b = self.bounds[self.next]
             self.work.append(self.dist.all_reduce(self.arena.flat[a:b], op=self.dist.ReduceOp.SUM, group=self.group,
                                                   async_op=True))
@@ -545,6 +548,7 @@ class _StackFn(torch.autograd.Function):
             if gb is not None:
                 T.col_sum(dfeat, gb)
         ctx.saved = None
+        tr.micro_steps += 1  # the stack's backward is the last node of a micro-step
         return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 8
 
 
@@ -583,7 +587,11 @@ class _HeadCEFn(torch.autograd.Function):
             Sp = (S + 7) // 8 * 8
             dlT = T.transpose(dl, ld_out=Sp)[:V]  # [V, Sp]
             hT = T.transpose(h2, ld_out=Sp)  # [D, Sp]
-            ops.linear(dlT, hT, out_dtype=f32, out=gW, force="tc")
+            if tr.micro_steps == 0:
+                ops.linear(dlT, hT, out_dtype=f32, out=gW, force="tc")  # first micro-step: write straight into the arena
+            else:  # gradient accumulation: the GEMM overwrites, so go through a temporary and add
+                tmp = ops.linear(dlT, hT, out_dtype=f32, force="tc")
+                T.col_sum(tmp.view(1, -1), gW.view(-1))
             if tr.reducer is not None:
                 tr.reducer.ready(tr.arena.end_of(W))
         ctx.logits = ctx.h2 = None
@@ -608,6 +616,7 @@ class Trainer:
             raise _lib.MplError("no trainable parameters (call attach_lora / set_trainable first)")
         self.arena = GradArena(self._order(model, named), dev)
         self.reducer = BucketReducer(self.arena, bucket_elems, group)
+        self.reducer.owner = self
         self.stack = LlamaTrainStack(model, self.arena, self.reducer)
         self.opt = FusedAdamW(self.arena, lr, betas, eps, weight_decay, max_grad_norm)
         self.lm_head_weight = model.lm_head.weight
@@ -615,6 +624,7 @@ class Trainer:
         self.anchor = torch.zeros(1, dtype=f32, device=dev, requires_grad=True)
         self.loss_scale = 1.0
         self.last_gate_logits = None
+        self.micro_steps = 0  # backward passes accumulated in the arena since the last step()
         self._sig = self.signature(model)
 
     @staticmethod
@@ -650,12 +660,36 @@ class Trainer:
     def head_ce(self, hidden, labels):
         return _HeadCEFn.apply(hidden, self, labels)
 
+    def _accum_ok(self):
+        # buckets may only have been launched during the LAST backward (reducer.reset() happens in zero_grad)
+        return getattr(self.reducer, "launch_micro_step", self.micro_steps - 1) == self.micro_steps - 1
+
     def zero_grad(self):
         self.arena.zero_()
         self.reducer.reset()
+        self.micro_steps = 0
+
+    def no_sync(self):
+        """Gradient accumulation (DeepSpeed gradient_accumulation_steps / DDP.no_sync): backward passes inside this
+        context only add into the arena; the buckets are all-reduced during the first backward OUTSIDE it (or by
+        step()), so every bucket is exchanged exactly once per optimizer step. Scale the loss by 1/k yourself."""
+        tr = self
+
+        class _NoSync:
+            def __enter__(self_):
+                self_.prev = tr.reducer.on
+                tr.reducer.on = False
+
+            def __exit__(self_, *a):
+                tr.reducer.on = self_.prev
+
+        return _NoSync()
 
     def step(self, lr=None):
         """all-reduce what is left (mean over the data-parallel group), clip, AdamW, zero the arena."""
+        if self.micro_steps > 1 and self.reducer.on and self.reducer.next > 0 and not self._accum_ok():
+            raise _lib.MplError("backward() ran more than once since the last step() with the bucket all-reduce enabled: "
+                                "wrap all but the last micro-step in `with trainer.no_sync():`")
         scale = self.reducer.finish()
         self.opt.step(grad_scale=scale, lr=lr)
         self.zero_grad()

@@ -302,3 +302,34 @@ def test_optimizer_step_matches_adamw(dev):
         assert err <= tol, f"{n}: update differs by {err:.3e} (tol {tol:.3e})"
     assert float(tr.arena.flat.abs().max()) == 0.0  # arena zeroed for the next step
     print(f"\nworst update error / tolerance: {worst:.3f}")
+
+
+def test_gradient_accumulation(dev):
+    """Two backward passes on the same batch before step() leave exactly twice the single-pass gradient in the arena
+    (every kernel accumulates; the lm_head wgrad GEMM goes through a temporary on later micro-steps)."""
+    m, sd, ocfg = build(dev, cf=1.5, aux=0.0)
+    ids, labels, am, clip_img, sam_img, gts = batch()
+    S = ids.shape[0] * (ids.shape[1] - 1 + 16)
+    g = torch.Generator().manual_seed(11)
+    noise = [torch.rand(S, 2, generator=g).to(dev) for _ in range(2)]
+    tr = m.trainer(lr=1e-2)
+
+    def one():
+        out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=None,
+                labels=labels.to(dev), attention_mask=am.to(dev), offset=None, masks_list=[], label_list=[],
+                resize_list=[], inference=False, seg_flag=False, moe_noise=noise)
+        out["loss"].backward()
+
+    tr.zero_grad()
+    one()
+    single = tr.arena.flat.clone()
+    assert tr.micro_steps == 1
+    tr.zero_grad()
+    with tr.no_sync():
+        one()
+    one()
+    assert tr.micro_steps == 2
+    err = (tr.arena.flat - 2 * single).abs().max().item() / single.abs().max().item()
+    assert err < 2e-3, err  # fp32 atomics reorder sums run to run
+    tr.step()
+    assert tr.micro_steps == 0 and float(tr.arena.flat.abs().max()) == 0.0
