@@ -58,6 +58,24 @@ def splice_inputs(use_se, D=16, V=50, n_img=6):
                 valid=valid)
 
 
+def icl_splice_inputs(use_se, D=16, V=50, n_img_tok=4, n_mask_tok=2):
+    """MedPLIB-ICL separate mode (medplib_arch.py:246-266): per sample a stack of image features and a stack of
+    exemplar-mask features, consumed by the IMAGE sentinels in the order image_token_types names."""
+    g = torch.Generator().manual_seed(18 + int(use_se))
+    embed = torch.randn(V, D, generator=torch.Generator().manual_seed(9))
+    ids = torch.randint(3, V, (2, 16), generator=g)
+    types = [["image", "mask", "image"], ["image", "mask", "image", "mask", "image"]]
+    for b, pos in enumerate(((1, 5, 9), (0, 3, 6, 9, 12))):
+        for p in pos:
+            ids[b, p] = -200
+    labels = ids.clone()
+    labels[labels < 0] = -100
+    am = torch.ones(2, 16, dtype=torch.bool)
+    img = [torch.randn(2, n_img_tok, D, generator=g), torch.randn(3, n_img_tok, D, generator=g)]
+    msk = [torch.randn(1, n_mask_tok, D, generator=g), torch.randn(2, n_mask_tok, D, generator=g)]
+    return dict(embed=embed, ids=ids, labels=labels, am=am, img=img, msk=msk, types=types)
+
+
 def heads_inputs():
     g = torch.Generator().manual_seed(10)
     low = torch.randn(1, 1, 64, 64, generator=g)

@@ -144,6 +144,9 @@ def make_splice():
             # `images` here ARE the per-image features [n, n_img, D]; region map = 2 * features
             return images, images, (2 * images if region_flag else None)
 
+        def encode_masks(self, masks):
+            return masks  # likewise: the exemplar-mask "images" are already their token features
+
     cases = []
     for use_se in (True, False):
         d = gi.splice_inputs(use_se)
@@ -153,7 +156,15 @@ def make_splice():
                 d["ids"], d["am"], None, d["labels"], d["feats_r"], d["region_masks"], d["valid"])
             _, am2, _, emb2, lab2 = fake.prepare_inputs_labels_for_multimodal(
                 d["ids2"], d["am"], None, d["labels"], d["feats"], None, None)
-        cases.append(dict(use_se=use_se, emb1=emb1, lab1=lab1, am1=am1, emb2=emb2, lab2=lab2, am2=am2))
+        # ICL separate mode: stacks of images / masks per sample, ragged lengths
+        di = gi.icl_splice_inputs(use_se)
+        fake = Fake(use_se, di["embed"])
+        with torch.no_grad():
+            _, am3, _, emb3, lab3 = fake.prepare_inputs_labels_for_multimodal(
+                di["ids"], di["am"], None, di["labels"], di["img"], None, None, mask_images=di["msk"],
+                image_token_types=di["types"])
+        cases.append(dict(use_se=use_se, emb1=emb1, lab1=lab1, am1=am1, emb2=emb2, lab2=lab2, am2=am2,
+                          emb3=emb3, lab3=lab3, am3=am3))
     save("splice", cases=cases)
 
 

@@ -208,3 +208,57 @@ def test_icl_separate_mode_matches_oracle(dev):
         ids.to(dev), torch.ones_like(ids, dtype=torch.bool).to(dev), None, None, [c.to(dev) for c in clip_imgs], None,
         None, mask_images=[x.to(dev) for x in mask_imgs], image_token_types=types_)
     _check(emb, ref["inputs_embeds"], 4e-2, "ICL inputs_embeds")
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_splice_matches_reference_golden(dev, case):
+    """MedPLIBForCausalLM.prepare_inputs_labels_for_multimodal (host plan + one row-gather kernel) against the
+    REFERENCE's own function (tests/golden/splice.pt, generated by tests/golden/make_golden.py): standard + region
+    slot, plain, and ICL separate mode with ragged samples. Labels and attention masks bit-exact, embeddings to bf16."""
+    import os
+    import sys
+    from medplib_b200.model import MedPLIBForCausalLM, MedPLIBMoELlamaConfig
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    import inputs as gi
+    g = torch.load(os.path.join(gdir, "splice.pt"), weights_only=False)["cases"][case]
+    use_se = g["use_se"]
+    cfg = MedPLIBMoELlamaConfig(hidden_size=16, intermediate_size=32, num_hidden_layers=1, num_attention_heads=1,
+                                num_key_value_heads=1, vocab_size=50, rms_norm_eps=1e-5, max_position_embeddings=64,
+                                mm_vision_select_layer=-2, mm_projector_type="mlp2x_gelu", max_sample_point=512)
+    cfg.clip_config = CLIP_CFG
+    cfg.sam_config = dict(image_size=256, embed_dim=64, depth=1, num_heads=1)
+    cfg.moe = dict(num_experts=[2], top_k_experts=1, capacity_factor=1.5, eval_capacity_factor=2.0, min_capacity=0,
+                   use_residual=False, router_aux_loss_coef=0.01, moe_layers_idx=None, moe_mode="dense", ep_size=1)
+    m = MedPLIBForCausalLM(cfg, test_only=True, seg_token_idx=42, use_mm_start_end=use_se)
+    m.config.mm_use_im_start_end = use_se
+    m = m.to(bf16).to(dev).eval()
+
+    def fake_images(images, region_flag=False, region_geo_sampler=False):
+        x = images.to(bf16)
+        return x, x, ((2 * images).to(bf16) if region_flag else None)
+
+    m.encode_images = fake_images
+    m.encode_masks = lambda masks: masks.to(bf16)
+
+    def run(d, feats, region_masks=None, valid=None, **kw):
+        with torch.no_grad():
+            m.model.embed_tokens.weight.copy_(d["embed"].to(bf16))
+        rm = [[x.to(dev) for x in r] for r in region_masks] if region_masks is not None else None
+        f = [x.to(dev) for x in feats] if isinstance(feats, list) else feats.to(dev)
+        _, am, _, emb, lab = m.prepare_inputs_labels_for_multimodal(
+            d["ids"].to(dev), d["am"].to(dev), None, d["labels"].to(dev), f, rm, valid, **kw)
+        return emb, lab, am
+
+    d = gi.splice_inputs(use_se)
+    emb, lab, am = run(d, d["feats_r"], d["region_masks"], d["valid"])
+    assert torch.equal(lab.cpu(), g["lab1"]) and torch.equal(am.cpu(), g["am1"])
+    _check(emb, g["emb1"], 2e-2, "region splice")
+    d2 = dict(d, ids=d["ids2"])
+    emb, lab, am = run(d2, d["feats"])
+    assert torch.equal(lab.cpu(), g["lab2"]) and torch.equal(am.cpu(), g["am2"])
+    _check(emb, g["emb2"], 2e-2, "plain splice")
+    di = gi.icl_splice_inputs(use_se)
+    emb, lab, am = run(di, di["img"], mask_images=[x.to(dev) for x in di["msk"]], image_token_types=di["types"])
+    assert torch.equal(lab.cpu(), g["lab3"]) and torch.equal(am.cpu(), g["am3"])
+    _check(emb, g["emb3"], 2e-2, "ICL splice")
