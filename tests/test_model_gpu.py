@@ -17,7 +17,7 @@ CLIP_CFG = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num
                 patch_size=14, layer_norm_eps=1e-5)
 
 
-def build(dev, compress=False):
+def build(dev, compress=False, moe_layers=None):
     from medplib_b200.model import MedPLIBForCausalLM, MedPLIBMoELlamaConfig
     torch.manual_seed(0)
     cfg = MedPLIBMoELlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
@@ -27,7 +27,7 @@ def build(dev, compress=False):
     cfg.clip_config = CLIP_CFG
     cfg.sam_config = dict(image_size=256, embed_dim=128, depth=3, num_heads=2)
     cfg.moe = dict(num_experts=[2], top_k_experts=1, capacity_factor=1.5, eval_capacity_factor=2.0, min_capacity=0,
-                   use_residual=False, router_aux_loss_coef=0.01, moe_layers_idx=None, moe_mode="dense", ep_size=1)
+                   use_residual=False, router_aux_loss_coef=0.01, moe_layers_idx=moe_layers, moe_mode="dense", ep_size=1)
     m = MedPLIBForCausalLM(cfg, test_only=True, seg_token_idx=SEG, mm_token_compress=compress, use_mm_start_end=True)
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():  # make experts differ, norms / biases / rel-pos non-trivial, router decisive

@@ -20,17 +20,19 @@ SFT = "wg,lm_head,embed_tokens,mask_decoder,text_hidden_fcs,region_fea_adapter"
 TOL = 1e-1
 
 
-def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,down_proj", sft=SFT, dropout=0.0):
+def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,down_proj", sft=SFT, dropout=0.0,
+          moe_layers=None):
     import test_model_gpu as tm
     from medplib_b200 import train
-    m, _, ocfg = tm.build(dev)
+    m, _, ocfg = tm.build(dev, moe_layers=moe_layers)
     m.config.moe["capacity_factor"] = cf
     m.config.moe["router_aux_loss_coef"] = aux
     m.router_aux_loss_coef = aux
     m.ce_loss_weight, m.bce_loss_weight, m.dice_loss_weight = W["ce"], W["bce"], W["dice"]
     m.iou_loss_weight, m.focal_loss_weight = W["iou"], W["focal"]
     names = train.attach_lora(m, r=8, lora_alpha=16, lora_dropout=dropout, target_modules=lora_targets)
-    assert len(names) == 2 * 2 + 2 * 2 * 3
+    if moe_layers is None and lora_targets.count(",") == 4:
+        assert len(names) == 2 * 2 + 2 * 2 * 3
     train.set_trainable(m, sft)
     g = torch.Generator().manual_seed(7)
     with torch.no_grad():
@@ -182,14 +184,17 @@ def dropout_masks(m, S, C, p, seed=21):
     return out
 
 
-def run_case(dev, seg_flag, cf, pad, aux, region=False, dropout=0.0):
-    m, sd, ocfg = build(dev, cf=cf, aux=aux, dropout=dropout)
-    b = batch(seg=seg_flag, pad=pad, region=region, seed=27 if region else (205 if dropout > 0 else 5))
+def run_case(dev, seg_flag, cf, pad, aux, region=False, dropout=0.0, **build_kw):
+    m, sd, ocfg = build(dev, cf=cf, aux=aux, dropout=dropout, **build_kw)
+    seed = 27 if region else (205 if dropout > 0 else (8 if build_kw.get("moe_layers") is not None else 5))
+    b = batch(seg=seg_flag, pad=pad, region=region, seed=seed)
     ids, labels, am, clip_img, sam_img, gts = b[:6]
     rm = [[x.to(dev) for x in r] for r in b[6]] if region else None
     S = ids.shape[0] * (ids.shape[1] - 1 + 16)
     g = torch.Generator().manual_seed(11)
     noise = [torch.rand(S, 2, generator=g) for _ in range(2)]
+    if build_kw.get("moe_layers") is not None:  # oracle / kernels index the noise by decoder layer
+        noise = [noise[i] if i in build_kw["moe_layers"] else None for i in range(2)]
     if seg_flag:
         calibrate_relu_margins(m, sd, ocfg, b, noise)
     train_names = [n for n, p in m.named_parameters() if p.requires_grad]
@@ -208,9 +213,10 @@ def run_case(dev, seg_flag, cf, pad, aux, region=False, dropout=0.0):
             valid_region_masks_bool=[[True]] * len(gts) if region else None,
             labels=labels.to(dev), attention_mask=am.to(dev), offset=None, masks_list=[x.to(dev) for x in gts],
             label_list=[x.to(dev) for x in gts], resize_list=[(256, 256)] * len(gts), inference=False,
-            seg_flag=seg_flag, moe_noise=[x.to(dev) for x in noise])
+            seg_flag=seg_flag, moe_noise=[x.to(dev) if x is not None else None for x in noise])
     assert set(out) == set(ref)
     # routing must agree exactly, otherwise gradients are not comparable
+    assert len(tr.last_gate_logits) == len(aux_o["gate_logits"])
     for l, lg in enumerate(tr.last_gate_logits):
         assert torch.equal(lg.argmax(-1).cpu(), aux_o["gate_logits"][l].argmax(-1)), f"routing differs in layer {l}"
         assert torch.equal(lg.argmax(-1).cpu(), aux16["gate_logits"][l].argmax(-1)), f"routing differs in layer {l}"
@@ -266,6 +272,17 @@ def test_region_prompt_gradients(dev):
     g = tr.arena.grads()
     assert float(g["model.region_fea_adapter.weight"].abs().max()) > 0
     assert float(sd["model.region_fea_adapter.weight"].grad.abs().max()) > 0
+
+
+def test_stage2_recipe_dense_layer_all_lora_targets_and_norm_weights(dev):
+    """scripts/train_stage2.sh / train_stage3.sh shapes: a DENSE decoder layer next to a MoE layer ("sparse" moe_mode),
+    LoRA on all seven projections (q,k,v,o,gate,up,down) and the RMSNorm weights trainable (--sft_modules
+    input_layernorm,post_attention_layernorm): exercises the k_proj / o_proj adapter paths, the plain-MLP backward and
+    the norm-weight gradients."""
+    run_case(dev, True, 1.5, False, 0.01, moe_layers=[1],
+             lora_targets="q_proj,k_proj,v_proj,o_proj,gate_proj,up_proj,down_proj",
+             sft="lm_head,embed_tokens,input_layernorm,post_attention_layernorm,model.norm,wg,mask_decoder,"
+                 "text_hidden_fcs")
 
 
 def test_lora_dropout(dev):
