@@ -515,7 +515,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
         if image_token_types is not None and mask_images is not None and len(mask_images) > 0:
             assert type(images) is list or images.ndim == 5
             assert not region_flag
-            _, img_f, _ = self.encode_images(torch.cat([im for im in images], dim=0))
+            raw_f, img_f, _ = self.encode_images(torch.cat([im for im in images], dim=0))
             msk_f = self.encode_masks(torch.cat([m for m in mask_images], dim=0))
             ii = mi = 0
             for types_ in image_token_types:
@@ -527,7 +527,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
             per_token = True
         elif type(images) is list or images.ndim == 5:
             assert not region_flag
-            _, img_f, _ = self.encode_images(torch.cat([im for im in images], dim=0))
+            raw_f, img_f, _ = self.encode_images(torch.cat([im for im in images], dim=0))
             feat_blocks = [f for f in img_f]
             per_token = True
         else:
@@ -610,6 +610,23 @@ class MedPLIBForCausalLM(PreTrainedModel):
         feats_all = torch.cat(feat_blocks + ([torch.stack(extra_rows)] if extra_rows else []), dim=0).contiguous()
         embeds = ops.gather_rows(idx.reshape(-1), self.model.embed_tokens.weight, feats_all, D=D).view(len(plans), T, D)
         self._splice_idx = idx.reshape(-1)  # adjoint of the splice (embed_tokens gradient) in the train step
+        self._proj_ctx = None
+        proj = self.get_model().mm_projector
+        if labels is not None and torch.is_grad_enabled() and any(p.requires_grad for p in proj.parameters()):
+            if per_token and image_token_types is not None or getattr(self.config, "mm_token_compress", False) \
+                    or isinstance(proj, nn.Linear):
+                raise _lib.MplError("mm_projector gradients are built for the mlp2x_gelu projector without token "
+                                    "compression / ICL mask tokens (scripts/train_stage2.sh); freeze it otherwise")
+            # inverse of the splice for the image rows: feature row k sits at output row pos[k] (-1: unused)
+            n_img_rows = off
+            pos = [-1] * n_img_rows
+            for b, p in enumerate(plans):
+                for t, v in enumerate(p):
+                    if v <= -2 and -v - 2 < n_img_rows:
+                        pos[-v - 2] = b * T + t
+            raw_all = raw_f if not isinstance(raw_f, list) else torch.cat(raw_f, 0)
+            self._proj_ctx = dict(pos=torch.tensor(pos, dtype=torch.int32, device=dev),
+                                  feats=raw_all.reshape(-1, raw_all.shape[-1]))
         if raw_samples:
             # output rows that hold region features, in extra_rows order (plan entries <= -(off) - 2)
             pos = [b * T + t for b, p in enumerate(plans) for t, v in enumerate(p) if v <= -off - 2]
@@ -704,8 +721,9 @@ class MedPLIBForCausalLM(PreTrainedModel):
         if attention_mask is not None and not bool(attention_mask.all()):
             kv_mask = attention_mask
         hidden, l_aux = tr.stack_hidden(inputs_embeds, kv_mask=kv_mask, moe_noise=moe_noise,
-                                        splice_idx=self._splice_idx, region_ctx=getattr(self, "_region_ctx", None))
-        self._region_ctx = None
+                                        splice_idx=self._splice_idx, region_ctx=getattr(self, "_region_ctx", None),
+                                        proj_ctx=getattr(self, "_proj_ctx", None))
+        self._region_ctx = self._proj_ctx = None
         self._fire_gate_hooks(tr.last_gate_logits)
         loss, logits = tr.head_ce(hidden, labels)
         moe_losses = list(l_aux.unbind(0)) if l_aux.numel() > 0 else []

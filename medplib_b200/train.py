@@ -512,9 +512,9 @@ class _StackFn(torch.autograd.Function):
     """hidden = decoder_stack(embeds). `anchor` is a dummy leaf that makes the output require grad."""
 
     @staticmethod
-    def forward(ctx, anchor, tr, embeds, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx):
+    def forward(ctx, anchor, tr, embeds, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx, proj_ctx):
         hidden, l_aux, gate_logits, saved = tr.stack.forward(embeds, B, Tn, kv_mask, moe_noise)
-        ctx.tr, ctx.saved, ctx.splice_idx, ctx.region_ctx = tr, saved, splice_idx, region_ctx
+        ctx.tr, ctx.saved, ctx.splice_idx, ctx.region_ctx, ctx.proj_ctx = tr, saved, splice_idx, region_ctx, proj_ctx
         tr.last_gate_logits = gate_logits
         if l_aux is None:
             l_aux = torch.zeros(0, dtype=f32, device=embeds.device)
@@ -547,9 +547,46 @@ class _StackFn(torch.autograd.Function):
                 T.gemm_small(dfeat, ctx.region_ctx["sampled"], out=gW, trans_a=True, accumulate=True)
             if gb is not None:
                 T.col_sum(dfeat, gb)
+        if ctx.proj_ctx is not None:
+            _projector_backward(tr, ctx.proj_ctx, dx0)
         ctx.saved = None
         tr.micro_steps += 1  # the stack's backward is the last node of a micro-step
-        return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 8
+        return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 9
+
+
+def _wgrad_tc(dy, x, out, accumulate):
+    """out (f32 [N, K]) (+)= dy^T x on the tensor cores: both operands transposed to K-major over the rows."""
+    M = dy.shape[0]
+    Mp = (M + 63) // 64 * 64  # whole K blocks of the tcgen05 tile; pad columns are zero
+    dyT = T.transpose(dy, ld_out=Mp)[:dy.shape[1]]
+    xT = T.transpose(x, ld_out=Mp)[:x.shape[1]]
+    if not accumulate:
+        ops.linear(dyT, xT, out_dtype=f32, out=out, force="tc")
+    else:
+        tmp = ops.linear(dyT, xT, out_dtype=f32, force="tc")
+        T.col_sum(tmp.view(1, -1), out.view(-1))
+
+
+def _projector_backward(tr, pc, dx0):
+    """mm_projector = Linear(1024, D) + GELU + Linear(D, D) (multimodal_projector/builder.py:39-46) on the frozen CLIP
+    features: weight / bias gradients from the input-embedding gradient at the image rows (no gradient into CLIP)."""
+    proj = tr.model.model.mm_projector
+    ar = tr.arena
+    acc = tr.micro_steps > 0
+    x = pc["feats"].contiguous()
+    dF = ops.gather_rows(pc["pos"], table=dx0)  # [n_img_rows, D]; rows the prompt never used are zero
+    z0 = ops.linear(x, proj[0].weight.detach(), bias=proj[0].bias.detach())
+    h1 = T.act_fwd(z0, "gelu")
+    if ar.of(proj[2].weight) is not None:
+        _wgrad_tc(dF, h1, ar.of(proj[2].weight), acc)
+    if ar.of(proj[2].bias) is not None:
+        T.col_sum(dF, ar.of(proj[2].bias))
+    dh1 = ops.linear(dF, T.transpose(proj[2].weight.detach()))
+    dz0 = T.act_bwd(z0, dh1, "gelu")
+    if ar.of(proj[0].weight) is not None:
+        _wgrad_tc(dz0, x, ar.of(proj[0].weight), acc)
+    if ar.of(proj[0].bias) is not None:
+        T.col_sum(dz0, ar.of(proj[0].bias))
 
 
 class _HeadCEFn(torch.autograd.Function):
@@ -651,11 +688,11 @@ class Trainer:
         return sorted(named, key=key)
 
     # tape
-    def stack_hidden(self, embeds, kv_mask=None, moe_noise=None, splice_idx=None, region_ctx=None):
+    def stack_hidden(self, embeds, kv_mask=None, moe_noise=None, splice_idx=None, region_ctx=None, proj_ctx=None):
         self.stack.training = bool(self.model.training)
         B, Tn, D = embeds.shape
         x = embeds.to(bf16).reshape(B * Tn, D).contiguous()
-        return _StackFn.apply(self.anchor, self, x, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx)
+        return _StackFn.apply(self.anchor, self, x, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx, proj_ctx)
 
     def head_ce(self, hidden, labels):
         return _HeadCEFn.apply(hidden, self, labels)

@@ -18,7 +18,12 @@ def train_losses(sd, cfg, images_clip, images, input_ids, labels, attention_mask
     """Returns (10-key loss dict, aux dict with routing / hidden states for diagnostics). ``w`` = dict(ce, bce, dice,
     iou, focal) loss weights (MedPLIB.py:233-240)."""
     with torch.no_grad():
-        feats, x = pipeline.encode_images(sd, cfg, images_clip)
+        feats, _ = pipeline.encode_images(sd, cfg, images_clip)
+    # the projector is differentiable (scripts/train_stage2.sh trains it); the CLIP tower is frozen
+    x = arch.mm_projector(sd, "model.mm_projector.", feats)
+    if cfg.get("mm_token_compress"):
+        x = arch.token_compressor(sd, "model.mm_token_compressor.", x, cfg.get("mm_compressed_token_count", 256))
+    with torch.no_grad():
         if seg_flag:
             image_emb = sam.image_encoder(sd, pipeline.SAM + "image_encoder.", images,
                                           num_heads=cfg["sam"]["num_heads"])

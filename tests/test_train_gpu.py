@@ -277,12 +277,12 @@ def test_region_prompt_gradients(dev):
 def test_stage2_recipe_dense_layer_all_lora_targets_and_norm_weights(dev):
     """scripts/train_stage2.sh / train_stage3.sh shapes: a DENSE decoder layer next to a MoE layer ("sparse" moe_mode),
     LoRA on all seven projections (q,k,v,o,gate,up,down) and the RMSNorm weights trainable (--sft_modules
-    input_layernorm,post_attention_layernorm): exercises the k_proj / o_proj adapter paths, the plain-MLP backward and
-    the norm-weight gradients."""
+    input_layernorm,post_attention_layernorm,mm_projector): exercises the k_proj / o_proj adapter paths, the plain-MLP
+    backward, the norm-weight gradients and the projector's gradients (through the image rows of the splice)."""
     run_case(dev, True, 1.5, False, 0.01, moe_layers=[1],
              lora_targets="q_proj,k_proj,v_proj,o_proj,gate_proj,up_proj,down_proj",
              sft="lm_head,embed_tokens,input_layernorm,post_attention_layernorm,model.norm,wg,mask_decoder,"
-                 "text_hidden_fcs")
+                 "text_hidden_fcs,mm_projector")
 
 
 def test_lora_dropout(dev):
