@@ -542,7 +542,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
             vsel = torch.tensor(valid, device=rmap.device)
             rmap = rmap[vsel]
             adapter = self.get_model().region_fea_adapter
-            want_grad = labels is not None and torch.is_grad_enabled() and adapter.weight.requires_grad
+            want_grad = labels is not None and torch.is_grad_enabled() and self.training and adapter.weight.requires_grad
             raw_samples = [] if want_grad else None
             region_features = self.extract_region_feature(rmap, region_masks,
                                                           raw_feature_map=raw_f[vsel] if want_grad else None,
@@ -612,11 +612,14 @@ class MedPLIBForCausalLM(PreTrainedModel):
         self._splice_idx = idx.reshape(-1)  # adjoint of the splice (embed_tokens gradient) in the train step
         self._proj_ctx = None
         proj = self.get_model().mm_projector
-        if labels is not None and torch.is_grad_enabled() and any(p.requires_grad for p in proj.parameters()):
+        if labels is not None and torch.is_grad_enabled() and self.training \
+                and any(p.requires_grad for p in proj.parameters()):
             if per_token and image_token_types is not None or getattr(self.config, "mm_token_compress", False) \
                     or isinstance(proj, nn.Linear):
-                raise _lib.MplError("mm_projector gradients are built for the mlp2x_gelu projector without token "
-                                    "compression / ICL mask tokens (scripts/train_stage2.sh); freeze it otherwise")
+                self._proj_ctx = dict(unsupported="mm_projector gradients are built for the mlp2x_gelu projector without "
+                                      "token compression / ICL mask tokens (scripts/train_stage2.sh); freeze it otherwise")
+        if labels is not None and torch.is_grad_enabled() and self.training and self._proj_ctx is None \
+                and any(p.requires_grad for p in proj.parameters()):
             # inverse of the splice for the image rows: feature row k sits at output row pos[k] (-1: unused)
             n_img_rows = off
             pos = [-1] * n_img_rows
@@ -717,6 +720,9 @@ class MedPLIBForCausalLM(PreTrainedModel):
         """Training branch of medplib_moe_llama.py:324-438: activations kept, loss = shifted CE + coef * sum(l_aux),
         differentiable through medplib_b200.train's tape nodes (loss.backward() fills the gradient arena)."""
         tr = self.trainer()
+        pc = getattr(self, "_proj_ctx", None)
+        if pc is not None and "unsupported" in pc:
+            raise _lib.MplError(pc["unsupported"])
         kv_mask = None
         if attention_mask is not None and not bool(attention_mask.all()):
             kv_mask = attention_mask
