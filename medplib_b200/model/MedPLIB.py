@@ -291,13 +291,21 @@ class MedPLIBForCausalLM(PreTrainedModel):
 
     # ------------------------------------------------------------------ HF plumbing
     def _init_weights(self, module):
+        """Random init of the tensors a checkpoint did not provide. from_pretrained() calls this AFTER loading: tensors
+        that came from the checkpoint carry `_is_hf_initialized` and must be left alone."""
         std = getattr(self.config, "initializer_range", 0.02)
+
+        def fresh(t):
+            return t is not None and not getattr(t, "_is_hf_initialized", False)
+
         if isinstance(module, (nn.Linear, nn.Conv2d, nn.ConvTranspose2d)):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.bias is not None:
+            if fresh(module.weight):
+                module.weight.data.normal_(mean=0.0, std=std)
+            if fresh(module.bias):
                 module.bias.data.zero_()
         elif isinstance(module, nn.Embedding):
-            module.weight.data.normal_(mean=0.0, std=std)
+            if fresh(module.weight):
+                module.weight.data.normal_(mean=0.0, std=std)
 
     def get_model(self):
         return self.model
