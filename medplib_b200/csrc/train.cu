@@ -799,9 +799,9 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_kernel(const AttnBwdParam
   extern __shared__ __align__(128) uint8_t ab_smem[];
   bf16_t* sK = reinterpret_cast<bf16_t*>(ab_smem);
   bf16_t* sV = sK + AB_BN * LDT;
-  bf16_t* sQ = sV + AB_BN * LDT;
-  bf16_t* sdO = sQ + AB_BM * LDT;
-  float* sS = reinterpret_cast<float*>(sdO + AB_BM * LDT);
+  bf16_t* sQ0 = sV + AB_BN * LDT;             // Q / dO tiles are double-buffered: the next query block streams in
+  bf16_t* sdO0 = sQ0 + 2 * AB_BM * LDT;       // (cp.async) while the current one is being multiplied
+  float* sS = reinterpret_cast<float*>(sdO0 + 2 * AB_BM * LDT);
   float* sdP = sS + AB_BM * LDS;
   bf16_t* sP = reinterpret_cast<bf16_t*>(sdP + AB_BM * LDS);
   bf16_t* sdS = sP + AB_BM * LDP;
@@ -833,6 +833,17 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_kernel(const AttnBwdParam
       *reinterpret_cast<uint4*>(dst + r * LDT + c * 8) = val;
     }
   };
+  auto load_tile_async = [&](bf16_t* dst, const bf16_t* src, long long stride_t, int t0) {
+    constexpr int CPR = D / 8;
+    for (int idx = threadIdx.x; idx < 64 * CPR; idx += AB_THREADS) {
+      const int r = idx / CPR, c = idx % CPR;
+      const int t = t0 + r;
+      const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst + r * LDT + c * 8));
+      const int sz = t < T ? 16 : 0;  // src-size 0: the 16 bytes are zero-filled
+      const bf16_t* g = src + static_cast<long long>(t < T ? t : 0) * stride_t + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(sz) : "memory");
+    }
+  };
   load_tile(sK, kg, p.k_st, k0);
   load_tile(sV, vg, p.v_st, k0);
 
@@ -847,10 +858,20 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_kernel(const AttnBwdParam
   }
 
   const int q_begin = p.causal ? (k0 / AB_BM) * AB_BM : 0;
-  for (int q0 = q_begin; q0 < T; q0 += AB_BM) {
-    __syncthreads();  // previous iteration done with sQ / sdO / staging
-    load_tile(sQ, qg, p.q_st, q0);
-    load_tile(sdO, og, p.o_st, q0);
+  load_tile_async(sQ0, qg, p.q_st, q_begin);
+  load_tile_async(sdO0, og, p.o_st, q_begin);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int buf = 0;
+  for (int q0 = q_begin; q0 < T; q0 += AB_BM, buf ^= 1) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();  // this block's tiles have landed for every thread; previous iteration done with the other buffer
+    bf16_t* sQ = sQ0 + buf * AB_BM * LDT;
+    bf16_t* sdO = sdO0 + buf * AB_BM * LDT;
+    if (q0 + AB_BM < T) {  // prefetch the next query block into the buffer the previous iteration used
+      load_tile_async(sQ0 + (buf ^ 1) * AB_BM * LDT, qg, p.q_st, q0 + AB_BM);
+      load_tile_async(sdO0 + (buf ^ 1) * AB_BM * LDT, og, p.o_st, q0 + AB_BM);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     if (threadIdx.x < AB_BM) {
       const int t = q0 + threadIdx.x;
       sLse[threadIdx.x] = t < T ? p.lse[bh * T + t] : INFINITY;
@@ -935,10 +956,15 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_kernel(const AttnBwdParam
     for (int i = 0; i < NF; ++i)
       wmma::store_matrix_sync(sdQ + acc_r * LDQ + acc_c + i * 16, dQf[i], LDQ, wmma::mem_row_major);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < AB_BM * D; idx += AB_THREADS) {
-      const int r = idx / D, c = idx % D;
+    // 16-byte vector reductions (red.global.add.v4.f32, sm_90+): a quarter of the atomic instructions
+    for (int idx = threadIdx.x; idx < AB_BM * (D / 4); idx += AB_THREADS) {
+      const int r = idx / (D / 4), c = (idx % (D / 4)) * 4;
       const int qi = q0 + r;
-      if (qi < T) atomicAdd(p.dq + ((static_cast<long long>(b) * T + qi) * p.H + h) * D + c, sdQ[r * LDQ + c]);
+      if (qi < T) {
+        float4* dst = reinterpret_cast<float4*>(p.dq + ((static_cast<long long>(b) * T + qi) * p.H + h) * D + c);
+        const float* sp = sdQ + r * LDQ + c;
+        atomicAdd(dst, make_float4(sp[0], sp[1], sp[2], sp[3]));
+      }
     }
   }
   // ---- write dK_j, dV_j (stage through shared memory as fp32)
@@ -1431,7 +1457,7 @@ extern "C" int mpl_attention_bwd(const mpl_attn_bwd_args* a, void* stream) {
   p.kv_mask_stride = a->kv_mask_stride > 0 ? a->kv_mask_stride : a->T;
   dim3 grid((a->T + AB_BN - 1) / AB_BN, a->H, a->B);
   auto smem_bytes = [](int D) {
-    return 4 * 64 * (D + 8) * 2 + 2 * 64 * (AB_BN + 4) * 4 + 2 * 64 * (AB_BN + 8) * 2 + 2 * 64 * 4;
+    return 6 * 64 * (D + 8) * 2 + 2 * 64 * (AB_BN + 4) * 4 + 2 * 64 * (AB_BN + 8) * 2 + 2 * 64 * 4;
   };
   if (a->head_dim == 128) {
     static bool set = false;
