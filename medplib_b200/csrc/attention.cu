@@ -422,7 +422,257 @@ static int launch_flash(const AttnParams& p, cudaStream_t stream) {
   return mpl::launch_status();
 }
 
+// ------------------------------------------------------------------------------------------ training backward (d = 128)
+// FlashAttention-2 style backward of causal self-attention on mma.sync m16n8k16 with register-resident accumulators
+// (replaces torch autograd through HF-4.31 LlamaAttention's eager softmax(QK^T)V in the train step, a-17).
+// One CTA (4 warps) owns 64 keys; warp w owns keys [16w, 16w+16) and keeps dK_w, dV_w (16 x 128 fp32 each) in registers
+// while it walks the query blocks that can see these keys. Everything is computed TRANSPOSED (keys are the M rows):
+//   S^T = K_w Q^T, dP^T = V_w dO^T  ->  P^T = 2^(S^T c - lse_q), dS^T = P^T (dP^T - delta_q) scale   (C fragments)
+//   dV_w += P^T dO, dK_w += dS^T Q   (the C fragments are re-packed as A fragments: no shared-memory round trip)
+//   dQ += dS K needs dS with queries as rows: dS^T goes through an 8 KB shared tile once, warp w then produces the
+//   16 x 128 slice of its 16 queries over this CTA's 64 keys and reduces it into the fp32 dQ with 8-byte vector REDs.
+// Q / dO tiles are double-buffered with cp.async; tiles use the forward kernel's XOR swizzle and ldmatrix patterns.
+struct AttnBwd2Params {
+  const __nv_bfloat16 *q, *k, *v, *dO;
+  long long q_sb, q_st, q_sh, k_sb, k_st, k_sh, v_sb, v_st, v_sh, o_sb, o_st, o_sh;
+  const float *lse, *delta;  // [B*H, T]
+  float* dq;                 // f32 [B, T, H, 128] contiguous, zero-initialised
+  __nv_bfloat16 *dk, *dv;
+  long long dk_sb, dk_st, dk_sh, dv_sb, dv_st, dv_sh;
+  int B, H, T;
+  float scale;
+  int causal;
+  const unsigned char* kv_mask;
+  long long kv_mask_stride;
+};
+
+constexpr int AB2_SMEM = 6 * 64 * 128 * 2 + 64 * 64 * 2 + 4 * 64 * 4;  // K, V, 2x(Q, dO), dS^T, 2x(lse, delta)
+
+__global__ void __launch_bounds__(FA_THREADS, 2) attn_bwd_fa2_kernel(const AttnBwd2Params p) {
+  constexpr int D = 128;
+  extern __shared__ __align__(128) uint8_t ab2_smem[];
+  const uint32_t sK = smem_u32(ab2_smem);
+  const uint32_t sV = sK + 64 * D * 2;
+  const uint32_t sQ0 = sV + 64 * D * 2;
+  const uint32_t sdO0 = sQ0 + 2 * 64 * D * 2;
+  const uint32_t sdS = sdO0 + 2 * 64 * D * 2;
+  uint8_t* sdS_ptr = ab2_smem + 6 * 64 * D * 2;
+  float* sLse = reinterpret_cast<float*>(ab2_smem + 6 * 64 * D * 2 + 64 * 64 * 2);  // [2][64]
+  float* sDelta = sLse + 128;                                                        // [2][64]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int k0 = blockIdx.x * 64;
+  const int T = p.T;
+  const __nv_bfloat16* qg = p.q + b * p.q_sb + h * p.q_sh;
+  const __nv_bfloat16* kg = p.k + b * p.k_sb + h * p.k_sh;
+  const __nv_bfloat16* vg = p.v + b * p.v_sb + h * p.v_sh;
+  const __nv_bfloat16* og = p.dO + b * p.o_sb + h * p.o_sh;
+  const long long bh = static_cast<long long>(b) * p.H + h;
+  const unsigned char* mrow = p.kv_mask ? p.kv_mask + static_cast<long long>(b) * p.kv_mask_stride : nullptr;
+  const float sl2 = p.scale * 1.4426950408889634f;
+
+  const int q_begin = p.causal ? k0 : 0;
+  load_tile<D>(sK, kg, p.k_st, k0, T, 64);
+  load_tile<D>(sV, vg, p.v_st, k0, T, 64);
+  load_tile<D>(sQ0, qg, p.q_st, q_begin, T, 64);
+  load_tile<D>(sdO0, og, p.o_st, q_begin, T, 64);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  float dv[D / 8][4], dk[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dv[i][j] = dk[i][j] = 0.0f;
+  // this lane's two key rows and their validity (bounds + key-padding mask)
+  const int key0 = k0 + warp * 16 + g, key1 = key0 + 8;
+  const bool kok0 = key0 < T && (mrow == nullptr || mrow[key0] != 0);
+  const bool kok1 = key1 < T && (mrow == nullptr || mrow[key1] != 0);
+
+  int buf = 0;
+  for (int q0 = q_begin; q0 < T; q0 += 64, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();  // tiles of this iteration landed; every warp is done with the previous iteration
+    const uint32_t sQ = sQ0 + buf * 64 * D * 2, sdO = sdO0 + buf * 64 * D * 2;
+    if (q0 + 64 < T) {
+      load_tile<D>(sQ0 + (buf ^ 1) * 64 * D * 2, qg, p.q_st, q0 + 64, T, 64);
+      load_tile<D>(sdO0 + (buf ^ 1) * 64 * D * 2, og, p.o_st, q0 + 64, T, 64);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (threadIdx.x < 64) {
+      const int t = q0 + threadIdx.x;
+      sLse[buf * 64 + threadIdx.x] = t < T ? p.lse[bh * T + t] : INFINITY;
+      sDelta[buf * 64 + threadIdx.x] = t < T ? p.delta[bh * T + t] : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- S^T = K_w Q^T and dP^T = V_w dO^T : [16 keys x 64 queries] each
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st[i][j] = dpt[i][j] = 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      uint32_t ka[4], va[4];
+      {
+        const int r = warp * 16 + (lane & 15);
+        const int c = kk * 2 + (lane >> 4);
+        ldmatrix_x4(ka, sK + swz<D>(r, c));
+        ldmatrix_x4(va, sV + swz<D>(r, c));
+      }
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t qb[4], ob[4];
+        const int r = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+        const int c = kk * 2 + ((lane >> 3) & 1);
+        ldmatrix_x4(qb, sQ + swz<D>(r, c));
+        ldmatrix_x4(ob, sdO + swz<D>(r, c));
+        mma_16816(st[np * 2], ka, qb[0], qb[1]);
+        mma_16816(st[np * 2 + 1], ka, qb[2], qb[3]);
+        mma_16816(dpt[np * 2], va, ob[0], ob[1]);
+        mma_16816(dpt[np * 2 + 1], va, ob[2], ob[3]);
+      }
+    }
+    // ---- P^T, dS^T (C fragments: rows = keys g / g+8, columns = queries nt*8 + 2*t4 + {0,1}) -> A fragments
+    uint32_t pa[4][4], dsa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float pv[4], dsv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ql = nt * 8 + t4 * 2 + (j & 1);
+        const int qi = q0 + ql;
+        const int key = (j >> 1) ? key1 : key0;
+        bool ok = ((j >> 1) ? kok1 : kok0) && qi < T;
+        if (p.causal) ok = ok && key <= qi;
+        float pr = 0.0f, ds = 0.0f;
+        if (ok) {
+          pr = exp2f(st[nt][j] * sl2 - sLse[buf * 64 + ql]);
+          ds = pr * (dpt[nt][j] - sDelta[buf * 64 + ql]) * p.scale;
+        }
+        pv[j] = pr;
+        dsv[j] = ds;
+      }
+      pa[nt >> 1][(nt & 1) * 2] = pack_bf16(pv[0], pv[1]);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(pv[2], pv[3]);
+      const uint32_t d01 = pack_bf16(dsv[0], dsv[1]), d23 = pack_bf16(dsv[2], dsv[3]);
+      dsa[nt >> 1][(nt & 1) * 2] = d01;
+      dsa[nt >> 1][(nt & 1) * 2 + 1] = d23;
+      // dS^T tile for the dQ pass: row = key (within the CTA's 64), 16-byte chunk nt, element pair t4
+      const int r0 = warp * 16 + g, r1 = r0 + 8;
+      *reinterpret_cast<uint32_t*>(sdS_ptr + swz<64>(r0, nt) + t4 * 4) = d01;
+      *reinterpret_cast<uint32_t*>(sdS_ptr + swz<64>(r1, nt) + t4 * 4) = d23;
+    }
+    // ---- dV_w += P^T dO ; dK_w += dS^T Q   (contraction over the 64 queries)
+#pragma unroll
+    for (int kq = 0; kq < 4; ++kq) {
+#pragma unroll
+      for (int dp = 0; dp < D / 16; ++dp) {
+        uint32_t ob[4], qb[4];
+        const int r = kq * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+        const int c = dp * 2 + (lane >> 4);
+        ldmatrix_x4_trans(ob, sdO + swz<D>(r, c));
+        ldmatrix_x4_trans(qb, sQ + swz<D>(r, c));
+        mma_16816(dv[dp * 2], pa[kq], ob[0], ob[1]);
+        mma_16816(dv[dp * 2 + 1], pa[kq], ob[2], ob[3]);
+        mma_16816(dk[dp * 2], dsa[kq], qb[0], qb[1]);
+        mma_16816(dk[dp * 2 + 1], dsa[kq], qb[2], qb[3]);
+      }
+    }
+    __syncthreads();  // dS^T of all four warps is in shared memory
+    // ---- dQ[16 queries of this warp, 128] = dS[16 x 64 keys] K[64 keys x 128], reduced into the fp32 dQ
+    {
+      float dq[D / 8][4];
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dq[i][j] = 0.0f;
+#pragma unroll
+      for (int kkk = 0; kkk < 4; ++kkk) {
+        uint32_t da[4];
+        {
+          // A = dS (rows = queries) read from the [key][query] tile: transposed 8x8 blocks
+          const int r = kkk * 16 + (lane & 7) + ((lane >> 4) << 3);
+          const int c = warp * 2 + ((lane >> 3) & 1);
+          ldmatrix_x4_trans(da, sdS + swz<64>(r, c));
+        }
+#pragma unroll
+        for (int dp = 0; dp < D / 16; ++dp) {
+          uint32_t kb[4];
+          const int r = kkk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+          const int c = dp * 2 + (lane >> 4);
+          ldmatrix_x4_trans(kb, sK + swz<D>(r, c));
+          mma_16816(dq[dp * 2], da, kb[0], kb[1]);
+          mma_16816(dq[dp * 2 + 1], da, kb[2], kb[3]);
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int qi = q0 + warp * 16 + g + rr * 8;
+        if (qi < T) {
+          float* drow = p.dq + ((static_cast<long long>(b) * T + qi) * p.H + h) * D + t4 * 2;
+#pragma unroll
+          for (int i = 0; i < D / 8; ++i)
+            atomicAdd(reinterpret_cast<float2*>(drow + i * 8), make_float2(dq[i][rr * 2], dq[i][rr * 2 + 1]));
+        }
+      }
+    }
+  }
+  // ---- write dK_w, dV_w
+  __nv_bfloat16* dkg = p.dk + b * p.dk_sb + h * p.dk_sh;
+  __nv_bfloat16* dvg = p.dv + b * p.dv_sb + h * p.dv_sh;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int key = rr ? key1 : key0;
+    if (key < T) {
+      __nv_bfloat16* kr = dkg + static_cast<long long>(key) * p.dk_st + t4 * 2;
+      __nv_bfloat16* vr = dvg + static_cast<long long>(key) * p.dv_st + t4 * 2;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        *reinterpret_cast<uint32_t*>(kr + i * 8) = pack_bf16(dk[i][rr * 2], dk[i][rr * 2 + 1]);
+        *reinterpret_cast<uint32_t*>(vr + i * 8) = pack_bf16(dv[i][rr * 2], dv[i][rr * 2 + 1]);
+      }
+    }
+  }
+}
+
+// Host entry used by mpl_attention_bwd (train.cu) for head_dim 128.
+int attn_bwd_fa2(const mpl_attn_bwd_args& a, cudaStream_t stream) {
+  AttnBwd2Params p;
+  p.q = static_cast<const __nv_bfloat16*>(a.q);
+  p.k = static_cast<const __nv_bfloat16*>(a.k);
+  p.v = static_cast<const __nv_bfloat16*>(a.v);
+  p.dO = static_cast<const __nv_bfloat16*>(a.d_o);
+  p.q_sb = a.q_stride[0]; p.q_st = a.q_stride[1]; p.q_sh = a.q_stride[2];
+  p.k_sb = a.k_stride[0]; p.k_st = a.k_stride[1]; p.k_sh = a.k_stride[2];
+  p.v_sb = a.v_stride[0]; p.v_st = a.v_stride[1]; p.v_sh = a.v_stride[2];
+  p.o_sb = a.o_stride[0]; p.o_st = a.o_stride[1]; p.o_sh = a.o_stride[2];
+  p.lse = a.lse;
+  p.delta = a.delta;
+  p.dq = a.dq_f32;
+  p.dk = static_cast<__nv_bfloat16*>(a.dk);
+  p.dv = static_cast<__nv_bfloat16*>(a.dv);
+  p.dk_sb = a.dk_stride[0]; p.dk_st = a.dk_stride[1]; p.dk_sh = a.dk_stride[2];
+  p.dv_sb = a.dv_stride[0]; p.dv_st = a.dv_stride[1]; p.dv_sh = a.dv_stride[2];
+  p.B = a.B; p.H = a.H; p.T = a.T;
+  p.scale = a.scale;
+  p.causal = a.causal;
+  p.kv_mask = a.kv_mask;
+  p.kv_mask_stride = a.kv_mask_stride > 0 ? a.kv_mask_stride : a.T;
+  static bool set = false;
+  if (!set) {
+    if (cudaFuncSetAttribute(attn_bwd_fa2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB2_SMEM) != cudaSuccess)
+      return MPL_ERR_CUDA;
+    set = true;
+  }
+  dim3 grid((a.T + 63) / 64, a.H, a.B);
+  attn_bwd_fa2_kernel<<<grid, FA_THREADS, AB2_SMEM, stream>>>(p);
+  return launch_status();
+}
+
 }  // namespace mpl
+
 
 extern "C" int mpl_attention(const mpl_attn_args* a, void* stream_) {
   using namespace mpl;

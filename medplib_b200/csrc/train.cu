@@ -7,6 +7,8 @@
 // All HBM-bound except attention backward (mma.sync via wmma fragments; tcgen05 version is future work).
 #include <mma.h>
 
+#include <cstdlib>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -1434,6 +1436,8 @@ extern "C" int mpl_attention_bwd(const mpl_attn_bwd_args* a, void* stream) {
       static_cast<const bf16_t*>(a->o), static_cast<const bf16_t*>(a->d_o), a->o_stride[0], a->o_stride[1],
       a->o_stride[2], a->delta, a->B, a->H, a->T, a->head_dim);
   if (launch_status() != MPL_OK) return MPL_ERR_CUDA;
+  if (a->head_dim == 128 && a->dk_stride[1] % 2 == 0 && a->dv_stride[1] % 2 == 0 && getenv("MPL_ATTN_BWD_WMMA") == nullptr)
+    return attn_bwd_fa2(*a, ST(stream));  // mma.sync FA2-style kernel (attention.cu); the wmma kernel below: d = 64
   AttnBwdParams p;
   p.q = static_cast<const bf16_t*>(a->q);
   p.k = static_cast<const bf16_t*>(a->k);
