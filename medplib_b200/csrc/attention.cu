@@ -90,8 +90,8 @@ template <int D>
 __global__ void __launch_bounds__(FA_THREADS) flash_fwd_kernel(const AttnParams p) {
   extern __shared__ __align__(128) uint8_t fa_smem[];
   const uint32_t sQ = smem_u32(fa_smem);
-  const uint32_t sK = sQ + FA_BM * D * 2;
-  const uint32_t sV = sK + FA_BN * D * 2;
+  const uint32_t sK0 = sQ + FA_BM * D * 2;       // K / V tiles are double-buffered: the next key block streams in
+  const uint32_t sV0 = sK0 + 2 * FA_BN * D * 2;  // (cp.async) while the current one is being multiplied
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -103,6 +103,9 @@ __global__ void __launch_bounds__(FA_THREADS) flash_fwd_kernel(const AttnParams 
   const __nv_bfloat16* vg = p.v + b * p.v_sb + h * p.v_sh;
 
   load_tile<D>(sQ, qg, p.q_st, q0, p.Tq, FA_BM);
+  load_tile<D>(sK0, kg, p.k_st, 0, Tk, FA_BN);  // first key block (k_end >= 1 whenever there is a query)
+  load_tile<D>(sV0, vg, p.v_st, 0, Tk, FA_BN);
+  asm volatile("cp.async.commit_group;" ::: "memory");
   cp_async_wait_all();
   __syncthreads();
   // Q fragments for this warp's 16 rows, all of D
@@ -138,12 +141,16 @@ __global__ void __launch_bounds__(FA_THREADS) flash_fwd_kernel(const AttnParams 
     }
   }
 
-  for (int k0 = 0; k0 < k_end; k0 += FA_BN) {
-    __syncthreads();  // previous iteration's reads of sK/sV done
-    load_tile<D>(sK, kg, p.k_st, k0, Tk, FA_BN);
-    load_tile<D>(sV, vg, p.v_st, k0, Tk, FA_BN);
+  int kbuf = 0;
+  for (int k0 = 0; k0 < k_end; k0 += FA_BN, kbuf ^= 1) {
     cp_async_wait_all();
-    __syncthreads();
+    __syncthreads();  // this block's K / V landed for every thread; the previous iteration's reads of the other buffer done
+    const uint32_t sK = sK0 + kbuf * FA_BN * D * 2, sV = sV0 + kbuf * FA_BN * D * 2;
+    if (k0 + FA_BN < k_end) {
+      load_tile<D>(sK0 + (kbuf ^ 1) * FA_BN * D * 2, kg, p.k_st, k0 + FA_BN, Tk, FA_BN);
+      load_tile<D>(sV0 + (kbuf ^ 1) * FA_BN * D * 2, vg, p.v_st, k0 + FA_BN, Tk, FA_BN);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
     float s[FA_BN / 8][4];
 #pragma unroll
@@ -410,7 +417,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(const AttnP
 
 template <int D>
 static int launch_flash(const AttnParams& p, cudaStream_t stream) {
-  constexpr int smem = (FA_BM + 2 * FA_BN) * D * 2;
+  constexpr int smem = (FA_BM + 4 * FA_BN) * D * 2;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(flash_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
