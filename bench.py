@@ -569,6 +569,12 @@ def main():
                     help="profiling aid: warm up, then run ONE step between cudaProfilerStart/Stop (use with "
                          "ncu --profile-from-start off); prints no bench line")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: Python-level prints keep the real stdout, anything a library writes to
+    # file descriptor 1 from C (NCCL's version banner at communicator creation) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
