@@ -409,11 +409,21 @@ class MedPLIBForCausalLM(PreTrainedModel):
     def _llama(self):
         if "llama" not in self._eng:
             self._check_ready()
-            if any(hasattr(mod, "lora_A") for mod in self.model.layers.modules()):
-                raise _lib.MplError("LoRA adapters are attached: the inference engines read the base weights only; "
-                                    "call medplib_b200.train.merge_lora(model) first (the reference merges before "
-                                    "evaluation too)")
-            self._eng["llama"] = engine.LlamaEngine(self._params(), llama_dims(self.config), "model.")
+            params = self._params()
+            adapted = [(n, mod) for n, mod in self.named_modules() if isinstance(mod, nn.Linear) and hasattr(mod, "lora_A")]
+            if adapted:
+                # validation in the middle of training (train_ds_medplib.py validate() runs the peft-wrapped model):
+                # the inference kernels read plain weights, so the engine is built on MERGED copies W + s B A of the
+                # adapted matrices (offline plumbing, rebuilt after every optimizer step); the parameters stay untouched
+                self._merged = {}
+                with torch.no_grad():
+                    for n, mod in adapted:
+                        A, Bm = mod.lora_A["default"].weight, mod.lora_B["default"].weight
+                        w = (mod.weight.float() + float(mod.scaling["default"]) * (Bm.float() @ A.float())).to(mod.weight.dtype)
+                        self._merged[n + ".weight"] = w
+                params = dict(params)
+                params.update(self._merged)
+            self._eng["llama"] = engine.LlamaEngine(params, llama_dims(self.config), "model.")
         return self._eng["llama"]
 
     def _sam_encoder(self):
@@ -721,8 +731,12 @@ class MedPLIBForCausalLM(PreTrainedModel):
         return tr
 
     def refresh_trained(self):
-        """After an optimizer step: engines that hold REPACKED copies of trainable weights (mask decoder) are rebuilt."""
+        """After an optimizer step: engines that hold REPACKED / MERGED copies of trainable weights (mask decoder,
+        LoRA-merged decoder matrices) are rebuilt on their next use."""
         self._eng.pop("sam_dec", None)
+        if getattr(self, "_merged", None):
+            self._eng.pop("llama", None)
+            self._merged = None
 
     def _lm_forward_train(self, inputs_embeds, attention_mask, labels, moe_noise=None):
         """Training branch of medplib_moe_llama.py:324-438: activations kept, loss = shifted CE + coef * sum(l_aux),

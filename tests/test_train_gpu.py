@@ -350,3 +350,35 @@ def test_gradient_accumulation(dev):
     assert err < 2e-3, err  # fp32 atomics reorder sums run to run
     tr.step()
     assert tr.micro_steps == 0 and float(tr.arena.flat.abs().max()) == 0.0
+
+
+def test_inference_with_unmerged_adapters_equals_merged_model(dev):
+    """train_ds_medplib.py's validate() calls the peft-wrapped model between optimizer steps: evaluate() / generate()
+    with adapters attached must equal the merged model (merge_lora), and must follow the weights after a step."""
+    from medplib_b200 import train
+    import test_model_gpu as tm
+    m, sd, ocfg = build(dev, cf=1.5, aux=0.0)
+    m.eval()
+    ids, clip_img, sam_img = tm.inputs()
+    label = torch.zeros(70, 90)
+    forced = {3: SEG}
+    out_ids, masks = m.evaluate(clip_img.to(dev), sam_img.to(dev), ids.to(dev), [(256, 256)], [label],
+                                max_new_tokens=6, forced_tokens=forced)
+    m2, _, _ = build(dev, cf=1.5, aux=0.0)  # deterministic: the same weights and adapters
+    m2.eval()
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    m2 = train.merge_lora(m2)
+    ref_ids, ref_masks = m2.evaluate(clip_img.to(dev), sam_img.to(dev), ids.to(dev), [(256, 256)], [label],
+                                     max_new_tokens=6, forced_tokens=forced)
+    assert torch.equal(out_ids, ref_ids)
+    err = (masks[0].float() - ref_masks[0].float()).abs().max().item()
+    assert err <= 2e-2 * ref_masks[0].float().abs().max().item(), err
+    # the adapters did matter (the unadapted base model gives different hidden states)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "lora_B" in n:
+                p.zero_()
+    m.refresh_trained()
+    _, base_masks = m.evaluate(clip_img.to(dev), sam_img.to(dev), ids.to(dev), [(256, 256)], [label],
+                               max_new_tokens=6, forced_tokens=forced)
+    assert (base_masks[0].float() - masks[0].float()).abs().max().item() > 0
