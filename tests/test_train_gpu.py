@@ -382,3 +382,89 @@ def test_inference_with_unmerged_adapters_equals_merged_model(dev):
     _, base_masks = m.evaluate(clip_img.to(dev), sam_img.to(dev), ids.to(dev), [(256, 256)], [label],
                                max_new_tokens=6, forced_tokens=forced)
     assert (base_masks[0].float() - masks[0].float()).abs().max().item() > 0
+
+
+def test_lisa_dense_twin_inference_and_train_step(dev):
+    """model/LISA.py::LISAForCausalLM (dense LlamaMLP everywhere, `attention_masks` spelling): single-pass grounding
+    forward against the oracle pipeline, then one training forward/backward (LoRA q,v + sft modules) against
+    torch.autograd over the oracle."""
+    import test_model_gpu as tm
+    from medplib_b200 import train
+    from medplib_b200.model import LISAForCausalLM
+    from medplib_b200.model.config import LlavaConfig
+    from oracle import pipeline
+    torch.manual_seed(0)
+    cfg = LlavaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,
+                      num_key_value_heads=2, vocab_size=300, rms_norm_eps=1e-5, max_position_embeddings=512,
+                      mm_vision_select_layer=-2, mm_projector_type="mlp2x_gelu", initializer_range=0.06)
+    cfg.clip_config = tm.CLIP_CFG
+    cfg.sam_config = dict(image_size=256, embed_dim=128, depth=3, num_heads=2)
+    m = LISAForCausalLM(cfg, seg_token_idx=SEG, use_mm_start_end=True, train_mask_decoder=True, out_dim=256,
+                        ce_loss_weight=W["ce"], dice_loss_weight=W["dice"], bce_loss_weight=W["bce"],
+                        iou_loss_weight=W["iou"], focal_loss_weight=W["focal"], vision_tower=None,
+                        region_fea_adapter=True, region_geo_sampler=False, max_sample_point=512,
+                        sampler_pooler_mode="max")
+    assert not any("deepspeed_moe" in n for n, _ in m.named_parameters())
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "rel_pos" in n or "pos_embed" in n or n.endswith(".bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.06)
+            if "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+    m.config.mm_use_im_start_end = True
+    m = m.to(bf16).to(dev).eval()
+    ocfg = dict(clip=dict(hidden_size=128, intermediate_size=256, num_layers=3, num_heads=2, image_size=56,
+                          patch_size=14),
+                llama=dict(hidden_size=256, intermediate_size=512, num_layers=2, num_heads=2, vocab_size=300,
+                           rms_norm_eps=1e-5, max_position_embeddings=512, rope_theta=1e4, moe=None),
+                sam=dict(num_heads=2), mm_use_im_start_end=True, mm_token_compress=False)
+    # ---- inference (model_forward(inference=True), LISA's `attention_masks` keyword)
+    sd_b = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    sd_b.update({k: v.detach().cpu() for k, v in m.named_buffers()})
+    ids, clip_img, sam_img = tm.inputs(seg_in_prompt=True)
+    label = torch.zeros(70, 90)
+    ref = pipeline.grounding_forward(sd_b, ocfg, clip_img, sam_img, ids, [(256, 256)], [(70, 90)], SEG)
+    out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=None,
+            labels=None, attention_masks=torch.ones_like(ids, dtype=torch.bool).to(dev), offset=None,
+            masks_list=[label], label_list=[label], resize_list=[(256, 256)], inference=True)
+    tm._check(out["pred_masks"][0], ref["pred_masks"][0], 8e-2, "LISA mask logits")
+    # ---- one train step
+    train.attach_lora(m, r=8, lora_alpha=16, target_modules="q_proj,v_proj")
+    train.set_trainable(m, "lm_head,embed_tokens,mask_decoder,text_hidden_fcs")
+    gg = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "lora_B" in n:
+                p.copy_((torch.randn(p.shape, generator=gg) * 0.05).to(p.dtype))
+    m.train()
+    sd = {k: v.detach().cpu().float() for k, v in m.state_dict().items()}
+    sd.update({k: v.detach().cpu().float() for k, v in m.named_buffers()})
+    sd["lora_scaling"] = 2.0
+    b = batch(seg=True)
+    calibrate_relu_margins(m, sd, ocfg, b, None, rounds=40)
+    names = [n for n, p in m.named_parameters() if p.requires_grad]
+    ref_l, aux_o, sd16, aux16 = oracle_pair(m, sd, ocfg, b, True, None, names)
+    ids, labels, am, clip_img, sam_img, gts = b
+    tr = m.trainer(lr=1e-2)
+    tr.zero_grad()
+    out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=None,
+            labels=labels.to(dev), attention_masks=am.to(dev), offset=None, masks_list=[x.to(dev) for x in gts],
+            label_list=[x.to(dev) for x in gts], resize_list=[(256, 256)] * len(gts), inference=False, seg_flag=True)
+    out["loss"].backward()
+    torch.cuda.synchronize()
+    for k in ref_l:
+        r, o = float(ref_l[k].detach()), float(out[k].detach())
+        assert abs(o - r) <= 2e-2 * max(abs(r), 1e-3) + 1e-4, f"{k}: {o} vs oracle {r}"
+    grads = tr.arena.grads()
+    bad = []
+    for n in names:
+        r32, r16 = sd[n].grad, sd16[n].grad
+        if r32 is None or r32.abs().max() < 1e-6:
+            continue
+        e32, _ = _relerr(grads[n], r32)
+        e16, _ = _relerr(grads[n], r16)
+        cond, _ = _relerr(r16, r32)
+        if not (e16 <= TOL or e32 <= TOL or e32 <= 1.5 * cond):
+            bad.append((n, e32, e16))
+    assert not bad, bad[:6]
