@@ -32,7 +32,7 @@ enum {
 };
 
 enum { MPL_ACT_NONE = 0, MPL_ACT_GELU = 1, MPL_ACT_QUICK_GELU = 2, MPL_ACT_RELU = 3, MPL_ACT_SILU = 4, MPL_ACT_SIGMOID = 5 };
-enum { MPL_DT_BF16 = 0, MPL_DT_F32 = 1 };
+enum { MPL_DT_BF16 = 0, MPL_DT_F32 = 1, MPL_DT_U8 = 2 /* mpl_preprocess_images only */ };
 #define MPL_MAX_EXPERTS 8
 
 /* Library / device probe. Returns the ABI version; fills sm count and compute capability when non-null. */
@@ -534,6 +534,43 @@ int mpl_bilinear_resize_bwd(const void* dy, int dy_is_f32, int Hout, int Wout, v
  * -> dpred bf16 [n], dpred_iou f32[1] (optional). */
 int mpl_mask_losses_bwd(const void* pred, const float* gt, const void* pred_iou, const float* sums6, const float* dloss4,
                         long long n, void* dpred, float* dpred_iou, void* stream);
+
+/* =========================================================================================================
+ * Image input pipeline: decoded u8 image -> model-ready tensor, one launch for a ragged batch.
+ * Replaces, per image, datasets/LazySupervisedDataset.py:539-553 (and :516-517 for region masks):
+ *   ResizeLongestSide.apply_image (model/segment_anything_med2d/utils/transforms.py:26-32) = PIL Image.resize(BILINEAR):
+ *     antialiased two-pass convolution on 8-bit channels, 22-bit fixed-point coefficients, u8 rounding between the
+ *     horizontal and the vertical pass (Pillow libImaging/Resample.c) — reproduced bit for bit;
+ *   preprocess + pad_tensor_channelwise (:446-502) and CLIPImageProcessor rescale/normalize: every output value is a
+ *     function of the resized u8 level, so the host passes a 256-entry fp32 table per channel (lut) and the pad value.
+ * Each job turns src u8 [H,W,C] (interleaved, C = 1 or 3) into dst [C, out_size, out_size]: the new_h x new_w resized
+ * image placed at (pad_top, pad_left), pad_value[c] elsewhere.  coef / bound are PIL's tables for one axis
+ * (coef int32 [n_out, ks], bound int32 [n_out, 2] = first tap, tap count), built by the host
+ * (medplib_b200/preprocess.py:pil_coeffs).  jobs_host and jobs_dev hold the same n_jobs structs (the pointers inside
+ * are device pointers); the host copy sizes the grid and the shared memory.  MPL_ERR_UNSUPPORTED when one output row's
+ * taps do not fit 200 KB of shared memory (downscales beyond ~100x). */
+typedef struct {
+  const void* src;
+  long long src_stride; /* bytes between source rows */
+  int H, W, C;
+  int new_h, new_w;
+  int out_size;
+  int pad_top, pad_left;
+  const int* coef_x;
+  const int* bound_x;
+  const int* coef_y;
+  const int* bound_y;
+  int ks_x, ks_y;
+  const float* lut; /* f32 [C,256], or NULL: the u8 level itself */
+  float pad_value[3];
+  int out_dtype; /* MPL_DT_BF16 / MPL_DT_F32 / MPL_DT_U8 */
+  void* dst;
+} mpl_preprocess_job;
+int mpl_preprocess_images(const mpl_preprocess_job* jobs_host, const mpl_preprocess_job* jobs_dev, int n_jobs,
+                          void* stream);
+/* Rows of the source a band of R output rows can touch (upper bound used to size shared memory; integer-only so the
+ * host and the kernel agree). Exposed for the host-side tests. */
+int mpl_preprocess_band_rows(int in_size, int out_size, int R);
 
 #ifdef __cplusplus
 }

@@ -88,3 +88,26 @@ def heads_inputs():
 
 
 POSTPROCESS_CASES = dict(square=((256, 256), (336, 336)), wide=((256, 192), (300, 225)), tiny=((48, 256), (60, 320)))
+
+
+# ---- image input pipeline: (H, W, SAM target, CLIP target); targets other than 256 / 336 keep the
+# fixture small — the reference's ResizeLongestSide / preprocess are size-parametric
+PREPROCESS_SIZES = [(512, 512, 256, 336), (300, 451, 256, 336), (1024, 768, 256, 336), (97, 130, 256, 336),
+                    (256, 256, 256, 336), (336, 200, 256, 336), (1300, 1777, 256, 336),
+                    (50, 40, 64, 84), (211, 97, 64, 84), (64, 84, 64, 84), (500, 333, 32, 42), (31, 200, 48, 70)]
+
+
+def preprocess_image(i, h, w):
+    """u8 RGB [h, w, 3] numpy: low-frequency structure + noise, so that both antialiasing and rounding matter."""
+    g = torch.Generator().manual_seed(100 + i)
+    base = torch.nn.functional.interpolate(torch.rand(1, 3, 8, 8, generator=g), size=(h, w), mode="bilinear")[0]
+    img = (base * 200 + torch.rand(3, h, w, generator=g) * 80 - 12).clamp(0, 255)
+    return img.permute(1, 2, 0).contiguous().to(torch.uint8).numpy()
+
+
+def preprocess_mask(i, h, w):
+    """u8 {0,1} [h, w] numpy region mask: a filled ellipse."""
+    g = torch.Generator().manual_seed(200 + i)
+    cy, cx, ry, rx = (torch.rand(4, generator=g) * torch.tensor([h, w, h / 2, w / 2]) + torch.tensor([0, 0, 2, 2])).tolist()
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    return ((((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) <= 1).to(torch.uint8).numpy()

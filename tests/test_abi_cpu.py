@@ -37,7 +37,8 @@ def test_struct_sizes_match_header():
              "mpl_llama_layer": _lib.LlamaLayer, "mpl_llama_model": _lib.LlamaModel, "mpl_llama_io": _lib.LlamaIO,
              "mpl_clip_layer": _lib.ClipLayer, "mpl_clip_model": _lib.ClipModel, "mpl_sam_block": _lib.SamBlock,
              "mpl_sam_encoder": _lib.SamEncoder, "mpl_sam_attn": _lib.SamAttn,
-             "mpl_sam_twoway_layer": _lib.SamTwoWayLayer, "mpl_sam_mask_decoder": _lib.SamMaskDecoder}
+             "mpl_sam_twoway_layer": _lib.SamTwoWayLayer, "mpl_sam_mask_decoder": _lib.SamMaskDecoder,
+             "mpl_preprocess_job": __import__("medplib_b200.preprocess", fromlist=["PreprocessJob"]).PreprocessJob}
     prog = '#include <stdio.h>\n#include "medplib_b200.h"\nint main(void){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs) + "return 0;}"
     with tempfile.TemporaryDirectory() as d:

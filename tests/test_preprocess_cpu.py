@@ -1,0 +1,122 @@
+"""CPU: the input-pipeline oracle (oracle/preprocess.py) against the reference's own pipeline — the committed
+digests in tests/golden/preprocess.pt (made by tests/golden/make_golden_preprocess.py from the reference's
+ResizeLongestSide / LazySupervisedDataset.preprocess / CLIPImageProcessor / cv2) and, when PIL is importable, PIL live."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import inputs as gi  # noqa: E402
+
+from oracle import preprocess as op  # noqa: E402
+
+GOLD = torch.load(os.path.join(HERE, "golden", "preprocess.pt"), weights_only=False)
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def oracle_outputs(i, h, w, ls, lc):
+    img = gi.preprocess_image(i, h, w)
+    sam_u8 = op.resize_longest_side(img, ls)
+    image_sam, resize = op.image_sam(img, ls)
+    rc = op.resize_longest_side(img, lc)
+    clip_u8 = op.centre_pad(np.ascontiguousarray(rc.transpose(2, 0, 1)), lc, op.CLIP_PAD_U8)
+    m = gi.preprocess_mask(i, h, w)
+    region_u8 = op.centre_pad(op.resize_longest_side(m, lc)[None], lc, np.zeros(1, np.uint8))[0]
+    return {"sam_u8": sam_u8, "image_sam": image_sam, "clip_u8": clip_u8, "image_clip": op.image_clip(img, lc),
+            "region_u8": region_u8, "region_grid": op.region_mask(m, lc)}, resize
+
+
+@pytest.mark.parametrize("i", range(len(gi.PREPROCESS_SIZES)))
+def test_oracle_matches_reference_pipeline_bit_for_bit(i):
+    h, w, ls, lc = gi.PREPROCESS_SIZES[i]
+    case = GOLD["cases"][i]
+    assert case["hw"] == (h, w) and case["targets"] == (ls, lc)
+    outs, resize = oracle_outputs(i, h, w, ls, lc)
+    assert tuple(resize) == case["resize"]
+    for name, arr in outs.items():
+        if "tensors" in case:  # small case kept whole: report where, not just that
+            ref = case["tensors"][name].numpy()
+            assert arr.shape == ref.shape and arr.dtype == ref.dtype, name
+            assert np.array_equal(arr, ref), f"{name}: {np.argwhere(arr != ref)[:4]}"
+        assert digest(arr) == case["sha256"][name], f"case {i} {name}: differs from the reference's output"
+    assert np.array_equal(outs["region_grid"], case["region_grid"].numpy())
+
+
+def test_coefficient_tables_are_normalised_and_monotone():
+    for n_in, n_out in [(512, 256), (97, 191), (1777, 256), (336, 336), (40, 269), (2, 336), (4000, 7)]:
+        bounds, coeffs = op.pil_coeffs(n_in, n_out)
+        assert (np.abs(coeffs.sum(1) - (1 << op.PRECISION_BITS)) <= coeffs.shape[1]).all()
+        assert (np.diff(bounds[:, 0]) >= 0).all() and (bounds[:, 1] >= 1).all()
+        assert (bounds[:, 0] + bounds[:, 1] <= n_in).all()
+        # the band bound the CUDA kernel sizes its shared memory with (medplib_b200/preprocess.py:band_rows_bound)
+        from medplib_b200.preprocess import band_rows_bound
+        for R in (1, 2, 4, 8):
+            for y0 in range(0, n_out, R):
+                y1 = min(y0 + R, n_out)
+                rows = bounds[y1 - 1, 0] + bounds[y1 - 1, 1] - bounds[y0, 0]
+                assert rows <= band_rows_bound(n_in, n_out, R), (n_in, n_out, R, y0)
+
+
+def test_constant_image_and_identity():
+    img = np.full((123, 77, 3), 201, np.uint8)
+    assert (op.resize_longest_side(img, 256) == 201).all()  # weights sum to one within rounding
+    img = gi.preprocess_image(0, 200, 336)
+    assert np.array_equal(op.resize_longest_side(img, 336), img)  # both passes skipped
+    sam, resize = op.image_sam(img, 256)
+    assert resize == (152, 256) and sam.shape == (3, 256, 256)
+    assert (sam[:, :52] == 0).all() and (sam[:, 52 + 152:] == 0).all()  # (256 - 152) // 2 rows of zero padding on top
+
+
+def test_live_pil_when_available():
+    PIL = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(3)
+    for (h, w, nh, nw) in [(301, 203, 256, 173), (33, 900, 12, 336), (700, 700, 336, 336), (5, 5, 256, 256)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.array(PIL.fromarray(img).resize((nw, nh), PIL.BILINEAR))
+        assert np.array_equal(op.pil_resize_bilinear(img, nh, nw), ref)
+
+
+def test_product_host_tables_equal_the_oracle():
+    """medplib_b200/preprocess.py builds the kernel's tables on the host (vectorised); they must equal the oracle's
+    sequential restatement of PIL for every size pair, and the value tables must equal the oracle's."""
+    from medplib_b200 import preprocess as pp
+    rng = np.random.default_rng(1)
+    pairs = [(512, 256), (512, 336), (97, 191), (1777, 256), (336, 336), (40, 269), (2, 336), (4000, 7), (1, 5), (5, 1)]
+    pairs += [(int(a), int(b)) for a, b in rng.integers(1, 3000, (60, 2))]
+    for n_in, n_out in pairs:
+        b0, c0 = op.pil_coeffs(n_in, n_out)
+        b1, c1 = pp.pil_coeffs(n_in, n_out)
+        assert np.array_equal(b0, b1) and np.array_equal(c0, c1), (n_in, n_out)
+    assert np.array_equal(pp.sam_level_table().numpy(), op.sam_lut())
+    assert np.array_equal(pp.clip_level_table().numpy(), op.clip_lut())
+    assert pp.clip_pad_levels() == op.CLIP_PAD_U8.tolist() == [122, 116, 104]
+    for hw in [(512, 512), (300, 451), (1, 9), (1300, 1777)]:
+        for L in (256, 336):
+            assert pp.get_preprocess_shape(*hw, L) == op.get_preprocess_shape(*hw, L)
+
+
+def test_library_band_bound_matches_host_mirror():
+    from medplib_b200 import _lib
+    from medplib_b200.preprocess import band_rows_bound
+    lib = _lib.load()
+    for n_in, n_out in [(512, 256), (97, 191), (1777, 256), (336, 336), (40000, 256), (3, 336)]:
+        for R in (1, 2, 4, 8):
+            assert lib.mpl_preprocess_band_rows(n_in, n_out, R) == band_rows_bound(n_in, n_out, R)
+    assert lib.mpl_preprocess_band_rows(0, 4, 1) == -1
+
+
+def test_preprocessor_fails_loudly_without_gpu():
+    from medplib_b200 import _lib
+    from medplib_b200.preprocess import ImagePreprocessor
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.MplError):
+        ImagePreprocessor()
