@@ -143,56 +143,58 @@ class ImagePreprocessor:
         j.out_dtype, j.dst = _DT[dst.dtype], dst.data_ptr()
         return j, (new_h, new_w)
 
-    def __call__(self, images, region_masks=None):
+    def plan(self, images, region_masks=None):
+        """Validate, stage the u8 inputs on the device (host inputs: one pinned ragged buffer, one copy; device inputs are
+        used in place) and build the job list.  Returns a plan ``launch`` runs; ``__call__`` = ``launch(plan(...))``."""
         B = len(images)
         arrays = [torch.as_tensor(im) for im in images]
         masks = [[torch.as_tensor(m) for m in (region_masks[i] if region_masks is not None else [])] for i in range(B)]
         for a in arrays:
             if a.dtype != torch.uint8 or a.dim() != 3 or a.shape[2] != 3:
                 raise ValueError("images must be uint8 [H, W, 3] RGB")
-        flat = [a.reshape(-1) for a in arrays] + [m.reshape(-1) for ms in masks for m in ms]
         for i, ms in enumerate(masks):
             for m in ms:
                 if m.dtype != torch.uint8 or tuple(m.shape) != tuple(arrays[i].shape[:2]):
                     raise ValueError("region masks must be uint8 [H, W] of their image's size")
-        # one ragged staging buffer -> one host-to-device copy (pinned when the inputs live on the host)
-        sizes = [f.numel() for f in flat]
-        offs = np.concatenate([[0], np.cumsum([(s + 15) // 16 * 16 for s in sizes])]).tolist()
-        if all(f.device.type == "cuda" for f in flat):
-            stage = torch.empty(offs[-1], dtype=torch.uint8, device=self.device)
-            for f, o, s in zip(flat, offs, sizes):
-                stage[o:o + s] = f
-        else:
+        flat = [a for a in arrays] + [m for ms in masks for m in ms]
+        keep, ptrs = [], []
+        if flat and all(f.device.type == "cuda" for f in flat):
+            for f in flat:
+                f = f.contiguous()
+                keep.append(f)
+                ptrs.append(f.data_ptr())
+        elif flat:
+            sizes = [f.numel() for f in flat]
+            offs = np.concatenate([[0], np.cumsum([(n + 15) // 16 * 16 for n in sizes])]).tolist()
             host = torch.empty(offs[-1], dtype=torch.uint8, pin_memory=True)
-            for f, o, s in zip(flat, offs, sizes):
-                host[o:o + s] = f.cpu()
+            for f, o, n in zip(flat, offs, sizes):
+                host[o:o + n] = f.reshape(-1).cpu()
             stage = host.to(self.device, non_blocking=True)
+            keep.append(stage)
+            ptrs = [stage.data_ptr() + o for o in offs[:-1]]
         n_masks = sum(len(ms) for ms in masks)
         out_sam = torch.empty(B, 3, self.sam_size, self.sam_size, dtype=self.out_dtype, device=self.device)
         out_clip = torch.empty(B, 3, self.clip_size, self.clip_size, dtype=self.out_dtype, device=self.device)
         out_mask = torch.empty(n_masks, 1, self.clip_size, self.clip_size, dtype=torch.uint8, device=self.device)
         jobs, resize_list = [], []
-        base = stage.data_ptr()
         for i, a in enumerate(arrays):
             H, W = int(a.shape[0]), int(a.shape[1])
-            j, resize = self._job(base + offs[i], H, W, 3, self.sam_size, self.sam_lut, (0.0, 0.0, 0.0), out_sam[i])
+            j, resize = self._job(ptrs[i], H, W, 3, self.sam_size, self.sam_lut, (0.0, 0.0, 0.0), out_sam[i])
             jobs.append(j)
             resize_list.append(resize)
-            jobs.append(self._job(base + offs[i], H, W, 3, self.clip_size, self.clip_lut, self.clip_pad, out_clip[i])[0])
+            jobs.append(self._job(ptrs[i], H, W, 3, self.clip_size, self.clip_lut, self.clip_pad, out_clip[i])[0])
         k = 0
         for i, ms in enumerate(masks):
             H, W = int(arrays[i].shape[0]), int(arrays[i].shape[1])
             for _ in ms:
-                jobs.append(self._job(base + offs[B + k], H, W, 1, self.clip_size, None, (0.0, 0.0, 0.0), out_mask[k])[0])
+                jobs.append(self._job(ptrs[B + k], H, W, 1, self.clip_size, None, (0.0, 0.0, 0.0), out_mask[k])[0])
                 k += 1
         n = len(jobs)
+        jobs_host = jobs_dev = None
         if n:
             jobs_host = (PreprocessJob * n)(*jobs)
             blob = torch.frombuffer(bytearray(bytes(jobs_host)), dtype=torch.uint8)
             jobs_dev = blob.pin_memory().to(self.device, non_blocking=True)
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            _lib.check(self.lib.mpl_preprocess_images(jobs_host, ctypes.c_void_p(jobs_dev.data_ptr()), n,
-                                                      ctypes.c_void_p(stream)), "mpl_preprocess_images")
         out = {"images": out_sam, "images_clip": out_clip, "resize_list": resize_list}
         if region_masks is not None:
             grids = out_mask[:, :, ::self.patch, ::self.patch]  # cv2.resize(fx=1/14, INTER_NEAREST): every 14th pixel
@@ -201,4 +203,18 @@ class ImagePreprocessor:
             for ms in masks:
                 out["region_masks"].append([grids[k + t] for t in range(len(ms))])
                 k += len(ms)
-        return out
+        src_bytes = sum(int(a.shape[0]) * int(a.shape[1]) * 3 * 2 for a in arrays) + sum(m.numel() for ms in masks for m in ms)
+        out_bytes = out_sam.numel() * out_sam.element_size() + out_clip.numel() * out_clip.element_size() + out_mask.numel()
+        return {"n": n, "jobs_host": jobs_host, "jobs_dev": jobs_dev, "keep": keep, "out": out,
+                "algorithmic_bytes": src_bytes + out_bytes}
+
+    def launch(self, plan):
+        """ONE kernel launch on the current stream for every job of the plan; returns the output dict."""
+        if plan["n"]:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.mpl_preprocess_images(plan["jobs_host"], ctypes.c_void_p(plan["jobs_dev"].data_ptr()),
+                                                      plan["n"], ctypes.c_void_p(stream)), "mpl_preprocess_images")
+        return plan["out"]
+
+    def __call__(self, images, region_masks=None):
+        return self.launch(self.plan(images, region_masks))
