@@ -544,9 +544,11 @@ int mpl_mask_losses_bwd(const void* pred, const float* gt, const void* pred_iou,
  *   preprocess + pad_tensor_channelwise (:446-502) and CLIPImageProcessor rescale/normalize: every output value is a
  *     function of the resized u8 level, so the host passes a 256-entry fp32 table per channel (lut) and the pad value.
  * Each job turns src u8 [H,W,C] (interleaved, C = 1 or 3) into dst [C, out_size, out_size]: the new_h x new_w resized
- * image placed at (pad_top, pad_left), pad_value[c] elsewhere.  coef / bound are PIL's tables for one axis
- * (coef int32 [n_out, ks], bound int32 [n_out, 2] = first tap, tap count), built by the host
- * (medplib_b200/preprocess.py:pil_coeffs).  jobs_host and jobs_dev hold the same n_jobs structs (the pointers inside
+ * image placed at (pad_top, pad_left), pad_value[c] elsewhere.  coef / bound are PIL's tables for one axis, built by
+ * the host (medplib_b200/preprocess.py:pil_coeffs): bound int32 [n_out, 2] = (first tap, tap count); coef_y int32
+ * [new_h, ks_y]; coef_x TAP-MAJOR int32 [ks_x, new_w] with ks_x a multiple of 4, zero-filled past each pixel's tap
+ * count (the horizontal pass consumes taps four at a time from aligned 32-bit source words).  src must be 4-byte
+ * aligned (MPL_ERR_ALIGN).  jobs_host and jobs_dev hold the same n_jobs structs (the pointers inside
  * are device pointers); the host copy sizes the grid and the shared memory.  MPL_ERR_UNSUPPORTED when one output row's
  * taps do not fit 200 KB of shared memory (downscales beyond ~100x). */
 typedef struct {

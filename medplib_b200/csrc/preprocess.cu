@@ -38,6 +38,10 @@ __device__ __forceinline__ int clip8(int acc) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
+__device__ __forceinline__ unsigned ld_word(uintptr_t addr, uintptr_t last) {
+  return __ldg(reinterpret_cast<const unsigned*>(addr < last ? addr : last));
+}
+
 __global__ void __launch_bounds__(kThreads) preprocess_kernel(const mpl_preprocess_job* __restrict__ jobs) {
   extern __shared__ unsigned char tmp[];  // [rows][new_w * C] u8: the horizontal pass of this band's source rows
   __shared__ mpl_preprocess_job sj;
@@ -57,26 +61,59 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(const mpl_preproce
     in_lo = sj.bound_y[2 * ry0];
     const int nrows = sj.bound_y[2 * (ry1 - 1)] + sj.bound_y[2 * (ry1 - 1) + 1] - in_lo;
     const unsigned char* src = static_cast<const unsigned char*>(sj.src);
+    // Source bytes are read as aligned 32-bit words and funnel-shifted to the pixel boundary: 4 taps of an RGB pixel
+    // are 12 bytes = 3 words (one word for a single-channel mask), so a tap group costs 3 word loads instead of 12
+    // byte loads.  Words past the image end are clamped to the last valid word: those positions only ever meet the
+    // zero coefficients that pad every tap list to a multiple of 4 (coef_x is tap-major [ks_x][new_w]).
+    const uintptr_t wlast =
+        (reinterpret_cast<uintptr_t>(src) + static_cast<uintptr_t>(sj.H - 1) * sj.src_stride + sj.W * C - 1) & ~uintptr_t(3);
     for (int idx = tid; idx < nrows * new_w; idx += kThreads) {
       const int r = idx / new_w, xx = idx - r * new_w;
       const int xmin = __ldg(sj.bound_x + 2 * xx), n = __ldg(sj.bound_x + 2 * xx + 1);
-      const int* k = sj.coef_x + static_cast<long long>(xx) * sj.ks_x;
-      const unsigned char* s = src + static_cast<long long>(in_lo + r) * sj.src_stride + static_cast<long long>(xmin) * C;
+      const int* k = sj.coef_x + xx;
+      const uintptr_t a = reinterpret_cast<uintptr_t>(src) + static_cast<uintptr_t>(in_lo + r) * sj.src_stride +
+                          static_cast<uintptr_t>(xmin) * C;
+      const unsigned sh = static_cast<unsigned>(a & 3) * 8;
+      uintptr_t wp = a & ~uintptr_t(3);
       unsigned char* d = tmp + r * pitch + xx * C;
+      unsigned w0 = ld_word(wp, wlast);
       if (C == 3) {
         int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-        for (int x = 0; x < n; ++x) {
-          const int kv = __ldg(k + x);
-          a0 += __ldg(s + 3 * x) * kv;
-          a1 += __ldg(s + 3 * x + 1) * kv;
-          a2 += __ldg(s + 3 * x + 2) * kv;
+        for (int g = 0; g < n; g += 4) {
+          const unsigned w1 = ld_word(wp + 4, wlast), w2 = ld_word(wp + 8, wlast), w3 = ld_word(wp + 12, wlast);
+          const unsigned u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh), u2 = __funnelshift_r(w2, w3, sh);
+          const int k0 = __ldg(k + g * new_w), k1 = __ldg(k + (g + 1) * new_w), k2 = __ldg(k + (g + 2) * new_w),
+                    k3 = __ldg(k + (g + 3) * new_w);
+          a0 += static_cast<int>(u0 & 0xff) * k0;
+          a1 += static_cast<int>((u0 >> 8) & 0xff) * k0;
+          a2 += static_cast<int>((u0 >> 16) & 0xff) * k0;
+          a0 += static_cast<int>(u0 >> 24) * k1;
+          a1 += static_cast<int>(u1 & 0xff) * k1;
+          a2 += static_cast<int>((u1 >> 8) & 0xff) * k1;
+          a0 += static_cast<int>((u1 >> 16) & 0xff) * k2;
+          a1 += static_cast<int>(u1 >> 24) * k2;
+          a2 += static_cast<int>(u2 & 0xff) * k2;
+          a0 += static_cast<int>((u2 >> 8) & 0xff) * k3;
+          a1 += static_cast<int>((u2 >> 16) & 0xff) * k3;
+          a2 += static_cast<int>(u2 >> 24) * k3;
+          w0 = w3;
+          wp += 12;
         }
         d[0] = static_cast<unsigned char>(clip8(a0));
         d[1] = static_cast<unsigned char>(clip8(a1));
         d[2] = static_cast<unsigned char>(clip8(a2));
       } else {
         int a0 = 1 << (kPrecisionBits - 1);
-        for (int x = 0; x < n; ++x) a0 += __ldg(s + x) * __ldg(k + x);
+        for (int g = 0; g < n; g += 4) {
+          const unsigned w1 = ld_word(wp + 4, wlast);
+          const unsigned u0 = __funnelshift_r(w0, w1, sh);
+          a0 += static_cast<int>(u0 & 0xff) * __ldg(k + g * new_w);
+          a0 += static_cast<int>((u0 >> 8) & 0xff) * __ldg(k + (g + 1) * new_w);
+          a0 += static_cast<int>((u0 >> 16) & 0xff) * __ldg(k + (g + 2) * new_w);
+          a0 += static_cast<int>(u0 >> 24) * __ldg(k + (g + 3) * new_w);
+          w0 = w1;
+          wp += 4;
+        }
         d[0] = static_cast<unsigned char>(clip8(a0));
       }
     }
@@ -129,9 +166,10 @@ extern "C" int mpl_preprocess_images(const mpl_preprocess_job* jobs_host, const 
     if (j.src == nullptr || j.dst == nullptr || j.coef_x == nullptr || j.bound_x == nullptr || j.coef_y == nullptr ||
         j.bound_y == nullptr || (j.C != 1 && j.C != 3) || j.H <= 0 || j.W <= 0 || j.new_h <= 0 || j.new_w <= 0 ||
         j.pad_top < 0 || j.pad_left < 0 || j.pad_top + j.new_h > j.out_size || j.pad_left + j.new_w > j.out_size ||
-        j.ks_x <= 0 || j.ks_y <= 0 || j.src_stride < static_cast<long long>(j.W) * j.C ||
+        j.ks_x <= 0 || (j.ks_x & 3) != 0 || j.ks_y <= 0 || j.src_stride < static_cast<long long>(j.W) * j.C ||
         (j.out_dtype != MPL_DT_BF16 && j.out_dtype != MPL_DT_F32 && j.out_dtype != MPL_DT_U8))
       return MPL_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(j.src) & 3) != 0) return MPL_ERR_ALIGN;  // word loads never reach below src
     const int R = pick_band(j.H, j.new_h, j.new_w, j.C);
     if (R == 0) return MPL_ERR_UNSUPPORTED;
     const int b = (j.out_size + R - 1) / R;

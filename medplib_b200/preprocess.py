@@ -114,13 +114,22 @@ class ImagePreprocessor:
         self.clip_pad = [float(clip[c, lvl]) for c, lvl in enumerate(clip_pad_levels())]
         self._tables = {}
 
-    def _axis(self, n_in, n_out):
-        key = (n_in, n_out)
+    def _axis(self, n_in, n_out, tap_major):
+        """Device tables of one axis. The horizontal pass reads its coefficients tap-major ([ks4, n_out], tap count
+        rounded up to a multiple of 4 with zeros: a warp's 32 coefficients of one tap are one 128-byte line and the
+        kernel consumes taps four at a time); the vertical pass reads PIL's own [n_out, ks] layout."""
+        key = (n_in, n_out, tap_major)
         t = self._tables.get(key)
         if t is None:
             bounds, coeffs = pil_coeffs(n_in, n_out)
-            t = (torch.from_numpy(bounds).contiguous().to(self.device), torch.from_numpy(coeffs).contiguous().to(self.device),
-                 coeffs.shape[1])
+            ks = coeffs.shape[1]
+            if tap_major:
+                ks = (ks + 3) // 4 * 4
+                padded = np.zeros((ks, n_out), np.int32)
+                padded[:coeffs.shape[1]] = coeffs.T
+                coeffs = padded
+            t = (torch.from_numpy(bounds).contiguous().to(self.device),
+                 torch.from_numpy(np.ascontiguousarray(coeffs)).to(self.device), ks)
             if len(self._tables) > 4096:
                 self._tables.clear()
             self._tables[key] = t
@@ -130,8 +139,8 @@ class ImagePreprocessor:
         new_h, new_w = get_preprocess_shape(H, W, target)
         if new_h < 1 or new_w < 1:  # the reference's PIL resize raises on an empty target as well
             raise ValueError(f"a {H}x{W} image has no pixels left at longest side {target}")
-        bx, cx, ksx = self._axis(W, new_w)
-        by, cy, ksy = self._axis(H, new_h)
+        bx, cx, ksx = self._axis(W, new_w, True)
+        by, cy, ksy = self._axis(H, new_h, False)
         j = PreprocessJob()
         j.src, j.src_stride, j.H, j.W, j.C = src, W * C, H, W, C
         j.new_h, j.new_w, j.out_size = new_h, new_w, target
@@ -161,6 +170,8 @@ class ImagePreprocessor:
         if flat and all(f.device.type == "cuda" for f in flat):
             for f in flat:
                 f = f.contiguous()
+                if f.data_ptr() % 4:  # the kernel reads aligned 32-bit words starting at the image's first byte
+                    f = f.clone()
                 keep.append(f)
                 ptrs.append(f.data_ptr())
         elif flat:
