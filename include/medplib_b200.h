@@ -547,10 +547,10 @@ int mpl_mask_losses_bwd(const void* pred, const float* gt, const void* pred_iou,
  * image placed at (pad_top, pad_left), pad_value[c] elsewhere.  coef / bound are PIL's tables for one axis, built by
  * the host (medplib_b200/preprocess.py:pil_coeffs): bound int32 [n_out, 2] = (first tap, tap count); coef_y int32
  * [new_h, ks_y]; coef_x TAP-MAJOR int32 [ks_x, new_w] with ks_x a multiple of 4, zero-filled past each pixel's tap
- * count (the horizontal pass consumes taps four at a time from aligned 32-bit source words).  src must be 4-byte
- * aligned (MPL_ERR_ALIGN).  jobs_host and jobs_dev hold the same n_jobs structs (the pointers inside
- * are device pointers); the host copy sizes the grid and the shared memory.  MPL_ERR_UNSUPPORTED when one output row's
- * taps do not fit 200 KB of shared memory (downscales beyond ~100x). */
+ * count (the horizontal pass consumes taps four at a time from aligned 32-bit source words).  src must be 16-byte
+ * aligned (MPL_ERR_ALIGN) and up to 15 bytes past the image's last byte, inside the same allocation, may be read.  jobs_host and jobs_dev hold the same n_jobs structs (the pointers inside
+ * are device pointers); the host copy sizes the grid and the shared memory.  MPL_ERR_UNSUPPORTED when two staged source
+ * rows plus one output row's taps do not fit 200 KB of shared memory (rows beyond ~30k pixels, downscales beyond ~100x). */
 typedef struct {
   const void* src;
   long long src_stride; /* bytes between source rows */

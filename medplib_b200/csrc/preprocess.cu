@@ -1,9 +1,10 @@
 // Image input pipeline: u8 decoded image -> resized / padded / normalised tensor, one launch per batch.
 //
 // PIL's BILINEAR resize is two integer convolutions with a u8 rounding in between, so the kernel keeps that structure:
-// a CTA owns a band of R output rows of one job, runs the horizontal pass over just the source rows that band's
-// vertical taps touch into shared memory (u8), then the vertical pass + the per-level fp32 table + the centre pad
-// straight to the [C, L, L] output.  HBM traffic is the source once per job (bands overlap by the filter support,
+// a CTA owns a band of R output rows of one job, streams just the source rows that band's vertical taps touch through a
+// double-buffered cp.async stage (RB rows at a time, 16-byte chunks, so the HBM/L2 latency is paid once per stage, not
+// once per tap), runs the horizontal pass from that stage into shared memory (u8), then the vertical pass + the
+// per-level fp32 table + the centre pad straight to the [C, L, L] output.  HBM traffic is the source once per job (bands overlap by the filter support,
 // absorbed by L2) and the output once; there is no intermediate image in HBM.  Integer arithmetic follows
 // Pillow's libImaging/Resample.c (ImagingResampleHorizontal_8bpc / Vertical_8bpc) so results are bit-exact.
 #include <cuda_bf16.h>
@@ -27,10 +28,22 @@ __host__ __device__ inline int band_rows_bound(int in_size, int out_size, int R)
   return b > in_size ? in_size : static_cast<int>(b);
 }
 
-__host__ __device__ inline int pick_band(int H, int new_h, int new_w, int C) {
-  for (int R = 8; R >= 1; R >>= 1)
-    if (static_cast<long long>(band_rows_bound(H, new_h, R)) * new_w * C <= kSmemBudget) return R;
+// Bytes of one staged source row: the row's 16-byte-aligned footprint (up to 15 bytes of misalignment in front) plus the
+// 4-tap group over-read behind it (< 16 bytes), in 16-byte chunks.
+__host__ __device__ inline int stage_pitch(int W, int C) { return ((W * C + 15) / 16 + 2) * 16; }
+
+// (R output rows per band, RB source rows per cp.async stage) as R | RB << 8, or 0 when nothing fits.
+__host__ __device__ inline int pick_band(int H, int W, int new_h, int new_w, int C) {
+  const int Rs[6] = {8, 4, 4, 2, 2, 1}, RBs[6] = {4, 4, 2, 2, 1, 1};
+  for (int t = 0; t < 6; ++t) {
+    const long long need = 2LL * RBs[t] * stage_pitch(W, C) + static_cast<long long>(band_rows_bound(H, new_h, Rs[t])) * new_w * C;
+    if (need <= kSmemBudget) return Rs[t] | (RBs[t] << 8);
+  }
   return 0;
+}
+
+__host__ __device__ inline long long band_smem(int H, int W, int new_h, int new_w, int C, int rrb) {
+  return 2LL * (rrb >> 8) * stage_pitch(W, C) + static_cast<long long>(band_rows_bound(H, new_h, rrb & 255)) * new_w * C;
 }
 
 __device__ __forceinline__ int clip8(int acc) {
@@ -38,84 +51,112 @@ __device__ __forceinline__ int clip8(int acc) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-__device__ __forceinline__ unsigned ld_word(uintptr_t addr, uintptr_t last) {
-  return __ldg(reinterpret_cast<const unsigned*>(addr < last ? addr : last));
+__device__ __forceinline__ void cp_async16(unsigned char* dst_smem, uintptr_t src_global) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst_smem))),
+               "l"(src_global)
+               : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads) preprocess_kernel(const mpl_preprocess_job* __restrict__ jobs) {
-  extern __shared__ unsigned char tmp[];  // [rows][new_w * C] u8: the horizontal pass of this band's source rows
+  extern __shared__ __align__(16) unsigned char smem[];  // [2][RB][stage_pitch] staged source rows | tmp
   __shared__ mpl_preprocess_job sj;
   __shared__ float s_lut[3 * 256];
   const int tid = threadIdx.x;
   if (tid == 0) sj = jobs[blockIdx.y];
   __syncthreads();
   const int C = sj.C, L = sj.out_size, new_h = sj.new_h, new_w = sj.new_w;
-  const int R = pick_band(sj.H, new_h, new_w, C);
+  const int rrb = pick_band(sj.H, sj.W, new_h, new_w, C);
+  const int R = rrb & 255, RB = rrb >> 8;
   const int y0 = blockIdx.x * R;
-  if (R == 0 || y0 >= L) return;
+  if (rrb == 0 || y0 >= L) return;
   const int y1 = min(y0 + R, L);
   const int ry0 = max(y0 - sj.pad_top, 0), ry1 = min(y1 - sj.pad_top, new_h);
   const int pitch = new_w * C;
+  const int sp = stage_pitch(sj.W, C), cpr = sp / 16;
+  unsigned char* tmp = smem + 2 * RB * sp;  // [rows][new_w * C] u8: the horizontal pass of this band's source rows
   int in_lo = 0;
   if (ry0 < ry1) {
     in_lo = sj.bound_y[2 * ry0];
     const int nrows = sj.bound_y[2 * (ry1 - 1)] + sj.bound_y[2 * (ry1 - 1) + 1] - in_lo;
-    const unsigned char* src = static_cast<const unsigned char*>(sj.src);
-    // Source bytes are read as aligned 32-bit words and funnel-shifted to the pixel boundary: 4 taps of an RGB pixel
-    // are 12 bytes = 3 words (one word for a single-channel mask), so a tap group costs 3 word loads instead of 12
-    // byte loads.  Words past the image end are clamped to the last valid word: those positions only ever meet the
-    // zero coefficients that pad every tap list to a multiple of 4 (coef_x is tap-major [ks_x][new_w]).
-    const uintptr_t wlast =
-        (reinterpret_cast<uintptr_t>(src) + static_cast<uintptr_t>(sj.H - 1) * sj.src_stride + sj.W * C - 1) & ~uintptr_t(3);
-    for (int idx = tid; idx < nrows * new_w; idx += kThreads) {
-      const int r = idx / new_w, xx = idx - r * new_w;
-      const int xmin = __ldg(sj.bound_x + 2 * xx), n = __ldg(sj.bound_x + 2 * xx + 1);
-      const int* k = sj.coef_x + xx;
-      const uintptr_t a = reinterpret_cast<uintptr_t>(src) + static_cast<uintptr_t>(in_lo + r) * sj.src_stride +
-                          static_cast<uintptr_t>(xmin) * C;
-      const unsigned sh = static_cast<unsigned>(a & 3) * 8;
-      uintptr_t wp = a & ~uintptr_t(3);
-      unsigned char* d = tmp + r * pitch + xx * C;
-      unsigned w0 = ld_word(wp, wlast);
-      if (C == 3) {
-        int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-        for (int g = 0; g < n; g += 4) {
-          const unsigned w1 = ld_word(wp + 4, wlast), w2 = ld_word(wp + 8, wlast), w3 = ld_word(wp + 12, wlast);
-          const unsigned u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh), u2 = __funnelshift_r(w2, w3, sh);
-          const int k0 = __ldg(k + g * new_w), k1 = __ldg(k + (g + 1) * new_w), k2 = __ldg(k + (g + 2) * new_w),
-                    k3 = __ldg(k + (g + 3) * new_w);
-          a0 += static_cast<int>(u0 & 0xff) * k0;
-          a1 += static_cast<int>((u0 >> 8) & 0xff) * k0;
-          a2 += static_cast<int>((u0 >> 16) & 0xff) * k0;
-          a0 += static_cast<int>(u0 >> 24) * k1;
-          a1 += static_cast<int>(u1 & 0xff) * k1;
-          a2 += static_cast<int>((u1 >> 8) & 0xff) * k1;
-          a0 += static_cast<int>((u1 >> 16) & 0xff) * k2;
-          a1 += static_cast<int>(u1 >> 24) * k2;
-          a2 += static_cast<int>(u2 & 0xff) * k2;
-          a0 += static_cast<int>((u2 >> 8) & 0xff) * k3;
-          a1 += static_cast<int>((u2 >> 16) & 0xff) * k3;
-          a2 += static_cast<int>(u2 >> 24) * k3;
-          w0 = w3;
-          wp += 12;
-        }
-        d[0] = static_cast<unsigned char>(clip8(a0));
-        d[1] = static_cast<unsigned char>(clip8(a1));
-        d[2] = static_cast<unsigned char>(clip8(a2));
-      } else {
-        int a0 = 1 << (kPrecisionBits - 1);
-        for (int g = 0; g < n; g += 4) {
-          const unsigned w1 = ld_word(wp + 4, wlast);
-          const unsigned u0 = __funnelshift_r(w0, w1, sh);
-          a0 += static_cast<int>(u0 & 0xff) * __ldg(k + g * new_w);
-          a0 += static_cast<int>((u0 >> 8) & 0xff) * __ldg(k + (g + 1) * new_w);
-          a0 += static_cast<int>((u0 >> 16) & 0xff) * __ldg(k + (g + 2) * new_w);
-          a0 += static_cast<int>(u0 >> 24) * __ldg(k + (g + 3) * new_w);
-          w0 = w1;
-          wp += 4;
-        }
-        d[0] = static_cast<unsigned char>(clip8(a0));
+    const uintptr_t src = reinterpret_cast<uintptr_t>(sj.src);  // 16-byte aligned (checked by the host entry)
+    // chunks past the image end are clamped to its last chunk: those bytes only ever meet the zero coefficients that
+    // pad every tap list to a multiple of 4 (coef_x is tap-major [ks_x][new_w])
+    const uintptr_t last_chunk = (src + static_cast<uintptr_t>(sj.H - 1) * sj.src_stride + sj.W * C - 1) & ~uintptr_t(15);
+    auto issue = [&](int stage, int r0) {
+      const int nb = min(RB, nrows - r0);
+      unsigned char* buf = smem + stage * RB * sp;
+      for (int idx = tid; idx < nb * cpr; idx += kThreads) {
+        const int i = idx / cpr, v = idx - i * cpr;
+        uintptr_t g = ((src + static_cast<uintptr_t>(in_lo + r0 + i) * sj.src_stride) & ~uintptr_t(15)) + 16 * v;
+        g = g < last_chunk ? g : last_chunk;
+        cp_async16(buf + i * sp + 16 * v, g);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0, 0);
+    int stage = 0;
+    for (int r0 = 0; r0 < nrows; r0 += RB, stage ^= 1) {
+      if (r0 + RB < nrows) {
+        issue(stage ^ 1, r0 + RB);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();
+      const int nb = min(RB, nrows - r0);
+      const unsigned char* buf = smem + stage * RB * sp;
+      // 4 taps of an RGB pixel are 12 bytes = 3 aligned words funnel-shifted to the pixel boundary (1 word for a mask)
+      for (int idx = tid; idx < nb * new_w; idx += kThreads) {
+        const int i = idx / new_w, xx = idx - i * new_w;
+        const int xmin = __ldg(sj.bound_x + 2 * xx), n = __ldg(sj.bound_x + 2 * xx + 1);
+        const int* k = sj.coef_x + xx;
+        const int mis = static_cast<int>((src + static_cast<uintptr_t>(in_lo + r0 + i) * sj.src_stride) & 15);
+        const int a = mis + xmin * C;
+        const unsigned sh = static_cast<unsigned>(a & 3) * 8;
+        const unsigned* wp = reinterpret_cast<const unsigned*>(buf + i * sp + (a & ~3));
+        unsigned char* d = tmp + (r0 + i) * pitch + xx * C;
+        unsigned w0 = wp[0];
+        if (C == 3) {
+          int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+          for (int g = 0; g < n; g += 4) {
+            const unsigned w1 = wp[1], w2 = wp[2], w3 = wp[3];
+            const unsigned u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh), u2 = __funnelshift_r(w2, w3, sh);
+            const int k0 = __ldg(k + g * new_w), k1 = __ldg(k + (g + 1) * new_w), k2 = __ldg(k + (g + 2) * new_w),
+                      k3 = __ldg(k + (g + 3) * new_w);
+            a0 += static_cast<int>(u0 & 0xff) * k0;
+            a1 += static_cast<int>((u0 >> 8) & 0xff) * k0;
+            a2 += static_cast<int>((u0 >> 16) & 0xff) * k0;
+            a0 += static_cast<int>(u0 >> 24) * k1;
+            a1 += static_cast<int>(u1 & 0xff) * k1;
+            a2 += static_cast<int>((u1 >> 8) & 0xff) * k1;
+            a0 += static_cast<int>((u1 >> 16) & 0xff) * k2;
+            a1 += static_cast<int>(u1 >> 24) * k2;
+            a2 += static_cast<int>(u2 & 0xff) * k2;
+            a0 += static_cast<int>((u2 >> 8) & 0xff) * k3;
+            a1 += static_cast<int>((u2 >> 16) & 0xff) * k3;
+            a2 += static_cast<int>(u2 >> 24) * k3;
+            w0 = w3;
+            wp += 3;
+          }
+          d[0] = static_cast<unsigned char>(clip8(a0));
+          d[1] = static_cast<unsigned char>(clip8(a1));
+          d[2] = static_cast<unsigned char>(clip8(a2));
+        } else {
+          int a0 = 1 << (kPrecisionBits - 1);
+          for (int g = 0; g < n; g += 4) {
+            const unsigned w1 = wp[1];
+            const unsigned u0 = __funnelshift_r(w0, w1, sh);
+            a0 += static_cast<int>(u0 & 0xff) * __ldg(k + g * new_w);
+            a0 += static_cast<int>((u0 >> 8) & 0xff) * __ldg(k + (g + 1) * new_w);
+            a0 += static_cast<int>((u0 >> 16) & 0xff) * __ldg(k + (g + 2) * new_w);
+            a0 += static_cast<int>(u0 >> 24) * __ldg(k + (g + 3) * new_w);
+            w0 = w1;
+            wp += 1;
+          }
+          d[0] = static_cast<unsigned char>(clip8(a0));
+        }
+      }
+      __syncthreads();  // the stage just read is the one the next iteration's cp.async overwrites
     }
   }
   if (sj.lut != nullptr)
@@ -169,12 +210,13 @@ extern "C" int mpl_preprocess_images(const mpl_preprocess_job* jobs_host, const 
         j.ks_x <= 0 || (j.ks_x & 3) != 0 || j.ks_y <= 0 || j.src_stride < static_cast<long long>(j.W) * j.C ||
         (j.out_dtype != MPL_DT_BF16 && j.out_dtype != MPL_DT_F32 && j.out_dtype != MPL_DT_U8))
       return MPL_ERR_ARG;
-    if ((reinterpret_cast<uintptr_t>(j.src) & 3) != 0) return MPL_ERR_ALIGN;  // word loads never reach below src
-    const int R = pick_band(j.H, j.new_h, j.new_w, j.C);
-    if (R == 0) return MPL_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(j.src) & 15) != 0) return MPL_ERR_ALIGN;  // aligned chunks never reach below src
+    const int rrb = pick_band(j.H, j.W, j.new_h, j.new_w, j.C);
+    if (rrb == 0) return MPL_ERR_UNSUPPORTED;
+    const int R = rrb & 255;
     const int b = (j.out_size + R - 1) / R;
     bands = b > bands ? b : bands;
-    const long long need = static_cast<long long>(band_rows_bound(j.H, j.new_h, R)) * j.new_w * j.C;
+    const long long need = band_smem(j.H, j.W, j.new_h, j.new_w, j.C, rrb);
     smem = need > smem ? need : smem;
   }
   static bool attr_set = false;

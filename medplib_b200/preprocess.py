@@ -170,7 +170,7 @@ class ImagePreprocessor:
         if flat and all(f.device.type == "cuda" for f in flat):
             for f in flat:
                 f = f.contiguous()
-                if f.data_ptr() % 4:  # the kernel reads aligned 32-bit words starting at the image's first byte
+                if f.data_ptr() % 16:  # the kernel stages aligned 16-byte chunks starting at the image's first byte
                     f = f.clone()
                 keep.append(f)
                 ptrs.append(f.data_ptr())
