@@ -248,7 +248,7 @@ class LlamaTrainStack:
         self.top_k = int(moe.get("top_k_experts", 1) or 1)
         self.aux_coef = float(getattr(model, "router_aux_loss_coef", 0.0) or 0.0)
         self.use_rts = True  # DeepSpeed top1gating default (use_rts=True): random token selection on overflow
-        self.debug = None  # dict: stage name -> tensor copies (tools/debug_train.py)
+        self.debug = None  # dict: stage name -> tensor copies (tests/dev/debug_train.py)
         self.training = True          # lora_dropout is active (model.train()); Trainer keeps it in sync with the model
         self.dropout_masks = None     # tests: {adapted module name: keep mask [rows, in_features]} instead of torch.rand
         from .engine import rope_tables

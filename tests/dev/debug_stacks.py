@@ -1,6 +1,6 @@
 """Stage-by-stage op-level replay of the CLIP / SAM-encoder block sequences against oracle intermediates (dev tool)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.nn.functional as F
 from medplib_b200 import ops, engine
 from oracle import clip, sam, weights

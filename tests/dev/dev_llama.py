@@ -1,8 +1,8 @@
 """Dev tool: per-layer / per-token error of the native LLaMA-MoE stack against the bf16 oracle for one test case, and a
-decode-step probe (CPU enqueue time vs GPU time). Usage: python tools/dev_llama.py [case|probe] ..."""
+decode-step probe (CPU enqueue time vs GPU time). Usage: python tests/dev/dev_llama.py [case|probe] ..."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import torch
 bf16 = torch.bfloat16
 dev = torch.device("cuda:0")

@@ -61,8 +61,15 @@ def test_no_cpu_fallback():
 
 def test_product_never_imports_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "medplib_b200")):
-        for f in files:
-            if f.endswith((".py", ".cu", ".h", ".cuh")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f"{f} imports the oracle"
+    for top in ("medplib_b200", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".h", ".cuh")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f"{top}/{f} imports the oracle"
+    # bench.py: only inside the CPU legs (cpu_reference / cpu_preprocess / _pre_one), never at module level
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    assert not re.search(r"^(from|import)\s+oracle\b", bench, re.M)
+    for m in re.finditer(r"^\s+from oracle import", bench, re.M):
+        fn = re.findall(r"^def (\w+)\(", bench[:m.start()], re.M)[-1]
+        assert fn in ("cpu_reference", "cpu_preprocess", "_pre_one"), f"bench.py:{fn} imports the oracle"
