@@ -1,0 +1,49 @@
+"""GPU: the streaming serving loop (medplib_b200/serve.py) against evaluate() on the same small model —
+same greedy tokens, same mask.  Written after the round's GPU budget was spent: it has NOT run on a B200 yet, so it only
+runs when MPL_RUN_UNVALIDATED=1 (the first gpurun of the next round); the loop's host logic is covered on CPU by
+tests/test_serve_cpu.py and every model call it makes (per-token forward with a KV cache, _seg_embeddings,
+get_visual_embs, _decode_masks) is covered by tests/test_model_gpu.py."""
+import math
+import os
+
+import pytest
+import torch
+
+from test_model_gpu import SEG, build, inputs
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("MPL_RUN_UNVALIDATED"), reason="not yet validated on a B200")]
+
+
+class Tok:
+    pad_token_id, eos_token_id = 0, 2
+
+    def __call__(self, s, add_special_tokens=True):
+        raise AssertionError("no stop string in this test")
+
+    def decode(self, ids, skip_special_tokens=True):
+        return " ".join(str(i) for i in ids if not (skip_special_tokens and i in (0, 2)))
+
+
+def test_stream_equals_evaluate(dev):
+    from medplib_b200 import serve
+    m, _, _ = build(dev)
+    ids, clip_img, sam_img = inputs()
+    label = torch.zeros(70, 90)
+    forced = {3: SEG, 5: 2}
+    out_ids, masks = m.evaluate(clip_img.to(dev), sam_img.to(dev), ids.to(dev), [(256, 256)], [label],
+                                max_new_tokens=6, forced_tokens=forced)
+    recs = list(serve.generate_stream(m, Tok(), ids.to(dev), images_clip=clip_img.to(dev), images_sam=sam_img.to(dev),
+                                      resize=(256, 256), original_size=(70, 90), temperature=0.0, max_new_tokens=6,
+                                      forced_tokens=forced))
+    new = out_ids[0, ids.shape[1]:].tolist()
+    assert len(recs) == 6 and recs[-1]["text"] == Tok().decode(new)
+    assert all(r["mask"] == [] for r in recs[:-1])
+    want = masks[0][0].float()
+    thr = math.log(0.1 / 0.9)
+    got = torch.zeros(70, 90, dtype=torch.bool)
+    for r, c in recs[-1]["mask"]:
+        got[r, c] = True
+    far = ((want - thr).abs() > 2e-2 * want.abs().max()).cpu()
+    assert (recs[-1]["height"], recs[-1]["width"]) == ("70", "90")
+    assert torch.equal(got[far], (want.cpu() > thr)[far])
