@@ -120,3 +120,21 @@ def test_preprocessor_fails_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(_lib.MplError):
         ImagePreprocessor()
+
+
+def test_oracle_equals_pil_on_random_shapes():
+    """Property check over the size space (up- and down-scales, 1-pixel axes, non-integer ratios, both channel counts)."""
+    PIL = pytest.importorskip("PIL.Image")
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import strategies as st
+
+    @hyp.settings(max_examples=60, deadline=None, derandomize=True)
+    @hyp.given(st.integers(1, 90), st.integers(1, 90), st.integers(1, 120), st.integers(1, 120), st.booleans(),
+               st.integers(0, 2 ** 31 - 1))
+    def check(h, w, nh, nw, rgb, seed):
+        rng = np.random.default_rng(seed)
+        img = rng.integers(0, 256, (h, w, 3) if rgb else (h, w), dtype=np.uint8)
+        ref = np.array(PIL.fromarray(img).resize((nw, nh), PIL.BILINEAR))
+        assert np.array_equal(op.pil_resize_bilinear(img, nh, nw), ref), (h, w, nh, nw, rgb)
+
+    check()
