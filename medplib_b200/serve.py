@@ -34,6 +34,27 @@ def insert_region_placeholders(input_ids, id_open, id_close):
     return ids
 
 
+def tokenize_with_sentinels(prompt, tokenizer, return_tensors=None):
+    """``tokenizer_image_token`` (datasets/LazySupervisedDataset.py:353-388, model_worker.py:307-318): tokenise the text
+    around every ``<image>`` separately, keep ONE leading BOS, put the IMAGE sentinel (-200) at each ``<image>`` and the
+    REGION sentinel (-300) inside each ``<region></region>`` pair."""
+    chunks = [tokenizer(c).input_ids for c in prompt.split("<image>")]
+    bos = getattr(tokenizer, "bos_token_id", None)
+    has_bos = bool(chunks and chunks[0] and chunks[0][0] == bos)
+    ids = [chunks[0][0]] if has_bos else []
+    for n, chunk in enumerate(chunks):
+        if n:
+            ids.append(IMAGE_TOKEN_INDEX)
+        ids.extend(chunk[1:] if has_bos else chunk)
+    ids = insert_region_placeholders(ids, tokenizer("<region>", add_special_tokens=False).input_ids[0],
+                                     tokenizer("</region>", add_special_tokens=False).input_ids[0])
+    if return_tensors is None:
+        return ids
+    if return_tensors != "pt":
+        raise ValueError(f"Unsupported tensor type: {return_tensors}")
+    return torch.tensor(ids, dtype=torch.long)
+
+
 def encode_sparse(mask):
     """model_worker.py:519-523: list of [row, col] of the non-zero pixels."""
     return torch.nonzero(torch.as_tensor(mask)).tolist()

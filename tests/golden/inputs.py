@@ -111,3 +111,32 @@ def preprocess_mask(i, h, w):
     cy, cx, ry, rx = (torch.rand(4, generator=g) * torch.tensor([h, w, h / 2, w / 2]) + torch.tensor([0, 0, 2, 2])).tolist()
     yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
     return ((((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2) <= 1).to(torch.uint8).numpy()
+
+
+class StubTokenizer:
+    """Deterministic stand-in for the LLaMA tokenizer (no tokenizer model offline): whitespace words -> ids by a fixed
+    hash, `<region>` / `</region>` / `<im_start>` as single added tokens, optional BOS — enough to exercise the sentinel
+    logic of tokenizer_image_token (datasets/LazySupervisedDataset.py:353-388)."""
+    ADDED = {"<region>": 32005, "</region>": 32006, "<im_start>": 32001, "<im_end>": 32002, "<SEG>": 32003}
+
+    def __init__(self, bos=True):
+        self.bos_token_id = 1 if bos else None
+        self.pad_token_id, self.eos_token_id = 0, 2
+
+    def __call__(self, text, add_special_tokens=True):
+        import re
+        from types import SimpleNamespace
+        ids = [1] if (self.bos_token_id is not None and add_special_tokens) else []
+        for piece in re.findall(r"</?[a-z_A-Z]+>|\S+", text):
+            ids.append(self.ADDED.get(piece, 3 + sum(ord(c) * (i + 7) for i, c in enumerate(piece)) % 31000))
+        return SimpleNamespace(input_ids=ids)
+
+
+TOKENIZE_PROMPTS = [
+    "USER: <image>\nWhat is shown in <region></region> ? ASSISTANT:",
+    "<image>",
+    "no image here, only <region></region> and <region></region>",
+    "<im_start><image><im_end> two images <image> and text <region> x </region>",
+    "",
+    "trailing image <image>",
+]

@@ -79,5 +79,10 @@ for i, (h, w, ls, lc) in enumerate(gi.PREPROCESS_SIZES):
         case["tensors"] = tensors  # small enough to keep whole, for debugging a digest mismatch
     out["cases"].append(case)
     print(i, (h, w), (ls, lc), tuple(r.shape), tuple(rm_grid.shape))
+# ---- sentinel tokenisation: the reference's tokenizer_image_token on a deterministic stub tokenizer
+from datasets.LazySupervisedDataset import tokenizer_image_token  # noqa: E402
+
+out["tokenize"] = [{"bos": bos, "prompt": pr, "ids": tokenizer_image_token(pr, gi.StubTokenizer(bos))}
+                   for bos in (True, False) for pr in gi.TOKENIZE_PROMPTS]
 torch.save(out, os.path.join(HERE, "preprocess.pt"))
 print("preprocess.pt %.1f KiB" % (os.path.getsize(os.path.join(HERE, "preprocess.pt")) / 1024))

@@ -120,3 +120,19 @@ def test_region_placeholders():
     assert serve.insert_region_placeholders([5, o, c, 6, o, c], o, c) == [5, o, -300, c, 6, o, -300, c]
     assert serve.insert_region_placeholders([o, 7, c, o], o, c) == [o, 7, c, o]
     assert serve.encode_sparse(torch.tensor([[0, 1], [1, 0]])) == [[0, 1], [1, 0]]
+
+
+def test_sentinel_tokenisation_matches_the_reference():
+    """tests/golden/preprocess.pt['tokenize'] = the reference's own tokenizer_image_token on the stub tokenizer."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import inputs as gi
+    gold = torch.load(os.path.join(here, "golden", "preprocess.pt"), weights_only=False)["tokenize"]
+    assert len(gold) == 2 * len(gi.TOKENIZE_PROMPTS)
+    for case in gold:
+        got = serve.tokenize_with_sentinels(case["prompt"], gi.StubTokenizer(case["bos"]))
+        assert got == case["ids"], case["prompt"]
+    t = serve.tokenize_with_sentinels(gi.TOKENIZE_PROMPTS[0], gi.StubTokenizer(), return_tensors="pt")
+    assert t.dtype == torch.long and t.tolist() == gold[0]["ids"]
