@@ -9,6 +9,7 @@
 // Pillow's libImaging/Resample.c (ImagingResampleHorizontal_8bpc / Vertical_8bpc) so results are bit-exact.
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "internal.h"
 
@@ -57,6 +58,10 @@ __device__ __forceinline__ void cp_async16(unsigned char* dst_smem, uintptr_t sr
                : "memory");
 }
 
+// V4 = candidate loop structure (MPL_PREPROCESS_V4=1), identical arithmetic: 128 pixel columns x 2 row groups per CTA,
+// so neither pass divides by a runtime value, and the vertical pass computes the channels of a pixel in one thread with
+// the row's coefficients loaded once per tap. Not the default until it has been validated and timed on a B200.
+template <bool V4>
 __global__ void __launch_bounds__(kThreads) preprocess_kernel(const mpl_preprocess_job* __restrict__ jobs) {
   extern __shared__ __align__(16) unsigned char smem[];  // [2][RB][stage_pitch] staged source rows | tmp
   __shared__ mpl_preprocess_job sj;
@@ -106,8 +111,24 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(const mpl_preproce
       const int nb = min(RB, nrows - r0);
       const unsigned char* buf = smem + stage * RB * sp;
       // 4 taps of an RGB pixel are 12 bytes = 3 aligned words funnel-shifted to the pixel boundary (1 word for a mask)
-      for (int idx = tid; idx < nb * new_w; idx += kThreads) {
-        const int i = idx / new_w, xx = idx - i * new_w;
+      const int n_items = V4 ? ((nb + 1) >> 1) * ((new_w + 127) & ~127) * 2 : nb * new_w;
+      for (int idx = tid; idx < n_items; idx += kThreads) {
+        int i, xx;
+        if (V4) {  // item = (row pair, 128-column block, row group, column): shifts and masks only
+          const int blk = idx >> 8;  // one 256-thread step = 128 columns x 2 rows
+          const int cb = (new_w + 127) >> 7;
+          int pair = 0, b = blk;
+          while (b >= cb) {  // at most RB / 2 - 1 = 1 iteration
+            b -= cb;
+            ++pair;
+          }
+          i = pair * 2 + ((idx >> 7) & 1);
+          xx = (b << 7) + (idx & 127);
+          if (i >= nb || xx >= new_w) continue;
+        } else {
+          i = idx / new_w;
+          xx = idx - i * new_w;
+        }
         const int xmin = __ldg(sj.bound_x + 2 * xx), n = __ldg(sj.bound_x + 2 * xx + 1);
         const int* k = sj.coef_x + xx;
         const int mis = static_cast<int>((src + static_cast<uintptr_t>(in_lo + r0 + i) * sj.src_stride) & 15);
@@ -164,6 +185,54 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(const mpl_preproce
   __syncthreads();
 
   const int rows = y1 - y0;
+  if (V4) {
+    const int col = tid & 127, rg = tid >> 7;
+    for (int r = rg; r < rows; r += 2) {
+      const int yo = y0 + r, ry = yo - sj.pad_top;
+      const bool in_y = ry >= 0 && ry < new_h;
+      const int ymin = in_y ? __ldg(sj.bound_y + 2 * ry) - in_lo : 0, n = in_y ? __ldg(sj.bound_y + 2 * ry + 1) : 0;
+      const int* k = sj.coef_y + static_cast<long long>(in_y ? ry : 0) * sj.ks_y;
+      for (int xo = col; xo < L; xo += 128) {
+        const int rx = xo - sj.pad_left;
+        float v[3] = {sj.pad_value[0], sj.pad_value[1], sj.pad_value[2]};
+        if (in_y && rx >= 0 && rx < new_w) {
+          const unsigned char* s = tmp + ymin * pitch + rx * C;
+          int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+          if (C == 3) {
+            for (int y = 0; y < n; ++y) {
+              const int kv = __ldg(k + y);
+              a0 += s[0] * kv;
+              a1 += s[1] * kv;
+              a2 += s[2] * kv;
+              s += pitch;
+            }
+          } else {
+            for (int y = 0; y < n; ++y) {
+              a0 += s[0] * __ldg(k + y);
+              s += pitch;
+            }
+          }
+          const int l0 = clip8(a0), l1 = clip8(a1), l2 = clip8(a2);
+          const bool lut = sj.lut != nullptr;
+          v[0] = lut ? s_lut[l0] : static_cast<float>(l0);
+          v[1] = lut ? s_lut[256 + l1] : static_cast<float>(l1);
+          v[2] = lut ? s_lut[512 + l2] : static_cast<float>(l2);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c >= C) break;
+          const long long o = (static_cast<long long>(c) * L + yo) * L + xo;
+          if (sj.out_dtype == MPL_DT_F32)
+            static_cast<float*>(sj.dst)[o] = v[c];
+          else if (sj.out_dtype == MPL_DT_BF16)
+            static_cast<__nv_bfloat16*>(sj.dst)[o] = __float2bfloat16_rn(v[c]);
+          else
+            static_cast<unsigned char*>(sj.dst)[o] = static_cast<unsigned char>(v[c]);
+        }
+      }
+    }
+    return;
+  }
   const int total = C * rows * L;
   for (int idx = tid; idx < total; idx += kThreads) {
     const int xo = idx % L, t = idx / L;
@@ -219,13 +288,20 @@ extern "C" int mpl_preprocess_images(const mpl_preprocess_job* jobs_host, const 
     const long long need = band_smem(j.H, j.W, j.new_h, j.new_w, j.C, rrb);
     smem = need > smem ? need : smem;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget) != cudaSuccess)
+  static int variant = -1;  // 0: default loops, 1: MPL_PREPROCESS_V4=1 (candidate, see preprocess_kernel)
+  if (variant < 0) {
+    if (cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget) !=
+            cudaSuccess)
       return MPL_ERR_CUDA;
-    attr_set = true;
+    const char* e = getenv("MPL_PREPROCESS_V4");
+    variant = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  preprocess_kernel<<<dim3(bands, n_jobs), kThreads, static_cast<size_t>(smem), static_cast<cudaStream_t>(stream)>>>(
-      jobs_dev);
+  const dim3 grid(bands, n_jobs);
+  if (variant == 1)
+    preprocess_kernel<true><<<grid, kThreads, static_cast<size_t>(smem), static_cast<cudaStream_t>(stream)>>>(jobs_dev);
+  else
+    preprocess_kernel<false><<<grid, kThreads, static_cast<size_t>(smem), static_cast<cudaStream_t>(stream)>>>(jobs_dev);
   return mpl::launch_status();
 }
