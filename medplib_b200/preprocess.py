@@ -97,7 +97,9 @@ class ImagePreprocessor:
 
     images: list of u8 RGB arrays / tensors [H, W, 3] (what ``cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2RGB)`` returns),
     any sizes.  region_masks: optional list (per image) of lists of u8 {0,1} [H, W] masks; returned as the 24x24 grids
-    the reference derives before its connected-component filter (LazySupervisedDataset.py:516-519).
+    the reference derives before its connected-component filter (LazySupervisedDataset.py:516-519).  encoder_masks:
+    optional list (per sample) of lists of u8 {0,1} [H, W] ICL exemplar masks (any sizes); returned as `mask_images`,
+    the {0,1} [m, 1, 336, 336] inputs of the MaskTokenEncoder (ICLLazySupervisedDataset.py:77-85).
     out_dtype: torch.float32 (the reference's contract, a-0) or torch.bfloat16 (what the model computes in; the same
     values rounded once, i.e. what ``.to(bfloat16)`` of the fp32 tensors gives).
     """
@@ -112,6 +114,7 @@ class ImagePreprocessor:
         clip = clip_level_table()
         self.clip_lut = clip.contiguous().to(self.device)
         self.clip_pad = [float(clip[c, lvl]) for c, lvl in enumerate(clip_pad_levels())]
+        self.enc_lut = (torch.arange(256) > 0).float().view(1, 256).contiguous().to(self.device)  # "resized mask > 0"
         self._tables = {}
 
     def _axis(self, n_in, n_out, tap_major):
@@ -152,7 +155,7 @@ class ImagePreprocessor:
         j.out_dtype, j.dst = _DT[dst.dtype], dst.data_ptr()
         return j, (new_h, new_w)
 
-    def plan(self, images, region_masks=None):
+    def plan(self, images, region_masks=None, encoder_masks=None):
         """Validate, stage the u8 inputs on the device (host inputs: one pinned ragged buffer, one copy; device inputs are
         used in place) and build the job list.  Returns a plan ``launch`` runs; ``__call__`` = ``launch(plan(...))``."""
         B = len(images)
@@ -165,7 +168,15 @@ class ImagePreprocessor:
             for m in ms:
                 if m.dtype != torch.uint8 or tuple(m.shape) != tuple(arrays[i].shape[:2]):
                     raise ValueError("region masks must be uint8 [H, W] of their image's size")
-        flat = [a for a in arrays] + [m for ms in masks for m in ms]
+        # ICL exemplar masks for the MaskTokenEncoder (ICLLazySupervisedDataset._preprocess_encoder_mask :77-85): the
+        # reference resizes mask * 255, so the {0,1} masks are scaled while they are staged
+        enc = [[torch.as_tensor(m) for m in ms] for ms in (encoder_masks or [])]
+        for ms in enc:
+            for m in ms:
+                if m.dtype != torch.uint8 or m.dim() != 2:
+                    raise ValueError("encoder masks must be uint8 {0,1} [H, W]")
+        enc_flat = [(m != 0).to(torch.uint8) * 255 for ms in enc for m in ms]
+        flat = [a for a in arrays] + [m for ms in masks for m in ms] + enc_flat
         keep, ptrs = [], []
         if flat and all(f.device.type == "cuda" for f in flat):
             for f in flat:
@@ -200,6 +211,11 @@ class ImagePreprocessor:
             for _ in ms:
                 jobs.append(self._job(ptrs[B + k], H, W, 1, self.clip_size, None, (0.0, 0.0, 0.0), out_mask[k])[0])
                 k += 1
+        n_enc = len(enc_flat)
+        out_enc = torch.empty(n_enc, 1, self.clip_size, self.clip_size, dtype=self.out_dtype, device=self.device)
+        for t, m in enumerate(enc_flat):
+            jobs.append(self._job(ptrs[B + n_masks + t], int(m.shape[0]), int(m.shape[1]), 1, self.clip_size,
+                                  self.enc_lut, (0.0, 0.0, 0.0), out_enc[t])[0])
         n = len(jobs)
         jobs_host = jobs_dev = None
         if n:
@@ -214,6 +230,12 @@ class ImagePreprocessor:
             for ms in masks:
                 out["region_masks"].append([grids[k + t] for t in range(len(ms))])
                 k += len(ms)
+        if encoder_masks is not None:  # the collator's `mask_images`: one [m, 1, S, S] tensor per sample that has masks
+            out["mask_images"], t = [], 0
+            for ms in enc:
+                if ms:
+                    out["mask_images"].append(out_enc[t:t + len(ms)])
+                t += len(ms)
         src_bytes = sum(int(a.shape[0]) * int(a.shape[1]) * 3 * 2 for a in arrays) + sum(m.numel() for ms in masks for m in ms)
         out_bytes = out_sam.numel() * out_sam.element_size() + out_clip.numel() * out_clip.element_size() + out_mask.numel()
         return {"n": n, "jobs_host": jobs_host, "jobs_dev": jobs_dev, "keep": keep, "out": out,
@@ -227,5 +249,5 @@ class ImagePreprocessor:
                                                       plan["n"], ctypes.c_void_p(stream)), "mpl_preprocess_images")
         return plan["out"]
 
-    def __call__(self, images, region_masks=None):
-        return self.launch(self.plan(images, region_masks))
+    def __call__(self, images, region_masks=None, encoder_masks=None):
+        return self.launch(self.plan(images, region_masks, encoder_masks))

@@ -137,3 +137,10 @@ def region_mask(mask_u8, clip_size=336, patch=14):
     r = resize_longest_side(mask_u8, clip_size)
     padded = centre_pad(r[None], clip_size, np.zeros(1, np.uint8))[0]
     return np.ascontiguousarray(padded[::patch, ::patch])
+
+
+def encoder_mask(mask_u8, clip_size=336):
+    """-> fp32 {0,1} [1, S, S] : ICLLazySupervisedDataset._preprocess_encoder_mask (datasets/ICLLazySupervisedDataset.py
+    :77-85): the {0,1} mask times 255, the same resize and zero pad, then ``> 0``."""
+    r = resize_longest_side((mask_u8 != 0).astype(np.uint8) * 255, clip_size)
+    return (centre_pad(r[None], clip_size, np.zeros(1, np.uint8)) > 0).astype(np.float32)

@@ -79,6 +79,17 @@ for i, (h, w, ls, lc) in enumerate(gi.PREPROCESS_SIZES):
         case["tensors"] = tensors  # small enough to keep whole, for debugging a digest mismatch
     out["cases"].append(case)
     print(i, (h, w), (ls, lc), tuple(r.shape), tuple(rm_grid.shape))
+# ---- ICL exemplar masks for the MaskTokenEncoder: ICLLazySupervisedDataset._preprocess_encoder_mask (:77-85)
+from datasets.ICLLazySupervisedDataset import ICLLazySupervisedDataset  # noqa: E402
+
+out["encoder_masks"] = []
+for i, (h, w, ls, lc) in enumerate(gi.PREPROCESS_SIZES):
+    icl = object.__new__(ICLLazySupervisedDataset)
+    icl.transform_clip, icl.clip_img_size = ResizeLongestSide(lc), lc
+    em = icl._preprocess_encoder_mask(gi.preprocess_mask(i, h, w))
+    assert em.dtype == torch.float32 and tuple(em.shape) == (1, lc, lc)
+    out["encoder_masks"].append({"sha256": digest(em), "ones": int(em.sum())})
+
 # ---- sentinel tokenisation: the reference's tokenizer_image_token on a deterministic stub tokenizer
 from datasets.LazySupervisedDataset import tokenizer_image_token  # noqa: E402
 

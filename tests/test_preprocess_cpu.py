@@ -138,3 +138,80 @@ def test_oracle_equals_pil_on_random_shapes():
         assert np.array_equal(op.pil_resize_bilinear(img, nh, nw), ref), (h, w, nh, nw, rgb)
 
     check()
+
+
+def test_icl_encoder_masks_match_the_reference():
+    """ICLLazySupervisedDataset._preprocess_encoder_mask digests (golden) vs the oracle."""
+    assert len(GOLD["encoder_masks"]) == len(gi.PREPROCESS_SIZES)
+    for i, (h, w, ls, lc) in enumerate(gi.PREPROCESS_SIZES):
+        em = op.encoder_mask(gi.preprocess_mask(i, h, w), lc)
+        assert em.shape == (1, lc, lc) and em.dtype == np.float32
+        assert int(em.sum()) == GOLD["encoder_masks"][i]["ones"]
+        assert digest(em) == GOLD["encoder_masks"][i]["sha256"], f"case {i}"
+
+
+def _emulate_job(j):
+    """What csrc/preprocess.cu computes for one mpl_preprocess_job, read straight from the struct's (host) pointers."""
+    import ctypes
+
+    def arr(ptr, n, ct, dt):
+        return np.frombuffer((ct * n).from_address(ptr), dtype=dt).copy()
+    H, W, C, nh, nw, L = j.H, j.W, j.C, j.new_h, j.new_w, j.out_size
+    assert j.src % 16 == 0 and j.ks_x % 4 == 0 and j.src_stride == W * C
+    src = arr(j.src, H * W * C, ctypes.c_ubyte, np.uint8).reshape(H, W, C).astype(np.int64)
+    bx = arr(j.bound_x, nw * 2, ctypes.c_int, np.int32).reshape(nw, 2)
+    cx = arr(j.coef_x, j.ks_x * nw, ctypes.c_int, np.int32).reshape(j.ks_x, nw).astype(np.int64)
+    by = arr(j.bound_y, nh * 2, ctypes.c_int, np.int32).reshape(nh, 2)
+    cy = arr(j.coef_y, nh * j.ks_y, ctypes.c_int, np.int32).reshape(nh, j.ks_y).astype(np.int64)
+    tmp = np.zeros((H, nw, C), np.int64)
+    for xx in range(nw):
+        x0, n = bx[xx]
+        acc = (1 << 21) + (src[:, x0:x0 + n, :] * cx[:n, xx][None, :, None]).sum(1)
+        tmp[:, xx] = np.clip(acc >> 22, 0, 255)
+    lv = np.zeros((nh, nw, C), np.int64)
+    for yy in range(nh):
+        y0, n = by[yy]
+        acc = (1 << 21) + (tmp[y0:y0 + n] * cy[yy, :n][:, None, None]).sum(0)
+        lv[yy] = np.clip(acc >> 22, 0, 255)
+    if j.lut:
+        lut = arr(j.lut, C * 256, ctypes.c_float, np.float32).reshape(C, 256)
+        val = np.stack([lut[c][lv[..., c]] for c in range(C)])
+    else:
+        val = lv.transpose(2, 0, 1).astype(np.float32)
+    out = np.empty((C, L, L), np.float32)
+    out[:] = np.array(list(j.pad_value)[:C], np.float32).reshape(C, 1, 1)
+    out[:, j.pad_top:j.pad_top + nh, j.pad_left:j.pad_left + nw] = val
+    return out
+
+
+def test_host_side_job_structs_describe_the_oracle_result(monkeypatch):
+    """ImagePreprocessor.plan() on CPU tensors (pinning stubbed out): the job array it hands to mpl_preprocess_images —
+    source offsets in the ragged staging buffer, sizes, pads, PIL tables in the kernel's layouts, value tables — evaluated
+    by a numpy reading of the kernel's contract, equals the oracle for images, region masks and ICL encoder masks."""
+    from medplib_b200 import preprocess as pp
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "pin_memory"}))
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    pre = object.__new__(pp.ImagePreprocessor)
+    pre.device = torch.device("cpu")
+    pre.sam_size, pre.clip_size, pre.patch, pre.out_dtype = 64, 84, 14, torch.float32
+    pre.sam_lut, pre.clip_lut = pp.sam_level_table().contiguous(), pp.clip_level_table().contiguous()
+    pre.clip_pad = [float(pre.clip_lut[c, lvl]) for c, lvl in enumerate(pp.clip_pad_levels())]
+    pre.enc_lut = (torch.arange(256) > 0).float().view(1, 256).contiguous()
+    pre._tables = {}
+    imgs = [gi.preprocess_image(i, h, w) for i, (h, w) in enumerate([(50, 40), (211, 97), (64, 84)])]
+    rms = [[gi.preprocess_mask(i, *im.shape[:2])] for i, im in enumerate(imgs)]
+    ems = [[gi.preprocess_mask(7, 33, 90)], [], [gi.preprocess_mask(8, 120, 45), gi.preprocess_mask(9, 84, 84)]]
+    plan = pre.plan(imgs, region_masks=rms, encoder_masks=ems)
+    jobs = list(plan["jobs_host"])
+    assert plan["n"] == len(jobs) == 2 * 3 + 3 + 3
+    for b, im in enumerate(imgs):
+        assert np.array_equal(_emulate_job(jobs[2 * b]), op.image_sam(im, 64)[0])
+        assert np.array_equal(_emulate_job(jobs[2 * b + 1]), op.image_clip(im, 84))
+        want = op.centre_pad(op.resize_longest_side(rms[b][0], 84)[None], 84, np.zeros(1, np.uint8))
+        assert np.array_equal(_emulate_job(jobs[6 + b]), want.astype(np.float32))
+    flat = [m for ms in ems for m in ms]
+    for t, m in enumerate(flat):
+        assert np.array_equal(_emulate_job(jobs[9 + t]), op.encoder_mask(m, 84))
+    assert [tuple(x.shape) for x in plan["out"]["mask_images"]] == [(1, 1, 84, 84), (2, 1, 84, 84)]
+    assert plan["out"]["resize_list"] == [op.get_preprocess_shape(*im.shape[:2], 64) for im in imgs]

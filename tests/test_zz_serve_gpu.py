@@ -47,3 +47,26 @@ def test_stream_equals_evaluate(dev):
     far = ((want - thr).abs() > 2e-2 * want.abs().max()).cpu()
     assert (recs[-1]["height"], recs[-1]["width"]) == ("70", "90")
     assert torch.equal(got[far], (want.cpu() > thr)[far])
+
+
+def test_icl_encoder_masks_match_reference_digests(dev):
+    """ImagePreprocessor(encoder_masks=...) -> `mask_images` vs the reference's _preprocess_encoder_mask (golden digests).
+    Uses the single-channel + value-table kernel path, which the validated tests do not exercise."""
+    import hashlib
+    import sys
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import inputs as gi
+    from oracle import preprocess as op
+    from medplib_b200.preprocess import ImagePreprocessor
+    gold = torch.load(os.path.join(here, "golden", "preprocess.pt"), weights_only=False)["encoder_masks"]
+    idxs = [i for i, s in enumerate(gi.PREPROCESS_SIZES) if s[3] == 336]
+    masks = [gi.preprocess_mask(i, *gi.PREPROCESS_SIZES[i][:2]) for i in idxs]
+    img = gi.preprocess_image(0, 64, 64)
+    out = ImagePreprocessor(dev)([img, img], encoder_masks=[masks[:3], masks[3:]])
+    got = torch.cat(out["mask_images"], 0).cpu().numpy()
+    assert out["mask_images"][0].shape == (3, 1, 336, 336)
+    for t, i in enumerate(idxs):
+        assert np.array_equal(got[t], op.encoder_mask(masks[t])), f"case {i}"
+        assert hashlib.sha256(np.ascontiguousarray(got[t]).tobytes()).hexdigest() == gold[i]["sha256"]
