@@ -7,11 +7,21 @@
 // per-level fp32 table + the centre pad straight to the [C, L, L] output.  HBM traffic is the source once per job (bands overlap by the filter support,
 // absorbed by L2) and the output once; there is no intermediate image in HBM.  Integer arithmetic follows
 // Pillow's libImaging/Resample.c (ImagingResampleHorizontal_8bpc / Vertical_8bpc) so results are bit-exact.
-#include <cuda_bf16.h>
+//
+// MPL_CPU_EMULATION: tests/dev/preprocess_emu.cpp compiles THIS file with g++ (one std::thread per CUDA thread, a
+// std::barrier for __syncthreads, memcpy for cp.async) so the index arithmetic, shared-memory layout, staging and
+// clamping of both loop structures are checked against the oracle without a GPU. Test infrastructure only; the
+// preprocessor switches below do not change the device code (the SASS of the nvcc build is unaffected).
 #include <stdint.h>
 #include <stdlib.h>
+#ifdef MPL_CPU_EMULATION
+#include "cuda_emu.h"  // tests/dev
+#include "../../include/medplib_b200.h"
+#else
+#include <cuda_bf16.h>
 
 #include "internal.h"
+#endif
 
 namespace {
 
@@ -53,17 +63,34 @@ __device__ __forceinline__ int clip8(int acc) {
 }
 
 __device__ __forceinline__ void cp_async16(unsigned char* dst_smem, uintptr_t src_global) {
+#ifdef MPL_CPU_EMULATION
+  mpl_emu::copy16(dst_smem, src_global);
+}
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(dst_smem))),
                "l"(src_global)
                : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+#endif
 
 // V4 = candidate loop structure (MPL_PREPROCESS_V4=1), identical arithmetic: 128 pixel columns x 2 row groups per CTA,
 // so neither pass divides by a runtime value, and the vertical pass computes the channels of a pixel in one thread with
 // the row's coefficients loaded once per tap. Not the default until it has been validated and timed on a B200.
 template <bool V4>
 __global__ void __launch_bounds__(kThreads) preprocess_kernel(const mpl_preprocess_job* __restrict__ jobs) {
+#ifdef MPL_CPU_EMULATION
+  unsigned char* smem = mpl_emu::dynamic_smem();
+#else
   extern __shared__ __align__(16) unsigned char smem[];  // [2][RB][stage_pitch] staged source rows | tmp
+#endif
   __shared__ mpl_preprocess_job sj;
   __shared__ float s_lut[3 * 256];
   const int tid = threadIdx.x;
@@ -96,16 +123,16 @@ __global__ void __launch_bounds__(kThreads) preprocess_kernel(const mpl_preproce
         g = g < last_chunk ? g : last_chunk;
         cp_async16(buf + i * sp + 16 * v, g);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      cp_async_commit();
     };
     issue(0, 0);
     int stage = 0;
     for (int r0 = 0; r0 < nrows; r0 += RB, stage ^= 1) {
       if (r0 + RB < nrows) {
         issue(stage ^ 1, r0 + RB);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        cp_async_wait<1>();
       } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        cp_async_wait<0>();
       }
       __syncthreads();
       const int nb = min(RB, nrows - r0);
@@ -265,10 +292,9 @@ extern "C" int mpl_preprocess_band_rows(int in_size, int out_size, int R) {
   return band_rows_bound(in_size, out_size, R);
 }
 
-extern "C" int mpl_preprocess_images(const mpl_preprocess_job* jobs_host, const mpl_preprocess_job* jobs_dev,
-                                     int n_jobs, void* stream) {
-  if (n_jobs <= 0) return MPL_OK;
-  if (jobs_host == nullptr || jobs_dev == nullptr || n_jobs > 65535) return MPL_ERR_ARG;
+// Validates the jobs and sizes the launch: grid.x = bands (the largest band count of any job), dynamic shared memory =
+// the largest per-job need. Shared by the CUDA entry below and the CPU emulation harness.
+static int plan_launch(const mpl_preprocess_job* jobs_host, int n_jobs, int* bands_out, long long* smem_out) {
   int bands = 0;
   long long smem = 0;
   for (int i = 0; i < n_jobs; ++i) {
@@ -288,6 +314,43 @@ extern "C" int mpl_preprocess_images(const mpl_preprocess_job* jobs_host, const 
     const long long need = band_smem(j.H, j.W, j.new_h, j.new_w, j.C, rrb);
     smem = need > smem ? need : smem;
   }
+  *bands_out = bands;
+  *smem_out = smem;
+  return MPL_OK;
+}
+
+#ifdef MPL_CPU_EMULATION
+// variant 0 = default loops, 1 = the MPL_PREPROCESS_V4 candidate; blocks run one after the other, 256 std::threads each
+extern "C" int mpl_emu_preprocess_images(const mpl_preprocess_job* jobs, int n_jobs, int variant) {
+  if (n_jobs <= 0) return MPL_OK;
+  int bands = 0;
+  long long smem = 0;
+  const int rc = plan_launch(jobs, n_jobs, &bands, &smem);
+  if (rc != MPL_OK) return rc;
+  if (smem > kSmemBudget) return MPL_ERR_UNSUPPORTED;
+  mpl_emu::allowed_ranges().clear();
+  for (int i = 0; i < n_jobs; ++i) {  // what the ABI lets the kernel read: the image, rounded up to 16 bytes
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(jobs[i].src);
+    const uintptr_t hi = lo + static_cast<uintptr_t>(jobs[i].H - 1) * jobs[i].src_stride + jobs[i].W * jobs[i].C;
+    mpl_emu::allowed_ranges().push_back({lo, (hi + 15) & ~uintptr_t(15)});
+  }
+  mpl_emu::run_grid(bands, n_jobs, kThreads, static_cast<size_t>(smem), [&]() {
+    if (variant == 1)
+      preprocess_kernel<true>(jobs);
+    else
+      preprocess_kernel<false>(jobs);
+  });
+  return mpl_emu::violations() == 0 ? MPL_OK : MPL_ERR_CUDA;
+}
+#else
+extern "C" int mpl_preprocess_images(const mpl_preprocess_job* jobs_host, const mpl_preprocess_job* jobs_dev,
+                                     int n_jobs, void* stream) {
+  if (n_jobs <= 0) return MPL_OK;
+  if (jobs_host == nullptr || jobs_dev == nullptr || n_jobs > 65535) return MPL_ERR_ARG;
+  int bands = 0;
+  long long smem = 0;
+  const int rc = plan_launch(jobs_host, n_jobs, &bands, &smem);
+  if (rc != MPL_OK) return rc;
   static int variant = -1;  // 0: default loops, 1: MPL_PREPROCESS_V4=1 (candidate, see preprocess_kernel)
   if (variant < 0) {
     if (cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget) !=
@@ -305,3 +368,4 @@ extern "C" int mpl_preprocess_images(const mpl_preprocess_job* jobs_host, const 
     preprocess_kernel<false><<<grid, kThreads, static_cast<size_t>(smem), static_cast<cudaStream_t>(stream)>>>(jobs_dev);
   return mpl::launch_status();
 }
+#endif

@@ -215,3 +215,77 @@ def test_host_side_job_structs_describe_the_oracle_result(monkeypatch):
         assert np.array_equal(_emulate_job(jobs[9 + t]), op.encoder_mask(m, 84))
     assert [tuple(x.shape) for x in plan["out"]["mask_images"]] == [(1, 1, 84, 84), (2, 1, 84, 84)]
     assert plan["out"]["resize_list"] == [op.get_preprocess_shape(*im.shape[:2], 64) for im in imgs]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The kernel source itself, executed on the CPU (tests/dev/cuda_emu.h: one std::thread per CUDA thread, std::barrier for
+# __syncthreads, checked memcpy for cp.async): index arithmetic, shared-memory layout, staging, clamping and both loop
+# structures against the oracle — without a GPU.  The B200 run (tests/test_preprocess_gpu.py) remains the parity test.
+def _cpu_preprocessor(monkeypatch, sam, clip, out_dtype=torch.float32):
+    from medplib_b200 import preprocess as pp
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "pin_memory"}))
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    pre = object.__new__(pp.ImagePreprocessor)
+    pre.device = torch.device("cpu")
+    pre.sam_size, pre.clip_size, pre.patch, pre.out_dtype = sam, clip, 14, out_dtype
+    pre.sam_lut, pre.clip_lut = pp.sam_level_table().contiguous(), pp.clip_level_table().contiguous()
+    pre.clip_pad = [float(pre.clip_lut[c, lvl]) for c, lvl in enumerate(pp.clip_pad_levels())]
+    pre.enc_lut = (torch.arange(256) > 0).float().view(1, 256).contiguous()
+    pre._tables = {}
+    return pre
+
+
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    import ctypes
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    root = os.path.dirname(HERE)
+    out = str(tmp_path_factory.mktemp("emu") / "preprocess_emu.so")
+    cmd = ["g++", "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", "-DMPL_CPU_EMULATION", "-I",
+           os.path.join(root, "tests", "dev"), "-x", "c++", os.path.join(root, "tests", "dev", "preprocess_emu.cpp"), "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = ctypes.CDLL(out)
+    lib.mpl_emu_preprocess_images.restype = ctypes.c_int
+    return lib
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["default_loops", "v4_candidate"])
+def test_kernel_source_on_cpu_matches_the_oracle(emu_lib, monkeypatch, variant):
+    pre = _cpu_preprocessor(monkeypatch, 64, 84)
+    sizes = [(50, 40), (211, 97), (64, 84), (31, 200), (300, 9), (1100, 130)]
+    imgs = [gi.preprocess_image(i, h, w) for i, (h, w) in enumerate(sizes)]
+    rms = [[gi.preprocess_mask(i, *im.shape[:2])] for i, im in enumerate(imgs)]
+    ems = [[gi.preprocess_mask(7, 33, 90)], [], [gi.preprocess_mask(8, 120, 45)], [], [], []]
+    plan = pre.plan(imgs, region_masks=rms, encoder_masks=ems)
+    for t in plan["out"].values():
+        if torch.is_tensor(t):
+            t.fill_(-7)
+    assert emu_lib.mpl_emu_preprocess_images(plan["jobs_host"], plan["n"], variant) == 0, \
+        "the kernel read outside the ranges the C ABI allows (or the jobs were rejected)"
+    out = plan["out"]
+    for b, im in enumerate(imgs):
+        assert np.array_equal(out["images"][b].numpy(), op.image_sam(im, 64)[0]), f"images[{b}] {im.shape}"
+        assert np.array_equal(out["images_clip"][b].numpy(), op.image_clip(im, 84)), f"images_clip[{b}] {im.shape}"
+        want = op.centre_pad(op.resize_longest_side(rms[b][0], 84)[None], 84, np.zeros(1, np.uint8))
+        assert np.array_equal(out["region_masks_u8"][b].numpy(), want), f"region mask {b}"
+    got = torch.cat(out["mask_images"], 0).numpy()
+    for t, m in enumerate([m for ms in ems for m in ms]):
+        assert np.array_equal(got[t], op.encoder_mask(m, 84)), f"encoder mask {t}"
+
+
+def test_kernel_source_on_cpu_full_size_and_bf16(emu_lib, monkeypatch):
+    """The real targets (256 / 336), a 4x downscale with the 4-row stage, bf16 output: both loop structures."""
+    pre = _cpu_preprocessor(monkeypatch, 256, 336, torch.bfloat16)
+    im = gi.preprocess_image(3, 700, 1024)
+    want_s = torch.from_numpy(op.image_sam(im)[0]).to(torch.bfloat16)
+    want_c = torch.from_numpy(op.image_clip(im)).to(torch.bfloat16)
+    for variant in (0, 1):
+        plan = pre.plan([im])
+        assert emu_lib.mpl_emu_preprocess_images(plan["jobs_host"], plan["n"], variant) == 0
+        assert torch.equal(plan["out"]["images"][0], want_s), variant
+        assert torch.equal(plan["out"]["images_clip"][0], want_c), variant
