@@ -359,7 +359,10 @@ def run_preprocess(args, rank, world, dev):
                 "h2d_bytes_per_step": PRE_B * PRE_HW[0] * PRE_HW[1] * 3 + 2 * PRE_B * 120, "d2h_bytes_per_step": 0},
         "gpu_launches": int(launches), "clocks": ck,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                     "traffic": None, "kernel": "preprocess_kernel (one launch per batch)",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture of this workload
+                     # (first kernel version; the source is read once, the 17 MB of outputs were still in L2 at kernel end)
+                     "traffic": 25.23e6, "traffic_source": "profiles/r01_ncu_preprocess.md",
+                     "kernel": "preprocess_kernel (one launch per batch)",
                      "algorithmic_bytes_per_launch": alg, "kernel_ms_per_launch": ms_k / args.steps,
                      "peak_source": pk["src"] + " HBM copy bandwidth",
                      "note": "algorithmic bytes = each source image once per target (2x) + every output once"},
