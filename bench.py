@@ -660,7 +660,7 @@ def run_train(args, rank, world, dev):
 def cpu_reference(sample_steps=1):
     """The reference's path on the host cores: oracle port (fp32, all threads) on a bounded sample — ONE decoder layer,
     ONE CLIP layer and ONE SAM block at full 7B width on the benchmark's shapes — scaled by the layer counts."""
-    from oracle import clip, llama, sam, weights, arch, heads
+    from oracle import clip, llama, sam, weights, heads
     torch.set_num_threads(os.cpu_count() or 1)
     d = DIMS
     t0 = time.time()
