@@ -299,7 +299,9 @@ typedef struct {
   const void* decode_plan; /* optional, from mpl_llama_decode_plan_build: T == 1 steps with B <= 8 and top-1 routing run
                               as ONE persistent cooperative kernel (llama_decode.cu) instead of ~7 launches per layer */
   const float* const* moe_noise; /* NULL or host array [n_layers] of f32 [B*T,E] (see mpl_moe_route) */
-  float* gate_logits;            /* NULL or f32 [n_layers, B*T, E] out (what a forward hook on wg observes) */
+  float* gate_logits;            /* NULL or f32 [n_layers, B*T * Emax] out: layer l owns block l (indexed by TRANSFORMER layer,
+                                    dense layers left untouched), rows inside it packed [B*T, E_l] (what a forward hook on wg
+                                    observes); exp_counts likewise [n_layers, Emax] */
   float* l_aux;                  /* NULL or f32 [n_layers] out */
   int* exp_counts;               /* NULL or int [n_layers, E] out */
   void* workspace;

@@ -24,6 +24,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -33,7 +34,7 @@
 namespace mpl {
 
 constexpr int DK_CONSUMERS = 8;
-constexpr int DK_THREADS = (DK_CONSUMERS + 1) * 32;
+constexpr int DK_THREADS = (DK_CONSUMERS + 2) * 32;  // 8 consumer warps + TMA producer warp + L2 prefetch warp
 constexpr int DK_STAGES = 6;
 constexpr int DK_STAGE_BYTES = 16384;  // [8 k-blocks][16 rows][128 B swizzled]  (dual: 2 x [8][8 rows][128 B])
 constexpr int DK_KC = 512;
@@ -80,13 +81,14 @@ struct DecParams {
   float* l_aux;        // [L] or NULL
   int* exp_counts;     // [L, Emax] or NULL
   int B, D, H, F, L, Tmax, pos, nsplit, Emax, timing_layer;
+  int kla, ela, spec;  // L2 prefetch look-ahead (16 KB chunks per CTA): known stream, expert stream; speculate all experts
   int cap[DK_MAXE + 1];  // capacity for a layer with E experts (index E)
   float eps, scale;
 };
 
 // Optional per-phase timestamps (dev tool): consumer thread 0 of every CTA records %globaltimer at the phase boundaries
 // of layer `timing_layer`.
-constexpr int DK_TSLOTS = 16;
+constexpr int DK_TSLOTS = 32;
 __device__ unsigned long long g_dk_times[160 * DK_TSLOTS];
 static int g_timing_layer = -1;
 __device__ __forceinline__ unsigned long long globaltimer() {
@@ -129,6 +131,11 @@ struct RouteSmem {
   int moe;
   float logits[DK_MAXB][DK_MAXE];
   float gates[DK_MAXB][DK_MAXE];
+  // L2 prefetcher coordination (monotonic counters, written by the producer / consumer thread 0, polled by the prefetcher)
+  unsigned int pf_kn;        // chunks of the known stream (q,k,v,o of all layers) the producer has issued so far
+  unsigned int pf_ex;        // (layer << 16) | chunks of that layer's expert stream issued so far
+  unsigned int pf_route;     // 1 + last layer whose expert choice is published
+  unsigned int pf_amask[4];  // expert masks of the last layers, slot l & 3
 };
 
 __device__ __forceinline__ void dk_hmma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -168,7 +175,12 @@ __device__ __forceinline__ void grid_sync(unsigned int* ctr, unsigned int& targe
 }
 
 // ------------------------------------------------------------------------------------------------ producer side
-__device__ __forceinline__ void produce_tile(Ring& r, const CUtensorMap* m0, const CUtensorMap* m1, int n0, int chunks) {
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void produce_tile(Ring& r, const CUtensorMap* m0, const CUtensorMap* m1, int n0, int chunks,
+                                             volatile unsigned int* progress, unsigned int& count) {
   for (int c = 0; c < chunks; ++c) {
     mbar_wait(&r.empty[r.stage], r.phase ^ 1);
     uint8_t* dst = r.base + r.stage * DK_STAGE_BYTES;
@@ -176,6 +188,7 @@ __device__ __forceinline__ void produce_tile(Ring& r, const CUtensorMap* m0, con
     tma_load_3d(dst, m0, &r.full[r.stage], 0, n0, c * (DK_KC / 64));
     if (m1 != nullptr) tma_load_3d(dst + DK_STAGE_BYTES / 2, m1, &r.full[r.stage], 0, n0, c * (DK_KC / 64));
     r.advance();
+    *progress = ++count;
   }
 }
 
@@ -253,7 +266,8 @@ __device__ __forceinline__ void dk_bulk_g2s(void* smem_dst, const void* gsrc, ui
                : "memory");
 }
 __device__ __noinline__ void stage_rows(ActStage st, const __nv_bfloat16* __restrict__ src, const uint8_t* s_ln,
-                                        uint64_t* ln_bar, uint32_t ln_phase, int B, int D, float eps, float* s_part) {
+                                        uint64_t* ln_bar, uint32_t ln_phase, int B, int D, float eps, float* s_part,
+                                        unsigned long long* ts = nullptr) {
   constexpr int NV = 2;  // vectors per thread and row: D <= 4096
   constexpr int RG = 4;  // rows per register group (spills are ruinous here: shared memory leaves almost no L1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,6 +275,7 @@ __device__ __noinline__ void stage_rows(ActStage st, const __nv_bfloat16* __rest
   const int pitch = st.pitch;
   const uint4 zero = make_uint4(0, 0, 0, 0);
   if (s_ln != nullptr) mbar_wait(ln_bar, ln_phase);
+  if (ts != nullptr) ts[0] = globaltimer();
 #pragma unroll 1
   for (int m0 = 0; m0 < B; m0 += RG) {
     uint4 v[RG][NV];
@@ -295,7 +310,9 @@ __device__ __noinline__ void stage_rows(ActStage st, const __nv_bfloat16* __rest
 #pragma unroll
         for (int r = 0; r < RG; ++r) s_part[r * DK_CONSUMERS + warp] = ss[r];
       }
+      if (ts != nullptr && m0 == 0) ts[1] = globaltimer();
       consumer_sync();
+      if (ts != nullptr && m0 == 0) ts[2] = globaltimer();
 #pragma unroll
       for (int r = 0; r < RG; ++r) {
         float tot = 0.0f;
@@ -326,8 +343,10 @@ __device__ __noinline__ void stage_rows(ActStage st, const __nv_bfloat16* __rest
         const int k = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
         if (m0 + r < B && k < D) *reinterpret_cast<uint4*>(s_a + (m0 + r) * pitch + k * 2) = v[r][j];
       }
+    if (ts != nullptr && m0 == 0) ts[3] = globaltimer();
     consumer_sync();  // rows complete for every reader; s_part reusable
   }
+  if (ts != nullptr) ts[4] = globaltimer();
 }
 
 // L2 prefetch of small per-layer tensors (router weights, norm weights) well before they are needed.
@@ -623,6 +642,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
     mbar_init(wg_bar, 1);
     mbar_init(lnin_bar, 1);
     fence_mbar_init();
+    rt->pf_kn = rt->pf_ex = rt->pf_route = 0;
+    rt->pf_amask[0] = rt->pf_amask[1] = rt->pf_amask[2] = rt->pf_amask[3] = 1u;
   }
   __syncthreads();
   Ring ring{smem, full_bar, empty_bar, 0, 0};
@@ -636,26 +657,121 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
     // ============================================================ producer: the whole step's weight schedule
     if (lane != 0) return;
     uint32_t route_phase = 0;
+    unsigned int kn = 0;
+    volatile unsigned int* pf_kn = &rt->pf_kn;
+    volatile unsigned int* pf_ex = &rt->pf_ex;
     for (int l = 0; l < p.L; ++l) {
       const DecLayerDev* L = p.layers + l;
       for (int tile = blockIdx.x; tile < 3 * tiles_d; tile += G) {
         const int which = tile / tiles_d;
         const CUtensorMap* tm = which == 0 ? &L->wq : (which == 1 ? &L->wk : &L->wv);
-        produce_tile(ring, tm, nullptr, (tile % tiles_d) * 16, chunks_d);
+        produce_tile(ring, tm, nullptr, (tile % tiles_d) * 16, chunks_d, pf_kn, kn);
       }
-      for (int tile = blockIdx.x; tile < tiles_d; tile += G) produce_tile(ring, &L->wo, nullptr, tile * 16, chunks_d);
+      for (int tile = blockIdx.x; tile < tiles_d; tile += G)
+        produce_tile(ring, &L->wo, nullptr, tile * 16, chunks_d, pf_kn, kn);
       mbar_wait(route_bar, route_phase);  // expert choice of this layer
       route_phase ^= 1;
       const unsigned int amask = rt->amask;
       const int nact = __popc(amask);
+      unsigned int ex = static_cast<unsigned int>(l) << 16;
+      *pf_ex = ex;
       for (int tile = blockIdx.x; tile < nact * tiles_f; tile += G) {
         const int e = __fns(amask, 0, tile / tiles_f + 1);
-        produce_tile(ring, &L->wgate[e], &L->wup[e], (tile % tiles_f) * 8, chunks_d);
+        produce_tile(ring, &L->wgate[e], &L->wup[e], (tile % tiles_f) * 8, chunks_d, pf_ex, ex);
       }
       for (int tile = blockIdx.x; tile < nact * tiles_d; tile += G) {
         const int e = __fns(amask, 0, tile / tiles_d + 1);
-        produce_tile(ring, &L->wdown[e], nullptr, (tile % tiles_d) * 16, chunks_f);
+        produce_tile(ring, &L->wdown[e], nullptr, (tile % tiles_d) * 16, chunks_f, pf_ex, ex);
       }
+    }
+    return;
+  }
+  if (warp == DK_CONSUMERS + 1) {
+    // ============================================================ L2 prefetcher
+    // Walks the same per-CTA tile schedule as the producer, a bounded number of 16 KB chunks AHEAD of it, with
+    // cp.async.bulk.prefetch.tensor (HBM -> L2, fire and forget): while the consumers sit in a grid barrier, the
+    // attention phase, activation staging or the router -- when the 6-stage ring is full and the producer is blocked --
+    // HBM keeps streaming into L2, and the ring refills from L2 afterwards. Two independent cursors:
+    //   known stream   q,k,v,o tiles of ALL layers (never depends on data): up to p.kla chunks ahead, across layers;
+    //   expert stream  gate/up/down tiles of one layer: needs that layer's expert choice (or, with p.spec, assumes every
+    //                  expert is hit -- B >= 4 -- and starts early): up to p.ela chunks ahead.
+    // Every wait is a poll of a monotonic shared-memory counter that the producer / consumers advance no matter what
+    // this thread does, a cursor that has fallen behind jumps forward, so the thread cannot block anyone and always exits.
+    if (lane != 0 || (p.kla <= 0 && p.ela <= 0)) return;
+    const int bid = blockIdx.x;
+    auto cnt = [&](int total) { return total > bid ? (total - bid + G - 1) / G : 0; };
+    const int n1 = cnt(3 * tiles_d), n3 = cnt(tiles_d);
+    const unsigned int per_layer = static_cast<unsigned int>((n1 + n3) * chunks_d);
+    const unsigned int total_known = p.kla > 0 ? per_layer * static_cast<unsigned int>(p.L) : 0u;
+    const unsigned int kla = static_cast<unsigned int>(p.kla), ela = static_cast<unsigned int>(p.ela);
+    volatile RouteSmem* vr = rt;
+    unsigned int kn_pf = 0, ex_pf = 0;
+    int le = p.ela > 0 ? 0 : p.L;
+    while (kn_pf < total_known || le < p.L) {
+      bool progress = false;
+      if (le < p.L) {
+        const bool known = static_cast<int>(vr->pf_route) > le;
+        if (known || p.spec) {
+          const DecLayerDev* Lp = p.layers + le;
+          const int E = Lp->wg != nullptr ? Lp->n_experts : 1;
+          unsigned int amask = known ? vr->pf_amask[le & 3] : ((1u << E) - 1u);
+          amask &= (1u << E) - 1u;
+          if (amask == 0) amask = 1u;
+          const int nact = __popc(amask);
+          const int n5 = cnt(nact * tiles_f), n6 = cnt(nact * tiles_d);
+          const unsigned int c5 = static_cast<unsigned int>(n5 * chunks_d);
+          const unsigned int total_e = c5 + static_cast<unsigned int>(n6 * chunks_f);
+          const unsigned int pos = vr->pf_ex;
+          const int ll = static_cast<int>(pos >> 16);
+          if (ll > le) {  // the producer is already past this layer
+            ++le;
+            ex_pf = 0;
+            progress = true;
+          } else {
+            const unsigned int base = ll == le ? (pos & 0xffffu) : 0u;
+            if (ex_pf < base) ex_pf = base;
+            if (ex_pf < total_e && ex_pf < base + ela) {
+              if (ex_pf < c5) {
+                const int tile = bid + static_cast<int>(ex_pf / chunks_d) * G, c = static_cast<int>(ex_pf % chunks_d);
+                const int e = __fns(amask, 0, tile / tiles_f + 1) & (DK_MAXE - 1);
+                tma_prefetch_3d(&Lp->wgate[e], 0, (tile % tiles_f) * 8, c * (DK_KC / 64));
+                tma_prefetch_3d(&Lp->wup[e], 0, (tile % tiles_f) * 8, c * (DK_KC / 64));
+              } else {
+                const unsigned int r = ex_pf - c5;
+                const int tile = bid + static_cast<int>(r / chunks_f) * G, c = static_cast<int>(r % chunks_f);
+                const int e = __fns(amask, 0, tile / tiles_d + 1) & (DK_MAXE - 1);
+                tma_prefetch_3d(&Lp->wdown[e], 0, (tile % tiles_d) * 16, c * (DK_KC / 64));
+              }
+              ++ex_pf;
+              progress = true;
+            }
+            if (ex_pf >= total_e) {
+              ++le;
+              ex_pf = 0;
+              progress = true;
+            }
+          }
+        }
+      }
+      if (kn_pf < total_known) {
+        const unsigned int kl = vr->pf_kn;
+        if (kn_pf < kl) kn_pf = kl;
+        if (kn_pf < total_known && kn_pf < kl + kla) {
+          const DecLayerDev* Lp = p.layers + kn_pf / per_layer;
+          const unsigned int r = kn_pf % per_layer;
+          const int ti = static_cast<int>(r / chunks_d), c = static_cast<int>(r % chunks_d);
+          if (ti < n1) {
+            const int tile = bid + ti * G, which = tile / tiles_d;
+            const CUtensorMap* tm = which == 0 ? &Lp->wq : (which == 1 ? &Lp->wk : &Lp->wv);
+            tma_prefetch_3d(tm, 0, (tile % tiles_d) * 16, c * (DK_KC / 64));
+          } else {
+            tma_prefetch_3d(&Lp->wo, 0, (bid + (ti - n1) * G) * 16, c * (DK_KC / 64));
+          }
+          ++kn_pf;
+          progress = true;
+        }
+      }
+      if (!progress) __nanosleep(100);
     }
     return;
   }
@@ -685,7 +801,10 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
         for (int e = 0; e < E; ++e) dk_bulk_g2s(s_wg + e * D, L->wg + static_cast<long long>(e) * D, D * 4, wg_bar);
     }
     // ---------------------------------------------------------- P1: q,k,v = RMSNorm(x) Wqkv^T
-    stage_rows(act, p.x, s_ln_in, lnin_bar, lnin_phase, B, D, p.eps, red);
+    unsigned long long* const tsp =
+        (l == p.timing_layer && threadIdx.x == 0 && blockIdx.x < 160) ? g_dk_times + blockIdx.x * DK_TSLOTS : nullptr;
+    DK_STAMP(14);
+    stage_rows(act, p.x, s_ln_in, lnin_bar, lnin_phase, B, D, p.eps, red, tsp != nullptr ? tsp + 15 : nullptr);
     lnin_phase ^= 1;
     consumer_sync();
     DK_STAMP(1);
@@ -737,8 +856,10 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
     grid_sync(p.sync, bar_target);
     DK_STAMP(8);
     // ---------------------------------------------------------- P4: h = RMSNorm(x), router (every CTA, no barrier)
-    stage_rows(act, p.x, s_ln_post, wg_bar, wg_phase, B, D, p.eps, red);  // (wg_bar also covers the router weights)
+    stage_rows(act, p.x, s_ln_post, wg_bar, wg_phase, B, D, p.eps, red,
+               tsp != nullptr ? tsp + 20 : nullptr);  // (wg_bar also covers the router weights)
     wg_phase ^= 1;
+    DK_STAMP(25);
     if (L->wg != nullptr) {
       // router logits from the stored (bf16-rounded) h, fp32 like DeepSpeed's TopKGate; all 8 warps share every row
       // (thread t owns k = 8t, 8t + 2048, ...), partial sums reduced lane -> warp -> CTA in a fixed order
@@ -820,6 +941,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
       }
     }
     consumer_sync();
+    DK_STAMP(26);
     if (threadIdx.x == 0) {
       // top-1 + capacity slots in token order (torch.cumsum), as moe_scan_kernel / moe_route_small_kernel
       const bool moe = L->wg != nullptr;
@@ -851,16 +973,19 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
         if (rt->kept[e] > 0) am |= 1u << e;
       rt->amask = am;
       rt->moe = moe ? 1 : 0;
+      rt->pf_amask[l & 3] = am;
+      __threadfence_block();
+      *const_cast<volatile unsigned int*>(&rt->pf_route) = static_cast<unsigned int>(l) + 1u;
       if (moe && blockIdx.x == 0) {
         float aux = 0.0f;
         for (int e = 0; e < E; ++e) {
           aux += (me[e] / B) * (static_cast<float>(cnt[e]) / B);
-          if (p.exp_counts != nullptr) p.exp_counts[l * E + e] = cnt[e];
+          if (p.exp_counts != nullptr) p.exp_counts[l * p.Emax + e] = cnt[e];
         }
         if (p.l_aux != nullptr) p.l_aux[l] = aux * E;
         if (p.gate_logits != nullptr)
           for (int s = 0; s < B; ++s)
-            for (int e = 0; e < E; ++e) p.gate_logits[(static_cast<long long>(l) * B + s) * E + e] = rt->logits[s][e];
+            for (int e = 0; e < E; ++e) p.gate_logits[static_cast<long long>(l) * B * p.Emax + s * E + e] = rt->logits[s][e];
       }
       mbar_arrive(route_bar);  // release: the producer may read the expert choice
     }
@@ -1030,6 +1155,21 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
   p.pos = io.past_len;
   p.Emax = emax;
   p.timing_layer = g_timing_layer;
+  {
+    // L2 prefetch look-ahead per CTA in 16 KB chunks (x 148 CTAs must stay well inside the 126 MB L2)
+    static int kla = -1, ela = -1, spec = -1;
+    if (kla < 0) {
+      const char* a = getenv("MPL_DK_KLA");
+      const char* b = getenv("MPL_DK_ELA");
+      const char* c = getenv("MPL_DK_SPEC");
+      kla = a != nullptr ? atoi(a) : 16;
+      ela = b != nullptr ? atoi(b) : 8;
+      spec = c != nullptr ? atoi(c) : 4;  // speculate "every expert is hit" from this many sequences up (0: never)
+    }
+    p.kla = kla;
+    p.ela = ela > 0xffff ? 0xffff : ela;
+    p.spec = (spec > 0 && io.B >= spec) ? 1 : 0;
+  }
   for (int e = 0; e <= DK_MAXE; ++e) p.cap[e] = cap_by_e[e];
   p.eps = m.rms_eps;
   p.scale = 1.0f / sqrtf(128.0f);

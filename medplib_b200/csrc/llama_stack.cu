@@ -133,6 +133,7 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
       return llama_decode_step(m, io, w.qkv, w.attn, w.h1, cap, emax, st);
   }
   const long long cache_layer = static_cast<long long>(B) * H * io.Tmax * hd;  // elements per layer
+  const int emax_all = max_experts(m);  // router outputs: one [S * Emax] block per transformer layer, rows packed by E_l
 
   for (int l = 0; l < m.n_layers; ++l) {
     const mpl_llama_layer& L = m.layers[l];
@@ -234,13 +235,13 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
     r.E = E;
     r.k = m.top_k;
     r.capacity = C;
-    r.logits = io.gate_logits ? io.gate_logits + static_cast<long long>(l) * S * E : w.logits;
+    r.logits = io.gate_logits ? io.gate_logits + static_cast<long long>(l) * S * emax_all : w.logits;  // layer block = S * Emax
     r.gates = w.gates;
     r.expert = w.expert;
     r.gate = w.gate;
     r.slot = w.slot;
     r.kept = w.kept;
-    r.exp_counts = io.exp_counts ? io.exp_counts + static_cast<long long>(l) * E : w.exp_counts;
+    r.exp_counts = io.exp_counts ? io.exp_counts + static_cast<long long>(l) * emax_all : w.exp_counts;
     r.l_aux = io.l_aux ? io.l_aux + l : w.l_aux;
     const bool fused_front = small && !(m.top_k == 1 && r.noise != nullptr);
     const bool gather = fused_front && C <= 16;  // streaming expert GEMMs read their rows through tok_of_slot

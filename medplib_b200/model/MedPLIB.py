@@ -711,7 +711,8 @@ class MedPLIBForCausalLM(PreTrainedModel):
             logits = ops.linear(hidden[:, -1], self.lm_head.weight, out_dtype=torch.float32).unsqueeze(1)
         else:
             logits = ops.linear(hidden, self.lm_head.weight, out_dtype=torch.float32)
-        moe_losses = list(out["l_aux"].unbind(0)) if out["l_aux"] is not None else []
+        # one entry per MoE layer, as MoELlamaModel_forward collects them (medplib_moe_llama.py:265-283): dense layers add none
+        moe_losses = [out["l_aux"][li] for li in self._moe_layer_ids()] if out["l_aux"] is not None else []
         moe_loss = self.router_aux_loss_coef * sum(moe_losses) if moe_losses else None
         loss = None
         hs = out["hidden_states"] if output_hidden_states else None
@@ -763,16 +764,30 @@ class MedPLIBForCausalLM(PreTrainedModel):
                                          hidden_states=(hidden,), moe_loss_list=moe_losses)
 
     def _fire_gate_hooks(self, gate_logits):
-        """vqa_infer.py:157-165 registers forward hooks on the `wg` Linears to read the router logits."""
+        """vqa_infer.py:157-165 registers forward hooks on the `wg` Linears to read the router logits.
+        gate_logits: the engine's [L, S * Emax] f32 buffer indexed by TRANSFORMER layer (rows of layer l packed [S, E_l]),
+        or the train path's list with one [S, E_l] tensor per MoE layer."""
         if gate_logits is None:
             return
-        li = 0
-        for layer in self.model.layers:
-            if isinstance(layer.mlp, M.MoE):
-                wg = layer.mlp.deepspeed_moe.gate.wg
+        per_moe = isinstance(gate_logits, (list, tuple))
+        mi = 0
+        for li, layer in enumerate(self.model.layers):
+            if not isinstance(layer.mlp, M.MoE):
+                continue
+            wg = layer.mlp.deepspeed_moe.gate.wg
+            if wg._forward_hooks:
+                if per_moe:
+                    lg = gate_logits[mi]
+                else:
+                    E = wg.weight.shape[0]
+                    flat = gate_logits[li].reshape(-1)
+                    lg = flat[:(flat.numel() // gate_logits.shape[-1]) * E].view(-1, E)
                 for hook in list(wg._forward_hooks.values()):
-                    hook(wg, (None,), gate_logits[li])
-                li += 1
+                    hook(wg, (None,), lg)
+            mi += 1
+
+    def _moe_layer_ids(self):
+        return [li for li, layer in enumerate(self.model.layers) if isinstance(layer.mlp, M.MoE)]
 
     def forward(self, **kwargs):
         if "past_key_values" in kwargs:

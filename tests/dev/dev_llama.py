@@ -81,17 +81,41 @@ def timing(B=1, layer=5):
     xs = torch.randn(B, 1, 4096, device=dev).to(bf16)
     for _ in range(3):
         eng.forward(xs.clone(), cache)
+    cache.len = T
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(16):
+        eng.forward(xs.clone(), cache)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"B={B}: {e0.elapsed_time(e1) / 16:.3f} ms/step over 16 steps (context {T}..{T + 16}); env "
+          f"KLA={os.environ.get('MPL_DK_KLA')} ELA={os.environ.get('MPL_DK_ELA')} SPEC={os.environ.get('MPL_DK_SPEC')}")
+    cache.len = T
     lib.mpl_debug_decode_timing(layer, None)
     eng.forward(xs.clone(), cache)
-    buf = (ctypes.c_ulonglong * (160 * 16))()
+    buf = (ctypes.c_ulonglong * (160 * 32))()
     lib.mpl_debug_decode_timing(-1, buf)
-    t = torch.tensor(list(buf), dtype=torch.float64).view(160, 16)[:148, :14]
+    full = torch.tensor(list(buf), dtype=torch.float64).view(160, 32)[:148]
+    t = full[:, :14]
     names = ["P1 stage", "P1 tiles", "bar1", "P2 attn", "bar2", "P3 stage", "P3 tiles", "bar3", "P4 route", "P5 tiles",
              "bar4", "P6 tiles", "bar5"]
     d = (t[:, 1:] - t[:, :-1]) / 1e3
     print(f"B={B} layer {layer}: total {(t[:, 13] - t[:, 0]).mean() / 1e3:.1f} us (per-CTA mean)")
     for i, n in enumerate(names):
         print(f"  {n:10s} mean {d[:, i].mean():7.2f} us  min {d[:, i].min():7.2f}  max {d[:, i].max():7.2f}")
+    # sub-stamps: 14 layer prologue done; 15..19 P1 stage_rows (ln wait, sums written, sync, stored, end);
+    # 20..24 the same for P4's stage_rows; 25 after P4 staging; 26 router logits + softmax done
+    def seg(a, b):
+        dd = (full[:, b] - full[:, a]) / 1e3
+        return f"mean {dd.mean():6.2f} min {dd.min():6.2f} max {dd.max():6.2f}"
+    for name, a, b in (("P1 prologue (L-> loads, bulk issue)", 0, 14), ("P1 stage: ln wait", 14, 15),
+                       ("P1 stage: loads + sumsq", 15, 16), ("P1 stage: sync", 16, 17), ("P1 stage: normalise + store", 17, 18),
+                       ("P1 stage: end sync", 18, 19), ("P1 after stage -> tiles", 19, 1),
+                       ("P4 stage: ln/wg wait", 8, 20), ("P4 stage: loads + sumsq", 20, 21), ("P4 stage: sync", 21, 22),
+                       ("P4 stage: normalise + store", 22, 23), ("P4 stage: end", 23, 25), ("P4 router logits", 25, 26),
+                       ("P4 scan + publish", 26, 9)):
+        print(f"    {name:38s} {seg(a, b)}")
     # phase end skew: when does the LAST CTA finish the phase's work relative to the first stamp
     t0 = t[:, 0].min()
     for i in (2, 4, 7, 10, 12):

@@ -133,6 +133,34 @@ def test_gate_hooks_and_lm_forward(dev):
     assert out2.logits.shape == (1, 1, 300) and out2.past_key_values.len == T + 1
 
 
+def test_gate_hooks_sparse_moe_layout(dev):
+    """MoE in layer 1 only (--moe_mode second_half / explicit moe_layers_idx): the single `wg` hook must observe layer
+    1's router logits (the engine's buffer is indexed by transformer layer), for the prefill and for a decode step
+    through the persistent kernel; moe_loss_list has one entry per MoE layer (medplib_moe_llama.py:265-283)."""
+    from oracle import llama, pipeline
+    m, sd, ocfg = build(dev, moe_layers=[1])
+    ids, clip_img, _ = inputs()
+    hooked = [n for n, mod in m.named_modules() if "wg" in n and isinstance(mod, torch.nn.Linear)]
+    assert hooked == ["model.layers.1.mlp.deepspeed_moe.gate.wg"]
+    seen = []
+    m.get_submodule(hooked[0]).register_forward_hook(lambda mod_, i, o: seen.append(o.detach().float().cpu()))
+    am = torch.ones_like(ids, dtype=torch.bool)
+    out = m(input_ids=ids.to(dev), images=clip_img.to(dev), past_key_values=None, use_cache=True,
+            attention_mask=am.to(dev))
+    emb, am2, _ = pipeline.prefill_inputs(sd, ocfg, clip_img, ids, am)
+    ref = llama.model_forward(sd, ocfg["llama"], emb, am2)
+    assert len(ref["gate_logits"]) == 1 and len(seen) == 1 and len(out.moe_loss_list) == 1
+    want = ref["gate_logits"][0].float()
+    assert seen[0].shape == want.shape
+    assert (seen[0] - want).abs().max() <= 4e-2 * want.abs().max()
+    assert seen[0].abs().max() > 0.1 * want.abs().max()
+    T = out.past_key_values.len
+    nxt = out.logits[:, -1].argmax(-1, keepdim=True)
+    m(input_ids=nxt, images=clip_img.to(dev), past_key_values=out.past_key_values, use_cache=True,
+      attention_mask=torch.ones((1, T + 1), dtype=torch.bool, device=dev))
+    assert len(seen) == 2 and seen[1].shape == (1, 2) and seen[1].abs().max() > 0
+
+
 def test_cpu_tensors_fail_loudly(dev):
     from medplib_b200 import ops, _lib
     with pytest.raises(_lib.MplError):

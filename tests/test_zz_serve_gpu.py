@@ -1,8 +1,7 @@
 """GPU: the streaming serving loop (medplib_b200/serve.py) against evaluate() on the same small model —
-same greedy tokens, same mask.  Written after the round's GPU budget was spent: it has NOT run on a B200 yet, so it only
-runs when MPL_RUN_UNVALIDATED=1 (the first gpurun of the next round); the loop's host logic is covered on CPU by
-tests/test_serve_cpu.py and every model call it makes (per-token forward with a KV cache, _seg_embeddings,
-get_visual_embs, _decode_masks) is covered by tests/test_model_gpu.py."""
+same greedy tokens, same mask — and the ICL exemplar-mask path of the input pipeline kernel.  (First run on a B200 in
+round 2, call 1: both green; the round-1 gate is gone.)  The loop's host logic is also covered on CPU by
+tests/test_serve_cpu.py."""
 import math
 import os
 
@@ -11,8 +10,7 @@ import torch
 
 from test_model_gpu import SEG, build, inputs
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("MPL_RUN_UNVALIDATED"), reason="not yet validated on a B200")]
+pytestmark = [pytest.mark.gpu]
 
 
 class Tok:
