@@ -2,23 +2,27 @@
 //
 // Replaces, for the autoregressive steps of MedPLIBForCausalLM.generate / evaluate (model/MedPLIB.py:592-606,
 // model/medplib/model/language_model/medplib_moe_llama.py:110-305,451-485), the ~7 launches per layer of the general
-// runner (llama_stack.cu). A decode step is HBM-bound: 13-22 GB of weights are read once per token, and every kernel
-// boundary costs the weight stream ~8 us of ramp-down / launch / ramp-up (measured: 152 us per layer against a 62 us
-// roofline). Here ONE cooperative grid (one CTA per SM) runs all layers:
+// runner (llama_stack.cu). A decode step is HBM-bound: 13-22 GB of weights are read once per token. ONE cooperative
+// grid (one CTA per SM) runs all layers:
 //   * a producer thread per CTA walks the whole step's weight-tile schedule and keeps a 6 x 16 KB TMA ring full; it does
-//     not take part in grid barriers, so the HBM stream continues across phase boundaries (the next phase's weights are
-//     already in shared memory when the consumers arrive) — the only stall is the wait for the router's expert choice;
-//   * 8 consumer warps run the phases of a layer, separated by grid barriers (atomic counter in L2):
-//       P1  q,k,v = RMSNorm(x) Wqkv^T           activations normalised once per CTA into shared memory
-//       P2  RoPE(q, k_new) + KV append + split-K attention over the cache, last-arriver merge per (b, h)
-//       P3  x += attn Wo^T
-//       P4  h = RMSNorm(x); router logits / softmax / top-1 / capacity slots — recomputed by every CTA (no barrier)
-//       P5  h1 = SiLU(h Wgate_e^T) * (h Wup_e^T)  only experts that received tokens are streamed
-//       P6  x += gate * (h1 Wdown_e^T)          MoE combine fused (dense layers: plain residual)
-//     then the final RMSNorm. The GEMM core is the streaming kernel's (skinny_gemm.cu): mma.sync m16n8k16 with the
-//     weight rows as the M operand, k split over the warps, cross-warp reduction through shared memory.
+//     not take part in grid barriers, so the next phase's first tiles are in shared memory when the consumers arrive;
+//   * a prefetch thread walks the same schedule a bounded distance ahead with cp.async.bulk.prefetch.tensor (HBM -> L2)
+//     so that HBM keeps streaming while the consumers sit in a barrier / attention / the router;
+//   * 8 consumer warps run, per layer, four weight phases separated by grid barriers (atomic counter in L2):
+//       step 0  q,k,v = RMSNorm(x) Wqkv^T, then RoPE + KV append + split-K attention over the cache
+//       step 1  x += attn Wo^T
+//       step 2  h = RMSNorm(x); router logits / softmax / top-1 / capacity slots (recomputed by every CTA, no
+//               barrier); h1 = SiLU(h Wgate_e^T) * (h Wup_e^T) for the experts that received tokens
+//       step 3  x += gate * (h1 Wdown_e^T)      MoE combine fused (dense layers: plain residual)
+//     then the final RMSNorm. The GEMM core is mma.sync m16n8k16 with the weight rows as the M operand, k split over
+//     the warps, cross-warp reduction through shared memory.
+// CODE SIZE IS A FIRST-ORDER CONCERN HERE (profiles/r02_ncu_decode_kernel.md): a layer executes every phase's code
+// exactly once, so anything outside the tile loop runs from a cold instruction cache — round 1's 300 KB of unrolled,
+// four-times-instantiated code spent 87 % of its inter-phase samples in `stall_no_inst`. The consumer side is
+// therefore ONE loop over (layer, step) with a single instance of the staging code, the tile loop and the grid barrier,
+// row loops are real loops, and helpers used twice are not inlined.
 // Rounding points are those of the general path (bf16 after every linear, RMSNorm's two roundings, RoPE's three, P
-// rounded before P·V, bf16(gate) * bf16(y)), so both paths produce the same bits.
+// rounded before P·V, bf16(gate) * bf16(y)); fp32 accumulation orders differ from it only inside the attention.
 #include <cooperative_groups.h>
 #include <cuda.h>
 
@@ -81,7 +85,7 @@ struct DecParams {
   float* l_aux;        // [L] or NULL
   int* exp_counts;     // [L, Emax] or NULL
   int B, D, H, F, L, Tmax, pos, nsplit, Emax, timing_layer;
-  int kla, ela, spec;  // L2 prefetch look-ahead (16 KB chunks per CTA): known stream, expert stream; speculate all experts
+  int la, spec, evict_first;  // L2 prefetch look-ahead (16 KB chunks per CTA, in consumption order); walk past undecided routers
   int cap[DK_MAXE + 1];  // capacity for a layer with E experts (index E)
   float eps, scale;
 };
@@ -129,11 +133,12 @@ struct RouteSmem {
   float gate_of_slot[DK_MAXE][DK_MAXB];
   unsigned int amask;
   int moe;
+  int nact;            // number of experts that received tokens
+  int act[DK_MAXE];    // their indices, ascending
   float logits[DK_MAXB][DK_MAXE];
   float gates[DK_MAXB][DK_MAXE];
   // L2 prefetcher coordination (monotonic counters, written by the producer / consumer thread 0, polled by the prefetcher)
-  unsigned int pf_kn;        // chunks of the known stream (q,k,v,o of all layers) the producer has issued so far
-  unsigned int pf_ex;        // (layer << 16) | chunks of that layer's expert stream issued so far
+  unsigned int pf_pos;       // producer position: (layer << 16) | chunks of that layer issued so far
   unsigned int pf_route;     // 1 + last layer whose expert choice is published
   unsigned int pf_amask[4];  // expert masks of the last layers, slot l & 3
 };
@@ -160,7 +165,7 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
 // Grid barrier for the consumer warps (the producer thread never waits here). Same structure as cooperative
 // groups' grid.sync(): CTA barrier, one thread fences + arrives + spins + fences (the gpu-scope fence also invalidates
 // this SM's L1, so plain loads after the barrier see the other CTAs' writes), CTA barrier.
-__device__ __forceinline__ void grid_sync(unsigned int* ctr, unsigned int& target) {
+__device__ __noinline__ void grid_sync(unsigned int* ctr, unsigned int& target) {
   consumer_sync();
   if (threadIdx.x == 0) {
     target += gridDim.x;
@@ -179,186 +184,80 @@ __device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// weights are read exactly once per step: with an evict-first policy the stream does not push the lines the prefetcher
+// has parked in L2 (normal priority) out before they are used
+__device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, "
+      "%5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void produce_tile(Ring& r, const CUtensorMap* m0, const CUtensorMap* m1, int n0, int chunks,
-                                             volatile unsigned int* progress, unsigned int& count) {
+                                             volatile unsigned int* progress, unsigned int& count, uint64_t policy) {
   for (int c = 0; c < chunks; ++c) {
     mbar_wait(&r.empty[r.stage], r.phase ^ 1);
     uint8_t* dst = r.base + r.stage * DK_STAGE_BYTES;
     mbar_expect_tx(&r.full[r.stage], DK_STAGE_BYTES);
-    tma_load_3d(dst, m0, &r.full[r.stage], 0, n0, c * (DK_KC / 64));
-    if (m1 != nullptr) tma_load_3d(dst + DK_STAGE_BYTES / 2, m1, &r.full[r.stage], 0, n0, c * (DK_KC / 64));
+    if (policy != 0) {
+      tma_load_3d_hint(dst, m0, &r.full[r.stage], 0, n0, c * (DK_KC / 64), policy);
+      if (m1 != nullptr)
+        tma_load_3d_hint(dst + DK_STAGE_BYTES / 2, m1, &r.full[r.stage], 0, n0, c * (DK_KC / 64), policy);
+    } else {
+      tma_load_3d(dst, m0, &r.full[r.stage], 0, n0, c * (DK_KC / 64));
+      if (m1 != nullptr) tma_load_3d(dst + DK_STAGE_BYTES / 2, m1, &r.full[r.stage], 0, n0, c * (DK_KC / 64));
+    }
     r.advance();
     *progress = ++count;
   }
 }
 
-// ------------------------------------------------------------------------------------------------ consumer GEMM core
-// One tile: 16 weight rows (DUAL: 8 gate + 8 up rows) x K, activation row of this lane's column group `arow` (generic
-// pointer into shared or global memory, or NULL for an empty column). Leaves the CTA-reduced sums in rbuf[row][m].
-template <bool DUAL>
-__device__ __forceinline__ void consume_tile(Ring& r, int chunks, int K, const __nv_bfloat16* arow, float* rbuf) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  constexpr int ROWS = DUAL ? 8 : 16;
-  float acc0[4] = {0.f, 0.f, 0.f, 0.f};  // one accumulator, same HMMA order as the streaming kernel: identical bits
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  // activation fragments run two chunks ahead of the weights (global-memory A of the down projection: L2 latency)
-  auto load_a = [&](int c, uint4& x0, uint4& x1) {
-    const int k = c * DK_KC + warp * 64 + t * 8;
-    x0 = (arow != nullptr && c < chunks && k < K) ? *reinterpret_cast<const uint4*>(arow + k) : zero;
-    x1 = (arow != nullptr && c < chunks && k + 32 < K) ? *reinterpret_cast<const uint4*>(arow + k + 32) : zero;
-  };
-  uint4 xa0, xa1, xn0, xn1;
-  load_a(0, xa0, xa1);
-  load_a(1, xn0, xn1);
-  for (int c = 0; c < chunks; ++c) {
-    const uint4 xb0 = xa0, xb1 = xa1;
-    xa0 = xn0;
-    xa1 = xn1;
-    load_a(c + 2, xn0, xn1);
-    mbar_wait(&r.full[r.stage], r.phase);
-    const uint32_t sbase = smem_u32(r.base + r.stage * DK_STAGE_BYTES) + warp * (ROWS * 128) + g * 128;
-    const uint32_t hi = DUAL ? DK_STAGE_BYTES / 2 : 1024;
-    {
-      const uint32_t sw = static_cast<uint32_t>((t ^ g) * 16);
-      const uint4 wa = dk_lds128(sbase + sw), wb = dk_lds128(sbase + hi + sw);
-      dk_hmma(acc0, wa.x, wb.x, wa.y, wb.y, xb0.x, xb0.y);
-      dk_hmma(acc0, wa.z, wb.z, wa.w, wb.w, xb0.z, xb0.w);
-    }
-    {
-      const uint32_t sw = static_cast<uint32_t>(((4 + t) ^ g) * 16);
-      const uint4 wa = dk_lds128(sbase + sw), wb = dk_lds128(sbase + hi + sw);
-      dk_hmma(acc0, wa.x, wb.x, wa.y, wb.y, xb1.x, xb1.y);
-      dk_hmma(acc0, wa.z, wb.z, wa.w, wb.w, xb1.z, xb1.w);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&r.empty[r.stage]);
-    r.advance();
-  }
-  // C fragment: c0,c1 -> (weight row g, m = 2t, 2t+1); c2,c3 -> (weight row g+8, same m)
-  float* rw = rbuf + warp * 16 * DK_RP;
-  rw[g * DK_RP + t * 2] = acc0[0];
-  rw[g * DK_RP + t * 2 + 1] = acc0[1];
-  rw[(g + 8) * DK_RP + t * 2] = acc0[2];
-  rw[(g + 8) * DK_RP + t * 2 + 1] = acc0[3];
-  consumer_sync();
-}
+// ------------------------------------------------------------------------------------------------ consumer helpers
 __device__ __forceinline__ float reduce_rows(const float* rbuf, int r, int m) {
   float v = 0.0f;
 #pragma unroll
   for (int w = 0; w < DK_CONSUMERS; ++w) v += rbuf[(w * 16 + r) * DK_RP + m];
   return v;
 }
-
-// Activation staging: the B rows go global (L2) -> registers -> shared memory with EVERY load of a thread issued before
-// its first store (thread t owns the 16-byte vectors t and t + 256 of every row: one L2 round trip for the whole block,
-// and not queued behind the weight ring in the TMA unit as a bulk copy would be). With a norm weight (already in shared
-// memory, completion on ln_bar / ln_phase) the rows are RMS-normalised on the way with HF LlamaRMSNorm's roundings
-// w * bf16(x * rstd); the sum of squares is reduced lane -> warp (shuffles) -> CTA (fixed order 0..7).
-struct ActStage {
-  uint8_t* s_a;  // [B][pitch]
-  int pitch;
-};
 __device__ __forceinline__ void dk_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __noinline__ void stage_rows(ActStage st, const __nv_bfloat16* __restrict__ src, const uint8_t* s_ln,
-                                        uint64_t* ln_bar, uint32_t ln_phase, int B, int D, float eps, float* s_part,
-                                        unsigned long long* ts = nullptr) {
-  constexpr int NV = 2;  // vectors per thread and row: D <= 4096
-  constexpr int RG = 4;  // rows per register group (spills are ruinous here: shared memory leaves almost no L1)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* const s_a = st.s_a;
-  const int pitch = st.pitch;
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  if (s_ln != nullptr) mbar_wait(ln_bar, ln_phase);
-  if (ts != nullptr) ts[0] = globaltimer();
-#pragma unroll 1
-  for (int m0 = 0; m0 < B; m0 += RG) {
-    uint4 v[RG][NV];
+__device__ __forceinline__ void dk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(const void* p) { return dk_lds128(smem_u32(p)); }
+__device__ __forceinline__ void sts_v4(void* p, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float sumsq8(const uint4& v, float a) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-    for (int r = 0; r < RG; ++r)
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int k = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
-        v[r][j] = (m0 + r < B && k < D) ? *reinterpret_cast<const uint4*>(src + static_cast<long long>(m0 + r) * D + k)
-                                        : zero;
-      }
-    if (s_ln != nullptr) {
-      float ss[RG];
-#pragma unroll
-      for (int r = 0; r < RG; ++r) {
-        ss[r] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v[r][j]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(h[i]);
-            ss[r] += f.x * f.x + f.y * f.y;
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int r = 0; r < RG; ++r) ss[r] += __shfl_xor_sync(0xffffffffu, ss[r], o);  // independent trees
-      if (lane == 0) {
-#pragma unroll
-        for (int r = 0; r < RG; ++r) s_part[r * DK_CONSUMERS + warp] = ss[r];
-      }
-      if (ts != nullptr && m0 == 0) ts[1] = globaltimer();
-      consumer_sync();
-      if (ts != nullptr && m0 == 0) ts[2] = globaltimer();
-#pragma unroll
-      for (int r = 0; r < RG; ++r) {
-        float tot = 0.0f;
-#pragma unroll
-        for (int wi = 0; wi < DK_CONSUMERS; ++wi) tot += s_part[r * DK_CONSUMERS + wi];
-        const float rstd = rsqrtf(tot / static_cast<float>(D) + eps);
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int k = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
-          const uint4 w = k < D ? *reinterpret_cast<const uint4*>(s_ln + k * 2) : zero;
-          const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&v[r][j]);
-          const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&w);
-          uint4 o;
-          uint32_t* op = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 xf = __bfloat1622float2(xp[i]), wf = __bfloat1622float2(wp[i]);
-            op[i] = pack_bf16(wf.x * bf16_round(xf.x * rstd), wf.y * bf16_round(xf.y * rstd));
-          }
-          v[r][j] = o;
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RG; ++r)
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int k = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
-        if (m0 + r < B && k < D) *reinterpret_cast<uint4*>(s_a + (m0 + r) * pitch + k * 2) = v[r][j];
-      }
-    if (ts != nullptr && m0 == 0) ts[3] = globaltimer();
-    consumer_sync();  // rows complete for every reader; s_part reusable
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    a += f.x * f.x + f.y * f.y;
   }
-  if (ts != nullptr) ts[4] = globaltimer();
+  return a;
+}
+// HF LlamaRMSNorm's roundings: w * bf16(x * rstd)
+__device__ __forceinline__ uint4 norm8(const uint4& x, const uint4& w, float rstd) {
+  const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
+  const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&w);
+  uint4 o;
+  uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 xf = __bfloat1622float2(xp[i]), wf = __bfloat1622float2(wp[i]);
+    op[i] = pack_bf16(wf.x * bf16_round(xf.x * rstd), wf.y * bf16_round(xf.y * rstd));
+  }
+  return o;
 }
 
-// L2 prefetch of small per-layer tensors (router weights, norm weights) well before they are needed.
-__device__ __forceinline__ void prefetch_l2(const void* ptr, long long bytes) {
-  const char* c = static_cast<const char*>(ptr);
-  for (long long off = static_cast<long long>(threadIdx.x) * 128; off < bytes; off += DK_CONSUMERS * 32 * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
-}
-
-// ------------------------------------------------------------------------------------------------ attention item
-// One (b, h, split) of the decode attention: 8 warps, 4 keys per warp step, 8 lanes x 16 dims per key. q and the new
-// key are rotated on the fly from the q,k,v buffer; the split that owns position `pos` appends k,v to the cache.
+// ------------------------------------------------------------------------------------------------ attention
 __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (&f)[16]) {
   const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
   const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
@@ -372,9 +271,10 @@ __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (
   }
 }
 // RoPE of dims d = gl*16 .. +15 of a 128-wide head (partner = d + 64 for the first half, rotated with a minus sign, or
-// d - 64), HF apply_rotary_pos_emb in bf16: every product and the sum rounded. Result packed as bf16.
-__device__ __forceinline__ void rope16(const __nv_bfloat16* src, const __nv_bfloat16* cr, const __nv_bfloat16* sr,
-                                       int gl, uint4& o0, uint4& o1) {
+// d - 64), HF apply_rotary_pos_emb in bf16: every product and the sum rounded. Result packed as bf16. (Not inlined:
+// used for q and for the new key; a second copy would only add cold code.)
+__device__ __noinline__ void rope16(const __nv_bfloat16* src, const __nv_bfloat16* cr, const __nv_bfloat16* sr, int gl,
+                                    uint4& o0, uint4& o1) {
   const int d0 = gl * 16;
   const bool first = gl < 4;
   const uint4* own = reinterpret_cast<const uint4*>(src + d0);
@@ -397,17 +297,33 @@ __device__ __forceinline__ void rope16(const __nv_bfloat16* src, const __nv_bflo
   o1.x = pack_bf16(out[8], out[9]); o1.y = pack_bf16(out[10], out[11]); o1.z = pack_bf16(out[12], out[13]); o1.w = pack_bf16(out[14], out[15]);
 }
 
-// P2. One (b, h, split) per WARP: 4 keys per step (8 lanes x 16 dims per key), 4 steps (16 keys, 8 KB) in flight per
-// warp, no CTA-level synchronisation: the 4 key groups merge by shuffles, splits merge through global scratch by the
-// last warp to arrive (atomic counter per (b, h), self-cleaning). The cached keys do not depend on this layer's q,k,v,
-// so the first 16 keys of the item are requested BEFORE the grid barrier that ends P1 and arrive while it is waiting.
-__device__ __noinline__ void attention_phase(const DecParams& p, int layer, int Tk, unsigned int& bar_target) {
+// work split of the decode attention over the grid's consumer warps: item = (b * H + h) * nsplit + z
+struct AttnItem {
+  int b, h, z, bh, k_lo, k_hi;
+};
+__device__ __forceinline__ AttnItem attn_item(const DecParams& p, int item, int Tk) {
+  AttnItem it;
+  const int per = ((Tk + p.nsplit - 1) / p.nsplit + 31) & ~31;
+  it.z = item % p.nsplit;
+  it.bh = item / p.nsplit;
+  it.b = it.bh / p.H;
+  it.h = it.bh % p.H;
+  it.k_lo = it.z * per;
+  it.k_hi = min(Tk, it.k_lo + per);
+  return it;
+}
+
+// One (b, h, split) per WARP: 4 keys per step (8 lanes x 16 dims per key), two steps per round with ONE online-softmax
+// update per round, two rounds (16 keys, 8 KB) in flight per warp, no CTA-level synchronisation: the 4 key groups merge
+// by shuffles, splits merge through global scratch by the last warp to arrive (atomic counter per (b, h), self-cleaning).
+// The cached keys do not depend on this layer's q,k,v, so the first 16 keys of the item are requested BEFORE the grid
+// barrier that ends the q,k,v phase and arrive while it is waiting. The new position (k rotated here, k,v appended to
+// the cache) is folded in after the cached keys by the split that owns it.
+__device__ __forceinline__ void attention_phase(const DecParams& p, int layer, int Tk, unsigned int& bar_target) {
   constexpr int D = 128;
-  constexpr int UNR = 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, gl = lane & 7;
   const int nsplit = p.nsplit;
-  const int per = ((Tk + nsplit - 1) / nsplit + 31) & ~31;
   const int pos = Tk - 1;
   const int n_items = p.B * p.H * nsplit;
   const int stride = gridDim.x * DK_CONSUMERS;
@@ -416,62 +332,43 @@ __device__ __noinline__ void attention_phase(const DecParams& p, int layer, int 
   const float sl2 = p.scale * 1.4426950408889634f;
   bool synced = false;
   // items are dealt round-robin over the CTAs first, so every SM pulls on the KV cache
+#pragma unroll 1
   for (int item = warp * gridDim.x + blockIdx.x; item < n_items || !synced; item += stride) {
     const bool has = item < n_items;
-    const int z = has ? item % nsplit : 0, bh = has ? item / nsplit : 0;
-    const int b = bh / p.H, h = bh % p.H;
-    const int k_lo = z * per;
-    const int k_hi = has ? min(Tk, k_lo + per) : k_lo;
-    const __nv_bfloat16* qrow = p.qkv + static_cast<long long>(b) * 3 * p.D + h * D;
-    const __nv_bfloat16* krow = qrow + p.D;
-    const __nv_bfloat16* vrow = qrow + 2 * p.D;
-    const long long head_off = (static_cast<long long>(b) * p.H + h) * p.Tmax * D;
+    const AttnItem it = attn_item(p, has ? item : 0, Tk);
+    const int k_lo = it.k_lo;
+    const int k_end = has ? min(it.k_hi, pos) : k_lo;  // cached keys of this split: [k_lo, k_end)
+    const __nv_bfloat16* qrow = p.qkv + static_cast<long long>(it.b) * 3 * p.D + it.h * D;
+    const long long head_off = (static_cast<long long>(it.b) * p.H + it.h) * p.Tmax * D;
     __nv_bfloat16* kc = p.kc + layer * p.cache_layer + head_off;
     __nv_bfloat16* vc = p.vc + layer * p.cache_layer + head_off;
-    const unsigned char* mrow = p.kv_mask ? p.kv_mask + static_cast<long long>(b) * p.kv_mask_stride : nullptr;
+    const unsigned char* mrow = p.kv_mask ? p.kv_mask + static_cast<long long>(it.b) * p.kv_mask_stride : nullptr;
 
-    // cached K/V of one key for this lane's 16 dims (packed bf16); the new position is filled in later
-    auto load_cached = [&](int k0, uint4& ka, uint4& kb, uint4& va, uint4& vb) {
-      const int key = k0 + grp;
-      const int kk = (key < k_hi && key != pos) ? key : k_lo;
-      if (kk == pos) {  // (k_lo == pos: nothing cached to read)
-        ka = kb = va = vb = make_uint4(0, 0, 0, 0);
-        return;
-      }
-      const __nv_bfloat16* kr = kc + static_cast<long long>(kk) * D + gl * 16;
-      const __nv_bfloat16* vr = vc + static_cast<long long>(kk) * D + gl * 16;
-      ka = *reinterpret_cast<const uint4*>(kr);
-      kb = *reinterpret_cast<const uint4*>(kr + 8);
-      va = *reinterpret_cast<const uint4*>(vr);
-      vb = *reinterpret_cast<const uint4*>(vr + 8);
-    };
-    // the new position: rotate k from the q,k,v buffer, append k,v to the cache (one lane group of one split owns it)
-    auto fix_new = [&](int k0, uint4& ka, uint4& kb, uint4& va, uint4& vb) {
-      if (k0 + grp != pos || pos >= k_hi) return;
-      rope16(krow, cr, sr, gl, ka, kb);
-      va = *reinterpret_cast<const uint4*>(vrow + gl * 16);
-      vb = *reinterpret_cast<const uint4*>(vrow + gl * 16 + 8);
-      __nv_bfloat16* kd = kc + static_cast<long long>(pos) * D + gl * 16;
-      *reinterpret_cast<uint4*>(kd) = ka;
-      *reinterpret_cast<uint4*>(kd + 8) = kb;
-      __nv_bfloat16* vd = vc + static_cast<long long>(pos) * D + gl * 16;
-      *reinterpret_cast<uint4*>(vd) = va;
-      *reinterpret_cast<uint4*>(vd + 8) = vb;
-    };
-
-    // two register buffers of UNR steps (8 keys) each, ping-pong: one is consumed while the other is in flight
-    uint4 ka[2][UNR], kb[2][UNR], va[2][UNR], vb[2][UNR];
+    // two register buffers of two steps (8 keys) each, ping-pong: one is consumed while the other is in flight
+    uint4 ka[2][2], kb[2][2], va[2][2], vb[2][2];
     auto load_round = [&](int kb0, int w) {
 #pragma unroll
-      for (int u = 0; u < UNR; ++u)
-        if (kb0 + 4 * u < k_hi) load_cached(kb0 + 4 * u, ka[w][u], kb[w][u], va[w][u], vb[w][u]);
+      for (int u = 0; u < 2; ++u) {
+        if (kb0 + 4 * u < k_end) {  // warp-uniform
+          const int key = kb0 + 4 * u + grp;
+          const int kk = key < k_end ? key : k_lo;
+          const __nv_bfloat16* kr = kc + static_cast<long long>(kk) * D + gl * 16;
+          const __nv_bfloat16* vr = vc + static_cast<long long>(kk) * D + gl * 16;
+          ka[w][u] = *reinterpret_cast<const uint4*>(kr);
+          kb[w][u] = *reinterpret_cast<const uint4*>(kr + 8);
+          va[w][u] = *reinterpret_cast<const uint4*>(vr);
+          vb[w][u] = *reinterpret_cast<const uint4*>(vr + 8);
+        } else {  // (a zero weight times a stale NaN pattern would still poison the accumulator)
+          ka[w][u] = kb[w][u] = va[w][u] = vb[w][u] = make_uint4(0, 0, 0, 0);
+        }
+      }
     };
     load_round(k_lo, 0);
-    load_round(k_lo + 4 * UNR, 1);
+    load_round(k_lo + 8, 1);
     if (!synced) {
-      DK_STAMP_L(layer, 2);
+      DK_STAMP_L(layer, 16);
       grid_sync(p.sync, bar_target);  // q,k,v of this layer are complete; the first keys are already in flight
-      DK_STAMP_L(layer, 3);
+      DK_STAMP_L(layer, 17);
       synced = true;
     }
     if (!has) break;
@@ -485,129 +382,156 @@ __device__ __noinline__ void attention_phase(const DecParams& p, int layer, int 
     float acc[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.0f;
-    auto compute_round = [&](int kb0, int w) {
+    // score of the key held in (ka, kb) against q (log2 domain), -inf when masked / out of range
+    auto score = [&](const uint4& k0, const uint4& k1, bool valid, int key) {
+      float kf[16];
+      unpack16(k0, k1, kf);
+      float dot = 0.0f;
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        if (kb0 + 4 * u >= k_hi) break;  // warp-uniform
-        fix_new(kb0 + 4 * u, ka[w][u], kb[w][u], va[w][u], vb[w][u]);
-        const int key = kb0 + 4 * u + grp;
-        const bool valid = key < k_hi;
-        const int kk = valid ? key : k_lo;
-        float kf[16], vf[16];
-        unpack16(ka[w][u], kb[w][u], kf);
-        unpack16(va[w][u], vb[w][u], vf);
-        // same association as the general decode kernel: pairs (e, e+1) of the low and the high 8 dims per step
-        float dot = 0.0f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          dot += qf[2 * e] * kf[2 * e] + qf[2 * e + 1] * kf[2 * e + 1] + qf[8 + 2 * e] * kf[8 + 2 * e] +
-                 qf[8 + 2 * e + 1] * kf[8 + 2 * e + 1];
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        float sc = dot * sl2;
-        if (!valid || (mrow != nullptr && mrow[kk] == 0)) sc = -INFINITY;
-        const float mn = fmaxf(m, sc);
-        const float msafe = (mn == -INFINITY) ? 0.0f : mn;
-        const float corr = exp2f(m - msafe);
-        const float pexp = exp2f(sc - msafe);
-        const float pv = bf16_round(pexp);  // P rounded to bf16 before P·V (softmax(...).to(bf16) @ v)
-        l = l * corr + pexp;
-        m = mn;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) acc[e] = acc[e] * corr + pv * vf[e];
-      }
+      for (int e = 0; e < 4; ++e)
+        dot += qf[2 * e] * kf[2 * e] + qf[2 * e + 1] * kf[2 * e + 1] + qf[8 + 2 * e] * kf[8 + 2 * e] +
+               qf[8 + 2 * e + 1] * kf[8 + 2 * e + 1];
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      float sc = dot * sl2;
+      if (!valid || (mrow != nullptr && mrow[key] == 0)) sc = -INFINITY;
+      return sc;
     };
-    for (int kb0 = k_lo; kb0 < k_hi; kb0 += 8 * UNR) {
+    // online-softmax update with two keys at once (P rounded to bf16 before P·V: softmax(...).to(bf16) @ v)
+    auto update2 = [&](float s0, float s1, const uint4& v00, const uint4& v01, const uint4& v10, const uint4& v11) {
+      const float mn = fmaxf(m, fmaxf(s0, s1));
+      const float msafe = (mn == -INFINITY) ? 0.0f : mn;
+      const float corr = exp2f(m - msafe);
+      const float p0 = exp2f(s0 - msafe), p1 = exp2f(s1 - msafe);
+      const float r0 = bf16_round(p0), r1 = bf16_round(p1);
+      l = l * corr + (p0 + p1);
+      m = mn;
+      float f0[16], f1[16];
+      unpack16(v00, v01, f0);
+      unpack16(v10, v11, f1);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) acc[e] = (acc[e] * corr + r0 * f0[e]) + r1 * f1[e];
+    };
+    auto compute_round = [&](int kb0, int w) {
+      const int key0 = kb0 + grp, key1 = kb0 + 4 + grp;
+      const bool v0 = key0 < k_end, v1 = key1 < k_end;
+      const float s0 = score(ka[w][0], kb[w][0], v0, v0 ? key0 : k_lo);
+      const float s1 = (kb0 + 4 < k_end) ? score(ka[w][1], kb[w][1], v1, v1 ? key1 : k_lo) : -INFINITY;
+      update2(s0, s1, va[w][0], vb[w][0], va[w][1], vb[w][1]);
+    };
+#pragma unroll 1
+    for (int kb0 = k_lo; kb0 < k_end; kb0 += 16) {
       compute_round(kb0, 0);
-      load_round(kb0 + 8 * UNR, 0);
-      if (kb0 + 4 * UNR < k_hi) {
-        compute_round(kb0 + 4 * UNR, 1);
-        load_round(kb0 + 12 * UNR, 1);
+      load_round(kb0 + 16, 0);
+      if (kb0 + 8 < k_end) {
+        compute_round(kb0 + 8, 1);
+        load_round(kb0 + 24, 1);
       }
     }
-  // merge the 4 key groups of the warp (lanes differing in bits 3,4)
-#pragma unroll
-  for (int sh = 8; sh <= 16; sh <<= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, sh);
-    const float l2 = __shfl_xor_sync(0xffffffffu, l, sh);
-    const float mn = fmaxf(m, m2);
-    const float msafe = (mn == -INFINITY) ? 0.0f : mn;
-    const float c1 = exp2f(m - msafe), c2 = exp2f(m2 - msafe);
-    l = l * c1 + l2 * c2;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const float a2 = __shfl_xor_sync(0xffffffffu, acc[e], sh);
-      acc[e] = acc[e] * c1 + a2 * c2;
+    if (pos >= k_lo && pos < it.k_hi) {
+      // the new position belongs to this split: rotate k, append k,v to the cache, add the key (all four lane groups
+      // compute the same score -- the shuffles need the whole warp -- but only group 0 accounts for it)
+      const __nv_bfloat16* krow = qrow + p.D;
+      const __nv_bfloat16* vrow = qrow + 2 * p.D;
+      uint4 kn0, kn1;
+      rope16(krow, cr, sr, gl, kn0, kn1);
+      const uint4 vn0 = *reinterpret_cast<const uint4*>(vrow + gl * 16);
+      const uint4 vn1 = *reinterpret_cast<const uint4*>(vrow + gl * 16 + 8);
+      if (grp == 0) {
+        __nv_bfloat16* kd = kc + static_cast<long long>(pos) * D + gl * 16;
+        *reinterpret_cast<uint4*>(kd) = kn0;
+        *reinterpret_cast<uint4*>(kd + 8) = kn1;
+        __nv_bfloat16* vd = vc + static_cast<long long>(pos) * D + gl * 16;
+        *reinterpret_cast<uint4*>(vd) = vn0;
+        *reinterpret_cast<uint4*>(vd + 8) = vn1;
+      }
+      const float s0 = score(kn0, kn1, grp == 0, pos);
+      // (ka[0][1] .. are dead here: any finite-free operand works for the absent second key, its weight is exp2(-inf) = 0)
+      update2(s0, -INFINITY, vn0, vn1, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0));
     }
-    m = mn;
-  }
-  __nv_bfloat16* optr = p.attn + static_cast<long long>(b) * p.D + h * D;
-  if (nsplit == 1) {
+    // merge the 4 key groups of the warp (lanes differing in bits 3,4)
+#pragma unroll
+    for (int sh = 8; sh <= 16; sh <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, sh);
+      const float l2 = __shfl_xor_sync(0xffffffffu, l, sh);
+      const float mn = fmaxf(m, m2);
+      const float msafe = (mn == -INFINITY) ? 0.0f : mn;
+      const float c1 = exp2f(m - msafe), c2 = exp2f(m2 - msafe);
+      l = l * c1 + l2 * c2;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float a2 = __shfl_xor_sync(0xffffffffu, acc[e], sh);
+        acc[e] = acc[e] * c1 + a2 * c2;
+      }
+      m = mn;
+    }
+    __nv_bfloat16* optr = p.attn + static_cast<long long>(it.b) * p.D + it.h * D;
+    if (nsplit == 1) {
+      if (grp == 0) {
+        const float inv = l > 0.0f ? __frcp_rn(l) : 0.0f;
+        uint4 o0, o1;
+        o0.x = pack_bf16(acc[0] * inv, acc[1] * inv); o0.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+        o0.z = pack_bf16(acc[4] * inv, acc[5] * inv); o0.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+        o1.x = pack_bf16(acc[8] * inv, acc[9] * inv); o1.y = pack_bf16(acc[10] * inv, acc[11] * inv);
+        o1.z = pack_bf16(acc[12] * inv, acc[13] * inv); o1.w = pack_bf16(acc[14] * inv, acc[15] * inv);
+        *reinterpret_cast<uint4*>(optr + gl * 16) = o0;
+        *reinterpret_cast<uint4*>(optr + gl * 16 + 8) = o1;
+      }
+      continue;
+    }
+    float* part = p.attn_part + static_cast<long long>(it.bh) * nsplit * (D + 4);
     if (grp == 0) {
-      const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-      uint4 o0, o1;
-      o0.x = pack_bf16(acc[0] * inv, acc[1] * inv); o0.y = pack_bf16(acc[2] * inv, acc[3] * inv);
-      o0.z = pack_bf16(acc[4] * inv, acc[5] * inv); o0.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-      o1.x = pack_bf16(acc[8] * inv, acc[9] * inv); o1.y = pack_bf16(acc[10] * inv, acc[11] * inv);
-      o1.z = pack_bf16(acc[12] * inv, acc[13] * inv); o1.w = pack_bf16(acc[14] * inv, acc[15] * inv);
-      *reinterpret_cast<uint4*>(optr + gl * 16) = o0;
-      *reinterpret_cast<uint4*>(optr + gl * 16 + 8) = o1;
-    }
-    continue;
-  }
-
-  float* part = p.attn_part + static_cast<long long>(bh) * nsplit * (D + 4);
-  if (grp == 0) {
-    float* mine = part + z * (D + 4);
+      float* mine = part + it.z * (D + 4);
 #pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4)
-      *reinterpret_cast<float4*>(mine + gl * 16 + q4 * 4) =
-          make_float4(acc[q4 * 4], acc[q4 * 4 + 1], acc[q4 * 4 + 2], acc[q4 * 4 + 3]);
-    if (gl == 0) {
-      mine[D] = m;
-      mine[D + 1] = l;
-    }
-  }
-  __threadfence();
-  __syncwarp();
-  int last = 0;
-  if (lane == 0) last = (atomicAdd(&p.attn_cnt[bh], 1) == nsplit - 1);
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) continue;
-  __threadfence();
-  // this warp merges all splits. Lane zz first fetches (max, sum) of split zz -- one round trip for all splits --
-  // then every lane accumulates its 4 dims over the splits with the loads of 8 splits in flight at a time.
-  const float mz = lane < nsplit ? __ldcg(part + lane * (D + 4) + D) : -INFINITY;
-  const float lz = lane < nsplit ? __ldcg(part + lane * (D + 4) + D + 1) : 0.0f;
-  const float gm = warp_max(mz);
-  const float gsafe = (gm == -INFINITY) ? 0.0f : gm;
-  const float cz = exp2f(mz - gsafe);  // 0 for absent / empty splits
-  const float gl_ = warp_sum(lz * cz);
-  float go[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int z0 = 0; z0 < nsplit; z0 += 8) {
-    float4 o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o[j] = z0 + j < nsplit ? __ldcg(reinterpret_cast<const float4*>(part + (z0 + j) * (D + 4) + lane * 4))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float c = __shfl_sync(0xffffffffu, cz, (z0 + j) & 31);
-      if (z0 + j < nsplit) {
-        go[0] += o[j].x * c;
-        go[1] += o[j].y * c;
-        go[2] += o[j].z * c;
-        go[3] += o[j].w * c;
+      for (int q4 = 0; q4 < 4; ++q4)
+        *reinterpret_cast<float4*>(mine + gl * 16 + q4 * 4) =
+            make_float4(acc[q4 * 4], acc[q4 * 4 + 1], acc[q4 * 4 + 2], acc[q4 * 4 + 3]);
+      if (gl == 0) {
+        mine[D] = m;
+        mine[D + 1] = l;
       }
     }
-  }
-  const float inv = gl_ > 0.0f ? 1.0f / gl_ : 0.0f;
-  uint2 o;
-  o.x = pack_bf16(go[0] * inv, go[1] * inv);
-  o.y = pack_bf16(go[2] * inv, go[3] * inv);
-  *reinterpret_cast<uint2*>(optr + lane * 4) = o;
-  if (lane == 0) p.attn_cnt[bh] = 0;  // self-cleaning for the next layer / launch
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&p.attn_cnt[it.bh], 1) == nsplit - 1);
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) continue;
+    __threadfence();
+    // this warp merges all splits. Lane zz first fetches (max, sum) of split zz -- one round trip for all splits --
+    // then every lane accumulates its 4 dims over the splits, 8 splits' loads in flight at a time.
+    const float mz = lane < nsplit ? __ldcg(part + lane * (D + 4) + D) : -INFINITY;
+    const float lz = lane < nsplit ? __ldcg(part + lane * (D + 4) + D + 1) : 0.0f;
+    const float gm = warp_max(mz);
+    const float gsafe = (gm == -INFINITY) ? 0.0f : gm;
+    const float cz = exp2f(mz - gsafe);  // 0 for absent / empty splits
+    const float gl_ = warp_sum(lz * cz);
+    float go[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int z0 = 0; z0 < nsplit; z0 += 8) {
+      float4 o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = z0 + j < nsplit ? __ldcg(reinterpret_cast<const float4*>(part + (z0 + j) * (D + 4) + lane * 4))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float c = __shfl_sync(0xffffffffu, cz, (z0 + j) & 31);
+        if (z0 + j < nsplit) {
+          go[0] += o[j].x * c;
+          go[1] += o[j].y * c;
+          go[2] += o[j].z * c;
+          go[3] += o[j].w * c;
+        }
+      }
+    }
+    const float inv = gl_ > 0.0f ? __frcp_rn(gl_) : 0.0f;
+    uint2 o;
+    o.x = pack_bf16(go[0] * inv, go[1] * inv);
+    o.y = pack_bf16(go[2] * inv, go[3] * inv);
+    *reinterpret_cast<uint2*>(optr + lane * 4) = o;
+    if (lane == 0) p.attn_cnt[it.bh] = 0;  // self-cleaning for the next layer / launch
   }
 }
 
@@ -642,7 +566,10 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
     mbar_init(wg_bar, 1);
     mbar_init(lnin_bar, 1);
     fence_mbar_init();
-    rt->pf_kn = rt->pf_ex = rt->pf_route = 0;
+    rt->pf_pos = rt->pf_route = 0;
+    rt->nact = 1;
+    rt->act[0] = 0;
+    rt->amask = 1u;
     rt->pf_amask[0] = rt->pf_amask[1] = rt->pf_amask[2] = rt->pf_amask[3] = 1u;
   }
   __syncthreads();
@@ -655,398 +582,479 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
 
   if (warp == DK_CONSUMERS) {
     // ============================================================ producer: the whole step's weight schedule
+    // publishes its position (layer << 16 | chunks issued in this layer) for the L2 prefetcher
     if (lane != 0) return;
     uint32_t route_phase = 0;
-    unsigned int kn = 0;
-    volatile unsigned int* pf_kn = &rt->pf_kn;
-    volatile unsigned int* pf_ex = &rt->pf_ex;
+    volatile unsigned int* pf_pos = &rt->pf_pos;
+    uint64_t policy = 0;
+    if (p.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     for (int l = 0; l < p.L; ++l) {
       const DecLayerDev* L = p.layers + l;
+      unsigned int pos = static_cast<unsigned int>(l) << 16;
+      *pf_pos = pos;
       for (int tile = blockIdx.x; tile < 3 * tiles_d; tile += G) {
         const int which = tile / tiles_d;
         const CUtensorMap* tm = which == 0 ? &L->wq : (which == 1 ? &L->wk : &L->wv);
-        produce_tile(ring, tm, nullptr, (tile % tiles_d) * 16, chunks_d, pf_kn, kn);
+        produce_tile(ring, tm, nullptr, (tile % tiles_d) * 16, chunks_d, pf_pos, pos, policy);
       }
       for (int tile = blockIdx.x; tile < tiles_d; tile += G)
-        produce_tile(ring, &L->wo, nullptr, tile * 16, chunks_d, pf_kn, kn);
+        produce_tile(ring, &L->wo, nullptr, tile * 16, chunks_d, pf_pos, pos, policy);
       mbar_wait(route_bar, route_phase);  // expert choice of this layer
       route_phase ^= 1;
-      const unsigned int amask = rt->amask;
-      const int nact = __popc(amask);
-      unsigned int ex = static_cast<unsigned int>(l) << 16;
-      *pf_ex = ex;
+      const int nact = rt->nact;
       for (int tile = blockIdx.x; tile < nact * tiles_f; tile += G) {
-        const int e = __fns(amask, 0, tile / tiles_f + 1);
-        produce_tile(ring, &L->wgate[e], &L->wup[e], (tile % tiles_f) * 8, chunks_d, pf_ex, ex);
+        const int e = rt->act[tile / tiles_f];
+        produce_tile(ring, &L->wgate[e], &L->wup[e], (tile % tiles_f) * 8, chunks_d, pf_pos, pos, policy);
       }
       for (int tile = blockIdx.x; tile < nact * tiles_d; tile += G) {
-        const int e = __fns(amask, 0, tile / tiles_d + 1);
-        produce_tile(ring, &L->wdown[e], nullptr, (tile % tiles_d) * 16, chunks_f, pf_ex, ex);
+        const int e = rt->act[tile / tiles_d];
+        produce_tile(ring, &L->wdown[e], nullptr, (tile % tiles_d) * 16, chunks_f, pf_pos, pos, policy);
       }
     }
+    *pf_pos = static_cast<unsigned int>(p.L) << 16;
     return;
   }
   if (warp == DK_CONSUMERS + 1) {
     // ============================================================ L2 prefetcher
-    // Walks the same per-CTA tile schedule as the producer, a bounded number of 16 KB chunks AHEAD of it, with
-    // cp.async.bulk.prefetch.tensor (HBM -> L2, fire and forget): while the consumers sit in a grid barrier, the
-    // attention phase, activation staging or the router -- when the 6-stage ring is full and the producer is blocked --
-    // HBM keeps streaming into L2, and the ring refills from L2 afterwards. Two independent cursors:
-    //   known stream   q,k,v,o tiles of ALL layers (never depends on data): up to p.kla chunks ahead, across layers;
-    //   expert stream  gate/up/down tiles of one layer: needs that layer's expert choice (or, with p.spec, assumes every
-    //                  expert is hit -- B >= 4 -- and starts early): up to p.ela chunks ahead.
-    // Every wait is a poll of a monotonic shared-memory counter that the producer / consumers advance no matter what
-    // this thread does, a cursor that has fallen behind jumps forward, so the thread cannot block anyone and always exits.
-    if (lane != 0 || (p.kla <= 0 && p.ela <= 0)) return;
+    // Walks the same per-CTA chunk schedule as the producer, IN CONSUMPTION ORDER, at most p.la 16 KB chunks ahead of
+    // it, with cp.async.bulk.prefetch.tensor (HBM -> L2, fire and forget). While the consumers sit in a grid barrier,
+    // the attention phase, activation staging or the tail of an unbalanced phase -- the 6-stage ring is full and the
+    // producer is blocked -- HBM keeps streaming the next chunks into L2 and the ring refills from there. (Measured:
+    // prefetching further ahead than ~40 MB across the grid, or out of consumption order, is evicted before its use
+    // and doubles the traffic.) The expert tiles of a layer need its routing decision: with p.spec (B >= 4: every
+    // expert is hit almost surely) the cursor walks on assuming all experts, otherwise it waits for the decision.
+    // Every wait polls a monotonic shared-memory word that the producer / consumers advance regardless of this thread,
+    // and a cursor that has fallen behind jumps forward: the thread can neither block anyone nor fail to exit.
+    if (lane != 0 || p.la <= 0) return;
     const int bid = blockIdx.x;
     auto cnt = [&](int total) { return total > bid ? (total - bid + G - 1) / G : 0; };
     const int n1 = cnt(3 * tiles_d), n3 = cnt(tiles_d);
-    const unsigned int per_layer = static_cast<unsigned int>((n1 + n3) * chunks_d);
-    const unsigned int total_known = p.kla > 0 ? per_layer * static_cast<unsigned int>(p.L) : 0u;
-    const unsigned int kla = static_cast<unsigned int>(p.kla), ela = static_cast<unsigned int>(p.ela);
+    const unsigned int nk = static_cast<unsigned int>((n1 + n3) * chunks_d);
+    const unsigned int la = static_cast<unsigned int>(p.la);
     volatile RouteSmem* vr = rt;
-    unsigned int kn_pf = 0, ex_pf = 0;
-    int le = p.ela > 0 ? 0 : p.L;
-    while (kn_pf < total_known || le < p.L) {
-      bool progress = false;
-      if (le < p.L) {
-        const bool known = static_cast<int>(vr->pf_route) > le;
-        if (known || p.spec) {
-          const DecLayerDev* Lp = p.layers + le;
-          const int E = Lp->wg != nullptr ? Lp->n_experts : 1;
-          unsigned int amask = known ? vr->pf_amask[le & 3] : ((1u << E) - 1u);
-          amask &= (1u << E) - 1u;
-          if (amask == 0) amask = 1u;
-          const int nact = __popc(amask);
-          const int n5 = cnt(nact * tiles_f), n6 = cnt(nact * tiles_d);
-          const unsigned int c5 = static_cast<unsigned int>(n5 * chunks_d);
-          const unsigned int total_e = c5 + static_cast<unsigned int>(n6 * chunks_f);
-          const unsigned int pos = vr->pf_ex;
-          const int ll = static_cast<int>(pos >> 16);
-          if (ll > le) {  // the producer is already past this layer
-            ++le;
-            ex_pf = 0;
-            progress = true;
-          } else {
-            const unsigned int base = ll == le ? (pos & 0xffffu) : 0u;
-            if (ex_pf < base) ex_pf = base;
-            if (ex_pf < total_e && ex_pf < base + ela) {
-              if (ex_pf < c5) {
-                const int tile = bid + static_cast<int>(ex_pf / chunks_d) * G, c = static_cast<int>(ex_pf % chunks_d);
-                const int e = __fns(amask, 0, tile / tiles_f + 1) & (DK_MAXE - 1);
-                tma_prefetch_3d(&Lp->wgate[e], 0, (tile % tiles_f) * 8, c * (DK_KC / 64));
-                tma_prefetch_3d(&Lp->wup[e], 0, (tile % tiles_f) * 8, c * (DK_KC / 64));
-              } else {
-                const unsigned int r = ex_pf - c5;
-                const int tile = bid + static_cast<int>(r / chunks_f) * G, c = static_cast<int>(r % chunks_f);
-                const int e = __fns(amask, 0, tile / tiles_d + 1) & (DK_MAXE - 1);
-                tma_prefetch_3d(&Lp->wdown[e], 0, (tile % tiles_d) * 16, c * (DK_KC / 64));
-              }
-              ++ex_pf;
-              progress = true;
-            }
-            if (ex_pf >= total_e) {
-              ++le;
-              ex_pf = 0;
-              progress = true;
-            }
-          }
-        }
+    int pl = 0;            // cursor: layer, chunk within the layer
+    unsigned int poff = 0;
+    int cur_l = -1, cur_E = 1;  // cached per-layer facts
+    auto experts_of = [&](int layer) {
+      if (layer != cur_l) {
+        const DecLayerDev* Lp = p.layers + layer;
+        cur_E = Lp->wg != nullptr ? Lp->n_experts : 1;
+        cur_l = layer;
       }
-      if (kn_pf < total_known) {
-        const unsigned int kl = vr->pf_kn;
-        if (kn_pf < kl) kn_pf = kl;
-        if (kn_pf < total_known && kn_pf < kl + kla) {
-          const DecLayerDev* Lp = p.layers + kn_pf / per_layer;
-          const unsigned int r = kn_pf % per_layer;
-          const int ti = static_cast<int>(r / chunks_d), c = static_cast<int>(r % chunks_d);
-          if (ti < n1) {
-            const int tile = bid + ti * G, which = tile / tiles_d;
-            const CUtensorMap* tm = which == 0 ? &Lp->wq : (which == 1 ? &Lp->wk : &Lp->wv);
-            tma_prefetch_3d(tm, 0, (tile % tiles_d) * 16, c * (DK_KC / 64));
-          } else {
-            tma_prefetch_3d(&Lp->wo, 0, (bid + (ti - n1) * G) * 16, c * (DK_KC / 64));
-          }
-          ++kn_pf;
-          progress = true;
-        }
+      return cur_E;
+    };
+    // chunks of layer `layer`'s expert part under mask `amask`
+    auto expert_chunks = [&](unsigned int amask, unsigned int& c5) {
+      const int nact = __popc(amask);
+      c5 = static_cast<unsigned int>(cnt(nact * tiles_f) * chunks_d);
+      return c5 + static_cast<unsigned int>(cnt(nact * tiles_d) * chunks_f);
+    };
+    auto mask_of = [&](int layer, bool& known) {
+      const int E = experts_of(layer);
+      const unsigned int full = (1u << E) - 1u;
+      known = static_cast<int>(vr->pf_route) > layer;
+      unsigned int m = known ? (vr->pf_amask[layer & 3] & full) : full;
+      return m != 0 ? m : 1u;
+    };
+    while (pl < p.L) {
+      const unsigned int lv = vr->pf_pos;
+      const int ll = static_cast<int>(lv >> 16);
+      const unsigned int loff = lv & 0xffffu;
+      if (ll >= p.L) break;
+      if (pl < ll || (pl == ll && poff < loff)) {  // fell behind the producer: jump to it
+        pl = ll;
+        poff = loff;
       }
-      if (!progress) __nanosleep(100);
+      // distance to the producer in chunks (the cursor is never more than one layer ahead)
+      unsigned int dist;
+      if (pl == ll) {
+        dist = poff - loff;
+      } else {
+        bool kn;
+        unsigned int c5;
+        const unsigned int end_ll = nk + expert_chunks(mask_of(ll, kn), c5);
+        dist = poff + (end_ll > loff ? end_ll - loff : 0u);
+        if (pl > ll + 1) dist = la;  // cannot happen (la << chunks per layer); be safe
+      }
+      if (dist >= la) {
+        __nanosleep(64);
+        continue;
+      }
+      const DecLayerDev* Lp = p.layers + pl;
+      if (poff < nk) {
+        const int ti = static_cast<int>(poff / chunks_d), c = static_cast<int>(poff % chunks_d);
+        if (ti < n1) {
+          const int tile = bid + ti * G, which = tile / tiles_d;
+          const CUtensorMap* tm = which == 0 ? &Lp->wq : (which == 1 ? &Lp->wk : &Lp->wv);
+          tma_prefetch_3d(tm, 0, (tile % tiles_d) * 16, c * (DK_KC / 64));
+        } else {
+          tma_prefetch_3d(&Lp->wo, 0, (bid + (ti - n1) * G) * 16, c * (DK_KC / 64));
+        }
+        ++poff;
+        continue;
+      }
+      bool known;
+      const unsigned int amask = mask_of(pl, known);
+      if (!known && !p.spec) {
+        __nanosleep(64);
+        continue;
+      }
+      unsigned int c5;
+      const unsigned int total_e = expert_chunks(amask, c5);
+      const unsigned int ex = poff - nk;
+      if (ex >= total_e) {
+        ++pl;
+        poff = 0;
+        continue;
+      }
+      if (ex < c5) {
+        const int tile = bid + static_cast<int>(ex / chunks_d) * G, c = static_cast<int>(ex % chunks_d);
+        const int e = __fns(amask, 0, tile / tiles_f + 1) & (DK_MAXE - 1);
+        tma_prefetch_3d(&Lp->wgate[e], 0, (tile % tiles_f) * 8, c * (DK_KC / 64));
+        tma_prefetch_3d(&Lp->wup[e], 0, (tile % tiles_f) * 8, c * (DK_KC / 64));
+      } else {
+        const unsigned int r = ex - c5;
+        const int tile = bid + static_cast<int>(r / chunks_f) * G, c = static_cast<int>(r % chunks_f);
+        const int e = __fns(amask, 0, tile / tiles_d + 1) & (DK_MAXE - 1);
+        tma_prefetch_3d(&Lp->wdown[e], 0, (tile % tiles_d) * 16, c * (DK_KC / 64));
+      }
+      ++poff;
     }
     return;
   }
 
   // ============================================================== consumers
-  const int g = lane >> 2;
+  // ONE loop over (layer, step) with a single instance of every piece of code (see the header: cold code is fetched at
+  // L2 latency, so size and straight-line-ness decide the time between the weight phases).
+  const int g = lane >> 2, t4 = lane & 3;
   unsigned int bar_target = 0;
   int buf = 0;
-  const ActStage act{s_a, pitch};
   uint32_t wg_phase = 0, lnin_phase = 0;
-  if (threadIdx.x == 0) {  // input norm weight of layer 0
+  const int k0 = threadIdx.x * 8, k1 = (threadIdx.x + DK_CONSUMERS * 32) * 8;  // this thread's two 8-element slices
+  const bool in0 = k0 < D, in1 = k1 < D;
+  const float inv_d = 1.0f / static_cast<float>(D);  // exact for the power-of-two widths
+  // small per-layer weights (post-attention norm + router) go to shared memory one layer ahead
+  auto issue_small = [&](int layer) {
+    const DecLayerDev* Ln = p.layers + layer;
+    const float* wgn = Ln->wg;
+    const int En = wgn != nullptr ? Ln->n_experts : 1;
+    const bool fits = wgn != nullptr && static_cast<long long>(En) * D * 4 <= DK_WG_SMEM;
+    fence_proxy_async();
+    mbar_expect_tx(wg_bar, static_cast<uint32_t>(D * 2 + (fits ? En * D * 4 : 0)));
+    dk_bulk_g2s(s_ln_post, Ln->post_ln, static_cast<uint32_t>(D * 2), wg_bar);
+    if (fits)
+      for (int e = 0; e < En; ++e) dk_bulk_g2s(s_wg + e * D, wgn + static_cast<long long>(e) * D, D * 4, wg_bar);
+  };
+  if (threadIdx.x == 0) {
     mbar_expect_tx(lnin_bar, static_cast<uint32_t>(D * 2));
     dk_bulk_g2s(s_ln_in, p.layers[0].input_ln, static_cast<uint32_t>(D * 2), lnin_bar);
+    issue_small(0);
   }
   const int pos = p.pos_dev ? *p.pos_dev : p.pos;
   const int Tk = pos + 1;
-  for (int l = 0; l < p.L; ++l) {
-    const DecLayerDev* L = p.layers + l;
-    DK_STAMP(0);
-    const int E = L->wg != nullptr ? L->n_experts : 1;
-    const bool wg_smem = L->wg != nullptr && static_cast<long long>(E) * D * 4 <= DK_WG_SMEM;
-    if (threadIdx.x == 0) {  // small weights of this layer: in shared memory long before P4 needs them
-      fence_proxy_async();
-      mbar_expect_tx(wg_bar, static_cast<uint32_t>(D * 2 + (wg_smem ? E * D * 4 : 0)));
-      dk_bulk_g2s(s_ln_post, L->post_ln, static_cast<uint32_t>(D * 2), wg_bar);
-      if (wg_smem)
-        for (int e = 0; e < E; ++e) dk_bulk_g2s(s_wg + e * D, L->wg + static_cast<long long>(e) * D, D * 4, wg_bar);
-    }
-    // ---------------------------------------------------------- P1: q,k,v = RMSNorm(x) Wqkv^T
-    unsigned long long* const tsp =
-        (l == p.timing_layer && threadIdx.x == 0 && blockIdx.x < 160) ? g_dk_times + blockIdx.x * DK_TSLOTS : nullptr;
-    DK_STAMP(14);
-    stage_rows(act, p.x, s_ln_in, lnin_bar, lnin_phase, B, D, p.eps, red, tsp != nullptr ? tsp + 15 : nullptr);
-    lnin_phase ^= 1;
-    consumer_sync();
-    DK_STAMP(1);
-    {
-      const __nv_bfloat16* arow = g < B ? reinterpret_cast<const __nv_bfloat16*>(s_a + g * pitch) : nullptr;
-      for (int tile = blockIdx.x; tile < 3 * tiles_d; tile += G) {
-        float* rbuf = red + buf * DK_RED_FLOATS;
-        buf ^= 1;
-        consume_tile<false>(ring, chunks_d, D, arow, rbuf);
-        const int which = tile / tiles_d, n0 = (tile % tiles_d) * 16;
-        if (threadIdx.x < 16 * DK_MAXB) {
-          const int r = threadIdx.x & 15, m = threadIdx.x >> 4;
-          if (m < B && n0 + r < D)
-            p.qkv[static_cast<long long>(m) * 3 * D + which * D + n0 + r] = __float2bfloat16_rn(reduce_rows(rbuf, r, m));
-        }
-      }
-    }
-    // ---------------------------------------------------------- P2 (includes the grid barrier that ends P1)
-    attention_phase(p, l, Tk, bar_target);
-    DK_STAMP(4);
-    grid_sync(p.sync, bar_target);
-    DK_STAMP(5);
-    // ---------------------------------------------------------- P3: x += attn Wo^T
-    stage_rows(act, p.attn, nullptr, nullptr, 0u, B, D, p.eps, red);
-    if (threadIdx.x == 0) {  // s_ln_in is free (all CTA threads are past P1's staging): next layer's input norm weight
-      fence_proxy_async();
-      mbar_expect_tx(lnin_bar, static_cast<uint32_t>(D * 2));
-      dk_bulk_g2s(s_ln_in, l + 1 < p.L ? p.layers[l + 1].input_ln : p.final_norm, static_cast<uint32_t>(D * 2), lnin_bar);
-    }
-    consumer_sync();
-    DK_STAMP(6);
-    {
-      const __nv_bfloat16* arow = g < B ? reinterpret_cast<const __nv_bfloat16*>(s_a + g * pitch) : nullptr;
-      for (int tile = blockIdx.x; tile < tiles_d; tile += G) {
-        float* rbuf = red + buf * DK_RED_FLOATS;
-        buf ^= 1;
-        consume_tile<false>(ring, chunks_d, D, arow, rbuf);
-        const int n0 = tile * 16;
-        if (threadIdx.x < 16 * DK_MAXB) {
-          const int r = threadIdx.x & 15, m = threadIdx.x >> 4;
-          if (m < B && n0 + r < D) {
-            __nv_bfloat16* xp = p.x + static_cast<long long>(m) * D + n0 + r;
-            *xp = __float2bfloat16_rn(bf16_round(reduce_rows(rbuf, r, m)) + __bfloat162float(*xp));
-          }
-        }
-      }
-    }
-    DK_STAMP(7);
-    grid_sync(p.sync, bar_target);
-    DK_STAMP(8);
-    // ---------------------------------------------------------- P4: h = RMSNorm(x), router (every CTA, no barrier)
-    stage_rows(act, p.x, s_ln_post, wg_bar, wg_phase, B, D, p.eps, red,
-               tsp != nullptr ? tsp + 20 : nullptr);  // (wg_bar also covers the router weights)
-    wg_phase ^= 1;
-    DK_STAMP(25);
-    if (L->wg != nullptr) {
-      // router logits from the stored (bf16-rounded) h, fp32 like DeepSpeed's TopKGate; all 8 warps share every row
-      // (thread t owns k = 8t, 8t + 2048, ...), partial sums reduced lane -> warp -> CTA in a fixed order
-      const float* wgp = wg_smem ? s_wg : L->wg;  // generic pointer: shared-memory copy when it fits
-      float* s_rp = red + 64;                     // [B][DK_MAXE][8 warps]
+  const float* wg_l = nullptr;
+  int E = 1;
+  bool wg_smem = false;
+  const int n_steps = 4 * p.L + (p.out_norm != nullptr && blockIdx.x == 0 ? 1 : 0);  // + the final RMSNorm (CTA 0)
 #pragma unroll 1
-      for (int e0 = 0; e0 < E; e0 += 2)
+  for (int it = 0; it < n_steps; ++it) {
+    const int l = it >> 2, step = it & 3;
+    const bool fin = l >= p.L;  // final norm pseudo-step
+    const DecLayerDev* L = p.layers + (fin ? p.L - 1 : l);
+    DK_STAMP(step * 4);
+    if (step == 0 && !fin) {  // (loads that step 2 needs: issued here, long before)
+      wg_l = L->wg;
+      E = wg_l != nullptr ? L->n_experts : 1;
+      wg_smem = wg_l != nullptr && static_cast<long long>(E) * D * 4 <= DK_WG_SMEM;
+    }
+    // ---------------------------------------------------------------------------------------------- staging
+    // steps 0 / 2: RMSNorm(x) rows; step 1: attention output rows; step 3: nothing (its A operand is h1 in global memory)
+    if (step != 3) {
+      const __nv_bfloat16* src = step == 1 ? p.attn : p.x;
+      // global (L2) -> shared memory with 16-byte cp.async copies, all rows in flight at once: one L2 round trip and no
+      // registers held meanwhile (10 warps on 4 schedulers cap a thread at 168 registers)
 #pragma unroll 1
-      for (int m0 = 0; m0 < B; m0 += 4) {
-        float acc[4][2];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) acc[m][0] = acc[m][1] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c = (threadIdx.x + j * DK_CONSUMERS * 32) * 8;
-          if (c < D) {
-            float4 wv[2][2];
-#pragma unroll
-            for (int ee = 0; ee < 2; ++ee) {
-              const int e = min(e0 + ee, E - 1);
-              wv[ee][0] = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + c);
-              wv[ee][1] = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + c + 4);
-            }
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              if (m0 + m < B) {
-                const uint4 raw = *reinterpret_cast<const uint4*>(s_a + (m0 + m) * pitch + c * 2);
-                const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
-                float xv[8];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 f = __bfloat1622float2(hp[i]);
-                  xv[2 * i] = f.x;
-                  xv[2 * i + 1] = f.y;
-                }
-#pragma unroll
-                for (int ee = 0; ee < 2; ++ee) {
-                  const float4 w0 = wv[ee][0], w1 = wv[ee][1];
-                  acc[m][ee] += xv[0] * w0.x + xv[1] * w0.y + xv[2] * w0.z + xv[3] * w0.w + xv[4] * w1.x +
-                                xv[5] * w1.y + xv[6] * w1.z + xv[7] * w1.w;
-                }
-              }
-            }
-          }
+      for (int r = 0; r < B; ++r) {
+        const __nv_bfloat16* row = src + static_cast<long long>(r) * D;
+        if (in0)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_a + r * pitch + k0 * 2)),
+                       "l"(row + k0)
+                       : "memory");
+        if (in1)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_a + r * pitch + k1 * 2)),
+                       "l"(row + k1)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (step == 1) {
+        if (threadIdx.x == 0) {  // s_ln_in is free (every thread is past step 0's staging): next layer's input norm
+          fence_proxy_async();
+          mbar_expect_tx(lnin_bar, static_cast<uint32_t>(D * 2));
+          dk_bulk_g2s(s_ln_in, l + 1 < p.L ? p.layers[l + 1].input_ln : p.final_norm, static_cast<uint32_t>(D * 2),
+                      lnin_bar);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            acc[m][0] += __shfl_xor_sync(0xffffffffu, acc[m][0], o);
-            acc[m][1] += __shfl_xor_sync(0xffffffffu, acc[m][1], o);
-          }
-        if (lane == 0) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            if (m0 + m < B) {
-              s_rp[((m0 + m) * DK_MAXE + e0) * DK_CONSUMERS + warp] = acc[m][0];
-              if (e0 + 1 < E) s_rp[((m0 + m) * DK_MAXE + e0 + 1) * DK_CONSUMERS + warp] = acc[m][1];
-            }
-          }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else {
+        const uint8_t* s_ln = step == 0 ? s_ln_in : s_ln_post;
+        if (step == 0) {
+          mbar_wait(lnin_bar, lnin_phase);
+          lnin_phase ^= 1;
+        } else {
+          mbar_wait(wg_bar, wg_phase);  // (also covers the router weights)
+          wg_phase ^= 1;
+        }
+        const uint4 w0 = in0 ? lds_v4(s_ln + k0 * 2) : make_uint4(0, 0, 0, 0);
+        const uint4 w1 = in1 ? lds_v4(s_ln + k1 * 2) : make_uint4(0, 0, 0, 0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // sum of squares of this thread's slices, row by row; lane -> warp (shuffles) -> CTA (fixed order 0..7)
+#pragma unroll 1
+        for (int r = 0; r < B; ++r) {
+          float ss = 0.0f;
+          if (in0) ss = sumsq8(lds_v4(s_a + r * pitch + k0 * 2), ss);
+          if (in1) ss = sumsq8(lds_v4(s_a + r * pitch + k1 * 2), ss);
+          ss = warp_sum(ss);
+          if (lane == 0) red[r * DK_CONSUMERS + warp] = ss;
+        }
+        consumer_sync();
+#pragma unroll 1
+        for (int r = 0; r < B; ++r) {
+          const float4 p0 = *reinterpret_cast<const float4*>(red + r * DK_CONSUMERS);
+          const float4 p1 = *reinterpret_cast<const float4*>(red + r * DK_CONSUMERS + 4);
+          const float tot = ((((((p0.x + p0.y) + p0.z) + p0.w) + p1.x) + p1.y) + p1.z) + p1.w;
+          const float rstd = rsqrtf(__fmul_rn(tot, inv_d) + p.eps);
+          if (in0) sts_v4(s_a + r * pitch + k0 * 2, norm8(lds_v4(s_a + r * pitch + k0 * 2), w0, rstd));
+          if (in1) sts_v4(s_a + r * pitch + k1 * 2, norm8(lds_v4(s_a + r * pitch + k1 * 2), w1, rstd));
         }
       }
-      consumer_sync();
-      if (threadIdx.x < B * E) {
-        const int m = threadIdx.x / E, e = threadIdx.x % E;
-        float t = 0.0f;
-#pragma unroll
-        for (int w = 0; w < DK_CONSUMERS; ++w) t += s_rp[(m * DK_MAXE + e) * DK_CONSUMERS + w];
-        rt->logits[m][e] = t;
-      }
-      consumer_sync();
-      if (threadIdx.x < B) {
-        const int m = threadIdx.x;
-        float mx = -INFINITY;
-        for (int e = 0; e < E; ++e) mx = fmaxf(mx, rt->logits[m][e]);
-        float sum = 0.0f;
-        for (int e = 0; e < E; ++e) sum += expf(rt->logits[m][e] - mx);
-        for (int e = 0; e < E; ++e) rt->gates[m][e] = expf(rt->logits[m][e] - mx) / sum;
+      if (fin) {  // hidden_states[-1] = RMSNorm(x) with the final norm weight (CTA 0 only)
+        consumer_sync();
+        for (int i = threadIdx.x; i < B * (D / 8); i += DK_CONSUMERS * 32) {
+          const int m = i / (D / 8), c = (i % (D / 8)) * 8;
+          *reinterpret_cast<uint4*>(p.out_norm + static_cast<long long>(m) * D + c) = lds_v4(s_a + m * pitch + c * 2);
+        }
+        break;
       }
     }
-    consumer_sync();
-    DK_STAMP(26);
-    if (threadIdx.x == 0) {
-      // top-1 + capacity slots in token order (torch.cumsum), as moe_scan_kernel / moe_route_small_kernel
-      const bool moe = L->wg != nullptr;
-      const int C = p.cap[E];
-      // (counters live in shared memory: a dynamically indexed local array would sit in local memory, i.e. L2)
-      int* cnt = rt->cnt;
-      float* me = rt->me;
-      for (int e = 0; e < E; ++e) cnt[e] = 0, me[e] = 0.0f, rt->kept[e] = 0;
-      for (int s = 0; s < B; ++s) {
-        int i1 = 0;
-        float gsel = 1.0f;
-        if (moe) {
-          float best = rt->gates[s][0];
-          for (int e = 0; e < E; ++e) {
-            me[e] += rt->gates[s][e];
-            if (rt->gates[s][e] > best) best = rt->gates[s][e], i1 = e;
-          }
-          gsel = best;
-        }
-        const int loc = cnt[i1]++;
-        if (loc < C || !moe) {
-          rt->tok_of_slot[i1][loc] = s;
-          rt->gate_of_slot[i1][loc] = gsel;
-          rt->kept[i1] = loc + 1;
-        }
-      }
-      unsigned int am = 0;
-      for (int e = 0; e < E; ++e)
-        if (rt->kept[e] > 0) am |= 1u << e;
-      rt->amask = am;
-      rt->moe = moe ? 1 : 0;
-      rt->pf_amask[l & 3] = am;
-      __threadfence_block();
-      *const_cast<volatile unsigned int*>(&rt->pf_route) = static_cast<unsigned int>(l) + 1u;
-      if (moe && blockIdx.x == 0) {
-        float aux = 0.0f;
+    // ---------------------------------------------------------------------------------------------- router (step 2)
+    if (step == 2) {
+      DK_STAMP(23);
+      if (wg_l != nullptr) {
+        // logits from the stored (bf16-rounded) h in fp32 like DeepSpeed's TopKGate. Thread t owns the two slices it
+        // has just written (its own shared-memory stores: readable without a barrier); partial sums lane -> warp
+        // (shuffles) -> CTA (fixed order 0..7, by the thread that owns the row)
+        const float* wgp = wg_smem ? s_wg : wg_l;  // generic pointer: shared-memory copy when it fits
+        float* s_rp = red + 64;                    // [B][DK_MAXE][8 warps]
+#pragma unroll 1
         for (int e = 0; e < E; ++e) {
-          aux += (me[e] / B) * (static_cast<float>(cnt[e]) / B);
-          if (p.exp_counts != nullptr) p.exp_counts[l * p.Emax + e] = cnt[e];
+          float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa, wc = wa, wd = wa;
+          if (in0) {
+            wa = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + k0);
+            wb = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + k0 + 4);
+          }
+          if (in1) {
+            wc = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + k1);
+            wd = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + k1 + 4);
+          }
+#pragma unroll 1
+          for (int m = 0; m < B; ++m) {
+            float acc = 0.0f;
+            auto dot8 = [&](const uint4& raw, const float4& a0, const float4& a1) {
+              const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+              const float2 f0 = __bfloat1622float2(hp[0]), f1 = __bfloat1622float2(hp[1]);
+              const float2 f2 = __bfloat1622float2(hp[2]), f3 = __bfloat1622float2(hp[3]);
+              acc += f0.x * a0.x + f0.y * a0.y + f1.x * a0.z + f1.y * a0.w + f2.x * a1.x + f2.y * a1.y + f3.x * a1.z +
+                     f3.y * a1.w;
+            };
+            if (in0) dot8(lds_v4(s_a + m * pitch + k0 * 2), wa, wb);
+            if (in1) dot8(lds_v4(s_a + m * pitch + k1 * 2), wc, wd);
+            acc = warp_sum(acc);
+            if (lane == 0) s_rp[(m * DK_MAXE + e) * DK_CONSUMERS + warp] = acc;
+          }
         }
-        if (p.l_aux != nullptr) p.l_aux[l] = aux * E;
-        if (p.gate_logits != nullptr)
-          for (int s = 0; s < B; ++s)
-            for (int e = 0; e < E; ++e) p.gate_logits[static_cast<long long>(l) * B * p.Emax + s * E + e] = rt->logits[s][e];
+        consumer_sync();
+        if (threadIdx.x < B) {  // the thread that owns row m: logits, softmax (rows 0..7 all live in warp 0)
+          const int m = threadIdx.x;
+          float mx = -INFINITY;
+          for (int e = 0; e < E; ++e) {
+            float v = 0.0f;
+#pragma unroll
+            for (int w = 0; w < DK_CONSUMERS; ++w) v += s_rp[(m * DK_MAXE + e) * DK_CONSUMERS + w];
+            rt->logits[m][e] = v;
+            mx = fmaxf(mx, v);
+          }
+          float sum = 0.0f;
+          for (int e = 0; e < E; ++e) sum += expf(rt->logits[m][e] - mx);
+          for (int e = 0; e < E; ++e) rt->gates[m][e] = expf(rt->logits[m][e] - mx) / sum;
+        }
+        if (warp == 0) __syncwarp();
       }
-      mbar_arrive(route_bar);  // release: the producer may read the expert choice
+      DK_STAMP(24);
+      if (threadIdx.x == 0) {
+        // top-1 + capacity slots in token order (torch.cumsum), as moe_scan_kernel / moe_route_small_kernel
+        const bool moe = wg_l != nullptr;
+        const int C = p.cap[E];
+        // (counters live in shared memory: a dynamically indexed local array would sit in local memory, i.e. L2)
+        int* cnt = rt->cnt;
+        float* me = rt->me;
+        for (int e = 0; e < E; ++e) cnt[e] = 0, me[e] = 0.0f, rt->kept[e] = 0;
+        for (int sq = 0; sq < B; ++sq) {
+          int i1 = 0;
+          float gsel = 1.0f;
+          if (moe) {
+            float best = rt->gates[sq][0];
+            for (int e = 0; e < E; ++e) {
+              me[e] += rt->gates[sq][e];
+              if (rt->gates[sq][e] > best) best = rt->gates[sq][e], i1 = e;
+            }
+            gsel = best;
+          }
+          const int loc = cnt[i1]++;
+          if (loc < C || !moe) {
+            rt->tok_of_slot[i1][loc] = sq;
+            rt->gate_of_slot[i1][loc] = gsel;
+            rt->kept[i1] = loc + 1;
+          }
+        }
+        unsigned int am = 0;
+        int na = 0;
+        for (int e = 0; e < E; ++e)
+          if (rt->kept[e] > 0) {
+            am |= 1u << e;
+            rt->act[na++] = e;
+          }
+        rt->amask = am;
+        rt->nact = na;
+        rt->moe = moe ? 1 : 0;
+        rt->pf_amask[l & 3] = am;
+        __threadfence_block();
+        *const_cast<volatile unsigned int*>(&rt->pf_route) = static_cast<unsigned int>(l) + 1u;
+        mbar_arrive(route_bar);  // release: the producer may read the expert choice
+      }
+      consumer_sync();  // staged rows + routing decision visible to every warp
+      if (threadIdx.x == 0) {  // off the critical path: statistics, next layer's small weights
+        if (wg_l != nullptr && blockIdx.x == 0) {
+          float aux = 0.0f;
+          for (int e = 0; e < E; ++e) {
+            aux += (rt->me[e] / B) * (static_cast<float>(rt->cnt[e]) / B);
+            if (p.exp_counts != nullptr) p.exp_counts[l * p.Emax + e] = rt->cnt[e];
+          }
+          if (p.l_aux != nullptr) p.l_aux[l] = aux * E;
+          if (p.gate_logits != nullptr)
+            for (int sq = 0; sq < B; ++sq)
+              for (int e = 0; e < E; ++e)
+                p.gate_logits[static_cast<long long>(l) * B * p.Emax + sq * E + e] = rt->logits[sq][e];
+        }
+        if (l + 1 < p.L) issue_small(l + 1);  // every warp is past its reads of s_ln_post / s_wg
+      }
+    } else if (step != 3) {
+      consumer_sync();  // staged rows visible to every warp
     }
-    consumer_sync();
-    DK_STAMP(9);
-    const unsigned int amask = rt->amask;
-    const int nact = __popc(amask);
-    // ---------------------------------------------------------- P5: h1 = SiLU(h Wgate^T) * (h Wup^T) per active expert
-    for (int tile = blockIdx.x; tile < nact * tiles_f; tile += G) {
-      const int e = __fns(amask, 0, tile / tiles_f + 1);
-      const int n0 = (tile % tiles_f) * 8;
-      const int M = rt->kept[e];
-      const __nv_bfloat16* arow =
-          g < M ? reinterpret_cast<const __nv_bfloat16*>(s_a + rt->tok_of_slot[e][g] * pitch) : nullptr;
-      float* rbuf = red + buf * DK_RED_FLOATS;
-      buf ^= 1;
-      consume_tile<true>(ring, chunks_d, D, arow, rbuf);
-      if (threadIdx.x < 8 * DK_MAXB) {
-        const int r = threadIdx.x & 7, m = threadIdx.x >> 3;
-        if (m < M && n0 + r < F) {
-          const float gte = bf16_round(reduce_rows(rbuf, r, m)), up = bf16_round(reduce_rows(rbuf, r + 8, m));
-          const float v = bf16_round(gte / (1.0f + __expf(-gte))) * up;
-          p.h1[(static_cast<long long>(e) * B + m) * F + n0 + r] = __float2bfloat16_rn(v);
+    DK_STAMP(step * 4 + 1);
+    // ---------------------------------------------------------------------------------------------- weight tiles
+    // 16 weight rows (step 2: 8 gate + 8 up rows) x K per tile; a warp owns one 64-wide k block of every 512-wide chunk
+    {
+      const bool dual = step == 2;
+      const int nact = rt->nact;
+      const int per_e = step == 2 ? tiles_f : tiles_d;  // tiles per weight matrix
+      const int n_tiles = step == 0 ? 3 * tiles_d : (step == 1 ? tiles_d : nact * per_e);
+      const int chunks = step == 3 ? chunks_f : chunks_d;
+      const int K = step == 3 ? F : D;
+      const uint32_t warp_off = static_cast<uint32_t>(warp * ((dual ? 8 : 16) * 128) + g * 128);
+      const uint32_t hi = dual ? DK_STAGE_BYTES / 2 : 1024;
+      const uint32_t sw0 = static_cast<uint32_t>((t4 ^ g) * 16), sw1 = static_cast<uint32_t>(((4 + t4) ^ g) * 16);
+      const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+      for (int tile = blockIdx.x; tile < n_tiles; tile += G) {
+        const int mat = tile / per_e, n0 = (tile - mat * per_e) * (dual ? 8 : 16);
+        int e = 0, M = B;
+        const __nv_bfloat16* arow = nullptr;  // activation row of this lane's column (generic: shared or global)
+        if (step >= 2) {
+          e = rt->act[mat];
+          M = rt->kept[e];
+          if (g < M)
+            arow = step == 2 ? reinterpret_cast<const __nv_bfloat16*>(s_a + rt->tok_of_slot[e][g] * pitch)
+                             : p.h1 + (static_cast<long long>(e) * B + g) * F;
+        } else if (g < B) {
+          arow = reinterpret_cast<const __nv_bfloat16*>(s_a + g * pitch);
+        }
+        float* rbuf = red + buf * DK_RED_FLOATS;
+        buf ^= 1;
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f};
+        // activation fragments run two chunks ahead of the weights (step 3 reads them from global memory: L2 latency)
+        const int kw = warp * 64 + t4 * 8;
+        auto load_a = [&](int c, uint4& x0, uint4& x1) {
+          const int k = c * DK_KC + kw;
+          x0 = (arow != nullptr && c < chunks && k < K) ? *reinterpret_cast<const uint4*>(arow + k) : zero;
+          x1 = (arow != nullptr && c < chunks && k + 32 < K) ? *reinterpret_cast<const uint4*>(arow + k + 32) : zero;
+        };
+        uint4 xa0, xa1, xn0, xn1;
+        load_a(0, xa0, xa1);
+        load_a(1, xn0, xn1);
+#pragma unroll 1
+        for (int c = 0; c < chunks; ++c) {
+          const uint4 xb0 = xa0, xb1 = xa1;
+          xa0 = xn0;
+          xa1 = xn1;
+          load_a(c + 2, xn0, xn1);
+          mbar_wait(&ring.full[ring.stage], ring.phase);
+          const uint32_t sbase = smem_u32(ring.base + ring.stage * DK_STAGE_BYTES) + warp_off;
+          {
+            const uint4 wa = dk_lds128(sbase + sw0), wb = dk_lds128(sbase + hi + sw0);
+            dk_hmma(acc0, wa.x, wb.x, wa.y, wb.y, xb0.x, xb0.y);
+            dk_hmma(acc0, wa.z, wb.z, wa.w, wb.w, xb0.z, xb0.w);
+          }
+          {
+            const uint4 wa = dk_lds128(sbase + sw1), wb = dk_lds128(sbase + hi + sw1);
+            dk_hmma(acc0, wa.x, wb.x, wa.y, wb.y, xb1.x, xb1.y);
+            dk_hmma(acc0, wa.z, wb.z, wa.w, wb.w, xb1.z, xb1.w);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ring.empty[ring.stage]);
+          ring.advance();
+        }
+        // C fragment: c0,c1 -> (weight row g, m = 2t, 2t+1); c2,c3 -> (weight row g+8, same m)
+        float* rw = rbuf + warp * 16 * DK_RP;
+        rw[g * DK_RP + t4 * 2] = acc0[0];
+        rw[g * DK_RP + t4 * 2 + 1] = acc0[1];
+        rw[(g + 8) * DK_RP + t4 * 2] = acc0[2];
+        rw[(g + 8) * DK_RP + t4 * 2 + 1] = acc0[3];
+        consumer_sync();
+        // epilogue: 16 rows (step 2: 8 gate/up pairs) x M sequences, one value per thread
+        if (threadIdx.x < 16 * DK_MAXB) {
+          const int r = dual ? (threadIdx.x & 7) : (threadIdx.x & 15);
+          const int m = dual ? (threadIdx.x >> 3) : (threadIdx.x >> 4);
+          const int n = n0 + r;
+          if (step == 0) {
+            if (m < B && n < D)
+              p.qkv[static_cast<long long>(m) * 3 * D + mat * D + n] = __float2bfloat16_rn(reduce_rows(rbuf, r, m));
+          } else if (step == 1) {
+            if (m < B && n < D) {
+              __nv_bfloat16* xp = p.x + static_cast<long long>(m) * D + n;
+              *xp = __float2bfloat16_rn(bf16_round(reduce_rows(rbuf, r, m)) + __bfloat162float(*xp));
+            }
+          } else if (step == 2) {
+            if (m < M && m < DK_MAXB && n < F) {
+              const float gte = bf16_round(reduce_rows(rbuf, r, m)), up = bf16_round(reduce_rows(rbuf, r + 8, m));
+              const float v = bf16_round(gte / (1.0f + __expf(-gte))) * up;
+              p.h1[(static_cast<long long>(e) * B + m) * F + n] = __float2bfloat16_rn(v);
+            }
+          } else {
+            if (m < M && n < D) {
+              float v = reduce_rows(rbuf, r, m);
+              if (rt->moe) v = bf16_round(v) * bf16_round(rt->gate_of_slot[e][m]);  // combine_weights.type_as(x)
+              __nv_bfloat16* xp = p.x + static_cast<long long>(rt->tok_of_slot[e][m]) * D + n;
+              *xp = __float2bfloat16_rn(bf16_round(v) + __bfloat162float(*xp));
+            }
+          }
         }
       }
     }
-    DK_STAMP(10);
+    DK_STAMP(step * 4 + 2);
+    // ---------------------------------------------------------------------------------------------- phase end
+    if (step == 0) attention_phase(p, l, Tk, bar_target);  // (includes the grid barrier that ends the q,k,v tiles)
+    DK_STAMP(step == 0 ? 18 : step * 4 + 3);
     grid_sync(p.sync, bar_target);
-    DK_STAMP(11);
-    // ---------------------------------------------------------- P6: x += gate * (h1 Wdown^T)
-    for (int tile = blockIdx.x; tile < nact * tiles_d; tile += G) {
-      const int e = __fns(amask, 0, tile / tiles_d + 1);
-      const int n0 = (tile % tiles_d) * 16;
-      const int M = rt->kept[e];
-      const __nv_bfloat16* arow = g < M ? p.h1 + (static_cast<long long>(e) * B + g) * F : nullptr;
-      float* rbuf = red + buf * DK_RED_FLOATS;
-      buf ^= 1;
-      consume_tile<false>(ring, chunks_f, F, arow, rbuf);
-      if (threadIdx.x < 16 * DK_MAXB) {
-        const int r = threadIdx.x & 15, m = threadIdx.x >> 4;
-        if (m < M && n0 + r < D) {
-          float v = reduce_rows(rbuf, r, m);
-          if (rt->moe) v = bf16_round(v) * bf16_round(rt->gate_of_slot[e][m]);  // combine_weights.type_as(x)
-          __nv_bfloat16* xp = p.x + static_cast<long long>(rt->tok_of_slot[e][m]) * D + n0 + r;
-          *xp = __float2bfloat16_rn(bf16_round(v) + __bfloat162float(*xp));
-        }
-      }
-    }
-    DK_STAMP(12);
-    grid_sync(p.sync, bar_target);
-    DK_STAMP(13);
-  }
-  // ------------------------------------------------------------ final RMSNorm (hidden_states[-1])
-  if (p.out_norm != nullptr && blockIdx.x == 0) {
-    stage_rows(act, p.x, s_ln_in, lnin_bar, lnin_phase, B, D, p.eps, red);
-    consumer_sync();
-    for (int i = threadIdx.x; i < B * (D / 8); i += DK_CONSUMERS * 32) {
-      const int m = i / (D / 8), c = (i % (D / 8)) * 8;
-      *reinterpret_cast<uint4*>(p.out_norm + static_cast<long long>(m) * D + c) =
-          *reinterpret_cast<const uint4*>(s_a + m * pitch + c * 2);
-    }
+    DK_STAMP(step == 0 ? 3 : 19 + step);
   }
   // reset the barrier counter for the next launch once every CTA is past its last wait
   if (threadIdx.x == 0) {
@@ -1156,19 +1164,19 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
   p.Emax = emax;
   p.timing_layer = g_timing_layer;
   {
-    // L2 prefetch look-ahead per CTA in 16 KB chunks (x 148 CTAs must stay well inside the 126 MB L2)
-    static int kla = -1, ela = -1, spec = -1;
-    if (kla < 0) {
-      const char* a = getenv("MPL_DK_KLA");
-      const char* b = getenv("MPL_DK_ELA");
+    // L2 prefetch look-ahead per CTA in 16 KB chunks (x 148 CTAs: 16 chunks = 38 MB, well inside the 126 MB L2)
+    static int la = -1, spec = -1, evict = 0;
+    if (la < 0) {
+      const char* a = getenv("MPL_DK_LA");
       const char* c = getenv("MPL_DK_SPEC");
-      kla = a != nullptr ? atoi(a) : 16;
-      ela = b != nullptr ? atoi(b) : 8;
-      spec = c != nullptr ? atoi(c) : 4;  // speculate "every expert is hit" from this many sequences up (0: never)
+      const char* d = getenv("MPL_DK_EVICT");
+      evict = d != nullptr ? atoi(d) : 0;
+      la = a != nullptr ? atoi(a) : 16;
+      spec = c != nullptr ? atoi(c) : 4;  // walk past an undecided router assuming "every expert is hit" from this B up
     }
-    p.kla = kla;
-    p.ela = ela > 0xffff ? 0xffff : ela;
+    p.la = la > 0x3fff ? 0x3fff : la;
     p.spec = (spec > 0 && io.B >= spec) ? 1 : 0;
+    p.evict_first = evict;
   }
   for (int e = 0; e <= DK_MAXE; ++e) p.cap[e] = cap_by_e[e];
   p.eps = m.rms_eps;

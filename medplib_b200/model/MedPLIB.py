@@ -15,6 +15,7 @@ There is no eager fallback: without the built library or on a CPU tensor every e
 """
 import os
 import types
+import weakref
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
@@ -216,17 +217,23 @@ class MedPLIBModel(nn.Module):
                                                if "mm_projector" in k})
 
     def initialize_bird_modules(self, config):
-        """MedPLIB.py:141-164: SAM-Med2D (frozen; mask decoder trainable when train_mask_decoder) + text_hidden_fcs."""
-        if not hasattr(self, "visual_model"):
-            sam_cfg = getattr(config, "sam_config", None) or {}
-            self.visual_model = M.Sam(**sam_cfg)
-            if self.vision_pretrained is not None:
-                state = torch.load(self.vision_pretrained, map_location="cpu")
-                state = state["model"] if "model" in state else state
-                self.visual_model.load_state_dict(state, strict=False)
-            in_dim, out_dim = config.hidden_size, getattr(config, "out_dim", 256)
-            self.text_hidden_fcs = nn.ModuleList([nn.Sequential(
-                nn.Linear(in_dim, in_dim), nn.ReLU(inplace=True), nn.Linear(in_dim, out_dim), nn.Dropout(0.0))])
+        """MedPLIB.py:141-164: (re)build SAM-Med2D from ``vision_pretrained`` (frozen; the mask decoder trainable when
+        train_mask_decoder) and a fresh text_hidden_fcs. Like the reference, an explicit call from the train driver
+        (train_ds_medplib.py:245) REPLACES both — weights that from_pretrained put there are dropped."""
+        sam_cfg = getattr(config, "sam_config", None) or {}
+        ref = next(self.parameters(), None)
+        self.visual_model = M.Sam(**sam_cfg)
+        if self.vision_pretrained is not None:
+            state = torch.load(self.vision_pretrained, map_location="cpu")
+            state = state["model"] if "model" in state else state
+            self.visual_model.load_state_dict(state, strict=False)
+        in_dim, out_dim = config.hidden_size, getattr(config, "out_dim", 256)
+        self.text_hidden_fcs = nn.ModuleList([nn.Sequential(
+            nn.Linear(in_dim, in_dim), nn.ReLU(inplace=True), nn.Linear(in_dim, out_dim), nn.Dropout(0.0))])
+        if ref is not None and (ref.is_cuda or ref.dtype != torch.float32) and hasattr(self, "embed_tokens"):
+            # rebuilt on an already placed model (the driver calls this after from_pretrained): follow it
+            self.visual_model.to(device=ref.device, dtype=ref.dtype)
+            self.text_hidden_fcs.to(device=ref.device, dtype=ref.dtype)
         for p in self.visual_model.parameters():
             p.requires_grad = False
         if getattr(config, "train_mask_decoder", True):
@@ -236,6 +243,14 @@ class MedPLIBModel(nn.Module):
         self.text_hidden_fcs.train()
         for p in self.text_hidden_fcs.parameters():
             p.requires_grad = True
+        owner = getattr(self, "_owner", None)
+        if owner is not None and owner() is not None:
+            owner().refresh_engines()
+
+    def initialize_lisa_modules(self, config):
+        """model/LISA.py:134-158 — the non-MoE recipes (train_ds_medplib.py:247,
+        merge_lora_weights_and_save_hf_model.py:109) call the same construction under this name."""
+        return self.initialize_bird_modules(config)
 
     def forward(self, *a, **k):
         raise _lib.MplError("call MedPLIBForCausalLM (the decoder stack runs as one fused native call)")
@@ -281,6 +296,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
         self.seg_token_idx = kwargs.pop("seg_token_idx", None)
         super().__init__(config)
         self.model = MedPLIBModel(config, **kwargs)
+        object.__setattr__(self.model, "_owner", weakref.ref(self))  # module rebuilds invalidate the native tables
         self.vocab_size = config.vocab_size
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
         self.router_aux_loss_coef = (getattr(config, "moe", None) or {}).get("router_aux_loss_coef", 0.0) or 0.0
@@ -397,6 +413,10 @@ class MedPLIBForCausalLM(PreTrainedModel):
     def _params(self):
         sd = dict(self.named_parameters())
         sd.update(dict(self.named_buffers()))
+        # peft's lora.Linear keeps the frozen matrix as `<name>.base_layer.weight`: the native tables look it up as
+        # `<name>.weight` (medplib_b200/compat/peft_shim.py, or the real peft package)
+        for k in [k for k in sd if ".base_layer." in k]:
+            sd.setdefault(k.replace(".base_layer.", "."), sd[k])
         return sd
 
     def _check_ready(self):
@@ -410,7 +430,7 @@ class MedPLIBForCausalLM(PreTrainedModel):
         if "llama" not in self._eng:
             self._check_ready()
             params = self._params()
-            adapted = [(n, mod) for n, mod in self.named_modules() if isinstance(mod, nn.Linear) and hasattr(mod, "lora_A")]
+            adapted = [(n, mod) for n, mod in self.named_modules() if hasattr(mod, "lora_A") and hasattr(mod, "scaling")]
             if adapted:
                 # validation in the middle of training (train_ds_medplib.py validate() runs the peft-wrapped model):
                 # the inference kernels read plain weights, so the engine is built on MERGED copies W + s B A of the

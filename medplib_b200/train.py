@@ -86,7 +86,11 @@ class _Lora:
     def __init__(self, lin, arena):
         self.A, self.B = lin.lora_A["default"].weight, lin.lora_B["default"].weight
         self.s = float(lin.scaling["default"])
-        self.p = float(getattr(lin, "lora_dropout_p", 0.0))
+        p = getattr(lin, "lora_dropout_p", None)
+        if p is None:  # a real peft lora.Linear: lora_dropout is a ModuleDict of nn.Dropout / nn.Identity
+            drop = getattr(lin, "lora_dropout", None)
+            p = getattr(drop["default"], "p", 0.0) if isinstance(drop, nn.ModuleDict) and "default" in drop else 0.0
+        self.p = float(p)
         self.name = getattr(lin, "lora_name", "")
         self.gA, self.gB = arena.of(self.A), arena.of(self.B)
         if self.A.shape[0] > 16:

@@ -90,37 +90,29 @@ def timing(B=1, layer=5):
     e1.record()
     torch.cuda.synchronize()
     print(f"B={B}: {e0.elapsed_time(e1) / 16:.3f} ms/step over 16 steps (context {T}..{T + 16}); env "
-          f"KLA={os.environ.get('MPL_DK_KLA')} ELA={os.environ.get('MPL_DK_ELA')} SPEC={os.environ.get('MPL_DK_SPEC')}")
+          f"LA={os.environ.get('MPL_DK_LA')} SPEC={os.environ.get('MPL_DK_SPEC')} EVICT={os.environ.get('MPL_DK_EVICT')}")
     cache.len = T
     lib.mpl_debug_decode_timing(layer, None)
     eng.forward(xs.clone(), cache)
     buf = (ctypes.c_ulonglong * (160 * 32))()
     lib.mpl_debug_decode_timing(-1, buf)
     full = torch.tensor(list(buf), dtype=torch.float64).view(160, 32)[:148]
-    t = full[:, :14]
-    names = ["P1 stage", "P1 tiles", "bar1", "P2 attn", "bar2", "P3 stage", "P3 tiles", "bar3", "P4 route", "P5 tiles",
-             "bar4", "P6 tiles", "bar5"]
-    d = (t[:, 1:] - t[:, :-1]) / 1e3
-    print(f"B={B} layer {layer}: total {(t[:, 13] - t[:, 0]).mean() / 1e3:.1f} us (per-CTA mean)")
-    for i, n in enumerate(names):
-        print(f"  {n:10s} mean {d[:, i].mean():7.2f} us  min {d[:, i].min():7.2f}  max {d[:, i].max():7.2f}")
-    # sub-stamps: 14 layer prologue done; 15..19 P1 stage_rows (ln wait, sums written, sync, stored, end);
-    # 20..24 the same for P4's stage_rows; 25 after P4 staging; 26 router logits + softmax done
-    def seg(a, b):
-        dd = (full[:, b] - full[:, a]) / 1e3
-        return f"mean {dd.mean():6.2f} min {dd.min():6.2f} max {dd.max():6.2f}"
-    for name, a, b in (("P1 prologue (L-> loads, bulk issue)", 0, 14), ("P1 stage: ln wait", 14, 15),
-                       ("P1 stage: loads + sumsq", 15, 16), ("P1 stage: sync", 16, 17), ("P1 stage: normalise + store", 17, 18),
-                       ("P1 stage: end sync", 18, 19), ("P1 after stage -> tiles", 19, 1),
-                       ("P4 stage: ln/wg wait", 8, 20), ("P4 stage: loads + sumsq", 20, 21), ("P4 stage: sync", 21, 22),
-                       ("P4 stage: normalise + store", 22, 23), ("P4 stage: end", 23, 25), ("P4 router logits", 25, 26),
-                       ("P4 scan + publish", 26, 9)):
-        print(f"    {name:38s} {seg(a, b)}")
-    # phase end skew: when does the LAST CTA finish the phase's work relative to the first stamp
-    t0 = t[:, 0].min()
-    for i in (2, 4, 7, 10, 12):
-        print(f"  work before barrier stamp {i}: first CTA done at {(t[:, i].min() - t0) / 1e3:7.2f} us, last at "
-              f"{(t[:, i].max() - t0) / 1e3:7.2f} us")
+    # stamps (consumer thread 0 of every CTA): step s in 0..3 = q,k,v / o-proj / gate,up / down:
+    #   4s = step start, 4s+1 = staged (+ routed), 4s+2 = tiles done, 4s+3 (s>0) = before the closing barrier,
+    #   19+s (s>0) = after it; step 0: 16/17 around the barrier inside the attention phase, 18 = attention done,
+    #   3 = after the barrier that closes the attention; 23/24 = router start / logits+softmax done
+    us = lambda a, b: (full[:, b] - full[:, a]) / 1e3
+    rows = [("s0 stage (RMSNorm)", 0, 1), ("s0 q,k,v tiles", 1, 2), ("s0 -> barrier", 2, 16), ("bar1", 16, 17),
+            ("attention", 17, 18), ("bar2", 18, 3), ("s1 stage", 4, 5), ("s1 o-proj tiles", 5, 6), ("bar3", 7, 20),
+            ("s2 stage (RMSNorm)", 8, 23), ("s2 router logits", 23, 24), ("s2 scan + publish", 24, 9),
+            ("s2 gate/up tiles", 9, 10), ("bar4", 11, 21), ("s3 down tiles", 13, 14), ("bar5", 15, 22)]
+    print(f"B={B} layer {layer}: total {((full[:, 22] - full[:, 0]) / 1e3).mean():.1f} us (per-CTA mean)")
+    for n, a, b in rows:
+        d = us(a, b)
+        print(f"  {n:22s} mean {d.mean():7.2f} us  min {d.min():7.2f}  max {d.max():7.2f}")
+    t0 = full[:, 0].min()
+    for n, i in (("q,k,v tiles", 2), ("attention", 18), ("o-proj tiles", 6), ("gate/up tiles", 10), ("down tiles", 14)):
+        print(f"  {n:14s} done: first CTA at {(full[:, i].min() - t0) / 1e3:7.2f} us, last at {(full[:, i].max() - t0) / 1e3:7.2f} us")
 
 
 if __name__ == "__main__":
