@@ -39,14 +39,14 @@ namespace mpl {
 
 constexpr int DK_CONSUMERS = 8;
 constexpr int DK_THREADS = (DK_CONSUMERS + 2) * 32;  // 8 consumer warps + TMA producer warp + L2 prefetch warp
-constexpr int DK_STAGES = 6;
+constexpr int DK_MAX_STAGES = 12;  // ring depth is chosen per launch: as many 16 KB stages as shared memory holds
 constexpr int DK_STAGE_BYTES = 16384;  // [8 k-blocks][16 rows][128 B swizzled]  (dual: 2 x [8][8 rows][128 B])
 constexpr int DK_KC = 512;
 constexpr int DK_MAXB = 8;
 constexpr int DK_MAXE = MPL_MAX_EXPERTS;
 constexpr int DK_RP = 9;  // reduction row pitch (floats)
 constexpr int DK_RED_FLOATS = DK_CONSUMERS * 16 * DK_RP;
-constexpr int DK_WG_SMEM = 32768;  // router weights staged in shared memory when E*D*4 fits
+constexpr int DK_WG_SMEM = 32768;  // router weights staged in shared memory when E*D*4 fits AND it costs no ring stage
 
 // Per-layer device-resident description (the "decode plan"): tensor maps + the small raw pointers.
 struct alignas(64) DecLayerDev {
@@ -85,6 +85,7 @@ struct DecParams {
   float* l_aux;        // [L] or NULL
   int* exp_counts;     // [L, Emax] or NULL
   int B, D, H, F, L, Tmax, pos, nsplit, Emax, timing_layer;
+  int stages, wg_smem;  // ring depth; bytes reserved for a shared-memory copy of the router weights (0: read from L2)
   int la, spec, evict_first;  // L2 prefetch look-ahead (16 KB chunks per CTA, in consumption order); walk past undecided routers
   int cap[DK_MAXE + 1];  // capacity for a layer with E experts (index E)
   float eps, scale;
@@ -116,8 +117,9 @@ struct Ring {
   uint64_t* empty;
   int stage;
   uint32_t phase;
+  int n;  // stages
   __device__ __forceinline__ void advance() {
-    if (++stage == DK_STAGES) {
+    if (++stage == n) {
       stage = 0;
       phase ^= 1;
     }
@@ -540,12 +542,12 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
   extern __shared__ uint8_t dk_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dk_raw) + 1023) & ~uintptr_t(1023));
   const int pitch = p.D * 2 + 64;  // activation row pitch in shared memory (conflict-free 16-byte reads)
-  uint8_t* s_a = smem + DK_STAGES * DK_STAGE_BYTES;
+  uint8_t* s_a = smem + p.stages * DK_STAGE_BYTES;
   float* red = reinterpret_cast<float*>(s_a + p.B * pitch);  // [2][8][16][9]; staging / router scratch between phases
   // (shared memory is sized by the actual B: what it does not take stays L1, which the few spilled values need)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(red + 2 * DK_RED_FLOATS);
-  uint64_t* empty_bar = full_bar + DK_STAGES;
-  uint64_t* route_bar = empty_bar + DK_STAGES;
+  uint64_t* empty_bar = full_bar + DK_MAX_STAGES;
+  uint64_t* route_bar = empty_bar + DK_MAX_STAGES;
   uint64_t* act_bar = route_bar + 1;
   uint64_t* wg_bar = route_bar + 2;  // post-attention norm weight + router weights of the layer
   uint64_t* lnin_bar = route_bar + 3;  // input norm weight of the next layer (or the final norm)
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < DK_STAGES; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], DK_CONSUMERS);
     }
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
     rt->pf_amask[0] = rt->pf_amask[1] = rt->pf_amask[2] = rt->pf_amask[3] = 1u;
   }
   __syncthreads();
-  Ring ring{smem, full_bar, empty_bar, 0, 0};
+  Ring ring{smem, full_bar, empty_bar, 0, 0, p.stages};
   const int D = p.D, F = p.F, B = p.B;
   const int tiles_d = (D + 15) / 16;         // 16-row tiles of a [D, *] matrix
   const int tiles_f = (F + 7) / 8;           // 8+8-row tiles of the gate/up pair
@@ -656,6 +658,17 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
       unsigned int m = known ? (vr->pf_amask[layer & 3] & full) : full;
       return m != 0 ? m : 1u;
     };
+    // chunk `off` of a layer's q,k,v / o part
+    auto issue_known = [&](const DecLayerDev* Lp, unsigned int off) {
+      const int ti = static_cast<int>(off / chunks_d), c = static_cast<int>(off % chunks_d);
+      if (ti < n1) {
+        const int tile = bid + ti * G, which = tile / tiles_d;
+        const CUtensorMap* tm = which == 0 ? &Lp->wq : (which == 1 ? &Lp->wk : &Lp->wv);
+        tma_prefetch_3d(tm, 0, (tile % tiles_d) * 16, c * (DK_KC / 64));
+      } else {
+        tma_prefetch_3d(&Lp->wo, 0, (bid + (ti - n1) * G) * 16, c * (DK_KC / 64));
+      }
+    };
     while (pl < p.L) {
       const unsigned int lv = vr->pf_pos;
       const int ll = static_cast<int>(lv >> 16);
@@ -682,20 +695,15 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
       }
       const DecLayerDev* Lp = p.layers + pl;
       if (poff < nk) {
-        const int ti = static_cast<int>(poff / chunks_d), c = static_cast<int>(poff % chunks_d);
-        if (ti < n1) {
-          const int tile = bid + ti * G, which = tile / tiles_d;
-          const CUtensorMap* tm = which == 0 ? &Lp->wq : (which == 1 ? &Lp->wk : &Lp->wv);
-          tma_prefetch_3d(tm, 0, (tile % tiles_d) * 16, c * (DK_KC / 64));
-        } else {
-          tma_prefetch_3d(&Lp->wo, 0, (bid + (ti - n1) * G) * 16, c * (DK_KC / 64));
-        }
+        issue_known(Lp, poff);
         ++poff;
         continue;
       }
       bool known;
       const unsigned int amask = mask_of(pl, known);
       if (!known && !p.spec) {
+        // (measured, round 2: parking the NEXT layer's q,k,v tiles in L2 during this window does not pay -- the lines do
+        // not survive the 270 MB expert stream even with evict-first on the ring loads, and get fetched twice)
         __nanosleep(64);
         continue;
       }
@@ -738,7 +746,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
     const DecLayerDev* Ln = p.layers + layer;
     const float* wgn = Ln->wg;
     const int En = wgn != nullptr ? Ln->n_experts : 1;
-    const bool fits = wgn != nullptr && static_cast<long long>(En) * D * 4 <= DK_WG_SMEM;
+    const bool fits = wgn != nullptr && static_cast<long long>(En) * D * 4 <= p.wg_smem;
     fence_proxy_async();
     mbar_expect_tx(wg_bar, static_cast<uint32_t>(D * 2 + (fits ? En * D * 4 : 0)));
     dk_bulk_g2s(s_ln_post, Ln->post_ln, static_cast<uint32_t>(D * 2), wg_bar);
@@ -765,7 +773,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
     if (step == 0 && !fin) {  // (loads that step 2 needs: issued here, long before)
       wg_l = L->wg;
       E = wg_l != nullptr ? L->n_experts : 1;
-      wg_smem = wg_l != nullptr && static_cast<long long>(E) * D * 4 <= DK_WG_SMEM;
+      wg_smem = wg_l != nullptr && static_cast<long long>(E) * D * 4 <= p.wg_smem;
     }
     // ---------------------------------------------------------------------------------------------- staging
     // steps 0 / 2: RMSNorm(x) rows; step 1: attention output rows; step 3: nothing (its A operand is h1 in global memory)
@@ -807,7 +815,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
         const uint4 w1 = in1 ? lds_v4(s_ln + k1 * 2) : make_uint4(0, 0, 0, 0);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         // sum of squares of this thread's slices, row by row; lane -> warp (shuffles) -> CTA (fixed order 0..7)
-#pragma unroll 1
+#pragma unroll 2
         for (int r = 0; r < B; ++r) {
           float ss = 0.0f;
           if (in0) ss = sumsq8(lds_v4(s_a + r * pitch + k0 * 2), ss);
@@ -816,7 +824,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
           if (lane == 0) red[r * DK_CONSUMERS + warp] = ss;
         }
         consumer_sync();
-#pragma unroll 1
+#pragma unroll 2
         for (int r = 0; r < B; ++r) {
           const float4 p0 = *reinterpret_cast<const float4*>(red + r * DK_CONSUMERS);
           const float4 p1 = *reinterpret_cast<const float4*>(red + r * DK_CONSUMERS + 4);
@@ -844,18 +852,22 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
         // (shuffles) -> CTA (fixed order 0..7, by the thread that owns the row)
         const float* wgp = wg_smem ? s_wg : wg_l;  // generic pointer: shared-memory copy when it fits
         float* s_rp = red + 64;                    // [B][DK_MAXE][8 warps]
+        // (weights of expert e + 1 are requested while expert e is computed: they may come from L2)
+        auto load_w = [&](int e, float4& a, float4& b, float4& c, float4& d) {
+          a = b = c = d = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < E) {
+            const float* we = wgp + static_cast<long long>(e) * D;
+            if (in0) a = *reinterpret_cast<const float4*>(we + k0), b = *reinterpret_cast<const float4*>(we + k0 + 4);
+            if (in1) c = *reinterpret_cast<const float4*>(we + k1), d = *reinterpret_cast<const float4*>(we + k1 + 4);
+          }
+        };
+        float4 wa, wb, wc, wd, na, nb, nc, nd;
+        load_w(0, na, nb, nc, nd);
 #pragma unroll 1
         for (int e = 0; e < E; ++e) {
-          float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa, wc = wa, wd = wa;
-          if (in0) {
-            wa = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + k0);
-            wb = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + k0 + 4);
-          }
-          if (in1) {
-            wc = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + k1);
-            wd = *reinterpret_cast<const float4*>(wgp + static_cast<long long>(e) * D + k1 + 4);
-          }
-#pragma unroll 1
+          wa = na, wb = nb, wc = nc, wd = nd;
+          load_w(e + 1, na, nb, nc, nd);
+#pragma unroll 2
           for (int m = 0; m < B; ++m) {
             float acc = 0.0f;
             auto dot8 = [&](const uint4& raw, const float4& a0, const float4& a1) {
@@ -875,7 +887,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
         if (threadIdx.x < B) {  // the thread that owns row m: logits, softmax (rows 0..7 all live in warp 0)
           const int m = threadIdx.x;
           float mx = -INFINITY;
-          for (int e = 0; e < E; ++e) {
+          _Pragma("unroll 1") for (int e = 0; e < E; ++e) {
             float v = 0.0f;
 #pragma unroll
             for (int w = 0; w < DK_CONSUMERS; ++w) v += s_rp[(m * DK_MAXE + e) * DK_CONSUMERS + w];
@@ -883,8 +895,8 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
             mx = fmaxf(mx, v);
           }
           float sum = 0.0f;
-          for (int e = 0; e < E; ++e) sum += expf(rt->logits[m][e] - mx);
-          for (int e = 0; e < E; ++e) rt->gates[m][e] = expf(rt->logits[m][e] - mx) / sum;
+          _Pragma("unroll 1") for (int e = 0; e < E; ++e) sum += expf(rt->logits[m][e] - mx);
+          _Pragma("unroll 1") for (int e = 0; e < E; ++e) rt->gates[m][e] = expf(rt->logits[m][e] - mx) / sum;
         }
         if (warp == 0) __syncwarp();
       }
@@ -896,13 +908,13 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
         // (counters live in shared memory: a dynamically indexed local array would sit in local memory, i.e. L2)
         int* cnt = rt->cnt;
         float* me = rt->me;
-        for (int e = 0; e < E; ++e) cnt[e] = 0, me[e] = 0.0f, rt->kept[e] = 0;
-        for (int sq = 0; sq < B; ++sq) {
+        _Pragma("unroll 1") for (int e = 0; e < E; ++e) cnt[e] = 0, me[e] = 0.0f, rt->kept[e] = 0;
+        _Pragma("unroll 1") for (int sq = 0; sq < B; ++sq) {
           int i1 = 0;
           float gsel = 1.0f;
           if (moe) {
             float best = rt->gates[sq][0];
-            for (int e = 0; e < E; ++e) {
+            _Pragma("unroll 1") for (int e = 0; e < E; ++e) {
               me[e] += rt->gates[sq][e];
               if (rt->gates[sq][e] > best) best = rt->gates[sq][e], i1 = e;
             }
@@ -917,7 +929,7 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
         }
         unsigned int am = 0;
         int na = 0;
-        for (int e = 0; e < E; ++e)
+        _Pragma("unroll 1") for (int e = 0; e < E; ++e)
           if (rt->kept[e] > 0) {
             am |= 1u << e;
             rt->act[na++] = e;
@@ -934,14 +946,14 @@ __global__ void __launch_bounds__(DK_THREADS, 1) llama_decode_kernel(const __gri
       if (threadIdx.x == 0) {  // off the critical path: statistics, next layer's small weights
         if (wg_l != nullptr && blockIdx.x == 0) {
           float aux = 0.0f;
-          for (int e = 0; e < E; ++e) {
+          _Pragma("unroll 1") for (int e = 0; e < E; ++e) {
             aux += (rt->me[e] / B) * (static_cast<float>(rt->cnt[e]) / B);
             if (p.exp_counts != nullptr) p.exp_counts[l * p.Emax + e] = rt->cnt[e];
           }
           if (p.l_aux != nullptr) p.l_aux[l] = aux * E;
           if (p.gate_logits != nullptr)
-            for (int sq = 0; sq < B; ++sq)
-              for (int e = 0; e < E; ++e)
+            _Pragma("unroll 1") for (int sq = 0; sq < B; ++sq)
+              _Pragma("unroll 1") for (int e = 0; e < E; ++e)
                 p.gate_logits[static_cast<long long>(l) * B * p.Emax + sq * E + e] = rt->logits[sq][e];
         }
         if (l + 1 < p.L) issue_small(l + 1);  // every warp is past its reads of s_ln_post / s_wg
@@ -1074,10 +1086,26 @@ static int tmap3(CUtensorMap* out, const void* W, int N, int K, int rows) {
   return encode_tmap_bf16(out, W, 3, dims, strides, box);
 }
 
-static long long decode_smem_bytes(int D, int B) {
-  return 1024 + static_cast<long long>(DK_STAGES) * DK_STAGE_BYTES + static_cast<long long>(B) * (D * 2 + 64) +
-         2LL * DK_RED_FLOATS * 4 + (2 * DK_STAGES + 4) * 8 + static_cast<long long>(sizeof(RouteSmem)) + 128 + 2 * D * 2 +
-         DK_WG_SMEM + 64;
+// shared memory of a launch: ring | activation rows | reduction buffers | barriers | routing state | norm weights |
+// (optional) router weights. The ring takes every 16 KB stage that fits: the weight stream is latency-bound by the
+// bytes in flight per SM (6 stages = 96 KB gave 46 GB/s per SM, i.e. the whole chip only just at the HBM rate and any
+// imbalance below it), so depth is worth more than the shared-memory copy of the router weights.
+static long long decode_smem_fixed(int D, int B) {
+  return 1024 + static_cast<long long>(B) * (D * 2 + 64) + 2LL * DK_RED_FLOATS * 4 + (2 * DK_MAX_STAGES + 4) * 8 +
+         static_cast<long long>(sizeof(RouteSmem)) + 128 + 2 * D * 2 + 64;
+}
+static void decode_smem_plan(int D, int B, int emax, int* stages, int* wg_smem, long long* total) {
+  const long long cap = 227 * 1024;
+  const long long fixed = decode_smem_fixed(D, B);
+  int st = static_cast<int>((cap - fixed) / DK_STAGE_BYTES);
+  if (st > DK_MAX_STAGES) st = DK_MAX_STAGES;
+  const char* env = getenv("MPL_DK_STAGES");
+  if (env != nullptr && atoi(env) >= 2 && atoi(env) < st) st = atoi(env);
+  long long wg = static_cast<long long>(emax) * D * 4;
+  if (wg > DK_WG_SMEM || fixed + static_cast<long long>(st) * DK_STAGE_BYTES + wg > cap) wg = 0;
+  *stages = st;
+  *wg_smem = static_cast<int>(wg);
+  *total = fixed + static_cast<long long>(st) * DK_STAGE_BYTES + wg;
 }
 
 bool llama_decode_supported(const mpl_llama_model& m, const mpl_llama_io& io) {
@@ -1085,7 +1113,7 @@ bool llama_decode_supported(const mpl_llama_model& m, const mpl_llama_io& io) {
   if (io.hidden_states != nullptr || io.moe_noise != nullptr) return false;
   if (m.top_k != 1 || (m.hidden % 64) != 0 || (m.ffn % 64) != 0 || m.hidden != m.n_heads * 128) return false;
   if (io.attn_scratch == nullptr) return false;
-  if (decode_smem_bytes(m.hidden, io.B) > 227 * 1024 || m.hidden > 4096) return false;
+  if (decode_smem_fixed(m.hidden, io.B) + 4LL * DK_STAGE_BYTES > 227 * 1024 || m.hidden > 4096) return false;
   return true;
 }
 
@@ -1170,7 +1198,7 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
       const char* a = getenv("MPL_DK_LA");
       const char* c = getenv("MPL_DK_SPEC");
       const char* d = getenv("MPL_DK_EVICT");
-      evict = d != nullptr ? atoi(d) : 0;
+      evict = d != nullptr ? atoi(d) : 1;
       la = a != nullptr ? atoi(a) : 16;
       spec = c != nullptr ? atoi(c) : 4;  // walk past an undecided router assuming "every expert is hit" from this B up
     }
@@ -1195,7 +1223,9 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
   p.nsplit = nsplit;
   p.attn_cnt = static_cast<int*>(io.attn_scratch);
   p.attn_part = reinterpret_cast<float*>(static_cast<char*>(io.attn_scratch) + ((static_cast<long long>(bh) * 4 + 255) & ~255LL));
-  const int smem = static_cast<int>(decode_smem_bytes(D, io.B));
+  long long smem_ll = 0;
+  decode_smem_plan(D, io.B, emax, &p.stages, &p.wg_smem, &smem_ll);
+  const int smem = static_cast<int>(smem_ll);
   static int attr_smem = 0;
   if (attr_smem < smem) {
     const cudaError_t e = cudaFuncSetAttribute(llama_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -90,7 +90,7 @@ def timing(B=1, layer=5):
     e1.record()
     torch.cuda.synchronize()
     print(f"B={B}: {e0.elapsed_time(e1) / 16:.3f} ms/step over 16 steps (context {T}..{T + 16}); env "
-          f"LA={os.environ.get('MPL_DK_LA')} SPEC={os.environ.get('MPL_DK_SPEC')} EVICT={os.environ.get('MPL_DK_EVICT')}")
+          f"LA={os.environ.get('MPL_DK_LA')} SPEC={os.environ.get('MPL_DK_SPEC')} EVICT={os.environ.get('MPL_DK_EVICT')} LA2={os.environ.get('MPL_DK_LA2')}")
     cache.len = T
     lib.mpl_debug_decode_timing(layer, None)
     eng.forward(xs.clone(), cache)
