@@ -82,6 +82,10 @@ int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream);
  * durations (ms) and the launch count since enabling; reading synchronises the device and resets the counters. */
 int mpl_profile_gemm(int enable);
 int mpl_profile_gemm_read(float* total_ms, int* launches);
+/* The same for the persistent decode-step kernel (one launch = one token step of all layers; replaces the per-token
+ * HF forward of generate(), model/MedPLIB.py:592-606). */
+int mpl_profile_decode(int enable);
+int mpl_profile_decode_read(float* total_ms, int* launches);
 
 /* K3  same contract as mpl_gemm_bf16 for M <= 16 (decode batch, [SEG] rows, mask-decoder tokens): HBM-bound
  * streaming kernel, weights read once with 16-byte loads into mma.sync fragments (nb <= 3 as grid.y).

@@ -180,7 +180,7 @@ class SamMaskDecoder(ctypes.Structure):
 
 # Every symbol include/medplib_b200.h declares; tests/test_abi.py checks the built library exports all of them.
 EXPORTS = [
-    "mpl_version", "mpl_device_info", "mpl_launch_count", "mpl_gemm_bf16", "mpl_profile_gemm", "mpl_profile_gemm_read", "mpl_skinny_gemm_bf16", "mpl_linear_bf16", "mpl_grouped_gemm_bf16", "mpl_moe_route_small", "mpl_llama_decode_plan_bytes", "mpl_llama_decode_plan_build", "mpl_debug_decode_timing",
+    "mpl_version", "mpl_device_info", "mpl_launch_count", "mpl_gemm_bf16", "mpl_profile_gemm", "mpl_profile_gemm_read", "mpl_profile_decode", "mpl_profile_decode_read", "mpl_skinny_gemm_bf16", "mpl_linear_bf16", "mpl_grouped_gemm_bf16", "mpl_moe_route_small", "mpl_llama_decode_plan_bytes", "mpl_llama_decode_plan_build", "mpl_debug_decode_timing",
     "mpl_rmsnorm", "mpl_layernorm", "mpl_pool_layernorm", "mpl_attention",
     "mpl_moe_route", "mpl_moe_dispatch", "mpl_moe_combine", "mpl_rope_kv", "mpl_gather_rows", "mpl_argmax_f32",
     "mpl_im2col_patch", "mpl_im2col_nhwc", "mpl_clip_embed", "mpl_sam_relpos", "mpl_col_mean",

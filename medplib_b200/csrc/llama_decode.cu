@@ -96,6 +96,9 @@ struct DecParams {
 constexpr int DK_TSLOTS = 32;
 __device__ unsigned long long g_dk_times[160 * DK_TSLOTS];
 static int g_timing_layer = -1;
+static bool g_dprof = false;  // bench.py: CUDA events around every launch of the decode kernel
+static std::vector<cudaEvent_t> g_dprof_ev;
+static size_t g_dprof_used = 0;
 __device__ __forceinline__ unsigned long long globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1236,6 +1239,18 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
     attr_smem = smem;
   }
   void* args[] = {&p};
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (g_dprof) {
+    if (g_dprof_used + 2 > g_dprof_ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return MPL_ERR_CUDA;
+      g_dprof_ev.push_back(a);
+      g_dprof_ev.push_back(b);
+    }
+    pe0 = g_dprof_ev[g_dprof_used], pe1 = g_dprof_ev[g_dprof_used + 1];
+    g_dprof_used += 2;
+    cudaEventRecord(pe0, st);
+  }
   const cudaError_t le = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(llama_decode_kernel), dim3(G),
                                                      dim3(DK_THREADS), args, smem, st);
   if (le != cudaSuccess) {
@@ -1243,10 +1258,31 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
     cudaGetLastError();
     return MPL_ERR_CUDA;
   }
+  if (pe1 != nullptr) cudaEventRecord(pe1, st);
   return launch_status();
 }
 
 }  // namespace mpl
+
+// In-situ timing of the decode kernel's launches (bench.py roofline): CUDA events on the launch stream around each one.
+extern "C" int mpl_profile_decode(int enable) {
+  mpl::g_dprof = enable != 0;
+  mpl::g_dprof_used = 0;
+  return MPL_OK;
+}
+extern "C" int mpl_profile_decode_read(float* total_ms, int* launches) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return MPL_ERR_CUDA;
+  float tot = 0.0f;
+  for (size_t i = 0; i + 1 < mpl::g_dprof_used; i += 2) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, mpl::g_dprof_ev[i], mpl::g_dprof_ev[i + 1]) != cudaSuccess) return MPL_ERR_CUDA;
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = static_cast<int>(mpl::g_dprof_used / 2);
+  mpl::g_dprof_used = 0;
+  return MPL_OK;
+}
 
 // Dev tool: layer >= 0 enables per-phase timestamps of that layer in the decode kernel; out (host, [160*16] u64) != NULL
 // copies the last recorded stamps back (after a device synchronise).
