@@ -31,24 +31,52 @@ def merge_deepspeed_states(directory, dtype=torch.float32, device="cpu"):
         for k, v in sd.items():
             if k in combined:
                 raise ValueError(f"Duplicate key found in state dicts: {k}")
-            combined[k] = v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v
+            combined[k] = v.to(dtype) if dtype is not None and torch.is_tensor(v) and v.is_floating_point() else v
     return combined
 
 
-def save_deepspeed_layout(model, directory, tag_prefix=""):
-    """Write `model` the way DeepSpeed's MoE engine checkpoints it (one file per expert + the rest under "module"), so
-    the reference's params_bf16_to_f32.py / merge scripts can read a model trained here."""
+def peft_state_dict(model):
+    """state_dict() of `model` under the key names a peft-wrapped model has (what the reference's
+    merge_lora_weights_and_save_hf_model*.py load with strict=False into ``get_peft_model(...)``): a model wrapped by
+    medplib_b200.compat.peft_shim (or real peft) already has them; a bare model with attach_lora adapters gets the
+    ``base_model.model.`` prefix and ``<linear>.base_layer.weight`` for every adapted Linear."""
+    sd = model.state_dict()
+    if any(k.startswith("base_model.model.") for k in sd):
+        return sd
+    adapted = {n for n, m in model.named_modules() if hasattr(m, "lora_A")}
+    if not adapted:
+        return sd
+    out = {}
+    for k, v in sd.items():
+        mod, _, leaf = k.rpartition(".")
+        if mod in adapted and leaf in ("weight", "bias"):
+            k = f"{mod}.base_layer.{leaf}"
+        out["base_model.model." + k] = v
+    return out
+
+
+def save_deepspeed_layout(model, directory, tag_prefix=None):
+    """Write `model` the way DeepSpeed's MoE engine checkpoints it, so the reference's params_bf16_to_f32.py / merge
+    scripts / ``engine.load_checkpoint`` can read a model trained here:
+      ``mp_rank_00_model_states.pt``  {"module": every non-expert tensor}
+      ``layer_{i}_expert_{e}_mp_rank_00_model_states.pt``  the tensors of expert e of the i-th MoE layer -- i counts MoE
+      layers (DeepSpeed's moe_layer_id), NOT transformer layers, which matters for --moe_mode second_half / sparse.
+    Keys follow peft's naming when adapters are attached (see peft_state_dict); tag_prefix overrides the prefix."""
     os.makedirs(directory, exist_ok=True)
+    sd = peft_state_dict(model)
+    if tag_prefix:
+        sd = {tag_prefix + k: v for k, v in sd.items()}
     rest, experts = {}, {}
-    for k, v in model.state_dict().items():
+    for k, v in sd.items():
         m = _EXPERT_RE.match(k)
         if m:
-            experts.setdefault((int(m.group(2)), int(m.group(3))), {})[tag_prefix + k] = v.detach().cpu()
+            experts.setdefault((int(m.group(2)), int(m.group(3))), {})[k] = v.detach().cpu()
         else:
-            rest[tag_prefix + k] = v.detach().cpu()
+            rest[k] = v.detach().cpu()
     torch.save({"module": rest}, os.path.join(directory, "mp_rank_00_model_states.pt"))
-    for (layer, e), sd in experts.items():
-        torch.save(sd, os.path.join(directory, f"layer_{layer}_expert_{e}_mp_rank_00_model_states.pt"))
+    moe_layer_id = {layer: i for i, layer in enumerate(sorted({l for l, _ in experts}))}
+    for (layer, e), esd in experts.items():
+        torch.save(esd, os.path.join(directory, f"layer_{moe_layer_id[layer]}_expert_{e}_mp_rank_00_model_states.pt"))
     return len(experts)
 
 
@@ -99,6 +127,9 @@ def load_into(model, sd, lora="auto", scaling=None, strict=False):
         elif not has_adapters:
             raise ValueError("the checkpoint has LoRA tensors but the model has no adapters (attach_lora first)")
     own = model.state_dict()
+    # a model whose adapted Linears are peft-style wrappers keeps the frozen matrix under `<name>.base_layer.weight`
+    alias = {k.replace(".base_layer.", "."): k for k in own if ".base_layer." in k}
+    sd = {alias.get(k, k): v for k, v in sd.items()}
     cast = {}
     for k, v in sd.items():
         if k in own and torch.is_tensor(v) and v.is_floating_point():

@@ -224,9 +224,14 @@ class MedPLIBModel(nn.Module):
         ref = next(self.parameters(), None)
         self.visual_model = M.Sam(**sam_cfg)
         if self.vision_pretrained is not None:
-            state = torch.load(self.vision_pretrained, map_location="cpu")
-            state = state["model"] if "model" in state else state
-            self.visual_model.load_state_dict(state, strict=False)
+            # build_sam.py:123-148: {"model": state_dict} checkpoints (SAM-Med2D's own) load non-strictly, bare state
+            # dicts strictly (image_size 256 with adapters)
+            with open(self.vision_pretrained, "rb") as f:
+                state = torch.load(f, map_location="cpu")
+            if "model" in state:
+                self.visual_model.load_state_dict(state["model"], strict=False)
+            else:
+                self.visual_model.load_state_dict(state)
         in_dim, out_dim = config.hidden_size, getattr(config, "out_dim", 256)
         self.text_hidden_fcs = nn.ModuleList([nn.Sequential(
             nn.Linear(in_dim, in_dim), nn.ReLU(inplace=True), nn.Linear(in_dim, out_dim), nn.Dropout(0.0))])

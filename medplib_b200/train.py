@@ -516,7 +516,10 @@ class _StackFn(torch.autograd.Function):
     """hidden = decoder_stack(embeds). `anchor` is a dummy leaf that makes the output require grad."""
 
     @staticmethod
-    def forward(ctx, anchor, tr, embeds, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx, proj_ctx):
+    def forward(ctx, anchor, tr, embeds, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx, proj_ctx, *params):
+        # (params: every trainable parameter in arena order when tr.foreign_grads -- autograd then routes their
+        # gradients, returned by backward(), through the ordinary AccumulateGrad nodes and their hooks)
+        ctx.n_params = len(params)
         hidden, l_aux, gate_logits, saved = tr.stack.forward(embeds, B, Tn, kv_mask, moe_noise)
         ctx.tr, ctx.saved, ctx.splice_idx, ctx.region_ctx, ctx.proj_ctx = tr, saved, splice_idx, region_ctx, proj_ctx
         tr.last_gate_logits = gate_logits
@@ -555,7 +558,15 @@ class _StackFn(torch.autograd.Function):
             _projector_backward(tr, ctx.proj_ctx, dx0)
         ctx.saved = None
         tr.micro_steps += 1  # the stack's backward is the last node of a micro-step
-        return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 9
+        grads = ()
+        if ctx.n_params:
+            # foreign-optimizer mode: this node runs last (every other tape node feeds from its output), so the arena is
+            # complete -- hand each parameter its gradient in the parameter's dtype and start the next micro-step from
+            # zero (accumulation is the foreign engine's business, as are the all-reduce and the optimizer step)
+            grads = tuple(tr.arena.of(p).to(p.dtype) for p in tr.arena.params)
+            tr.arena.zero_()
+            tr.micro_steps = 0
+        return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 9 + grads
 
 
 def _wgrad_tc(dy, x, out, accumulate):
@@ -648,9 +659,14 @@ class Trainer:
     """
 
     def __init__(self, model, lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0,
-                 bucket_elems=64 << 20, group=None):
+                 bucket_elems=64 << 20, group=None, foreign_grads=False):
+        """foreign_grads=True: for a foreign engine / optimizer (real DeepSpeed ZeRO, torch.optim, DDP): after
+        ``loss.backward()`` every trainable parameter has an ordinary ``.grad`` (parameter dtype) delivered through
+        autograd -- gradient hooks fire, ``.grad`` accumulates across backward calls -- and this Trainer neither
+        all-reduces nor steps. Costs one cast pass over the arena per backward (318 M parameters: ~0.4 ms)."""
         model._check_ready()
         self.model = model
+        self.foreign_grads = bool(foreign_grads)
         dev = model.lm_head.weight.device
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         if not named:
@@ -666,6 +682,8 @@ class Trainer:
         self.loss_scale = 1.0
         self.last_gate_logits = None
         self.micro_steps = 0  # backward passes accumulated in the arena since the last step()
+        if self.foreign_grads:
+            self.reducer.on = False
         self._sig = self.signature(model)
 
     @staticmethod
@@ -696,7 +714,11 @@ class Trainer:
         self.stack.training = bool(self.model.training)
         B, Tn, D = embeds.shape
         x = embeds.to(bf16).reshape(B * Tn, D).contiguous()
-        return _StackFn.apply(self.anchor, self, x, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx, proj_ctx)
+        extra = ()
+        if self.foreign_grads:
+            self.model.refresh_trained()  # the foreign optimizer may have moved the weights since the last forward
+            extra = tuple(self.arena.params)
+        return _StackFn.apply(self.anchor, self, x, B, Tn, kv_mask, moe_noise, splice_idx, region_ctx, proj_ctx, *extra)
 
     def head_ce(self, hidden, labels):
         return _HeadCEFn.apply(hidden, self, labels)
@@ -728,6 +750,9 @@ class Trainer:
 
     def step(self, lr=None):
         """all-reduce what is left (mean over the data-parallel group), clip, AdamW, zero the arena."""
+        if self.foreign_grads:
+            raise _lib.MplError("this Trainer was built with foreign_grads=True: the gradients are in p.grad and the "
+                                "optimizer step belongs to the foreign engine")
         if self.micro_steps > 1 and self.reducer.on and self.reducer.next > 0 and not self._accum_ok():
             raise _lib.MplError("backward() ran more than once since the last step() with the bucket all-reduce enabled: "
                                 "wrap all but the last micro-step in `with trainer.no_sync():`")

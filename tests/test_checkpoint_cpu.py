@@ -145,3 +145,109 @@ def test_lora_checkpoint_fold_and_keep(tmp_path):
     assert not missing and not unexpected
     ref = train.merge_lora(m)
     _same(ref, m_fold)
+
+
+REF = "/root/reference"
+needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "params_bf16_to_f32.py")), reason="needs the reference tree")
+
+
+def _ref_loader():
+    """The reference's own merge function (params_bf16_to_f32.py:5-28), imported from where it lies."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_params_bf16_to_f32", os.path.join(REF, "params_bf16_to_f32.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.load_model_parameters
+
+
+@needs_ref
+def test_reference_merge_script_reads_the_written_layout(tmp_path):
+    """save_deepspeed_layout -> the REFERENCE's params_bf16_to_f32.load_model_parameters -> load_into: every tensor comes
+    back. With adapters attached the keys are exactly the ones a peft-wrapped model has (what
+    merge_lora_weights_and_save_hf_model_moe.py loads with strict=False: a key without the `base_model.model.` prefix
+    or without `base_layer` would be dropped silently and the merge would emit an untrained model)."""
+    from medplib_b200 import checkpoint as ck
+    from medplib_b200 import train
+    from medplib_b200.compat import peft_shim
+    m = _moe()
+    train.attach_lora(m, r=4, lora_alpha=8, target_modules="q_proj,v_proj,gate_proj,up_proj,down_proj")
+    _randomize(m, 3)
+    assert ck.save_deepspeed_layout(m, tmp_path) == 4
+    merged = _ref_loader()(str(tmp_path), "cpu")
+    assert all(v.dtype == torch.float32 for v in merged.values())
+    # the key set of a peft-wrapped model of the same architecture (the stand-in reproduces peft's nesting)
+    twin = _moe()
+    wrapped = peft_shim.get_peft_model(twin, peft_shim.LoraConfig(r=4, lora_alpha=8, lora_dropout=0.0, target_modules=[
+        n for n, mod in twin.named_modules() if isinstance(mod, torch.nn.Linear)
+        and any(t in n for t in ("q_proj", "v_proj", "gate_proj", "up_proj", "down_proj"))
+        and not any(x in n for x in ("visual_model", "vision_tower", "mm_projector"))]))
+    assert set(merged) == set(wrapped.state_dict())
+    assert "base_model.model.model.layers.0.self_attn.q_proj.base_layer.weight" in merged
+    # ... and loads straight into that wrapped model, like the reference's merge script does (strict=False, nothing dropped)
+    res = wrapped.load_state_dict({k: v.to(wrapped.state_dict()[k].dtype) for k, v in merged.items()}, strict=False)
+    assert not res.missing_keys and not res.unexpected_keys
+    folded = wrapped.merge_and_unload()
+    _same(train.merge_lora(m), folded)
+
+
+@needs_ref
+def test_expert_files_are_numbered_by_moe_layer(tmp_path):
+    """DeepSpeed names expert files by moe_layer_id — a counter over MoE layers — not by transformer layer: with MoE in
+    layer 1 only (--moe_mode second_half on 2 layers) the files are layer_0_expert_{0,1}_…; the keys inside keep the
+    transformer layer index (medplib_moe_llama.py:617-635)."""
+    from medplib_b200 import checkpoint as ck
+    m = _dense()
+    m.initialize_moe_modules(types.SimpleNamespace(**dict(MOE_ARGS, moe_mode="second_half")))
+    _randomize(m, 4)
+    assert ck.save_deepspeed_layout(m, tmp_path) == 2
+    files = sorted(f for f in os.listdir(tmp_path) if "expert" in f)
+    assert files == ["layer_0_expert_0_mp_rank_00_model_states.pt", "layer_0_expert_1_mp_rank_00_model_states.pt"]
+    merged = _ref_loader()(str(tmp_path), "cpu")
+    assert "model.layers.1.mlp.deepspeed_moe.experts.deepspeed_experts.1.up_proj.weight" in merged
+    m2 = _dense()
+    m2.initialize_moe_modules(types.SimpleNamespace(**dict(MOE_ARGS, moe_mode="second_half")))
+    missing, unexpected = ck.load_into(m2, merged)
+    assert not missing and not unexpected
+    _same(m, m2)
+
+
+def test_compat_engine_checkpoint_round_trip(tmp_path):
+    """deepspeed stand-in: engine.save_checkpoint(dir) writes <dir>/<tag>/… + <dir>/latest like DeepSpeed
+    (train_ds_medplib.py:693-698), engine.load_checkpoint(dir) reads `latest` and restores the peft-wrapped model and
+    the step counters (auto-resume, train_ds_medplib.py:452-470)."""
+    from medplib_b200.compat import deepspeed_shim as ds
+    from medplib_b200.compat import peft_shim
+    cfg = {"train_micro_batch_size_per_gpu": 2, "gradient_accumulation_steps": 2,
+           "optimizer": {"type": "AdamW", "params": {"lr": 3e-4, "weight_decay": 0.0, "betas": (0.9, 0.95)}},
+           "scheduler": {"type": "WarmupDecayLR", "params": {"total_num_steps": 100, "warmup_min_lr": 0, "warmup_max_lr": 3e-4,
+                                                             "warmup_num_steps": 10, "warmup_type": "linear"}},
+           "gradient_clipping": 1.0, "bf16": {"enabled": True}}
+
+    def wrapped(seed):
+        m = _moe()
+        w = peft_shim.get_peft_model(m, peft_shim.LoraConfig(r=4, lora_alpha=8, target_modules=["q_proj", "v_proj"]))
+        _randomize(w, seed)
+        return w
+
+    a = wrapped(6)
+    eng, opt, loader, sched = ds.initialize(model=a, model_parameters=a.parameters(), config=cfg)
+    assert opt is None and loader is None and sched is eng.lr_scheduler
+    eng.global_steps, eng.micro_steps = 7, 14
+    for _ in range(7):
+        eng.lr_scheduler.step()
+    eng.save_checkpoint(str(tmp_path))
+    assert open(os.path.join(tmp_path, "latest")).read().strip() == "global_step7"
+    b = wrapped(9)
+    eng2, _, _, _ = ds.initialize(model=b, model_parameters=b.parameters(), config=cfg)
+    path, client = eng2.load_checkpoint(str(tmp_path))
+    assert path.endswith("global_step7") and client == {}
+    assert eng2.global_steps == 7 and eng2.get_lr() == eng.get_lr()
+    _same(a, b)
+    assert eng2.load_checkpoint(os.path.join(tmp_path, "nothing_here")) == (None, None)
+    # linear warm-up then linear decay (deepspeed/runtime/lr_schedules.py::WarmupDecayLR)
+    s = ds.WarmupDecayLR(total_num_steps=100, warmup_min_lr=0.0, warmup_max_lr=1.0, warmup_num_steps=10, warmup_type="linear")
+    lrs = []
+    for _ in range(101):
+        s.step()
+        lrs.append(s.get_lr()[0])
+    assert lrs[0] == 0.0 and abs(lrs[5] - 0.5) < 1e-9 and lrs[10] == 1.0 and abs(lrs[55] - 0.5) < 1e-9 and lrs[100] == 0.0

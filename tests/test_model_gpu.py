@@ -62,10 +62,8 @@ def inputs(n_text=12, seg_in_prompt=False):
 
 
 def _check(got, ref, rtol, name):
-    got, ref = got.float().cpu(), ref.float()
-    scale = ref.abs().max().item()
-    err = (got - ref).abs().max().item()
-    assert err <= rtol * scale, f"{name}: max err {err:.4e} > {rtol} * {scale:.4e}"
+    from parity import close
+    return close(got, ref, rtol, name)
 
 
 def test_evaluate_matches_oracle(dev):

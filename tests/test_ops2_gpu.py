@@ -9,11 +9,7 @@ pytestmark = pytest.mark.gpu
 bf16 = torch.bfloat16
 
 
-def _close(got, ref, rtol, name=""):
-    got, ref = got.float().cpu(), ref.float().cpu()
-    scale = max(ref.abs().max().item(), 1e-6)
-    err = (got - ref).abs().max().item()
-    assert err <= rtol * scale, f"{name}: max err {err:.4e} > {rtol} * scale {scale:.4e}"
+from parity import close as _close  # noqa: E402  (logs the measured error, asserts the stated tolerance)
 
 
 @pytest.mark.parametrize("S,D,E,k,cf", [(615, 4096, 2, 1, 2.0), (8, 4096, 2, 1, 2.0), (5120, 256, 2, 1, 1.5),

@@ -17,11 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 
 
-def _close(got, ref, rtol, name=""):
-    got, ref = got.float().cpu(), ref.float().cpu()
-    scale = max(ref.abs().max().item(), 1e-6)
-    err = (got - ref).abs().max().item()
-    assert err <= rtol * scale, f"{name}: max err {err:.4e} > {rtol} * scale {scale:.4e}"
+from parity import close as _close  # noqa: E402  (logs the measured error, asserts the stated tolerance)
 
 
 def _to(sd, dev):

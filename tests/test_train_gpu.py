@@ -321,6 +321,54 @@ def test_optimizer_step_matches_adamw(dev):
     print(f"\nworst update error / tolerance: {worst:.3f}")
 
 
+def test_foreign_optimizer_sees_ordinary_grads(dev):
+    """Engine expectations of SURVEY 8b (deepspeed.initialize wraps the module, engine.backward = loss.backward, ZeRO
+    hangs hooks on the parameters): with Trainer(foreign_grads=True) a plain loss.backward() leaves every trainable
+    parameter with an ordinary .grad in its own dtype, delivered through autograd (post-accumulate hooks fire once per
+    parameter per backward, .grad accumulates over two backward calls), equal to what the arena path computes; a
+    torch.optim step on them is picked up by the next forward."""
+    m, sd, ocfg = build(dev)
+    b = batch(seg=True)
+    m.train()
+
+    def fwd():
+        ids, labels, am, clip_img, sam_img, gts = b
+        return m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), labels=labels.to(dev),
+                 attention_mask=am.to(dev), offset=None, masks_list=[g.to(dev) for g in gts],
+                 label_list=[g.to(dev) for g in gts], resize_list=[(256, 256)] * len(gts), inference=False, seg_flag=True,
+                 region_masks=None)
+
+    tr = m.trainer()
+    fwd()["loss"].backward()
+    want = {n: g.clone() for n, g in tr.arena.grads().items()}
+    tr.zero_grad()
+    tr = m.trainer(foreign_grads=True)
+    params = dict(m.named_parameters())
+    fired = {}
+    for n in want:
+        params[n].register_post_accumulate_grad_hook(lambda p, n=n: fired.__setitem__(n, fired.get(n, 0) + 1))
+    loss0 = fwd()["loss"]
+    loss0.backward()
+    assert set(fired) == set(want) and set(fired.values()) == {1}
+    for n, g in want.items():
+        p = params[n]
+        assert p.grad is not None and p.grad.dtype == p.dtype and p.grad.shape == p.shape
+        a, w1 = p.grad.float(), g.to(p.dtype).float()  # (atomic accumulation orders differ from run to run)
+        assert (a - w1).abs().max() <= 1e-2 * w1.abs().max() + 1e-12, n
+    assert float(tr.arena.flat.abs().max()) == 0.0  # handed over: the next micro-step starts from zero
+    fwd()["loss"].backward()  # accumulation is autograd's now
+    for n in ("lm_head.weight", "model.text_hidden_fcs.0.2.weight"):
+        a, w2 = params[n].grad.float(), 2 * want[n].to(params[n].dtype).float()
+        assert (a - w2).abs().max() <= 2e-2 * w2.abs().max() + 1e-12, n
+    with pytest.raises(Exception):
+        tr.step()
+    opt = torch.optim.SGD([params[n] for n in want], lr=0.05)
+    opt.step()
+    opt.zero_grad()
+    loss1 = fwd()["loss"]
+    assert float(loss1) < float(loss0)
+
+
 def test_gradient_accumulation(dev):
     """Two backward passes on the same batch before step() leave exactly twice the single-pass gradient in the arena
     (every kernel accumulates; the lm_head wgrad GEMM goes through a temporary on later micro-steps)."""
