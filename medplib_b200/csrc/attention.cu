@@ -726,6 +726,7 @@ extern "C" int mpl_attention(const mpl_attn_args* a, void* stream_) {
     return mpl::launch_status();
   }
   if (p.tk_dev != nullptr) return MPL_ERR_UNSUPPORTED;  // device-side Tk only on the decode path
+  if (attention_tc_supported(*a)) return attention_tc(*a, stream);  // tcgen05 + TMA tiles (attention_tc.cu)
   if (p.o_st % 2 != 0 || p.o_sh % 2 != 0 || p.o_sb % 2 != 0) return MPL_ERR_ALIGN;
   switch (a->head_dim) {
     case 16: return launch_flash<16>(p, stream);

@@ -28,6 +28,9 @@ int llama_decode_plan_build(const mpl_llama_model& m, void* plan_dev, cudaStream
 int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qkv, void* attn, void* h1,
                       const int* cap_by_e, int emax, cudaStream_t st);
 int attn_bwd_fa2(const mpl_attn_bwd_args& a, cudaStream_t stream);
+// attention_tc.cu: tcgen05 + TMA flash-attention forward (head_dim 64 / 128, Tq >= 32, no relative-position bias)
+bool attention_tc_supported(const mpl_attn_args& a);
+int attention_tc(const mpl_attn_args& a, cudaStream_t stream);
 int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D, cudaStream_t stream);
 int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
                 long long ldo, int S, int k, int D, cudaStream_t stream);

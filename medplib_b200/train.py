@@ -563,7 +563,7 @@ class _StackFn(torch.autograd.Function):
             # foreign-optimizer mode: this node runs last (every other tape node feeds from its output), so the arena is
             # complete -- hand each parameter its gradient in the parameter's dtype and start the next micro-step from
             # zero (accumulation is the foreign engine's business, as are the all-reduce and the optimizer step)
-            grads = tuple(tr.arena.of(p).to(p.dtype) for p in tr.arena.params)
+            grads = tuple(tr.arena.of(p).to(p.dtype, copy=True) for p in tr.arena.params)  # (fp32 params: a COPY, not a view)
             tr.arena.zero_()
             tr.micro_steps = 0
         return (torch.zeros(1, dtype=f32, device=dx0.device),) + (None,) * 9 + grads

@@ -177,6 +177,9 @@ def _ref_attention(q, k, v, scale, causal=False, kv_mask=None, bias=None):
     (1, 32, 615, 615, 128, True, False), (2, 4, 200, 200, 128, True, True), (1, 16, 577, 577, 64, False, False),
     (1, 8, 6, 256, 16, False, False), (1, 8, 256, 6, 16, False, False), (1, 8, 6, 6, 32, False, False),
     (2, 3, 70, 133, 64, False, False), (1, 2, 5, 77, 128, True, False),
+    # tcgen05 path (attention_tc.cu): many key tiles, ragged tails, a causal window with a past (Tk > Tq), masks
+    (2, 4, 639, 639, 128, True, True), (1, 4, 1299, 1299, 128, True, False), (2, 3, 130, 517, 128, True, True),
+    (3, 16, 577, 577, 64, False, False), (2, 2, 300, 1000, 64, True, True), (1, 2, 33, 40, 128, False, False),
 ])
 def test_attention_prefill(dev, B, H, Tq, Tk, d, causal, masked):
     from medplib_b200 import ops
