@@ -117,6 +117,8 @@ typedef struct {
   int groups, M, N, K, act, out_dtype;
   int m_dev_stable; /* 1: m_dev was already final before the PREVIOUS launch on this stream began, so the weight
                        stream may start before the dependency wait (programmatic dependent launch) */
+  int m_total_hint; /* 0, or the number of rows all groups hold together (host-side estimate, e.g. S * top_k): picks the
+                       tile width of the tensor-core path; the true per-group counts are always read from m_dev */
 } mpl_grouped_gemm_args;
 int mpl_grouped_gemm_bf16(const mpl_grouped_gemm_args* args, void* stream);
 

@@ -64,6 +64,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+__device__ __forceinline__ float ex2_approx(float x) {  // one MUFU: 2^x, flush-to-zero, 2^-inf = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t m, uint32_t n) {
   return umma_idesc_bf16(m, n) | (1u << 16);  // b_major = MN
 }
@@ -75,7 +80,7 @@ struct AttnTcCfg {
   static constexpr int KV_BYTES = AT_BN * D * 2;       // one of K / V
   static constexpr int P_BYTES = AT_BM * AT_BN * 2;    // [2 key blocks][128 rows][128 B]
   static constexpr int STAGES = 2;
-  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + P_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 2 * P_BYTES + 1024 + 256;  // P double-buffered
   static constexpr int TMEM_COLS = 512;  // S0 | S1 | PV (128 + 128 + D columns), power of two
 };
 
@@ -90,17 +95,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Cfg::Q_BYTES;  // stage s: K at s * 2 * KV_BYTES, V right after it
   uint8_t* sP = sKV + Cfg::STAGES * 2 * Cfg::KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::P_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    // [2]
-  uint64_t* s_empty = bars + 7;   // [2]
-  uint64_t* p_full = bars + 9;
-  uint64_t* p_empty = bars + 10;
-  uint64_t* pv_full = bars + 11;
-  uint64_t* pv_empty = bars + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* k_full = bars + 1;    // [2]  K and V have separate barriers: a K stage is free as soon as S_j is done
+  uint64_t* k_empty = bars + 3;   // [2]  (long before P_j V_j), so K_{j+2} is requested two tiles ahead of its use
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* s_empty = bars + 11;  // [2]
+  uint64_t* p_full = bars + 13;
+  uint64_t* pv_full = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   uint32_t* mask_words = tmem_slot + 2;  // [2][4]: key-padding bits of the current tile, double-buffered by tile parity
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,15 +124,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 4);
     }
     mbar_init(p_full, 4);
-    mbar_init(p_empty, 1);
     mbar_init(pv_full, 1);
-    mbar_init(pv_empty, 4);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -144,12 +149,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       for (int kb = 0; kb < KB; ++kb) tma_load_4d(sQ + kb * (AT_BM * 128), &tmQ, q_full, kb * 64, q0, h, b);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        const uint32_t ph = ((j >> 1) & 1) ^ 1;
         uint8_t* sK = sKV + s * 2 * Cfg::KV_BYTES;
         uint8_t* sV = sK + Cfg::KV_BYTES;
-        mbar_expect_tx(&kv_full[s], 2 * Cfg::KV_BYTES);
-        for (int kb = 0; kb < KB; ++kb) tma_load_4d(sK + kb * (AT_BN * 128), &tmK, &kv_full[s], kb * 64, j * AT_BN, h, b);
-        for (int kb = 0; kb < KB; ++kb) tma_load_4d(sV + kb * (AT_BN * 128), &tmV, &kv_full[s], kb * 64, j * AT_BN, h, b);
+        mbar_wait(&k_empty[s], ph);
+        mbar_expect_tx(&k_full[s], Cfg::KV_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_4d(sK + kb * (AT_BN * 128), &tmK, &k_full[s], kb * 64, j * AT_BN, h, b);
+        mbar_wait(&v_empty[s], ph);
+        mbar_expect_tx(&v_full[s], Cfg::KV_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_4d(sV + kb * (AT_BN * 128), &tmV, &v_full[s], kb * 64, j * AT_BN, h, b);
       }
     }
   } else if (warp == 1) {
@@ -160,7 +168,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       auto issue_s = [&](int j) {
         const int s = j & 1;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        mbar_wait(&k_full[s], (j >> 1) & 1);
         mbar_wait(&s_empty[s], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sKV + s * 2 * Cfg::KV_BYTES);
@@ -171,6 +179,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             umma_bf16_ss(tm_S0 + s * AT_BN, umma_desc_k_sw128(q_addr + kb * (AT_BM * 128) + k * 32),
                          umma_desc_k_sw128(k_addr + kb * (AT_BN * 128) + k * 32), idesc_s, (kb | k) != 0 ? 1u : 0u);
         umma_commit(&s_full[s]);
+        umma_commit(&k_empty[s]);  // K_j is not needed again
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -178,14 +187,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (j + 1 < n_tiles) issue_s(j + 1);
         const int s = j & 1;
         mbar_wait(p_full, j & 1);  // P_j written (and O rescaled if the row maximum jumped)
+        mbar_wait(&v_full[s], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sKV + s * 2 * Cfg::KV_BYTES + Cfg::KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < AT_BN / 16; ++kk)
-          umma_bf16_ss(tm_PV, umma_desc_k_sw128(p_addr + (kk >> 2) * (AT_BM * 128) + (kk & 3) * 32),
+          umma_bf16_ss(tm_PV, umma_desc_k_sw128(p_addr + s * Cfg::P_BYTES + (kk >> 2) * (AT_BM * 128) + (kk & 3) * 32),
                        umma_desc_mn_sw128(v_addr + kk * 2048, AT_BN * 128), idesc_pv, (j | kk) != 0 ? 1u : 0u);
         umma_commit(pv_full);       // O += P_j V_j complete: O may be rescaled, the P tile overwritten
-        umma_commit(&kv_empty[s]);  // K_j / V_j stage reusable
+        umma_commit(&v_empty[s]);   // V_j stage reusable
       }
     }
   } else {
@@ -239,16 +249,52 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             if (!(i <= lim && ((mw[c] >> i) & 1u))) r[c * 32 + i] = 0xff800000u;  // -inf
         }
       }
-      float mx = -INFINITY;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;  // four independent chains
 #pragma unroll
-      for (int i = 0; i < AT_BN; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-      mx *= sl2;  // scale > 0: max commutes with it (-inf stays -inf)
+      for (int i = 0; i < AT_BN; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;  // scale > 0: max commutes with it
       const bool bump = mx > m + 8.0f;  // (m = -inf on the first tile: any finite maximum bumps)
       const float m_new = bump ? mx : m;
-      const float corr = bump ? exp2f(m - m_new) : 1.0f;  // 0 when m was -inf
+      const float corr = bump ? ex2_approx(m - m_new) : 1.0f;  // 0 when m was -inf
       const float msafe = (m_new == -INFINITY) ? 0.0f : m_new;
+      l *= corr;
+      // P_j = 2^(x * scale - m_new) as bf16 into the swizzled K-major tile (buffer j & 1: P_{j-2} V_{j-2} is complete,
+      // this thread waited for it a tile ago), row sum in fp32 (4 partial sums)
+      float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
+      uint8_t* sPj = sP + s * Cfg::P_BYTES;
+#pragma unroll
+      for (int c = 0; c < AT_BN / 32; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[c * 32 + i]), sl2, -msafe));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[c * 32 + i + 1]), sl2, -msafe));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(r[c * 32 + i + 2]), sl2, -msafe));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(r[c * 32 + i + 3]), sl2, -msafe));
+          sum0 += p0;
+          sum1 += p1;
+          sum2 += p2;
+          sum3 += p3;
+          pk[i >> 1] = pack_bf16(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+        }
+        // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key block c / 2
+        uint8_t* line = sPj + (c >> 1) * (AT_BM * 128) + row * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
+          *reinterpret_cast<uint4*>(line + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        }
+      }
       if (j > 0) {
-        mbar_wait(pv_full, (j - 1) & 1);  // P_{j-1} V_{j-1} complete: O may be rescaled, the P tile overwritten
+        // O += P_{j-1} V_{j-1} has been running behind this tile's softmax. It must be complete before O is rescaled
+        // (rare) and before P_j V_j is issued; waiting here also keeps this thread's view of the barrier one phase behind
+        mbar_wait(pv_full, (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, bump)) {
 #pragma unroll
@@ -261,33 +307,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             tmem_st_32x32(tm_PV + t_lane + c * 32, t);
           }
           tmem_st_wait();
-        }
-      }
-      l *= corr;
-      // P_j = 2^(x * scale - m_new) as bf16 into the swizzled K-major tile, row sum in fp32 (4 partial sums)
-      float sum0 = 0.0f, sum1 = 0.0f, sum2 = 0.0f, sum3 = 0.0f;
-#pragma unroll
-      for (int c = 0; c < AT_BN / 32; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float p0 = exp2f(fmaf(__uint_as_float(r[c * 32 + i]), sl2, -msafe));
-          const float p1 = exp2f(fmaf(__uint_as_float(r[c * 32 + i + 1]), sl2, -msafe));
-          const float p2 = exp2f(fmaf(__uint_as_float(r[c * 32 + i + 2]), sl2, -msafe));
-          const float p3 = exp2f(fmaf(__uint_as_float(r[c * 32 + i + 3]), sl2, -msafe));
-          sum0 += p0;
-          sum1 += p1;
-          sum2 += p2;
-          sum3 += p3;
-          pk[i >> 1] = pack_bf16(p0, p1);
-          pk[(i >> 1) + 1] = pack_bf16(p2, p3);
-        }
-        // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key block c / 2
-        uint8_t* line = sP + (c >> 1) * (AT_BM * 128) + row * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ (row & 7);
-          *reinterpret_cast<uint4*>(line + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         }
       }
       l += (sum0 + sum1) + (sum2 + sum3);

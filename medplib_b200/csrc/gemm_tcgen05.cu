@@ -44,7 +44,73 @@ struct GemmDevParams {
   int act;
   int out_f32;
   int dual;
+  // grouped mode (groups > 0): group g multiplies A rows [g * a_group_rows, +m_dev[g]) by its own weight matrix (tensor
+  // maps in GroupMaps) into C + g * c_group_stride; ONE launch walks the tiles of all groups (m fastest inside a group)
+  int groups;
+  long long a_group_rows;
+  long long c_group_stride;  // elements
 };
+
+struct GroupMaps {
+  CUtensorMap b[MPL_MAX_EXPERTS];
+  CUtensorMap b2[MPL_MAX_EXPERTS];
+};
+
+// tile index -> (group / weight matrix, first row, first column, rows of the group)
+struct TileCoord {
+  int g, m0, n0, M;
+};
+struct TileSpace {
+  int groups, tiles_n1, nb, out_bn, num_tiles;
+  int tm[MPL_MAX_EXPERTS], Mg[MPL_MAX_EXPERTS];
+  int tiles_m, M;
+  __device__ __forceinline__ TileCoord at(int tile) const {
+    TileCoord c;
+    if (groups > 0) {
+      int g = 0, t = tile;
+#pragma unroll 1
+      while (g + 1 < groups && t >= tm[g] * tiles_n1) t -= tm[g++] * tiles_n1;
+      c.g = g;
+      c.m0 = (t % tm[g]) * BM;
+      c.n0 = (t / tm[g]) * out_bn;
+      c.M = Mg[g];
+    } else {
+      const int nt = tile / tiles_m;
+      c.g = nt / tiles_n1;  // which weight matrix (nb > 1)
+      c.m0 = (tile % tiles_m) * BM;
+      c.n0 = (nt % tiles_n1) * out_bn;
+      c.M = M;
+    }
+    return c;
+  }
+};
+__device__ __forceinline__ TileSpace make_tile_space(const GemmDevParams& p, int out_bn) {
+  TileSpace ts;
+  ts.groups = p.groups;
+  ts.out_bn = out_bn;
+  ts.nb = p.nb;
+  ts.tiles_n1 = (p.N + out_bn - 1) / out_bn;
+  if (p.groups > 0) {
+    int total = 0;
+#pragma unroll 1
+    for (int g = 0; g < p.groups; ++g) {
+      const int Mg = min(p.M, p.m_dev != nullptr ? p.m_dev[g] : p.M);
+      ts.Mg[g] = Mg;
+      ts.tm[g] = (Mg + BM - 1) / BM;
+      total += ts.tm[g] * ts.tiles_n1;
+    }
+    ts.num_tiles = total;
+    ts.tiles_m = 0;
+    ts.M = 0;
+  } else {
+    int M = p.M;
+    if (p.m_dev != nullptr) M = min(M, *p.m_dev);
+    ts.M = M;
+    ts.tiles_m = (M + BM - 1) / BM;
+    ts.num_tiles = ts.tiles_m * ts.tiles_n1 * p.nb;
+  }
+  return ts;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -77,7 +143,7 @@ template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
-                         const GemmDevParams p) {
+                         const GemmDevParams p, const __grid_constant__ GroupMaps gmaps) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -93,13 +159,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  int M = p.M;
-  if (p.m_dev != nullptr) M = min(M, *p.m_dev);
   const int out_bn = p.dual ? BN / 2 : BN;
-  const int tiles_m = (M + BM - 1) / BM;
-  const int tiles_n1 = (p.N + out_bn - 1) / out_bn;  // per weight matrix
-  const int tiles_n = tiles_n1 * p.nb;
-  const int num_tiles = tiles_m * tiles_n;
+  __shared__ TileSpace ts;  // (per-group tile counts are indexed dynamically: shared memory, not a local array)
+  if (threadIdx.x == 0) ts = make_tile_space(p, out_bn);
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -122,6 +184,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = ts.num_tiles;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -129,15 +192,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * BM;
-        const int nt = tile / tiles_m;
-        const int which = nt / tiles_n1;
-        const int n0 = (nt % tiles_n1) * out_bn;
+        const TileCoord tc = ts.at(tile);
+        const int which = tc.g, n0 = tc.n0;
+        const int m0 = p.groups > 0 ? static_cast<int>(tc.g * p.a_group_rows) + tc.m0 : tc.m0;  // row in the A buffer
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
           tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
-          if (p.dual) {
+          if (p.groups > 0) {
+            // per-group weight maps: a __grid_constant__ array, indexed in param space
+            if (p.dual) {
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &gmaps.b[which], &full_bar[stage], kb * BK, n0);
+              tma_load_2d(sB + stage * Cfg::B_BYTES + Cfg::B_BYTES / 2, &gmaps.b2[which], &full_bar[stage], kb * BK, n0);
+            } else {
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &gmaps.b[which], &full_bar[stage], kb * BK, n0);
+            }
+          } else if (p.dual) {
             tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full_bar[stage], kb * BK, n0);
             tma_load_2d(sB + stage * Cfg::B_BYTES + Cfg::B_BYTES / 2, &tmB2, &full_bar[stage], kb * BK, n0);
           } else {
@@ -200,12 +270,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const bool vec_ok = p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool res_vec_ok = (p.ldr & 7) == 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * BM;
-      const int nt = tile / tiles_m;
-      const int which = nt / tiles_n1;
-      const int n0 = (nt % tiles_n1) * out_bn;
-      const __nv_bfloat16* bias = which == 0 ? p.bias[0] : (which == 1 ? p.bias[1] : p.bias[2]);
+      const TileCoord tc = ts.at(tile);
+      const int which = tc.g, m0 = tc.m0, n0 = tc.n0, M = tc.M;
+      const __nv_bfloat16* bias = p.groups > 0 ? nullptr : (which == 0 ? p.bias[0] : (which == 1 ? p.bias[1] : p.bias[2]));
       void* Cout = which == 0 ? p.C[0] : (which == 1 ? p.C[1] : p.C[2]);
+      if (p.groups > 0)
+        Cout = static_cast<char*>(p.C[0]) + static_cast<long long>(which) * p.c_group_stride * (p.out_f32 ? 4 : 2);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
@@ -457,7 +527,11 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   if (grid < 1) grid = 1;
   const bool prof = g_prof && !g_prof_suppress;
   if (prof) cudaEventRecord(prof_event(), stream);
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB1, tmB2, p);
+  p.groups = 0;
+  p.a_group_rows = 0;
+  p.c_group_stride = 0;
+  static const GroupMaps no_groups = {};
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB1, tmB2, p, no_groups);
   if (prof) cudaEventRecord(prof_event(), stream);
   return mpl::launch_status();
 }
@@ -486,73 +560,84 @@ int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
   return launch_gemm<128>(a, stream);
 }
 
-// Grouped (per-expert) GEMM for M > 16: one tcgen05 launch per group (device-side row counts via m_dev). Each expert's
-// launch is a partial wave at prefill sizes (e.g. down_proj at M_e ~ 300: 66 tiles on 148 SMs), so the groups are
-// launched on side streams forked from / joined to the caller's stream and run CONCURRENTLY on disjoint SMs.
-static cudaStream_t g_aux_stream[MPL_MAX_EXPERTS];
-static cudaEvent_t g_fork_ev, g_join_ev[MPL_MAX_EXPERTS];
-static bool g_aux_ready = false;
-static bool aux_streams_ready() {
-  if (g_aux_ready) return true;
-  if (cudaEventCreateWithFlags(&g_fork_ev, cudaEventDisableTiming) != cudaSuccess) return false;
-  for (int i = 0; i < MPL_MAX_EXPERTS; ++i) {
-    if (cudaStreamCreateWithFlags(&g_aux_stream[i], cudaStreamNonBlocking) != cudaSuccess) return false;
-    if (cudaEventCreateWithFlags(&g_join_ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+template <int BN>
+static int launch_grouped(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
+        cudaSuccess)
+      return MPL_ERR_CUDA;
+    attr_set = true;
   }
-  g_aux_ready = true;
-  return true;
+  const int dual = a.B2[0] != nullptr;
+  const long long group_rows = a.a_group_stride / a.lda;
+  CUtensorMap tmA;
+  GroupMaps gm;
+  memset(&gm, 0, sizeof(gm));
+  // ONE map over the whole expert buffer: group g starts at row g * group_rows; rows past a group's count are read
+  // (they belong to the next group or are zero-filled past the end) but never stored
+  int rc = make_tmap(&tmA, a.A, group_rows * (a.groups - 1) + a.M, a.K, a.lda, BM);
+  for (int g = 0; g < a.groups && rc == MPL_OK; ++g) {
+    rc = make_tmap(&gm.b[g], a.B[g], a.N, a.K, a.ldb, dual ? BN / 2 : BN);
+    if (rc == MPL_OK && dual) rc = make_tmap(&gm.b2[g], a.B2[g], a.N, a.K, a.ldb, BN / 2);
+  }
+  if (rc != MPL_OK) return rc;
+  GemmDevParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.nb = 1;
+  p.C[0] = a.C;
+  p.ldc = a.ldc;
+  p.residual = static_cast<const __nv_bfloat16*>(a.residual);
+  p.ldr = a.ldr;
+  p.m_dev = a.m_dev;
+  p.act = a.act;
+  p.out_f32 = a.out_dtype == MPL_DT_F32;
+  p.dual = dual;
+  p.groups = a.groups;
+  p.a_group_rows = group_rows;
+  p.c_group_stride = a.c_group_stride;
+  const int out_bn = dual ? BN / 2 : BN;
+  const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn) * a.groups;
+  int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  if (grid < 1) grid = 1;
+  const bool prof = g_prof && !g_prof_suppress;
+  if (prof) cudaEventRecord(prof_event(), stream);
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, gm.b[0], gm.b[0], gm.b[0], p, gm);
+  if (prof) cudaEventRecord(prof_event(), stream);
+  return mpl::launch_status();
 }
 
+// Grouped (per-expert) GEMM for M > 16: ONE tcgen05 launch walks the tiles of every group (device-side row counts via
+// m_dev; m fastest inside a group so concurrently running CTAs share a weight panel). Round 1 launched one kernel per
+// expert on forked streams: at prefill sizes every such launch was a partial wave (profiles/r01_ncu_gemm_prefill.md).
 int grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
   if (a.row_map != nullptr || a.a_row_map != nullptr) return MPL_ERR_UNSUPPORTED;
-  const long long csz = a.out_dtype == MPL_DT_F32 ? 4 : 2;
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(stream, &cap);
-  const bool fork = a.groups > 1 && a.groups <= MPL_MAX_EXPERTS && cap == cudaStreamCaptureStatusNone &&
-                    aux_streams_ready();
-  // in-situ profiling: the concurrent launches are timed as one interval on the caller's stream (fork -> join)
-  const bool prof_region = fork && g_prof && !g_prof_suppress;
-  if (prof_region) {
-    cudaEventRecord(prof_event(), stream);
-    g_prof_suppress = true;
-  }
-  if (fork && cudaEventRecord(g_fork_ev, stream) != cudaSuccess) return MPL_ERR_CUDA;
-  int rc_all = MPL_OK;
-  for (int g = 0; g < a.groups && rc_all == MPL_OK; ++g) {
-    mpl_gemm_args x;
-    memset(&x, 0, sizeof(x));
-    x.A = static_cast<const char*>(a.A) + static_cast<long long>(g) * a.a_group_stride * 2;
-    x.lda = a.lda;
-    x.B[0] = a.B[g];
-    x.B2 = a.B2[g];
-    x.ldb = a.ldb;
-    x.C[0] = static_cast<char*>(a.C) + static_cast<long long>(g) * a.c_group_stride * csz;
-    x.ldc = a.ldc;
-    x.residual = a.residual;
-    x.ldr = a.ldr;
-    x.m_dev = a.m_dev ? a.m_dev + g : nullptr;
-    x.M = a.M;
-    x.N = a.N;
-    x.K = a.K;
-    x.nb = 1;
-    x.act = a.act;
-    x.out_dtype = a.out_dtype;
-    cudaStream_t s = stream;
-    if (fork && g > 0) {
-      s = g_aux_stream[g];
-      if (cudaStreamWaitEvent(s, g_fork_ev, 0) != cudaSuccess) return MPL_ERR_CUDA;
-    }
-    rc_all = gemm_bf16(x, s);
-    if (rc_all == MPL_OK && fork && g > 0) {
-      if (cudaEventRecord(g_join_ev[g], s) != cudaSuccess || cudaStreamWaitEvent(stream, g_join_ev[g], 0) != cudaSuccess)
-        rc_all = MPL_ERR_CUDA;
-    }
-  }
-  if (prof_region) {
-    g_prof_suppress = false;
-    cudaEventRecord(prof_event(), stream);
-  }
-  return rc_all;
+  if (a.groups < 1 || a.groups > MPL_MAX_EXPERTS || a.M <= 0 || a.N <= 0) return a.groups < 1 || a.M <= 0 ? MPL_OK : MPL_ERR_ARG;
+  if (a.K <= 0 || a.A == nullptr || a.C == nullptr || a.lda <= 0 || a.a_group_stride % a.lda != 0) return MPL_ERR_ARG;
+  for (int g = 0; g < a.groups; ++g)
+    if (a.B[g] == nullptr) return MPL_ERR_ARG;
+  // tile width: the lowest (waves x tile width x penalty) for the EXPECTED number of row tiles (rows spread evenly over
+  // the groups; m_total_hint = rows of all groups together, default = the capacity of every group)
+  const int sms = num_sms();
+  const int dual = a.B2[0] != nullptr;
+  const long long rows_total = a.m_total_hint > 0 ? a.m_total_hint : static_cast<long long>(a.M) * a.groups;
+  long long per_group = (rows_total + a.groups - 1) / a.groups;
+  if (per_group > a.M) per_group = a.M;
+  const long long m_tiles = a.groups * ((per_group + BM - 1) / BM);
+  auto cost = [&](int bn, double penalty) {
+    const int out_bn = dual ? bn / 2 : bn;
+    const long long tiles = m_tiles * ((a.N + out_bn - 1) / out_bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    return static_cast<double>(waves) * bn * penalty;
+  };
+  const double c256 = cost(256, 1.0), c192 = cost(192, 1.08), c128 = cost(128, 1.25);
+  if (c256 <= c192 && c256 <= c128) return launch_grouped<256>(a, stream);
+  if (c192 <= c128) return launch_grouped<192>(a, stream);
+  return launch_grouped<128>(a, stream);
 }
 
 }  // namespace mpl

@@ -22,6 +22,8 @@ int skinny_grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream
 int moe_route_small(const mpl_moe_route_args& a, const void* x, long long ldx, const void* ln_w, float eps, void* h,
                     long long ldh, void* xperm, int* tok_of_slot, float* gate_of_slot, cudaStream_t stream);
 int moe_route(const mpl_moe_route_args& a, cudaStream_t stream);
+int moe_norm_route(const mpl_moe_route_args& a, const void* x, long long ldx, const void* ln_w, float eps,
+                   cudaStream_t stream);  // RMSNorm fused into the router (D <= 4096), else MPL_ERR_UNSUPPORTED
 bool llama_decode_supported(const mpl_llama_model& m, const mpl_llama_io& io);
 long long llama_decode_plan_bytes(const mpl_llama_model& m);
 int llama_decode_plan_build(const mpl_llama_model& m, void* plan_dev, cudaStream_t st);

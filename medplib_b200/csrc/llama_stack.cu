@@ -250,8 +250,13 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
       MPL_TRY(moe_route_small(r, io.x, D, L.post_ln, m.rms_eps, w.h, D, gather ? nullptr : w.xperm, w.tok_of_slot,
                               w.gate_of_slot, st));
     } else {
-      MPL_TRY(mpl_rmsnorm(io.x, D, L.post_ln, w.h, D, S, D, m.rms_eps, st_));
-      MPL_TRY(moe_route(r, st));
+      const int frc = moe_norm_route(r, io.x, D, L.post_ln, m.rms_eps, st);  // RMSNorm fused into the router
+      if (frc == MPL_ERR_UNSUPPORTED) {
+        MPL_TRY(mpl_rmsnorm(io.x, D, L.post_ln, w.h, D, S, D, m.rms_eps, st_));
+        MPL_TRY(moe_route(r, st));
+      } else if (frc != MPL_OK) {
+        return frc;
+      }
       MPL_TRY(moe_dispatch(w.h, D, w.slot, w.xperm, S, m.top_k, D, st));
     }
     const bool fused_combine = fused_front && m.top_k == 1 && C <= 16;
@@ -279,6 +284,7 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
       g.N = F;
       g.K = D;
       g.out_dtype = MPL_DT_BF16;
+      g.m_total_hint = S * m.top_k;
       MPL_TRY(mpl_grouped_gemm_bf16(&g, st_));
       mpl_grouped_gemm_args d;
       memset(&d, 0, sizeof(d));
@@ -294,6 +300,7 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
       d.N = D;
       d.K = F;
       d.out_dtype = MPL_DT_BF16;
+      d.m_total_hint = S * m.top_k;
       if (fused_combine) {
         d.C = io.x;
         d.ldc = D;

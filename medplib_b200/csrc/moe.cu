@@ -72,6 +72,93 @@ __global__ void __launch_bounds__(128) moe_router_kernel(const __nv_bfloat16* __
   }
 }
 
+// RMSNorm fused into the router: h = w * bf16(x * rstd) (HF LlamaRMSNorm roundings, stored for the expert GEMMs) and
+// the router logits from the stored (rounded) h, one warp per token, the whole row in registers (D <= 4096: every
+// global load of the warp is issued before the first use -- one round trip instead of the sixteen of the generic loop).
+template <int NV>  // 16-byte vectors per lane = D / 256 rounded up
+__global__ void __launch_bounds__(128) moe_norm_router_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                              const __nv_bfloat16* __restrict__ ln_w, float eps,
+                                                              __nv_bfloat16* __restrict__ h, long long ldh,
+                                                              const float* __restrict__ wg, int S, int D, int E,
+                                                              float* __restrict__ logits, float* __restrict__ gates) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * 4 + warp;
+  if (s >= S) return;
+  const __nv_bfloat16* xr = x + static_cast<long long>(s) * ldx;
+  uint4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 8;
+    v[j] = c < D ? *reinterpret_cast<const uint4*>(xr + c) : make_uint4(0, 0, 0, 0);
+  }
+  float ss = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(hp[i]);
+      ss += f.x * f.x + f.y * f.y;
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / static_cast<float>(D) + eps);
+  float acc[MOE_MAX_E];
+#pragma unroll
+  for (int e = 0; e < MOE_MAX_E; ++e) acc[e] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = (j * 32 + lane) * 8;
+    if (c < D) {
+      const uint4 wr = *reinterpret_cast<const uint4*>(ln_w + c);
+      const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
+      const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&wr);
+      float hv[8];
+      uint4 o;
+      uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xf = __bfloat1622float2(xp[i]), wf = __bfloat1622float2(wp[i]);
+        hv[2 * i] = bf16_round(wf.x * bf16_round(xf.x * rstd));
+        hv[2 * i + 1] = bf16_round(wf.y * bf16_round(xf.y * rstd));
+        op[i] = pack_bf16(hv[2 * i], hv[2 * i + 1]);
+      }
+      *reinterpret_cast<uint4*>(h + static_cast<long long>(s) * ldh + c) = o;
+#pragma unroll
+      for (int e = 0; e < MOE_MAX_E; ++e) {
+        if (e < E) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wg + static_cast<long long>(e) * D + c));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(wg + static_cast<long long>(e) * D + c + 4));
+          acc[e] += hv[0] * w0.x + hv[1] * w0.y + hv[2] * w0.z + hv[3] * w0.w + hv[4] * w1.x + hv[5] * w1.y +
+                    hv[6] * w1.z + hv[7] * w1.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < MOE_MAX_E; ++e) acc[e] = warp_sum(acc[e]);
+  if (lane == 0) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e)
+      if (e < E) m = fmaxf(m, acc[e]);
+    float ex[MOE_MAX_E];
+    float sum = 0.0f;
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e)
+      if (e < E) {
+        ex[e] = expf(acc[e] - m);
+        sum += ex[e];
+      }
+#pragma unroll
+    for (int e = 0; e < MOE_MAX_E; ++e)
+      if (e < E) {
+        logits[static_cast<long long>(s) * E + e] = acc[e];
+        gates[static_cast<long long>(s) * E + e] = ex[e] / sum;
+      }
+  }
+}
+
 constexpr int SCAN_THREADS = 1024;
 
 __device__ __forceinline__ int block_sum_int(int v, int* red) {
@@ -600,6 +687,33 @@ __global__ void __launch_bounds__(SMALL_THREADS) moe_route_small_kernel(
   }
 }
 
+static int moe_scan_launch(const mpl_moe_route_args& a, cudaStream_t stream);
+
+// RMSNorm(x) -> h, router logits / gates, then the scan: what mpl_rmsnorm + moe_route do, in two launches instead of
+// three and without re-reading h. Returns MPL_ERR_UNSUPPORTED for widths the register-resident kernel does not cover.
+int moe_norm_route(const mpl_moe_route_args& a, const void* x, long long ldx, const void* ln_w, float eps,
+                   cudaStream_t stream) {
+  if (a.S <= 0) return MPL_OK;
+  if (a.D > 4096 || (a.D % 8) != 0 || (a.ldh % 8) != 0 || (ldx % 8) != 0) return MPL_ERR_UNSUPPORTED;
+  if (a.h == nullptr || x == nullptr || ln_w == nullptr || a.wg == nullptr || a.logits == nullptr || a.gates == nullptr)
+    return MPL_ERR_ARG;
+  if (a.E < 1 || a.E > MOE_MAX_E || a.k < 1 || a.k > 2 || a.k > a.E || a.capacity < 1) return MPL_ERR_UNSUPPORTED;
+  const dim3 grid((a.S + 3) / 4);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* lw = static_cast<const __nv_bfloat16*>(ln_w);
+  __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(const_cast<void*>(a.h));
+  const int nv = (a.D + 255) / 256;
+  if (nv <= 4)
+    moe_norm_router_kernel<4><<<grid, 128, 0, stream>>>(xb, ldx, lw, eps, hb, a.ldh, a.wg, a.S, a.D, a.E, a.logits, a.gates);
+  else if (nv <= 8)
+    moe_norm_router_kernel<8><<<grid, 128, 0, stream>>>(xb, ldx, lw, eps, hb, a.ldh, a.wg, a.S, a.D, a.E, a.logits, a.gates);
+  else
+    moe_norm_router_kernel<16><<<grid, 128, 0, stream>>>(xb, ldx, lw, eps, hb, a.ldh, a.wg, a.S, a.D, a.E, a.logits, a.gates);
+  const int rc = launch_status();
+  if (rc != MPL_OK) return rc;
+  return moe_scan_launch(a, stream);
+}
+
 int moe_route(const mpl_moe_route_args& a, cudaStream_t stream) {
   if (a.S <= 0) return MPL_OK;
   if (a.h == nullptr || a.wg == nullptr || a.logits == nullptr || a.gates == nullptr || a.expert == nullptr ||
@@ -609,6 +723,15 @@ int moe_route(const mpl_moe_route_args& a, cudaStream_t stream) {
   if ((a.D % 8) != 0 || (a.ldh % 8) != 0) return MPL_ERR_ALIGN;
   moe_router_kernel<<<(a.S + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(a.h), a.ldh, a.wg, a.S, a.D,
                                                       a.E, a.logits, a.gates);
+  const int rc = launch_status();
+  if (rc != MPL_OK) return rc;
+  return moe_scan_launch(a, stream);
+}
+
+static int moe_scan_launch(const mpl_moe_route_args& a, cudaStream_t stream) {
+  if (a.expert == nullptr || a.gate == nullptr || a.slot == nullptr || a.kept == nullptr || a.exp_counts == nullptr ||
+      a.l_aux == nullptr)
+    return MPL_ERR_ARG;
   size_t skey_bytes = 0;
   if (a.k == 1 && a.noise != nullptr && static_cast<size_t>(a.S) * 4 <= 160 * 1024) {
     skey_bytes = static_cast<size_t>(a.S) * 4;
@@ -622,7 +745,7 @@ int moe_route(const mpl_moe_route_args& a, cudaStream_t stream) {
   moe_scan_kernel<<<1, SCAN_THREADS, skey_bytes, stream>>>(a.logits, a.gates, a.noise, a.S, a.E, a.k, a.capacity, a.expert,
                                                            a.gate, a.slot, a.kept, a.exp_counts, a.l_aux,
                                                            skey_bytes > 0 ? 1 : 0);
-  return launch_status(2);
+  return launch_status();
 }
 
 int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D,

@@ -353,17 +353,18 @@ def test_foreign_optimizer_sees_ordinary_grads(dev):
     for n, g in want.items():
         p = params[n]
         assert p.grad is not None and p.grad.dtype == p.dtype and p.grad.shape == p.shape
-        a, w1 = p.grad.float(), g.to(p.dtype).float()  # (atomic accumulation orders differ from run to run)
-        assert (a - w1).abs().max() <= 1e-2 * w1.abs().max() + 1e-12, n
+        a, w1 = p.grad.float(), g.to(p.dtype).float()  # (atomic accumulation orders differ from run to run; a key bias
+        # has a mathematically zero gradient -- softmax is shift invariant -- so its value is rounding noise: absolute floor)
+        assert (a - w1).abs().max() <= 1e-2 * w1.abs().max() + 1e-4, n
     left = {n: float(g.abs().max()) for n, g in tr.arena.grads().items() if float(g.abs().max()) != 0.0}
     assert not left, f"arena not handed over clean: {left}"  # the next micro-step starts from zero
     fwd()["loss"].backward()  # accumulation is autograd's now
     for n in ("lm_head.weight", "model.text_hidden_fcs.0.2.weight"):
         a, w2 = params[n].grad.float(), 2 * want[n].to(params[n].dtype).float()
-        assert (a - w2).abs().max() <= 2e-2 * w2.abs().max() + 1e-12, n
+        assert (a - w2).abs().max() <= 2e-2 * w2.abs().max() + 1e-4, n
     with pytest.raises(Exception):
         tr.step()
-    opt = torch.optim.SGD([params[n] for n in want], lr=0.05)
+    opt = torch.optim.SGD([params[n] for n in want], lr=1e-3)  # (.grad holds two accumulated backward passes)
     opt.step()
     opt.zero_grad()
     loss1 = fwd()["loss"]
