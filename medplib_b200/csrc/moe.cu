@@ -73,23 +73,24 @@ __global__ void __launch_bounds__(128) moe_router_kernel(const __nv_bfloat16* __
 }
 
 // RMSNorm fused into the router: h = w * bf16(x * rstd) (HF LlamaRMSNorm roundings, stored for the expert GEMMs) and
-// the router logits from the stored (rounded) h, one warp per token, the whole row in registers (D <= 4096: every
-// global load of the warp is issued before the first use -- one round trip instead of the sixteen of the generic loop).
-template <int NV>  // 16-byte vectors per lane = D / 256 rounded up
+// the router logits from the stored (rounded) h. One 128-thread CTA per token, the row in registers (D <= 4096: every
+// global load is issued before the first use), lane -> warp (shuffles) -> CTA (shared memory, fixed order) reductions.
 __global__ void __launch_bounds__(128) moe_norm_router_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                               const __nv_bfloat16* __restrict__ ln_w, float eps,
                                                               __nv_bfloat16* __restrict__ h, long long ldh,
-                                                              const float* __restrict__ wg, int S, int D, int E,
+                                                              const float* __restrict__ wg, int D, int E,
                                                               float* __restrict__ logits, float* __restrict__ gates) {
+  constexpr int NV = 4;  // 16-byte vectors per thread: D <= 128 * 4 * 8
+  __shared__ float red[4][MOE_MAX_E + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = blockIdx.x * 4 + warp;
-  if (s >= S) return;
+  const int s = blockIdx.x;
   const __nv_bfloat16* xr = x + static_cast<long long>(s) * ldx;
-  uint4 v[NV];
+  uint4 v[NV], wr[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const int c = (j * 32 + lane) * 8;
+    const int c = (j * 128 + threadIdx.x) * 8;
     v[j] = c < D ? *reinterpret_cast<const uint4*>(xr + c) : make_uint4(0, 0, 0, 0);
+    wr[j] = c < D ? *reinterpret_cast<const uint4*>(ln_w + c) : make_uint4(0, 0, 0, 0);
   }
   float ss = 0.0f;
 #pragma unroll
@@ -102,17 +103,19 @@ __global__ void __launch_bounds__(128) moe_norm_router_kernel(const __nv_bfloat1
     }
   }
   ss = warp_sum(ss);
-  const float rstd = rsqrtf(ss / static_cast<float>(D) + eps);
+  if (lane == 0) red[warp][MOE_MAX_E] = ss;
+  __syncthreads();
+  const float rstd = rsqrtf((((red[0][MOE_MAX_E] + red[1][MOE_MAX_E]) + red[2][MOE_MAX_E]) + red[3][MOE_MAX_E]) /
+                                static_cast<float>(D) + eps);
   float acc[MOE_MAX_E];
 #pragma unroll
   for (int e = 0; e < MOE_MAX_E; ++e) acc[e] = 0.0f;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const int c = (j * 32 + lane) * 8;
+    const int c = (j * 128 + threadIdx.x) * 8;
     if (c < D) {
-      const uint4 wr = *reinterpret_cast<const uint4*>(ln_w + c);
       const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&v[j]);
-      const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&wr);
+      const __nv_bfloat162* wp = reinterpret_cast<const __nv_bfloat162*>(&wr[j]);
       float hv[8];
       uint4 o;
       uint32_t* op = reinterpret_cast<uint32_t*>(&o);
@@ -136,24 +139,33 @@ __global__ void __launch_bounds__(128) moe_norm_router_kernel(const __nv_bfloat1
     }
   }
 #pragma unroll
-  for (int e = 0; e < MOE_MAX_E; ++e) acc[e] = warp_sum(acc[e]);
-  if (lane == 0) {
+  for (int e = 0; e < MOE_MAX_E; ++e)
+    if (e < E) {
+      acc[e] = warp_sum(acc[e]);
+      if (lane == 0) red[warp][e] = acc[e];
+    }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float lg[MOE_MAX_E];
     float m = -INFINITY;
 #pragma unroll
     for (int e = 0; e < MOE_MAX_E; ++e)
-      if (e < E) m = fmaxf(m, acc[e]);
+      if (e < E) {
+        lg[e] = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
+        m = fmaxf(m, lg[e]);
+      }
     float ex[MOE_MAX_E];
     float sum = 0.0f;
 #pragma unroll
     for (int e = 0; e < MOE_MAX_E; ++e)
       if (e < E) {
-        ex[e] = expf(acc[e] - m);
+        ex[e] = expf(lg[e] - m);
         sum += ex[e];
       }
 #pragma unroll
     for (int e = 0; e < MOE_MAX_E; ++e)
       if (e < E) {
-        logits[static_cast<long long>(s) * E + e] = acc[e];
+        logits[static_cast<long long>(s) * E + e] = lg[e];
         gates[static_cast<long long>(s) * E + e] = ex[e] / sum;
       }
   }
@@ -698,17 +710,10 @@ int moe_norm_route(const mpl_moe_route_args& a, const void* x, long long ldx, co
   if (a.h == nullptr || x == nullptr || ln_w == nullptr || a.wg == nullptr || a.logits == nullptr || a.gates == nullptr)
     return MPL_ERR_ARG;
   if (a.E < 1 || a.E > MOE_MAX_E || a.k < 1 || a.k > 2 || a.k > a.E || a.capacity < 1) return MPL_ERR_UNSUPPORTED;
-  const dim3 grid((a.S + 3) / 4);
-  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
-  const __nv_bfloat16* lw = static_cast<const __nv_bfloat16*>(ln_w);
-  __nv_bfloat16* hb = static_cast<__nv_bfloat16*>(const_cast<void*>(a.h));
-  const int nv = (a.D + 255) / 256;
-  if (nv <= 4)
-    moe_norm_router_kernel<4><<<grid, 128, 0, stream>>>(xb, ldx, lw, eps, hb, a.ldh, a.wg, a.S, a.D, a.E, a.logits, a.gates);
-  else if (nv <= 8)
-    moe_norm_router_kernel<8><<<grid, 128, 0, stream>>>(xb, ldx, lw, eps, hb, a.ldh, a.wg, a.S, a.D, a.E, a.logits, a.gates);
-  else
-    moe_norm_router_kernel<16><<<grid, 128, 0, stream>>>(xb, ldx, lw, eps, hb, a.ldh, a.wg, a.S, a.D, a.E, a.logits, a.gates);
+  moe_norm_router_kernel<<<a.S, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                                 static_cast<const __nv_bfloat16*>(ln_w), eps,
+                                                 static_cast<__nv_bfloat16*>(const_cast<void*>(a.h)), a.ldh, a.wg, a.D, a.E,
+                                                 a.logits, a.gates);
   const int rc = launch_status();
   if (rc != MPL_OK) return rc;
   return moe_scan_launch(a, stream);

@@ -159,26 +159,63 @@ __global__ void __launch_bounds__(NORM_THREADS) pool_ln_kernel(const __nv_bfloat
   __nv_bfloat16* yr = y + (static_cast<long long>(n) * Tout + i) * D;
   float v[NORM_MAX_VEC][8];
   float s = 0.0f;
+  const int nt = t1 - t0;
+  constexpr int WMAX = 4;  // windows of up to 4 tokens (576 -> 256: always 3) have every load in flight before the first use
+  if (nt <= WMAX) {
+    uint4 raw[NORM_MAX_VEC][WMAX];
 #pragma unroll
-  for (int k = 0; k < NORM_MAX_VEC; ++k) {
-    const int c = (k * NORM_THREADS + threadIdx.x) * 8;
-    if (c < D) {
+    for (int k = 0; k < NORM_MAX_VEC; ++k) {
+      const int c = (k * NORM_THREADS + threadIdx.x) * 8;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[k][e] = 0.0f;
-      for (int t = 0; t < t1 - t0; ++t) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(t) * D + c);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      for (int t = 0; t < WMAX; ++t)
+        raw[k][t] = (c < D && t < nt) ? *reinterpret_cast<const uint4*>(xb + static_cast<long long>(t) * D + c)
+                                      : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(h[e]);
-          v[k][2 * e] += f.x;
-          v[k][2 * e + 1] += f.y;
+    for (int k = 0; k < NORM_MAX_VEC; ++k) {
+      const int c = (k * NORM_THREADS + threadIdx.x) * 8;
+      if (c < D) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[k][e] = 0.0f;
+#pragma unroll
+        for (int t = 0; t < WMAX; ++t) {  // (absent tokens are +0: the sum is unchanged, same order as the loop below)
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[k][t]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            v[k][2 * e] += f.x;
+            v[k][2 * e + 1] += f.y;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[k][e] = bf16_round(v[k][e] * inv);
+          s += v[k][e];
         }
       }
+    }
+  } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        v[k][e] = bf16_round(v[k][e] * inv);
-        s += v[k][e];
+    for (int k = 0; k < NORM_MAX_VEC; ++k) {
+      const int c = (k * NORM_THREADS + threadIdx.x) * 8;
+      if (c < D) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[k][e] = 0.0f;
+        for (int t = 0; t < nt; ++t) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(xb + static_cast<long long>(t) * D + c);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            v[k][2 * e] += f.x;
+            v[k][2 * e + 1] += f.y;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[k][e] = bf16_round(v[k][e] * inv);
+          s += v[k][e];
+        }
       }
     }
   }

@@ -1173,15 +1173,36 @@ __global__ void __launch_bounds__(128) scatter_add_rows_kernel(const bf16_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------- optimizer
+// DETERMINISTIC: every data-parallel rank must derive the same clip factor from the same (all-reduced) gradients, or the
+// replicas' parameters drift apart one ulp at a time. Block partials go to a scratch array; the last block to finish
+// (atomic ticket) adds them in index order. *out is ADDED to (callers zero it), like the atomic version it replaces.
+constexpr int SUMSQ_MAX_BLOCKS = 1024;
+__device__ float g_sumsq_partial[SUMSQ_MAX_BLOCKS];
+__device__ unsigned int g_sumsq_ticket = 0;
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   __shared__ float red[8];
+  __shared__ bool last;
   float acc = 0.0f;
   for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256) {
     const float v = g[i];
     acc += v * v;
   }
   acc = block_sum_t<256>(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) {
+    g_sumsq_partial[blockIdx.x] = acc;
+    __threadfence();
+    last = atomicAdd(&g_sumsq_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.0f;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) t += __ldcg(&g_sumsq_partial[i]);  // fixed assignment
+  t = block_sum_t<256>(t, red);                                                                   // fixed tree
+  if (threadIdx.x == 0) {
+    *out += t;
+    g_sumsq_ticket = 0;  // ready for the next launch (launches on one stream are serialised)
+  }
 }
 // AdamW (torch.optim.AdamW / DeepSpeed FusedAdam adam_w_mode): fp32 master + moments; clip = min(1, max_norm/(norm+1e-6))
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ master, float* __restrict__ m, float* __restrict__ v,
@@ -1550,6 +1571,7 @@ extern "C" int mpl_sumsq_f32(const float* g, long long n, float* out, void* stre
   if (g == nullptr || out == nullptr) return MPL_ERR_ARG;
   long long blocks = (n + 255) / 256;
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  if (blocks > SUMSQ_MAX_BLOCKS) blocks = SUMSQ_MAX_BLOCKS;
   sumsq_kernel<<<static_cast<unsigned>(blocks), 256, 0, ST(stream)>>>(g, n, out);
   return launch_status();
 }

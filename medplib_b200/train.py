@@ -16,6 +16,7 @@ Design (B200-first, 180 GB per GPU):
   is ours. There is no eager fallback: CPU tensors raise MplError.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -144,9 +145,15 @@ class BucketReducer:
     """Data-parallel gradient exchange: all-reduce(mean) of the arena in fixed-size buckets, each
     launched asynchronously as soon as the backward has passed its end, on the process group's own stream."""
 
-    def __init__(self, arena, bucket_elems=64 << 20, group=None):
+    def __init__(self, arena, bucket_elems=64 << 20, group=None, wire_dtype=None):
+        """wire_dtype: the dtype on the wire. Default bf16 on CUDA -- what the reference exchanges (DeepSpeed reduces the
+        bf16 gradients of a bf16 engine, train_ds_medplib.py:408-419): half the bytes of the fp32 arena, 636 MB per step
+        for the stage-4 trainable set as SURVEY 2.2 counts it; the sum lands back in the fp32 arena. fp32 elsewhere."""
         import torch.distributed as dist
         self.dist, self.arena, self.group = dist, arena, group
+        if wire_dtype is None:
+            wire_dtype = bf16 if arena.flat.is_cuda and os.environ.get("MPL_DP_WIRE", "bf16") == "bf16" else f32
+        self.wire = wire_dtype
         self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.world = dist.get_world_size(group) if self.on else 1
         n = arena.numel
@@ -165,16 +172,19 @@ class BucketReducer:
             if self.next == 0 and self.owner is not None:
                 self.launch_micro_step = self.owner.micro_steps
             a, b = self.bounds[self.next]
-            self.work.append(self.dist.all_reduce(self.arena.flat[a:b], op=self.dist.ReduceOp.SUM, group=self.group,
-                                                  async_op=True))
+            buf = self.arena.flat[a:b] if self.wire == f32 else self.arena.flat[a:b].to(self.wire)
+            self.work.append((self.dist.all_reduce(buf, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True),
+                              a, b, buf))
             self.next += 1
 
     def finish(self):
         """Launch what is left and make the current stream wait for every bucket. Returns 1/world (the mean factor the
         optimizer folds into its gradient scale)."""
         self.ready(self.arena.numel)
-        for w in self.work:
+        for w, a, b, buf in self.work:
             w.wait()
+            if self.wire != f32:
+                self.arena.flat[a:b].copy_(buf)
         self.reset()
         return 1.0 / self.world
 

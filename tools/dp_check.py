@@ -51,10 +51,16 @@ def spy(upto):
 tr.reducer.ready = spy
 got = run(5 + rank, True)
 err = (got - expect).abs().max().item() / expect.abs().max().item()
-# fp32 atomics make the per-rank gradients run-to-run non-bit-identical; the reduced mean must match to fp32 noise
-assert err < 2e-3, f"rank {rank}: reduced gradient differs from the mean of per-rank gradients: {err}"
+# fp32 atomics make the per-rank gradients run-to-run non-bit-identical; the reduced mean must match to the noise of the
+# wire format (bf16 by default, like the reference's bf16 engine: one rounding of every addend, 2^-9 relative)
+tol = 2e-3 if tr.reducer.wire == torch.float32 else 6e-3
+assert err < tol, f"rank {rank}: reduced gradient differs from the mean of per-rank gradients: {err}"
 assert max(launched_early[:-1] or [0]) > 0, "no bucket was launched before the backward finished"
 tr.reducer.ready = orig_ready
+got0 = got.clone()
+dist.broadcast(got0, 0)
+assert torch.equal(got, got0), (f"rank {rank}: the all-reduced arena differs from rank 0's: max diff "
+                                f"{(got - got0).abs().max().item():.3e} at {int((got - got0).abs().argmax())} of {got.numel()}")
 # one optimizer step from the reduced arena: parameters must stay identical across ranks
 tr.arena.flat.copy_(got / (1.0 / world))
 tr.reducer.reset()
