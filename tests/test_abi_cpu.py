@@ -67,9 +67,10 @@ def test_product_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".h", ".cuh")):
                     txt = open(os.path.join(dirpath, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f"{top}/{f} imports the oracle"
-    # bench.py: only inside the CPU legs (cpu_reference / cpu_preprocess / _pre_one), never at module level
+    # bench.py: only inside the CPU legs (the reference arm's weights + one-image pass, the input pipeline's port), never
+    # at module level
     bench = open(os.path.join(ROOT, "bench.py")).read()
     assert not re.search(r"^(from|import)\s+oracle\b", bench, re.M)
     for m in re.finditer(r"^\s+from oracle import", bench, re.M):
         fn = re.findall(r"^def (\w+)\(", bench[:m.start()], re.M)[-1]
-        assert fn in ("cpu_reference", "cpu_preprocess", "_pre_one"), f"bench.py:{fn} imports the oracle"
+        assert fn in ("_cpu_state", "cpu_image", "cpu_preprocess", "_pre_one"), f"bench.py:{fn} imports the oracle"

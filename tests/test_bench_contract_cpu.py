@@ -14,7 +14,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def final_lines():
-    return sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_*_final.json")))
+    return sorted(glob.glob(os.path.join(ROOT, "profiles", "r0[12]_bench_*_final.json")))
 
 
 @pytest.mark.parametrize("path", final_lines(), ids=os.path.basename)
@@ -38,6 +38,25 @@ def test_committed_bench_lines_follow_the_contract(path):
 def test_there_is_a_final_line_for_the_headline_workload():
     names = [os.path.basename(p) for p in final_lines()]
     assert "r01_bench_grounding_final.json" in names
+
+
+def test_round2_line_carries_every_baseline_config():
+    """Round 2: ONE line per default run -- the grounding headline with decode / train / icl under `secondary`, each
+    with its own e2e, clocks and roofline; the dominant-kernel roofline entry is the decode kernel (HBM bound)."""
+    path = os.path.join(ROOT, "profiles", "r02_bench_all_final.json")
+    if not os.path.exists(path):
+        pytest.skip("no round-2 final line committed yet")
+    line = json.loads(open(path).read().strip().splitlines()[-1])
+    assert BASE_KEYS <= set(line) and line["unit"] == "images/s"
+    assert line["roofline"]["bound"] == "hbm" and "llama_decode_kernel" in line["roofline"]["kernel"]
+    assert line["roofline_gemm"]["bound"] == "tensor"
+    assert set(line["secondary"]) == {"decode", "train", "icl"}
+    for name, unit in (("decode", "tokens/s"), ("train", "samples/s"), ("icl", "images/s")):
+        sec = line["secondary"][name]
+        assert "error" not in sec, sec
+        assert sec["unit"] == unit and sec["value"] > 0 and sec["e2e"]["h2d_bytes_per_step"] > 0
+        assert 0 < sec["roofline"]["frac"] < 1.2 and sec["clocks"]["sm_mhz"]
+    assert line["cpu_baseline"]["kind"] == "port" and "FULL depth" in line["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_of_the_input_pipeline_runs_on_cpu():
