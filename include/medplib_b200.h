@@ -73,7 +73,7 @@ typedef struct {
   int nb;        /* number of weight matrices, 1..3 */
   int act;       /* MPL_ACT_* */
   int out_dtype; /* MPL_DT_* */
-  int tile_n;    /* 0 = auto, else 128, 192 or 256 */
+  int tile_n;    /* 0 = auto, else a multiple of 16 in [128, 256] (144, 160, ... 256 are compiled in) */
   const void* ln_weight; /* streaming (M <= 16) path only: fused LlamaRMSNorm prologue on A, bf16 [K] or NULL */
   float ln_eps;
 } mpl_gemm_args;
@@ -119,6 +119,7 @@ typedef struct {
                        stream may start before the dependency wait (programmatic dependent launch) */
   int m_total_hint; /* 0, or the number of rows all groups hold together (host-side estimate, e.g. S * top_k): picks the
                        tile width of the tensor-core path; the true per-group counts are always read from m_dev */
+  int tile_n;       /* 0 = auto, else a multiple of 16 in [128, 256] (tensor-core path only) */
 } mpl_grouped_gemm_args;
 int mpl_grouped_gemm_bf16(const mpl_grouped_gemm_args* args, void* stream);
 

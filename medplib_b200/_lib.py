@@ -41,7 +41,7 @@ class GroupedGemmArgs(ctypes.Structure):
         ("residual", c_void_p), ("ldr", c_ll), ("m_dev", c_void_p), ("a_row_map", c_void_p),
         ("row_map", c_void_p), ("row_gate", c_void_p), ("map_group_stride", c_ll),
         ("groups", c_int), ("M", c_int), ("N", c_int), ("K", c_int), ("act", c_int), ("out_dtype", c_int),
-        ("m_dev_stable", c_int), ("m_total_hint", c_int),
+        ("m_dev_stable", c_int), ("m_total_hint", c_int), ("tile_n", c_int),
     ]
 
 

@@ -1,9 +1,19 @@
 // Library probe entry points of the C ABI.
 #include "internal.h"
 
+#include <cstdlib>
+
 namespace mpl {
 unsigned long long g_launches = 0;
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MPL_PDL");
+    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return on != 0;
 }
+}  // namespace mpl
 
 extern "C" int mpl_version(void) { return 1; }
 extern "C" long long mpl_launch_count(void) { return static_cast<long long>(mpl::g_launches); }

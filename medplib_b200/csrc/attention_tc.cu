@@ -136,6 +136,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  griddep_wait();  // programmatic dependent launch: q, k, v of the previous kernels are read from here on
+  griddep_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -394,7 +396,7 @@ static int launch_attn_tc(const mpl_attn_args& a, cudaStream_t stream) {
   p.causal = a.causal;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   dim3 grid((a.Tq + AT_BM - 1) / AT_BM, a.B * a.H);
-  attn_fwd_tcgen05_kernel<D><<<grid, AT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  launch_pdl(attn_fwd_tcgen05_kernel<D>, grid, dim3(AT_THREADS), Cfg::SMEM_BYTES, stream, tmQ, tmK, tmV, p);
   return launch_status();
 }
 

@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -131,11 +132,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  // BN: any multiple of 16 in [128, 256] (the UMMA N of a 128-row tile); the launcher picks the width whose tile count
+  // fills the 148 SMs best (M = 615 prefill: 145 tiles of 144 columns for o_proj instead of 110 of 192)
+  static_assert(BN % 16 == 0 && BN >= 128 && BN <= 256, "tile width");
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int ACC_STRIDE = (BN == 192) ? 256 : BN;  // column offset between the two accumulator stages
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;           // power of two >= 32
+  static constexpr int STAGES_FIT = (232448 - 1024 - 256 - 512 /*static smem*/) / (A_BYTES + B_BYTES);
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // column offset between the two accumulator stages
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;          // power of two >= 32
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -161,7 +166,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int out_bn = p.dual ? BN / 2 : BN;
   __shared__ TileSpace ts;  // (per-group tile counts are indexed dynamically: shared memory, not a local array)
-  if (threadIdx.x == 0) ts = make_tile_space(p, out_bn);
   const int kblocks = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -180,6 +184,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  // programmatic dependent launch: everything above overlapped the previous kernel's tail; its outputs (A, the residual,
+  // the device-side row counts) are touched only from here on
+  griddep_wait();
+  griddep_launch_dependents();
+  if (threadIdx.x == 0) ts = make_tile_space(p, out_bn);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -283,8 +292,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
       const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.0f;
       const bool f32 = p.out_f32 != 0;
+      const int nlim = min(p.N, n0 + out_bn);  // columns of this tile (the last 32-column chunk may be partial)
 #pragma unroll 1
-      for (int c = 0; c < out_bn / 32; ++c) {
+      for (int c = 0; c < (out_bn + 31) / 32; ++c) {
         uint32_t r[32];
         float v[32];
         tmem_ld_32x32(t_row + c * 32, r);
@@ -306,12 +316,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int nc = n0 + c * 32;
-        if (nc >= p.N || !row_ok) continue;
-        const bool full = (nc + 32 <= p.N);
+        if (nc >= nlim || !row_ok) continue;
+        const bool full = (nc + 32 <= nlim);
         if (bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (full || nc + j < p.N) v[j] += __bfloat162float(bias[nc + j]);
+            if (full || nc + j < nlim) v[j] += __bfloat162float(bias[nc + j]);
         }
         if (p.act != MPL_ACT_NONE) {
 #pragma unroll
@@ -342,7 +352,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) v[j] += __bfloat162float(rp[j]);
+              if (nc + j < nlim) v[j] += __bfloat162float(rp[j]);
           }
         }
         if (f32) {
@@ -354,7 +364,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) cp[j] = v[j];
+              if (nc + j < nlim) cp[j] = v[j];
           }
         } else {
           __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<long long>(row) * p.ldc + nc;
@@ -368,10 +378,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
               *reinterpret_cast<uint4*>(cp + q * 8) = o;
             }
+          } else if (vec_ok) {
+            // partial chunk (tile widths that are not a multiple of 32, or the matrix edge): whole 8-column groups
+            // still go out as 16-byte stores
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (nc + q * 8 + 8 <= nlim) {
+                uint4 o;
+                o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                *reinterpret_cast<uint4*>(cp + q * 8) = o;
+              } else {
+#pragma unroll
+                for (int j = q * 8; j < q * 8 + 8; ++j)
+                  if (nc + j < nlim) cp[j] = __float2bfloat16_rn(v[j]);
+              }
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) cp[j] = __float2bfloat16_rn(v[j]);
+              if (nc + j < nlim) cp[j] = __float2bfloat16_rn(v[j]);
           }
         }
       }
@@ -472,6 +500,37 @@ int num_sms() {
   return g_num_sms;
 }
 
+// Tile widths compiled in (UMMA N of a 128-row tile: any multiple of 16; these cover the wave counts that matter).
+#define MPL_TILE_WIDTHS(X) X(128) X(144) X(160) X(176) X(192) X(208) X(224) X(240) X(256)
+
+// Pick the tile width with the lowest (waves x per-tile time) estimate for `m_tiles` row tiles (x weight matrices) of an
+// N-column output on a persistent grid of one CTA per SM. Measured on B200 (tools/gemm_tiles.py, profiles/
+// r02_gemm_tile_widths.md): at prefill sizes the kernel is bound by the L2 -> shared-memory fill (~100 GB/s per SM,
+// 13-15 TB/s over the chip), so a tile costs ~ the bytes it stages per k-block, (128 + width) rows, plus a fixed part;
+// widths that leave only 4 ring stages (240, 256) pay ~10 % more. Ties go to the wider tile.
+static int pick_tile_n(long long m_tiles, int N, int dual) {
+  const int sms = num_sms();
+  static const int widths[] = {
+#define MPL_BN_LIST(W) W,
+      MPL_TILE_WIDTHS(MPL_BN_LIST)
+#undef MPL_BN_LIST
+  };
+  int best = 256;
+  double best_cost = 0.0;
+  for (int i = static_cast<int>(sizeof(widths) / sizeof(widths[0])) - 1; i >= 0; --i) {
+    const int bn = widths[i];
+    const int out_bn = dual ? bn / 2 : bn;
+    const long long tiles = m_tiles * ((N + out_bn - 1) / out_bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double c = static_cast<double>(waves) * (bn + 150) * (bn > 224 ? 1.1 : 1.0);
+    if (i == static_cast<int>(sizeof(widths) / sizeof(widths[0])) - 1 || c < best_cost) {
+      best = bn;
+      best_cost = c;
+    }
+  }
+  return best;
+}
+
 template <int BN>
 static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -531,7 +590,8 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   p.a_group_rows = 0;
   p.c_group_stride = 0;
   static const GroupMaps no_groups = {};
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB1, tmB2, p, no_groups);
+  launch_pdl(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmB1, tmB2, p,
+             no_groups);
   if (prof) cudaEventRecord(prof_event(), stream);
   return mpl::launch_status();
 }
@@ -539,25 +599,19 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return MPL_OK;
   if (a.K <= 0 || a.A == nullptr || a.B[0] == nullptr || a.C[0] == nullptr) return MPL_ERR_ARG;
-  if (a.tile_n == 128) return launch_gemm<128>(a, stream);
-  if (a.tile_n == 192) return launch_gemm<192>(a, stream);
-  if (a.tile_n == 256) return launch_gemm<256>(a, stream);
-  if (a.tile_n != 0) return MPL_ERR_ARG;
-  // Pick the tile width with the lowest (waves x per-tile time) estimate. Per-tile time is ~ proportional to the
-  // tile width; the narrower tiles carry a measured efficiency penalty (A traffic per flop, fewer MMAs in flight).
-  const int sms = num_sms();
   const int dual = a.B2 != nullptr;
   const int nb = a.nb < 1 ? 1 : a.nb;
-  auto cost = [&](int bn, double penalty) {
-    const int out_bn = dual ? bn / 2 : bn;
-    const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn) * nb;
-    const long long waves = (tiles + sms - 1) / sms;
-    return static_cast<double>(waves) * bn * penalty;
-  };
-  const double c256 = cost(256, 1.0), c192 = cost(192, 1.08), c128 = cost(128, 1.25);
-  if (c256 <= c192 && c256 <= c128) return launch_gemm<256>(a, stream);
-  if (c192 <= c128) return launch_gemm<192>(a, stream);
-  return launch_gemm<128>(a, stream);
+  int bn = a.tile_n;
+  if (bn == 0) bn = pick_tile_n(static_cast<long long>((a.M + BM - 1) / BM) * nb, a.N, dual);
+  switch (bn) {
+#define MPL_BN_CASE(W) \
+  case W:              \
+    return launch_gemm<W>(a, stream);
+    MPL_TILE_WIDTHS(MPL_BN_CASE)
+#undef MPL_BN_CASE
+    default:
+      return MPL_ERR_ARG;
+  }
 }
 
 template <int BN>
@@ -606,7 +660,8 @@ static int launch_grouped(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
   if (grid < 1) grid = 1;
   const bool prof = g_prof && !g_prof_suppress;
   if (prof) cudaEventRecord(prof_event(), stream);
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, gm.b[0], gm.b[0], gm.b[0], p, gm);
+  launch_pdl(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, gm.b[0], gm.b[0],
+             gm.b[0], p, gm);
   if (prof) cudaEventRecord(prof_event(), stream);
   return mpl::launch_status();
 }
@@ -622,22 +677,22 @@ int grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
     if (a.B[g] == nullptr) return MPL_ERR_ARG;
   // tile width: the lowest (waves x tile width x penalty) for the EXPECTED number of row tiles (rows spread evenly over
   // the groups; m_total_hint = rows of all groups together, default = the capacity of every group)
-  const int sms = num_sms();
   const int dual = a.B2[0] != nullptr;
   const long long rows_total = a.m_total_hint > 0 ? a.m_total_hint : static_cast<long long>(a.M) * a.groups;
   long long per_group = (rows_total + a.groups - 1) / a.groups;
   if (per_group > a.M) per_group = a.M;
   const long long m_tiles = a.groups * ((per_group + BM - 1) / BM);
-  auto cost = [&](int bn, double penalty) {
-    const int out_bn = dual ? bn / 2 : bn;
-    const long long tiles = m_tiles * ((a.N + out_bn - 1) / out_bn);
-    const long long waves = (tiles + sms - 1) / sms;
-    return static_cast<double>(waves) * bn * penalty;
-  };
-  const double c256 = cost(256, 1.0), c192 = cost(192, 1.08), c128 = cost(128, 1.25);
-  if (c256 <= c192 && c256 <= c128) return launch_grouped<256>(a, stream);
-  if (c192 <= c128) return launch_grouped<192>(a, stream);
-  return launch_grouped<128>(a, stream);
+  int bn = a.tile_n;
+  if (bn == 0) bn = pick_tile_n(m_tiles, a.N, dual);
+  switch (bn) {
+#define MPL_BN_CASE(W) \
+  case W:              \
+    return launch_grouped<W>(a, stream);
+    MPL_TILE_WIDTHS(MPL_BN_CASE)
+#undef MPL_BN_CASE
+    default:
+      return MPL_ERR_ARG;
+  }
 }
 
 }  // namespace mpl

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "../../include/medplib_b200.h"
 
 namespace mpl {
@@ -12,6 +14,27 @@ inline int launch_status(int n = 1) {
   return cudaGetLastError() == cudaSuccess ? MPL_OK : MPL_ERR_CUDA;
 }
 int num_sms();
+
+// Programmatic dependent launch: the kernel may become resident (and run its prologue up to its griddep_wait()) while the
+// previous kernel of the stream is still finishing. ONLY for kernels that execute griddep_wait() before their first
+// read or write of global memory another kernel may touch. MPL_PDL=0 in the environment turns the attribute off.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 int encode_tmap_bf16(void* out, const void* ptr, int rank, const unsigned long long* dims,
                      const unsigned long long* strides_bytes, const unsigned* box);
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream);

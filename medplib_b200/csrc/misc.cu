@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(__nv_bfloat16* __restrict_
                                                       __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc,
                                                       int T, int H, int hd, int Tmax, int pos0,
                                                       const int* __restrict__ pos_dev) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   const int row = blockIdx.x;
   const int b = row / T, t = row % T;
   const int pos = (pos_dev ? *pos_dev : pos0) + t;
@@ -85,6 +87,8 @@ __global__ void __launch_bounds__(128) gather_rows_kernel(const __nv_bfloat16* _
                                                           const __nv_bfloat16* __restrict__ feats, long long ldf,
                                                           const int* __restrict__ idx, __nv_bfloat16* __restrict__ out,
                                                           long long ldo, int D) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   const int r = blockIdx.x;
   const int i = idx[r];
   uint4* o = reinterpret_cast<uint4*>(out + static_cast<long long>(r) * ldo);
@@ -356,6 +360,8 @@ __global__ void __launch_bounds__(128) convt4s2_col2im_kernel(const float* __res
 __global__ void __launch_bounds__(256) add_kernel(const __nv_bfloat16* __restrict__ a, const void* __restrict__ b,
                                                   int b_f32, __nv_bfloat16* __restrict__ out, long long n,
                                                   long long b_period) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   const long long i = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) * 8;
   if (i >= n) return;
   const long long j = i % b_period;
@@ -459,7 +465,7 @@ extern "C" int mpl_rope_kv(void* q, void* k, const void* v, long long ld, const 
   if (cos_t == nullptr || sin_t == nullptr || (q == nullptr && k == nullptr)) return MPL_ERR_ARG;
   if ((head_dim % 16) != 0 || (ld % 8) != 0) return MPL_ERR_ALIGN;
   if (k_cache != nullptr && pos_dev == nullptr && pos0 + T > Tmax) return MPL_ERR_ARG;
-  rope_kv_kernel<<<B * T, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(rope_kv_kernel, dim3(B * T), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<bf*>(q), static_cast<bf*>(k), static_cast<const bf*>(v), ld, static_cast<const bf*>(cos_t),
       static_cast<const bf*>(sin_t), static_cast<bf*>(k_cache), static_cast<bf*>(v_cache), T, H, head_dim, Tmax, pos0,
       pos_dev);
@@ -471,7 +477,7 @@ extern "C" int mpl_gather_rows(const void* table, long long ld_table, const void
   if (rows <= 0) return MPL_OK;
   if (idx == nullptr || out == nullptr) return MPL_ERR_ARG;
   if ((D % 8) != 0 || (ld_table % 8) != 0 || (ld_feats % 8) != 0 || (ld_out % 8) != 0) return MPL_ERR_ALIGN;
-  gather_rows_kernel<<<rows, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(gather_rows_kernel, dim3(rows), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const bf*>(table), ld_table, static_cast<const bf*>(feats), ld_feats, idx, static_cast<bf*>(out),
       ld_out, D);
   return launched();
@@ -556,7 +562,7 @@ extern "C" int mpl_add(const void* a, const void* b, int b_is_f32, void* out, lo
   if (n <= 0) return MPL_OK;
   if (a == nullptr || b == nullptr || out == nullptr) return MPL_ERR_ARG;
   if ((n % 8) != 0 || b_period <= 0 || (b_period % 8) != 0) return MPL_ERR_ALIGN;
-  add_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(add_kernel, dim3(static_cast<unsigned>((n / 8 + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const bf*>(a), b, b_is_f32, static_cast<bf*>(out), n, b_period);
   return launched();
 }

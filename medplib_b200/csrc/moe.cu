@@ -21,6 +21,8 @@ constexpr int MOE_MAX_E = 8;
 __global__ void __launch_bounds__(128) moe_router_kernel(const __nv_bfloat16* __restrict__ h, long long ldh,
                                                          const float* __restrict__ wg, int S, int D, int E,
                                                          float* __restrict__ logits, float* __restrict__ gates) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * 4 + warp;
   if (s >= S) return;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(128) moe_norm_router_kernel(const __nv_bfloat1
                                                               __nv_bfloat16* __restrict__ h, long long ldh,
                                                               const float* __restrict__ wg, int D, int E,
                                                               float* __restrict__ logits, float* __restrict__ gates) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   constexpr int NV = 4;  // 16-byte vectors per thread: D <= 128 * 4 * 8
   __shared__ float red[4][MOE_MAX_E + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -194,6 +198,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) moe_scan_kernel(const float* __r
                                                                 float* __restrict__ gate, int* __restrict__ slot,
                                                                 int* __restrict__ kept, int* __restrict__ exp_counts,
                                                                 float* __restrict__ l_aux, int skey_ok) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   extern __shared__ float skey[];  // [S] when skey_ok: RTS keys of one expert
   __shared__ int cnt[SCAN_THREADS][MOE_MAX_E];  // per-thread segment counts, then exclusive offsets
   __shared__ int total1[MOE_MAX_E], total2[MOE_MAX_E];
@@ -431,6 +437,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) moe_scan_kernel(const float* __r
 __global__ void __launch_bounds__(128) moe_dispatch_kernel(const __nv_bfloat16* __restrict__ h, long long ldh,
                                                            const int* __restrict__ slot,
                                                            __nv_bfloat16* __restrict__ xperm, int k, int D) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   const int r = blockIdx.x;  // token * k + route
   const int dst = slot[r];
   if (dst < 0) return;
@@ -445,6 +453,8 @@ __global__ void __launch_bounds__(128) moe_combine_kernel(const __nv_bfloat16* _
                                                           const __nv_bfloat16* __restrict__ residual, long long ldr,
                                                           __nv_bfloat16* __restrict__ out, long long ldo, int k,
                                                           int D) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   const int s = blockIdx.x;
   int sl[2] = {-1, -1};
   float g[2] = {0.0f, 0.0f};
@@ -710,7 +720,7 @@ int moe_norm_route(const mpl_moe_route_args& a, const void* x, long long ldx, co
   if (a.h == nullptr || x == nullptr || ln_w == nullptr || a.wg == nullptr || a.logits == nullptr || a.gates == nullptr)
     return MPL_ERR_ARG;
   if (a.E < 1 || a.E > MOE_MAX_E || a.k < 1 || a.k > 2 || a.k > a.E || a.capacity < 1) return MPL_ERR_UNSUPPORTED;
-  moe_norm_router_kernel<<<a.S, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+  launch_pdl(moe_norm_router_kernel, dim3(a.S), dim3(128), 0, stream, static_cast<const __nv_bfloat16*>(x), ldx,
                                                  static_cast<const __nv_bfloat16*>(ln_w), eps,
                                                  static_cast<__nv_bfloat16*>(const_cast<void*>(a.h)), a.ldh, a.wg, a.D, a.E,
                                                  a.logits, a.gates);
@@ -726,7 +736,7 @@ int moe_route(const mpl_moe_route_args& a, cudaStream_t stream) {
     return MPL_ERR_ARG;
   if (a.E < 1 || a.E > MOE_MAX_E || a.k < 1 || a.k > 2 || a.k > a.E || a.capacity < 1) return MPL_ERR_UNSUPPORTED;
   if ((a.D % 8) != 0 || (a.ldh % 8) != 0) return MPL_ERR_ALIGN;
-  moe_router_kernel<<<(a.S + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(a.h), a.ldh, a.wg, a.S, a.D,
+  launch_pdl(moe_router_kernel, dim3((a.S + 3) / 4), dim3(128), 0, stream, static_cast<const __nv_bfloat16*>(a.h), a.ldh, a.wg, a.S, a.D,
                                                       a.E, a.logits, a.gates);
   const int rc = launch_status();
   if (rc != MPL_OK) return rc;
@@ -747,7 +757,7 @@ static int moe_scan_launch(const mpl_moe_route_args& a, cudaStream_t stream) {
       attr = true;
     }
   }
-  moe_scan_kernel<<<1, SCAN_THREADS, skey_bytes, stream>>>(a.logits, a.gates, a.noise, a.S, a.E, a.k, a.capacity, a.expert,
+  launch_pdl(moe_scan_kernel, dim3(1), dim3(SCAN_THREADS), skey_bytes, stream, a.logits, a.gates, a.noise, a.S, a.E, a.k, a.capacity, a.expert,
                                                            a.gate, a.slot, a.kept, a.exp_counts, a.l_aux,
                                                            skey_bytes > 0 ? 1 : 0);
   return launch_status();
@@ -758,7 +768,7 @@ int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int
   if (S <= 0) return MPL_OK;
   if (h == nullptr || slot == nullptr || xperm == nullptr) return MPL_ERR_ARG;
   if ((D % 8) != 0 || (ldh % 8) != 0) return MPL_ERR_ALIGN;
-  moe_dispatch_kernel<<<S * k, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(h), ldh, slot,
+  launch_pdl(moe_dispatch_kernel, dim3(S * k), dim3(128), 0, stream, static_cast<const __nv_bfloat16*>(h), ldh, slot,
                                                  static_cast<__nv_bfloat16*>(xperm), k, D);
   return mpl::launch_status();
 }
@@ -768,7 +778,7 @@ int moe_combine(const void* y, const int* slot, const float* gate, const void* r
   if (S <= 0) return MPL_OK;
   if (y == nullptr || slot == nullptr || gate == nullptr || out == nullptr) return MPL_ERR_ARG;
   if ((D % 8) != 0 || (ldr % 8) != 0 || (ldo % 8) != 0 || k < 1 || k > 2) return MPL_ERR_ALIGN;
-  moe_combine_kernel<<<S, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), slot, gate,
+  launch_pdl(moe_combine_kernel, dim3(S), dim3(128), 0, stream, static_cast<const __nv_bfloat16*>(y), slot, gate,
                                             static_cast<const __nv_bfloat16*>(residual), ldr,
                                             static_cast<__nv_bfloat16*>(out), ldo, k, D);
   return mpl::launch_status();

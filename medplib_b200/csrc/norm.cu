@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_kernel(const __nv_bfloat
                                                                const __nv_bfloat16* __restrict__ w,
                                                                __nv_bfloat16* __restrict__ y, long long ldy, int D,
                                                                float eps) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   __shared__ float red[NORM_THREADS / 32];
   const long long row = blockIdx.x;
   const __nv_bfloat16* xr = x + row * ldx;
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(NORM_THREADS) layernorm_kernel(const __nv_bflo
                                                                  const __nv_bfloat16* __restrict__ b,
                                                                  __nv_bfloat16* __restrict__ y, long long ldy, int D,
                                                                  float eps, int act) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   __shared__ float red[NORM_THREADS / 32];
   const long long row = blockIdx.x;
   const __nv_bfloat16* xr = x + row * ldx;
@@ -149,6 +153,8 @@ __global__ void __launch_bounds__(NORM_THREADS) pool_ln_kernel(const __nv_bfloat
                                                                const __nv_bfloat16* __restrict__ b,
                                                                __nv_bfloat16* __restrict__ y, int Tin, int Tout, int D,
                                                                float eps) {
+  griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
+  griddep_launch_dependents();
   __shared__ float red[NORM_THREADS / 32];
   const int n = blockIdx.x / Tout;
   const int i = blockIdx.x % Tout;
@@ -265,7 +271,7 @@ extern "C" int mpl_rmsnorm(const void* x, long long ldx, const void* weight, voi
                            float eps, void* stream) {
   if (rows <= 0) return MPL_OK;
   if (!mpl::norm_args_ok(x, y, D, ldx, ldy) || weight == nullptr) return MPL_ERR_ARG;
-  mpl::rmsnorm_kernel<<<rows, mpl::NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  mpl::launch_pdl(mpl::rmsnorm_kernel, dim3(rows), dim3(mpl::NORM_THREADS), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
       static_cast<__nv_bfloat16*>(y), ldy, D, eps);
   return mpl::launch_status();
@@ -275,7 +281,7 @@ extern "C" int mpl_layernorm(const void* x, long long ldx, const void* weight, c
                              long long ldy, int rows, int D, float eps, int act, void* stream) {
   if (rows <= 0) return MPL_OK;
   if (!mpl::norm_args_ok(x, y, D, ldx, ldy) || weight == nullptr || bias == nullptr) return MPL_ERR_ARG;
-  mpl::layernorm_kernel<<<rows, mpl::NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  mpl::launch_pdl(mpl::layernorm_kernel, dim3(rows), dim3(mpl::NORM_THREADS), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(weight),
       static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), ldy, D, eps, act);
   return mpl::launch_status();
@@ -285,7 +291,7 @@ extern "C" int mpl_pool_layernorm(const void* x, const void* weight, const void*
                                   int t_out, int D, float eps, void* stream) {
   if (n <= 0 || t_out <= 0) return MPL_OK;
   if (!mpl::norm_args_ok(x, y, D, D, D) || weight == nullptr || bias == nullptr || t_in < t_out) return MPL_ERR_ARG;
-  mpl::pool_ln_kernel<<<n * t_out, mpl::NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  mpl::launch_pdl(mpl::pool_ln_kernel, dim3(n * t_out), dim3(mpl::NORM_THREADS), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight),
       static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(y), t_in, t_out, D, eps);
   return mpl::launch_status();

@@ -374,7 +374,7 @@ def region_sample_mean(fmap, pts, h, w):
 
 
 def grouped_linear(xperm, weights, m_dev, rows_per_group, weights2=None, out=None, row_map=None, row_gate=None,
-                   residual=None, a_row_map=None):
+                   residual=None, a_row_map=None, tile_n=0, m_total_hint=0):
     """Per-expert linears in one launch (mpl_grouped_gemm_bf16). xperm bf16 [G*rows_per_group, K]; weights: list of
     G [N,K]; m_dev int32 [G]. With row_map/row_gate (+residual): fused MoE combine into `out` [S, N] (token rows).
     With a_row_map (slot -> token): `xperm` is the un-dispatched [S, K] token matrix (fused MoE dispatch)."""
@@ -401,6 +401,7 @@ def grouped_linear(xperm, weights, m_dev, rows_per_group, weights2=None, out=Non
         a.residual, a.ldr = residual.data_ptr(), residual.stride(0)
     a.groups, a.M, a.N, a.K = G, rows_per_group, N, K
     a.out_dtype = DT_BF16
+    a.tile_n, a.m_total_hint = tile_n, m_total_hint
     _lib.check(lib.mpl_grouped_gemm_bf16(ctypes.byref(a), _stream()), "mpl_grouped_gemm_bf16")
     return out
 

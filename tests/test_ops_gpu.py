@@ -21,6 +21,14 @@ from parity import close as _close  # noqa: E402  (logs the measured error, asse
     (2048, 4096, 4096, {"tile_n": 128}), (2048, 4096, 4096, {"tile_n": 192}), (2048, 4096, 4096, {"tile_n": 256}),
     (615, 4096, 4096, {"nb": 3}), (577, 1024, 1024, {"nb": 3, "bias": True}), (256, 768, 192, {"act": "sigmoid"}),
     (700, 4096, 11008, {"res": True, "row_scale": True, "m_dev": 300}), (64, 768, 6912, {"act": "relu"}),
+    # every compiled tile width (multiples of 16: the last 32-column chunk of a tile is partial for 144, 176, 208, 240;
+    # dual halves 72 .. 120 columns), matrix edges that fall inside a partial chunk, fp32 output
+    (615, 4096, 4096, {"tile_n": 144, "res": True}), (615, 4096, 4096, {"tile_n": 160, "bias": True}),
+    (615, 4096, 4096, {"tile_n": 176, "res": True}), (615, 4096, 4096, {"tile_n": 208}),
+    (615, 4096, 4096, {"tile_n": 224, "nb": 3}), (615, 4096, 4096, {"tile_n": 240, "f32": True}),
+    (300, 1000, 512, {"tile_n": 144, "bias": True, "res": True}), (300, 1001, 520, {"tile_n": 176, "f32": True}),
+    (615, 11008, 4096, {"dual": True, "tile_n": 240}), (615, 11008, 4096, {"dual": True, "tile_n": 144}),
+    (615, 11008, 4096, {"dual": True, "tile_n": 208}), (330, 1000, 512, {"dual": True, "tile_n": 176}),
 ])
 def test_gemm_tcgen05(dev, M, N, K, kw):
     from medplib_b200 import ops
