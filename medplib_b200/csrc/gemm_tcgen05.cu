@@ -62,7 +62,7 @@ struct TileCoord {
   int g, m0, n0, M;
 };
 struct TileSpace {
-  int groups, tiles_n1, nb, out_bn, num_tiles;
+  int groups, tiles_n1, nb, out_bn, num_tiles, bm;  // bm = rows of a tile: 128 (one CTA) or 256 (a CTA pair)
   int tm[MPL_MAX_EXPERTS], Mg[MPL_MAX_EXPERTS];
   int tiles_m, M;
   __device__ __forceinline__ TileCoord at(int tile) const {
@@ -72,21 +72,22 @@ struct TileSpace {
 #pragma unroll 1
       while (g + 1 < groups && t >= tm[g] * tiles_n1) t -= tm[g++] * tiles_n1;
       c.g = g;
-      c.m0 = (t % tm[g]) * BM;
+      c.m0 = (t % tm[g]) * bm;
       c.n0 = (t / tm[g]) * out_bn;
       c.M = Mg[g];
     } else {
       const int nt = tile / tiles_m;
       c.g = nt / tiles_n1;  // which weight matrix (nb > 1)
-      c.m0 = (tile % tiles_m) * BM;
+      c.m0 = (tile % tiles_m) * bm;
       c.n0 = (nt % tiles_n1) * out_bn;
       c.M = M;
     }
     return c;
   }
 };
-__device__ __forceinline__ TileSpace make_tile_space(const GemmDevParams& p, int out_bn) {
+__device__ __forceinline__ TileSpace make_tile_space(const GemmDevParams& p, int out_bn, int bm) {
   TileSpace ts;
+  ts.bm = bm;
   ts.groups = p.groups;
   ts.out_bn = out_bn;
   ts.nb = p.nb;
@@ -97,7 +98,7 @@ __device__ __forceinline__ TileSpace make_tile_space(const GemmDevParams& p, int
     for (int g = 0; g < p.groups; ++g) {
       const int Mg = min(p.M, p.m_dev != nullptr ? p.m_dev[g] : p.M);
       ts.Mg[g] = Mg;
-      ts.tm[g] = (Mg + BM - 1) / BM;
+      ts.tm[g] = (Mg + bm - 1) / bm;
       total += ts.tm[g] * ts.tiles_n1;
     }
     ts.num_tiles = total;
@@ -107,7 +108,7 @@ __device__ __forceinline__ TileSpace make_tile_space(const GemmDevParams& p, int
     int M = p.M;
     if (p.m_dev != nullptr) M = min(M, *p.m_dev);
     ts.M = M;
-    ts.tiles_m = (M + BM - 1) / BM;
+    ts.tiles_m = (M + bm - 1) / bm;
     ts.num_tiles = ts.tiles_m * ts.tiles_n1 * p.nb;
   }
   return ts;
@@ -127,6 +128,128 @@ __device__ __forceinline__ float apply_act(float v, int act) {
       return 1.0f / (1.0f + __expf(-v));
     default:
       return v;
+  }
+}
+
+// Epilogue of one accumulator row (one thread = one output row of the tile): tcgen05.ld 32 columns at a time, apply
+// bias / activation / SiLU(gate)*up / row scale / residual with the reference's bf16 rounding points, store.
+// t_row = TMEM address of this thread's lane at the first column of the accumulator.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmDevParams& p, const __nv_bfloat16* bias, void* Cout, int row, int M,
+                                              int n0, int out_bn, uint32_t t_row, bool vec_ok, bool res_vec_ok) {
+  const bool row_ok = row < M;
+  const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.0f;
+  const bool f32 = p.out_f32 != 0;
+  const int nlim = min(p.N, n0 + out_bn);  // columns of this tile (the last 32-column chunk may be partial)
+#pragma unroll 1
+  for (int c = 0; c < (out_bn + 31) / 32; ++c) {
+    uint32_t r[32];
+    float v[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    if (p.dual) {
+      uint32_t r2[32];
+      tmem_ld_32x32(t_row + BN / 2 + c * 32, r2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // reference: down(silu(gate(x)) * up(x)) with every intermediate rounded to bf16
+        const float g = bf16_round(__uint_as_float(r[j]));
+        const float u = bf16_round(__uint_as_float(r2[j]));
+        const float s = bf16_round(g / (1.0f + __expf(-g)));
+        v[j] = s * u;
+      }
+    } else {
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    }
+    const int nc = n0 + c * 32;
+    if (nc >= nlim || !row_ok) continue;
+    const bool full = (nc + 32 <= nlim);
+    if (bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (full || nc + j < nlim) v[j] += __bfloat162float(bias[nc + j]);
+    }
+    if (p.act != MPL_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(f32 ? v[j] : bf16_round(v[j]), p.act);
+    }
+    if (p.row_scale != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (f32 ? v[j] : bf16_round(v[j])) * rscale;
+    }
+    if (p.residual != nullptr) {
+      if (!f32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+      }
+      const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + nc;
+      if (full && res_vec_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(rp + q * 8);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h[e]);
+            v[q * 8 + e * 2] += f.x;
+            v[q * 8 + e * 2 + 1] += f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nc + j < nlim) v[j] += __bfloat162float(rp[j]);
+      }
+    }
+    if (f32) {
+      float* cp = reinterpret_cast<float*>(Cout) + static_cast<long long>(row) * p.ldc + nc;
+      if (full && vec_ok) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(cp + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nc + j < nlim) cp[j] = v[j];
+      }
+    } else {
+      __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<long long>(row) * p.ldc + nc;
+      if (full && vec_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+          o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+          o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+          o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+          *reinterpret_cast<uint4*>(cp + q * 8) = o;
+        }
+      } else if (vec_ok) {
+        // partial chunk (tile widths that are not a multiple of 32, or the matrix edge): whole 8-column groups
+        // still go out as 16-byte stores
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (nc + q * 8 + 8 <= nlim) {
+            uint4 o;
+            o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+            o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+            o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+            o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(cp + q * 8) = o;
+          } else {
+#pragma unroll
+            for (int j = q * 8; j < q * 8 + 8; ++j)
+              if (nc + j < nlim) cp[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nc + j < nlim) cp[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
   }
 }
 
@@ -188,7 +311,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   // the device-side row counts) are touched only from here on
   griddep_wait();
   griddep_launch_dependents();
-  if (threadIdx.x == 0) ts = make_tile_space(p, out_bn);
+  if (threadIdx.x == 0) ts = make_tile_space(p, out_bn, BM);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -287,122 +410,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         Cout = static_cast<char*>(p.C[0]) + static_cast<long long>(which) * p.c_group_stride * (p.out_f32 ? 4 : 2);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < M;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE;
-      const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.0f;
-      const bool f32 = p.out_f32 != 0;
-      const int nlim = min(p.N, n0 + out_bn);  // columns of this tile (the last 32-column chunk may be partial)
-#pragma unroll 1
-      for (int c = 0; c < (out_bn + 31) / 32; ++c) {
-        uint32_t r[32];
-        float v[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        if (p.dual) {
-          uint32_t r2[32];
-          tmem_ld_32x32(t_row + BN / 2 + c * 32, r2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            // reference: down(silu(gate(x)) * up(x)) with every intermediate rounded to bf16
-            const float g = bf16_round(__uint_as_float(r[j]));
-            const float u = bf16_round(__uint_as_float(r2[j]));
-            const float s = bf16_round(g / (1.0f + __expf(-g)));
-            v[j] = s * u;
-          }
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        }
-        const int nc = n0 + c * 32;
-        if (nc >= nlim || !row_ok) continue;
-        const bool full = (nc + 32 <= nlim);
-        if (bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || nc + j < nlim) v[j] += __bfloat162float(bias[nc + j]);
-        }
-        if (p.act != MPL_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(f32 ? v[j] : bf16_round(v[j]), p.act);
-        }
-        if (p.row_scale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (f32 ? v[j] : bf16_round(v[j])) * rscale;
-        }
-        if (p.residual != nullptr) {
-          if (!f32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
-          }
-          const __nv_bfloat16* rp = p.residual + static_cast<long long>(row) * p.ldr + nc;
-          if (full && res_vec_ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(rp + q * 8);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __bfloat1622float2(h[e]);
-                v[q * 8 + e * 2] += f.x;
-                v[q * 8 + e * 2 + 1] += f.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < nlim) v[j] += __bfloat162float(rp[j]);
-          }
-        }
-        if (f32) {
-          float* cp = reinterpret_cast<float*>(Cout) + static_cast<long long>(row) * p.ldc + nc;
-          if (full && vec_ok) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(cp + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < nlim) cp[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<long long>(row) * p.ldc + nc;
-          if (full && vec_ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(cp + q * 8) = o;
-            }
-          } else if (vec_ok) {
-            // partial chunk (tile widths that are not a multiple of 32, or the matrix edge): whole 8-column groups
-            // still go out as 16-byte stores
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (nc + q * 8 + 8 <= nlim) {
-                uint4 o;
-                o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-                o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-                o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-                o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-                *reinterpret_cast<uint4*>(cp + q * 8) = o;
-              } else {
-#pragma unroll
-                for (int j = q * 8; j < q * 8 + 8; ++j)
-                  if (nc + j < nlim) cp[j] = __float2bfloat16_rn(v[j]);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < nlim) cp[j] = __float2bfloat16_rn(v[j]);
-          }
-        }
-      }
+      epilogue_rows<BN>(p, bias, Cout, m0 + quad * 32 + lane, M, n0, out_bn,
+                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE, vec_ok, res_vec_ok);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -416,6 +425,192 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// Same GEMM on `cta_group::2`: a cluster of two CTAs (one TPC) owns a 256 x BN tile. Each CTA stages ITS 128 rows of A
+// and HALF of the weight rows (BN/2) per k-block -- (128 + BN/2) x 128 B instead of (128 + BN) x 128 B for the same
+// 128 x BN of output per CTA -- and one thread of the leader (cluster rank 0) issues tcgen05.mma.cta_group::2
+// (M = 256, N = BN), which reads both CTAs' shared memory and writes 128 accumulator lanes into each CTA's TMEM. The
+// kernel exists because the one-CTA kernel is bound by the L2 -> shared-memory fill, not by the tensor pipe
+// (profiles/r02_gemm_tile_widths.md): a third fewer staged bytes per MAC at BN = 256.
+//   full[s]    lives in the leader: ONE arrive.expect_tx by the leader's producer for the bytes of BOTH CTAs; the peer's TMA
+//              loads complete on the leader's barrier (cp.async.bulk.tensor.cta_group::2)
+//   empty[s]   in each CTA, signalled by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[a]   in each CTA (multicast commit); tempty[a] in the leader, 8 arrivals = 4 epilogue warps x 2 CTAs
+// SiLU(gate)*up: the leader stages the gate rows, the peer the up rows of the same features, so the accumulator columns
+// are [gate | up] exactly as in the one-CTA kernel and the epilogue is shared.
+template <int BN>
+struct PairCfg {
+  static_assert(BN % 16 == 0 && BN >= 128 && BN <= 256, "pair tile width");
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // per CTA
+  static constexpr int STAGES_FIT = (232448 - 1024 - 256 - 512) / (A_BYTES + B_BYTES);
+  static constexpr int STAGES = STAGES_FIT > 7 ? 7 : STAGES_FIT;
+  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
+                              const GemmDevParams p, const __grid_constant__ GroupMaps gmaps) {
+  using Cfg = PairCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  const int out_bn = p.dual ? BN / 2 : BN;
+  __shared__ TileSpace ts;
+  const int kblocks = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.dual || p.nb > 2) tma_prefetch_desc(&tmB2);
+    if (p.nb > 1) tma_prefetch_desc(&tmB1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);  // 4 epilogue warps of each CTA (only the leader's copy is used)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+  griddep_wait();
+  griddep_launch_dependents();
+  if (threadIdx.x == 0) ts = make_tile_space(p, out_bn, 2 * BM);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised and their TMEM allocated before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = ts.num_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (one thread in EACH CTA)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const TileCoord tc = ts.at(tile);
+        const int which = tc.g;
+        const int m0 = (p.groups > 0 ? static_cast<int>(tc.g * p.a_group_rows) + tc.m0 : tc.m0) + static_cast<int>(rank) * BM;
+        // weight rows of this CTA: the two halves of the tile's columns, or (dual) gate rows in the leader / up rows in the peer
+        const int nrow = p.dual ? tc.n0 : tc.n0 + static_cast<int>(rank) * (BN / 2);
+        const bool second = p.dual && rank == 1;  // the peer reads W2 (up)
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
+          tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, fb, kb * BK, m0);
+          uint8_t* dstB = sB + stage * Cfg::B_BYTES;
+          if (p.groups > 0) {
+            if (second)
+              tma_load_2d_pair(dstB, &gmaps.b2[which], fb, kb * BK, nrow);
+            else
+              tma_load_2d_pair(dstB, &gmaps.b[which], fb, kb * BK, nrow);
+          } else if (second) {
+            tma_load_2d_pair(dstB, &tmB2, fb, kb * BK, nrow);
+          } else if (which == 0) {
+            tma_load_2d_pair(dstB, &tmB, fb, kb * BK, nrow);
+          } else if (which == 1) {
+            tma_load_2d_pair(dstB, &tmB1, fb, kb * BK, nrow);
+          } else {
+            tma_load_2d_pair(dstB, &tmB2, fb, kb * BK, nrow);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: one thread of the LEADER
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(a_addr + k * 32);
+            const uint64_t db = umma_desc_k_sw128(b_addr + k * 32);
+            umma_bf16_ss_pair(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);  // the slot is reusable in BOTH CTAs once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tfull_bar[acc], 3);  // accumulator complete (each CTA's epilogue waits on its own copy)
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5 of each CTA: its own 128 rows)
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = p.out_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
+    const bool res_vec_ok = (p.ldr & 7) == 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const TileCoord tc = ts.at(tile);
+      const int which = tc.g, m0 = tc.m0 + static_cast<int>(rank) * BM, n0 = tc.n0, M = tc.M;
+      const __nv_bfloat16* bias = p.groups > 0 ? nullptr : (which == 0 ? p.bias[0] : (which == 1 ? p.bias[1] : p.bias[2]));
+      void* Cout = which == 0 ? p.C[0] : (which == 1 ? p.C[1] : p.C[2]);
+      if (p.groups > 0)
+        Cout = static_cast<char*>(p.C[0]) + static_cast<long long>(which) * p.c_group_stride * (p.out_f32 ? 4 : 2);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      epilogue_rows<BN>(p, bias, Cout, m0 + quad * 32 + lane, M, n0, out_bn,
+                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE, vec_ok, res_vec_ok);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the other CTA may still signal its barriers / read its smem
+  if (warp == 1) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -500,70 +695,124 @@ int num_sms() {
   return g_num_sms;
 }
 
-// Tile widths compiled in (UMMA N of a 128-row tile: any multiple of 16; these cover the wave counts that matter).
+// Tile widths compiled in (UMMA N: any multiple of 16; these cover the wave counts that matter). One-CTA tiles are
+// 128 x W, CTA-pair tiles 256 x W.
 #define MPL_TILE_WIDTHS(X) X(128) X(144) X(160) X(176) X(192) X(208) X(224) X(240) X(256)
+#define MPL_PAIR_WIDTHS(X) X(128) X(160) X(176) X(192) X(224) X(240) X(256)
+constexpr int PAIR_FLAG = 1000;  // tile_n = PAIR_FLAG + W selects the CTA-pair kernel with width W
 
-// Pick the tile width with the lowest (waves x per-tile time) estimate for `m_tiles` row tiles (x weight matrices) of an
-// N-column output on a persistent grid of one CTA per SM. Measured on B200 (tools/gemm_tiles.py, profiles/
-// r02_gemm_tile_widths.md): at prefill sizes the kernel is bound by the L2 -> shared-memory fill (~100 GB/s per SM,
-// 13-15 TB/s over the chip), so a tile costs ~ the bytes it stages per k-block, (128 + width) rows, plus a fixed part;
-// widths that leave only 4 ring stages (240, 256) pay ~10 % more. Ties go to the wider tile.
-static int pick_tile_n(long long m_tiles, int N, int dual) {
+// Pick the tile shape with the lowest (waves x per-tile time) estimate for an [rows, N] output (x `mats` weight matrices /
+// `groups` row groups of `rows` each) on a persistent grid of one CTA (or one CTA pair) per SM (per TPC). Measured on
+// B200 (tools/gemm_tiles.py, profiles/r02_gemm_tile_widths.md): at prefill sizes the kernels are bound by the L2 ->
+// shared-memory fill (~100 GB/s per SM, 13-15 TB/s over the chip), so a tile costs ~ the rows it stages per k-block --
+// 128 + W for one CTA, 128 + W/2 per CTA of a pair -- plus a fixed part; one-CTA widths that leave only 4 ring stages
+// (240, 256) pay ~10 % more. Ties go to the wider tile. MPL_GEMM_PAIR=0 keeps the one-CTA kernel.
+static bool pair_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MPL_GEMM_PAIR");
+    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return on != 0;
+}
+static int pair_min_rows() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MPL_GEMM_PAIR_MIN_ROWS");
+    v = e != nullptr ? atoi(e) : 1024;
+  }
+  return v;
+}
+static int pick_tile_n(long long rows, int row_sets, int N, int dual) {
   const int sms = num_sms();
   static const int widths[] = {
 #define MPL_BN_LIST(W) W,
       MPL_TILE_WIDTHS(MPL_BN_LIST)
+  };
+  static const int pair_widths[] = {MPL_PAIR_WIDTHS(MPL_BN_LIST)
 #undef MPL_BN_LIST
   };
   int best = 256;
-  double best_cost = 0.0;
+  double best_cost = 1e300;
   for (int i = static_cast<int>(sizeof(widths) / sizeof(widths[0])) - 1; i >= 0; --i) {
     const int bn = widths[i];
     const int out_bn = dual ? bn / 2 : bn;
-    const long long tiles = m_tiles * ((N + out_bn - 1) / out_bn);
+    const long long tiles = row_sets * ((rows + BM - 1) / BM) * ((N + out_bn - 1) / out_bn);
     const long long waves = (tiles + sms - 1) / sms;
-    const double c = static_cast<double>(waves) * (bn + 150) * (bn > 224 ? 1.1 : 1.0);
-    if (i == static_cast<int>(sizeof(widths) / sizeof(widths[0])) - 1 || c < best_cost) {
+    const double c = static_cast<double>(waves) * (128 + bn + 22) * (bn > 224 ? 1.1 : 1.0);
+    if (c < best_cost) {
       best = bn;
       best_cost = c;
+    }
+  }
+  // CTA pairs pay off once a weight panel is re-used by enough row tiles to be served from L2 (M = 5112: 1.45-1.6
+  // PFLOP/s against 1.2-1.3 for one CTA); at M = 615 the weights stream from DRAM in 128-byte pieces per row and both
+  // kernels sit at the same ~2.5 us stage round trip (profiles/r02_gemm_tile_widths.md)
+  if (pair_enabled() && rows >= pair_min_rows()) {
+    const int pairs = sms / 2;
+    for (int i = static_cast<int>(sizeof(pair_widths) / sizeof(pair_widths[0])) - 1; i >= 0; --i) {
+      const int bn = pair_widths[i];
+      const int out_bn = dual ? bn / 2 : bn;
+      const long long tiles = row_sets * ((rows + 2 * BM - 1) / (2 * BM)) * ((N + out_bn - 1) / out_bn);
+      const long long waves = (tiles + pairs - 1) / pairs;
+      const double c = static_cast<double>(waves) * (128 + bn / 2 + 22);
+      if (c < best_cost) {
+        best = PAIR_FLAG + bn;
+        best_cost = c;
+      }
     }
   }
   return best;
 }
 
-template <int BN>
-static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, bool PAIR>
+static int launch_any(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const CUtensorMap& tmB2,
+                      const GemmDevParams& p, const GroupMaps& gm, long long tiles, cudaStream_t stream) {
+  constexpr int smem = PAIR ? PairCfg<BN>::SMEM_BYTES : GemmCfg<BN>::SMEM_BYTES;
+  auto kernel = PAIR ? gemm_bf16_tcgen05_pair_kernel<BN> : gemm_bf16_tcgen05_kernel<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return MPL_ERR_CUDA;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MPL_ERR_CUDA;
     attr_set = true;
   }
+  const int units = PAIR ? num_sms() / 2 : num_sms();  // CTAs, or CTA pairs (one per TPC)
+  int grid = static_cast<int>(tiles < units ? tiles : units);
+  if (grid < 1) grid = 1;
+  if (PAIR) grid *= 2;
+  const bool prof = g_prof && !g_prof_suppress;
+  if (prof) cudaEventRecord(prof_event(), stream);
+  launch_pdl(kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmB1, tmB2, p, gm);
+  if (prof) cudaEventRecord(prof_event(), stream);
+  return mpl::launch_status();
+}
+
+template <int BN, bool PAIR>
+static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   const int dual = a.B2 != nullptr;
   const int nb = a.nb < 1 ? 1 : a.nb;
   if (nb > 3 || (dual && nb != 1)) return MPL_ERR_ARG;
+  const int box_b = (PAIR || dual) ? BN / 2 : BN;  // weight rows per TMA box
   CUtensorMap tmA, tmB, tmB1, tmB2;
   int rc = make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM);
   if (rc) return rc;
-  rc = make_tmap(&tmB, a.B[0], a.N, a.K, a.ldb, dual ? BN / 2 : BN);
+  rc = make_tmap(&tmB, a.B[0], a.N, a.K, a.ldb, box_b);
   if (rc) return rc;
   tmB1 = tmB;
   tmB2 = tmB;
   if (dual) {
-    rc = make_tmap(&tmB2, a.B2, a.N, a.K, a.ldb, BN / 2);
+    rc = make_tmap(&tmB2, a.B2, a.N, a.K, a.ldb, box_b);
     if (rc) return rc;
   }
   if (nb > 1) {
-    rc = make_tmap(&tmB1, a.B[1], a.N, a.K, a.ldb, BN);
+    rc = make_tmap(&tmB1, a.B[1], a.N, a.K, a.ldb, box_b);
     if (rc) return rc;
   }
   if (nb > 2) {
-    rc = make_tmap(&tmB2, a.B[2], a.N, a.K, a.ldb, BN);
+    rc = make_tmap(&tmB2, a.B[2], a.N, a.K, a.ldb, box_b);
     if (rc) return rc;
   }
   GemmDevParams p;
+  memset(&p, 0, sizeof(p));
   p.M = a.M;
   p.N = a.N;
   p.K = a.K;
@@ -581,19 +830,10 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   p.out_f32 = a.out_dtype == MPL_DT_F32;
   p.dual = dual;
   const int out_bn = dual ? BN / 2 : BN;
-  const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn) * nb;
-  int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  if (grid < 1) grid = 1;
-  const bool prof = g_prof && !g_prof_suppress;
-  if (prof) cudaEventRecord(prof_event(), stream);
-  p.groups = 0;
-  p.a_group_rows = 0;
-  p.c_group_stride = 0;
+  const int bm = PAIR ? 2 * BM : BM;
+  const long long tiles = static_cast<long long>((a.M + bm - 1) / bm) * ((a.N + out_bn - 1) / out_bn) * nb;
   static const GroupMaps no_groups = {};
-  launch_pdl(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmB1, tmB2, p,
-             no_groups);
-  if (prof) cudaEventRecord(prof_event(), stream);
-  return mpl::launch_status();
+  return launch_any<BN, PAIR>(tmA, tmB, tmB1, tmB2, p, no_groups, tiles, stream);
 }
 
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
@@ -602,29 +842,27 @@ int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
   const int dual = a.B2 != nullptr;
   const int nb = a.nb < 1 ? 1 : a.nb;
   int bn = a.tile_n;
-  if (bn == 0) bn = pick_tile_n(static_cast<long long>((a.M + BM - 1) / BM) * nb, a.N, dual);
+  if (bn == 0) bn = pick_tile_n(a.M, nb, a.N, dual);
   switch (bn) {
 #define MPL_BN_CASE(W) \
   case W:              \
-    return launch_gemm<W>(a, stream);
+    return launch_gemm<W, false>(a, stream);
     MPL_TILE_WIDTHS(MPL_BN_CASE)
+#undef MPL_BN_CASE
+#define MPL_BN_CASE(W)   \
+  case PAIR_FLAG + W:    \
+    return launch_gemm<W, true>(a, stream);
+    MPL_PAIR_WIDTHS(MPL_BN_CASE)
 #undef MPL_BN_CASE
     default:
       return MPL_ERR_ARG;
   }
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_grouped(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) !=
-        cudaSuccess)
-      return MPL_ERR_CUDA;
-    attr_set = true;
-  }
   const int dual = a.B2[0] != nullptr;
+  const int box_b = (PAIR || dual) ? BN / 2 : BN;
   const long long group_rows = a.a_group_stride / a.lda;
   CUtensorMap tmA;
   GroupMaps gm;
@@ -633,8 +871,8 @@ static int launch_grouped(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
   // (they belong to the next group or are zero-filled past the end) but never stored
   int rc = make_tmap(&tmA, a.A, group_rows * (a.groups - 1) + a.M, a.K, a.lda, BM);
   for (int g = 0; g < a.groups && rc == MPL_OK; ++g) {
-    rc = make_tmap(&gm.b[g], a.B[g], a.N, a.K, a.ldb, dual ? BN / 2 : BN);
-    if (rc == MPL_OK && dual) rc = make_tmap(&gm.b2[g], a.B2[g], a.N, a.K, a.ldb, BN / 2);
+    rc = make_tmap(&gm.b[g], a.B[g], a.N, a.K, a.ldb, box_b);
+    if (rc == MPL_OK && dual) rc = make_tmap(&gm.b2[g], a.B2[g], a.N, a.K, a.ldb, box_b);
   }
   if (rc != MPL_OK) return rc;
   GemmDevParams p;
@@ -655,15 +893,9 @@ static int launch_grouped(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
   p.a_group_rows = group_rows;
   p.c_group_stride = a.c_group_stride;
   const int out_bn = dual ? BN / 2 : BN;
-  const long long tiles = static_cast<long long>((a.M + BM - 1) / BM) * ((a.N + out_bn - 1) / out_bn) * a.groups;
-  int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  if (grid < 1) grid = 1;
-  const bool prof = g_prof && !g_prof_suppress;
-  if (prof) cudaEventRecord(prof_event(), stream);
-  launch_pdl(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, gm.b[0], gm.b[0],
-             gm.b[0], p, gm);
-  if (prof) cudaEventRecord(prof_event(), stream);
-  return mpl::launch_status();
+  const int bm = PAIR ? 2 * BM : BM;
+  const long long tiles = static_cast<long long>((a.M + bm - 1) / bm) * ((a.N + out_bn - 1) / out_bn) * a.groups;
+  return launch_any<BN, PAIR>(tmA, gm.b[0], gm.b[0], gm.b[0], p, gm, tiles, stream);
 }
 
 // Grouped (per-expert) GEMM for M > 16: ONE tcgen05 launch walks the tiles of every group (device-side row counts via
@@ -675,20 +907,24 @@ int grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream) {
   if (a.K <= 0 || a.A == nullptr || a.C == nullptr || a.lda <= 0 || a.a_group_stride % a.lda != 0) return MPL_ERR_ARG;
   for (int g = 0; g < a.groups; ++g)
     if (a.B[g] == nullptr) return MPL_ERR_ARG;
-  // tile width: the lowest (waves x tile width x penalty) for the EXPECTED number of row tiles (rows spread evenly over
-  // the groups; m_total_hint = rows of all groups together, default = the capacity of every group)
+  // tile shape for the EXPECTED rows per group (rows spread evenly over the groups; m_total_hint = rows of all groups
+  // together, default = the capacity of every group); the true per-group counts are read on the device
   const int dual = a.B2[0] != nullptr;
   const long long rows_total = a.m_total_hint > 0 ? a.m_total_hint : static_cast<long long>(a.M) * a.groups;
   long long per_group = (rows_total + a.groups - 1) / a.groups;
   if (per_group > a.M) per_group = a.M;
-  const long long m_tiles = a.groups * ((per_group + BM - 1) / BM);
   int bn = a.tile_n;
-  if (bn == 0) bn = pick_tile_n(m_tiles, a.N, dual);
+  if (bn == 0) bn = pick_tile_n(per_group, a.groups, a.N, dual);
   switch (bn) {
 #define MPL_BN_CASE(W) \
   case W:              \
-    return launch_grouped<W>(a, stream);
+    return launch_grouped<W, false>(a, stream);
     MPL_TILE_WIDTHS(MPL_BN_CASE)
+#undef MPL_BN_CASE
+#define MPL_BN_CASE(W)   \
+  case PAIR_FLAG + W:    \
+    return launch_grouped<W, true>(a, stream);
+    MPL_PAIR_WIDTHS(MPL_BN_CASE)
 #undef MPL_BN_CASE
     default:
       return MPL_ERR_ARG;

@@ -168,6 +168,68 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
          | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2, cluster of 2 CTAs on one TPC)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: the bytes land in THIS CTA's shared memory, the completion is signalled on `mbar_cluster_addr`
+// (a shared::cluster address: the leader CTA's barrier, so ONE barrier collects both halves of a stage)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint32_t mbar_cluster_addr, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {  // the same warp of BOTH CTAs executes this
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs, 128 lanes each] (+)= A[256 rows: 128 from each CTA's smem] * B[N rows: N/2 from each CTA]^T.
+// Issued by ONE thread of the leader CTA (rank 0); the descriptors are leader-CTA addresses, the peer uses the same offsets.
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the barrier at this shared-memory offset in EVERY CTA of `cta_mask` once the pair's MMAs issued so far retired.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // wait: blocks until every prerequisite grid has completed and its writes are visible (no-op without a dependency).
 // launch_dependents: lets the next kernel in the stream (launched with the programmatic-serialization attribute)

@@ -29,6 +29,15 @@ from parity import close as _close  # noqa: E402  (logs the measured error, asse
     (300, 1000, 512, {"tile_n": 144, "bias": True, "res": True}), (300, 1001, 520, {"tile_n": 176, "f32": True}),
     (615, 11008, 4096, {"dual": True, "tile_n": 240}), (615, 11008, 4096, {"dual": True, "tile_n": 144}),
     (615, 11008, 4096, {"dual": True, "tile_n": 208}), (330, 1000, 512, {"dual": True, "tile_n": 176}),
+    # CTA-pair kernel (cta_group::2, 256-row tiles; tile_n = 1000 + width): ragged last pair (615 = 2 x 256 + 103, the
+    # peer CTA of the last pair owns no valid row), M below one CTA, three matrices, every epilogue, dual, edges
+    (615, 4096, 4096, {"tile_n": 1256}), (615, 4096, 4096, {"tile_n": 1176, "res": True}),
+    (615, 4096, 4096, {"tile_n": 1224, "nb": 3}), (100, 200, 72, {"tile_n": 1128, "bias": True}),
+    (2048, 4096, 4096, {"tile_n": 1256, "f32": True}), (577, 4096, 1024, {"tile_n": 1240, "bias": True, "act": "gelu"}),
+    (615, 11008, 4096, {"dual": True, "tile_n": 1256}), (615, 11008, 4096, {"dual": True, "tile_n": 1240}),
+    (700, 4096, 11008, {"tile_n": 1256, "res": True, "row_scale": True, "m_dev": 300}),
+    (300, 1001, 520, {"tile_n": 1160, "f32": True}), (330, 1000, 512, {"dual": True, "tile_n": 1192}),
+    (5112, 4096, 4096, {"tile_n": 1256}),
 ])
 def test_gemm_tcgen05(dev, M, N, K, kw):
     from medplib_b200 import ops
