@@ -465,16 +465,17 @@ int mpl_attention_bwd(const mpl_attn_bwd_args* args, void* stream);
 int mpl_rope_bwd(const float* dq_f32, void* dq, void* dk, long long ld, const void* cos_t, const void* sin_t, int B, int T,
                  int H, int head_dim, int pos0, void* stream);
 
-/* MoE backward (DeepSpeed top-1 gating autograd):
+/* MoE backward (DeepSpeed top-1 / top-2 gating autograd):
  *   mpl_moe_combine_bwd: dy[slot[s,j]] = gate[s,j] * dout[s]; dgate[s,j] = <dout[s], y[slot[s,j]]> (0 when dropped)
  *   (the dispatch's backward is mpl_moe_combine with unit gates)
- *   mpl_moe_router_bwd (k = 1): dlogits = softmax-backward of (dgate on the chosen expert + aux_scale * dl_aux/dgates);
- *   dh[s,:] += dlogits[s,:] wg. dwg = dlogits^T h via mpl_rank_wgrad. */
+ *   mpl_moe_router_bwd: dlogits = softmax-backward of (dgate on the chosen expert(s) + aux_scale * dl_aux/dgates);
+ *   k = 2 first takes dgate back through top2gating's renormalisation g_i / max(g_1 + g_2, eps) over the kept choices
+ *   (expert / slot / dgate are [S,k]); dh[s,:] += dlogits[s,:] wg. dwg = dlogits^T h via mpl_rank_wgrad. */
 int mpl_moe_combine_bwd(const void* dout, long long ldd, const void* y, const int* slot, const float* gate, void* dy,
                         float* dgate, int S, int k, int D, void* stream);
 int mpl_moe_router_bwd(const float* gates, const int* expert, const int* slot, const float* dgate, const int* exp_counts,
                        float aux_scale, const float* wg, float* dlogits, void* dh, long long ldh, int S, int D, int E,
-                       void* stream);
+                       int k, void* stream);
 
 /* Shifted cross-entropy of medplib_moe_llama.py:399-421 on fp32 logits: labels i64 [rows] (already shifted; < 0 ignored).
  * fwd: lse[r], acc[0] += sum of row losses, acc[1] += valid rows (acc zeroed by the caller; loss = acc[0]/acc[1]).
@@ -526,6 +527,14 @@ int mpl_layernorm_bwd(const void* x, long long ldx, const void* weight, const vo
 /* y = act(x) and dx = act'(x) dy for MPL_ACT_GELU (erf form; x = the input) / MPL_ACT_RELU (x = input or output). */
 int mpl_act_fwd(const void* x, void* y, long long n, int act, void* stream);
 int mpl_act_bwd(const void* x, const void* dy, void* dx, long long n, int act, void* stream);
+/* Vision-side adapters of the ICL recipe (scripts/train_medplib_icl.sh: --sft_modules mm_token_compressor,mask_encoder):
+ *   mpl_token_pool_bwd: adjoint of AdaptiveAvgPool1d over tokens (medplib_arch.py:73,104): dy bf16 [n,t_out,D] -> dx [n,t_in,D]
+ *   mpl_col2im_nhwc:    adjoint of mpl_im2col_nhwc (dgrad of the MaskTokenEncoder's 3x3 stride-2 convs, :84-93):
+ *                       dcols bf16 [B*Ho*Wo, kh*kw*C] -> dx bf16 [B,H,W,C] */
+int mpl_token_pool(const void* x, void* y, int n, int t_in, int t_out, int D, void* stream); /* the pool itself */
+int mpl_token_pool_bwd(const void* dy, void* dx, int n, int t_in, int t_out, int D, void* stream);
+int mpl_col2im_nhwc(const void* dcols, void* dx, int B, int H, int W, int C, int kh, int kw, int stride, int pad,
+                    void* stream);
 /* Backward of softmax(scale q k^T) v for the mask decoder's attentions (transformer.py:185-244): q [batch*Tq, ld],
  * k / v [batch*Tk, ld] (batches stacked along rows), head h = columns [h*head_dim, (h+1)*head_dim), head_dim <= 32;
  * one CTA per (head, batch). */

@@ -368,6 +368,80 @@ __global__ void __launch_bounds__(256) mask_scale_kernel(const bf16_t* __restric
   *reinterpret_cast<uint4*>(out + i) = ov;
 }
 
+// ------------------------------------------------------------------------------------------------- token pool backward
+// Adjoint of AdaptiveAvgPool1d over the token axis (TokenCompressor / MaskTokenEncoder, medplib_arch.py:67-108):
+// window j = [floor(j*Tin/Tout), ceil((j+1)*Tin/Tout)); dx[n,t,:] = sum over the windows that contain t of dy[n,j,:]/len_j.
+// Gather form (one CTA per input token): deterministic, every dy row read ~once.
+__global__ void __launch_bounds__(128) token_pool_bwd_kernel(const bf16_t* __restrict__ dy, bf16_t* __restrict__ dx,
+                                                             int t_in, int t_out, int D) {
+  const int n = blockIdx.x / t_in, t = blockIdx.x % t_in;
+  // candidate windows: j with start_j <= t < end_j; start_j is non-decreasing, so scan around floor(t*Tout/Tin)
+  int j0 = static_cast<int>((static_cast<long long>(t) * t_out) / t_in);
+  while (j0 > 0 && (static_cast<long long>(j0) * t_in + t_out - 1) / t_out > t) --j0;  // end_{j0-1} = ceil(j0*Tin/Tout) > t
+  for (int c = threadIdx.x * 2; c < D; c += 256) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = j0; j < t_out; ++j) {
+      const int st = static_cast<int>((static_cast<long long>(j) * t_in) / t_out);
+      if (st > t) break;
+      const int en = static_cast<int>((static_cast<long long>(j + 1) * t_in + t_out - 1) / t_out);
+      if (t >= en) continue;
+      const float inv = 1.0f / static_cast<float>(en - st);
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(dy + (static_cast<long long>(n) * t_out + j) * D + c);
+      a0 += __bfloat162float(v.x) * inv;
+      a1 += __bfloat162float(v.y) * inv;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(dx + (static_cast<long long>(n) * t_in + t) * D + c) = __floats2bfloat162_rn(a0, a1);
+  }
+}
+
+// AdaptiveAvgPool1d over the token axis itself (fp32 mean, one rounding): y[n,j,:] = mean_{t in window j} x[n,t,:]
+__global__ void __launch_bounds__(128) token_pool_kernel(const bf16_t* __restrict__ x, bf16_t* __restrict__ y, int t_in,
+                                                         int t_out, int D) {
+  const int n = blockIdx.x / t_out, j = blockIdx.x % t_out;
+  const int st = static_cast<int>((static_cast<long long>(j) * t_in) / t_out);
+  const int en = static_cast<int>((static_cast<long long>(j + 1) * t_in + t_out - 1) / t_out);
+  const float inv = 1.0f / static_cast<float>(en - st);
+  for (int c = threadIdx.x * 2; c < D; c += 256) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int t = st; t < en; ++t) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + (static_cast<long long>(n) * t_in + t) * D + c);
+      a0 += __bfloat162float(v.x);
+      a1 += __bfloat162float(v.y);
+    }
+    *reinterpret_cast<__nv_bfloat162*>(y + (static_cast<long long>(n) * t_out + j) * D + c) =
+        __floats2bfloat162_rn(a0 * inv, a1 * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- col2im (conv dgrad)
+// Adjoint of mpl_im2col_nhwc: dcols bf16 [B*Ho*Wo, kh*kw*C] (column (ky*kw+kx)*C+c) -> dx bf16 [B,H,W,C];
+// dx[b,y,x,c] = sum over taps (ky,kx) and outputs (oy,ox) with oy*stride - pad + ky == y, ox*stride - pad + kx == x.
+// Gather form, one CTA per input pixel.
+__global__ void __launch_bounds__(128) col2im_nhwc_kernel(const bf16_t* __restrict__ dcols, bf16_t* __restrict__ dx, int H,
+                                                          int W, int C, int kh, int kw, int stride, int pad, int Ho,
+                                                          int Wo) {
+  const int r = blockIdx.x;
+  const int b = r / (H * W), p = r % (H * W);
+  const int y = p / W, x = p % W;
+  for (int c = threadIdx.x * 2; c < C; c += 256) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int ny = y + pad - ky;
+      if (ny < 0 || ny % stride != 0 || ny / stride >= Ho) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int nx = x + pad - kx;
+        if (nx < 0 || nx % stride != 0 || nx / stride >= Wo) continue;
+        const long long row = (static_cast<long long>(b) * Ho + ny / stride) * Wo + nx / stride;
+        const __nv_bfloat162 v =
+            *reinterpret_cast<const __nv_bfloat162*>(dcols + row * kh * kw * C + (ky * kw + kx) * C + c);
+        a0 += __bfloat162float(v.x);
+        a1 += __bfloat162float(v.y);
+      }
+    }
+    *reinterpret_cast<__nv_bfloat162*>(dx + static_cast<long long>(r) * C + c) = __floats2bfloat162_rn(a0, a1);
+  }
+}
+
 }  // namespace mpl
 
 using mpl::bf16_t;
@@ -487,5 +561,35 @@ extern "C" int mpl_mask_losses_bwd(const void* pred, const float* gt, const void
   mpl::mask_losses_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ST(stream)>>>(
       static_cast<const bf16_t*>(pred), gt, static_cast<const bf16_t*>(pred_iou), sums6, dloss4, n,
       static_cast<bf16_t*>(dpred), dpred_iou);
+  return mpl::launch_status();
+}
+
+extern "C" int mpl_token_pool_bwd(const void* dy, void* dx, int n, int t_in, int t_out, int D, void* stream) {
+  if (n <= 0) return MPL_OK;
+  if (dy == nullptr || dx == nullptr || t_in <= 0 || t_out <= 0) return MPL_ERR_ARG;
+  if (D % 2 != 0) return MPL_ERR_ALIGN;
+  mpl::token_pool_bwd_kernel<<<n * t_in, 128, 0, ST(stream)>>>(static_cast<const mpl::bf16_t*>(dy),
+                                                               static_cast<mpl::bf16_t*>(dx), t_in, t_out, D);
+  return mpl::launch_status();
+}
+
+extern "C" int mpl_col2im_nhwc(const void* dcols, void* dx, int B, int H, int W, int C, int kh, int kw, int stride, int pad,
+                               void* stream) {
+  if (B <= 0) return MPL_OK;
+  if (dcols == nullptr || dx == nullptr || kh <= 0 || kw <= 0 || stride <= 0) return MPL_ERR_ARG;
+  if (C % 2 != 0) return MPL_ERR_ALIGN;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  mpl::col2im_nhwc_kernel<<<B * H * W, 128, 0, ST(stream)>>>(static_cast<const mpl::bf16_t*>(dcols),
+                                                             static_cast<mpl::bf16_t*>(dx), H, W, C, kh, kw, stride, pad, Ho,
+                                                             Wo);
+  return mpl::launch_status();
+}
+
+extern "C" int mpl_token_pool(const void* x, void* y, int n, int t_in, int t_out, int D, void* stream) {
+  if (n <= 0) return MPL_OK;
+  if (x == nullptr || y == nullptr || t_in <= 0 || t_out <= 0) return MPL_ERR_ARG;
+  if (D % 2 != 0) return MPL_ERR_ALIGN;
+  mpl::token_pool_kernel<<<n * t_out, 128, 0, ST(stream)>>>(static_cast<const mpl::bf16_t*>(x), static_cast<mpl::bf16_t*>(y),
+                                                            t_in, t_out, D);
   return mpl::launch_status();
 }

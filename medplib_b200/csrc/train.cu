@@ -1068,21 +1068,46 @@ __global__ void __launch_bounds__(128) moe_router_bwd_kernel(const float* __rest
                                                              const int* __restrict__ slot, const float* __restrict__ dgate,
                                                              const int* __restrict__ exp_counts, float aux_scale,
                                                              const float* __restrict__ wg, float* __restrict__ dlogits,
-                                                             bf16_t* __restrict__ dh, long long ldh, int S, int D, int E) {
+                                                             bf16_t* __restrict__ dh, long long ldh, int S, int D, int E,
+                                                             int k) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * 4 + warp;
   if (s >= S) return;
   float g[MPL_MAX_EXPERTS], dl[MPL_MAX_EXPERTS];
-  const int ex = expert[s];
-  const bool kept = slot[s] >= 0;
+#pragma unroll
+  for (int e = 0; e < MPL_MAX_EXPERTS; ++e) g[e] = e < E ? gates[static_cast<long long>(s) * E + e] : 0.0f;
+  // gradient of the loss w.r.t. the softmax output of each chosen expert
+  const int ex1 = expert[static_cast<long long>(s) * k];
+  const bool kept1 = slot[static_cast<long long>(s) * k] >= 0;
+  int ex2 = -1;
+  float dsel1 = kept1 ? dgate[static_cast<long long>(s) * k] : 0.0f, dsel2 = 0.0f;
+  if (k == 2) {
+    // top2gating: the two kept gate values are renormalised by max(g1 + g2, eps) (dropped ones count as 0);
+    // n_i = g_i / den  ->  dg_i = (dn_i - (dn_1 n_1 + dn_2 n_2)) / den  (the clamp passes no gradient to the sum)
+    ex2 = expert[static_cast<long long>(s) * 2 + 1];
+    const bool kept2 = slot[static_cast<long long>(s) * 2 + 1] >= 0;
+    float g1 = 0.0f, g2 = 0.0f;
+#pragma unroll
+    for (int e = 0; e < MPL_MAX_EXPERTS; ++e) {
+      if (e == ex1 && kept1) g1 = g[e];
+      if (e == ex2 && kept2) g2 = g[e];
+    }
+    const float eps = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
+    const float sum = g1 + g2, den = fmaxf(sum, eps);
+    const float dn1 = dsel1, dn2 = kept2 ? dgate[static_cast<long long>(s) * 2 + 1] : 0.0f;
+    const float t = sum > eps ? (dn1 * g1 + dn2 * g2) / den : 0.0f;
+    dsel1 = kept1 ? (dn1 - t) / den : 0.0f;
+    dsel2 = kept2 ? (dn2 - t) / den : 0.0f;
+  }
   float inner = 0.0f;
 #pragma unroll
   for (int e = 0; e < MPL_MAX_EXPERTS; ++e) {
-    g[e] = e < E ? gates[static_cast<long long>(s) * E + e] : 0.0f;
     float dg = 0.0f;
     if (e < E) {
+      // l_aux = E * sum_e mean_s(gates)[e] * mean_s(mask1)[e] for both gatings (top-2: mean(me * ce) * E * E)
       dg = aux_scale * E * (static_cast<float>(exp_counts[e]) / S) / S;
-      if (e == ex && kept) dg += dgate[s];
+      if (e == ex1) dg += dsel1;
+      if (e == ex2) dg += dsel2;
     }
     dl[e] = dg;
     inner += g[e] * dg;
@@ -1529,14 +1554,14 @@ extern "C" int mpl_moe_combine_bwd(const void* dout, long long ldd, const void* 
 
 extern "C" int mpl_moe_router_bwd(const float* gates, const int* expert, const int* slot, const float* dgate,
                                   const int* exp_counts, float aux_scale, const float* wg, float* dlogits, void* dh,
-                                  long long ldh, int S, int D, int E, void* stream) {
+                                  long long ldh, int S, int D, int E, int k, void* stream) {
   if (S <= 0) return MPL_OK;
   if (gates == nullptr || expert == nullptr || slot == nullptr || dgate == nullptr || exp_counts == nullptr ||
-      wg == nullptr || dlogits == nullptr || dh == nullptr || E < 1 || E > MPL_MAX_EXPERTS)
+      wg == nullptr || dlogits == nullptr || dh == nullptr || E < 1 || E > MPL_MAX_EXPERTS || (k != 1 && k != 2))
     return MPL_ERR_ARG;
   if (D % 2 != 0) return MPL_ERR_ALIGN;
   moe_router_bwd_kernel<<<(S + 3) / 4, 128, 0, ST(stream)>>>(gates, expert, slot, dgate, exp_counts, aux_scale, wg, dlogits,
-                                                             static_cast<bf16_t*>(dh), ldh, S, D, E);
+                                                             static_cast<bf16_t*>(dh), ldh, S, D, E, k);
   return launch_status();
 }
 

@@ -554,19 +554,25 @@ class MedPLIBForCausalLM(PreTrainedModel):
             return input_ids, attention_mask, past_key_values, None, labels
         per_token = False
         feat_blocks = []  # list of [n_tokens, D] tensors in sentinel order
+        block_kinds = None  # ICL separate mode: "image" / "mask" per block (None: all image blocks)
+        mask_cat = None
 
         if image_token_types is not None and mask_images is not None and len(mask_images) > 0:
             assert type(images) is list or images.ndim == 5
             assert not region_flag
             raw_f, img_f, _ = self.encode_images(torch.cat([im for im in images], dim=0))
-            msk_f = self.encode_masks(torch.cat([m for m in mask_images], dim=0))
+            mask_cat = torch.cat([m for m in mask_images], dim=0)
+            msk_f = self.encode_masks(mask_cat)
             ii = mi = 0
+            block_kinds = []
             for types_ in image_token_types:
                 for t in types_:
                     if t == "mask":
                         feat_blocks.append(msk_f[mi]); mi += 1
+                        block_kinds.append("mask")
                     else:
                         feat_blocks.append(img_f[ii]); ii += 1
+                        block_kinds.append("image")
             per_token = True
         elif type(images) is list or images.ndim == 5:
             assert not region_flag
@@ -653,26 +659,37 @@ class MedPLIBForCausalLM(PreTrainedModel):
         feats_all = torch.cat(feat_blocks + ([torch.stack(extra_rows)] if extra_rows else []), dim=0).contiguous()
         embeds = ops.gather_rows(idx.reshape(-1), self.model.embed_tokens.weight, feats_all, D=D).view(len(plans), T, D)
         self._splice_idx = idx.reshape(-1)  # adjoint of the splice (embed_tokens gradient) in the train step
+        # ---- train step: what the backward of the vision-side adapters needs (mm_projector: scripts/train_stage2.sh;
+        # mm_token_compressor / mask_encoder: scripts/train_medplib_icl.sh). Feature row k of a block sits at output row
+        # pos[k] of the spliced prompt (-1: the prompt never used it).
         self._proj_ctx = None
-        proj = self.get_model().mm_projector
-        if labels is not None and torch.is_grad_enabled() and self.training \
-                and any(p.requires_grad for p in proj.parameters()):
-            if per_token and image_token_types is not None or getattr(self.config, "mm_token_compress", False) \
-                    or isinstance(proj, nn.Linear):
-                self._proj_ctx = dict(unsupported="mm_projector gradients are built for the mlp2x_gelu projector without "
-                                      "token compression / ICL mask tokens (scripts/train_stage2.sh); freeze it otherwise")
-        if labels is not None and torch.is_grad_enabled() and self.training and self._proj_ctx is None \
-                and any(p.requires_grad for p in proj.parameters()):
-            # inverse of the splice for the image rows: feature row k sits at output row pos[k] (-1: unused)
-            n_img_rows = off
-            pos = [-1] * n_img_rows
+        mdl = self.get_model()
+        proj = mdl.mm_projector
+        compress = bool(getattr(self.config, "mm_token_compress", False))
+        tracking = labels is not None and torch.is_grad_enabled() and self.training
+        proj_tr = tracking and any(p.requires_grad for p in proj.parameters())
+        comp_tr = tracking and compress and any(p.requires_grad for p in mdl.mm_token_compressor.parameters())
+        menc_tr = tracking and mask_cat is not None and any(p.requires_grad for p in mdl.mask_encoder.parameters())
+        if proj_tr and isinstance(proj, nn.Linear):
+            self._proj_ctx = dict(unsupported="mm_projector gradients are built for the mlp2x_gelu projector "
+                                  "(multimodal_projector/builder.py:39-46); freeze a linear projector")
+        elif proj_tr or comp_tr or menc_tr:
+            n_rows = off
+            pos = [-1] * n_rows
             for b, p in enumerate(plans):
                 for t, v in enumerate(p):
-                    if v <= -2 and -v - 2 < n_img_rows:
+                    if v <= -2 and -v - 2 < n_rows:
                         pos[-v - 2] = b * T + t
+            img_pos, mask_pos = [], []
+            for bi, f in enumerate(feat_blocks):
+                seg = pos[offsets[bi]:offsets[bi] + f.shape[0]]
+                (mask_pos if block_kinds is not None and block_kinds[bi] == "mask" else img_pos).extend(seg)
             raw_all = raw_f if not isinstance(raw_f, list) else torch.cat(raw_f, 0)
-            self._proj_ctx = dict(pos=torch.tensor(pos, dtype=torch.int32, device=dev),
-                                  feats=raw_all.reshape(-1, raw_all.shape[-1]))
+            self._proj_ctx = dict(pos=torch.tensor(img_pos, dtype=torch.int32, device=dev),
+                                  feats=raw_all.reshape(-1, raw_all.shape[-1]), n_img=int(raw_all.shape[0]),
+                                  compress=compress, proj_train=proj_tr, comp_train=comp_tr)
+            if menc_tr:
+                self._proj_ctx["mask"] = dict(pos=torch.tensor(mask_pos, dtype=torch.int32, device=dev), images=mask_cat)
         if raw_samples:
             # output rows that hold region features, in extra_rows order (plan entries <= -(off) - 2)
             pos = [b * T + t for b, p in enumerate(plans) for t, v in enumerate(p) if v <= -off - 2]
@@ -1106,14 +1123,9 @@ class MedPLIBForCausalLM(PreTrainedModel):
 
 
 def _adaptive_pool_tokens(x, n_out):
-    """AdaptiveAvgPool1d over the token axis as the pool+LN kernel with an identity LayerNorm bypassed: windows are
-    [floor(i*T/n), ceil((i+1)*T/n)). Implemented with mpl_col_mean per window group to stay on hand-written kernels."""
-    n, T, C = x.shape
-    outs = []
-    for i in range(n_out):
-        a, b = (i * T) // n_out, -((-(i + 1) * T) // n_out)
-        outs.append(ops.col_mean(x[:, a:b].contiguous()))
-    return torch.stack(outs, dim=1)
+    """AdaptiveAvgPool1d over the token axis: windows [floor(i*T/n), ceil((i+1)*T/n)), fp32 mean (mpl_token_pool)."""
+    from .. import train_ops
+    return train_ops.token_pool(x, n_out)
 
 
 def _grow_cache(eng, cache, new_tmax):

@@ -286,9 +286,8 @@ class LlamaTrainStack:
                 T.transpose(w.detach(), out=L.wqkvT[:, j * D:(j + 1) * D])
             L.woT = T.transpose(L.wo.detach())
             if isinstance(layer.mlp, M.MoE):
-                if self.top_k != 1:
-                    raise _lib.MplError("the train step is built for top-1 gating (scripts/train_stage4.sh); top-2 "
-                                        "backward is not")
+                if self.top_k not in (1, 2):
+                    raise _lib.MplError("DeepSpeed's TopKGate supports top-1 and top-2 gating only")
                 L.wg = layer.mlp.deepspeed_moe.gate.wg.weight
                 mlps = list(layer.mlp.deepspeed_moe.experts.deepspeed_experts)
             else:
@@ -341,7 +340,7 @@ class LlamaTrainStack:
             T.mask_scale(tmp, mask, 1.0 / (1.0 - lo.p), out=dx, accumulate=True)
 
     def capacity(self, S, E):
-        return ops.moe_capacity(S, E, self.cf, self.min_cap, 1)
+        return ops.moe_capacity(S, E, self.cf, self.min_cap, self.top_k)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, B, Tn, kv_mask=None, moe_noise=None):
@@ -382,9 +381,12 @@ class LlamaTrainStack:
             if L.wg is not None:
                 C = self.capacity(S, E)
                 noise = moe_noise[li] if moe_noise is not None else None
-                if noise is None and self.use_rts:
+                if noise is None and self.top_k == 2:
+                    # top2gating draws Gumbel(0, 1) noise for the second choice (gumbel_rsample), in eval mode too
+                    noise = -torch.log(-torch.log(torch.rand((S, E), dtype=f32, device=dev).clamp_(1e-20, 1.0 - 1e-7)))
+                elif noise is None and self.use_rts:
                     noise = torch.rand((S, E), dtype=f32, device=dev)
-                route = ops.moe_route(n2, L.wg.detach(), 1, C, noise)
+                route = ops.moe_route(n2, L.wg.detach(), self.top_k, C, noise)
                 l_aux.append(route["l_aux"])
                 gate_logits.append(route["logits"])
                 rows = E * C
@@ -565,7 +567,7 @@ class _StackFn(torch.autograd.Function):
             if gb is not None:
                 T.col_sum(dfeat, gb)
         if ctx.proj_ctx is not None:
-            _projector_backward(tr, ctx.proj_ctx, dx0)
+            _vision_backward(tr, ctx.proj_ctx, dx0)
         ctx.saved = None
         tr.micro_steps += 1  # the stack's backward is the last node of a micro-step
         grads = ()
@@ -592,14 +594,12 @@ def _wgrad_tc(dy, x, out, accumulate):
         T.col_sum(tmp.view(1, -1), out.view(-1))
 
 
-def _projector_backward(tr, pc, dx0):
+def _projector_backward(tr, x, dF):
     """mm_projector = Linear(1024, D) + GELU + Linear(D, D) (multimodal_projector/builder.py:39-46) on the frozen CLIP
-    features: weight / bias gradients from the input-embedding gradient at the image rows (no gradient into CLIP)."""
+    features x: weight / bias gradients from dF = the gradient at the projector's output rows (no gradient into CLIP)."""
     proj = tr.model.model.mm_projector
     ar = tr.arena
     acc = tr.micro_steps > 0
-    x = pc["feats"].contiguous()
-    dF = ops.gather_rows(pc["pos"], table=dx0)  # [n_img_rows, D]; rows the prompt never used are zero
     z0 = ops.linear(x, proj[0].weight.detach(), bias=proj[0].bias.detach())
     h1 = T.act_fwd(z0, "gelu")
     if ar.of(proj[2].weight) is not None:
@@ -612,6 +612,98 @@ def _projector_backward(tr, pc, dx0):
         _wgrad_tc(dz0, x, ar.of(proj[0].weight), acc)
     if ar.of(proj[0].bias) is not None:
         T.col_sum(dz0, ar.of(proj[0].bias))
+
+
+def _vision_backward(tr, pc, dx0):
+    """Backward of the vision-side adapters from dx0, the gradient w.r.t. the spliced input embeddings:
+    TokenCompressor (AdaptiveAvgPool1d 576 -> 256 + LayerNorm + Linear, medplib_arch.py:67-77) and, below it, the
+    mm_projector; MaskTokenEncoder (4 x conv3x3 s2 + GELU, pool, Linear, LayerNorm, medplib_arch.py:80-108). The forward
+    intermediates are recomputed here (the adapters are < 0.1 % of a step); the CLIP tower is frozen."""
+    mdl = tr.model.model
+    ar = tr.arena
+    acc = tr.micro_steps > 0
+    x = pc["feats"].contiguous()
+    dF = ops.gather_rows(pc["pos"], table=dx0)  # [image feature rows, D]; rows the prompt never used are zero
+    if pc.get("compress"):
+        c = mdl.mm_token_compressor
+        proj = mdl.mm_projector
+        if pc.get("comp_train") or pc.get("proj_train"):
+            n_img = pc["n_img"]
+            if isinstance(proj, nn.Linear):
+                x1 = ops.linear(x, proj.weight.detach(), bias=proj.bias.detach())
+            else:
+                x1 = ops.linear(x, proj[0].weight.detach(), bias=proj[0].bias.detach(), act="gelu")
+                x1 = ops.linear(x1, proj[2].weight.detach(), bias=proj[2].bias.detach())
+            D = x1.shape[-1]
+            t_in = x1.shape[0] // n_img
+            pooled = T.token_pool(x1.view(n_img, t_in, D), c.num_tokens).view(-1, D)
+            ln_out = ops.layernorm(pooled, c.norm.weight.detach(), c.norm.bias.detach(), c.norm.eps)
+            if ar.of(c.proj.weight) is not None:
+                _wgrad_tc(dF, ln_out, ar.of(c.proj.weight), acc)
+            if ar.of(c.proj.bias) is not None:
+                T.col_sum(dF, ar.of(c.proj.bias))
+            d_ln = ops.linear(dF, T.transpose(c.proj.weight.detach()))
+            d_pooled = T.layernorm_bwd(pooled, c.norm.weight.detach(), d_ln, c.norm.eps, dweight=ar.of(c.norm.weight),
+                                       dbias=ar.of(c.norm.bias))
+            dF = T.token_pool_bwd(d_pooled.view(n_img, c.num_tokens, D), t_in).view(-1, D) if pc.get("proj_train") else None
+    if pc.get("proj_train") and dF is not None:
+        _projector_backward(tr, x, dF)
+    if pc.get("mask") is not None:
+        _mask_encoder_backward(tr, pc["mask"], dx0)
+
+
+def _mask_encoder_backward(tr, mc, dx0):
+    """MaskTokenEncoder backward (medplib_arch.py:80-108): the convs are im2col GEMMs on NHWC rows, so their dgrad is a
+    GEMM + col2im (mpl_col2im_nhwc) and their wgrad dz^T cols."""
+    me = tr.model.model.mask_encoder
+    ar = tr.arena
+    x = mc["images"]
+    if x.dim() == 3:
+        x = x.unsqueeze(1)
+    x = x[:, :1].to(bf16).permute(0, 2, 3, 1).contiguous()
+    n = x.shape[0]
+    x = torch.cat([x, x.new_zeros(*x.shape[:3], 7)], dim=-1)  # C = 1 -> 8 (16-byte rows), as the forward
+    saved = []
+    for i in (0, 2, 4, 6):
+        conv = me.encoder[i]
+        H, Cin = x.shape[1], x.shape[-1]
+        w = conv.weight.detach()
+        if w.shape[1] != Cin:
+            w = torch.cat([w, w.new_zeros(w.shape[0], Cin - w.shape[1], 3, 3)], dim=1)
+        w2 = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+        cols = ops.im2col_nhwc(x, 3, 3, 2, 1)
+        Ho = (H + 2 - 3) // 2 + 1
+        z = ops.linear(cols, w2, bias=conv.bias.detach())
+        saved.append((conv, H, Cin, w2, cols, z))
+        x = T.act_fwd(z, "gelu").view(n, Ho, Ho, -1)
+    C = x.shape[-1]
+    feats = x.reshape(n, -1, C)
+    pooled = T.token_pool(feats, me.num_tokens).view(-1, C)
+    y = ops.linear(pooled, me.proj.weight.detach(), bias=me.proj.bias.detach())
+    d_out = ops.gather_rows(mc["pos"], table=dx0)  # [n * num_tokens, D]
+    dy = T.layernorm_bwd(y, me.norm.weight.detach(), d_out, me.norm.eps, dweight=ar.of(me.norm.weight),
+                         dbias=ar.of(me.norm.bias))
+    if ar.of(me.proj.weight) is not None:
+        T.gemm_small(dy, pooled, out=ar.of(me.proj.weight), trans_a=True, accumulate=True)
+    if ar.of(me.proj.bias) is not None:
+        T.col_sum(dy, ar.of(me.proj.bias))
+    d_pooled = ops.linear(dy, T.transpose(me.proj.weight.detach()))
+    d = T.token_pool_bwd(d_pooled.view(n, me.num_tokens, C), feats.shape[1]).view(-1, C)
+    for li in range(len(saved) - 1, -1, -1):
+        conv, H, Cin, w2, cols, z = saved[li]
+        dz = T.act_bwd(z, d, "gelu")
+        gW = ar.of(conv.weight)
+        if gW is not None:
+            # dW2 [Cout, (ky, kx, ci)] = dz^T cols; the parameter is [Cout, Cin, ky, kx] (first conv: channel 0 of the 8)
+            dW2 = torch.zeros((dz.shape[1], cols.shape[1]), dtype=f32, device=dz.device)
+            T.gemm_small(dz, cols, out=dW2, trans_a=True, accumulate=True)  # (accumulate mode: split-K over the rows)
+            cin_p = conv.weight.shape[1]
+            gW.add_(dW2.view(dW2.shape[0], 3, 3, Cin)[..., :cin_p].permute(0, 3, 1, 2))
+        if ar.of(conv.bias) is not None:
+            T.col_sum(dz, ar.of(conv.bias))
+        if li > 0:
+            dcols = ops.linear(dz, T.transpose(w2))
+            d = T.col2im_nhwc(dcols, n, H, H, Cin, 3, 3, 2, 1).view(-1, Cin)
 
 
 class _HeadCEFn(torch.autograd.Function):

@@ -174,14 +174,15 @@ def moe_combine_bwd(dout, y, slot, gate, rows):
 
 
 def moe_router_bwd(route, dgate, wg, dh, aux_scale=0.0):
-    """top-1 router backward; dh (bf16 [S,D]) is updated in place; returns dlogits f32 [S,E]."""
+    """top-1 / top-2 router backward; dh (bf16 [S,D]) is updated in place; returns dlogits f32 [S,E]."""
     lib = _lib.load()
     S, E = route["gates"].shape
     D = dh.shape[-1]
     dlogits = torch.empty((S, E), dtype=f32, device=dh.device)
     _lib.check(lib.mpl_moe_router_bwd(_ptr(route["gates"]), _ptr(route["expert"]), _ptr(route["slot"]), _ptr(dgate),
                                       _ptr(route["exp_counts"]), _F(aux_scale), _ptr(wg), _ptr(dlogits), _ptr(dh),
-                                      _ll(dh.stride(0)), S, D, E, _stream()), "mpl_moe_router_bwd")
+                                      _ll(dh.stride(0)), S, D, E, int(route["slot"].shape[1]), _stream()),
+               "mpl_moe_router_bwd")
     return dlogits
 
 
@@ -363,3 +364,32 @@ def mask_scale(x, mask, scale, out=None, accumulate=False):
     _lib.check(lib.mpl_mask_scale_bf16(_ptr(x), _ptr(mask), _F(scale), _ptr(out), int(accumulate), _ll(x.numel()),
                                        _stream()), "mpl_mask_scale_bf16")
     return out
+
+
+def token_pool(x, t_out):
+    """AdaptiveAvgPool1d over tokens: x bf16 [n, t_in, D] -> [n, t_out, D]."""
+    lib = _lib.load()
+    x = x.contiguous()
+    n, t_in, D = x.shape
+    y = torch.empty((n, t_out, D), dtype=bf16, device=x.device)
+    _lib.check(lib.mpl_token_pool(_ptr(x), _ptr(y), n, t_in, t_out, D, _stream()), "mpl_token_pool")
+    return y
+
+
+def token_pool_bwd(dy, t_in):
+    """Adjoint of AdaptiveAvgPool1d over tokens: dy bf16 [n, t_out, D] -> dx bf16 [n, t_in, D]."""
+    lib = _lib.load()
+    dy = dy.contiguous()
+    n, t_out, D = dy.shape
+    dx = torch.empty((n, t_in, D), dtype=bf16, device=dy.device)
+    _lib.check(lib.mpl_token_pool_bwd(_ptr(dy), _ptr(dx), n, t_in, t_out, D, _stream()), "mpl_token_pool_bwd")
+    return dx
+
+
+def col2im_nhwc(dcols, B, H, W, C, kh, kw, stride, pad):
+    """Adjoint of ops.im2col_nhwc: dcols bf16 [B*Ho*Wo, kh*kw*C] -> dx bf16 [B, H, W, C]."""
+    lib = _lib.load()
+    dcols = dcols.contiguous()
+    dx = torch.empty((B, H, W, C), dtype=bf16, device=dcols.device)
+    _lib.check(lib.mpl_col2im_nhwc(_ptr(dcols), _ptr(dx), B, H, W, C, kh, kw, stride, pad, _stream()), "mpl_col2im_nhwc")
+    return dx

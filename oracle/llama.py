@@ -133,7 +133,10 @@ def decoder_layer(sd, i, x, cfg, mask, position_ids, past_kv, cos, sin, training
     x = residual + h
     residual = x
     h = rmsnorm(x, sd[prefix + "post_attention_layernorm.weight"], eps)
-    h, l_aux, exp_counts, logits = layer_mlp(sd, prefix, h, cfg, training, rts_uniform)
+    # the injected per-layer noise is what the gating of this layer consumes: RTS uniforms (top-1) / Gumbel noise (top-2)
+    top2 = (cfg.get("moe") or {}).get("top_k_experts", 1) == 2
+    h, l_aux, exp_counts, logits = layer_mlp(sd, prefix, h, cfg, training, None if top2 else rts_uniform,
+                                             rts_uniform if top2 else None)
     x = residual + h
     return x, kv, l_aux, exp_counts, logits
 

@@ -21,11 +21,12 @@ TOL = 1e-1
 
 
 def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,down_proj", sft=SFT, dropout=0.0,
-          moe_layers=None):
+          moe_layers=None, top_k=1):
     import test_model_gpu as tm
     from medplib_b200 import train
     m, _, ocfg = tm.build(dev, moe_layers=moe_layers)
     m.config.moe["capacity_factor"] = cf
+    m.config.moe["top_k_experts"] = top_k
     m.config.moe["router_aux_loss_coef"] = aux
     m.router_aux_loss_coef = aux
     m.ce_loss_weight, m.bce_loss_weight, m.dice_loss_weight = W["ce"], W["bce"], W["dice"]
@@ -184,9 +185,10 @@ def dropout_masks(m, S, C, p, seed=21):
     return out
 
 
-def run_case(dev, seg_flag, cf, pad, aux, region=False, dropout=0.0, **build_kw):
+def run_case(dev, seg_flag, cf, pad, aux, region=False, dropout=0.0, seed=None, **build_kw):
     m, sd, ocfg = build(dev, cf=cf, aux=aux, dropout=dropout, **build_kw)
-    seed = 27 if region else (205 if dropout > 0 else (8 if build_kw.get("moe_layers") is not None else 5))
+    if seed is None:
+        seed = 27 if region else (205 if dropout > 0 else (8 if build_kw.get("moe_layers") is not None else 5))
     b = batch(seg=seg_flag, pad=pad, region=region, seed=seed)
     ids, labels, am, clip_img, sam_img, gts = b[:6]
     rm = [[x.to(dev) for x in r] for r in b[6]] if region else None
@@ -249,6 +251,17 @@ def run_case(dev, seg_flag, cf, pad, aux, region=False, dropout=0.0, **build_kw)
         print("  %.3e  %s  %.3e  %.3e  %.3e  %.3e" % r)
     assert not bad, f"gradients out of tolerance: {bad[:8]} ({len(bad)} of {len(train_names)})"
     return m, tr, sd, train_names
+
+
+@pytest.mark.parametrize("cf,pad,aux", [(1.0, False, 0.01), (0.4, True, 0.01)])
+def test_top2_gating_loss_and_gradients(dev, cf, pad, aux):
+    """top_k_experts = 2 (the reference config class's default, model/MedPLIB.py:258): both choices dispatched, combine
+    weights renormalised by g1 + g2, capacity 2 * cf * S / E with position-order drops (cf = 0.4 drops second choices and
+    some first ones), the injected per-layer noise is top2gating's Gumbel term. Gradients through the renormalisation,
+    the softmax and the aux loss vs torch.autograd over oracle/moe.py::top2gating."""
+    # (a batch seed where every token's router margin (> 0.12 on the GPU and in both oracles, tests/dev/debug_top2.py) is
+    # well above the bf16 activation noise of ~0.04 in both layers)
+    run_case(dev, False, cf, pad, aux, top_k=2, seed=53)
 
 
 @pytest.mark.parametrize("cf,pad,aux", [(1.5, False, 0.01), (0.6, True, 0.0)])
@@ -518,3 +531,101 @@ def test_lisa_dense_twin_inference_and_train_step(dev):
         if not (e16 <= TOL or e32 <= TOL or e32 <= 1.5 * cond):
             bad.append((n, e32, e16))
     assert not bad, bad[:6]
+
+
+def test_icl_recipe_compressor_and_mask_encoder_gradients(dev):
+    """scripts/train_medplib_icl.sh with ICL_MASK_MODE=separate: --sft_modules mask_decoder,text_hidden_fcs,mask_encoder,
+    mm_token_compressor, LoRA on gate/up/down, two (image, mask) exemplars + the query image per sample, compressed
+    image tokens (16 -> 8) and MaskTokenEncoder tokens (4 per mask), [SEG] + ground-truth mask. Every trainable
+    tensor's gradient -- the TokenCompressor's LayerNorm / Linear, the MaskTokenEncoder's four convs, Linear and
+    LayerNorm included -- against torch.autograd over oracle/train.py::train_losses_icl; mm_projector trained too in a
+    second pass (its gradient flows back through the pool)."""
+    import test_model_gpu as tm
+    from medplib_b200 import train
+    from oracle import train as otrain
+    for sft in ("mask_decoder,text_hidden_fcs,mask_encoder,mm_token_compressor",
+                "mask_encoder,mm_token_compressor,mm_projector"):
+        m, _, ocfg = tm.build_icl(dev)
+        m.config.moe["capacity_factor"] = 1.5
+        m.router_aux_loss_coef = 0.01
+        m.ce_loss_weight, m.bce_loss_weight, m.dice_loss_weight = W["ce"], W["bce"], W["dice"]
+        m.iou_loss_weight, m.focal_loss_weight = W["iou"], W["focal"]
+        train.attach_lora(m, r=8, lora_alpha=16, lora_dropout=0.0, target_modules="gate_proj,up_proj,down_proj")
+        train.set_trainable(m, sft)
+        g = torch.Generator().manual_seed(7)
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if "lora_B" in n:
+                    p.copy_((torch.randn(p.shape, generator=g) * 0.05).to(p.dtype))
+                if "wg.weight" in n:
+                    p.mul_(0.2)
+        m.train()
+        sd = {k: v.detach().cpu().float() for k, v in m.state_dict().items()}
+        sd.update({k: v.detach().cpu().float() for k, v in m.named_buffers()})
+        sd["lora_scaling"] = 2.0
+        ocfg["llama"]["moe"] = dict(m.config.moe)
+        g = torch.Generator().manual_seed(4)
+        types_ = [["image", "mask", "image", "mask", "image"]]
+        lengths = [[8, 4, 8, 4, 8]]
+        ids = torch.randint(3, 290, (1, 26), generator=g)
+        for pos in (2, 6, 10, 14, 18):
+            ids[0, pos] = -200
+        ids[0, 23] = SEG
+        labels = ids.clone()
+        labels[:, :20] = -100
+        am = torch.ones_like(ids, dtype=torch.bool)
+        clip_imgs = [torch.randn(3, 3, 56, 56, generator=g).to(bf16)]
+        mask_imgs = [(torch.rand(2, 1, 56, 56, generator=g) > 0.8).to(bf16)]
+        sam_img = torch.randn(1, 3, 256, 256, generator=g).to(bf16)
+        gts = [(torch.rand(70, 90, generator=g) > 0.6).float()]
+        S = 26 - 5 + 3 * 8 + 2 * 4
+        noise = [torch.rand(S, 2, generator=g) for _ in range(2)]
+        train_names = [n for n, p in m.named_parameters() if p.requires_grad]
+        assert any("mm_token_compressor" in n for n in train_names) and any("mask_encoder.encoder.0" in n for n in train_names)
+
+        def oracle(sdx, dtype):
+            out, aux = otrain.train_losses_icl(sdx, ocfg, [c.to(dtype) for c in clip_imgs], [x.to(dtype) for x in mask_imgs],
+                                               types_, lengths, sam_img.to(dtype), ids, labels, am, gts, [(70, 90)],
+                                               [(256, 256)], SEG, W, rts_uniforms=noise)
+            return out, aux
+
+        sd16 = {k: ((v.to(bf16) if "wg.weight" not in k else v.detach().clone())
+                    if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in sd.items()}
+        for n in train_names:
+            sd[n].requires_grad_(True)
+            sd16[n].requires_grad_(True)
+        ref, aux_o = oracle(sd, torch.float32)
+        ref["loss"].backward()
+        ref16, _ = oracle(sd16, bf16)
+        ref16["loss"].backward()
+        tr = m.trainer(lr=1e-2)
+        tr.zero_grad()
+        out = m(images=sam_img.to(dev), images_clip=[c.to(dev) for c in clip_imgs], input_ids=ids.to(dev),
+                region_masks=None, labels=labels.to(dev), attention_mask=am.to(dev), offset=None,
+                masks_list=[x.to(dev) for x in gts], label_list=[x.to(dev) for x in gts], resize_list=[(256, 256)],
+                inference=False, mask_images=[x.to(dev) for x in mask_imgs], image_token_types=types_,
+                image_token_lengths=lengths, icl_image_counts=[3], moe_noise=[x.to(dev) for x in noise])
+        for l, lg in enumerate(tr.last_gate_logits):
+            assert torch.equal(lg.argmax(-1).cpu(), aux_o["gate_logits"][l].argmax(-1)), f"routing differs in layer {l}"
+        out["loss"].backward()
+        torch.cuda.synchronize()
+        for k in ref:
+            r, o = float(ref[k].detach()), float(out[k].detach())
+            assert abs(o - r) <= 3e-2 * max(abs(r), 1e-3) + 1e-4, f"{k}: {o} vs oracle {r}"
+        grads = tr.arena.grads()
+        assert set(grads) == set(train_names)
+        bad, report = [], []
+        for n in train_names:
+            if not ("mm_token_compressor" in n or "mask_encoder" in n or "mm_projector" in n):
+                continue  # (the rest of the step is covered by the tests above)
+            r32, r16 = sd[n].grad, sd16[n].grad
+            e32, scale = _relerr(grads[n], r32)
+            e16, _ = _relerr(grads[n], r16)
+            cond, _ = _relerr(r16, r32)
+            report.append((n, e32, e16, cond, scale))
+            if not (e16 <= TOL or e32 <= TOL or e32 <= 1.5 * cond):
+                bad.append(n)
+        print("\nvision-side adapter gradients: name | vs fp32 oracle | vs bf16 oracle | bf16-vs-fp32 oracle | scale")
+        for r in report:
+            print("  %s  %.3e  %.3e  %.3e  %.3e" % r)
+        assert len(report) >= 12 and not bad, f"gradients out of tolerance: {bad}"
