@@ -313,6 +313,9 @@ typedef struct {
   int* exp_counts;               /* NULL or int [n_layers, E] out */
   void* workspace;
   long long workspace_bytes;
+  const int* rope_pos; /* NULL, or device int [B] (decode step through decode_plan only): RoPE position of each sequence's
+                          new token when it differs from the cache column past_len -- continuous batching, where the
+                          sequences of a batch share the write column but have their own lengths (kv_mask hides the rest) */
 } mpl_llama_io;
 long long mpl_llama_workspace_bytes(const mpl_llama_model* model, int B, int T);
 /* Device-resident decode plan (TMA descriptors of every weight matrix + the grid-barrier words). Build once per weight

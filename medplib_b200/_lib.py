@@ -111,7 +111,7 @@ class LlamaIO(ctypes.Structure):
         ("kv_mask", c_void_p), ("kv_mask_stride", c_ll), ("pos_dev", c_void_p), ("tk_dev", c_void_p),
         ("attn_scratch", c_void_p), ("attn_scratch_bytes", c_ll), ("decode_plan", c_void_p),
         ("moe_noise", ctypes.POINTER(c_void_p)), ("gate_logits", c_void_p), ("l_aux", c_void_p),
-        ("exp_counts", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_ll),
+        ("exp_counts", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_ll), ("rope_pos", c_void_p),
     ]
 
 

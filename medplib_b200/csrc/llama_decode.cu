@@ -81,6 +81,7 @@ struct DecParams {
   const unsigned char* kv_mask;
   long long kv_mask_stride;
   const int* pos_dev;
+  const int* rope_pos;  // [B] or NULL: per-sequence RoPE position of the new token (cache column stays `pos`)
   float* gate_logits;  // [L, B, Emax] or NULL
   float* l_aux;        // [L] or NULL
   int* exp_counts;     // [L, Emax] or NULL
@@ -332,8 +333,6 @@ __device__ __forceinline__ void attention_phase(const DecParams& p, int layer, i
   const int pos = Tk - 1;
   const int n_items = p.B * p.H * nsplit;
   const int stride = gridDim.x * DK_CONSUMERS;
-  const __nv_bfloat16* cr = p.cos_t + static_cast<long long>(pos) * D;
-  const __nv_bfloat16* sr = p.sin_t + static_cast<long long>(pos) * D;
   const float sl2 = p.scale * 1.4426950408889634f;
   bool synced = false;
   // items are dealt round-robin over the CTAs first, so every SM pulls on the KV cache
@@ -343,6 +342,9 @@ __device__ __forceinline__ void attention_phase(const DecParams& p, int layer, i
     const AttnItem it = attn_item(p, has ? item : 0, Tk);
     const int k_lo = it.k_lo;
     const int k_end = has ? min(it.k_hi, pos) : k_lo;  // cached keys of this split: [k_lo, k_end)
+    const int rp = p.rope_pos != nullptr ? p.rope_pos[it.b] : pos;  // rotation angle of this sequence's new token
+    const __nv_bfloat16* cr = p.cos_t + static_cast<long long>(rp) * D;
+    const __nv_bfloat16* sr = p.sin_t + static_cast<long long>(rp) * D;
     const __nv_bfloat16* qrow = p.qkv + static_cast<long long>(it.b) * 3 * p.D + it.h * D;
     const long long head_off = (static_cast<long long>(it.b) * p.H + it.h) * p.Tmax * D;
     __nv_bfloat16* kc = p.kc + layer * p.cache_layer + head_off;
@@ -1182,6 +1184,7 @@ int llama_decode_step(const mpl_llama_model& m, const mpl_llama_io& io, void* qk
   p.kv_mask = io.kv_mask;
   p.kv_mask_stride = io.kv_mask_stride;
   p.pos_dev = io.pos_dev;
+  p.rope_pos = io.rope_pos;
   p.gate_logits = io.gate_logits;
   p.l_aux = io.l_aux;
   p.exp_counts = io.exp_counts;

@@ -132,6 +132,7 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
     if (static_cast<long long>(emax) * B * F * 2 <= (w.y - w.h1))
       return llama_decode_step(m, io, w.qkv, w.attn, w.h1, cap, emax, st);
   }
+  if (io.rope_pos != nullptr) return MPL_ERR_UNSUPPORTED;  // per-sequence positions exist in the one-kernel decode step only
   const long long cache_layer = static_cast<long long>(B) * H * io.Tmax * hd;  // elements per layer
   const int emax_all = max_experts(m);  // router outputs: one [S * Emax] block per transformer layer, rows packed by E_l
 

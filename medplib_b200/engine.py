@@ -154,7 +154,7 @@ class LlamaEngine:
         return KVCache(c["num_layers"], B, c["num_heads"], Tmax, self.head_dim, self.device)
 
     def forward(self, x, cache, training=False, kv_mask=None, want_hidden_states=False, moe_noise=None,
-                want_router=False, pos_dev=None, tk_dev=None):
+                want_router=False, pos_dev=None, tk_dev=None, rope_pos=None):
         """x bf16 [B,T,D] inputs_embeds (clobbered: holds the last layer's output afterwards). Appends to cache.
 
         Returns dict(last_hidden_state [B,T,D], hidden_states (tuple or None), gate_logits [L,S,E] f32, l_aux [L],
@@ -190,6 +190,9 @@ class LlamaEngine:
             io.kv_mask, io.kv_mask_stride = kv_mask.data_ptr(), kv_mask.stride(0)
         if pos_dev is not None:
             io.pos_dev, io.tk_dev = pos_dev.data_ptr(), tk_dev.data_ptr()
+        if rope_pos is not None:  # continuous batching: per-sequence RoPE positions, shared cache column (decode step)
+            assert T == 1 and rope_pos.dtype == torch.int32 and rope_pos.numel() == B and rope_pos.is_cuda
+            io.rope_pos = rope_pos.data_ptr()
         if moe_noise is not None:
             noise = [n.contiguous() if n is not None else None for n in moe_noise]
             io.moe_noise = (ctypes.c_void_p * L)(*[_p(n) for n in noise])

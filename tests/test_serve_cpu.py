@@ -136,3 +136,97 @@ def test_sentinel_tokenisation_matches_the_reference():
         assert got == case["ids"], case["prompt"]
     t = serve.tokenize_with_sentinels(gi.TOKENIZE_PROMPTS[0], gi.StubTokenizer(), return_tensors="pt")
     assert t.dtype == torch.long and t.tolist() == gold[0]["ids"]
+
+
+# ----------------------------------------------------------------------------------------------- continuous batching
+class ScriptBackend:
+    """Stand-in for the device side of serve.ContinuousBatcher: every request follows its own token script; hidden rows
+    carry the sequence's own position; the cache layout (slot, start column, rope position) is recorded and checked."""
+
+    def __init__(self, scripts, B):
+        self.scripts, self.B = scripts, B
+        self.slot_of, self.installs, self.decodes, self.released = {}, [], [], []
+        self.step_of = {}
+
+    def _logits(self, rid):
+        lg = torch.zeros(V)
+        lg[self.scripts[rid][self.step_of[rid]]] = 5.0
+        self.step_of[rid] += 1
+        return lg
+
+    def prefill(self, req):
+        ids = req["input_ids"]
+        n = ids.shape[1] + int((ids == serve.IMAGE_TOKEN_INDEX).sum()) * (N_PATCH - 1)
+        self.step_of[req["id"]] = 0
+        hidden = torch.arange(n, dtype=torch.float32)[:, None].expand(n, D)
+        return self._logits(req["id"]), hidden, SimpleNamespace(rid=req["id"], len=n), n
+
+    def install(self, slot, kv, start, n):
+        assert kv.len == n and start >= 0
+        self.slot_of[slot] = dict(rid=kv.rid, start=start, n=n, fed=0)
+        self.installs.append((kv.rid, slot, start, n))
+
+    def release(self, slot):
+        self.released.append(self.slot_of.pop(slot)["rid"])
+
+    def decode(self, tokens, col, rope_pos):
+        assert len(tokens) == len(rope_pos) == self.B
+        self.decodes.append((col, dict((s["rid"], rope_pos[b]) for b, s in self.slot_of.items())))
+        logits, hidden = torch.zeros(self.B, V), torch.zeros(self.B, D)
+        for b, s in self.slot_of.items():
+            # the token fed back is the request's previous script entry, at ITS OWN position, written at the shared column
+            assert tokens[b] == self.scripts[s["rid"]][self.step_of[s["rid"]] - 1]
+            assert rope_pos[b] == s["n"] + s["fed"] and col >= s["start"] + s["n"] + s["fed"]
+            s["fed"] += 1
+            logits[b] = self._logits(s["rid"])
+            hidden[b] = float(rope_pos[b])
+        return logits, hidden
+
+
+def test_continuous_batching_host_logic():
+    scripts = {0: [33, 34, 35, 36, EOS], 1: [40, SEG, 41, EOS], 2: [44, EOS], 3: [45, 46, 47, 48, 49, 50 - 1, EOS]}
+    m = Model([])
+    be = ScriptBackend(scripts, B=2)
+    cb = serve.ContinuousBatcher(m, Tok(), max_batch=2, max_len=64, temperature=0.0, backend=be)
+    short = torch.tensor([[1, 40, 41]])
+    cb.submit(short, max_new_tokens=10, request_id=0)                                   # 3 rows, no image
+    out = cb.step()                                                                     # admits 0, decodes token 2 of 0
+    assert [r[0] for r in out] == [0, 0] and cb.col == 4
+    cb.submit(prompt(), images_clip=torch.zeros(1, 3, 4, 4), images_sam=torch.zeros(1, 3, 4, 4), resize=(3, 4),
+              original_size=(5, 6), max_new_tokens=10, request_id=1)                     # 8 rows: the column jumps 4 -> 8
+    cb.submit(short, max_new_tokens=10, request_id=2)                                   # waits for a free slot
+    cb.submit(short, max_new_tokens=10, request_id=3)
+    final = {}
+    while not cb.idle():
+        for rid, rec, done in cb.step():
+            if done:
+                final[rid] = rec
+    assert {k: v["text"] for k, v in final.items()} == {0: "ABCD", 1: "HI", 2: "L", 3: "MNOPQQ"}
+    # request 1 joined mid-flight in slot 1 behind the column; its prompt is longer than the column was
+    assert be.installs[0] == (0, 0, 0, 3) and be.installs[1] == (1, 1, 0, 8)
+    assert be.installs[2][0] == 2 and be.installs[3][0] == 3 and len(be.installs) == 4
+    # requests 2 and 3 re-used freed slots while another request was still decoding (no drain between them)
+    rids_per_step = [set(d[1]) for d in be.decodes]
+    assert {0, 1} in rids_per_step and any(2 in s and len(s) == 2 for s in rids_per_step)
+    assert any(3 in s and len(s) == 2 for s in rids_per_step)
+    # mask tail of request 1: the row in front of its first <SEG> = the last prompt row + 1 generated token = position 8
+    assert m.tail_rows == [[8.0]]
+    assert final[1]["mask"] == [[0, 0], [1, 2], [4, 5]] and (final[1]["height"], final[1]["width"]) == ("5", "6")
+    assert final[0]["mask"] == [] and sorted(be.released + [2]) and set(be.released) | {2} >= {0, 1, 3}
+
+
+def test_continuous_batching_restarts_the_column_and_refuses_what_cannot_fit():
+    scripts = {0: [33, EOS], 1: [34, EOS]}
+    be = ScriptBackend(scripts, B=1)
+    cb = serve.ContinuousBatcher(Model([]), Tok(), max_batch=1, max_len=16, temperature=0.0, backend=be)
+    cb.submit(torch.tensor([[1, 40, 41]]), max_new_tokens=4, request_id=0)
+    cb.submit(torch.tensor([[1, 40, 41, 42]]), max_new_tokens=4, request_id=1)
+    final = cb.run()
+    assert final[0]["text"] == "A" and final[1]["text"] == "B"
+    assert be.installs == [(0, 0, 0, 3), (1, 0, 0, 4)]  # the second request started a fresh column
+    cb.submit(torch.tensor([[1] * 14]), max_new_tokens=8, request_id=2)
+    try:
+        cb.run()
+        assert False, "a request longer than max_len must be refused"
+    except ValueError:
+        pass
