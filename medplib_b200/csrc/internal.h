@@ -58,5 +58,6 @@ bool attention_tc_supported(const mpl_attn_args& a);
 int attention_tc(const mpl_attn_args& a, cudaStream_t stream);
 int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D, cudaStream_t stream);
 int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
-                long long ldo, int S, int k, int D, cudaStream_t stream);
+                long long ldo, int S, int k, int D, cudaStream_t stream, const void* ln_w = nullptr, float eps = 0.0f,
+                void* h_out = nullptr, long long ldh = 0);  // ln_w: + RMSNorm of the combined row into h_out
 }  // namespace mpl

@@ -136,6 +136,8 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
   const long long cache_layer = static_cast<long long>(B) * H * io.Tmax * hd;  // elements per layer
   const int emax_all = max_experts(m);  // router outputs: one [S * Emax] block per transformer layer, rows packed by E_l
 
+  bool h_ready = false;  // w.h already holds RMSNorm(x) with this layer's input_ln (fused into the previous MoE combine)
+  bool out_norm_done = false;
   for (int l = 0; l < m.n_layers; ++l) {
     const mpl_llama_layer& L = m.layers[l];
     if (io.hidden_states != nullptr && io.hidden_states[l] != nullptr)
@@ -144,7 +146,8 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
         return MPL_ERR_CUDA;
     // ---- attention block (decode: the RMSNorm runs as the prologue of the streaming q,k,v GEMM)
     const bool small = S <= 16;
-    if (!small) MPL_TRY(mpl_rmsnorm(io.x, D, L.input_ln, w.h, D, S, D, m.rms_eps, st_));
+    if (!small && !h_ready) MPL_TRY(mpl_rmsnorm(io.x, D, L.input_ln, w.h, D, S, D, m.rms_eps, st_));
+    h_ready = false;
     {
       mpl_gemm_args g = gemm_base(small ? io.x : w.h, D, S, D, D);
       if (small) {
@@ -318,9 +321,29 @@ int llama_forward(const mpl_llama_model& m, const mpl_llama_io& io, cudaStream_t
       MPL_TRY(mpl_grouped_gemm_bf16(&d, st_));
     }
     if (fused_combine) continue;
-    MPL_TRY(moe_combine(w.y, w.slot, w.gate, io.x, D, io.x, D, S, m.top_k, D, st));
+    // combine (+ residual) and, while the row is in registers, the RMSNorm its next consumer needs: the next layer's
+    // input_layernorm (into w.h) or the final norm (into out_norm)
+    const void* next_ln = nullptr;
+    void* next_h = nullptr;
+    if (!small && D <= 4096) {
+      if (l + 1 < m.n_layers) {
+        next_ln = m.layers[l + 1].input_ln;
+        next_h = w.h;
+      } else if (io.out_norm != nullptr) {
+        next_ln = m.final_norm;
+        next_h = io.out_norm;
+      }
+    }
+    MPL_TRY(moe_combine(w.y, w.slot, w.gate, io.x, D, io.x, D, S, m.top_k, D, st, next_ln, m.rms_eps, next_h, D));
+    if (next_ln != nullptr) {
+      if (l + 1 < m.n_layers)
+        h_ready = true;
+      else
+        out_norm_done = true;
+    }
   }
-  if (io.out_norm != nullptr) MPL_TRY(mpl_rmsnorm(io.x, D, m.final_norm, io.out_norm, D, S, D, m.rms_eps, st_));
+  if (io.out_norm != nullptr && !out_norm_done)
+    MPL_TRY(mpl_rmsnorm(io.x, D, m.final_norm, io.out_norm, D, S, D, m.rms_eps, st_));
   return MPL_OK;
 }
 

@@ -447,14 +447,18 @@ __global__ void __launch_bounds__(128) moe_dispatch_kernel(const __nv_bfloat16* 
   for (int c = threadIdx.x; c < D / 8; c += 128) out[c] = src[c];
 }
 
+// ln_w != NULL: the row just written is also normalised for its next consumer -- h_out[s] = ln_w * bf16(out[s] * rstd),
+// LlamaRMSNorm of the NEXT decoder layer's input (or the final norm) -- while it is still in registers (D <= 4096).
 __global__ void __launch_bounds__(128) moe_combine_kernel(const __nv_bfloat16* __restrict__ y,
                                                           const int* __restrict__ slot,
                                                           const float* __restrict__ gate,
                                                           const __nv_bfloat16* __restrict__ residual, long long ldr,
                                                           __nv_bfloat16* __restrict__ out, long long ldo, int k,
-                                                          int D) {
+                                                          int D, const __nv_bfloat16* __restrict__ ln_w, float eps,
+                                                          __nv_bfloat16* __restrict__ h_out, long long ldh) {
   griddep_wait();  // programmatic dependent launch: the previous kernel's outputs are read from here on
   griddep_launch_dependents();
+  __shared__ float red[4];
   const int s = blockIdx.x;
   int sl[2] = {-1, -1};
   float g[2] = {0.0f, 0.0f};
@@ -464,7 +468,12 @@ __global__ void __launch_bounds__(128) moe_combine_kernel(const __nv_bfloat16* _
   }
   const __nv_bfloat16* rr = residual ? residual + static_cast<long long>(s) * ldr : nullptr;
   __nv_bfloat16* orow = out + static_cast<long long>(s) * ldo;
-  for (int c = threadIdx.x * 8; c < D; c += 128 * 8) {
+  uint4 kept[4];  // the row's outputs (bf16) for the fused RMSNorm: 4 x 8 columns per thread = D <= 4096
+  float ss = 0.0f;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int c = (it * 128 + threadIdx.x) * 8;
+    if (c >= D) continue;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
@@ -495,9 +504,40 @@ __global__ void __launch_bounds__(128) moe_combine_kernel(const __nv_bfloat16* _
     o.z = pack_bf16(acc[4], acc[5]);
     o.w = pack_bf16(acc[6], acc[7]);
     *reinterpret_cast<uint4*>(orow + c) = o;
+    kept[it] = o;
+    if (ln_w != nullptr) {
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(hp[i]);
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  if (ln_w == nullptr) return;  // (uniform over the CTA)
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  const float tot = ((red[0] + red[1]) + red[2]) + red[3];
+  const float rstd = rsqrtf(tot / static_cast<float>(D) + eps);
+  __nv_bfloat16* hrow = h_out + static_cast<long long>(s) * ldh;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int c = (it * 128 + threadIdx.x) * 8;
+    if (c >= D) continue;
+    const uint4 wraw = *reinterpret_cast<const uint4*>(ln_w + c);
+    const __nv_bfloat162* wh = reinterpret_cast<const __nv_bfloat162*>(&wraw);
+    const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&kept[it]);
+    uint4 o;
+    uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 wf = __bfloat1622float2(wh[e]), xf = __bfloat1622float2(xh[e]);
+      op[e] = pack_bf16(wf.x * bf16_round(xf.x * rstd), wf.y * bf16_round(xf.y * rstd));
+    }
+    *reinterpret_cast<uint4*>(hrow + c) = o;
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------ small-S fused path
 // Decode-time MoE front end for S <= 64 tokens in ONE CTA: [RMSNorm] -> router -> top-k -> slots -> dispatch.
@@ -773,14 +813,17 @@ int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int
   return mpl::launch_status();
 }
 
+
 int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
-                long long ldo, int S, int k, int D, cudaStream_t stream) {
+                long long ldo, int S, int k, int D, cudaStream_t stream, const void* ln_w, float eps, void* h_out,
+                long long ldh) {
   if (S <= 0) return MPL_OK;
   if (y == nullptr || slot == nullptr || gate == nullptr || out == nullptr) return MPL_ERR_ARG;
-  if ((D % 8) != 0 || (ldr % 8) != 0 || (ldo % 8) != 0 || k < 1 || k > 2) return MPL_ERR_ALIGN;
+  if ((D % 8) != 0 || (ldr % 8) != 0 || (ldo % 8) != 0 || k < 1 || k > 2 || D > 4096) return MPL_ERR_ALIGN;
+  if (ln_w != nullptr && (h_out == nullptr || (ldh % 8) != 0)) return MPL_ERR_ARG;
   launch_pdl(moe_combine_kernel, dim3(S), dim3(128), 0, stream, static_cast<const __nv_bfloat16*>(y), slot, gate,
-                                            static_cast<const __nv_bfloat16*>(residual), ldr,
-                                            static_cast<__nv_bfloat16*>(out), ldo, k, D);
+             static_cast<const __nv_bfloat16*>(residual), ldr, static_cast<__nv_bfloat16*>(out), ldo, k, D,
+             static_cast<const __nv_bfloat16*>(ln_w), eps, static_cast<__nv_bfloat16*>(h_out), ldh);
   return mpl::launch_status();
 }
 
