@@ -10,7 +10,7 @@ T = int(sys.argv[1]) if len(sys.argv) > 1 else 615
 dev = "cuda"
 torch.manual_seed(0)
 D, F = 4096, 11008
-WIDTHS = [0] if (len(sys.argv) > 2 and sys.argv[2] == "ncu") else [0, 128, 144, 160, 176, 192, 208, 224, 240, 256, 1128, 1160, 1176, 1192, 1224, 1240, 1256]
+WIDTHS = [int(v) for v in os.environ["MPL_TILES"].split(",")] if os.environ.get("MPL_TILES") else [0] if (len(sys.argv) > 2 and sys.argv[2] == "ncu") else [0, 128, 144, 160, 176, 192, 208, 224, 240, 256, 1128, 1160, 1176, 1192, 1224, 1240, 1256]
 
 
 def timeit(fn, n_rot, iters=24):
