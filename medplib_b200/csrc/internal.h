@@ -56,6 +56,9 @@ int attn_bwd_fa2(const mpl_attn_bwd_args& a, cudaStream_t stream);
 // attention_tc.cu: tcgen05 + TMA flash-attention forward (head_dim 64 / 128, Tq >= 32, no relative-position bias)
 bool attention_tc_supported(const mpl_attn_args& a);
 int attention_tc(const mpl_attn_args& a, cudaStream_t stream);
+// tcgen05 + TMA flash-attention backward (head_dim 128); delta precomputed, dq_f32 zeroed by the caller
+bool attention_bwd_tc_supported(const mpl_attn_bwd_args& a);
+int attention_bwd_tc(const mpl_attn_bwd_args& a, cudaStream_t stream);
 int moe_dispatch(const void* h, long long ldh, const int* slot, void* xperm, int S, int k, int D, cudaStream_t stream);
 int moe_combine(const void* y, const int* slot, const float* gate, const void* residual, long long ldr, void* out,
                 long long ldo, int S, int k, int D, cudaStream_t stream, const void* ln_w = nullptr, float eps = 0.0f,

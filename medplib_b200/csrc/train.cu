@@ -1482,6 +1482,7 @@ extern "C" int mpl_attention_bwd(const mpl_attn_bwd_args* a, void* stream) {
       static_cast<const bf16_t*>(a->o), static_cast<const bf16_t*>(a->d_o), a->o_stride[0], a->o_stride[1],
       a->o_stride[2], a->delta, a->B, a->H, a->T, a->head_dim);
   if (launch_status() != MPL_OK) return MPL_ERR_CUDA;
+  if (attention_bwd_tc_supported(*a)) return attention_bwd_tc(*a, ST(stream));  // tcgen05 kernel (attention_tc.cu)
   if (a->head_dim == 128 && a->dk_stride[1] % 2 == 0 && a->dv_stride[1] % 2 == 0 && getenv("MPL_ATTN_BWD_WMMA") == nullptr)
     return attn_bwd_fa2(*a, ST(stream));  // mma.sync FA2-style kernel (attention.cu); the wmma kernel below: d = 64
   AttnBwdParams p;
