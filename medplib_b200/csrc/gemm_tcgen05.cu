@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -257,7 +258,7 @@ template <int BN>
 struct GemmCfg {
   // BN: any multiple of 16 in [128, 256] (the UMMA N of a 128-row tile); the launcher picks the width whose tile count
   // fills the 148 SMs best (M = 615 prefill: 145 tiles of 144 columns for o_proj instead of 110 of 192)
-  static_assert(BN % 16 == 0 && BN >= 128 && BN <= 256, "tile width");
+  static_assert(BN % 16 == 0 && BN >= 64 && BN <= 256, "tile width");
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGES_FIT = (232448 - 1024 - 256 - 512 /*static smem*/) / (A_BYTES + B_BYTES);
@@ -697,7 +698,7 @@ int num_sms() {
 
 // Tile widths compiled in (UMMA N: any multiple of 16; these cover the wave counts that matter). One-CTA tiles are
 // 128 x W, CTA-pair tiles 256 x W.
-#define MPL_TILE_WIDTHS(X) X(128) X(144) X(160) X(176) X(192) X(208) X(224) X(240) X(256)
+#define MPL_TILE_WIDTHS(X) X(64) X(96) X(128) X(144) X(160) X(176) X(192) X(208) X(224) X(240) X(256)
 #define MPL_PAIR_WIDTHS(X) X(128) X(160) X(176) X(192) X(224) X(240) X(256)
 constexpr int PAIR_FLAG = 1000;  // tile_n = PAIR_FLAG + W selects the CTA-pair kernel with width W
 
@@ -719,7 +720,7 @@ static int pair_min_rows() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MPL_GEMM_PAIR_MIN_ROWS");
-    v = e != nullptr ? atoi(e) : 1024;
+    v = e != nullptr ? atoi(e) : 640;  // (measured: 650 rows per expert at T = 1299 already favour pairs, 615 do not)
   }
   return v;
 }
@@ -768,8 +769,14 @@ static int pick_tile_n(long long rows, int row_sets, int N, int dual) {
 template <int BN, bool PAIR>
 static int launch_any(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const CUtensorMap& tmB2,
                       const GemmDevParams& p, const GroupMaps& gm, long long tiles, cudaStream_t stream) {
-  constexpr int smem = PAIR ? PairCfg<BN>::SMEM_BYTES : GemmCfg<BN>::SMEM_BYTES;
-  auto kernel = PAIR ? gemm_bf16_tcgen05_pair_kernel<BN> : gemm_bf16_tcgen05_kernel<BN>;
+  using Cfg = std::conditional_t<PAIR, PairCfg<BN>, GemmCfg<BN>>;  // (only the selected kernel is instantiated)
+  constexpr int smem = Cfg::SMEM_BYTES;
+  auto kernel = [] {
+    if constexpr (PAIR)
+      return &gemm_bf16_tcgen05_pair_kernel<BN>;
+    else
+      return &gemm_bf16_tcgen05_kernel<BN>;
+  }();
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MPL_ERR_CUDA;

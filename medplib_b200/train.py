@@ -550,6 +550,10 @@ class _StackFn(torch.autograd.Function):
             dh = torch.zeros((ctx.saved["B"] * ctx.saved["T"], D), dtype=bf16, device=tr.anchor.device)
         else:
             dh = dhidden.to(bf16).reshape(-1, D).contiguous()
+        if tr.reducer is not None and tr.arena.of(tr.lm_head_weight) is not None:
+            # every consumer of `hidden` (CE head, mask head) has finished its backward by the time this node runs: the
+            # arena prefix up to and including lm_head is final whatever order autograd ran those branches in
+            tr.reducer.ready(tr.arena.end_of(tr.lm_head_weight))
         dx0 = tr.stack.backward(ctx.saved, dh, aux_scale=aux)
         g_emb = tr.arena.of(tr.embed_weight)
         if g_emb is not None and ctx.splice_idx is not None:
@@ -746,8 +750,9 @@ class _HeadCEFn(torch.autograd.Function):
             else:  # gradient accumulation: the GEMM overwrites, so go through a temporary and add
                 tmp = ops.linear(dlT, hT, out_dtype=f32, force="tc")
                 T.col_sum(tmp.view(1, -1), gW.view(-1))
-            if tr.reducer is not None:
-                tr.reducer.ready(tr.arena.end_of(W))
+            # (no reducer.ready() here: the regions in front of lm_head in the arena -- mask decoder, text_hidden_fcs --
+            # are written by other tape nodes whose order relative to this one autograd does not promise; the stack's
+            # backward, which depends on every branch, releases them)
         ctx.logits = ctx.h2 = None
         return dh.view(ctx.shape), None, None
 

@@ -38,6 +38,9 @@ from parity import close as _close  # noqa: E402  (logs the measured error, asse
     (700, 4096, 11008, {"tile_n": 1256, "res": True, "row_scale": True, "m_dev": 300}),
     (300, 1001, 520, {"tile_n": 1160, "f32": True}), (330, 1000, 512, {"dual": True, "tile_n": 1192}),
     (5112, 4096, 4096, {"tile_n": 1256}),
+    # narrow tiles for small-N layers (CLIP fc2 / out_proj at M = 577: 40 tiles of 128 columns leave 108 SMs idle)
+    (577, 1024, 4096, {"tile_n": 64, "bias": True, "res": True}), (577, 1024, 1024, {"tile_n": 96, "nb": 3, "bias": True}),
+    (577, 1024, 4096, {"bias": True, "res": True}),
 ])
 def test_gemm_tcgen05(dev, M, N, K, kw):
     from medplib_b200 import ops
