@@ -234,8 +234,8 @@ def run_ours(args, rank, world, dev):
         "roofline": {"bound": "hbm", "achieved": dk_ach, "peak": pk["hbm"], "unit": "GB/s",
                      "frac": (dk_ach / pk["hbm"]) if dk_ach else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, ncu --set full capture of this kernel
-                     # at B = 1, context 615 (profiles/r02_ncu_decode_kernel.md): 13.4 GB read + 0.27 GB written
-                     "traffic": None if args.small else 13.67e9, "traffic_source": "profiles/r02_ncu_decode_kernel.md",
+                     # at B = 1, context 615 (profiles/r02_ncu_decode_kernel.md): 13.42 GB read + 0.10 GB written
+                     "traffic": None if args.small else 13.52e9, "traffic_source": "profiles/r02_ncu_decode_kernel.md",
                      "kernel": "llama_decode_kernel (one persistent cooperative launch per generated token: all 32 "
                                "layers; algorithmic bytes = one expert's weights + attention weights + KV cache, once)",
                      "algorithmic_bytes_per_launch": dk_bytes, "kernel_ms_per_launch": dk_ms,
@@ -244,10 +244,11 @@ def run_ours(args, rank, world, dev):
                      "peak_source": pk["src"] + " copy bandwidth"},
         "roofline_gemm": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s",
                           "frac": (ach / pk["tf_sus"]) if ach else None,
-                          "traffic": None if args.small else 111.9e6, "traffic_source": "profiles/r01_ncu_gemm_prefill.md "
-                          "(mean DRAM bytes per launch of the 7 LLaMA-layer launches)",
-                          "kernel": "gemm_bf16_tcgen05_kernel (all launches of a step: algorithmic 2MNK / summed "
-                                    "CUDA-event durations; per-expert launches that run concurrently are one interval)",
+                          "traffic": None if args.small else 186.8e6, "traffic_source": "profiles/r02_gemm_tile_widths.md "
+                          "(mean DRAM bytes per launch of the 4 LLaMA-layer launches: o_proj, q,k,v, grouped gate|up, "
+                          "grouped down)",
+                          "kernel": "gemm_bf16_tcgen05_kernel / gemm_bf16_tcgen05_pair_kernel (all launches of a step: "
+                                    "algorithmic 2MNK / summed CUDA-event durations)",
                           "kernel_ms_per_step": gemm_ms, "kernel_launches_per_step": cnt.value / psteps,
                           "share_of_step": gemm_ms / step_ms if step_ms > 0 else None,
                           "peak_source": pk["src"] + " sustained bf16"},

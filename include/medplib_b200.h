@@ -50,7 +50,7 @@ long long mpl_launch_count(void);
  * (model/medplib/model/medplib_arch.py:73,131), text_hidden_fcs (model/MedPLIB.py:153-164), SAM-Med2D linears
  * and im2col'ed convs (model/segment_anything_med2d/modeling/image_encoder.py).
  * Epilogue order (each step rounds to bf16 first when the output is bf16, like the reference's eager ops):
- *   acc (+ bias) -> act -> (* row_scale[m]) -> (+ residual[m,n]) -> store
+ *   acc (+ bias) -> act -> (* row_scale[m]) -> (+ LoRA terms) -> (+ residual[m,n]) -> store
  * nb in 1..3 weight matrices of identical shape share A in ONE launch (q/k/v projections): output i goes to C[i]
  *   with bias[i]; this fills the 148 SMs where a single N=4096 projection leaves 40% of them idle.
  * B2 != NULL (nb == 1) selects the fused LlamaMLP front half: out[m,n] = silu(A·B[0][n]^T) * (A·B2[n]^T).
@@ -76,6 +76,17 @@ typedef struct {
   int tile_n;    /* 0 = auto, else a multiple of 16 in [128, 256] (144, 160, ... 256 are compiled in) */
   const void* ln_weight; /* streaming (M <= 16) path only: fused LlamaRMSNorm prologue on A, bf16 [K] or NULL */
   float ln_eps;
+  /* Tensor-core path only, bf16 output: up to two fused rank-r LoRA up-projections (peft Linear.forward / its dgrad,
+   * train_ds_medplib.py:294-302), applied after the activation and before the residual, in peft's bf16 rounding:
+   *   C[lora_mat[t]][m,n] = bf16(C + bf16(lora_scale[t] * bf16(sum_j bf16(u_t[m,j]) * b_t[n,j])))   for t = 0, 1 in order.
+   * u_t: [M, lora_r] row-major (bf16, or f32 when lora_u_f32[t]); b_t: bf16 [N, lora_r] row-major (lora_B.weight; for
+   * the dgrad the transposed lora_A); lora_r in {0 (off), 8}; unused terms have lora_u[t] == NULL. */
+  const void* lora_u[2];
+  const void* lora_b[2];
+  float lora_scale[2];
+  int lora_u_f32[2];
+  int lora_mat[2];
+  int lora_r;
 } mpl_gemm_args;
 int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream);
 /* In-situ timing of the tcgen05 GEMM launches (bench.py roofline): enable, run, then read the summed CUDA-event

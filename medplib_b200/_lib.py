@@ -29,6 +29,8 @@ class GemmArgs(ctypes.Structure):
         ("M", c_int), ("N", c_int), ("K", c_int),
         ("nb", c_int), ("act", c_int), ("out_dtype", c_int), ("tile_n", c_int),
         ("ln_weight", c_void_p), ("ln_eps", c_float),
+        ("lora_u", c_void_p * 2), ("lora_b", c_void_p * 2), ("lora_scale", c_float * 2), ("lora_u_f32", c_int * 2),
+        ("lora_mat", c_int * 2), ("lora_r", c_int),
     ]
 
 

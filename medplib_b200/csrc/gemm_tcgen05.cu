@@ -32,6 +32,7 @@ namespace mpl {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
+constexpr int LORA_STAGE_BYTES = 2 * 256 * 16;  // staged b rows of up to two rank-8 LoRA terms (launches that carry them)
 
 struct GemmDevParams {
   int M, N, K;
@@ -51,6 +52,13 @@ struct GemmDevParams {
   int groups;
   long long a_group_rows;
   long long c_group_stride;  // elements
+  // fused LoRA up-projections (see mpl_gemm_args): term t adds to output matrix lora_mat[t]
+  const void* lora_u[2];
+  const __nv_bfloat16* lora_b[2];
+  float lora_scale[2];
+  int lora_u_f32[2];
+  int lora_mat[2];
+  int lora_r;
 };
 
 struct GroupMaps {
@@ -137,8 +145,49 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // t_row = TMEM address of this thread's lane at the first column of the accumulator.
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const GemmDevParams& p, const __nv_bfloat16* bias, void* Cout, int row, int M,
-                                              int n0, int out_bn, uint32_t t_row, bool vec_ok, bool res_vec_ok) {
+                                              int n0, int out_bn, uint32_t t_row, bool vec_ok, bool res_vec_ok,
+                                              int which, uint8_t* s_lora) {
   const bool row_ok = row < M;
+  // fused LoRA up-projections (rank 8): this row's coefficients (rounded to bf16 like the MMA operand of the unfused
+  // kernel) once per tile; the tile's rows of b ([out_bn][8] bf16 = 16 B per column, per term) are staged in shared
+  // memory by the four epilogue warps together -- read straight from global memory they cost one L2 round trip per
+  // 8 columns on the epilogue's critical path
+  float lu[2][8];
+  bool lon[2] = {false, false};
+  if (p.lora_r > 0) {
+    const int et = static_cast<int>(threadIdx.x) - 64;  // 0..127 over the epilogue warps
+    asm volatile("bar.sync 1, 128;" ::: "memory");       // the previous tile's reads of the staging area are done
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const bool term = p.lora_u[t] != nullptr && p.lora_mat[t] == which;
+      lon[t] = term && row_ok;
+      if (term) {
+        for (int cidx = et; cidx < out_bn; cidx += 128) {
+          const int col = min(n0 + cidx, p.N - 1);
+          *reinterpret_cast<uint4*>(s_lora + (t * 256 + cidx) * 16) =
+              *reinterpret_cast<const uint4*>(p.lora_b[t] + static_cast<long long>(col) * 8);
+        }
+      }
+      if (lon[t]) {
+        if (p.lora_u_f32[t]) {
+          const float4* up = reinterpret_cast<const float4*>(static_cast<const float*>(p.lora_u[t]) + static_cast<long long>(row) * 8);
+          const float4 a0 = up[0], a1 = up[1];
+          lu[t][0] = bf16_round(a0.x), lu[t][1] = bf16_round(a0.y), lu[t][2] = bf16_round(a0.z), lu[t][3] = bf16_round(a0.w);
+          lu[t][4] = bf16_round(a1.x), lu[t][5] = bf16_round(a1.y), lu[t][6] = bf16_round(a1.z), lu[t][7] = bf16_round(a1.w);
+        } else {
+          const uint4 raw = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.lora_u[t]) + static_cast<long long>(row) * 8);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(h2[e]);
+            lu[t][2 * e] = f.x;
+            lu[t][2 * e + 1] = f.y;
+          }
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // staging complete
+  }
   const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[row] : 1.0f;
   const bool f32 = p.out_f32 != 0;
   const int nlim = min(p.N, n0 + out_bn);  // columns of this tile (the last 32-column chunk may be partial)
@@ -179,6 +228,27 @@ __device__ __forceinline__ void epilogue_rows(const GemmDevParams& p, const __nv
     if (p.row_scale != nullptr) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = (f32 ? v[j] : bf16_round(v[j])) * rscale;
+    }
+    if (p.lora_r > 0 && (lon[0] || lon[1])) {
+      // v = bf16(bf16(v) + bf16(scale * bf16(sum_j u[j] b[n][j]))), b from the staged rows (broadcast reads)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (!lon[t]) continue;
+        const float sc = p.lora_scale[t];
+        const uint8_t* sb = s_lora + (t * 256 + c * 32) * 16;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const uint4 bw = *reinterpret_cast<const uint4*>(sb + j * 16);
+          const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&bw);
+          float acc = 0.0f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(bh[e]);
+            acc += lu[t][2 * e] * f.x + lu[t][2 * e + 1] * f.y;
+          }
+          v[j] = bf16_round(bf16_round(v[j]) + bf16_round(sc * bf16_round(acc)));
+        }
+      }
     }
     if (p.residual != nullptr) {
       if (!f32) {
@@ -412,7 +482,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       epilogue_rows<BN>(p, bias, Cout, m0 + quad * 32 + lane, M, n0, out_bn,
-                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE, vec_ok, res_vec_ok);
+                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE, vec_ok, res_vec_ok,
+                        which, reinterpret_cast<uint8_t*>(tmem_slot) + 64);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -446,7 +517,7 @@ struct PairCfg {
   static_assert(BN % 16 == 0 && BN >= 128 && BN <= 256, "pair tile width");
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // per CTA
-  static constexpr int STAGES_FIT = (232448 - 1024 - 256 - 512) / (A_BYTES + B_BYTES);
+  static constexpr int STAGES_FIT = (232448 - 1024 - 256 - 512 - LORA_STAGE_BYTES) / (A_BYTES + B_BYTES);
   static constexpr int STAGES = STAGES_FIT > 7 ? 7 : STAGES_FIT;
   static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -597,7 +668,8 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       epilogue_rows<BN>(p, bias, Cout, m0 + quad * 32 + lane, M, n0, out_bn,
-                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE, vec_ok, res_vec_ok);
+                        tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_STRIDE, vec_ok, res_vec_ok,
+                        which, reinterpret_cast<uint8_t*>(tmem_slot) + 64);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
@@ -724,7 +796,7 @@ static int pair_min_rows() {
   }
   return v;
 }
-static int pick_tile_n(long long rows, int row_sets, int N, int dual) {
+static int pick_tile_n(long long rows, int row_sets, int N, int dual, bool lora = false) {
   const int sms = num_sms();
   static const int widths[] = {
 #define MPL_BN_LIST(W) W,
@@ -737,6 +809,7 @@ static int pick_tile_n(long long rows, int row_sets, int N, int dual) {
   double best_cost = 1e300;
   for (int i = static_cast<int>(sizeof(widths) / sizeof(widths[0])) - 1; i >= 0; --i) {
     const int bn = widths[i];
+    if (lora && bn == 224) continue;  // 5 stages of 44 KB leave no room for the staged LoRA rows
     const int out_bn = dual ? bn / 2 : bn;
     const long long tiles = row_sets * ((rows + BM - 1) / BM) * ((N + out_bn - 1) / out_bn);
     const long long waves = (tiles + sms - 1) / sms;
@@ -777,18 +850,21 @@ static int launch_any(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     else
       return &gemm_bf16_tcgen05_kernel<BN>;
   }();
+  constexpr int smem_max = smem + LORA_STAGE_BYTES <= 232448 ? smem + LORA_STAGE_BYTES : smem;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return MPL_ERR_CUDA;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) return MPL_ERR_CUDA;
     attr_set = true;
   }
+  const int smem_launch = smem + (p.lora_r > 0 ? LORA_STAGE_BYTES : 0);
+  if (smem_launch > smem_max) return MPL_ERR_UNSUPPORTED;  // (one-CTA width 224: no room for the staged LoRA rows)
   const int units = PAIR ? num_sms() / 2 : num_sms();  // CTAs, or CTA pairs (one per TPC)
   int grid = static_cast<int>(tiles < units ? tiles : units);
   if (grid < 1) grid = 1;
   if (PAIR) grid *= 2;
   const bool prof = g_prof && !g_prof_suppress;
   if (prof) cudaEventRecord(prof_event(), stream);
-  launch_pdl(kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmB1, tmB2, p, gm);
+  launch_pdl(kernel, dim3(grid), dim3(GEMM_THREADS), smem_launch, stream, tmA, tmB, tmB1, tmB2, p, gm);
   if (prof) cudaEventRecord(prof_event(), stream);
   return mpl::launch_status();
 }
@@ -836,6 +912,19 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   p.act = a.act;
   p.out_f32 = a.out_dtype == MPL_DT_F32;
   p.dual = dual;
+  if (a.lora_r != 0) {
+    if (a.lora_r != 8 || dual || a.out_dtype == MPL_DT_F32) return MPL_ERR_UNSUPPORTED;
+    p.lora_r = a.lora_r;
+    for (int t = 0; t < 2; ++t) {
+      if (a.lora_u[t] != nullptr && (a.lora_b[t] == nullptr || (reinterpret_cast<uintptr_t>(a.lora_b[t]) & 15) != 0))
+        return MPL_ERR_ALIGN;
+      p.lora_u[t] = a.lora_u[t];
+      p.lora_b[t] = static_cast<const __nv_bfloat16*>(a.lora_b[t]);
+      p.lora_scale[t] = a.lora_scale[t];
+      p.lora_u_f32[t] = a.lora_u_f32[t];
+      p.lora_mat[t] = a.lora_mat[t];
+    }
+  }
   const int out_bn = dual ? BN / 2 : BN;
   const int bm = PAIR ? 2 * BM : BM;
   const long long tiles = static_cast<long long>((a.M + bm - 1) / bm) * ((a.N + out_bn - 1) / out_bn) * nb;
@@ -849,7 +938,7 @@ int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
   const int dual = a.B2 != nullptr;
   const int nb = a.nb < 1 ? 1 : a.nb;
   int bn = a.tile_n;
-  if (bn == 0) bn = pick_tile_n(a.M, nb, a.N, dual);
+  if (bn == 0) bn = pick_tile_n(a.M, nb, a.N, dual, a.lora_r != 0);
   switch (bn) {
 #define MPL_BN_CASE(W) \
   case W:              \

@@ -4,6 +4,7 @@ Every function here enqueues hand-written sm_100a kernels from ``libmedplib_b200
 stream. There is no eager / CPU fallback: a CPU tensor or a missing library raises :class:`MplError`.
 """
 import ctypes
+import os
 
 import torch
 
@@ -40,11 +41,13 @@ def _rows(x):
 
 
 def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scale=None, m_dev=None,
-           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5):
+           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5, lora=None):
     """y = epilogue(x @ weight.T); x [..., K] bf16, weight [N, K] bf16 (nn.Linear layout).
 
     weight may be a list/tuple of 1..3 same-shape matrices sharing x in one launch (returns a list of outputs).
     weight2 selects the fused SiLU(x W^T) * (x W2^T). force in {None, "tc", "skinny"}. See mpl_gemm_bf16.
+    lora: up to two fused rank-r up-projections [(u [M, r] bf16 / f32, b [N, r] bf16 contiguous, scale, matrix index)]:
+    out[i] = bf16(out[i] + bf16(scale * bf16(u b^T))) in the epilogue (tensor-core path, bf16 output).
     """
     lib = _lib.load()
     ws = list(weight) if isinstance(weight, (list, tuple)) else [weight]
@@ -95,8 +98,26 @@ def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scal
     if ln_weight is not None:  # fused LlamaRMSNorm prologue (streaming path, M <= 16)
         _req(ln_weight, bf16, "ln_weight")
         a.ln_weight, a.ln_eps = ln_weight.data_ptr(), ln_eps
+    unfused = []
+    if lora and (os.environ.get("MPL_LORA_FUSE", "1") == "0" or any(t[0].shape[-1] != 8 for t in lora)):
+        # (A/B switch, or a rank the epilogue does not take: the adapters as their own passes over the output)
+        unfused, lora = lora, None
+    if lora:
+        assert len(lora) <= 2 and weight2 is None and outs[0].dtype == bf16
+        keep = []
+        for t, (u, b, sc, mat) in enumerate(lora):
+            r = u.shape[-1]
+            assert u.is_contiguous() and b.is_contiguous() and u.shape == (M, r) and b.shape == (N, r) and b.dtype == bf16
+            assert r == 8 and u.dtype in (bf16, torch.float32)
+            a.lora_r = r
+            a.lora_u[t], a.lora_b[t] = u.data_ptr(), b.data_ptr()
+            a.lora_scale[t], a.lora_u_f32[t], a.lora_mat[t] = float(sc), int(u.dtype == torch.float32), int(mat)
+            keep.append((u, b))
     fn = {None: lib.mpl_linear_bf16, "tc": lib.mpl_gemm_bf16, "skinny": lib.mpl_skinny_gemm_bf16}[force]
     _lib.check(fn(ctypes.byref(a), _stream()), "mpl_linear_bf16")
+    for u, b, sc, mat in unfused:
+        from . import train_ops
+        train_ops.lora_up_add(outs[mat], u, b, sc)
     lead = x.shape[:-1]
     res = [o.reshape(*lead, N) if out is None else o for o in outs]
     return res if isinstance(weight, (list, tuple)) else res[0]

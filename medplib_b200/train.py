@@ -27,6 +27,8 @@ from .model import modules as M
 
 bf16 = torch.bfloat16
 f32 = torch.float32
+# LoRA up-projections in the epilogue of the base GEMM (mpl_gemm_args.lora_*) instead of a separate pass over its output
+LORA_FUSE = os.environ.get("MPL_LORA_FUSE", "1") != "0"
 LORA_EXCLUDE = ("visual_model", "vision_tower", "mm_projector")  # train_ds_medplib.py:272-281
 
 
@@ -308,9 +310,9 @@ class LlamaTrainStack:
             self.layers.append(L)
 
     # ------------------------------------------------------------------ helpers
-    def _lora_fwd(self, lo, x, y):
-        """y += s * (dropout(x) A^T) B^T in peft's bf16 rounding; returns what the backward needs: (a = dropout(x) A^T
-        (bf16 [M, r]), dropped input or None, keep mask or None)."""
+    def _lora_a(self, lo, x):
+        """a = dropout(x) A^T (bf16 [M, r]) in peft's rounding; returns what the backward needs: (a, dropped input or
+        None, keep mask or None)."""
         xd = mask = None
         if lo.p > 0.0 and self.training:
             # peft: lora_B(lora_A(lora_dropout(x))) — every adapted Linear owns its dropout, masks are per call
@@ -321,23 +323,48 @@ class LlamaTrainStack:
                 mask = (torch.rand(x.shape, device=x.device) >= lo.p).to(torch.uint8)
             xd = T.mask_scale(x if x.is_contiguous() else x.contiguous(), mask, 1.0 / (1.0 - lo.p))
         a = T.lora_down(xd if xd is not None else x, lo.A)
-        T.lora_up_add(y, a, lo.B, lo.s)
         return (a, xd, mask)
 
-    def _lora_bwd(self, lo, x, saved, dy, dx):
-        """Gradients of y = ... + s (dropout(x) A^T) B^T: dB, dA into the arena, dx += dropout'(du A)."""
+    def _lora_fwd(self, lo, x, y):
+        """y += s * (dropout(x) A^T) B^T as its own pass over y (the GEMM that produced y could not take the adapter in its
+        epilogue)."""
+        saved = self._lora_a(lo, x)
+        T.lora_up_add(y, saved[0], lo.B, lo.s)
+        return saved
+
+    @staticmethod
+    def _lora_term(lo, saved, mat=0):
+        """The adapter as a fused epilogue term of the base GEMM: (u, b [N, r], scale, output matrix)."""
+        return (saved[0], lo.B.detach(), lo.s, mat)
+
+    def _lora_bwd_pre(self, lo, x, saved, dy):
+        """Everything of the adapter's backward except dx: dB, dA into the arena. Returns the epilogue term of the base
+        dgrad GEMM, (du f32 [M, r], A^T [in, r], 1.0, 0), or None when lora_dropout is active (dx then needs the mask:
+        _lora_bwd_dx)."""
         a, xd, mask = saved
         if lo.gB is not None:
             T.rank_wgrad(dy, a, lo.gB, scale=lo.s)
         du = T.lora_down(dy, T.transpose(lo.B.detach()), scale=lo.s, out_f32=True)
         if lo.gA is not None:
             T.rank_wgrad(xd if xd is not None else x, du, lo.gA, transposed=True)
+        if mask is not None:
+            return None, du
+        return (du, T.transpose(lo.A.detach()), 1.0, 0), du
+
+    def _lora_bwd_dx(self, lo, saved, du, dx):
+        """dx += dropout'(du A) as its own pass (lora_dropout active, or no base GEMM to fuse into)."""
+        mask = saved[2]
         if mask is None:
             T.lora_up_add(dx, du, lo.A, 1.0, transposed=True)
         else:
             tmp = torch.zeros((dx.shape[0], dx.shape[1]), dtype=bf16, device=dx.device)
             T.lora_up_add(tmp, du, lo.A, 1.0, transposed=True)
             T.mask_scale(tmp, mask, 1.0 / (1.0 - lo.p), out=dx, accumulate=True)
+
+    def _lora_bwd(self, lo, x, saved, dy, dx):
+        """Gradients of y = ... + s (dropout(x) A^T) B^T: dB, dA into the arena, dx += dropout'(du A)."""
+        _, du = self._lora_bwd_pre(lo, x, saved, dy)
+        self._lora_bwd_dx(lo, saved, du, dx)
 
     def capacity(self, S, E):
         return ops.moe_capacity(S, E, self.cf, self.min_cap, self.top_k)
@@ -360,10 +387,16 @@ class LlamaTrainStack:
             n1 = ops.rmsnorm(x, L.ln1, eps)
             qkv = torch.empty((S, 3 * D), dtype=bf16, device=dev)
             views = [qkv[:, j * D:(j + 1) * D] for j in range(3)]
-            ops.linear(n1, [L.wq, L.wk, L.wv], out=views)
+            # adapters ride in the epilogue of the base GEMM (two terms per launch; a third one takes its own pass)
+            terms, later = [], []
             for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
                 if L.lo[nm] is not None:
-                    sv["a_" + nm] = self._lora_fwd(L.lo[nm], n1, views[j])
+                    sv["a_" + nm] = self._lora_a(L.lo[nm], n1)
+                    (terms if len(terms) < 2 else later).append((j, nm))
+            ops.linear(n1, [L.wq, L.wk, L.wv], out=views,
+                       lora=[self._lora_term(L.lo[nm], sv["a_" + nm], j) for j, nm in terms] or None)
+            for j, nm in later:
+                T.lora_up_add(views[j], sv["a_" + nm][0], L.lo[nm].B, L.lo[nm].s)
             q5 = qkv.view(B, Tn, 3, H, hd)
             q, k, v = q5[:, :, 0], q5[:, :, 1], q5[:, :, 2]
             ops.rope_kv(q, k, None, cos, sin, 0)
@@ -372,9 +405,8 @@ class LlamaTrainStack:
             if L.lo["o_proj"] is None:
                 h1 = ops.linear(o2, L.wo, residual=x)
             else:
-                y = ops.linear(o2, L.wo)
-                sv["a_o_proj"] = self._lora_fwd(L.lo["o_proj"], o2, y)
-                h1 = ops.add(x, y)
+                sv["a_o_proj"] = self._lora_a(L.lo["o_proj"], o2)
+                h1 = ops.linear(o2, L.wo, residual=x, lora=[self._lora_term(L.lo["o_proj"], sv["a_o_proj"])])
             n2 = ops.rmsnorm(h1, L.ln2, eps)
             sv.update(n1=n1, qkv=qkv, o=o, lse=lse, h1=h1, n2=n2)
             E = L.E
@@ -404,12 +436,13 @@ class LlamaTrainStack:
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None
                 force = "tc" if md is not None else None
-                ops.linear(xin[r0:r1], L.w_gate[e], out=g[r0:r1], m_dev=md, force=force)
-                ops.linear(xin[r0:r1], L.w_up[e], out=u[r0:r1], m_dev=md, force=force)
                 am = {}
-                for nm, buf in (("gate_proj", g), ("up_proj", u)):
-                    if L.lo_mlp[e][nm] is not None:
-                        am[nm] = self._lora_fwd(L.lo_mlp[e][nm], xin[r0:r1], buf[r0:r1])
+                for nm, wt, buf in (("gate_proj", L.w_gate[e], g), ("up_proj", L.w_up[e], u)):
+                    lo = L.lo_mlp[e][nm]
+                    if lo is not None:
+                        am[nm] = self._lora_a(lo, xin[r0:r1])
+                    ops.linear(xin[r0:r1], wt, out=buf[r0:r1], m_dev=md, force="tc" if lo is not None else force,
+                               lora=[self._lora_term(lo, am[nm])] if lo is not None else None)
                 a_mlp.append(am)
             h = T.silu_mul(g, u)
             for e in range(E):
@@ -420,13 +453,13 @@ class LlamaTrainStack:
                     if lo is None:
                         x_next = ops.linear(h, L.w_down[0], residual=h1)
                     else:
-                        yd = ops.linear(h, L.w_down[0])
-                        a_mlp[0]["down_proj"] = self._lora_fwd(lo, h, yd)
-                        x_next = ops.add(h1, yd)
+                        a_mlp[0]["down_proj"] = self._lora_a(lo, h)
+                        x_next = ops.linear(h, L.w_down[0], residual=h1, lora=[self._lora_term(lo, a_mlp[0]["down_proj"])])
                 else:
-                    ops.linear(h[r0:r1], L.w_down[e], out=y[r0:r1], m_dev=md, force="tc")
                     if lo is not None:
-                        a_mlp[e]["down_proj"] = self._lora_fwd(lo, h[r0:r1], y[r0:r1])
+                        a_mlp[e]["down_proj"] = self._lora_a(lo, h[r0:r1])
+                    ops.linear(h[r0:r1], L.w_down[e], out=y[r0:r1], m_dev=md, force="tc",
+                               lora=[self._lora_term(lo, a_mlp[e]["down_proj"])] if lo is not None else None)
             if route is not None:
                 x_next = ops.moe_combine(y, route["slot"], route["gate"], residual=h1)
             sv.update(xin=xin, g=g, u=u, h=h, y=y, a_mlp=a_mlp)
@@ -469,22 +502,32 @@ class LlamaTrainStack:
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None
                 force = "tc" if md is not None else None
-                ops.linear(dy[r0:r1], L.w_downT[e], out=dh[r0:r1], m_dev=md, force=force)
                 lo = L.lo_mlp[e]["down_proj"]
+                term = du = None
                 if lo is not None:
-                    self._lora_bwd(lo, h[r0:r1], sv["a_mlp"][e]["down_proj"], dy[r0:r1], dh[r0:r1])
+                    term, du = self._lora_bwd_pre(lo, h[r0:r1], sv["a_mlp"][e]["down_proj"], dy[r0:r1])
+                ops.linear(dy[r0:r1], L.w_downT[e], out=dh[r0:r1], m_dev=md, force="tc" if term is not None else force,
+                           lora=[term] if term is not None else None)
+                if lo is not None and term is None:
+                    self._lora_bwd_dx(lo, sv["a_mlp"][e]["down_proj"], du, dh[r0:r1])
             T.silu_mul_bwd(g, u, dh)  # g <- dg, u <- du
             dxin = torch.zeros_like(xin) if route is not None else torch.empty_like(xin)
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None
                 force = "tc" if md is not None else None
-                ops.linear(g[r0:r1], L.w_gateT[e], out=dxin[r0:r1], m_dev=md, force=force)
-                ops.linear(u[r0:r1], L.w_upT[e], out=dxin[r0:r1], residual=dxin[r0:r1], m_dev=md, force=force)
-                for nm, buf in (("gate_proj", g), ("up_proj", u)):
+                pend = []
+                for nm, buf, wT, res in (("gate_proj", g, L.w_gateT[e], None), ("up_proj", u, L.w_upT[e], dxin[r0:r1])):
                     lo = L.lo_mlp[e][nm]
+                    term = du = None
                     if lo is not None:
-                        self._lora_bwd(lo, xin[r0:r1], sv["a_mlp"][e][nm], buf[r0:r1], dxin[r0:r1])
+                        term, du = self._lora_bwd_pre(lo, xin[r0:r1], sv["a_mlp"][e][nm], buf[r0:r1])
+                        if term is None:
+                            pend.append((lo, sv["a_mlp"][e][nm], du))
+                    ops.linear(buf[r0:r1], wT, out=dxin[r0:r1], residual=res, m_dev=md,
+                               force="tc" if term is not None else force, lora=[term] if term is not None else None)
+                for lo, svd, du in pend:
+                    self._lora_bwd_dx(lo, svd, du, dxin[r0:r1])
             if route is not None:
                 ones = torch.ones_like(route["gate"])
                 dn2 = ops.moe_combine(dxin, route["slot"], ones)
@@ -497,9 +540,12 @@ class LlamaTrainStack:
             dh1 = T.rmsnorm_bwd(sv["h1"], L.ln2, dn2, eps, add=dx, dweight=ar.of(L.ln2))
             # attention block
             o2 = sv["o"].view(S, D)
-            do = ops.linear(dh1, L.woT)
+            term = du = None
             if L.lo["o_proj"] is not None:
-                self._lora_bwd(L.lo["o_proj"], o2, sv["a_o_proj"], dh1, do)
+                term, du = self._lora_bwd_pre(L.lo["o_proj"], o2, sv["a_o_proj"], dh1)
+            do = ops.linear(dh1, L.woT, lora=[term] if term is not None else None)
+            if L.lo["o_proj"] is not None and term is None:
+                self._lora_bwd_dx(L.lo["o_proj"], sv["a_o_proj"], du, do)
             qkv = sv["qkv"]
             q5 = qkv.view(B, Tn, 3, H, hd)
             dqkv = torch.empty_like(qkv)
@@ -507,10 +553,17 @@ class LlamaTrainStack:
             dq32 = T.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], sv["o"], do.view(B, Tn, H, hd), sv["lse"], scale,
                                    d5[:, :, 1], d5[:, :, 2], causal=True, kv_mask=km)
             T.rope_bwd(dq32, d5[:, :, 0], d5[:, :, 1], cos, sin, 0)
-            dn1 = ops.linear(dqkv, L.wqkvT)
+            terms, pend = [], []
             for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
                 if L.lo[nm] is not None:
-                    self._lora_bwd(L.lo[nm], sv["n1"], sv["a_" + nm], dqkv[:, j * D:(j + 1) * D], dn1)
+                    term, du = self._lora_bwd_pre(L.lo[nm], sv["n1"], sv["a_" + nm], dqkv[:, j * D:(j + 1) * D])
+                    if term is not None and len(terms) < 2:
+                        terms.append(term)
+                    else:
+                        pend.append((L.lo[nm], sv["a_" + nm], du))
+            dn1 = ops.linear(dqkv, L.wqkvT, lora=terms or None)
+            for lo, svd, du in pend:
+                self._lora_bwd_dx(lo, svd, du, dn1)
             dx_in = dx
             dx = T.rmsnorm_bwd(sv["x"], L.ln1, dn1, eps, add=dh1, dweight=ar.of(L.ln1))
             if self.debug is not None:
