@@ -491,6 +491,10 @@ int mpl_moe_router_bwd(const float* gates, const int* expert, const int* slot, c
                        float aux_scale, const float* wg, float* dlogits, void* dh, long long ldh, int S, int D, int E,
                        int k, void* stream);
 
+/* Zero rows [e*C + kept[e], (e+1)*C) of an expert buffer bf16 [groups*C, width] (row pitch ld): everything the per-expert
+ * kernels leave unwritten, instead of zero-filling the whole buffer first. */
+int mpl_zero_tail_rows(void* buf, long long ld, int groups, int C, int width, const int* kept, void* stream);
+
 /* Shifted cross-entropy of medplib_moe_llama.py:399-421 on fp32 logits: labels i64 [rows] (already shifted; < 0 ignored).
  * fwd: lse[r], acc[0] += sum of row losses, acc[1] += valid rows (acc zeroed by the caller; loss = acc[0]/acc[1]).
  * bwd: dlogits bf16 [rows, ldd] = (softmax - onehot) * (*grad_out) / acc[1], columns [V, ldd) zero. */

@@ -194,7 +194,7 @@ EXPORTS = [
     "mpl_silu_mul_bwd", "mpl_attention_bwd", "mpl_rope_bwd", "mpl_moe_combine_bwd", "mpl_moe_router_bwd", "mpl_ce_fwd",
     "mpl_ce_bwd", "mpl_scatter_add_rows", "mpl_sumsq_f32", "mpl_adamw", "mpl_adamw_multi", "mpl_mask_losses",
     "mpl_gemm_small", "mpl_col_sum", "mpl_layernorm_bwd", "mpl_act_fwd", "mpl_act_bwd", "mpl_attn_small_bwd",
-    "mpl_bilinear_resize_bwd", "mpl_mask_losses_bwd", "mpl_mask_scale_bf16", "mpl_token_pool", "mpl_token_pool_bwd", "mpl_col2im_nhwc",
+    "mpl_bilinear_resize_bwd", "mpl_mask_losses_bwd", "mpl_mask_scale_bf16", "mpl_token_pool", "mpl_token_pool_bwd", "mpl_col2im_nhwc", "mpl_zero_tail_rows",
     "mpl_preprocess_images", "mpl_preprocess_band_rows",
 ]
 _LL_RET = {"mpl_launch_count", "mpl_llama_workspace_bytes", "mpl_clip_workspace_bytes", "mpl_sam_encoder_workspace_bytes",

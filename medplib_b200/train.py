@@ -422,15 +422,15 @@ class LlamaTrainStack:
                 l_aux.append(route["l_aux"])
                 gate_logits.append(route["logits"])
                 rows = E * C
-                xin = torch.zeros((rows, D), dtype=bf16, device=dev)
+                xin = T.expert_buffer(rows, D, C, route["kept"], dev)  # (rows past kept[e]: zero; the rest: dispatch)
                 ops.moe_dispatch(n2, route["slot"], rows, out=xin)
                 sv.update(route=route, C=C)
             else:
                 C, rows, xin, route = S, S, n2, None
-            g = torch.zeros((rows, F_), dtype=bf16, device=dev) if route is not None else \
+            g = T.expert_buffer(rows, F_, C, route["kept"], dev) if route is not None else \
                 torch.empty((rows, F_), dtype=bf16, device=dev)
-            u = torch.zeros_like(g) if route is not None else torch.empty_like(g)
-            y = torch.zeros((rows, D), dtype=bf16, device=dev) if route is not None else None
+            u = T.expert_buffer(rows, F_, C, route["kept"], dev) if route is not None else torch.empty_like(g)
+            y = T.expert_buffer(rows, D, C, route["kept"], dev) if route is not None else None
             a_mlp = []
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
@@ -493,8 +493,8 @@ class LlamaTrainStack:
             g, u, h, xin = sv["g"], sv["u"], sv["h"], sv["xin"]
             rows = g.shape[0]
             if route is not None:
-                dy, dgate = T.moe_combine_bwd(dx, sv["y"], route["slot"], route["gate"], rows)
-                dh = torch.zeros_like(h)
+                dy, dgate = T.moe_combine_bwd(dx, sv["y"], route["slot"], route["gate"], rows, C=C, kept=route["kept"])
+                dh = T.expert_buffer(rows, h.shape[1], C, route["kept"], dev)
             else:
                 dy, dgate = dx, None
                 dh = torch.empty_like(h)
@@ -511,7 +511,7 @@ class LlamaTrainStack:
                 if lo is not None and term is None:
                     self._lora_bwd_dx(lo, sv["a_mlp"][e]["down_proj"], du, dh[r0:r1])
             T.silu_mul_bwd(g, u, dh)  # g <- dg, u <- du
-            dxin = torch.zeros_like(xin) if route is not None else torch.empty_like(xin)
+            dxin = T.expert_buffer(rows, xin.shape[1], C, route["kept"], dev) if route is not None else torch.empty_like(xin)
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None

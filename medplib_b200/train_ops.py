@@ -2,6 +2,7 @@
 backward kernels of the LLaMA-MoE stack with LoRA, fused cross-entropy, mask losses, AdamW. Same rules as ops.py: CUDA
 tensors only, kernels go on torch's current stream, no eager fallback."""
 import ctypes
+import os
 
 import torch
 
@@ -160,13 +161,15 @@ def rope_bwd(dq_f32, dq, dk, cos, sin, pos0=0):
                                 _stream()), "mpl_rope_bwd")
 
 
-def moe_combine_bwd(dout, y, slot, gate, rows):
-    """Returns (dy bf16 [rows, D] zero elsewhere, dgate f32 [S,k])."""
+def moe_combine_bwd(dout, y, slot, gate, rows, C=None, kept=None):
+    """Returns (dy bf16 [rows, D] zero elsewhere, dgate f32 [S,k]). With C / kept (rows per expert, kept count per expert)
+    only the rows no kept slot writes are zeroed."""
     lib = _lib.load()
     d2 = _rows(dout)
     S, k = slot.shape
     D = y.shape[-1]
-    dy = torch.zeros((rows, D), dtype=bf16, device=y.device)
+    dy = expert_buffer(rows, D, C, kept, y.device) if kept is not None else torch.zeros((rows, D), dtype=bf16,
+                                                                                          device=y.device)
     dgate = torch.empty((S, k), dtype=f32, device=y.device)
     _lib.check(lib.mpl_moe_combine_bwd(_ptr(d2), _ll(d2.stride(0)), _ptr(y), _ptr(slot), _ptr(gate), _ptr(dy),
                                        _ptr(dgate), S, k, D, _stream()), "mpl_moe_combine_bwd")
@@ -393,3 +396,15 @@ def col2im_nhwc(dcols, B, H, W, C, kh, kw, stride, pad):
     dx = torch.empty((B, H, W, C), dtype=bf16, device=dcols.device)
     _lib.check(lib.mpl_col2im_nhwc(_ptr(dcols), _ptr(dx), B, H, W, C, kh, kw, stride, pad, _stream()), "mpl_col2im_nhwc")
     return dx
+
+
+def expert_buffer(rows, width, C, kept, device):
+    """bf16 [rows = E * C, width] whose rows past every expert's kept count are zero (the rest is left for the per-expert
+    kernels to write)."""
+    lib = _lib.load()
+    if os.environ.get("MPL_ZERO_TAIL", "1") == "0":  # A/B switch: the whole buffer zero-filled, as before
+        return torch.zeros((rows, width), dtype=bf16, device=device)
+    buf = torch.empty((rows, width), dtype=bf16, device=device)
+    _lib.check(lib.mpl_zero_tail_rows(_ptr(buf), _ll(width), rows // C, C, width, _ptr(kept), _stream()),
+               "mpl_zero_tail_rows")
+    return buf

@@ -366,9 +366,11 @@ def test_foreign_optimizer_sees_ordinary_grads(dev):
     for n, g in want.items():
         p = params[n]
         assert p.grad is not None and p.grad.dtype == p.dtype and p.grad.shape == p.shape
-        a, w1 = p.grad.float(), g.to(p.dtype).float()  # (atomic accumulation orders differ from run to run; a key bias
-        # has a mathematically zero gradient -- softmax is shift invariant -- so its value is rounding noise: absolute floor)
-        assert (a - w1).abs().max() <= 1e-2 * w1.abs().max() + 1e-4, n
+        a, w1 = p.grad.float(), g.to(p.dtype).float()  # (atomic accumulation orders differ from run to run: two passes
+        # of the SAME path differ by up to 1.4e-2 of a LoRA gradient's scale, tests/dev/debug_determinism.py -- the fp32
+        # dQ / weight-gradient REDs land in a different order and the next bf16 rounding amplifies it; a key bias has a
+        # mathematically zero gradient -- softmax is shift invariant -- so its value is rounding noise: absolute floor)
+        assert (a - w1).abs().max() <= 2.5e-2 * w1.abs().max() + 1e-4, n
     left = {n: float(g.abs().max()) for n, g in tr.arena.grads().items() if float(g.abs().max()) != 0.0}
     assert not left, f"arena not handed over clean: {left}"  # the next micro-step starts from zero
     fwd()["loss"].backward()  # accumulation is autograd's now
