@@ -87,6 +87,13 @@ typedef struct {
   int lora_u_f32[2];
   int lora_mat[2];
   int lora_r;
+  /* Tensor-core path only: ONE extra k-block (64 columns of K) appended to the contraction, C[i] = epilogue(A B[i]^T +
+   * ext_a ext_b[i]^T): the rank-r adapters of a LoRA-wrapped Linear (or of its dgrad) enter the fp32 accumulator on the
+   * tensor cores -- ext_a = [u_0 | u_1 | ... | 0] bf16 [M, 64] (adapter t in columns [8t, 8t+8)), ext_b = bf16
+   * [(nb, or 2 with B2) * N, 64], matrix-major, rows of matrix i = [s B_0 | ... ] with zeros for the adapters that do not
+   * feed it. One rounding (the GEMM's) instead of peft's three; NULL = off. */
+  const void* ext_a;
+  const void* ext_b;
 } mpl_gemm_args;
 int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream);
 /* In-situ timing of the tcgen05 GEMM launches (bench.py roofline): enable, run, then read the summed CUDA-event
@@ -446,6 +453,14 @@ int mpl_lora_down(const void* x, long long ldx, const void* A, long long lda, vo
                   float scale, void* stream);
 int mpl_lora_up_add(void* y, long long ldy, const void* u, int u_is_f32, const void* Bm, long long bm_stride_n,
                     long long bm_stride_r, float scale, int M, int N, int r, void* stream);
+/* The adapters as an extension k-block of the base GEMM (mpl_gemm_args.ext_a / ext_b):
+ *   mpl_lora_down_ext = mpl_lora_down + a second copy of u in columns [pad_col, pad_col + r) of u_pad bf16 [M, 64]
+ *   mpl_lora_pack     fills the weight-side operands of EVERY adapter in one launch: items = device array of
+ *                     {const bf16* src; bf16* dst; long long sn, sr; int N, r, col; float scale} (48 bytes),
+ *                     dst[n, col + j] = bf16(scale * src[n * sn + j * sr]), dst bf16 [N, 64] zero elsewhere. */
+int mpl_lora_down_ext(const void* x, long long ldx, const void* A, long long lda, void* u, int u_is_f32, int M, int K,
+                      int r, float scale, void* u_pad, int pad_col, void* stream);
+int mpl_lora_pack(const void* items, int n_items, void* stream);
 int mpl_rank_wgrad(const void* X, long long ldx, const void* U, int u_is_f32, float* out, long long out_stride_n,
                    long long out_stride_r, float scale, int M, int N, int r, void* stream);
 

@@ -30,7 +30,7 @@ class GemmArgs(ctypes.Structure):
         ("nb", c_int), ("act", c_int), ("out_dtype", c_int), ("tile_n", c_int),
         ("ln_weight", c_void_p), ("ln_eps", c_float),
         ("lora_u", c_void_p * 2), ("lora_b", c_void_p * 2), ("lora_scale", c_float * 2), ("lora_u_f32", c_int * 2),
-        ("lora_mat", c_int * 2), ("lora_r", c_int),
+        ("lora_mat", c_int * 2), ("lora_r", c_int), ("ext_a", c_void_p), ("ext_b", c_void_p),
     ]
 
 
@@ -194,7 +194,7 @@ EXPORTS = [
     "mpl_silu_mul_bwd", "mpl_attention_bwd", "mpl_rope_bwd", "mpl_moe_combine_bwd", "mpl_moe_router_bwd", "mpl_ce_fwd",
     "mpl_ce_bwd", "mpl_scatter_add_rows", "mpl_sumsq_f32", "mpl_adamw", "mpl_adamw_multi", "mpl_mask_losses",
     "mpl_gemm_small", "mpl_col_sum", "mpl_layernorm_bwd", "mpl_act_fwd", "mpl_act_bwd", "mpl_attn_small_bwd",
-    "mpl_bilinear_resize_bwd", "mpl_mask_losses_bwd", "mpl_mask_scale_bf16", "mpl_token_pool", "mpl_token_pool_bwd", "mpl_col2im_nhwc", "mpl_zero_tail_rows",
+    "mpl_bilinear_resize_bwd", "mpl_mask_losses_bwd", "mpl_mask_scale_bf16", "mpl_token_pool", "mpl_token_pool_bwd", "mpl_col2im_nhwc", "mpl_zero_tail_rows", "mpl_lora_down_ext", "mpl_lora_pack",
     "mpl_preprocess_images", "mpl_preprocess_band_rows",
 ]
 _LL_RET = {"mpl_launch_count", "mpl_llama_workspace_bytes", "mpl_clip_workspace_bytes", "mpl_sam_encoder_workspace_bytes",

@@ -52,6 +52,7 @@ struct GemmDevParams {
   int groups;
   long long a_group_rows;
   long long c_group_stride;  // elements
+  int ext;  // 1: one extra k-block whose operands come from the extension maps (rank-r adapters inside the accumulator)
   // fused LoRA up-projections (see mpl_gemm_args): term t adds to output matrix lora_mat[t]
   const void* lora_u[2];
   const __nv_bfloat16* lora_b[2];
@@ -342,7 +343,8 @@ template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
-                         const GemmDevParams p, const __grid_constant__ GroupMaps gmaps) {
+                         const GemmDevParams p, const __grid_constant__ GroupMaps gmaps,
+                         const __grid_constant__ CUtensorMap tmAx, const __grid_constant__ CUtensorMap tmBx) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -398,9 +400,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const TileCoord tc = ts.at(tile);
         const int which = tc.g, n0 = tc.n0;
         const int m0 = p.groups > 0 ? static_cast<int>(tc.g * p.a_group_rows) + tc.m0 : tc.m0;  // row in the A buffer
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = 0; kb < kblocks + p.ext; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+          if (kb == kblocks) {
+            // extension k-block: [u_0 | u_1 | ... | 0] x [s B_0 | s B_1 | ... | 0]^T -- the rank-r adapters of this output
+            // enter the fp32 accumulator as 64 more columns of K (rows of the weight-side tensor: matrix / group major)
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmAx, &full_bar[stage], 0, m0);
+            if (p.dual) {
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmBx, &full_bar[stage], 0, n0);
+              tma_load_2d(sB + stage * Cfg::B_BYTES + Cfg::B_BYTES / 2, &tmBx, &full_bar[stage], 0, p.N + n0);
+            } else {
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmBx, &full_bar[stage], 0, which * p.N + n0);
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           tma_load_2d(sA + stage * Cfg::A_BYTES, &tmA, &full_bar[stage], kb * BK, m0);
           if (p.groups > 0) {
             // per-group weight maps: a __grid_constant__ array, indexed in param space
@@ -441,7 +459,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = 0; kb < kblocks + p.ext; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
@@ -528,7 +546,8 @@ template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                               const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2,
-                              const GemmDevParams p, const __grid_constant__ GroupMaps gmaps) {
+                              const GemmDevParams p, const __grid_constant__ GroupMaps gmaps,
+                              const __grid_constant__ CUtensorMap tmAx, const __grid_constant__ CUtensorMap tmBx) {
   using Cfg = PairCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -588,12 +607,21 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         // weight rows of this CTA: the two halves of the tile's columns, or (dual) gate rows in the leader / up rows in the peer
         const int nrow = p.dual ? tc.n0 : tc.n0 + static_cast<int>(rank) * (BN / 2);
         const bool second = p.dual && rank == 1;  // the peer reads W2 (up)
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = 0; kb < kblocks + p.ext; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (Cfg::A_BYTES + Cfg::B_BYTES));
-          tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, fb, kb * BK, m0);
           uint8_t* dstB = sB + stage * Cfg::B_BYTES;
+          if (kb == kblocks) {  // extension k-block (see the one-CTA kernel)
+            tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmAx, fb, 0, m0);
+            tma_load_2d_pair(dstB, &tmBx, fb, 0, p.dual ? static_cast<int>(rank) * p.N + tc.n0 : which * p.N + nrow);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmA, fb, kb * BK, m0);
           if (p.groups > 0) {
             if (second)
               tma_load_2d_pair(dstB, &gmaps.b2[which], fb, kb * BK, nrow);
@@ -627,7 +655,7 @@ gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __g
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = 0; kb < kblocks + p.ext; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
@@ -841,7 +869,8 @@ static int pick_tile_n(long long rows, int row_sets, int N, int dual, bool lora 
 
 template <int BN, bool PAIR>
 static int launch_any(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB1, const CUtensorMap& tmB2,
-                      const GemmDevParams& p, const GroupMaps& gm, long long tiles, cudaStream_t stream) {
+                      const GemmDevParams& p, const GroupMaps& gm, long long tiles, cudaStream_t stream,
+                      const CUtensorMap* tmAx = nullptr, const CUtensorMap* tmBx = nullptr) {
   using Cfg = std::conditional_t<PAIR, PairCfg<BN>, GemmCfg<BN>>;  // (only the selected kernel is instantiated)
   constexpr int smem = Cfg::SMEM_BYTES;
   auto kernel = [] {
@@ -864,7 +893,8 @@ static int launch_any(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   if (PAIR) grid *= 2;
   const bool prof = g_prof && !g_prof_suppress;
   if (prof) cudaEventRecord(prof_event(), stream);
-  launch_pdl(kernel, dim3(grid), dim3(GEMM_THREADS), smem_launch, stream, tmA, tmB, tmB1, tmB2, p, gm);
+  launch_pdl(kernel, dim3(grid), dim3(GEMM_THREADS), smem_launch, stream, tmA, tmB, tmB1, tmB2, p, gm,
+             tmAx != nullptr ? *tmAx : tmA, tmBx != nullptr ? *tmBx : tmB);
   if (prof) cudaEventRecord(prof_event(), stream);
   return mpl::launch_status();
 }
@@ -929,6 +959,16 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   const int bm = PAIR ? 2 * BM : BM;
   const long long tiles = static_cast<long long>((a.M + bm - 1) / bm) * ((a.N + out_bn - 1) / out_bn) * nb;
   static const GroupMaps no_groups = {};
+  CUtensorMap tmAx, tmBx;
+  if (a.ext_a != nullptr) {
+    // rank-r adapters as 64 more columns of K: ext_a bf16 [M, 64], ext_b bf16 [(nb, or 2 with B2) * N, 64], zero where unused
+    if (a.ext_b == nullptr) return MPL_ERR_ARG;
+    rc = make_tmap(&tmAx, a.ext_a, a.M, BK, BK, BM);
+    if (rc == MPL_OK) rc = make_tmap(&tmBx, a.ext_b, static_cast<long long>(dual ? 2 : nb) * a.N, BK, BK, box_b);
+    if (rc) return rc;
+    p.ext = 1;
+    return launch_any<BN, PAIR>(tmA, tmB, tmB1, tmB2, p, no_groups, tiles, stream, &tmAx, &tmBx);
+  }
   return launch_any<BN, PAIR>(tmA, tmB, tmB1, tmB2, p, no_groups, tiles, stream);
 }
 

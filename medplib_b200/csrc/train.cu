@@ -440,7 +440,7 @@ __device__ __forceinline__ uint32_t u32_of(const uint4& v, int i) {
 __global__ void __launch_bounds__(256) lora_down_mma_kernel(const bf16_t* __restrict__ x, long long ldx,
                                                             const bf16_t* __restrict__ A, long long lda,
                                                             void* __restrict__ u, int u_f32, int M, int K, int r,
-                                                            float scale) {
+                                                            float scale, bf16_t* __restrict__ u_pad, int pad_col) {
   __shared__ float red[8][16][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const long long m0 = static_cast<long long>(blockIdx.x) * 16;
@@ -491,7 +491,28 @@ __global__ void __launch_bounds__(256) lora_down_mma_kernel(const bf16_t* __rest
         static_cast<float*>(u)[m * r + j] = v * scale;
       else
         static_cast<bf16_t*>(u)[m * r + j] = __float2bfloat16_rn(v * scale);
+      // second copy for the GEMM's extension k-block: columns [pad_col, pad_col + r) of a [M, 64] bf16 operand
+      if (u_pad != nullptr) u_pad[m * 64 + pad_col + j] = __float2bfloat16_rn(v * scale);
     }
+  }
+}
+
+// Extension-operand rows of one adapter: dst[n, col + j] = bf16(scale * src[n * sn + j * sr]) for j < r (dst bf16 [N, 64],
+// zero elsewhere -- written once at allocation). One launch packs EVERY adapter of the model (device-side item table).
+struct LoraPackItem {
+  const bf16_t* src;
+  bf16_t* dst;
+  long long sn, sr;
+  int N, r, col;
+  float scale;
+};
+__global__ void __launch_bounds__(256) lora_pack_kernel(const LoraPackItem* __restrict__ items) {
+  const LoraPackItem it = items[blockIdx.y];
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < static_cast<long long>(it.N) * it.r;
+       i += static_cast<long long>(gridDim.x) * 256) {
+    const long long n = i / it.r;
+    const int j = static_cast<int>(i % it.r);
+    it.dst[n * 64 + it.col + j] = __float2bfloat16_rn(it.scale * __bfloat162float(it.src[n * it.sn + j * it.sr]));
   }
 }
 
@@ -1364,6 +1385,31 @@ extern "C" int mpl_transpose_bf16(const void* in, long long ld_in, void* out, lo
   return launch_status();
 }
 
+// mpl_lora_down + a second, padded copy of u for the GEMM's extension k-block (mpl_gemm_args.ext_a): u_pad bf16 [M, 64],
+// columns [pad_col, pad_col + r). MPL_ERR_UNSUPPORTED when the shape does not take the tensor-core kernel.
+extern "C" int mpl_lora_down_ext(const void* x, long long ldx, const void* A, long long lda, void* u, int u_is_f32, int M,
+                                 int K, int r, float scale, void* u_pad, int pad_col, void* stream) {
+  if (M <= 0) return MPL_OK;
+  if (x == nullptr || A == nullptr || u == nullptr || u_pad == nullptr || r < 1 || pad_col < 0 || pad_col + r > 64)
+    return MPL_ERR_ARG;
+  if (!(r <= 8 && K % 32 == 0 && ldx % 8 == 0 && lda % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(A) & 15) == 0))
+    return MPL_ERR_UNSUPPORTED;
+  lora_down_mma_kernel<<<(M + 15) / 16, 256, 0, ST(stream)>>>(static_cast<const bf16_t*>(x), ldx,
+                                                              static_cast<const bf16_t*>(A), lda, u, u_is_f32, M, K, r, scale,
+                                                              static_cast<bf16_t*>(u_pad), pad_col);
+  return launch_status();
+}
+
+// items: device array of n_items {src, dst, sn, sr, N, r, col, scale} (see LoraPackItem; 48 bytes each)
+extern "C" int mpl_lora_pack(const void* items, int n_items, void* stream) {
+  if (n_items <= 0) return MPL_OK;
+  if (items == nullptr) return MPL_ERR_ARG;
+  dim3 grid(32, static_cast<unsigned>(n_items));
+  lora_pack_kernel<<<grid, 256, 0, ST(stream)>>>(static_cast<const LoraPackItem*>(items));
+  return launch_status();
+}
+
 extern "C" int mpl_lora_down(const void* x, long long ldx, const void* A, long long lda, void* u, int u_is_f32, int M,
                              int K, int r, float scale, void* stream) {
   if (M <= 0) return MPL_OK;
@@ -1372,7 +1418,7 @@ extern "C" int mpl_lora_down(const void* x, long long ldx, const void* A, long l
   if (r <= 8 && K % 32 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
     lora_down_mma_kernel<<<(M + 15) / 16, 256, 0, ST(stream)>>>(static_cast<const bf16_t*>(x), ldx,
                                                                 static_cast<const bf16_t*>(A), lda, u, u_is_f32, M, K, r,
-                                                                scale);
+                                                                scale, nullptr, 0);
     return launch_status();
   }
   if (r <= LR8 && static_cast<size_t>(r) * K * 2 <= 200 * 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&

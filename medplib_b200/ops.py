@@ -41,13 +41,15 @@ def _rows(x):
 
 
 def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scale=None, m_dev=None,
-           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5, lora=None):
+           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5, lora=None, ext=None):
     """y = epilogue(x @ weight.T); x [..., K] bf16, weight [N, K] bf16 (nn.Linear layout).
 
     weight may be a list/tuple of 1..3 same-shape matrices sharing x in one launch (returns a list of outputs).
     weight2 selects the fused SiLU(x W^T) * (x W2^T). force in {None, "tc", "skinny"}. See mpl_gemm_bf16.
     lora: up to two fused rank-r up-projections [(u [M, r] bf16 / f32, b [N, r] bf16 contiguous, scale, matrix index)]:
     out[i] = bf16(out[i] + bf16(scale * bf16(u b^T))) in the epilogue (tensor-core path, bf16 output).
+    ext: (ext_a bf16 [M, 64], ext_b bf16 [len(weight) * N (2 * N with weight2), 64]): one extra k-block, the adapters
+    inside the accumulator (mpl_gemm_args.ext_a / ext_b).
     """
     lib = _lib.load()
     ws = list(weight) if isinstance(weight, (list, tuple)) else [weight]
@@ -113,6 +115,11 @@ def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scal
             a.lora_u[t], a.lora_b[t] = u.data_ptr(), b.data_ptr()
             a.lora_scale[t], a.lora_u_f32[t], a.lora_mat[t] = float(sc), int(u.dtype == torch.float32), int(mat)
             keep.append((u, b))
+    if ext is not None:
+        ea, eb = ext
+        assert ea.dtype == bf16 and eb.dtype == bf16 and ea.is_contiguous() and eb.is_contiguous()
+        assert ea.shape[0] >= M and ea.shape[1] == 64 and eb.shape == ((2 if weight2 is not None else nb) * N, 64)
+        a.ext_a, a.ext_b = ea.data_ptr(), eb.data_ptr()
     fn = {None: lib.mpl_linear_bf16, "tc": lib.mpl_gemm_bf16, "skinny": lib.mpl_skinny_gemm_bf16}[force]
     _lib.check(fn(ctypes.byref(a), _stream()), "mpl_linear_bf16")
     for u, b, sc, mat in unfused:

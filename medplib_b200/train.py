@@ -29,6 +29,9 @@ bf16 = torch.bfloat16
 f32 = torch.float32
 # LoRA up-projections in the epilogue of the base GEMM (mpl_gemm_args.lora_*) instead of a separate pass over its output
 LORA_FUSE = os.environ.get("MPL_LORA_FUSE", "1") != "0"
+# ... and, where every adapter of an output qualifies (rank 8, no lora_dropout), inside the GEMM's accumulator: one extra
+# k-block [u_0 | u_1 | ..] x [s B_0 | s B_1 | ..]^T on the tensor cores (mpl_gemm_args.ext_a / ext_b)
+LORA_EXT = os.environ.get("MPL_LORA_EXT", "1") != "0"
 LORA_EXCLUDE = ("visual_model", "vision_tower", "mm_projector")  # train_ds_medplib.py:272-281
 
 
@@ -249,6 +252,28 @@ def _frozen(w, what):
     return w
 
 
+class _ExtSite:
+    """The adapters feeding ONE base GEMM as its extension k-block: weight-side operand `b` (bf16 [n_mats * N, 64], adapter t
+    in columns [8t, 8t + 8) of the rows of the matrix it feeds, zero elsewhere) + the pack records that fill it."""
+
+    def __init__(self, n_mats, N, device):
+        self.N = N
+        self.b = torch.zeros((n_mats * N, 64), dtype=bf16, device=device)
+        self.col = {}     # id(_Lora) -> first column
+        self.items = []   # (src tensor, dst row offset, sn, sr, N, r, col, scale)
+
+    def add(self, lo, mat, transposed):
+        """transposed=False: forward, rows = s * lora_B [N, r]; True: dgrad, rows = lora_A^T (lora_A is [r, N])."""
+        col = 8 * len(self.col)
+        self.col[id(lo)] = col
+        src = lo.A if transposed else lo.B
+        r = lo.A.shape[0]
+        if transposed:
+            self.items.append((src, mat * self.N, src.stride(1), src.stride(0), self.N, r, col, 1.0))
+        else:
+            self.items.append((src, mat * self.N, src.stride(0), src.stride(1), self.N, r, col, lo.s))
+
+
 class LlamaTrainStack:
     """Training forward (activations kept) and backward of the decoder stack of a MedPLIBForCausalLM."""
 
@@ -307,10 +332,131 @@ class LlamaTrainStack:
             # arena offset below which everything is final once this layer's backward is done
             ends = [arena.end_of(p) for p in layer.parameters() if arena.of(p) is not None]
             L.arena_end = max(ends) if ends else None
+            self._ext_sites(L, D, self.F, L.wq.device)
             self.layers.append(L)
+        self._ext_table()
+
+    # ------------------------------------------------------------------ adapters as extension k-blocks
+    @staticmethod
+    def _ext_ok(los):
+        return LORA_EXT and LORA_FUSE and len(los) > 0 and len(los) <= 8 and all(lo.A.shape[0] == 8 for lo in los)
+
+    def _ext_sites(self, L, D, F_, dev):
+        """Forward and dgrad sites of one layer (None where no adapter feeds the GEMM or one of them does not qualify)."""
+        L.ext_f, L.ext_b = {}, {}
+
+        def make(key, n_mats, N, pairs, transposed, table):
+            los = [lo for _, lo in pairs]
+            if not self._ext_ok(los):
+                table[key] = None
+                return
+            site = _ExtSite(n_mats, N, dev)
+            for mat, lo in pairs:
+                site.add(lo, mat, transposed)
+            table[key] = site
+
+        qkv = [(j, L.lo[nm]) for j, nm in enumerate(("q_proj", "k_proj", "v_proj")) if L.lo[nm] is not None]
+        make("qkv", 3, D, qkv, False, L.ext_f)
+        make("qkv", 1, D, [(0, lo) for _, lo in qkv], True, L.ext_b)
+        o = [(0, L.lo["o_proj"])] if L.lo["o_proj"] is not None else []
+        make("o", 1, D, o, False, L.ext_f)
+        make("o", 1, D, o, True, L.ext_b)
+        for e in range(L.E):
+            for nm, n_out, n_in in (("gate_proj", F_, D), ("up_proj", F_, D), ("down_proj", D, F_)):
+                lo = L.lo_mlp[e][nm]
+                one = [(0, lo)] if lo is not None else []
+                make((nm, e), 1, n_out, one, False, L.ext_f)
+                make((nm, e), 1, n_in, one, True, L.ext_b)
+
+    def _ext_table(self):
+        """Device table of pack records (48 bytes each, mpl_lora_pack) over every site of the model + its dirty flag."""
+        import struct
+        recs, keep = [], []
+        for L in self.layers:
+            for table in (L.ext_f, L.ext_b):
+                for site in table.values():
+                    if site is None:
+                        continue
+                    for src, row0, sn, sr, N, r, col, scale in site.items:
+                        recs.append(struct.pack("<QQqqiiif", src.data_ptr(), site.b.data_ptr() + row0 * 64 * 2, sn, sr, N, r, col,
+                                                scale))
+                        keep.append(src)
+        self._ext_n = len(recs)
+        self._ext_keep = keep
+        self._ext_items = None
+        if recs:
+            dev = self.layers[0].wq.device
+            self._ext_items = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev)
+        self.ext_dirty = True
+        self._pads = {}
+
+    def _ext_refresh(self):
+        """(Re)build every weight-side extension operand from the current adapter weights: one launch, after each
+        optimizer step (every forward when a foreign optimizer owns the weights)."""
+        if self._ext_items is not None and self.ext_dirty:
+            T.lora_pack(self._ext_items, self._ext_n)
+            self.ext_dirty = False
+
+    def _pad(self, rows, dev):
+        """Activation-side extension operand bf16 [rows, 64]: zero once, columns [8t, 8t + 8) rewritten per use."""
+        buf = self._pads.get(rows)
+        if buf is None:
+            buf = self._pads[rows] = torch.zeros((rows, 64), dtype=bf16, device=dev)
+        return buf
+
+    def _site_usable(self, site, los):
+        return site is not None and not (self.training and any(lo.p > 0.0 for lo in los))
+
+    def _linear_lora(self, x, weights, los, site, out=None, residual=None, m_dev=None, force=None):
+        """y_i = x W_i^T (+ residual) with the adapters `los` = [(matrix index, _Lora)] of its outputs. Returns
+        (result of ops.linear, {matrix index: saved for the backward})."""
+        saved = {}
+        multi = isinstance(weights, (list, tuple))
+        if not los:
+            return ops.linear(x, weights, out=out, residual=residual, m_dev=m_dev, force=force), saved
+        if self._site_usable(site, [lo for _, lo in los]):
+            buf = self._pad(x.shape[0], x.device)
+            for mat, lo in los:
+                saved[mat] = self._lora_a(lo, x, pad=(buf, site.col[id(lo)]))
+            return ops.linear(x, weights, out=out, residual=residual, m_dev=m_dev, force="tc", ext=(buf, site.b)), saved
+        terms, later = [], []
+        for mat, lo in los:
+            saved[mat] = self._lora_a(lo, x)
+            (terms if len(terms) < 2 else later).append((mat, lo))
+        y = ops.linear(x, weights, out=out, residual=residual if not later else None, m_dev=m_dev, force="tc",
+                       lora=[self._lora_term(lo, saved[mat], mat) for mat, lo in terms])
+        ys = y if multi else [y]
+        for mat, lo in later:
+            T.lora_up_add(ys[mat], saved[mat][0], lo.B, lo.s)
+        if later and residual is not None:
+            assert not multi
+            y = ops.add(residual, y)
+        return y, saved
+
+    def _dgrad_lora(self, dy, wT, adapters, site, out=None, residual=None, m_dev=None, force=None):
+        """dx = dy W (+ residual) + sum over `adapters` = [(_Lora, x, saved, dy slice of that adapter)] of du A; their dA, dB
+        go into the arena."""
+        if not adapters:
+            return ops.linear(dy, wT, out=out, residual=residual, m_dev=m_dev, force=force)
+        if self._site_usable(site, [a[0] for a in adapters]):
+            buf = self._pad(dy.shape[0], dy.device)
+            for lo, x, saved, dys in adapters:
+                self._lora_bwd_pre(lo, x, saved, dys, pad=(buf, site.col[id(lo)]))
+            return ops.linear(dy, wT, out=out, residual=residual, m_dev=m_dev, force="tc", ext=(buf, site.b))
+        terms, pend = [], []
+        for lo, x, saved, dys in adapters:
+            term, du = self._lora_bwd_pre(lo, x, saved, dys)
+            if term is not None and len(terms) < 2:
+                terms.append(term)
+            else:
+                pend.append((lo, saved, du))
+        dx = ops.linear(dy, wT, out=out, residual=residual, m_dev=m_dev, force="tc" if terms else force, lora=terms or None)
+        for lo, saved, du in pend:
+            self._lora_bwd_dx(lo, saved, du, dx)
+        return dx
 
     # ------------------------------------------------------------------ helpers
-    def _lora_a(self, lo, x):
+    def _lora_a(self, lo, x, pad=None):
         """a = dropout(x) A^T (bf16 [M, r]) in peft's rounding; returns what the backward needs: (a, dropped input or
         None, keep mask or None)."""
         xd = mask = None
@@ -322,7 +468,7 @@ class LlamaTrainStack:
             else:
                 mask = (torch.rand(x.shape, device=x.device) >= lo.p).to(torch.uint8)
             xd = T.mask_scale(x if x.is_contiguous() else x.contiguous(), mask, 1.0 / (1.0 - lo.p))
-        a = T.lora_down(xd if xd is not None else x, lo.A)
+        a = T.lora_down(xd if xd is not None else x, lo.A, pad=pad)
         return (a, xd, mask)
 
     def _lora_fwd(self, lo, x, y):
@@ -337,17 +483,17 @@ class LlamaTrainStack:
         """The adapter as a fused epilogue term of the base GEMM: (u, b [N, r], scale, output matrix)."""
         return (saved[0], lo.B.detach(), lo.s, mat)
 
-    def _lora_bwd_pre(self, lo, x, saved, dy):
+    def _lora_bwd_pre(self, lo, x, saved, dy, pad=None):
         """Everything of the adapter's backward except dx: dB, dA into the arena. Returns the epilogue term of the base
         dgrad GEMM, (du f32 [M, r], A^T [in, r], 1.0, 0), or None when lora_dropout is active (dx then needs the mask:
         _lora_bwd_dx)."""
         a, xd, mask = saved
         if lo.gB is not None:
             T.rank_wgrad(dy, a, lo.gB, scale=lo.s)
-        du = T.lora_down(dy, T.transpose(lo.B.detach()), scale=lo.s, out_f32=True)
+        du = T.lora_down(dy, T.transpose(lo.B.detach()), scale=lo.s, out_f32=True, pad=pad)
         if lo.gA is not None:
             T.rank_wgrad(xd if xd is not None else x, du, lo.gA, transposed=True)
-        if mask is not None:
+        if mask is not None or pad is not None:
             return None, du
         return (du, T.transpose(lo.A.detach()), 1.0, 0), du
 
@@ -382,31 +528,28 @@ class LlamaTrainStack:
         scale = 1.0 / math.sqrt(hd)
         km = kv_mask.to(torch.uint8).contiguous() if kv_mask is not None else None
         saved, l_aux, gate_logits = [], [], []
+        self.ext_dirty = True  # (one ~50 us launch per step: cheaper than tracking who may have touched the adapters)
+        self._ext_refresh()
         for li, L in enumerate(self.layers):
             sv = {"x": x}
             n1 = ops.rmsnorm(x, L.ln1, eps)
             qkv = torch.empty((S, 3 * D), dtype=bf16, device=dev)
             views = [qkv[:, j * D:(j + 1) * D] for j in range(3)]
-            # adapters ride in the epilogue of the base GEMM (two terms per launch; a third one takes its own pass)
-            terms, later = [], []
+            # adapters ride inside the base GEMM: as an extension k-block where they qualify, else in its epilogue
+            los = [(j, L.lo[nm]) for j, nm in enumerate(("q_proj", "k_proj", "v_proj")) if L.lo[nm] is not None]
+            _, sav = self._linear_lora(n1, [L.wq, L.wk, L.wv], los, L.ext_f["qkv"], out=views)
             for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
-                if L.lo[nm] is not None:
-                    sv["a_" + nm] = self._lora_a(L.lo[nm], n1)
-                    (terms if len(terms) < 2 else later).append((j, nm))
-            ops.linear(n1, [L.wq, L.wk, L.wv], out=views,
-                       lora=[self._lora_term(L.lo[nm], sv["a_" + nm], j) for j, nm in terms] or None)
-            for j, nm in later:
-                T.lora_up_add(views[j], sv["a_" + nm][0], L.lo[nm].B, L.lo[nm].s)
+                if j in sav:
+                    sv["a_" + nm] = sav[j]
             q5 = qkv.view(B, Tn, 3, H, hd)
             q, k, v = q5[:, :, 0], q5[:, :, 1], q5[:, :, 2]
             ops.rope_kv(q, k, None, cos, sin, 0)
             o, lse = T.attention_fwd_lse(q, k, v, scale, causal=True, kv_mask=km)
             o2 = o.view(S, D)
-            if L.lo["o_proj"] is None:
-                h1 = ops.linear(o2, L.wo, residual=x)
-            else:
-                sv["a_o_proj"] = self._lora_a(L.lo["o_proj"], o2)
-                h1 = ops.linear(o2, L.wo, residual=x, lora=[self._lora_term(L.lo["o_proj"], sv["a_o_proj"])])
+            h1, sav = self._linear_lora(o2, L.wo, [(0, L.lo["o_proj"])] if L.lo["o_proj"] is not None else [],
+                                        L.ext_f["o"], residual=x)
+            if 0 in sav:
+                sv["a_o_proj"] = sav[0]
             n2 = ops.rmsnorm(h1, L.ln2, eps)
             sv.update(n1=n1, qkv=qkv, o=o, lse=lse, h1=h1, n2=n2)
             E = L.E
@@ -439,27 +582,24 @@ class LlamaTrainStack:
                 am = {}
                 for nm, wt, buf in (("gate_proj", L.w_gate[e], g), ("up_proj", L.w_up[e], u)):
                     lo = L.lo_mlp[e][nm]
-                    if lo is not None:
-                        am[nm] = self._lora_a(lo, xin[r0:r1])
-                    ops.linear(xin[r0:r1], wt, out=buf[r0:r1], m_dev=md, force="tc" if lo is not None else force,
-                               lora=[self._lora_term(lo, am[nm])] if lo is not None else None)
+                    _, sav = self._linear_lora(xin[r0:r1], wt, [(0, lo)] if lo is not None else [], L.ext_f[(nm, e)],
+                                               out=buf[r0:r1], m_dev=md, force=force)
+                    if 0 in sav:
+                        am[nm] = sav[0]
                 a_mlp.append(am)
             h = T.silu_mul(g, u)
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None
                 lo = L.lo_mlp[e]["down_proj"]
+                one = [(0, lo)] if lo is not None else []
                 if route is None:
-                    if lo is None:
-                        x_next = ops.linear(h, L.w_down[0], residual=h1)
-                    else:
-                        a_mlp[0]["down_proj"] = self._lora_a(lo, h)
-                        x_next = ops.linear(h, L.w_down[0], residual=h1, lora=[self._lora_term(lo, a_mlp[0]["down_proj"])])
+                    x_next, sav = self._linear_lora(h, L.w_down[0], one, L.ext_f[("down_proj", 0)], residual=h1)
                 else:
-                    if lo is not None:
-                        a_mlp[e]["down_proj"] = self._lora_a(lo, h[r0:r1])
-                    ops.linear(h[r0:r1], L.w_down[e], out=y[r0:r1], m_dev=md, force="tc",
-                               lora=[self._lora_term(lo, a_mlp[e]["down_proj"])] if lo is not None else None)
+                    _, sav = self._linear_lora(h[r0:r1], L.w_down[e], one, L.ext_f[("down_proj", e)], out=y[r0:r1],
+                                               m_dev=md, force="tc")
+                if 0 in sav:
+                    a_mlp[e]["down_proj"] = sav[0]
             if route is not None:
                 x_next = ops.moe_combine(y, route["slot"], route["gate"], residual=h1)
             sv.update(xin=xin, g=g, u=u, h=h, y=y, a_mlp=a_mlp)
@@ -503,31 +643,19 @@ class LlamaTrainStack:
                 md = route["kept"][e:e + 1] if route is not None else None
                 force = "tc" if md is not None else None
                 lo = L.lo_mlp[e]["down_proj"]
-                term = du = None
-                if lo is not None:
-                    term, du = self._lora_bwd_pre(lo, h[r0:r1], sv["a_mlp"][e]["down_proj"], dy[r0:r1])
-                ops.linear(dy[r0:r1], L.w_downT[e], out=dh[r0:r1], m_dev=md, force="tc" if term is not None else force,
-                           lora=[term] if term is not None else None)
-                if lo is not None and term is None:
-                    self._lora_bwd_dx(lo, sv["a_mlp"][e]["down_proj"], du, dh[r0:r1])
+                ad = [(lo, h[r0:r1], sv["a_mlp"][e]["down_proj"], dy[r0:r1])] if lo is not None else []
+                self._dgrad_lora(dy[r0:r1], L.w_downT[e], ad, L.ext_b[("down_proj", e)], out=dh[r0:r1], m_dev=md, force=force)
             T.silu_mul_bwd(g, u, dh)  # g <- dg, u <- du
             dxin = T.expert_buffer(rows, xin.shape[1], C, route["kept"], dev) if route is not None else torch.empty_like(xin)
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None
                 force = "tc" if md is not None else None
-                pend = []
                 for nm, buf, wT, res in (("gate_proj", g, L.w_gateT[e], None), ("up_proj", u, L.w_upT[e], dxin[r0:r1])):
                     lo = L.lo_mlp[e][nm]
-                    term = du = None
-                    if lo is not None:
-                        term, du = self._lora_bwd_pre(lo, xin[r0:r1], sv["a_mlp"][e][nm], buf[r0:r1])
-                        if term is None:
-                            pend.append((lo, sv["a_mlp"][e][nm], du))
-                    ops.linear(buf[r0:r1], wT, out=dxin[r0:r1], residual=res, m_dev=md,
-                               force="tc" if term is not None else force, lora=[term] if term is not None else None)
-                for lo, svd, du in pend:
-                    self._lora_bwd_dx(lo, svd, du, dxin[r0:r1])
+                    ad = [(lo, xin[r0:r1], sv["a_mlp"][e][nm], buf[r0:r1])] if lo is not None else []
+                    self._dgrad_lora(buf[r0:r1], wT, ad, L.ext_b[(nm, e)], out=dxin[r0:r1], residual=res, m_dev=md,
+                                     force=force)
             if route is not None:
                 ones = torch.ones_like(route["gate"])
                 dn2 = ops.moe_combine(dxin, route["slot"], ones)
@@ -540,12 +668,8 @@ class LlamaTrainStack:
             dh1 = T.rmsnorm_bwd(sv["h1"], L.ln2, dn2, eps, add=dx, dweight=ar.of(L.ln2))
             # attention block
             o2 = sv["o"].view(S, D)
-            term = du = None
-            if L.lo["o_proj"] is not None:
-                term, du = self._lora_bwd_pre(L.lo["o_proj"], o2, sv["a_o_proj"], dh1)
-            do = ops.linear(dh1, L.woT, lora=[term] if term is not None else None)
-            if L.lo["o_proj"] is not None and term is None:
-                self._lora_bwd_dx(L.lo["o_proj"], sv["a_o_proj"], du, do)
+            ad = [(L.lo["o_proj"], o2, sv["a_o_proj"], dh1)] if L.lo["o_proj"] is not None else []
+            do = self._dgrad_lora(dh1, L.woT, ad, L.ext_b["o"])
             qkv = sv["qkv"]
             q5 = qkv.view(B, Tn, 3, H, hd)
             dqkv = torch.empty_like(qkv)
@@ -553,17 +677,9 @@ class LlamaTrainStack:
             dq32 = T.attention_bwd(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], sv["o"], do.view(B, Tn, H, hd), sv["lse"], scale,
                                    d5[:, :, 1], d5[:, :, 2], causal=True, kv_mask=km)
             T.rope_bwd(dq32, d5[:, :, 0], d5[:, :, 1], cos, sin, 0)
-            terms, pend = [], []
-            for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
-                if L.lo[nm] is not None:
-                    term, du = self._lora_bwd_pre(L.lo[nm], sv["n1"], sv["a_" + nm], dqkv[:, j * D:(j + 1) * D])
-                    if term is not None and len(terms) < 2:
-                        terms.append(term)
-                    else:
-                        pend.append((L.lo[nm], sv["a_" + nm], du))
-            dn1 = ops.linear(dqkv, L.wqkvT, lora=terms or None)
-            for lo, svd, du in pend:
-                self._lora_bwd_dx(lo, svd, du, dn1)
+            ad = [(L.lo[nm], sv["n1"], sv["a_" + nm], dqkv[:, j * D:(j + 1) * D])
+                  for j, nm in enumerate(("q_proj", "k_proj", "v_proj")) if L.lo[nm] is not None]
+            dn1 = self._dgrad_lora(dqkv, L.wqkvT, ad, L.ext_b["qkv"])
             dx_in = dx
             dx = T.rmsnorm_bwd(sv["x"], L.ln1, dn1, eps, add=dh1, dweight=ar.of(L.ln1))
             if self.debug is not None:

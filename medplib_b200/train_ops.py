@@ -28,8 +28,9 @@ def transpose(x, out=None, ld_out=None):
     return out
 
 
-def lora_down(x, A, scale=1.0, out_f32=False):
-    """u = scale * x @ A.T; x bf16 [M,K], A bf16 [r,K] -> u [M,r] (bf16 or f32)."""
+def lora_down(x, A, scale=1.0, out_f32=False, pad=None):
+    """u = scale * x @ A.T; x bf16 [M,K], A bf16 [r,K] -> u [M,r] (bf16 or f32). pad = (u_pad bf16 [>= M, 64], col): a
+    second bf16 copy of u in columns [col, col + r) of u_pad (the extension operand of the base GEMM)."""
     lib = _lib.load()
     _req(x, bf16, "x"); _req(A, bf16, "A")
     x2 = _rows(x)
@@ -37,6 +38,12 @@ def lora_down(x, A, scale=1.0, out_f32=False):
     r = A.shape[0]
     assert A.shape[1] == K and A.stride(1) == 1
     u = torch.empty((M, r), dtype=f32 if out_f32 else bf16, device=x.device)
+    if pad is not None:
+        buf, col = pad
+        assert buf.dtype == bf16 and buf.is_contiguous() and buf.shape[0] >= M and buf.shape[1] == 64
+        _lib.check(lib.mpl_lora_down_ext(_ptr(x2), _ll(x2.stride(0)), _ptr(A), _ll(A.stride(0)), _ptr(u), int(out_f32), M, K,
+                                         r, _F(scale), _ptr(buf), int(col), _stream()), "mpl_lora_down_ext")
+        return u
     _lib.check(lib.mpl_lora_down(_ptr(x2), _ll(x2.stride(0)), _ptr(A), _ll(A.stride(0)), _ptr(u), int(out_f32), M, K, r,
                                  _F(scale), _stream()), "mpl_lora_down")
     return u
@@ -408,3 +415,10 @@ def expert_buffer(rows, width, C, kept, device):
     _lib.check(lib.mpl_zero_tail_rows(_ptr(buf), _ll(width), rows // C, C, width, _ptr(kept), _stream()),
                "mpl_zero_tail_rows")
     return buf
+
+
+def lora_pack(items_dev, n_items):
+    """One launch fills the weight-side extension operands of every adapter (mpl_lora_pack; items: uint8 device tensor
+    of 48-byte records)."""
+    lib = _lib.load()
+    _lib.check(lib.mpl_lora_pack(_ptr(items_dev), int(n_items), _stream()), "mpl_lora_pack")
