@@ -1,13 +1,15 @@
-"""Dev probe (GPU box): router margins of the top-2 drop case, GPU vs fp32 / bf16 oracle, over a few batch seeds."""
+"""Dev probe (GPU box): router margins of a train-test case, GPU vs fp32 / bf16 oracle, over a few batch seeds.
+   python tests/dev/debug_top2.py [cf pad(0/1) top_k seeds,comma,separated]"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import torch
 import test_train_gpu as tt
 dev = torch.device("cuda:0")
-cf, pad = 0.4, True
-for seed in (52, 53, 5, 8, 21, 33, 47):
-    m, sd, ocfg = tt.build(dev, cf=cf, aux=0.01, top_k=2)
+cf, pad, top_k = (float(sys.argv[1]), sys.argv[2] == "1", int(sys.argv[3])) if len(sys.argv) > 3 else (0.4, True, 2)
+seeds = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else (52, 53, 5, 8, 21, 33, 47)
+for seed in seeds:
+    m, sd, ocfg = tt.build(dev, cf=cf, aux=0.0 if top_k == 1 else 0.01, top_k=top_k)
     b = tt.batch(seg=False, pad=pad, seed=seed)
     ids, labels, am, clip_img, sam_img, gts = b[:6]
     S = ids.shape[0] * (ids.shape[1] - 1 + 16)

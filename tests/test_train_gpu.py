@@ -267,8 +267,10 @@ def test_top2_gating_loss_and_gradients(dev, cf, pad, aux):
 @pytest.mark.parametrize("cf,pad,aux", [(1.5, False, 0.01), (0.6, True, 0.0)])
 def test_text_loss_and_gradients(dev, cf, pad, aux):
     """seg_flag=False: CE (+ aux) loss; LoRA q,v,gate,up,down of every expert, wg, lm_head, embed_tokens gradients.
-    cf=0.6 forces capacity overflow (tokens dropped by injected RTS uniforms); pad=True adds key padding."""
-    run_case(dev, False, cf, pad, aux)
+    cf=0.6 forces capacity overflow (tokens dropped by injected RTS uniforms); pad=True adds key padding. (The drop case
+    uses the batch seed whose smallest router margin, 0.17 over both layers and all three arithmetics, is far above the
+    bf16 activation noise of ~0.04 -- tests/dev/debug_top2.py; the default seed sat at 0.014 in layer 1.)"""
+    run_case(dev, False, cf, pad, aux, seed=53 if pad else None)
 
 
 def test_grounding_loss_and_gradients(dev):
