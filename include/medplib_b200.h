@@ -94,6 +94,10 @@ typedef struct {
    * feed it. One rounding (the GEMM's) instead of peft's three; NULL = off. */
   const void* ext_a;
   const void* ext_b;
+  /* B2 != NULL, tensor-core path: also store the two projections themselves, bf16 [M, N] with row pitch ldc each (the
+   * train forward keeps gate(x) and up(x) for the backward); NULL = only silu(gate) * up goes out. */
+  void* dual_g;
+  void* dual_u;
 } mpl_gemm_args;
 int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream);
 /* In-situ timing of the tcgen05 GEMM launches (bench.py roofline): enable, run, then read the summed CUDA-event

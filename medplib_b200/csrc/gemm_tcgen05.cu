@@ -52,6 +52,8 @@ struct GemmDevParams {
   int groups;
   long long a_group_rows;
   long long c_group_stride;  // elements
+  __nv_bfloat16* dual_g;  // dual mode, optional: the rounded gate / up projections themselves (train forward keeps them)
+  __nv_bfloat16* dual_u;
   int ext;  // 1: one extra k-block whose operands come from the extension maps (rank-r adapters inside the accumulator)
   // fused LoRA up-projections (see mpl_gemm_args): term t adds to output matrix lora_mat[t]
   const void* lora_u[2];
@@ -201,6 +203,35 @@ __device__ __forceinline__ void epilogue_rows(const GemmDevParams& p, const __nv
       uint32_t r2[32];
       tmem_ld_32x32(t_row + BN / 2 + c * 32, r2);
       tmem_ld_wait();
+      if (p.dual_g != nullptr && row_ok && n0 + c * 32 < nlim) {
+        // the train forward keeps gate(x) and up(x) for the backward: same rounding as the two separate GEMMs gave
+        const int nc0 = n0 + c * 32;
+        __nv_bfloat16* gp = p.dual_g + static_cast<long long>(row) * p.ldc + nc0;
+        __nv_bfloat16* up = p.dual_u + static_cast<long long>(row) * p.ldc + nc0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (nc0 + q * 8 + 8 <= nlim && vec_ok) {
+            uint4 og, ou;
+            og.x = pack_bf16(__uint_as_float(r[q * 8 + 0]), __uint_as_float(r[q * 8 + 1]));
+            og.y = pack_bf16(__uint_as_float(r[q * 8 + 2]), __uint_as_float(r[q * 8 + 3]));
+            og.z = pack_bf16(__uint_as_float(r[q * 8 + 4]), __uint_as_float(r[q * 8 + 5]));
+            og.w = pack_bf16(__uint_as_float(r[q * 8 + 6]), __uint_as_float(r[q * 8 + 7]));
+            ou.x = pack_bf16(__uint_as_float(r2[q * 8 + 0]), __uint_as_float(r2[q * 8 + 1]));
+            ou.y = pack_bf16(__uint_as_float(r2[q * 8 + 2]), __uint_as_float(r2[q * 8 + 3]));
+            ou.z = pack_bf16(__uint_as_float(r2[q * 8 + 4]), __uint_as_float(r2[q * 8 + 5]));
+            ou.w = pack_bf16(__uint_as_float(r2[q * 8 + 6]), __uint_as_float(r2[q * 8 + 7]));
+            *reinterpret_cast<uint4*>(gp + q * 8) = og;
+            *reinterpret_cast<uint4*>(up + q * 8) = ou;
+          } else {
+#pragma unroll
+            for (int j = q * 8; j < q * 8 + 8; ++j)
+              if (nc0 + j < nlim) {
+                gp[j] = __float2bfloat16_rn(__uint_as_float(r[j]));
+                up[j] = __float2bfloat16_rn(__uint_as_float(r2[j]));
+              }
+          }
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         // reference: down(silu(gate(x)) * up(x)) with every intermediate rounded to bf16
@@ -942,6 +973,11 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   p.act = a.act;
   p.out_f32 = a.out_dtype == MPL_DT_F32;
   p.dual = dual;
+  if (a.dual_g != nullptr || a.dual_u != nullptr) {
+    if (!dual || a.dual_g == nullptr || a.dual_u == nullptr || a.out_dtype == MPL_DT_F32) return MPL_ERR_ARG;
+    p.dual_g = static_cast<__nv_bfloat16*>(a.dual_g);
+    p.dual_u = static_cast<__nv_bfloat16*>(a.dual_u);
+  }
   if (a.lora_r != 0) {
     if (a.lora_r != 8 || dual || a.out_dtype == MPL_DT_F32) return MPL_ERR_UNSUPPORTED;
     p.lora_r = a.lora_r;

@@ -41,7 +41,7 @@ def _rows(x):
 
 
 def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scale=None, m_dev=None,
-           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5, lora=None, ext=None):
+           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5, lora=None, ext=None, dual_out=None):
     """y = epilogue(x @ weight.T); x [..., K] bf16, weight [N, K] bf16 (nn.Linear layout).
 
     weight may be a list/tuple of 1..3 same-shape matrices sharing x in one launch (returns a list of outputs).
@@ -115,6 +115,11 @@ def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scal
             a.lora_u[t], a.lora_b[t] = u.data_ptr(), b.data_ptr()
             a.lora_scale[t], a.lora_u_f32[t], a.lora_mat[t] = float(sc), int(u.dtype == torch.float32), int(mat)
             keep.append((u, b))
+    if dual_out is not None:  # (weight2 given) also keep gate(x), up(x): bf16 [M, N] views with the row pitch of `out`
+        dg, du = dual_out
+        assert weight2 is not None and dg.dtype == bf16 and du.dtype == bf16 and dg.stride(1) == 1 and du.stride(1) == 1
+        assert dg.stride(0) == outs[0].stride(0) and du.stride(0) == outs[0].stride(0)
+        a.dual_g, a.dual_u = dg.data_ptr(), du.data_ptr()
     if ext is not None:
         ea, eb = ext
         assert ea.dtype == bf16 and eb.dtype == bf16 and ea.is_contiguous() and eb.is_contiguous()

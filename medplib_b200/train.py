@@ -362,6 +362,9 @@ class LlamaTrainStack:
         make("o", 1, D, o, False, L.ext_f)
         make("o", 1, D, o, True, L.ext_b)
         for e in range(L.E):
+            # gate and up as ONE dual GEMM (SiLU(gate) * up in its epilogue): both adapters in the same extension block
+            gu = [(j, L.lo_mlp[e][nm]) for j, nm in enumerate(("gate_proj", "up_proj")) if L.lo_mlp[e][nm] is not None]
+            make(("gateup", e), 2, F_, gu, False, L.ext_f)
             for nm, n_out, n_in in (("gate_proj", F_, D), ("up_proj", F_, D), ("down_proj", D, F_)):
                 lo = L.lo_mlp[e][nm]
                 one = [(0, lo)] if lo is not None else []
@@ -575,11 +578,35 @@ class LlamaTrainStack:
             u = T.expert_buffer(rows, F_, C, route["kept"], dev) if route is not None else torch.empty_like(g)
             y = T.expert_buffer(rows, D, C, route["kept"], dev) if route is not None else None
             a_mlp = []
+            # gate, up and SiLU(gate) * up in ONE dual GEMM per expert (g and u are kept for the backward) when no adapter of
+            # the pair needs the epilogue / separate-pass route; else two GEMMs + the SiLU * up pass
+            fuse_gu = LORA_FUSE and all(
+                (not [lo for lo in (L.lo_mlp[e]["gate_proj"], L.lo_mlp[e]["up_proj"]) if lo is not None])
+                or self._site_usable(L.ext_f[("gateup", e)], [lo for lo in (L.lo_mlp[e]["gate_proj"], L.lo_mlp[e]["up_proj"])
+                                                              if lo is not None]) for e in range(E))
+            h = None
+            if fuse_gu:
+                h = T.expert_buffer(rows, F_, C, route["kept"], dev) if route is not None else \
+                    torch.empty((rows, F_), dtype=bf16, device=dev)
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None
                 force = "tc" if md is not None else None
                 am = {}
+                if fuse_gu:
+                    site = L.ext_f[("gateup", e)]
+                    ext = None
+                    if site is not None:
+                        buf = self._pad(r1 - r0, dev)
+                        for nm in ("gate_proj", "up_proj"):
+                            lo = L.lo_mlp[e][nm]
+                            if lo is not None:
+                                am[nm] = self._lora_a(lo, xin[r0:r1], pad=(buf, site.col[id(lo)]))
+                        ext = (buf, site.b)
+                    ops.linear(xin[r0:r1], L.w_gate[e], weight2=L.w_up[e], out=h[r0:r1], m_dev=md, force="tc", ext=ext,
+                               dual_out=(g[r0:r1], u[r0:r1]))
+                    a_mlp.append(am)
+                    continue
                 for nm, wt, buf in (("gate_proj", L.w_gate[e], g), ("up_proj", L.w_up[e], u)):
                     lo = L.lo_mlp[e][nm]
                     _, sav = self._linear_lora(xin[r0:r1], wt, [(0, lo)] if lo is not None else [], L.ext_f[(nm, e)],
@@ -587,7 +614,8 @@ class LlamaTrainStack:
                     if 0 in sav:
                         am[nm] = sav[0]
                 a_mlp.append(am)
-            h = T.silu_mul(g, u)
+            if h is None:
+                h = T.silu_mul(g, u)
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None
