@@ -98,6 +98,11 @@ typedef struct {
    * train forward keeps gate(x) and up(x) for the backward); NULL = only silu(gate) * up goes out. */
   void* dual_g;
   void* dual_u;
+  /* Tensor-core path, nb == 1: this GEMM is the dgrad of LlamaMLP.down_proj (its result is dh) and the SiLU(gate) * up
+   * backward runs in its epilogue: g <- bf16(dh u s (1 + g (1 - s))), u <- bf16(dh g s), s = sigmoid(g), in place over
+   * bf16 [M, N] buffers with row pitch ldc; C may be NULL (dh itself is not stored). */
+  void* silu_bwd_g;
+  void* silu_bwd_u;
 } mpl_gemm_args;
 int mpl_gemm_bf16(const mpl_gemm_args* args, void* stream);
 /* In-situ timing of the tcgen05 GEMM launches (bench.py roofline): enable, run, then read the summed CUDA-event

@@ -31,7 +31,7 @@ class GemmArgs(ctypes.Structure):
         ("ln_weight", c_void_p), ("ln_eps", c_float),
         ("lora_u", c_void_p * 2), ("lora_b", c_void_p * 2), ("lora_scale", c_float * 2), ("lora_u_f32", c_int * 2),
         ("lora_mat", c_int * 2), ("lora_r", c_int), ("ext_a", c_void_p), ("ext_b", c_void_p),
-        ("dual_g", c_void_p), ("dual_u", c_void_p),
+        ("dual_g", c_void_p), ("dual_u", c_void_p), ("silu_bwd_g", c_void_p), ("silu_bwd_u", c_void_p),
     ]
 
 

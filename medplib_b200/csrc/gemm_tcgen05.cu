@@ -52,6 +52,8 @@ struct GemmDevParams {
   int groups;
   long long a_group_rows;
   long long c_group_stride;  // elements
+  __nv_bfloat16* sb_g;  // SiLU*up backward in the epilogue: v = dh -> g <- dh u silu'(g), u <- dh silu(g) (in place), no C
+  __nv_bfloat16* sb_u;
   __nv_bfloat16* dual_g;  // dual mode, optional: the rounded gate / up projections themselves (train forward keeps them)
   __nv_bfloat16* dual_u;
   int ext;  // 1: one extra k-block whose operands come from the extension maps (rank-r adapters inside the accumulator)
@@ -281,6 +283,40 @@ __device__ __forceinline__ void epilogue_rows(const GemmDevParams& p, const __nv
           v[j] = bf16_round(bf16_round(v[j]) + bf16_round(sc * bf16_round(acc)));
         }
       }
+    }
+    if (p.sb_g != nullptr) {
+      // this GEMM is the dgrad of down_proj: v = dh. The SiLU(gate) * up backward consumes it right here (dh rounded to bf16
+      // as the separate pass read it): dg = dh u s (1 + g (1 - s)), du = dh g s with s = sigmoid(g), written over g and u
+      __nv_bfloat16* gp = p.sb_g + static_cast<long long>(row) * p.ldc + nc;
+      __nv_bfloat16* up = p.sb_u + static_cast<long long>(row) * p.ldc + nc;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (nc + q * 8 + 8 <= nlim && vec_ok) {
+          uint4 gr = *reinterpret_cast<const uint4*>(gp + q * 8), ur = *reinterpret_cast<const uint4*>(up + q * 8);
+          __nv_bfloat162* g2 = reinterpret_cast<__nv_bfloat162*>(&gr);
+          __nv_bfloat162* u2 = reinterpret_cast<__nv_bfloat162*>(&ur);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 gf = __bfloat1622float2(g2[e]), uf = __bfloat1622float2(u2[e]);
+            const float d0 = bf16_round(v[q * 8 + 2 * e]), d1 = bf16_round(v[q * 8 + 2 * e + 1]);
+            const float s0 = 1.0f / (1.0f + __expf(-gf.x)), s1 = 1.0f / (1.0f + __expf(-gf.y));
+            g2[e] = __floats2bfloat162_rn(d0 * uf.x * s0 * (1.0f + gf.x * (1.0f - s0)), d1 * uf.y * s1 * (1.0f + gf.y * (1.0f - s1)));
+            u2[e] = __floats2bfloat162_rn(d0 * gf.x * s0, d1 * gf.y * s1);
+          }
+          *reinterpret_cast<uint4*>(gp + q * 8) = gr;
+          *reinterpret_cast<uint4*>(up + q * 8) = ur;
+        } else {
+#pragma unroll
+          for (int j = q * 8; j < q * 8 + 8; ++j)
+            if (nc + j < nlim) {
+              const float gv = __bfloat162float(gp[j]), uv = __bfloat162float(up[j]), dv = bf16_round(v[j]);
+              const float sg = 1.0f / (1.0f + __expf(-gv));
+              gp[j] = __float2bfloat16_rn(dv * uv * sg * (1.0f + gv * (1.0f - sg)));
+              up[j] = __float2bfloat16_rn(dv * gv * sg);
+            }
+        }
+      }
+      continue;  // nothing else leaves this tile
     }
     if (p.residual != nullptr) {
       if (!f32) {
@@ -973,6 +1009,11 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
   p.act = a.act;
   p.out_f32 = a.out_dtype == MPL_DT_F32;
   p.dual = dual;
+  if (a.silu_bwd_g != nullptr || a.silu_bwd_u != nullptr) {
+    if (dual || nb != 1 || a.silu_bwd_g == nullptr || a.silu_bwd_u == nullptr || a.residual != nullptr) return MPL_ERR_ARG;
+    p.sb_g = static_cast<__nv_bfloat16*>(a.silu_bwd_g);
+    p.sb_u = static_cast<__nv_bfloat16*>(a.silu_bwd_u);
+  }
   if (a.dual_g != nullptr || a.dual_u != nullptr) {
     if (!dual || a.dual_g == nullptr || a.dual_u == nullptr || a.out_dtype == MPL_DT_F32) return MPL_ERR_ARG;
     p.dual_g = static_cast<__nv_bfloat16*>(a.dual_g);
@@ -1010,7 +1051,7 @@ static int launch_gemm(const mpl_gemm_args& a, cudaStream_t stream) {
 
 int gemm_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0) return MPL_OK;
-  if (a.K <= 0 || a.A == nullptr || a.B[0] == nullptr || a.C[0] == nullptr) return MPL_ERR_ARG;
+  if (a.K <= 0 || a.A == nullptr || a.B[0] == nullptr || (a.C[0] == nullptr && a.silu_bwd_g == nullptr)) return MPL_ERR_ARG;
   const int dual = a.B2 != nullptr;
   const int nb = a.nb < 1 ? 1 : a.nb;
   int bn = a.tile_n;

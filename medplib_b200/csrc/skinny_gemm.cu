@@ -521,7 +521,7 @@ int skinny_grouped_gemm_bf16(const mpl_grouped_gemm_args& a, cudaStream_t stream
 
 // Dispatcher used by the host side: tensor-core tiles for M > 16, streaming kernel otherwise.
 int linear_bf16(const mpl_gemm_args& a, cudaStream_t stream) {
-  if (a.lora_r != 0 || a.ext_a != nullptr || a.dual_g != nullptr) return gemm_bf16(a, stream);  // fused LoRA: tensor-core path only
+  if (a.lora_r != 0 || a.ext_a != nullptr || a.dual_g != nullptr || a.silu_bwd_g != nullptr) return gemm_bf16(a, stream);  // fused LoRA: tensor-core path only
   if (a.M <= 16 && (a.K % 8) == 0) return skinny_gemm_bf16(a, stream);
   if (a.ln_weight != nullptr) return MPL_ERR_UNSUPPORTED;  // the RMSNorm prologue exists on the streaming path only
   return gemm_bf16(a, stream);

@@ -41,7 +41,7 @@ def _rows(x):
 
 
 def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scale=None, m_dev=None,
-           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5, lora=None, ext=None, dual_out=None):
+           out_dtype=bf16, out=None, tile_n=0, force=None, ln_weight=None, ln_eps=1e-5, lora=None, ext=None, dual_out=None, silu_bwd=None):
     """y = epilogue(x @ weight.T); x [..., K] bf16, weight [N, K] bf16 (nn.Linear layout).
 
     weight may be a list/tuple of 1..3 same-shape matrices sharing x in one launch (returns a list of outputs).
@@ -63,7 +63,12 @@ def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scal
     assert ws[0].shape[1] == K
     x2 = _rows(x)
     M = x2.shape[0]
-    if out is None:
+    if silu_bwd is not None:
+        # the dgrad of down_proj with the SiLU(gate) * up backward in its epilogue: (g, u) bf16 [M, N] are rewritten in
+        # place with (dg, du); dh itself is not stored
+        assert nb == 1 and out is None and weight2 is None and residual is None
+        outs = [silu_bwd[0]]
+    elif out is None:
         outs = [torch.empty((M, N), dtype=out_dtype, device=x.device) for _ in range(nb)]
     else:
         outs = list(out) if isinstance(out, (list, tuple)) else [out]
@@ -115,6 +120,12 @@ def linear(x, weight, bias=None, act=None, residual=None, weight2=None, row_scal
             a.lora_u[t], a.lora_b[t] = u.data_ptr(), b.data_ptr()
             a.lora_scale[t], a.lora_u_f32[t], a.lora_mat[t] = float(sc), int(u.dtype == torch.float32), int(mat)
             keep.append((u, b))
+    if silu_bwd is not None:
+        sg, su = silu_bwd
+        assert sg.dtype == bf16 and su.dtype == bf16 and sg.shape == (M, N) and su.shape == (M, N)
+        assert sg.stride(1) == 1 and su.stride(1) == 1 and sg.stride(0) == su.stride(0)
+        a.silu_bwd_g, a.silu_bwd_u, a.ldc = sg.data_ptr(), su.data_ptr(), sg.stride(0)
+        a.C[0] = None
     if dual_out is not None:  # (weight2 given) also keep gate(x), up(x): bf16 [M, N] views with the row pitch of `out`
         dg, du = dual_out
         assert weight2 is not None and dg.dtype == bf16 and du.dtype == bf16 and dg.stride(1) == 1 and du.stride(1) == 1

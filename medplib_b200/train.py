@@ -32,6 +32,7 @@ LORA_FUSE = os.environ.get("MPL_LORA_FUSE", "1") != "0"
 # ... and, where every adapter of an output qualifies (rank 8, no lora_dropout), inside the GEMM's accumulator: one extra
 # k-block [u_0 | u_1 | ..] x [s B_0 | s B_1 | ..]^T on the tensor cores (mpl_gemm_args.ext_a / ext_b)
 LORA_EXT = os.environ.get("MPL_LORA_EXT", "1") != "0"
+SILU_BWD_FUSE = os.environ.get("MPL_SILU_BWD_FUSE", "0") == "1"
 LORA_EXCLUDE = ("visual_model", "vision_tower", "mm_projector")  # train_ds_medplib.py:272-281
 
 
@@ -436,16 +437,19 @@ class LlamaTrainStack:
             y = ops.add(residual, y)
         return y, saved
 
-    def _dgrad_lora(self, dy, wT, adapters, site, out=None, residual=None, m_dev=None, force=None):
+    def _dgrad_lora(self, dy, wT, adapters, site, out=None, residual=None, m_dev=None, force=None, silu_bwd=None):
         """dx = dy W (+ residual) + sum over `adapters` = [(_Lora, x, saved, dy slice of that adapter)] of du A; their dA, dB
         go into the arena."""
         if not adapters:
-            return ops.linear(dy, wT, out=out, residual=residual, m_dev=m_dev, force=force)
+            return ops.linear(dy, wT, out=out, residual=residual, m_dev=m_dev, force="tc" if silu_bwd is not None else force,
+                              silu_bwd=silu_bwd)
         if self._site_usable(site, [a[0] for a in adapters]):
             buf = self._pad(dy.shape[0], dy.device)
             for lo, x, saved, dys in adapters:
                 self._lora_bwd_pre(lo, x, saved, dys, pad=(buf, site.col[id(lo)]))
-            return ops.linear(dy, wT, out=out, residual=residual, m_dev=m_dev, force="tc", ext=(buf, site.b))
+            return ops.linear(dy, wT, out=out, residual=residual, m_dev=m_dev, force="tc", ext=(buf, site.b),
+                              silu_bwd=silu_bwd)
+        assert silu_bwd is None
         terms, pend = [], []
         for lo, x, saved, dys in adapters:
             term, du = self._lora_bwd_pre(lo, x, saved, dys)
@@ -662,18 +666,33 @@ class LlamaTrainStack:
             rows = g.shape[0]
             if route is not None:
                 dy, dgate = T.moe_combine_bwd(dx, sv["y"], route["slot"], route["gate"], rows, C=C, kept=route["kept"])
-                dh = T.expert_buffer(rows, h.shape[1], C, route["kept"], dev)
             else:
                 dy, dgate = dx, None
-                dh = torch.empty_like(h)
+            # dh = dy W_down (+ adapter) is consumed by the SiLU(gate) * up backward in the SAME launch's epilogue (g <- dg,
+            # u <- du in place) where every adapter of down_proj rides in the extension block; else dh goes through memory
+            # (measured on B200: the fused epilogue costs the GEMMs 9 ms per step and saves a 3.8 ms pass -- two loads, an
+            # exponential and two stores per element do not hide behind a K = 4096 main loop -- so it is off unless
+            # MPL_SILU_BWD_FUSE=1)
+            fuse_sb = SILU_BWD_FUSE and LORA_FUSE and all(L.lo_mlp[e]["down_proj"] is None or
+                                        self._site_usable(L.ext_b[("down_proj", e)], [L.lo_mlp[e]["down_proj"]])
+                                        for e in range(E))
+            dh = None
+            if not fuse_sb:
+                dh = T.expert_buffer(rows, h.shape[1], C, route["kept"], dev) if route is not None else torch.empty_like(h)
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
                 md = route["kept"][e:e + 1] if route is not None else None
                 force = "tc" if md is not None else None
                 lo = L.lo_mlp[e]["down_proj"]
                 ad = [(lo, h[r0:r1], sv["a_mlp"][e]["down_proj"], dy[r0:r1])] if lo is not None else []
-                self._dgrad_lora(dy[r0:r1], L.w_downT[e], ad, L.ext_b[("down_proj", e)], out=dh[r0:r1], m_dev=md, force=force)
-            T.silu_mul_bwd(g, u, dh)  # g <- dg, u <- du
+                if fuse_sb:
+                    self._dgrad_lora(dy[r0:r1], L.w_downT[e], ad, L.ext_b[("down_proj", e)], m_dev=md, force="tc",
+                                     silu_bwd=(g[r0:r1], u[r0:r1]))
+                else:
+                    self._dgrad_lora(dy[r0:r1], L.w_downT[e], ad, L.ext_b[("down_proj", e)], out=dh[r0:r1], m_dev=md,
+                                     force=force)
+            if not fuse_sb:
+                T.silu_mul_bwd(g, u, dh)  # g <- dg, u <- du
             dxin = T.expert_buffer(rows, xin.shape[1], C, route["kept"], dev) if route is not None else torch.empty_like(xin)
             for e in range(E):
                 r0, r1 = e * C, (e + 1) * C
