@@ -465,8 +465,9 @@ int mpl_lora_up_add(void* y, long long ldy, const void* u, int u_is_f32, const v
 /* The adapters as an extension k-block of the base GEMM (mpl_gemm_args.ext_a / ext_b):
  *   mpl_lora_down_ext = mpl_lora_down + a second copy of u in columns [pad_col, pad_col + r) of u_pad bf16 [M, 64]
  *   mpl_lora_pack     fills the weight-side operands of EVERY adapter in one launch: items = device array of
- *                     {const bf16* src; bf16* dst; long long sn, sr; int N, r, col; float scale} (48 bytes),
- *                     dst[n, col + j] = bf16(scale * src[n * sn + j * sr]), dst bf16 [N, 64] zero elsewhere. */
+ *                     {const bf16* src; bf16* dst; long long sn, sr; int N, r, col; float scale; long long dn, dj}
+ *                     (64 bytes): dst[n * dn + (col + j) * dj] = bf16(scale * src[n * sn + j * sr]) -- dn, dj = 64, 1 for an
+ *                     extension operand bf16 [N, 64] (zero elsewhere), 1, N for a plain transposed copy [r, N]. */
 int mpl_lora_down_ext(const void* x, long long ldx, const void* A, long long lda, void* u, int u_is_f32, int M, int K,
                       int r, float scale, void* u_pad, int pad_col, void* stream);
 int mpl_lora_pack(const void* items, int n_items, void* stream);

@@ -505,6 +505,7 @@ struct LoraPackItem {
   long long sn, sr;
   int N, r, col;
   float scale;
+  long long dn, dj;  // destination strides (64, 1 for an extension operand; 1, N for a plain transposed copy [r, N])
 };
 __global__ void __launch_bounds__(256) lora_pack_kernel(const LoraPackItem* __restrict__ items) {
   const LoraPackItem it = items[blockIdx.y];
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(256) lora_pack_kernel(const LoraPackItem* __re
        i += static_cast<long long>(gridDim.x) * 256) {
     const long long n = i / it.r;
     const int j = static_cast<int>(i % it.r);
-    it.dst[n * 64 + it.col + j] = __float2bfloat16_rn(it.scale * __bfloat162float(it.src[n * it.sn + j * it.sr]));
+    it.dst[n * it.dn + (it.col + j) * it.dj] = __float2bfloat16_rn(it.scale * __bfloat162float(it.src[n * it.sn + j * it.sr]));
   }
 }
 
@@ -1401,7 +1402,7 @@ extern "C" int mpl_lora_down_ext(const void* x, long long ldx, const void* A, lo
   return launch_status();
 }
 
-// items: device array of n_items {src, dst, sn, sr, N, r, col, scale} (see LoraPackItem; 48 bytes each)
+// items: device array of n_items {src, dst, sn, sr, N, r, col, scale, dn, dj} (see LoraPackItem; 64 bytes each)
 extern "C" int mpl_lora_pack(const void* items, int n_items, void* stream) {
   if (n_items <= 0) return MPL_OK;
   if (items == nullptr) return MPL_ERR_ARG;

@@ -88,7 +88,7 @@ def set_trainable(model, sft_modules):
 
 
 class _Lora:
-    __slots__ = ("A", "B", "s", "gA", "gB", "p", "name")
+    __slots__ = ("A", "B", "s", "gA", "gB", "p", "name", "BT")
 
     def __init__(self, lin, arena):
         self.A, self.B = lin.lora_A["default"].weight, lin.lora_B["default"].weight
@@ -382,9 +382,17 @@ class LlamaTrainStack:
                     if site is None:
                         continue
                     for src, row0, sn, sr, N, r, col, scale in site.items:
-                        recs.append(struct.pack("<QQqqiiif", src.data_ptr(), site.b.data_ptr() + row0 * 64 * 2, sn, sr, N, r, col,
-                                                scale))
+                        recs.append(struct.pack("<QQqqiiifqq", src.data_ptr(), site.b.data_ptr() + row0 * 64 * 2, sn, sr, N, r, col,
+                                                scale, 64, 1))
                         keep.append(src)
+            # lora_B^T [r, N] of every adapter (the down-projection du = s dY B of its backward), refreshed by the same launch
+            los = [lo for lo in L.lo.values() if lo is not None] + [lo for d in L.lo_mlp for lo in d.values() if lo is not None]
+            for lo in los:
+                N, r = lo.B.shape
+                lo.BT = torch.empty((r, N), dtype=bf16, device=lo.B.device)
+                recs.append(struct.pack("<QQqqiiifqq", lo.B.data_ptr(), lo.BT.data_ptr(), lo.B.stride(0), lo.B.stride(1), N, r, 0,
+                                        1.0, 1, N))
+                keep.append(lo.BT)
         self._ext_n = len(recs)
         self._ext_keep = keep
         self._ext_items = None
@@ -497,7 +505,8 @@ class LlamaTrainStack:
         a, xd, mask = saved
         if lo.gB is not None:
             T.rank_wgrad(dy, a, lo.gB, scale=lo.s)
-        du = T.lora_down(dy, T.transpose(lo.B.detach()), scale=lo.s, out_f32=True, pad=pad)
+        bt = getattr(lo, "BT", None)  # (kept current by the per-step lora_pack launch)
+        du = T.lora_down(dy, bt if bt is not None else T.transpose(lo.B.detach()), scale=lo.s, out_f32=True, pad=pad)
         if lo.gA is not None:
             T.rank_wgrad(xd if xd is not None else x, du, lo.gA, transposed=True)
         if mask is not None or pad is not None:
