@@ -1,0 +1,100 @@
+"""CPU: pins oracle/geo.py (GeoRegionSampler) against the REFERENCE's own module through
+tests/golden/geo.pt (made by tests/golden/make_golden_geo.py from /root/reference/model/rp_sampler/GeoSampler.py).
+
+What is held equal, per case: the sampled points (same RNG draws), the FPS indices of every stage (bit-exact: the
+first-maximum rule is the reference's), the kNN DISTANCE multisets (the index choice among equal distances is the
+implementation's in the reference, see oracle/geo.py), and the final output with the reference's kNN choice injected.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import geo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = torch.load(os.path.join(HERE, "golden", "geo.pt"), weights_only=False)
+DT = {"torch.float32": torch.float32, "torch.bfloat16": torch.bfloat16}
+
+
+def unpack(case):
+    dt = DT[case["dtype"]]
+    d, out_dim, n_init, subs, neighs = case["cfg"]
+    sd = {k: v.to(dt) for k, v in case["sd"].items()}
+    fmaps = [f.to(dt) for f in case["fmaps"]]
+    masks = [[m.long() for m in per] for per in case["masks"]]
+    n_stage = len(subs)
+    draws = [t for _, t in case["draws"]]
+    sample_draws, fps_start = draws[:len(draws) - n_stage], draws[len(draws) - n_stage:]
+    return dt, (n_init, subs, neighs), sd, fmaps, masks, sample_draws, fps_start
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_geo_sampler_matches_reference(ci):
+    case = CASES[ci]
+    dt, (n_init, subs, neighs), sd, fmaps, masks, sample_draws, fps_start = unpack(case)
+    rec = {}
+    out = geo.geo_region_sampler(sd, "", fmaps, masks, dt, dt, n_init, subs, neighs, case["pooler"],
+                                 draws=list(sample_draws), fps_start=fps_start, knn_override=case["knn"], record=rec)
+    for s in range(len(subs)):
+        assert torch.equal(rec["fps"][s], case["fps"][s]), f"FPS indices of stage {s}"
+    tol = 2e-5 if dt == torch.float32 else 2e-2
+    for o, r in zip(out, case["out"]):
+        assert (o is None) == (r is None)
+        if o is not None:
+            assert o.shape == r.shape and o.dtype == r.dtype
+            scale = float(r.float().abs().max())
+            assert float((o.float() - r.float()).abs().max()) <= tol * scale
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_same_seed_draws_the_reference_points(ci):
+    """The restatement makes the reference's RNG calls in the reference's order: seeded alike, it needs no injection."""
+    case = CASES[ci]
+    dt, (n_init, subs, neighs), sd, fmaps, masks, sample_draws, fps_start = unpack(case)
+    rec_a, rec_b = {}, {}
+    geo.geo_region_sampler(sd, "", fmaps, masks, dt, dt, n_init, subs, neighs, case["pooler"],
+                           draws=list(sample_draws), fps_start=fps_start, record=rec_a)
+    torch.manual_seed(1234)
+    geo.geo_region_sampler(sd, "", fmaps, masks, dt, dt, n_init, subs, neighs, case["pooler"], record=rec_b)
+    torch.manual_seed(1234)
+    pts = torch.cat([geo.sample_points(m, n_init) for m in masks if len(m)], 0)
+    assert torch.equal(pts.to(dt), rec_b["points"])
+    assert rec_a["points"].shape == rec_b["points"].shape
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_knn_choice_is_a_valid_topk_of_the_reference(ci):
+    """Stable (distance, index) kNN: the same distance multiset as the reference's torch.topk at every anchor, and the
+    same index set wherever the k-th and (k+1)-th distances differ."""
+    case = CASES[ci]
+    dt, (n_init, subs, neighs), sd, fmaps, masks, sample_draws, fps_start = unpack(case)
+    rec = {}
+    geo.geo_region_sampler(sd, "", fmaps, masks, dt, dt, n_init, subs, neighs, case["pooler"],
+                           draws=list(sample_draws), fps_start=fps_start, record=rec)
+    xy = rec["points"]
+    n_equal = n_total = 0
+    for s, k in enumerate(neighs):
+        fi = rec["fps"][s]
+        assert torch.equal(fi, case["fps"][s])
+        new_xy = geo.index_points(xy, fi)
+        d = geo.square_distance(new_xy, xy).float()
+        mine, ref = rec["knn"][s], case["knn"][s]
+        dm, dr = torch.gather(d, -1, mine).sort(-1)[0], torch.gather(d, -1, ref).sort(-1)[0]
+        assert torch.equal(dm, dr), f"stage {s}: kNN distance multisets differ"
+        srt = d.sort(-1)[0]
+        untied = srt[..., k - 1] < srt[..., k] if d.shape[-1] > k else torch.ones_like(srt[..., 0], dtype=torch.bool)
+        same = (mine.sort(-1)[0] == ref.sort(-1)[0]).all(-1)
+        assert bool(same[untied].all()), f"stage {s}: index sets differ where no tie exists"
+        n_equal, n_total = n_equal + int(same.sum()), n_total + same.numel()
+        if dt == torch.bfloat16:  # the kernel contract: the bf16 rounding points written out in fp32
+            assert torch.equal(geo.knn_dist_bf16(new_xy, xy), d)
+        xy = new_xy
+    assert n_total > 0
+
+
+def test_bf16_fps_distance_written_out():
+    torch.manual_seed(0)
+    xy = (torch.randint(0, 24, (3, 200, 2)).float() / 24).to(torch.bfloat16)
+    c = xy[:, 17:18]
+    assert torch.equal(geo.fps_dist_bf16(xy, c), torch.sum((xy - c) ** 2, -1).float())
