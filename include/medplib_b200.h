@@ -280,6 +280,33 @@ int mpl_bilinear_resize(const void* in, long long in_stride_n, long long in_stri
  * (align_corners=True, fp32) samples of fmap bf16 [h*w, C] at pts f32 [P,2] = (x,y) in [0,1]; out bf16 [C]. */
 int mpl_region_sample_mean(const void* fmap, const float* pts, int P, int h, int w, int C, void* out, void* stream);
 
+/* GeoRegionSampler (model/rp_sampler/GeoSampler.py:162-345, behind --region_geo_sampler): the
+ * non-GEMM steps. A stage's point set is a bf16 "point table" [R regions, N points, ld]: d feature columns, the two
+ * normalised coordinates (row / H, col / W), zeros up to ld (ld % 8 == 0, ld >= d + 2) -- torch.cat([fea, xy], -1) of
+ * :302-303 padded into a GEMM operand. Rounding points: the eager bf16 reference's. Ties: FPS = first maximum (torch.max
+ * on CPU), kNN = the k smallest by (distance, index), listed in that order (the reference's topk(sorted=False) leaves
+ * the choice among equal distances open).
+ *   mpl_geo_point_table: point_sample :31-56,263-276. fmap bf16 [n_img, h*w, C], img_of_region int [R], pts f32
+ *                        [R, P, 2] = (row / H, col / W) -> table [R, P, ld]
+ *   mpl_geo_fps:         farthest_point_sample :59-80 from start[r]; xy = table + d (row pitch ld); N <= 1024
+ *                        -> fps_idx int [R, S]
+ *   mpl_geo_knn:         square_distance + topk :101-136 of the S anchors fps_idx among the N points -> knn_idx int [R, S, k]
+ *   mpl_geo_group:       :302-308. row (r, s, j): a1[row, 0:ld] = table[r, knn] - table[r, fps] (bf16; the operand of
+ *                        diff_projector), a2[row, ld:2ld] = table[r, fps] (a2 bf16 [R*S*k, 2*ld]; its first half is the
+ *                        diff_projector GEMM's output: the operand of the agg_projector's 1x1 conv)
+ *   mpl_geo_ln_pool:     ConvReLULN1D's LayerNorm :152-156 + AvgPool1d(k) (mode 0) / AdaptiveMaxPool1d(1) (mode 1) :317
+ *                        over y bf16 [R*S, k, D] (ReLU applied by the GEMM epilogue) -> out[R*S, 0:D] (row pitch ldo);
+ *                        with xy_src (= stage table + d, pitch ld_src) also the anchors' coordinates and zero padding:
+ *                        out is then the next stage's point table. */
+int mpl_geo_point_table(const void* fmap, const int* img_of_region, const float* pts, int R, int P, int h, int w, int C,
+                        void* table, int ld, void* stream);
+int mpl_geo_fps(const void* xy, long long ld, int R, int N, int S, const int* start, int* fps_idx, void* stream);
+int mpl_geo_knn(const void* xy, long long ld, int R, int N, int S, int k, const int* fps_idx, int* knn_idx, void* stream);
+int mpl_geo_group(const void* table, int ld, int R, int N, int S, int k, const int* fps_idx, const int* knn_idx, void* a1,
+                  void* a2, void* stream);
+int mpl_geo_ln_pool(const void* y, int R, int S, int k, int D, const void* weight, const void* bias, float eps, int mode,
+                    const void* xy_src, long long ld_src, int N, const int* fps_idx, void* out, long long ldo, void* stream);
+
 /* =========================================================================================================
  * Native stack runners: ONE call enqueues every kernel of a sub-model forward (no Python between kernels).
  * Weight structs hold device pointers into the caller's nn.Parameters (read in place; nothing is copied or

@@ -197,6 +197,7 @@ EXPORTS = [
     "mpl_gemm_small", "mpl_col_sum", "mpl_layernorm_bwd", "mpl_act_fwd", "mpl_act_bwd", "mpl_attn_small_bwd",
     "mpl_bilinear_resize_bwd", "mpl_mask_losses_bwd", "mpl_mask_scale_bf16", "mpl_token_pool", "mpl_token_pool_bwd", "mpl_col2im_nhwc", "mpl_zero_tail_rows", "mpl_lora_down_ext", "mpl_lora_pack",
     "mpl_preprocess_images", "mpl_preprocess_band_rows",
+    "mpl_geo_point_table", "mpl_geo_fps", "mpl_geo_knn", "mpl_geo_group", "mpl_geo_ln_pool",
 ]
 _LL_RET = {"mpl_launch_count", "mpl_llama_workspace_bytes", "mpl_clip_workspace_bytes", "mpl_sam_encoder_workspace_bytes",
            "mpl_sam_mask_decoder_workspace_bytes"}

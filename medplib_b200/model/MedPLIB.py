@@ -178,6 +178,13 @@ class MedPLIBModel(nn.Module):
         if getattr(config, "icl_mask_encoder", False):
             self.mask_encoder = M.MaskTokenEncoder(D, getattr(config, "mask_encoder_token_count", 64))
         self.region_fea_adapter = nn.Linear(Dv, D)
+        if getattr(config, "region_geo_sampler", False):
+            # the instantiation the reference keeps commented out (medplib_arch.py:134-142), with its arguments
+            from .geo_sampler import GeoRegionSampler
+            self.region_geo_sampler = GeoRegionSampler(input_dim=Dv, output_dim=D,
+                                                       num_init_point=getattr(config, "max_sample_point", 512) or 512,
+                                                       num_sub_point=[128, 32], num_neighbor=[24, 24],
+                                                       pooler_mode=getattr(config, "sampler_pooler_mode", None) or "max")
         self.max_sample_point = getattr(config, "max_sample_point", 512)
         # MedPLIBMetaModel
         self.vision_pretrained = kwargs.get("vision_pretrained", None)
@@ -468,9 +475,10 @@ class MedPLIBForCausalLM(PreTrainedModel):
     # ------------------------------------------------------------------ vision / glue
     def encode_images(self, images, region_flag=False, region_geo_sampler=False):
         """medplib_arch.py:198-212 -> (raw CLIP features, projected [compressed] features, region feature map)."""
-        if region_geo_sampler:
-            raise _lib.MplError("region_geo_sampler is disabled in the reference (medplib_arch.py:134-142)")
         m = self.get_model()
+        if region_geo_sampler and not hasattr(m, "region_geo_sampler"):
+            raise _lib.MplError("region_geo_sampler requested but the model was built without config.region_geo_sampler "
+                                "(the reference keeps the module commented out, medplib_arch.py:134-142)")
         feats = m.get_vision_tower()(images)
         proj = m.mm_projector
         if isinstance(proj, nn.Linear):
@@ -484,7 +492,9 @@ class MedPLIBForCausalLM(PreTrainedModel):
             x = ops.linear(x, c.proj.weight, bias=c.proj.bias)
         rmap = None
         if region_flag:
-            rmap = ops.linear(feats, m.region_fea_adapter.weight, bias=m.region_fea_adapter.bias)
+            # :204-208 — the geometric sampler reads the raw CLIP features, the default path the adapted ones
+            rmap = feats if region_geo_sampler else ops.linear(feats, m.region_fea_adapter.weight,
+                                                               bias=m.region_fea_adapter.bias)
         return feats, x, rmap
 
     def encode_masks(self, mask_images):
@@ -580,7 +590,8 @@ class MedPLIBForCausalLM(PreTrainedModel):
             feat_blocks = [f for f in img_f]
             per_token = True
         else:
-            raw_f, img_f, rmap = self.encode_images(images, region_flag)
+            geo = region_flag and bool(getattr(self.config, "region_geo_sampler", False))  # medplib_arch.py:229
+            raw_f, img_f, rmap = self.encode_images(images, region_flag, geo)
             feat_blocks = [f for f in img_f]
         region_features = None
         valid = None
@@ -591,11 +602,16 @@ class MedPLIBForCausalLM(PreTrainedModel):
             vsel = torch.tensor(valid, device=rmap.device)
             rmap = rmap[vsel]
             adapter = self.get_model().region_fea_adapter
-            want_grad = labels is not None and torch.is_grad_enabled() and self.training and adapter.weight.requires_grad
+            want_grad = (labels is not None and torch.is_grad_enabled() and self.training
+                         and adapter.weight.requires_grad and not geo)
             raw_samples = [] if want_grad else None
-            region_features = self.extract_region_feature(rmap, region_masks,
-                                                          raw_feature_map=raw_f[vsel] if want_grad else None,
-                                                          raw_out=raw_samples)
+            if geo:  # medplib_arch.py:285-289
+                region_features = self.get_model().region_geo_sampler(rmap, region_masks, original_dtype=raw_f.dtype,
+                                                                      return_dtype=img_f.dtype)
+            else:
+                region_features = self.extract_region_feature(rmap, region_masks,
+                                                              raw_feature_map=raw_f[vsel] if want_grad else None,
+                                                              raw_out=raw_samples)
 
         # ---- host-side plan: one int per output row
         D = self.config.hidden_size

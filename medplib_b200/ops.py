@@ -483,3 +483,74 @@ def moe_route_small(x, wg, k, capacity, ln_weight=None, ln_eps=1e-5, noise=None)
                                        _ptr(out["tok_of_slot"]), _ptr(out["gate_of_slot"]), _stream()),
                "mpl_moe_route_small")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ GeoRegionSampler (f-4)
+def geo_point_table(fmaps, img_of_region, pts, h, w, ld):
+    """point_sample of GeoSampler.py:263-276 into a stage-0 point table. fmaps bf16 [n_img, h*w, C]; img_of_region int32
+    [R]; pts f32 [R, P, 2] = (row / H, col / W) -> bf16 [R, P, ld] = [features | row / H | col / W | 0...]."""
+    lib = _lib.load()
+    _req(fmaps, bf16, "fmaps"); _req(pts, torch.float32, "pts"); _req(img_of_region, torch.int32, "img_of_region")
+    assert fmaps.is_contiguous() and pts.is_contiguous() and fmaps.shape[1] == h * w
+    R, P, _ = pts.shape
+    C = fmaps.shape[-1]
+    table = torch.empty((R, P, ld), dtype=bf16, device=fmaps.device)
+    _lib.check(lib.mpl_geo_point_table(_ptr(fmaps), _ptr(img_of_region), _ptr(pts), R, P, h, w, C, _ptr(table), ld,
+                                       _stream()), "mpl_geo_point_table")
+    return table
+
+
+def geo_fps(table, d, S, start):
+    """farthest_point_sample (:59-80) over the coordinates of a point table [R, N, ld] -> int32 [R, S]."""
+    lib = _lib.load()
+    _req(table, bf16, "table"); _req(start, torch.int32, "start")
+    R, N, ld = table.shape
+    assert table.is_contiguous() and start.shape == (R,)
+    out = torch.empty((R, S), dtype=torch.int32, device=table.device)
+    xy = ctypes.c_void_p(table.data_ptr() + 2 * d)
+    _lib.check(lib.mpl_geo_fps(xy, ctypes.c_longlong(ld), R, N, S, _ptr(start), _ptr(out), _stream()), "mpl_geo_fps")
+    return out
+
+
+def geo_knn(table, d, fps_idx, k):
+    """knn_point (:124-136): the k nearest of the table's N points to every anchor -> int32 [R, S, k]."""
+    lib = _lib.load()
+    _req(table, bf16, "table"); _req(fps_idx, torch.int32, "fps_idx")
+    R, N, ld = table.shape
+    S = fps_idx.shape[1]
+    assert table.is_contiguous() and fps_idx.is_contiguous()
+    out = torch.empty((R, S, k), dtype=torch.int32, device=table.device)
+    xy = ctypes.c_void_p(table.data_ptr() + 2 * d)
+    _lib.check(lib.mpl_geo_knn(xy, ctypes.c_longlong(ld), R, N, S, k, _ptr(fps_idx), _ptr(out), _stream()), "mpl_geo_knn")
+    return out
+
+
+def geo_group(table, fps_idx, knn_idx):
+    """:302-308 -> (a1 [R*S*k, ld] = local - anchor, a2 [R*S*k, 2*ld] with the anchor rows in its second half)."""
+    lib = _lib.load()
+    R, N, ld = table.shape
+    _, S, k = knn_idx.shape
+    a1 = torch.empty((R * S * k, ld), dtype=bf16, device=table.device)
+    a2 = torch.empty((R * S * k, 2 * ld), dtype=bf16, device=table.device)
+    _lib.check(lib.mpl_geo_group(_ptr(table), ld, R, N, S, k, _ptr(fps_idx), _ptr(knn_idx), _ptr(a1), _ptr(a2),
+                                 _stream()), "mpl_geo_group")
+    return a1, a2
+
+
+def geo_ln_pool(y, R, S, k, weight, bias, eps, mode, table=None, d=None, fps_idx=None, ldo=None):
+    """LayerNorm + pool over the k neighbours (:152-156, 317). y bf16 [R*S*k, D] -> [R, S, ldo]; with ``table`` the
+    result is the next stage's point table (anchor coordinates + padding appended)."""
+    lib = _lib.load()
+    _req(y, bf16, "y"); _req(weight, bf16, "weight"); _req(bias, bf16, "bias")
+    D = y.shape[-1]
+    assert y.is_contiguous() and y.shape[0] == R * S * k
+    ldo = D if ldo is None else ldo
+    out = torch.empty((R, S, ldo), dtype=bf16, device=y.device)
+    if table is not None:
+        xy, ld_src, N = ctypes.c_void_p(table.data_ptr() + 2 * d), table.shape[2], table.shape[1]
+    else:
+        xy, ld_src, N = None, 0, 0
+    _lib.check(lib.mpl_geo_ln_pool(_ptr(y), R, S, k, D, _ptr(weight), _ptr(bias), ctypes.c_float(eps),
+                                   {"mean": 0, "max": 1}[mode], xy, ctypes.c_longlong(ld_src), N, _ptr(fps_idx),
+                                   _ptr(out), ctypes.c_longlong(ldo), _stream()), "mpl_geo_ln_pool")
+    return out

@@ -98,3 +98,43 @@ def test_bf16_fps_distance_written_out():
     xy = (torch.randint(0, 24, (3, 200, 2)).float() / 24).to(torch.bfloat16)
     c = xy[:, 17:18]
     assert torch.equal(geo.fps_dist_bf16(xy, c), torch.sum((xy - c) ** 2, -1).float())
+
+
+def test_product_module_has_the_reference_parameter_tree():
+    """medplib_b200.model.geo_sampler.GeoRegionSampler: constructor arguments, parameter names and shapes of the
+    reference's module (the golden state dicts ARE the reference's), and no CPU path."""
+    from medplib_b200 import _lib
+    from medplib_b200.model.geo_sampler import GeoRegionSampler
+    for case in CASES:
+        d, out_dim, n_init, subs, neighs = case["cfg"]
+        mod = GeoRegionSampler(input_dim=d, output_dim=out_dim, num_init_point=n_init, num_sub_point=subs,
+                               num_neighbor=neighs, pooler_mode=case["pooler"])
+        mine = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+        assert mine == {k: tuple(v.shape) for k, v in case["sd"].items()}
+        mod.load_state_dict(case["sd"], strict=True)
+    with pytest.raises(_lib.MplError):
+        mod([torch.zeros(576, d)], [[torch.ones(24, 24)]], torch.float32, torch.float32)
+    with pytest.raises(NotImplementedError):
+        GeoRegionSampler(8, 8, 8, [4], [2], pooler_mode="sum")
+
+
+def test_model_instantiates_the_sampler_only_when_configured():
+    from medplib_b200.model import MedPLIBForCausalLM, MedPLIBMoELlamaConfig
+
+    def make(**extra):
+        cfg = MedPLIBMoELlamaConfig(hidden_size=16, intermediate_size=32, num_hidden_layers=1, num_attention_heads=1,
+                                    num_key_value_heads=1, vocab_size=50, max_position_embeddings=64,
+                                    mm_projector_type="mlp2x_gelu", max_sample_point=512)
+        cfg.clip_config = dict(hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=1,
+                               image_size=28, patch_size=14, layer_norm_eps=1e-5)
+        cfg.sam_config = dict(image_size=256, embed_dim=64, depth=1, num_heads=1)
+        cfg.moe = dict(num_experts=[2], top_k_experts=1, capacity_factor=1.5, eval_capacity_factor=2.0, min_capacity=0,
+                       use_residual=False, router_aux_loss_coef=0.01, moe_layers_idx=None, moe_mode="dense", ep_size=1)
+        for k, v in extra.items():
+            setattr(cfg, k, v)
+        return MedPLIBForCausalLM(cfg, test_only=True, seg_token_idx=42)
+
+    assert not hasattr(make().get_model(), "region_geo_sampler")
+    s = make(region_geo_sampler=True, sampler_pooler_mode="mean").get_model().region_geo_sampler
+    assert (s.input_dim, s.output_dim, s.num_init_point, s.num_sub_point, s.num_neighbor, s.pooler_mode) == \
+        (32, 16, 512, [128, 32], [24, 24], "mean")
