@@ -277,7 +277,8 @@ int mpl_add(const void* a, const void* b, int b_is_f32, void* out, long long n, 
 int mpl_bilinear_resize(const void* in, long long in_stride_n, long long in_stride_y, int Hin, int Win, void* out,
                         int out_dtype, int Hout, int Wout, int N, void* stream);
 /* extract_region_feature (model/medplib/model/medplib_arch.py:580-614): mean over P points of the bilinear
- * (align_corners=True, fp32) samples of fmap bf16 [h*w, C] at pts f32 [P,2] = (x,y) in [0,1]; out bf16 [C]. */
+ * (align_corners=True, fp32) samples of fmap bf16 [h*w, C] at pts f32 [P,2] = (x,y) in [0,1] (bf16-representable); the
+ * sampling grid is bf16(2 * pts - 1) as point_sample :51 forms it on the run-dtype coordinates; out bf16 [C]. */
 int mpl_region_sample_mean(const void* fmap, const float* pts, int P, int h, int w, int C, void* out, void* stream);
 
 /* GeoRegionSampler (model/rp_sampler/GeoSampler.py:162-345, behind --region_geo_sampler): the

@@ -3,7 +3,7 @@
 // Linears per stage, flatten_projector and dim_projector run on the tcgen05 / streaming GEMMs (gemm_tcgen05.cu).
 //
 // Data layout: a stage's point set is ONE bf16 "point table" [R regions, N points, ld] whose row is
-//   [ d feature columns | x=row/H | y=col/W | zero padding up to ld ]        (ld = round_up(d + 2, 64))
+//   [ d feature columns | row/H | col/W | zero padding up to ld ]        (ld = round_up(d + 2, 64))
 // i.e. exactly the rows torch.cat([fea, xy], -1) builds at :302-303, padded so that they are GEMM operands as they are.
 //   geo_point_table : point_sample (:31-56, 263-276) -> stage-0 table         one CTA per (region, point)
 //   geo_fps         : farthest_point_sample (:59-80)                          one warp per region, points in registers
@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(128) geo_point_table_kernel(const bf* __restri
                                                               bf* __restrict__ table, int ld) {
   const int rp = blockIdx.x, r = rp / P;
   const float py = bf16_round(pts[2 * rp]), px = bf16_round(pts[2 * rp + 1]);  // .type(original_dtype), flipped to (x, y)
-  const float gx = 2.0f * px - 1.0f, gy = 2.0f * py - 1.0f;
+  // (2.0 * point_coords - 1.0) is formed on the bf16 coordinates before point_sample's .float() (:51): a bf16 grid
+  const float gx = bf16_round(2.0f * px - 1.0f), gy = bf16_round(2.0f * py - 1.0f);
   const float fx = (gx + 1.0f) * 0.5f * (w - 1), fy = (gy + 1.0f) * 0.5f * (h - 1);
   const int x0 = static_cast<int>(floorf(fx)), y0 = static_cast<int>(floorf(fy));
   const float lx = fx - x0, ly = fy - y0;

@@ -423,7 +423,8 @@ __global__ void __launch_bounds__(256) bilinear_kernel(const __nv_bfloat16* __re
 
 // ------------------------------------------------------------------------------------------------- region sample
 // fmap bf16 [h*w, C]; pts f32 [P,2] = (x, y) in [0,1] (already rounded the way the reference rounds them);
-// grid_sample(bilinear, align_corners=True, zeros padding) in fp32 -> bf16 per point -> mean over points -> bf16.
+// grid = bf16(2 * pts - 1); grid_sample(bilinear, align_corners=True, zeros padding) in fp32 -> bf16 per point -> mean
+// over points -> bf16.
 __global__ void __launch_bounds__(128) region_sample_kernel(const __nv_bfloat16* __restrict__ fmap,
                                                             const float* __restrict__ pts, int P, int h, int w, int C,
                                                             __nv_bfloat16* __restrict__ out) {
@@ -431,7 +432,9 @@ __global__ void __launch_bounds__(128) region_sample_kernel(const __nv_bfloat16*
   if (c >= C) return;
   float acc = 0.0f;
   for (int p = 0; p < P; ++p) {
-    const float gx = 2.0f * pts[2 * p] - 1.0f, gy = 2.0f * pts[2 * p + 1] - 1.0f;
+    // point_sample (medplib_arch.py:39-64) forms 2 * coords - 1 on the run-dtype (bf16) coordinates BEFORE its .float():
+    // the grid itself is rounded to bf16 (2 * c is exact, the subtraction is not)
+    const float gx = bf16_round(2.0f * pts[2 * p] - 1.0f), gy = bf16_round(2.0f * pts[2 * p + 1] - 1.0f);
     const float fx = (gx + 1.0f) * 0.5f * (w - 1), fy = (gy + 1.0f) * 0.5f * (h - 1);
     const int x0 = static_cast<int>(floorf(fx)), y0 = static_cast<int>(floorf(fy));
     const float lx = fx - x0, ly = fy - y0;

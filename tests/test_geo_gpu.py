@@ -66,7 +66,7 @@ def _run_both(sd, cfg, pooler, fmaps, masks, draws, dev, tol_ulps, tag):
     tab = tr["table"].cpu()
     assert torch.equal(tab[..., d:d + 2], rec["points"]), "point coordinates"
     assert not bool(tab[..., d + 2:].any()), "table padding"
-    _close(tab[..., :d], rec["features"], 1.0 * BF16_ULP, f"{tag} point features")
+    _close(tab[..., :d], rec["features"], 0.0, f"{tag} point features")  # same rounding points: bit-exact
     for s in range(n_stage):
         assert torch.equal(tr["fps"][s].cpu().long(), rec["fps"][s]), f"FPS indices, stage {s}"
         assert torch.equal(tr["knn"][s].cpu().long(), rec["knn"][s]), f"kNN indices, stage {s}"
@@ -88,7 +88,7 @@ def test_geo_sampler_vs_reference_bf16_run(dev):
     fmaps = [f.to(bf16) for f in case["fmaps"]]
     masks = [[m.long() for m in per] for per in case["masks"]]
     draws = [t for _, t in case["draws"]]
-    out, rec = _run_both(sd, tuple(case["cfg"]), case["pooler"], fmaps, masks, draws, dev, 4.0, "golden")
+    out, rec = _run_both(sd, tuple(case["cfg"]), case["pooler"], fmaps, masks, draws, dev, 1.0, "golden")
     for s in range(len(case["fps"])):
         assert torch.equal(rec["fps"][s], case["fps"][s])
     # the reference's output itself used another (equally valid) choice among tied neighbours: same scale, not equal
@@ -141,7 +141,7 @@ def test_geo_sampler_matches_oracle(dev, pooler, d, out_dim, n_init, subs, neigh
             N = S
     finally:
         torch.randint, torch.randperm = o_ri, o_rp
-    _run_both(sd, (d, out_dim, n_init, subs, neighs), pooler, fmaps, masks, draws, dev, 6.0, f"d={d} {pooler}")
+    _run_both(sd, (d, out_dim, n_init, subs, neighs), pooler, fmaps, masks, draws, dev, 3.0, f"d={d} {pooler}")
 
 
 def test_geo_sampler_no_regions_and_refusals(dev):

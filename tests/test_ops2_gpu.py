@@ -228,7 +228,7 @@ def test_region_sample_mean(dev):
         nz = (m.nonzero() / torch.tensor([[24, 24]])).to(bf16).float()  # the reference casts coords to the run dtype
         pts = nz.flip(1)
         out = ops.region_sample_mean(fmap.to(dev), pts.to(dev).reshape(-1, 2), 24, 24)
-        _close(out, r, 2 ** -5, "region")  # the CPU bf16 mean does not accumulate in a defined order
+        _close(out, r, 2 ** -9, "region")  # half a bf16 ulp (measured: bit-exact once the sampling grid is rounded to bf16)
 
 
 @pytest.mark.parametrize("M,N,K,nb", [(8, 4096, 4096, 3), (1, 4096, 4096, 1), (5, 512, 264, 1)])
