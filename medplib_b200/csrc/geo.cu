@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(128) geo_point_table_kernel(const bf* __restri
 constexpr int GEO_PPL = 32;
 __global__ void __launch_bounds__(32) geo_fps_kernel(const bf* __restrict__ xy, long long ld, int N, int S,
                                                      const int* __restrict__ start, int* __restrict__ fps_idx) {
+  // the S iterations are one dependent chain: the centroid of an iteration is read back from shared memory (a global
+  // load there cost ~0.8 us of L2 latency per iteration: 219 us for S = 128, profiles/r02_ncu_geo.md)
+  __shared__ float2 s_xy[32 * GEO_PPL];
   const int r = blockIdx.x, lane = threadIdx.x;
   const bf* base = xy + static_cast<long long>(r) * N * ld;
   float px[GEO_PPL], py[GEO_PPL], dist[GEO_PPL];
@@ -79,11 +82,14 @@ __global__ void __launch_bounds__(32) geo_fps_kernel(const bf* __restrict__ xy, 
     px[i] = n < N ? __bfloat162float(base[n * ld]) : 0.0f;
     py[i] = n < N ? __bfloat162float(base[n * ld + 1]) : 0.0f;
     dist[i] = n < N ? 1e10f : -1.0f;
+    s_xy[n] = make_float2(px[i], py[i]);
   }
+  __syncwarp();
   int far = start[r];
   for (int s = 0; s < S; ++s) {
     if (lane == 0) fps_idx[r * S + s] = far;
-    const float cx = __bfloat162float(base[far * ld]), cy = __bfloat162float(base[far * ld + 1]);
+    const float2 c = s_xy[far];
+    const float cx = c.x, cy = c.y;
     float best = -2.0f;
     int bi = 0x7fffffff;
 #pragma unroll

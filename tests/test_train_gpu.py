@@ -21,7 +21,7 @@ TOL = 1e-1
 
 
 def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,down_proj", sft=SFT, dropout=0.0,
-          moe_layers=None, top_k=1):
+          moe_layers=None, top_k=1, lora_r=8):
     import test_model_gpu as tm
     from medplib_b200 import train
     m, _, ocfg = tm.build(dev, moe_layers=moe_layers)
@@ -31,7 +31,7 @@ def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,d
     m.router_aux_loss_coef = aux
     m.ce_loss_weight, m.bce_loss_weight, m.dice_loss_weight = W["ce"], W["bce"], W["dice"]
     m.iou_loss_weight, m.focal_loss_weight = W["iou"], W["focal"]
-    names = train.attach_lora(m, r=8, lora_alpha=16, lora_dropout=dropout, target_modules=lora_targets)
+    names = train.attach_lora(m, r=lora_r, lora_alpha=16, lora_dropout=dropout, target_modules=lora_targets)
     if moe_layers is None and lora_targets.count(",") == 4:
         assert len(names) == 2 * 2 + 2 * 2 * 3
     train.set_trainable(m, sft)
@@ -47,7 +47,7 @@ def build(dev, cf=1.5, aux=0.01, lora_targets="q_proj,v_proj,gate_proj,up_proj,d
     m.train()
     sd = {k: v.detach().cpu().float() for k, v in m.state_dict().items()}
     sd.update({k: v.detach().cpu().float() for k, v in m.named_buffers()})
-    sd["lora_scaling"] = 2.0
+    sd["lora_scaling"] = 16.0 / lora_r  # peft: lora_alpha / r
     ocfg["llama"]["moe"] = dict(m.config.moe)
     return m, sd, ocfg
 
@@ -298,6 +298,16 @@ def test_stage2_recipe_dense_layer_all_lora_targets_and_norm_weights(dev):
              lora_targets="q_proj,k_proj,v_proj,o_proj,gate_proj,up_proj,down_proj",
              sft="lm_head,embed_tokens,input_layernorm,post_attention_layernorm,model.norm,wg,mask_decoder,"
                  "text_hidden_fcs,mm_projector")
+
+
+def test_stage2_recipe_rank_16(dev):
+    """scripts/train_stage2.sh trains with --lora_r 16 (lora_alpha 16: scaling 1.0) on all seven projections: the
+    rank-16 adapters take the separate-pass kernels (the GEMM-fused forms are rank-8 only), same losses and gradients."""
+    m, tr, sd, names = run_case(dev, True, 1.5, False, 0.01, moe_layers=[1], lora_r=16,
+                                lora_targets="q_proj,k_proj,v_proj,o_proj,gate_proj,up_proj,down_proj",
+                                sft="lm_head,embed_tokens,input_layernorm,post_attention_layernorm,model.norm,wg,"
+                                    "mask_decoder,text_hidden_fcs,mm_projector")
+    assert any(p.shape[0] == 16 for n, p in m.named_parameters() if "lora_A" in n)
 
 
 def test_lora_dropout(dev):
