@@ -128,18 +128,26 @@ __device__ __forceinline__ TileSpace make_tile_space(const GemmDevParams& p, int
   return ts;
 }
 
+// SiLU(gate) of the dual epilogue: fast divide by default (see apply_act); -DMPL_SILU_IEEE_DIV restores div.rn
+#ifdef MPL_SILU_IEEE_DIV
+#define MPL_SILU_DIV(a, b) ((a) / (b))
+#else
+#define MPL_SILU_DIV(a, b) __fdividef((a), (b))
+#endif
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case MPL_ACT_GELU:
       return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    // __fdividef (MUFU.RCP + FMUL, <= 2 ulp of fp32, no slow-path call): an IEEE divide carries a predicated CALL per
+    // element that keeps the scheduler from interleaving the 32 elements of a chunk; the result is rounded to bf16
     case MPL_ACT_QUICK_GELU:
-      return v / (1.0f + __expf(-1.702f * v));
+      return __fdividef(v, 1.0f + __expf(-1.702f * v));
     case MPL_ACT_RELU:
       return fmaxf(v, 0.0f);
     case MPL_ACT_SILU:
-      return v / (1.0f + __expf(-v));
+      return __fdividef(v, 1.0f + __expf(-v));
     case MPL_ACT_SIGMOID:
-      return 1.0f / (1.0f + __expf(-v));
+      return __fdividef(1.0f, 1.0f + __expf(-v));
     default:
       return v;
   }
@@ -239,7 +247,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmDevParams& p, const __nv
         // reference: down(silu(gate(x)) * up(x)) with every intermediate rounded to bf16
         const float g = bf16_round(__uint_as_float(r[j]));
         const float u = bf16_round(__uint_as_float(r2[j]));
-        const float s = bf16_round(g / (1.0f + __expf(-g)));
+        const float s = bf16_round(MPL_SILU_DIV(g, 1.0f + __expf(-g)));
         v[j] = s * u;
       }
     } else {
@@ -251,13 +259,46 @@ __device__ __forceinline__ void epilogue_rows(const GemmDevParams& p, const __nv
     if (nc >= nlim || !row_ok) continue;
     const bool full = (nc + 32 <= nlim);
     if (bias != nullptr) {
+      if (full && (reinterpret_cast<uintptr_t>(bias + nc) & 15) == 0) {  // four 16-byte broadcast loads instead of 32 scalar ones
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (full || nc + j < nlim) v[j] += __bfloat162float(bias[nc + j]);
+        for (int q = 0; q < 4; ++q) {
+          const uint4 bw = *reinterpret_cast<const uint4*>(bias + nc + q * 8);
+          const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&bw);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(bh[e]);
+            v[q * 8 + 2 * e] += f.x;
+            v[q * 8 + 2 * e + 1] += f.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nc + j < nlim) v[j] += __bfloat162float(bias[nc + j]);
+      }
     }
     if (p.act != MPL_ACT_NONE) {
+      // The activation is chosen ONCE per chunk and each case is a straight-line unrolled loop: with the switch inside
+      // the element loop every element was its own basic block, i.e. 32 serial exp / divide dependency chains on the
+      // one epilogue warp a scheduler has (CLIP fc1 at M = 577: 42 us against 16 us without the activation).
+      if (!f32) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(f32 ? v[j] : bf16_round(v[j]), p.act);
+        for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+      }
+      switch (p.act) {
+#define MPL_ACT_LOOP(A)                                       \
+  case A:                                                     \
+    _Pragma("unroll") for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], A); \
+    break;
+        MPL_ACT_LOOP(MPL_ACT_GELU)
+        MPL_ACT_LOOP(MPL_ACT_QUICK_GELU)
+        MPL_ACT_LOOP(MPL_ACT_RELU)
+        MPL_ACT_LOOP(MPL_ACT_SILU)
+        MPL_ACT_LOOP(MPL_ACT_SIGMOID)
+#undef MPL_ACT_LOOP
+        default:
+          break;
+      }
     }
     if (p.row_scale != nullptr) {
 #pragma unroll
