@@ -102,7 +102,10 @@ def timing(B=1, layer=5):
     #   19+s (s>0) = after it; step 0: 16/17 around the barrier inside the attention phase, 18 = attention done,
     #   3 = after the barrier that closes the attention; 23/24 = router start / logits+softmax done
     us = lambda a, b: (full[:, b] - full[:, a]) / 1e3
-    rows = [("s0 stage (RMSNorm)", 0, 1), ("s0 q,k,v tiles", 1, 2), ("s0 -> barrier", 2, 16), ("bar1", 16, 17),
+    rows = [("  s0: issue cp.async", 0, 25), ("  s0: ln weights (mbar)", 25, 26), ("  s0: cp.async wait", 26, 27),
+            ("  s0: sumsq + sync", 27, 28), ("  s0: normalise", 28, 1), ("  s2: router dots", 23, 29),
+            ("  s2: router sync", 29, 30), ("  s2: softmax", 30, 24),
+            ("s0 stage (RMSNorm)", 0, 1), ("s0 q,k,v tiles", 1, 2), ("s0 -> barrier", 2, 16), ("bar1", 16, 17),
             ("attention", 17, 18), ("bar2", 18, 3), ("s1 stage", 4, 5), ("s1 o-proj tiles", 5, 6), ("bar3", 7, 20),
             ("s2 stage (RMSNorm)", 8, 23), ("s2 router logits", 23, 24), ("s2 scan + publish", 24, 9),
             ("s2 gate/up tiles", 9, 10), ("bar4", 11, 21), ("s3 down tiles", 13, 14), ("bar5", 15, 22)]
