@@ -1,7 +1,8 @@
 """GPU end-to-end parity of MedPLIBForCausalLM (evaluate / model_forward(inference=True) / generate) against the CPU
 oracle pipeline on a small random-init model with the reference's architecture (MoE top-1, 2 experts, SAM adapters).
 
-Stated tolerances (bf16 path vs bf16 oracle): step logits and mask logits within 6e-2 * max|ref|; greedy token ids
+Stated tolerances (bf16 path vs bf16 oracle; measured values in profiles/r02_parity_errors.md): hidden states and mask
+logits within 4e-2 * max|ref|, step logits within 3.5e-2 (measured 2.5e-2 / 2.4e-2 / 2.0e-2); greedy token ids
 bit-exact wherever the oracle's top-2 logit margin exceeds that noise; mask indices (logit > logit(0.1), the
 reference's `sigmoid(pred) > 0.1`, vqa_infer.py:565) bit-exact wherever the oracle's logit is farther than the noise
 from the threshold."""
@@ -80,20 +81,20 @@ def test_evaluate_matches_oracle(dev):
     gen = m.generate(input_ids=ids.to(dev), images=clip_img.to(dev), max_new_tokens=6, output_hidden_states=True,
                      return_dict_in_generate=True, output_scores=True, forced_tokens=force_all, eos_token_id=-1)
     assert torch.equal(gen.sequences.cpu(), ref["output_ids"])
-    _check(gen.last_hidden_state, ref["hidden"], 6e-2, "hidden states")
+    _check(gen.last_hidden_state, ref["hidden"], 4e-2, "hidden states")
     for s, (got, want) in enumerate(zip(gen.scores, ref["step_logits"])):
-        _check(got, want, 6e-2, f"step {s} logits")
+        _check(got, want, 3.5e-2, f"step {s} logits")
         top2 = want[0].topk(2).values
-        if s not in forced and (top2[0] - top2[1]) > 6e-2 * want.abs().max():
+        if s not in forced and (top2[0] - top2[1]) > 4e-2 * want.abs().max():  # 2 x the measured logit noise
             assert int(got[0].argmax()) == int(want[0].argmax()), f"argmax at step {s}"
     out_ids, masks = m.evaluate(clip_img.to(dev), sam_img.to(dev), ids.to(dev), [(256, 256)], [label],
                                 max_new_tokens=6, forced_tokens=force_all)
     assert torch.equal(out_ids.cpu(), ref["output_ids"])
     assert masks[0].shape == (1, 70, 90)
-    _check(masks[0], ref["pred_masks"][0], 8e-2, "mask logits")
+    _check(masks[0], ref["pred_masks"][0], 4e-2, "mask logits")
     thr = math.log(0.1 / 0.9)
     want = ref["pred_masks"][0].float()
-    far = (want - thr).abs() > 8e-2 * want.abs().max()
+    far = (want - thr).abs() > 4e-2 * want.abs().max()
     assert far.float().mean() > 0.5
     assert torch.equal((masks[0].float().cpu() > thr)[far], (want > thr)[far]), "mask indices"
 
@@ -108,7 +109,7 @@ def test_grounding_forward_matches_oracle(dev):
             labels=None, attention_mask=torch.ones_like(ids, dtype=torch.bool).to(dev), offset=None,
             masks_list=[label], label_list=[label], resize_list=[(256, 256)], inference=True)
     assert set(out) == {"pred_masks", "gt_masks"}
-    _check(out["pred_masks"][0], ref["pred_masks"][0], 8e-2, "mask logits")
+    _check(out["pred_masks"][0], ref["pred_masks"][0], 3e-2, "mask logits")
 
 
 def test_gate_hooks_and_lm_forward(dev):
@@ -228,12 +229,12 @@ def test_icl_separate_mode_matches_oracle(dev):
             mask_images=[x.to(dev) for x in mask_imgs], image_token_types=types_, image_token_lengths=lengths,
             icl_image_counts=[3])
     assert out["pred_masks"][0].shape == (1, 70, 90)
-    _check(out["pred_masks"][0], ref["pred_masks"][0], 8e-2, "ICL mask logits")
+    _check(out["pred_masks"][0], ref["pred_masks"][0], 3.5e-2, "ICL mask logits")
     # the spliced prompt itself (compressor + mask encoder + sentinel order) against the oracle's inputs_embeds
     _, _, _, emb, _ = m.prepare_inputs_labels_for_multimodal(
         ids.to(dev), torch.ones_like(ids, dtype=torch.bool).to(dev), None, None, [c.to(dev) for c in clip_imgs], None,
         None, mask_images=[x.to(dev) for x in mask_imgs], image_token_types=types_)
-    _check(emb, ref["inputs_embeds"], 4e-2, "ICL inputs_embeds")
+    _check(emb, ref["inputs_embeds"], 1.6e-2, "ICL inputs_embeds")
 
 
 @pytest.mark.parametrize("case", [0, 1])
@@ -279,12 +280,12 @@ def test_splice_matches_reference_golden(dev, case):
     d = gi.splice_inputs(use_se)
     emb, lab, am = run(d, d["feats_r"], d["region_masks"], d["valid"])
     assert torch.equal(lab.cpu(), g["lab1"]) and torch.equal(am.cpu(), g["am1"])
-    _check(emb, g["emb1"], 2e-2, "region splice")
+    _check(emb, g["emb1"], 6e-3, "region splice")
     d2 = dict(d, ids=d["ids2"])
     emb, lab, am = run(d2, d["feats"])
     assert torch.equal(lab.cpu(), g["lab2"]) and torch.equal(am.cpu(), g["am2"])
-    _check(emb, g["emb2"], 2e-2, "plain splice")
+    _check(emb, g["emb2"], 6e-3, "plain splice")
     di = gi.icl_splice_inputs(use_se)
     emb, lab, am = run(di, di["img"], mask_images=[x.to(dev) for x in di["msk"]], image_token_types=di["types"])
     assert torch.equal(lab.cpu(), g["lab3"]) and torch.equal(am.cpu(), g["am3"])
-    _check(emb, g["emb3"], 2e-2, "ICL splice")
+    _check(emb, g["emb3"], 6e-3, "ICL splice")

@@ -215,7 +215,7 @@ def test_attention_prefill(dev, B, H, Tq, Tk, d, causal, masked):
     ref = _ref_attention(q, k, v, scale, causal, kv_mask)
     o = ops.attention(q.to(dev), k.to(dev), v.to(dev), scale, causal=causal,
                       kv_mask=kv_mask.to(dev) if kv_mask is not None else None)
-    _close(o, ref, 2e-2, "attention")
+    _close(o, ref, 8e-3, "attention")  # 2 bf16 ulp (measured 0.97)
 
 
 @pytest.mark.parametrize("B,H,hw,d", [(4, 12, 14, 64), (1, 12, 16, 64)])
@@ -232,7 +232,7 @@ def test_attention_relpos(dev, B, H, hw, d):
     scale = d ** -0.5
     ref = _ref_attention(q, k, v, scale, bias=bias)
     o = ops.attention(q.to(dev), k.to(dev), v.to(dev), scale, rel_h=rel_h.to(dev), rel_w=rel_w.to(dev))
-    _close(o, ref, 2e-2, "attention relpos")
+    _close(o, ref, 8e-3, "attention relpos")
 
 
 @pytest.mark.parametrize("B,H,Tk,use_dev", [(8, 32, 615, False), (8, 32, 1127, True), (1, 32, 40, False), (2, 4, 3, True)])
@@ -252,10 +252,10 @@ def test_attention_decode(dev, B, H, Tk, use_dev):
     for _ in range(2):  # twice: the counters are self-cleaning
         o2 = ops.attention(q.to(dev), kd[:, :, :Tk].permute(0, 2, 1, 3), vd[:, :, :Tk].permute(0, 2, 1, 3), scale,
                            scratch=scratch)
-        _close(o2, ref, 2e-2, "decode attention split-K")
+        _close(o2, ref, 8e-3, "decode attention split-K")
     if use_dev:
         tk_dev = torch.tensor([Tk], dtype=torch.int32, device=dev)
         o = ops.attention(q.to(dev), kd.permute(0, 2, 1, 3), vd.permute(0, 2, 1, 3), scale, tk_dev=tk_dev)
     else:
         o = ops.attention(q.to(dev), kd[:, :, :Tk].permute(0, 2, 1, 3), vd[:, :, :Tk].permute(0, 2, 1, 3), scale)
-    _close(o, ref, 2e-2, "decode attention")
+    _close(o, ref, 8e-3, "decode attention")

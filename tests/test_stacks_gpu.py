@@ -63,23 +63,23 @@ def test_llama_stack_prefill_and_decode(dev, name, B, T, steps, padded):
         # of a token with a clear margin is an error.
         for l, lg in enumerate(ref["gate_logits"]):
             got = out["gate_logits"][l].cpu()
-            _close(got[margin_ok], lg[margin_ok], 6e-2 * (1 + 0.5 * l), f"router logits L{l}")  # bf16 noise grows with depth
+            _close(got[margin_ok], lg[margin_ok], 1e-2 * (1 + 0.75 * l), f"router logits L{l}")  # bf16 noise grows with depth
             m = (lg[:, 0] - lg[:, 1]).abs()
             flip = (got.argmax(-1) != lg.argmax(-1)) & margin_ok
             assert bool((m[flip] <= 0.05 * lg.abs().max()).all()), f"layer {l}: expert flip despite a clear margin"
             margin_ok &= ~flip.reshape(B, T).cummax(dim=1).values.reshape(-1)
         assert margin_ok.float().mean() > 0.4
     keep = margin_ok.reshape(B, T)
-    _close(out["last_hidden_state"].cpu()[keep], ref["last_hidden_state"][keep], 4e-2, "last hidden")
+    _close(out["last_hidden_state"].cpu()[keep], ref["last_hidden_state"][keep], 3e-2, "last hidden")
     for l in range(cfg["num_layers"]):
-        _close(out["hidden_states"][l].cpu()[keep], ref["hidden_states"][l][keep], 4e-2, f"hidden {l}")
+        _close(out["hidden_states"][l].cpu()[keep], ref["hidden_states"][l][keep], 2.5e-2, f"hidden {l}")
     if cfg["moe"] and bool(margin_ok.all()):
         for l in range(cfg["num_layers"]):
             assert torch.equal(out["exp_counts"][l].cpu().long(), ref["exp_counts"][l])
             _close(out["l_aux"][l], ref["moe_losses"][l], 1e-2, "l_aux")
     # KV cache contents
     kref = torch.stack([kv[0] for kv in ref["past_key_values"]])
-    _close(cache.k[:, :, :, :T].cpu().permute(1, 3, 0, 2, 4)[keep], kref.permute(1, 3, 0, 2, 4)[keep], 4e-2, "k cache")
+    _close(cache.k[:, :, :, :T].cpu().permute(1, 3, 0, 2, 4)[keep], kref.permute(1, 3, 0, 2, 4)[keep], 2e-2, "k cache")
     # decode steps through the cache (fresh inputs per step; compares per-step hidden states)
     kv = ref["past_key_values"]
     seq_ok = keep.all(1) if padded is False else (keep | ~valid).all(1)
@@ -97,7 +97,7 @@ def test_llama_stack_prefill_and_decode(dev, name, B, T, steps, padded):
                 seq_ok &= ~flip  # the sequence's cache now differs from the oracle's
         ok = seq_ok
         if ok.any():
-            _close(o["last_hidden_state"].cpu()[ok], r["last_hidden_state"][ok], 4e-2, f"decode step {s}")
+            _close(o["last_hidden_state"].cpu()[ok], r["last_hidden_state"][ok], 2.5e-2, f"decode step {s}")
     assert cache.len == T + steps
 
 
@@ -119,7 +119,7 @@ def test_llama_training_capacity_drop(dev):
     out = eng.forward(x.to(dev).clone(), eng.new_cache(B, T), training=True, moe_noise=[u.to(dev)], want_router=True)
     lg = ref["gate_logits"][0]
     ok = ((lg[:, 0] - lg[:, 1]).abs() > 0.05 * lg.abs().max()).reshape(B, T)
-    _close(out["last_hidden_state"].cpu()[ok], ref["last_hidden_state"][ok], 4e-2, "train forward with drops")
+    _close(out["last_hidden_state"].cpu()[ok], ref["last_hidden_state"][ok], 1.5e-2, "train forward with drops")
 
 
 CLIP_CFGS = {
@@ -139,7 +139,7 @@ def test_clip_stack(dev, name, B):
     ref = clip.vision_tower(sd, "", img, cfg, select_layer=-2)
     eng = engine.ClipEngine(_to(sd, dev), cfg, "", select_layer=-2)
     out = eng.forward(img.to(dev))
-    _close(out, ref, 4e-2, "clip features")
+    _close(out, ref, 1.7e-2, "clip features")
 
 
 def test_sam_encoder_stack_vs_reference_golden(dev):
@@ -153,7 +153,7 @@ def test_sam_encoder_stack_vs_reference_golden(dev):
     eng = engine.SamEncoderEngine(_to(sd, dev), cfg, "")
     out = eng.forward(gi.sam_encoder_images().to(dev))  # [B, 256, O] token-major
     ref = g["out"].permute(0, 2, 3, 1).reshape(out.shape)
-    _close(out, ref, 6e-2, "sam encoder vs reference fp32")
+    _close(out, ref, 2e-2, "sam encoder vs reference fp32")
 
 
 @pytest.mark.parametrize("embed,heads,depth,B", [(128, 2, 4, 2), (768, 12, 3, 1)])
@@ -166,7 +166,7 @@ def test_sam_encoder_stack(dev, embed, heads, depth, B):
     ref = sam.image_encoder(sd, "", img, num_heads=heads)
     eng = engine.SamEncoderEngine(_to(sd, dev), cfg, "")
     out = eng.forward(img.to(dev))
-    _close(out, ref.permute(0, 2, 3, 1).reshape(out.shape), 5e-2, "sam encoder")
+    _close(out, ref.permute(0, 2, 3, 1).reshape(out.shape), 3e-2, "sam encoder")
 
 
 def test_sam_mask_decoder_stack(dev):
@@ -184,9 +184,9 @@ def test_sam_mask_decoder_stack(dev):
     _close(eng._keep[0], dpe[0].permute(1, 2, 0).reshape(256, 256), 1e-5, "dense pe")
     tok_major = emb[0].permute(1, 2, 0).reshape(256, 256).contiguous()
     mask, iou = eng.forward(tok_major.to(dev), text.reshape(-1).to(dev))
-    _close(mask, ref_m, 5e-2, "low-res mask vs bf16 oracle")
-    _close(iou, ref_iou, 5e-2, "iou vs bf16 oracle")
-    _close(mask, g["masks"], 8e-2, "low-res mask vs reference fp32 golden")
+    _close(mask, ref_m, 2.5e-2, "low-res mask vs bf16 oracle")
+    _close(iou, ref_iou, 3.5e-2, "iou vs bf16 oracle")
+    _close(mask, g["masks"], 3e-2, "low-res mask vs reference fp32 golden")
     # mask indices (sigmoid > 0.1 <=> logit > log(1/9)) agree with the reference away from the threshold
     thr = -2.1972246
     far = (g["masks"] - thr).abs() > 0.05 * g["masks"].abs().max()

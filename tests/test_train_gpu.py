@@ -505,7 +505,7 @@ def test_lisa_dense_twin_inference_and_train_step(dev):
     out = m(images=sam_img.to(dev), images_clip=clip_img.to(dev), input_ids=ids.to(dev), region_masks=None,
             labels=None, attention_masks=torch.ones_like(ids, dtype=torch.bool).to(dev), offset=None,
             masks_list=[label], label_list=[label], resize_list=[(256, 256)], inference=True)
-    tm._check(out["pred_masks"][0], ref["pred_masks"][0], 8e-2, "LISA mask logits")
+    tm._check(out["pred_masks"][0], ref["pred_masks"][0], 3.5e-2, "LISA mask logits")
     # ---- one train step
     train.attach_lora(m, r=8, lora_alpha=16, target_modules="q_proj,v_proj")
     train.set_trainable(m, "lm_head,embed_tokens,mask_decoder,text_hidden_fcs")
