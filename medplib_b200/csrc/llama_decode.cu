@@ -168,6 +168,12 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Grid barrier for the consumer warps (the producer thread never waits here). Same structure as cooperative
 // groups' grid.sync(): CTA barrier, one thread fences + arrives + spins + fences (the gpu-scope fence also invalidates
 // this SM's L1, so plain loads after the barrier see the other CTAs' writes), CTA barrier.
@@ -178,9 +184,16 @@ __device__ __noinline__ void grid_sync(unsigned int* ctr, unsigned int& target) 
     // release (cumulative over the CTA's writes ordered by the bar.sync above) ... relaxed polling ... one acquire
     // fence, which also invalidates this SM's L1 (SASS: MEMBAR.ALL.GPU + RED / LDG.STRONG / MEMBAR + CCTL.IVALL)
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+#ifdef MPL_DK_BARRIER_FENCE  // (round-2 form: relaxed polling + one acquire fence)
     while (ld_relaxed_u32(ctr) < target) {
     }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#else
+    // acquire polling (the form of CUTLASS's GenericBarrier::wait_*): the load that observes the last arrival is the
+    // acquire operation itself, no trailing MEMBAR on the critical path of the last arriver
+    while (ld_acquire_u32(ctr) < target) {
+    }
+#endif
   }
   consumer_sync();
 }
@@ -499,13 +512,19 @@ __device__ __forceinline__ void attention_phase(const DecParams& p, int layer, i
         mine[D + 1] = l;
       }
     }
-    __threadfence();
+    // ONE acq_rel atomic by lane 0 instead of a sequentially-consistent fence by all 32 lanes on either side of a relaxed
+    // one (two MEMBAR.SC.GPU per item on the critical path of the phase): __syncwarp orders the lanes' partial stores
+    // before the release, the last arriver's acquire before the merge's loads (which are ld.cg: L2, never a stale L1 line)
     __syncwarp();
     int last = 0;
-    if (lane == 0) last = (atomicAdd(&p.attn_cnt[it.bh], 1) == nsplit - 1);
+    if (lane == 0) {
+      unsigned int old;
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.attn_cnt + it.bh) : "memory");
+      last = old == static_cast<unsigned int>(nsplit - 1);
+    }
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) continue;
-    __threadfence();
+    __syncwarp();
     // this warp merges all splits. Lane zz first fetches (max, sum) of split zz -- one round trip for all splits --
     // then every lane accumulates its 4 dims over the splits, 8 splits' loads in flight at a time.
     const float mz = lane < nsplit ? __ldcg(part + lane * (D + 4) + D) : -INFINITY;
