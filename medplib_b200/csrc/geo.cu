@@ -6,7 +6,7 @@
 //   [ d feature columns | row/H | col/W | zero padding up to ld ]        (ld = round_up(d + 2, 64))
 // i.e. exactly the rows torch.cat([fea, xy], -1) builds at :302-303, padded so that they are GEMM operands as they are.
 //   geo_point_table : point_sample (:31-56, 263-276) -> stage-0 table         one CTA per (region, point)
-//   geo_fps         : farthest_point_sample (:59-80)                          one warp per region, points in registers
+//   geo_fps         : farthest_point_sample (:59-80)                          one 8-warp CTA per region, points in registers
 //   geo_knn         : square_distance + topk (:101-136)                       one warp per anchor, k rounds of a
 //                                                                             lexicographic (distance, index) warp-min
 //   geo_group       : local - anchor | anchor (:302-308)  -> GEMM operands    one CTA per (region, anchor, neighbour)
@@ -66,40 +66,45 @@ __global__ void __launch_bounds__(128) geo_point_table_kernel(const bf* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------- FPS
-// xy = table + d (row pitch ld); one warp per region, N <= 32 * GEO_PPL points held in registers.
-constexpr int GEO_PPL = 32;
-__global__ void __launch_bounds__(32) geo_fps_kernel(const bf* __restrict__ xy, long long ld, int N, int S,
-                                                     const int* __restrict__ start, int* __restrict__ fps_idx) {
-  // the S iterations are one dependent chain: the centroid of an iteration is read back from shared memory (a global
-  // load there cost ~0.8 us of L2 latency per iteration: 219 us for S = 128, profiles/r02_ncu_geo.md)
-  __shared__ float2 s_xy[32 * GEO_PPL];
-  const int r = blockIdx.x, lane = threadIdx.x;
+// xy = table + d (row pitch ld); one CTA of 8 warps per region, N <= 1024 points: thread t holds points t, t + 256, ...
+// The S iterations are one dependent chain (the next centroid is the arg-max of the running minimum distance): per
+// iteration a thread updates its <= 4 distances, the warp reduces (value, index) by shuffles -- first maximum: the lower
+// index wins a tie --, the eight warp results meet in a double-buffered shared-memory slot (ONE CTA barrier per
+// iteration) and every thread reduces them redundantly. (One warp per region with 32 points per lane took 1.7 us per
+// iteration, 217 us for S = 128: profiles/r02_ncu_geo.md.)
+constexpr int GEO_FPS_THREADS = 256;
+constexpr int GEO_FPS_PPT = 4;  // points per thread
+__global__ void __launch_bounds__(GEO_FPS_THREADS) geo_fps_kernel(const bf* __restrict__ xy, long long ld, int N, int S,
+                                                                  const int* __restrict__ start, int* __restrict__ fps_idx) {
+  __shared__ float2 s_xy[GEO_FPS_THREADS * GEO_FPS_PPT];
+  __shared__ float s_best[2][GEO_FPS_THREADS / 32];
+  __shared__ int s_bidx[2][GEO_FPS_THREADS / 32];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bf* base = xy + static_cast<long long>(r) * N * ld;
-  float px[GEO_PPL], py[GEO_PPL], dist[GEO_PPL];
+  float px[GEO_FPS_PPT], py[GEO_FPS_PPT], dist[GEO_FPS_PPT];
 #pragma unroll
-  for (int i = 0; i < GEO_PPL; ++i) {
-    const int n = i * 32 + lane;
+  for (int i = 0; i < GEO_FPS_PPT; ++i) {
+    const int n = i * GEO_FPS_THREADS + tid;
     px[i] = n < N ? __bfloat162float(base[n * ld]) : 0.0f;
     py[i] = n < N ? __bfloat162float(base[n * ld + 1]) : 0.0f;
-    dist[i] = n < N ? 1e10f : -1.0f;
+    dist[i] = 1e10f;
     s_xy[n] = make_float2(px[i], py[i]);
   }
-  __syncwarp();
+  __syncthreads();
   int far = start[r];
   for (int s = 0; s < S; ++s) {
-    if (lane == 0) fps_idx[r * S + s] = far;
+    if (tid == 0) fps_idx[r * S + s] = far;
     const float2 c = s_xy[far];
-    const float cx = c.x, cy = c.y;
     float best = -2.0f;
     int bi = 0x7fffffff;
 #pragma unroll
-    for (int i = 0; i < GEO_PPL; ++i) {
-      const int n = i * 32 + lane;
+    for (int i = 0; i < GEO_FPS_PPT; ++i) {
+      const int n = i * GEO_FPS_THREADS + tid;
       if (n < N) {
-        const float dx = bf16_round(px[i] - cx), dy = bf16_round(py[i] - cy);
+        const float dx = bf16_round(px[i] - c.x), dy = bf16_round(py[i] - c.y);
         const float d = bf16_round(bf16_round(dx * dx) + bf16_round(dy * dy));
         dist[i] = fminf(dist[i], d);
-        if (dist[i] > best) {  // ascending n within the lane: strict > keeps the first maximum
+        if (dist[i] > best) {  // ascending n within the thread: strict > keeps the first maximum
           best = dist[i];
           bi = n;
         }
@@ -114,12 +119,30 @@ __global__ void __launch_bounds__(32) geo_fps_kernel(const bf* __restrict__ xy, 
         bi = oi;
       }
     }
+    const int buf = s & 1;
+    if (lane == 0) {
+      s_best[buf][warp] = best;
+      s_bidx[buf][warp] = bi;
+    }
+    __syncthreads();  // (the other buffer is rewritten only after the NEXT barrier: every thread has read this one by then)
+    best = s_best[buf][0];
+    bi = s_bidx[buf][0];
+#pragma unroll
+    for (int q = 1; q < GEO_FPS_THREADS / 32; ++q) {
+      const float ob = s_best[buf][q];
+      const int oi = s_bidx[buf][q];
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
     far = bi;
   }
 }
 
 // ---------------------------------------------------------------------------------------------------- kNN
 // one warp per anchor (r, s); the k smallest of N by (distance, index), written in that order.
+constexpr int GEO_PPL = 32;  // candidates per lane: N <= 32 * GEO_PPL
 __global__ void __launch_bounds__(128) geo_knn_kernel(const bf* __restrict__ xy, long long ld, int N, int S, int k,
                                                       const int* __restrict__ fps_idx, int* __restrict__ knn_idx,
                                                       int anchors) {
@@ -287,6 +310,104 @@ __global__ void __launch_bounds__(GEO_LN_THREADS) geo_ln_pool_kernel(const bf* _
   }
 }
 
+// Warp-per-row form for D <= 1024 (the CLIP-L width): each of the CTA's four warps takes every fourth neighbour row, holds
+// it in registers (4 x 16-byte loads per lane, all in flight), gets its LayerNorm statistics from warp shuffles alone (no
+// CTA barrier per row: the row-at-a-time kernel above walks k rows through two barriers each and ran at 0.11 of the HBM
+// peak, profiles/r02_ncu_geo.md) and pools into registers; the four partial pools meet once in shared memory.
+__global__ void __launch_bounds__(GEO_LN_THREADS) geo_ln_pool_warp_kernel(const bf* __restrict__ y, int k, int D,
+                                                                          const bf* __restrict__ w, const bf* __restrict__ b,
+                                                                          float eps, int mode, const bf* __restrict__ xy_src,
+                                                                          long long ld_src, int N, int S,
+                                                                          const int* __restrict__ fps_idx,
+                                                                          bf* __restrict__ out, long long ldo) {
+  __shared__ float part[GEO_LN_THREADS / 32][1024];
+  const int a = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[4][8];
+  float wv[4][8], bv[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    uint4 wr = make_uint4(0, 0, 0, 0), br = wr;
+    if (c < D) {
+      wr = *reinterpret_cast<const uint4*>(w + c);
+      br = *reinterpret_cast<const uint4*>(b + c);
+    }
+    const bf* wp = reinterpret_cast<const bf*>(&wr);
+    const bf* bp = reinterpret_cast<const bf*>(&br);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      wv[i][e] = __bfloat162float(wp[e]);
+      bv[i][e] = __bfloat162float(bp[e]);
+      acc[i][e] = mode == 0 ? 0.0f : -INFINITY;
+    }
+  }
+  const float inv_d = 1.0f / static_cast<float>(D);
+  for (int j = warp; j < k; j += GEO_LN_THREADS / 32) {
+    const bf* yr = y + (static_cast<long long>(a) * k + j) * D;
+    uint4 raw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (i * 32 + lane) * 8;
+      raw[i] = c < D ? *reinterpret_cast<const uint4*>(yr + c) : make_uint4(0, 0, 0, 0);
+    }
+    float v[4][8];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bf* hv = reinterpret_cast<const bf*>(&raw[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[i][e] = __bfloat162float(hv[e]);
+        s += v[i][e];
+      }
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((i * 32 + lane) * 8 < D) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dlt = v[i][e] - mean;
+          sq += dlt * dlt;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float o = bf16_round((v[i][e] - mean) * rstd * wv[i][e] + bv[i][e]);
+        acc[i][e] = mode == 0 ? acc[i][e] + o : fmaxf(acc[i][e], o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (c < D) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part[warp][c + e] = acc[i][e];
+    }
+  }
+  __syncthreads();
+  bf* orow = out + static_cast<long long>(a) * ldo;
+  const float inv_k = 1.0f / static_cast<float>(k);
+  for (int c = threadIdx.x; c < D; c += GEO_LN_THREADS) {
+    float r = part[0][c];
+#pragma unroll
+    for (int q = 1; q < GEO_LN_THREADS / 32; ++q) r = mode == 0 ? r + part[q][c] : fmaxf(r, part[q][c]);
+    orow[c] = __float2bfloat16_rn(mode == 0 ? r * inv_k : r);
+  }
+  if (xy_src != nullptr) {
+    const int r = a / S;
+    const bf* src = xy_src + (static_cast<long long>(r) * N + fps_idx[a]) * ld_src;
+    for (int c = D + threadIdx.x; c < ldo; c += GEO_LN_THREADS)
+      orow[c] = c < D + 2 ? src[c - D] : __float2bfloat16_rn(0.0f);
+  }
+}
+
 }  // namespace mpl
 
 using namespace mpl;
@@ -305,8 +426,9 @@ extern "C" int mpl_geo_fps(const void* xy, long long ld, int R, int N, int S, co
                            void* stream) {
   if (R <= 0 || S <= 0) return MPL_OK;
   if (xy == nullptr || start == nullptr || fps_idx == nullptr || N <= 0) return MPL_ERR_ARG;
-  if (N > 32 * GEO_PPL) return MPL_ERR_UNSUPPORTED;
-  geo_fps_kernel<<<R, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(xy), ld, N, S, start, fps_idx);
+  if (N > GEO_FPS_THREADS * GEO_FPS_PPT) return MPL_ERR_UNSUPPORTED;
+  geo_fps_kernel<<<R, GEO_FPS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const bf*>(xy), ld, N, S, start,
+                                                                             fps_idx);
   return launch_status();
 }
 
@@ -339,6 +461,12 @@ extern "C" int mpl_geo_ln_pool(const void* y, int R, int S, int k, int D, const 
   if (xy_src != nullptr && (fps_idx == nullptr || ldo < D + 2)) return MPL_ERR_ARG;
   if ((D % 8) != 0 || (ldo % 8) != 0) return MPL_ERR_ALIGN;
   if (D > GEO_LN_THREADS * 8 * GEO_LN_VEC) return MPL_ERR_UNSUPPORTED;
+  if (D <= 1024 && k >= GEO_LN_THREADS / 32) {  // (max pooling over fewer rows than warps would pool a -inf partial: row form)
+    geo_ln_pool_warp_kernel<<<R * S, GEO_LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const bf*>(y), k, D, static_cast<const bf*>(weight), static_cast<const bf*>(bias), eps, mode,
+        static_cast<const bf*>(xy_src), ld_src, N, S, fps_idx, static_cast<bf*>(out), ldo);
+    return launch_status();
+  }
   geo_ln_pool_kernel<<<R * S, GEO_LN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf*>(y), k, D, static_cast<const bf*>(weight), static_cast<const bf*>(bias), eps, mode,
       static_cast<const bf*>(xy_src), ld_src, N, S, fps_idx, static_cast<bf*>(out), ldo);
