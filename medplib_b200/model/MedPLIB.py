@@ -1115,17 +1115,21 @@ class MedPLIBForCausalLM(PreTrainedModel):
                                 attention_mask=attention_mask, forced_tokens=forced_tokens)
             output_ids = gen.sequences
             hidden = gen.last_hidden_state
-            has_seg = bool((output_ids[:, 1:] == self.seg_token_idx).any())
+            # ONE device -> host copy of the generated ids (the number of <SEG> rows decides shapes, so the host has to
+            # see them once); the <SEG> bookkeeping then runs on the host copy and the selected hidden row is a view --
+            # no `.any()` reduction, no boolean-index kernels and no second / third synchronisation on the device
+            ids_host = output_ids.cpu()
+            has_seg = bool((ids_host[:, 1:] == self.seg_token_idx).any())
             if not has_seg and inference_demo:
                 if side is not None:
                     torch.cuda.current_stream().wait_stream(side)
                 return output_ids, []
-            seg_mask = self.build_seg_token_mask(output_ids, image_token_lengths=image_token_lengths)
+            seg_mask = self.build_seg_token_mask(ids_host, image_token_lengths=image_token_lengths)
             seg_mask = seg_mask[:, :hidden.shape[1]]  # App. B-1: the last mask entry is always False
-            rows = hidden[seg_mask]
-            if rows.shape[0] > 1:
-                rows = rows[:1]
-            elif rows.shape[0] == 0:
+            pos = seg_mask.nonzero()  # row-major order == the order of hidden[seg_mask]; the reference keeps the first
+            if pos.shape[0] > 0:
+                rows = hidden[int(pos[0, 0]), int(pos[0, 1])][None]
+            else:
                 rows = hidden[:1, -2:-1, :].squeeze(1)
             pred_embeddings = self._seg_embeddings(rows)
             if side is not None:
