@@ -681,6 +681,100 @@ int attn_bwd_fa2(const mpl_attn_bwd_args& a, cudaStream_t stream) {
 }  // namespace mpl
 
 
+namespace mpl {
+// ------------------------------------------------------------------------------------------------- small attention
+// The SAM mask decoder's two-way attention (transformer.py:185-244): 8 heads of 16 (cross) or 32 (self) channels, 6 token
+// rows against 256 image rows and back -- 50-180 KB per call, pure latency on the mma.sync tile kernel (one 64-row tile
+// per CTA mostly empty: 8-16 us per launch, profiles/r02_ncu_maskdec_attention.md). Here ONE WARP owns one query row:
+// lane l scores keys l, l + 32, ... (Tk <= 256: at most 8 scores per lane, kept in registers), the row maximum and sum are
+// warp-shuffle reductions, the normalised probabilities are rounded to bf16 exactly where the eager reference rounds them
+// (softmax output -> bf16 -> @ V), every lane accumulates its keys' share of P V and a last shuffle reduction adds the lanes.
+template <int HD>
+__global__ void __launch_bounds__(128) attn_small_kernel(const AttnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = static_cast<long long>(blockIdx.x) * 4 + warp;
+  if (item >= static_cast<long long>(p.B) * p.H * p.Tq) return;
+  const int i = static_cast<int>(item % p.Tq);
+  const long long bh = item / p.Tq;
+  const int h = static_cast<int>(bh % p.H);
+  const long long b = bh / p.H;
+  const __nv_bfloat16* qr = p.q + b * p.q_sb + i * p.q_st + h * p.q_sh;
+  const __nv_bfloat16* kb = p.k + b * p.k_sb + h * p.k_sh;
+  const __nv_bfloat16* vb = p.v + b * p.v_sb + h * p.v_sh;
+  float qf[HD];
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(qr + c * 8);
+    const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qf[c * 8 + e] = __bfloat162float(hv[e]);
+  }
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float sc[8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int j = lane + 32 * t;
+    sc[t] = -INFINITY;
+    if (j < p.Tk) {
+      const __nv_bfloat16* kr = kb + static_cast<long long>(j) * p.k_st;
+      float dot = 0.0f;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(kr + c * 8);
+        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot += qf[c * 8 + e] * __bfloat162float(hv[e]);
+      }
+      sc[t] = dot * sl2;
+      mx = fmaxf(mx, sc[t]);
+    }
+  }
+  mx = warp_max(mx);
+  float l = 0.0f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    sc[t] = lane + 32 * t < p.Tk ? exp2f(sc[t] - mx) : 0.0f;
+    l += sc[t];
+  }
+  l = warp_sum(l);
+  const float inv = 1.0f / l;
+  float acc[HD];
+#pragma unroll
+  for (int e = 0; e < HD; ++e) acc[e] = 0.0f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int j = lane + 32 * t;
+    if (j < p.Tk) {
+      const float pj = bf16_round(sc[t] * inv);
+      const __nv_bfloat16* vr = vb + static_cast<long long>(j) * p.v_st;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(vr + c * 8);
+        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[c * 8 + e] += pj * __bfloat162float(hv[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < HD; ++e) acc[e] = warp_sum(acc[e]);
+  if (lane == 0) {
+    __nv_bfloat16* orow = p.o + b * p.o_sb + i * p.o_st + h * p.o_sh;
+#pragma unroll
+    for (int e = 0; e < HD; e += 2)
+      *reinterpret_cast<uint32_t*>(orow + e) = pack_bf16(acc[e], acc[e + 1]);
+  }
+}
+static bool attn_small_enabled() {
+  static const bool on = [] {
+    const char* c = getenv("MPL_ATTN_SMALL");
+    return c == nullptr || atoi(c) != 0;
+  }();
+  return on;
+}
+}  // namespace mpl
+
 extern "C" int mpl_attention(const mpl_attn_args* a, void* stream_) {
   using namespace mpl;
   if (a == nullptr || a->q == nullptr || a->k == nullptr || a->v == nullptr || a->o == nullptr) return MPL_ERR_ARG;
@@ -728,6 +822,16 @@ extern "C" int mpl_attention(const mpl_attn_args* a, void* stream_) {
   if (p.tk_dev != nullptr) return MPL_ERR_UNSUPPORTED;  // device-side Tk only on the decode path
   if (attention_tc_supported(*a)) return attention_tc(*a, stream);  // tcgen05 + TMA tiles (attention_tc.cu)
   if (p.o_st % 2 != 0 || p.o_sh % 2 != 0 || p.o_sb % 2 != 0) return MPL_ERR_ALIGN;
+  if ((a->head_dim == 16 || a->head_dim == 32) && a->Tq <= 64 && a->Tk >= 1 && a->Tk <= 256 && !a->causal && a->kv_mask == nullptr &&
+      a->rel_h == nullptr && a->lse == nullptr && attn_small_enabled()) {
+    const long long items = static_cast<long long>(p.B) * p.H * p.Tq;
+    const unsigned grid = static_cast<unsigned>((items + 3) / 4);
+    if (a->head_dim == 16)
+      attn_small_kernel<16><<<grid, 128, 0, stream>>>(p);
+    else
+      attn_small_kernel<32><<<grid, 128, 0, stream>>>(p);
+    return mpl::launch_status();
+  }
   switch (a->head_dim) {
     case 16: return launch_flash<16>(p, stream);
     case 32: return launch_flash<32>(p, stream);
