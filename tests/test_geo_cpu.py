@@ -138,3 +138,36 @@ def test_model_instantiates_the_sampler_only_when_configured():
     s = make(region_geo_sampler=True, sampler_pooler_mode="mean").get_model().region_geo_sampler
     assert (s.input_dim, s.output_dim, s.num_init_point, s.num_sub_point, s.num_neighbor, s.pooler_mode) == \
         (32, 16, 512, [128, 32], [24, 24], "mean")
+
+
+def test_padded_gemm_operands_reproduce_the_grouped_linears():
+    """Host logic of the product module (runs on CPU: pure tensor packing): the zero-padded operands `_weights()` builds
+    for the point-table layout [features | row/H | col/W | 0...] give exactly what diff_projector / the 1x1 agg conv give
+    on the unpadded rows (fp32 evaluation of the bf16 operands)."""
+    from medplib_b200.model.geo_sampler import GeoRegionSampler
+    torch.manual_seed(0)
+    d = 40
+    mod = GeoRegionSampler(d, 16, 32, [8, 4], [4, 2]).to(torch.bfloat16)
+    ld = (d + 2 + 63) // 64 * 64
+    rows = 11
+    local = torch.randn(rows, d + 2).to(torch.bfloat16)
+    anchor = torch.randn(rows, d + 2).to(torch.bfloat16)
+    for s, (wd, bd, wa) in enumerate(mod._weights()):
+        assert wd.shape == (ld, ld) and bd.shape == (ld,) and wa.shape == (d, 2 * ld)
+        pad = lambda t: torch.cat([t, torch.zeros(rows, ld - (d + 2), dtype=t.dtype)], 1)
+        dl, ag = mod.diff_projector_list[s], mod.agg_projector_list[s]
+        diff = (local.float() - anchor.float()).to(torch.bfloat16)
+        want_d = torch.nn.functional.linear(diff.float(), dl.weight.float(), dl.bias.float())
+        got_d = torch.nn.functional.linear(pad(diff).float(), wd.float(), bd.float())
+        assert torch.equal(got_d[:, :d + 2], want_d) and not bool(got_d[:, d + 2:].any())
+        dproj = want_d.to(torch.bfloat16)
+        cat = torch.cat([dproj, anchor], 1).float()                         # what the reference's conv sees
+        want_a = torch.nn.functional.conv1d(cat.t()[None], ag.net[0].weight.float(), ag.net[0].bias.float())[0].t()
+        got_a = torch.nn.functional.linear(torch.cat([pad(dproj), pad(anchor)], 1).float(), wa.float(),
+                                           ag.net[0].bias.float())
+        torch.testing.assert_close(got_a, want_a, rtol=1e-6, atol=1e-6)
+    # the cache follows parameter updates
+    before = mod._weights()[0][0].clone()
+    with torch.no_grad():
+        mod.diff_projector_list[0].weight.add_(1.0)
+    assert not torch.equal(mod._weights()[0][0], before)
