@@ -109,3 +109,39 @@ def test_lisa_accepts_both_mask_spellings():
     from medplib_b200.model import LISAForCausalLM
     sig = inspect.signature(LISAForCausalLM.model_forward)
     assert "attention_masks" in sig.parameters  # LISA.py:267
+
+
+def test_evaluate_seg_bookkeeping_on_the_host(model, monkeypatch):
+    """evaluate() (model/MedPLIB.py:574-680) with the device work scripted: the row handed to text_hidden_fcs is the
+    hidden state in front of the FIRST <SEG> of the generated ids (what `hidden[seg_mask][:1]` selects in the reference),
+    position -2 when there is none, and `inference_demo` returns no mask without one. The product does this on ONE host
+    copy of the ids; the expectation here is computed the reference's way (boolean indexing with the seg-token mask)."""
+    from medplib_b200.model.MedPLIB import GenerateOutput
+    SEG = model.seg_token_idx
+    n_img = (getattr(model.config, "mm_compressed_token_count", 256) if getattr(model.config, "mm_token_compress", False)
+             else model.get_model().get_vision_tower().num_patches)
+    picked = {}
+
+    def run(ids_row, demo=False):
+        ids = torch.tensor([ids_row])
+        T = len(ids_row) - 1 + n_img  # one -200 sentinel expands to n_img rows
+        hidden = torch.randn(1, T - 1, 8, generator=torch.Generator().manual_seed(len(ids_row)))
+        monkeypatch.setattr(model, "generate", lambda **kw: GenerateOutput(sequences=ids, hidden_states=None,
+                                                                           last_hidden_state=hidden, scores=None))
+        monkeypatch.setattr(model, "_seg_embeddings", lambda rows: picked.__setitem__("rows", rows.clone()) or rows)
+        monkeypatch.setattr(model, "get_visual_embs", lambda images: torch.zeros(1))
+        monkeypatch.setattr(model, "_decode_masks", lambda pe, ie, rl, sizes: (["mask"], None))
+        model.overlap_vision = False
+        picked.clear()
+        out = model.evaluate(torch.zeros(1), torch.zeros(1), ids, [(256, 256)], [torch.zeros(4, 4)], inference_demo=demo)
+        mask = model.build_seg_token_mask(ids)[:, :hidden.shape[1]]
+        return out, hidden, mask
+
+    out, hidden, mask = run([1, 5, -200, 7, 8, SEG, 9, SEG, 2])          # two <SEG>: the first one counts
+    assert out[1] == ["mask"] and torch.equal(picked["rows"], hidden[mask][:1])
+    out, hidden, mask = run([1, -200, 7, SEG, 2], demo=True)
+    assert out[1] == ["mask"] and torch.equal(picked["rows"], hidden[mask][:1])
+    out, hidden, mask = run([1, 5, -200, 7, 8, 9, 2])                     # none: position -2 (MedPLIB.py:640-644)
+    assert int(mask.sum()) == 0 and torch.equal(picked["rows"], hidden[:1, -2])
+    out, hidden, mask = run([1, 5, -200, 7, 8, 9, 2], demo=True)
+    assert out[1] == [] and "rows" not in picked
